@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- IDFF particle-steps/s on B200 (BASELINE.json metric), one JSON line on stdout (rank 0).
+
+Workload (BASELINE.json configs[1]): 2-D checkerboard, order-2 IDFF field (gamma1 = gamma2 = 0.2, sigma = 0.2), the
+shipped 3->256->256->256->2 checkpoint, fixed-grid 3/8-rule RK4 over nfe intervals (4*nfe field evaluations per
+particle; the two at t = 0 and t = 1 are boundary evaluations), x0 = randn(N, 2)/1.5 generated in seeded chunks.
+One "step" = one full solve of this rank's N particles + the MMD evaluation of a gathered 8192-row subsample per rank
+against 16384 true checkerboard rows.  1 particle-step = one particle x one field evaluation.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--particles P] [--nfe F] [--impl ours|reference]
+  torchrun --nproc-per-node N bench.py --gpus N ...          (one rank per GPU, weak scaling: P particles per GPU)
+
+--impl reference times the reference's own PyTorch CPU code path for the same workload (the oracle: nested
+autograd.grad field under the restated torchdiffeq rk4) on the host cores, on a bounded sample of the particles.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+SIGMA, GAMMAS, ORDER = 0.2, (0.2, 0.2), 2
+W, DIN, DOUT = 256, 3, 2
+MAC_PER_PASS = DIN * W + 2 * W * W + W * DOUT        # F(Din,w,Dout) = 132352
+
+
+def flops_per_particle_solve(nfe: int, order: int = ORDER) -> float:
+    """2F per MLP pass; a boundary evaluation is 1 pass, an interior order-n one is 2n (n jets + n reverse chains)."""
+    interior = 4 * nfe - 2
+    return 2.0 * MAC_PER_PASS * (interior * 2 * order + 2)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def load_layers():
+    w = np.load(os.path.join(GOLDEN, "weights_checkerboard.npz"))
+    return [(torch.tensor(w[f"W{i}"]), torch.tensor(w[f"b{i}"])) for i in range(4)]
+
+
+# ----------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_rate(n_particles: int, nfe: int, runs: int, warmup: int = 1):
+    """The reference's PyTorch CPU path (oracle/idff_oracle.py: Field2D = CustomNetModel.forward with nested
+    autograd.grad, Autograd_example_order2.py:36-76, under the restated torchdiffeq rk4) on all host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import idff_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    field = O.Field2D(load_layers(), SIGMA, GAMMAS, ORDER)
+    x0 = torch.randn(n_particles, 2, generator=torch.Generator().manual_seed(1000)) / 1.5
+    ts = torch.linspace(0, 1, nfe + 1)
+    times = []
+    for i in range(warmup + runs):
+        t0 = time.perf_counter()
+        O.odeint_rk4(field, x0, ts)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    per = statistics.median(times)
+    return n_particles * 4 * nfe / per, per, cores, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.cpu_particles
+    rate, per, cores, times = cpu_reference_rate(n, args.nfe, args.steps, args.warmup)
+    sample = f"{n} of the workload's particles per step, nfe={args.nfe} (torch CPU fp32, {cores} threads)"
+    line = {"impl": "reference", "metric": "idff_particle_steps_per_sec", "value": rate, "unit": "particle-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, n),
+            "cpu_baseline": {"value": rate, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_per_gpu):
+    return {"workload": f"2-D checkerboard IDFF order-2 sampler, MLP 3-256-256-256-2 (shipped checkpoint), rk4(3/8) "
+                        f"nfe={args.nfe} ({4 * args.nfe} field evals/particle), gamma=(0.2,0.2), sigma=0.2",
+            "particles_per_gpu": n_per_gpu, "nfe": args.nfe,
+            "mmd_eval": "8192 generated rows/rank all-gathered vs 16384 true rows, every step",
+            "l2": "inputs+outputs (16 B/particle) exceed the 126 MB L2 at >= 2^23 particles; compute-bound kernel",
+            "parallelism": f"particle-sharded x{args.gpus}"}
+
+
+# ----------------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch.distributed as dist
+    from idff_b200 import _lib, fields, launcher, sampler
+    from idff_b200.mmd import mmd_partial_sums
+    from idff_b200.torchcfm import conditional_flow_matching as cfm
+    from idff_b200.weights import PackedWeights
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (idff_b200 has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if ws > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    P, nfe = args.particles, args.nfe
+    n_total = P * ws
+
+    pw = PackedWeights.from_npz(os.path.join(GOLDEN, "weights_checkerboard.npz"), device=dev)
+    model = fields.CustomNetModel(pw, SIGMA, *GAMMAS)
+    model.impl = {"auto": 0, "generic": 1, "fused": 2}[args.kernel]
+    shard = launcher.ShardedSampler(model, 2, dev, base_seed=1000)
+    x0 = shard.x0(n_total)
+    ts = torch.linspace(0, 1, nfe + 1)
+    out = torch.empty_like(x0)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    np.random.seed(0)
+    torch.manual_seed(0)
+    from idff_b200.torchcfm.utils import sample_checkerboard
+    true_x = sample_checkerboard(16384).to(dev)
+
+    def step():
+        sampler.sample_rk4(model, x0, ts, out=out)
+        return launcher.sharded_mmd(true_x, out, 8192, 1.0)[0]
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        mmd_val = step()
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ks, ke = [], []
+    e0.record()
+    for _ in range(args.steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        sampler.sample_rk4(model, x0, ts, out=out)
+        b.record()
+        ks.append(a)
+        ke.append(b)
+        mmd_val = launcher.sharded_mmd(true_x, out, 8192, 1.0)[0]
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    clk = clocks.stop() if clocks else None
+    total_ms = e0.elapsed_time(e1)
+    kern_ms = [a.elapsed_time(b) for a, b in zip(ks, ke)]
+    tmax = torch.tensor([total_ms], device=dev)
+    if ws > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms = float(tmax.item())
+    steps_per_solve = 4 * nfe
+    value = n_total * steps_per_solve * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    h_x0 = x0.cpu().pin_memory()
+    h_out = torch.empty_like(h_x0).pin_memory()
+    d_in = torch.empty_like(x0)
+    for _ in range(2):
+        d_in.copy_(h_x0, non_blocking=True)
+        h_out.copy_(sampler.sample_rk4(model, d_in, ts, out=out), non_blocking=True)
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(args.steps):
+        d_in.copy_(h_x0, non_blocking=True)
+        h_out.copy_(sampler.sample_rk4(model, d_in, ts, out=out), non_blocking=True)
+    s1.record()
+    barrier()
+    e2e_ms = torch.tensor([s0.elapsed_time(s1)], device=dev)
+    if ws > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_val = n_total * steps_per_solve * args.steps / (float(e2e_ms.item()) * 1e-3)
+    assert torch.equal(h_out, out.cpu())
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        k_ms = statistics.mean(kern_ms)
+        flops = P * flops_per_particle_solve(nfe)
+        achieved = flops / (k_ms * 1e-3) / 1e12
+        fma_peak = 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+        roofline = {"bound": "fma", "kernel": "idff sampler (whole rk4 solve, one launch)", "achieved": achieved,
+                    "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved / fma_peak, "traffic": None,
+                    "peak_source": "fp32 FFMA issue peak 148 SM x 128 lanes x 2 x clocks.max.sm "
+                                   f"({peak_src} sm_max_mhz); MEASURED_PEAKS.json holds no fp32 figure. fp32 results at "
+                                   "1e-5 rule out single-pass TF32/BF16 tensor MMA",
+                    "algorithmic_flops_per_launch": flops, "kernel_ms": k_ms,
+                    "kernel_share_of_step": k_ms * args.steps / total_ms,
+                    "frac_of_bf16_tensor_peak": achieved / peaks.get("bf16_tflops", 1590.0)}
+        aux = aux_measurements(dev, pw, model, peaks) if not args.no_aux else {}
+        cpu_rate, cpu_per, cores, _ = cpu_reference_rate(args.cpu_particles, nfe, runs=5) if not args.no_cpu else (None, None, 0, [])
+        line = {"metric": "idff_particle_steps_per_sec", "value": value, "unit": "particle-steps/s", "n_gpus": ws,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(args, P), "clocks": clk,
+                "e2e": {"value": e2e_val, "unit": "particle-steps/s", "h2d_bytes_per_step": int(x0.numel() * 4) * ws,
+                        "d2h_bytes_per_step": int(out.numel() * 4) * ws},
+                "gpu_launches": int(launches), "roofline": roofline,
+                "cpu_baseline": {"value": cpu_rate, "unit": "particle-steps/s", "cores": cores, "kind": "port",
+                                 "sample": f"{args.cpu_particles} particles x 5 solves, nfe={nfe}, torch CPU fp32 "
+                                           "(oracle = the reference's nested-autograd field under restated rk4)"},
+                "mmd": mmd_val, "particles_per_sec": value / steps_per_solve, "aux": aux}
+        print(json.dumps(line), flush=True)
+    if ws > 1:
+        dist.destroy_process_group()
+
+
+def aux_measurements(dev, pw, model, peaks):
+    """Secondary kernels, each timed alone with CUDA events on inputs larger than L2 (reported, not the headline)."""
+    from idff_b200 import losses, sampler
+    from idff_b200.mmd import mmd_partial_sums
+    from idff_b200.torchcfm import conditional_flow_matching as cfm
+    aux = {}
+
+    def timeit(fn, reps=5, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps * 1e-3
+
+    B, D = 1 << 24, 2
+    g = torch.Generator(device=dev).manual_seed(1)
+    x0, x1, eps = (torch.randn(B, D, device=dev, generator=g) for _ in range(3))
+    t = torch.rand(B, device=dev, generator=g)
+    s = timeit(lambda: cfm._path_sample(x0, x1, t, eps, 0.2, 1))
+    by = (5 * D + 1) * 4 * B
+    aux["path_sample"] = {"rows_per_s": B / s, "GBps": by / s / 1e9, "frac_hbm": by / s / 1e9 / peaks["hbm_gbs"],
+                          "shape": [B, D], "bound": "hbm", "bytes_per_row": (5 * D + 1) * 4}
+    vt = torch.randn(B, D, device=dev, generator=g).requires_grad_(True)
+
+    def loss_fb():
+        losses.flow_loss(vt, x1, t).backward()
+    s = timeit(loss_fb)
+    by = (3 * D + 1) * 4 * B
+    aux["flow_loss_fwd_bwd"] = {"rows_per_s": B / s, "GBps": by / s / 1e9, "frac_hbm": by / s / 1e9 / peaks["hbm_gbs"],
+                                "shape": [B, D], "bound": "hbm", "bytes_per_row": (3 * D + 1) * 4,
+                                "note": "includes torch's grad*g multiply of the autograd wrapper"}
+    del x0, x1, eps, vt, t
+    n = 32768
+    a = torch.randn(n, 2, device=dev, generator=g)
+    b = torch.randn(n, 2, device=dev, generator=g)
+    s = timeit(lambda: mmd_partial_sums(a, b, 1.0))
+    aux["mmd_rbf"] = {"pairs_per_s": 3.0 * n * n / s, "shape": [n, n, 2], "bound": "mufu.ex2",
+                      "frac_ex2_peak": 3.0 * n * n / s / (148 * 16 * peaks.get("sm_max_mhz", 1965.0) * 1e6)}
+    sweep = {}
+    xs = torch.randn(1 << 21, 2, device=dev, generator=g) / 1.5
+    for nfe in (2, 5, 10):
+        ts = torch.linspace(0, 1, nfe + 1)
+        s = timeit(lambda: sampler.sample_rk4(model, xs, ts), reps=2, warm=1)
+        sweep[str(nfe)] = xs.shape[0] * 4 * nfe / s
+    aux["sampler_nfe_sweep_particle_steps_per_s"] = sweep
+    return aux
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--particles", type=int, default=1 << 24, help="particles per GPU")
+    ap.add_argument("--nfe", type=int, default=2)
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fused"])
+    ap.add_argument("--cpu-particles", type=int, default=65536)
+    ap.add_argument("--no-aux", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

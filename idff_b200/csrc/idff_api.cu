@@ -1,0 +1,217 @@
+// extern "C" entry points of the sampler side: stage-table construction on the host (fp32, in the operation
+// order of torchdiffeq / torchsde / the reference wrappers) and dispatch to the kernel families.
+#include <cmath>
+#include <vector>
+
+#include "idff_common.cuh"
+
+namespace idff {
+// idff_field_generic.cu
+int check_field_args(const idff_weights_t* w, const idff_field_params_t* p, const char* who);
+void jets_needed(const idff_field_params_t& p, int* nj, int* reverse);
+int generic_field_eval(const idff_weights_t* w, const idff_field_params_t* p, float t, const float* d_x,
+                       const float* d_x0, float* d_out, int64_t N, void* stream);
+int generic_mlp_forward(const idff_weights_t* w, const float* d_in, float* d_out, int64_t N, int t_idx, void* stream);
+int generic_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, const float* d_x0, const Stage* stages,
+                       const float* dts, int n_iv, float* d_out_final, float* d_out_traj, int64_t N, void* stream);
+int generic_sample_sde(const idff_weights_t* w, const idff_field_params_t* p, const SdeTable& tab, const float* d_y0,
+                       const float* d_Ik, const float* d_Ik0, float* d_out, int64_t N, void* stream);
+// idff_sampler_fused.cu
+bool fused_supports(const idff_weights_t* w, const idff_field_params_t* p);
+int fused_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, const float* d_x0, const Stage* stages,
+                     const float* dts, int n_iv, float* d_out_final, float* d_out_traj, int64_t N, void* stream);
+int fused_field_eval(const idff_weights_t* w, const idff_field_params_t* p, float t, const float* d_x, float* d_out,
+                     int64_t N, void* stream);
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+    if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// torchsde BaseSDESolver.integrate: curr_t += dt (fp32 tensor + Python float), clipped to ts[-1].
+static std::vector<float> sde_grid(const float* ts, int n_ts, float dt) {
+  std::vector<float> g;
+  g.push_back(ts[0]);
+  const float end = ts[n_ts - 1];
+  while (g.back() < end && g.size() < 100000) {
+    volatile float nxt = g.back() + dt;
+    g.push_back(nxt < end ? nxt : end);
+  }
+  return g;
+}
+}  // namespace idff
+
+using namespace idff;
+
+extern "C" int idff_stage_scalars(const idff_field_params_t* p, float t, float* h_out8) {
+  IDFF_CHECK_ARG(p && h_out8, "idff_stage_scalars: null pointer");
+  Stage s;
+  make_stage(*p, t, &s);
+  h_out8[0] = s.t; h_out8[1] = (float)s.kind; h_out8[2] = s.a; h_out8[3] = s.den;
+  h_out8[4] = s.c[0]; h_out8[5] = s.c[1]; h_out8[6] = s.c[2]; h_out8[7] = s.end_div;
+  return IDFF_OK;
+}
+
+extern "C" int idff_mlp_forward(const idff_weights_t* w, const float* d_in, float* d_out, int64_t N, int32_t t_idx,
+                                void* stream) {
+  IDFF_CHECK_ARG(w && d_in && d_out, "idff_mlp_forward: null pointer");
+  IDFF_CHECK_ARG(t_idx >= 0 && t_idx < w->v.n_tidx, "idff_mlp_forward: t_idx %d outside the embedding table (%d rows)", t_idx, w->v.n_tidx);
+  if (N == 0) return IDFF_OK;
+  IDFF_CHECK_ARG(N > 0, "idff_mlp_forward: negative N");
+  DeviceGuard g(w->device);
+  return generic_mlp_forward(w, d_in, d_out, N, t_idx, stream);
+}
+
+extern "C" int idff_field_eval(const idff_weights_t* w, const idff_field_params_t* p, float t, const float* d_x,
+                               const float* d_x0, float* d_out, int64_t N, void* stream) {
+  int rc = check_field_args(w, p, "idff_field_eval");
+  if (rc) return rc;
+  if (N == 0) return IDFF_OK;
+  IDFF_CHECK_ARG(N > 0 && d_x && d_out, "idff_field_eval: null pointer or negative N");
+  IDFF_CHECK_ARG(p->variant != IDFF_FIELD_CFM || t == 0.0f || d_x0, "idff_field_eval: the CFM field needs x0 (captured at t == 0) when t != 0");
+  DeviceGuard g(w->device);
+  if (p->impl == IDFF_IMPL_FUSED || (p->impl == IDFF_IMPL_AUTO && fused_supports(w, p))) {
+    if (!fused_supports(w, p)) {
+      set_error("idff_field_eval: the fused kernel does not support this shape/variant");
+      return IDFF_EUNSUPPORTED;
+    }
+    return fused_field_eval(w, p, t, d_x, d_out, N, stream);
+  }
+  return generic_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
+}
+
+extern "C" int idff_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, const float* d_x0,
+                               const float* h_t_grid, int32_t n_grid, float* d_out_final, float* d_out_traj, int64_t N,
+                               void* stream) {
+  int rc = check_field_args(w, p, "idff_sample_rk4");
+  if (rc) return rc;
+  IDFF_CHECK_ARG(p->variant != IDFF_FIELD_MD, "idff_sample_rk4: the MD field is an SDE drift; use idff_sample_sde");
+  IDFF_CHECK_ARG(h_t_grid && n_grid >= 1 && n_grid <= 100000, "idff_sample_rk4: bad time grid (n_grid=%d)", n_grid);
+  for (int i = 1; i < n_grid; ++i)
+    IDFF_CHECK_ARG(h_t_grid[i] > h_t_grid[i - 1], "idff_sample_rk4: t_grid must be strictly increasing");
+  if (N == 0) return IDFF_OK;
+  IDFF_CHECK_ARG(N > 0 && d_x0 && d_out_final, "idff_sample_rk4: null pointer or negative N");
+  DeviceGuard g(w->device);
+  const size_t row_bytes = (size_t)N * p->dim * sizeof(float);
+  if (d_out_traj) IDFF_CUDA(cudaMemcpyAsync(d_out_traj, d_x0, row_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  const int n_iv = n_grid - 1;
+  if (n_iv == 0) {
+    if (d_out_final != d_x0)
+      IDFF_CUDA(cudaMemcpyAsync(d_out_final, d_x0, row_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return IDFF_OK;
+  }
+  // stage times exactly as torchdiffeq rk_common.rk4_alt_step_func forms them (fp32 tensor * Python float)
+  std::vector<Stage> st(4 * (size_t)n_iv);
+  std::vector<float> dts(n_iv);
+  const float third = (float)(1.0 / 3.0), two_thirds = (float)(2.0 / 3.0);
+  for (int i = 0; i < n_iv; ++i) {
+    const float t0 = h_t_grid[i], t1 = h_t_grid[i + 1];
+    volatile float dt = t1 - t0;
+    volatile float a = dt * third, b = dt * two_thirds;
+    volatile float tb = t0 + a, tc = t0 + b;
+    dts[i] = dt;
+    make_stage(*p, t0, &st[4 * i + 0]);
+    make_stage(*p, tb, &st[4 * i + 1]);
+    make_stage(*p, tc, &st[4 * i + 2]);
+    make_stage(*p, t1, &st[4 * i + 3]);
+  }
+  const bool want_fused = p->impl == IDFF_IMPL_FUSED || (p->impl == IDFF_IMPL_AUTO && fused_supports(w, p));
+  if (want_fused) {
+    if (!fused_supports(w, p)) {
+      set_error("idff_sample_rk4: the fused kernel does not support this shape/variant");
+      return IDFF_EUNSUPPORTED;
+    }
+    return fused_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream);
+  }
+  return generic_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream);
+}
+
+extern "C" int idff_sde_num_steps(const float* h_ts, int32_t n_ts, float dt) {
+  IDFF_CHECK_ARG(h_ts && n_ts >= 1 && dt > 0.0f, "idff_sde_num_steps: bad argument");
+  return (int)sde_grid(h_ts, n_ts, dt).size() - 1;
+}
+
+extern "C" int idff_sample_sde(const idff_weights_t* w, const idff_field_params_t* p, const float* d_y0,
+                               const float* h_ts, int32_t n_ts, float dt, int32_t method, const float* d_I_k,
+                               const float* d_I_k0, float* d_out, int64_t N, void* stream) {
+  int rc = check_field_args(w, p, "idff_sample_sde");
+  if (rc) return rc;
+  IDFF_CHECK_ARG(p->variant == IDFF_FIELD_MD, "idff_sample_sde: only the MD field (SDE_cal) has a diffusion term");
+  IDFF_CHECK_ARG(h_ts && n_ts >= 1 && dt > 0.0f, "idff_sample_sde: bad ts/dt");
+  IDFF_CHECK_ARG(method == 0 || method == 1, "idff_sample_sde: method %d (0 srk, 1 euler)", method);
+  for (int i = 1; i < n_ts; ++i) IDFF_CHECK_ARG(h_ts[i] >= h_ts[i - 1], "idff_sample_sde: ts must be non-decreasing");
+  if (N == 0) return IDFF_OK;
+  IDFF_CHECK_ARG(N > 0 && d_y0 && d_out, "idff_sample_sde: null pointer or negative N");
+  const std::vector<float> grid = sde_grid(h_ts, n_ts, dt);
+  const int n_steps = (int)grid.size() - 1;
+  IDFF_CHECK_ARG(n_steps == 0 || d_I_k, "idff_sample_sde: Brownian increments d_I_k are required");
+  IDFF_CHECK_ARG(n_steps == 0 || method == 1 || d_I_k0, "idff_sample_sde: srk needs the space-time Levy term d_I_k0");
+  if (n_steps > kMaxSdeSteps || n_ts - 1 > kMaxSdeEmit) {
+    set_error("idff_sample_sde: %d steps / %d outputs exceed the per-call limits (%d / %d)", n_steps, n_ts - 1, kMaxSdeSteps, kMaxSdeEmit);
+    return IDFF_EUNSUPPORTED;
+  }
+  static thread_local SdeTable tab;
+  memset(&tab, 0, sizeof(tab));
+  tab.n_steps = n_steps;
+  tab.method = method;
+  const float sig2f = (float)(p->sigma * p->sigma);
+  const float C0[3] = {0.0f, 1.0f, 0.5f}, C1[4] = {0.0f, 0.25f, 1.0f, 0.25f};
+  for (int s = 0; s < n_steps; ++s) {
+    const float t0 = grid[s];
+    volatile float h = grid[s + 1] - t0;
+    tab.h[s] = h;
+    for (int q = 0; q < 3; ++q) {
+      volatile float ch = C0[q] * h;
+      volatile float tq = t0 + ch;
+      make_stage(*p, tq, &tab.st[s][q]);
+    }
+    for (int q = 0; q < 4; ++q) {
+      // g = ones * 180 * sigma**2 * sqrt(t * (1 - t))      MD_simulation.py:528-529
+      volatile float ch = C1[q] * h;
+      volatile float tq = t0 + ch;
+      volatile float om = 1.0f - tq;
+      volatile float pr = tq * om;
+      volatile float sq = sqrtf(pr);
+      volatile float k = 180.0f * sig2f;
+      tab.gval[s][q] = k * sq;
+    }
+  }
+  // outputs: ys[i] = linear_interp(prev_t, prev_y, curr_t, curr_y, ts[i]) after the first step with curr_t >= ts[i]
+  int gi = 0, ne = 0;
+  for (int i = 1; i < n_ts; ++i) {
+    const float out_t = h_ts[i];
+    while (grid[gi] < out_t) ++gi;
+    if (gi == 0) {   // out_t == ts[0]: the solver returns y0 (no step taken yet)
+      tab.emit_step[ne] = -1;
+    } else {
+      tab.emit_step[ne] = gi - 1;
+    }
+    const float tp = gi > 0 ? grid[gi - 1] : grid[0], tc = grid[gi];
+    float w0 = 0.0f, w1 = 1.0f;
+    if (gi > 0 && tc > tp) {   // torchsde interp.linear_interp: (t1-t)/(t1-t0)*y0 + (t-t0)/(t1-t0)*y1
+      volatile float span = tc - tp;
+      volatile float a = tc - out_t, b = out_t - tp;
+      w0 = a / span;
+      w1 = b / span;
+    }
+    tab.emit_out[ne] = i;
+    tab.emit_w0[ne] = w0;
+    tab.emit_w1[ne] = w1;
+    ++ne;
+  }
+  tab.n_emit = ne;
+  DeviceGuard g(w->device);
+  // outputs requested at ts[0] itself (emit_step == -1) are y0
+  for (int e = 0; e < ne; ++e)
+    if (tab.emit_step[e] < 0)
+      IDFF_CUDA(cudaMemcpyAsync(d_out + (size_t)tab.emit_out[e] * N * p->dim, d_y0, (size_t)N * p->dim * sizeof(float),
+                                cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return generic_sample_sde(w, p, tab, d_y0, d_I_k, d_I_k0, d_out, N, stream);
+}

@@ -1,0 +1,135 @@
+// Shared declarations of libidff_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/idff_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "idff_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace idff {
+
+// ---- error plumbing ---------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define IDFF_CHECK_ARG(cond, ...)        \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::idff::set_error(__VA_ARGS__);    \
+      return IDFF_EINVAL;                \
+    }                                    \
+  } while (0)
+
+#define IDFF_CUDA(call)                                                                              \
+  do {                                                                                               \
+    cudaError_t e__ = (call);                                                                        \
+    if (e__ != cudaSuccess) {                                                                        \
+      ::idff::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return IDFF_ECUDA;                                                                             \
+    }                                                                                                \
+  } while (0)
+
+// ---- the packed network --------------------------------------------------------------------------------------
+// Device view of one 4-layer SELU MLP (torchcfm/models/models.py:4-21).  All pointers are device pointers.
+struct NetView {
+  int din;       // layer-0 input columns that depend on the particle: [x.., t] (embedding columns folded away)
+  int din_pad;   // din rounded up to 4
+  int w;         // hidden width
+  int dout;      // network outputs
+  int n_tidx;    // rows of the folded layer-0 bias table (1 without an embedding)
+  const float* wt0;   // [din_pad][w]   W0^T (rows >= din are zero)
+  const float* wt1;   // [w][w]         W1^T : forward operand  (row k = input unit k, contiguous over outputs)
+  const float* wt2;   // [w][w]         W2^T
+  const float* w1;    // [w][w]         W1 as stored by nn.Linear ([out][in]): reverse-sweep operand
+  const float* w2;    // [w][w]         W2
+  const float* w3;    // [dout][w]      W3 as stored
+  const float* wt3;   // [w][dout]      W3^T
+  const float* b0;    // [n_tidx][w]    layer-0 bias (+ W0[:, din:] . emb[t_idx])
+  const float* b1;    // [w]
+  const float* b2;    // [w]
+  const float* b3;    // [dout]
+  const float* u3;    // [w]  sum_k W3[k][n]   : adjoint seed of phi = sum_k out_k
+  const float* zd1;   // [w]  sum_{d<D} W0[n][d] : tangent of z1 along d = (1,..,1)  (D = din - 1)
+};
+
+}  // namespace idff
+
+struct idff_weights {
+  idff::NetView v;
+  int device;
+  int dims[5];
+  int emb_rows, emb_dim;
+  float* d_blob;        // single allocation holding every array above
+  size_t blob_floats;
+};
+
+namespace idff {
+
+// ---- per-evaluation scalars, computed on the host in fp32 in the reference's operation order ------------------
+// One Stage = one call of the field at a scalar time t.
+struct Stage {
+  float t;        // evaluation time
+  int kind;       // 0: t == 0 branch, 1: t == 1 branch, 2: interior
+  float a;        // sqrt(1 - Gamma*sigma_t^2)            (multiplies (x1hat - x))
+  float den;      // (1 - t)
+  float c[3];     // folded momentum coefficients of g1,g2,g3 (sign included); SCOREHEAD: c[0] scales st, c[1] is the constant term
+  float end_div;  // divisor of the t == 1 branch
+};
+
+void make_stage(const idff_field_params_t& p, float t, Stage* out);
+
+
+// ---- launch tables (passed by value as __grid_constant__ kernel parameters; CUDA 12.1+ allows 32 KB) ---------
+constexpr int kMaxIntervals = 96;
+struct Rk4Table {
+  int n_iv;
+  float dt[kMaxIntervals];
+  Stage st[4 * kMaxIntervals];
+};
+
+constexpr int kMaxSdeSteps = 48;
+constexpr int kMaxSdeEmit = 64;
+struct SdeTable {
+  int n_steps, n_emit, method;      // method 0 srk, 1 euler
+  float h[kMaxSdeSteps];
+  float gval[kMaxSdeSteps][4];      // g at t0 + C1[s]*h (state independent)
+  Stage st[kMaxSdeSteps][3];        // f evaluations at t0 + C0[s]*h, s = 0,1,2 (alpha[3] == 0)
+  int emit_step[kMaxSdeEmit];       // after this step (-1: before the first) ...
+  int emit_out[kMaxSdeEmit];        // ... write output row emit_out = w0*prev_y + w1*y
+  float emit_w0[kMaxSdeEmit], emit_w1[kMaxSdeEmit];
+};
+
+constexpr float kSeluLambda = 1.0507009873554805f;
+constexpr float kSeluAlpha = 1.6732632423543772f;
+constexpr float kSeluLA = 1.0507009873554805f * 1.6732632423543772f;
+
+#ifdef __CUDACC__
+// SELU value and the derivative code.  ATen evaluates ELU as (exp(x) - 1) * (alpha*scale) for x <= 0 and its
+// backward as (alpha*scale) * exp(x) (x <= 0) / scale (x > 0); all higher derivatives on the negative branch
+// equal E = alpha*scale*exp(x) and vanish on the positive branch.  `code` packs both: code < 0 -> positive
+// branch (s' = lambda, E = 0), else s' = E = code.
+__device__ __forceinline__ float selu_fwd(float z, float& code) {
+  if (z <= 0.0f) {
+    float e = expf(z);
+    code = kSeluLA * e;
+    return (e - 1.0f) * kSeluLA;
+  }
+  code = -1.0f;
+  return z * kSeluLambda;
+}
+__device__ __forceinline__ float selu_val(float z) {
+  return z <= 0.0f ? (expf(z) - 1.0f) * kSeluLA : z * kSeluLambda;
+}
+__device__ __forceinline__ void selu_decode(float code, float& s1, float& E) {
+  s1 = code < 0.0f ? kSeluLambda : code;
+  E = code < 0.0f ? 0.0f : code;
+}
+#endif
+
+}  // namespace idff

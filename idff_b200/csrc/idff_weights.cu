@@ -1,0 +1,181 @@
+// Weights handle, error plumbing and the host-side per-evaluation scalars.
+#include <cmath>
+#include <cstdarg>
+#include <atomic>
+#include <vector>
+
+#include "idff_common.cuh"
+
+namespace idff {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+// Scalars of one field evaluation, in fp32 and in the operation order of the reference wrappers
+// (Autograd_example_order2.py:47,73-75; example_order1_with_prediction_head.py:75,93-95;
+//  MD_simulation.py:502,523-525).  The per-element products c*g*sigma_t2/sigma^2 are folded into one scalar.
+void make_stage(const idff_field_params_t& p, float t, Stage* out) {
+  Stage s;
+  memset(&s, 0, sizeof(s));
+  s.t = t;
+  s.kind = (t == 0.0f) ? 0 : (t == 1.0f ? 1 : 2);
+  s.end_div = (float)p.end_div;
+  volatile float one_m_t = 1.0f - t;
+  s.den = one_m_t;
+  const float sigf = (float)p.sigma;
+  const float sig2f = (float)(p.sigma * p.sigma);
+  const float c1f = (float)(0.5 * (2.0 * p.gamma[0] - 1.0));
+  if (p.variant == IDFF_FIELD_MOMENTUM) {
+    volatile float prod = t * one_m_t;
+    volatile float sq = sqrtf(prod);
+    volatile float sig_t = sigf * sq;
+    volatile float sig_t2 = sig_t * sig_t;
+    double G = 0.0;
+    for (int i = 0; i < p.order; ++i) G += p.gamma[i];
+    volatile float gs = (float)G * sig_t2;
+    volatile float om = 1.0f - gs;
+    s.a = sqrtf(om);
+    volatile float m0 = c1f * sig_t2;
+    s.c[0] = m0 / sig2f;
+    for (int i = 1; i < p.order && i < 3; ++i) {
+      volatile float mi = (float)p.gamma[i] * sig_t2;
+      s.c[i] = mi / sig2f;
+    }
+  } else if (p.variant == IDFF_FIELD_MD) {
+    volatile float m = sig2f * t;
+    volatile float sig_t2 = m * one_m_t;
+    volatile float om = 1.0f - sig_t2;
+    s.a = sqrtf(om);
+    volatile float m0 = c1f * sig_t2;
+    s.c[0] = -(m0 / sig2f);
+    volatile float m1 = (float)p.gamma[1] * sig_t2;
+    s.c[1] = -(m1 / sig2f);
+  } else if (p.variant == IDFF_FIELD_SCOREHEAD) {
+    volatile float prod = t * one_m_t;
+    volatile float sq = sqrtf(prod);
+    volatile float sig_t = sigf * sq;
+    volatile float sig_t2 = sig_t * sig_t;
+    volatile float gs = (float)(p.gamma[0] + p.gamma[1]) * sig_t2;
+    volatile float om = 1.0f - gs;
+    s.a = sqrtf(om);
+    s.c[0] = c1f * sig_t2;
+    s.c[1] = (float)p.gamma[1] * sig_t2;
+  } else {
+    s.a = 1.0f;
+  }
+  *out = s;
+}
+
+}  // namespace idff
+
+using namespace idff;
+
+extern "C" int idff_version(void) { return 100; }
+extern "C" const char* idff_last_error(void) { return idff::g_err; }
+extern "C" uint64_t idff_launch_count(void) { return idff::g_launches.load(); }
+
+extern "C" int idff_weights_create(const float* const* h_W, const float* const* h_b, const int32_t* dims,
+                                   int32_t n_layers, const float* h_emb, int32_t emb_rows, int32_t emb_dim,
+                                   int32_t device, idff_weights_t** out) {
+  IDFF_CHECK_ARG(h_W && h_b && dims && out, "idff_weights_create: null argument");
+  IDFF_CHECK_ARG(n_layers == 4, "idff_weights_create: n_layers must be 4 (Linear-SELU x3 -Linear), got %d", n_layers);
+  const int din_total = dims[0], w = dims[1], dout = dims[4];
+  IDFF_CHECK_ARG(dims[2] == w && dims[3] == w, "idff_weights_create: hidden widths differ (%d,%d,%d)", dims[1], dims[2], dims[3]);
+  IDFF_CHECK_ARG(w >= 32 && w % 32 == 0 && w <= 4096, "idff_weights_create: hidden width %d must be a multiple of 32 in [32,4096]", w);
+  const bool has_emb = h_emb != nullptr;
+  IDFF_CHECK_ARG(!has_emb || (emb_rows > 0 && emb_dim > 0 && emb_dim < din_total), "idff_weights_create: bad embedding shape");
+  const int din = has_emb ? din_total - emb_dim : din_total;
+  IDFF_CHECK_ARG(din >= 1 && din <= 256 && dout >= 1 && dout <= 256, "idff_weights_create: din %d / dout %d out of range", din, dout);
+  const int din_pad = (din + 3) & ~3;
+  const int n_tidx = has_emb ? emb_rows : 1;
+
+  // layout of the blob (all offsets multiples of 4 floats = 16 B, the TMA bulk-copy granule)
+  auto al = [](size_t n) { return (n + 31) & ~size_t(31); };
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += al(n); return o; };
+  const size_t o_wt0 = take((size_t)din_pad * w), o_wt1 = take((size_t)w * w), o_wt2 = take((size_t)w * w);
+  const size_t o_w1 = take((size_t)w * w), o_w2 = take((size_t)w * w), o_w3 = take((size_t)dout * w);
+  const size_t o_wt3 = take((size_t)w * dout), o_b0 = take((size_t)n_tidx * w), o_b1 = take(w), o_b2 = take(w);
+  const size_t o_b3 = take(dout), o_u3 = take(w), o_zd1 = take(w);
+  std::vector<float> blob(off, 0.0f);
+
+  const float *W0 = h_W[0], *W1 = h_W[1], *W2 = h_W[2], *W3 = h_W[3];
+  for (int n = 0; n < w; ++n)
+    for (int k = 0; k < din; ++k) blob[o_wt0 + (size_t)k * w + n] = W0[(size_t)n * din_total + k];
+  for (int n = 0; n < w; ++n)
+    for (int k = 0; k < w; ++k) {
+      blob[o_wt1 + (size_t)k * w + n] = W1[(size_t)n * w + k];
+      blob[o_wt2 + (size_t)k * w + n] = W2[(size_t)n * w + k];
+    }
+  memcpy(&blob[o_w1], W1, sizeof(float) * w * w);
+  memcpy(&blob[o_w2], W2, sizeof(float) * w * w);
+  memcpy(&blob[o_w3], W3, sizeof(float) * dout * w);
+  for (int d = 0; d < dout; ++d)
+    for (int n = 0; n < w; ++n) blob[o_wt3 + (size_t)n * dout + d] = W3[(size_t)d * w + n];
+  for (int r = 0; r < n_tidx; ++r)
+    for (int n = 0; n < w; ++n) {
+      double acc = h_b[0][n];
+      if (has_emb)
+        for (int e = 0; e < emb_dim; ++e)
+          acc += (double)W0[(size_t)n * din_total + din + e] * (double)h_emb[(size_t)r * emb_dim + e];
+      blob[o_b0 + (size_t)r * w + n] = (float)acc;
+    }
+  memcpy(&blob[o_b1], h_b[1], sizeof(float) * w);
+  memcpy(&blob[o_b2], h_b[2], sizeof(float) * w);
+  memcpy(&blob[o_b3], h_b[3], sizeof(float) * dout);
+  for (int n = 0; n < w; ++n) {
+    double u = 0.0, z = 0.0;
+    for (int d = 0; d < dout; ++d) u += W3[(size_t)d * w + n];
+    for (int d = 0; d < din - 1; ++d) z += W0[(size_t)n * din_total + d];
+    blob[o_u3 + n] = (float)u;
+    blob[o_zd1 + n] = (float)z;
+  }
+
+  int prev = 0;
+  IDFF_CUDA(cudaGetDevice(&prev));
+  IDFF_CUDA(cudaSetDevice(device));
+  float* d_blob = nullptr;
+  cudaError_t e = cudaMalloc(&d_blob, off * sizeof(float));
+  if (e != cudaSuccess) {
+    cudaSetDevice(prev);
+    set_error("idff_weights_create: cudaMalloc(%zu) failed: %s", off * sizeof(float), cudaGetErrorString(e));
+    return IDFF_ENOMEM;
+  }
+  e = cudaMemcpy(d_blob, blob.data(), off * sizeof(float), cudaMemcpyHostToDevice);
+  cudaSetDevice(prev);
+  if (e != cudaSuccess) {
+    cudaFree(d_blob);
+    set_error("idff_weights_create: cudaMemcpy failed: %s", cudaGetErrorString(e));
+    return IDFF_ECUDA;
+  }
+  idff_weights* h = new idff_weights();
+  h->device = device;
+  for (int i = 0; i < 5; ++i) h->dims[i] = dims[i];
+  h->emb_rows = has_emb ? emb_rows : 0;
+  h->emb_dim = has_emb ? emb_dim : 0;
+  h->d_blob = d_blob;
+  h->blob_floats = off;
+  NetView& v = h->v;
+  v.din = din; v.din_pad = din_pad; v.w = w; v.dout = dout; v.n_tidx = n_tidx;
+  v.wt0 = d_blob + o_wt0; v.wt1 = d_blob + o_wt1; v.wt2 = d_blob + o_wt2;
+  v.w1 = d_blob + o_w1; v.w2 = d_blob + o_w2; v.w3 = d_blob + o_w3; v.wt3 = d_blob + o_wt3;
+  v.b0 = d_blob + o_b0; v.b1 = d_blob + o_b1; v.b2 = d_blob + o_b2; v.b3 = d_blob + o_b3;
+  v.u3 = d_blob + o_u3; v.zd1 = d_blob + o_zd1;
+  *out = h;
+  return IDFF_OK;
+}
+
+extern "C" int idff_weights_destroy(idff_weights_t* w) {
+  if (!w) return IDFF_OK;
+  cudaFree(w->d_blob);
+  delete w;
+  return IDFF_OK;
+}

@@ -1,0 +1,166 @@
+"""Conditional-flow-matching path samplers behind the reference's API
+(torchcfm/conditional_flow_matching.py:12-312), computed by the fused B200 path-sample kernel.
+
+    xt = t*x1 + (1-t)*x0 + sigma_t*eps ,   ut = x1 - x0
+
+`sample_location_and_conditional_flow` keeps the reference's draw order (t from torch.rand on the CPU generator,
+then eps = randn_like(x0)) and produces xt and ut in ONE kernel launch, bit-exact with the reference's fp32
+operation order.  Inputs must be CUDA float32 tensors; there is no CPU path."""
+import math
+from typing import Union
+
+import torch
+
+from .. import _lib
+
+__all__ = ["pad_t_like_x", "ConditionalFlowMatcher", "ExactOptimalTransportConditionalFlowMatcher",
+           "TargetConditionalFlowMatcher", "VariancePreservingConditionalFlowMatcher"]
+
+
+def pad_t_like_x(t, x):
+    """(bs,) -> (bs, 1, ..., 1) so t broadcasts against x; numbers pass through (reference :12-33)."""
+    if isinstance(t, (float, int)):
+        return t
+    return t.reshape(-1, *([1] * (x.dim() - 1)))
+
+
+def _path_sample(x0, x1, t, eps, sigma, sigma_mode, want_ut=True, idx0=None, idx1=None):
+    for n, v in (("x0", x0), ("x1", x1), ("t", t)):
+        _lib.require_cuda(v, n)
+    if x0.shape != x1.shape:
+        raise _lib.IdffError(f"x0 {tuple(x0.shape)} and x1 {tuple(x1.shape)} differ")
+    B = x0.shape[0] if idx0 is None else idx0.shape[0]
+    D = x0[0].numel() if x0.shape[0] > 0 else int(math.prod(x0.shape[1:]))
+    x0c, x1c, tc = x0.contiguous(), x1.contiguous(), t.contiguous()
+    epsc = None
+    if eps is not None:
+        _lib.require_cuda(eps, "eps")
+        epsc = eps.contiguous()
+    out_shape = (B,) + tuple(x0.shape[1:])
+    xt = torch.empty(out_shape, device=x0.device, dtype=torch.float32)
+    ut = torch.empty(out_shape, device=x0.device, dtype=torch.float32) if want_ut else None
+    _lib.check(_lib.lib().idff_path_sample(_lib.ptr(x0c), _lib.ptr(x1c), _lib.ptr(tc), _lib.ptr(epsc),
+                                           _lib.ptr(idx0), _lib.ptr(idx1), float(sigma), int(sigma_mode),
+                                           _lib.ptr(xt), _lib.ptr(ut), B, D, _lib.stream_of(x0)),
+               "idff_path_sample")
+    return xt, ut
+
+
+class ConditionalFlowMatcher:
+    """Independent CFM: N(t*x1 + (1-t)*x0, sigma) (reference :36-211)."""
+    _sigma_mode = 0      # sigma_t = sigma
+    _lambda_dynamic = 0  # 2*sigma_t**2/(sigma**2+1e-8)   (reference :210-211)
+
+    def __init__(self, sigma: Union[float, int] = 0.0):
+        self.sigma = sigma
+
+    # -- pieces (kept for API parity; the fused call below does not go through them) -------------------------
+    def compute_mu_t(self, x0, x1, t):
+        xt, _ = _path_sample(x0, x1, t, None, 0.0, 0, want_ut=False)
+        return xt
+
+    def compute_sigma_t(self, t):
+        del t
+        return self.sigma
+
+    def sample_xt(self, x0, x1, t, epsilon):
+        xt, _ = _path_sample(x0, x1, t, epsilon, self.sigma, self._sigma_mode, want_ut=False)
+        return xt
+
+    def compute_conditional_flow(self, x0, x1, t, xt):
+        del t, xt
+        return x1 - x0
+
+    def sample_noise_like(self, x):
+        return torch.randn_like(x)
+
+    def _fusable(self):
+        c = type(self)
+        base = ConditionalFlowMatcher
+        return (c.compute_mu_t is base.compute_mu_t and c.sample_xt is base.sample_xt
+                and c.compute_conditional_flow is base.compute_conditional_flow)
+
+    def sample_location_and_conditional_flow(self, x0, x1, t=None, return_noise=False):
+        if t is None:
+            t = torch.rand(x0.shape[0]).type_as(x0)          # CPU generator first (reference :184)
+        assert len(t) == x0.shape[0], "t has to have batch size dimension"
+        eps = self.sample_noise_like(x0)                     # then the noise (reference :187)
+        if self._fusable():
+            xt, ut = _path_sample(x0, x1, t, eps, self.sigma, self._sigma_mode)
+        else:
+            xt = self.sample_xt(x0, x1, t, eps)
+            ut = self.compute_conditional_flow(x0, x1, t, xt)
+        if return_noise:
+            return t, xt, ut, eps
+        return t, xt, ut
+
+    def compute_lambda(self, t):
+        _lib.require_cuda(t, "t")
+        tc = t.contiguous()
+        out = torch.empty_like(tc)
+        _lib.check(_lib.lib().idff_compute_lambda(_lib.ptr(tc), float(self.sigma), self._sigma_mode,
+                                                  self._lambda_dynamic, _lib.ptr(out), tc.numel(),
+                                                  _lib.stream_of(tc)), "idff_compute_lambda")
+        return out
+
+
+class ExactOptimalTransportConditionalFlowMatcher(ConditionalFlowMatcher):
+    """The matcher every IDFF script uses (reference :214-312): sigma_t = sigma*sqrt(t(1-t)); the OT re-pairing is
+    disabled in this file (reference :265) and the batch is remembered in .x0/.x1 for the loss
+    (Autograd_example_order2.py:105)."""
+    _sigma_mode = 1
+
+    def __init__(self, sigma: Union[float, int] = 0.0):
+        super().__init__(sigma)
+        self.ot_sampler = None
+
+    def compute_sigma_t(self, t):
+        return self.sigma * torch.sqrt(t * (1 - t))
+
+    def sample_location_and_conditional_flow(self, x0, x1, t=None, return_noise=False):
+        self.x1 = x1
+        self.x0 = x0
+        return super().sample_location_and_conditional_flow(x0, x1, t, return_noise)
+
+    def guided_sample_location_and_conditional_flow(self, x0, x1, y0=None, y1=None, t=None, return_noise=False):
+        out = ConditionalFlowMatcher.sample_location_and_conditional_flow(self, x0, x1, t, return_noise)
+        if return_noise:
+            t, xt, ut, eps = out
+            return t, xt, ut, y0, y1, eps
+        t, xt, ut = out
+        return t, xt, ut, y0, y1
+
+
+class TargetConditionalFlowMatcher(ConditionalFlowMatcher):
+    """Lipman-style target path (reference :315-388).  No IDFF configuration uses it: plain torch ops."""
+
+    def compute_mu_t(self, x0, x1, t):
+        del x0
+        return pad_t_like_x(t, x1) * x1
+
+    def compute_sigma_t(self, t):
+        return 1 - (1 - self.sigma) * t
+
+    def sample_xt(self, x0, x1, t, epsilon):
+        return self.compute_mu_t(x0, x1, t) + pad_t_like_x(self.compute_sigma_t(t), x0) * epsilon
+
+    def compute_conditional_flow(self, x0, x1, t, xt):
+        del x0
+        tp = pad_t_like_x(t, x1)
+        return (x1 - (1 - self.sigma) * xt) / (1 - (1 - self.sigma) * tp)
+
+
+class VariancePreservingConditionalFlowMatcher(ConditionalFlowMatcher):
+    """Trigonometric interpolant (reference :550-608).  No IDFF configuration uses it: plain torch ops."""
+
+    def compute_mu_t(self, x0, x1, t):
+        tp = pad_t_like_x(t, x0)
+        return torch.cos(math.pi / 2 * tp) * x0 + torch.sin(math.pi / 2 * tp) * x1
+
+    def sample_xt(self, x0, x1, t, epsilon):
+        return self.compute_mu_t(x0, x1, t) + pad_t_like_x(self.compute_sigma_t(t), x0) * epsilon
+
+    def compute_conditional_flow(self, x0, x1, t, xt):
+        del xt
+        tp = pad_t_like_x(t, x0)
+        return math.pi / 2 * (torch.cos(math.pi / 2 * tp) * x1 - torch.sin(math.pi / 2 * tp) * x0)

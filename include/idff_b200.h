@@ -1,0 +1,141 @@
+/* idff_b200.h -- C-ABI of the B200-native IDFF hot path (libidff_b200.so).
+ *
+ * The reference (MrRezaeiUofT/IDFF) is pure Python and has no FFI; each entry point below names the
+ * reference interface it replaces (file:line under the reference root).  The host-side mirror of the
+ * reference's call conventions (torchcfm matchers, forward(t,x) modules, f/g SDE objects) lives in
+ * idff_b200/*.py and reaches these functions through ctypes -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative IDFF_E* code; it never throws and never aborts;
+ *     idff_last_error() returns a thread-local message for the last failure on the calling thread;
+ *   - pointers named d_* are DEVICE pointers owned by the caller (torch tensors), fp32 row-major unless
+ *     stated; pointers named h_* are HOST pointers;  `stream` is a cudaStream_t passed as void*;
+ *   - nothing is allocated per call; the only persistent allocation is the weights handle;
+ *   - no global mutable state: handles are independent, calls on one handle may be issued from one host
+ *     thread at a time.
+ */
+#ifndef IDFF_B200_H
+#define IDFF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IDFF_OK 0
+#define IDFF_EINVAL (-1)   /* bad argument (shape, null pointer, unsupported size) */
+#define IDFF_ECUDA (-2)    /* CUDA runtime error (message in idff_last_error) */
+#define IDFF_ENOMEM (-3)
+#define IDFF_EUNSUPPORTED (-4)
+
+/* field variants (the reference's four wrappers around the MLP) */
+#define IDFF_FIELD_MOMENTUM 0 /* CustomNetModel, 2D_examples/Autograd_example_order2.py:36-76 (order 2),
+                                 Autograd_example_order3.py:34-77 (order 3); order 1 = g2 = g3 = 0 */
+#define IDFF_FIELD_SCOREHEAD 1 /* CustomNetModel, 2D_examples/example_order1_with_prediction_head.py:64-96 */
+#define IDFF_FIELD_CFM 2       /* CFMModel, 2D_examples/Autograd_example_order2.py:310-332 */
+#define IDFF_FIELD_MD 3        /* SDE_cal.f, timeseris_example/MD_simulation.py:497-526 */
+
+/* which kernel family serves a sampler call */
+#define IDFF_IMPL_AUTO 0
+#define IDFF_IMPL_GENERIC 1 /* any width / dimension: one thread per hidden unit, weights from L2 */
+#define IDFF_IMPL_FUSED 2   /* persistent warp-tiled kernel, weights streamed by TMA bulk copies */
+
+typedef struct idff_weights idff_weights_t; /* opaque: packed device copies of one 4-layer SELU MLP */
+
+typedef struct idff_field_params {
+  int32_t variant;   /* IDFF_FIELD_* */
+  int32_t order;     /* 1..3: number of gamma terms (MOMENTUM); 2 for MD; ignored otherwise */
+  int32_t dim;       /* state dimension D of one particle */
+  int32_t t_idx;     /* MD: embedding row (SDE_cal init_ind, MD_simulation.py:501); else 0 */
+  int32_t impl;      /* IDFF_IMPL_* */
+  int32_t reserved;
+  double sigma;      /* sigma of the probability path (order2.py:30; MD_simulation.py:542) -- Python floats */
+  double gamma[3];   /* gamma1..gamma3 */
+  double end_div;    /* divisor of the t == 1 branch: 1e-2 (order2.py:60) or SDE_cal.dt (MD_simulation.py:510) */
+} idff_field_params_t;
+
+int idff_version(void);
+const char* idff_last_error(void);
+/* number of kernels this library has launched from the calling process so far (bench.py's gpu_launches) */
+uint64_t idff_launch_count(void);
+
+/* ---- a1/a2: the networks, torchcfm/models/models.py:4-21 (MLP) and :23-42 (MLP_Embedding) ------------
+ * h_W[l] is nn.Linear.weight of layer l, row-major [dims[l+1]][dims[l]] (+emb_dim extra input columns on
+ * layer 0 when an embedding is given); h_b[l] its bias.  n_layers must be 4 and dims[1]==dims[2]==dims[3].
+ * h_emb (optional) is nn.Embedding.weight [emb_rows][emb_dim]; because every row of a batch shares one
+ * time index during generation (MD_simulation.py:501) it is folded into a per-index layer-0 bias table. */
+int idff_weights_create(const float* const* h_W, const float* const* h_b, const int32_t* dims, int32_t n_layers,
+                        const float* h_emb, int32_t emb_rows, int32_t emb_dim, int32_t device,
+                        idff_weights_t** out);
+int idff_weights_destroy(idff_weights_t* w);
+
+/* plain MLP forward on rows of cat[x, t] (models.py:20-21 / :40-42 with the folded embedding): d_in [N][dims[0]],
+ * d_out [N][dims[4]]. */
+int idff_mlp_forward(const idff_weights_t* w, const float* d_in, float* d_out, int64_t N, int32_t t_idx,
+                     void* stream);
+
+/* ---- a3..a7: one evaluation of the IDFF field f(t, x); backs forward(t, x) / SDE_cal.f(t, y) ------------
+ * d_x [N][dim] -> d_out [N][dim].  d_x0 is only read by IDFF_FIELD_CFM at t != 0 (the x captured at t == 0). */
+int idff_field_eval(const idff_weights_t* w, const idff_field_params_t* p, float t, const float* d_x,
+                    const float* d_x0, float* d_out, int64_t N, void* stream);
+
+/* Host-only diagnostic: the per-evaluation scalars the kernels receive for time t, computed in fp32 in the
+ * reference's operation order.  out[0..7] = {t, kind (0: t==0, 1: t==1, 2: interior), a = sqrt(1-Gamma sigma_t^2),
+ * 1-t, c1, c2, c3, end_div}.  Needs no GPU. */
+int idff_stage_scalars(const idff_field_params_t* p, float t, float* h_out8);
+
+/* ---- a8 + a3..a6 fused: torchdiffeq.odeint(model, x0, t_grid, method='rk4') (3/8 rule, grid == t_grid;
+ * call sites Autograd_example_order2.py:167,213,291).  h_t_grid: n_grid fp32 times on the host.
+ * d_out_final [N][dim] = traj[-1]; d_out_traj (optional) [n_grid][N][dim] = the whole traj. */
+int idff_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, const float* d_x0,
+                    const float* h_t_grid, int32_t n_grid, float* d_out_final, float* d_out_traj, int64_t N,
+                    void* stream);
+
+/* ---- a8 + a7 fused: torchsde.sdeint(sde, y0, ts, dt) for SDE_cal (MD_simulation.py:209,228); method 0 = srk
+ * (torchsde default for ito/diagonal), 1 = euler.  Brownian increments are injected: d_I_k, d_I_k0
+ * [n_steps][N][dim] with n_steps = idff_sde_num_steps(h_ts, n_ts, dt); d_I_k0 may be NULL for euler.
+ * d_out [n_ts][N][dim] (linear interpolation at ts, as torchsde does). g(t,y) = 180 sigma^2 sqrt(t(1-t)). */
+int idff_sde_num_steps(const float* h_ts, int32_t n_ts, float dt);
+int idff_sample_sde(const idff_weights_t* w, const idff_field_params_t* p, const float* d_y0, const float* h_ts,
+                    int32_t n_ts, float dt, int32_t method, const float* d_I_k, const float* d_I_k0, float* d_out,
+                    int64_t N, void* stream);
+
+/* ---- a9/a10: ConditionalFlowMatcher.sample_xt + compute_conditional_flow,
+ * torchcfm/conditional_flow_matching.py:98-148 (= conditional_flow_matching_dynamic.py:101-151):
+ *   xt = t*x1 + (1-t)*x0 + sigma_t*eps,  ut = x1 - x0      (bit-exact: no FMA contraction)
+ * sigma_mode 0: sigma_t = sigma (:79-96); 1: sigma_t = sigma*sqrt(t(1-t)) (ExactOT :231-233).
+ * d_idx0/d_idx1 (optional int64 [B]) re-pair rows first: x0[idx0[b]], x1[idx1[b]] (the OT plan's output,
+ * conditional_flow_matching_dynamic.py:268 / optimal_transport.py:140-142).  d_t [B], others [B][D]. */
+int idff_path_sample(const float* d_x0, const float* d_x1, const float* d_t, const float* d_eps,
+                     const int64_t* d_idx0, const int64_t* d_idx1, float sigma, int32_t sigma_mode, float* d_xt,
+                     float* d_ut, int64_t B, int64_t D, void* stream);
+
+/* ---- a11: compute_lambda, conditional_flow_matching.py:195-211 (dynamic = 0: 2 sigma_t^2/(sigma^2+1e-8))
+ * and conditional_flow_matching_dynamic.py:198-214 (dynamic = 1: 2 sigma_t/(sigma^2+1e-8)). */
+int idff_compute_lambda(const float* d_t, float sigma, int32_t sigma_mode, int32_t dynamic, float* d_out,
+                        int64_t B, void* stream);
+
+/* ---- a12: losses.  kind 0: flow loss mean(((vt-x1)/(1e-2+1-t))^2), Autograd_example_order2.py:105;
+ * kind 1: score loss mean((st-logp)^2) with logp of example_order1_with_prediction_head.py:26-51,124-132
+ *         (a = st, needs x1,x0,xt,t, sigma0_sq = the value passed at :126);
+ * kind 2: PolyALA periodic loss sum_k mean((vt-(x1+k))^2), k in {0,+360,-360}, MD_simulation.py:137-141.
+ * d_loss: one fp32.  d_grad (optional) [B][D]: d loss / d a, scaled by grad_scale.
+ * d_scratch: >= idff_loss_scratch_bytes() bytes of device scratch (partial sums). */
+int64_t idff_loss_scratch_bytes(void);
+int idff_loss(int32_t kind, const float* d_a, const float* d_x1, const float* d_x0, const float* d_xt,
+              const float* d_t, float sigma0_sq, float grad_scale, float* d_loss, float* d_grad, int64_t B,
+              int64_t D, void* d_scratch, void* stream);
+
+/* ---- a13: compute_mmd_rbf, Autograd_example_order2.py:260-278 (= compute_mmd, MD_simulation.py:50-86):
+ * biased V-statistic with K = exp(-|a-b|^2 / (2 sigma_k^2)).  Accumulates into d_sums[3] (fp64, caller
+ * zeroes them): sum of Kxx over rows [row_begin,row_end) x all x, sum of Kyy over the matching share of y
+ * rows, sum of Kxy over x rows [row_begin,row_end) x all y -- so ranks can split the work by rows and add. */
+int idff_mmd_rbf(const float* d_x, int64_t N, const float* d_y, int64_t M, int32_t D, float sigma_k,
+                 double* d_sums, int64_t x_row_begin, int64_t x_row_end, int64_t y_row_begin, int64_t y_row_end,
+                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IDFF_B200_H */

@@ -206,12 +206,24 @@ _SRI2 = dict(
 
 
 def sde_step_grid(ts, dt):
-    """Fixed-step grid of torchsde BaseSDESolver.integrate: curr_t += dt, clipped to ts[-1]."""
-    grid = [float(ts[0])]
-    end = float(ts[-1])
+    """Fixed-step grid of torchsde BaseSDESolver.integrate: curr_t = min(curr_t + dt, ts[-1]) evaluated on fp32
+    tensors (ts is an fp32 tensor, dt a Python float), so the grid accumulates in fp32."""
+    grid = [np.float32(ts[0])]
+    end = np.float32(ts[-1])
+    step = np.float32(dt)
     while grid[-1] < end:
-        grid.append(min(grid[-1] + dt, end))
-    return grid
+        grid.append(min(np.float32(grid[-1] + step), end))
+    return [float(g) for g in grid]
+
+
+def _linear_interp(t0, y0, t1, y1, t):
+    """torchsde _core/interp.py linear_interp: (t1 - t)/(t1 - t0)*y0 + (t - t0)/(t1 - t0)*y1, in fp32."""
+    t0, t1, t = np.float32(t0), np.float32(t1), np.float32(t)
+    if t1 == t0:
+        return y1
+    w0 = float(np.float32(t1 - t) / np.float32(t1 - t0))
+    w1 = float(np.float32(t - t0) / np.float32(t1 - t0))
+    return w0 * y0 + w1 * y1
 
 
 def sdeint_srk(sde, y0, ts, dt, I_k, I_k0):
@@ -257,11 +269,7 @@ def sdeint_srk(sde, y0, ts, dt, I_k, I_k0):
             y = y1
             gi += 1
             step += 1
-        t0f, t1f = prev_t, grid[gi]
-        if out_t == t1f:
-            ys.append(y)
-        else:
-            ys.append(prev_y + (y - prev_y) * ((out_t - t0f) / (t1f - t0f)))
+        ys.append(y0 if gi == 0 else _linear_interp(prev_t, prev_y, grid[gi], y, out_t))
     return torch.stack(ys)
 
 
@@ -279,10 +287,7 @@ def sdeint_euler(sde, y0, ts, dt, I_k):
             prev_t, prev_y = grid[gi], y
             y = y + sde.f(t0, y) * h + sde.g(t0, y) * I_k[gi]
             gi += 1
-        if out_t == grid[gi]:
-            ys.append(y)
-        else:
-            ys.append(prev_y + (y - prev_y) * ((out_t - prev_t) / (grid[gi] - prev_t)))
+        ys.append(y0 if gi == 0 else _linear_interp(prev_t, prev_y, grid[gi], y, out_t))
     return torch.stack(ys)
 
 

@@ -1,0 +1,82 @@
+"""CPU-only checks of the C-ABI: the library loads, exports every symbol include/idff_b200.h declares, validates
+arguments without touching a GPU, and its host-side scalars follow the reference's fp32 operation order."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from idff_b200 import _lib
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "idff_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(idff_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared_symbols()
+    assert len(names) >= 15
+    L = C.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/idff_b200.h but not exported"
+    assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
+    assert _lib.lib().idff_version() >= 100
+
+
+def test_argument_validation_needs_no_gpu():
+    L = _lib.lib()
+    assert L.idff_path_sample(None, None, None, None, None, None, 0.0, 0, None, None, -1, 2, None) == -1
+    assert b"bad shape" in L.idff_last_error()
+    assert L.idff_path_sample(None, None, None, None, None, None, 0.0, 0, None, None, 0, 2, None) == 0   # empty batch
+    assert L.idff_path_sample(None, None, None, None, None, None, 0.0, 0, None, None, 4, 2, None) == -1  # null pointers
+    assert L.idff_loss(7, None, None, None, None, None, 0.0, 1.0, None, None, 1, 1, None, None) == -1
+    assert L.idff_loss(0, None, None, None, None, None, 0.0, 1.0, None, None, 0, 2, None, None) == -1    # mean over nothing
+    assert L.idff_mmd_rbf(None, 1, None, 1, 2, 1.0, None, 0, 1, 0, 1, None) == -1
+    assert L.idff_sde_num_steps(None, 0, 0.1) == -1
+    ts = np.array([0.0, 0.5, 1.0], dtype=np.float32)
+    assert L.idff_sde_num_steps(ts.ctypes.data_as(C.c_void_p), 3, 0.3) == 4        # 0,.3,.6,.9,1
+    assert L.idff_sde_num_steps(ts.ctypes.data_as(C.c_void_p), 3, 0.25) == 4
+    with pytest.raises(_lib.IdffError):
+        _lib.require_cuda(torch.zeros(2), "x")                                      # no CPU path
+
+
+def _stage(variant, order, t, sigma, gam, end_div=1e-2):
+    p = _lib.FieldParams()
+    p.variant, p.order, p.dim, p.sigma, p.end_div = variant, order, 2, sigma, end_div
+    for i, g in enumerate(gam):
+        p.gamma[i] = g
+    out = (C.c_float * 8)()
+    assert _lib.lib().idff_stage_scalars(C.byref(p), t, out) == 0
+    return np.array(out[:], dtype=np.float32)
+
+
+def test_stage_scalars_follow_reference_op_order():
+    for tv in (0.0, 1.0 / 6.0, 0.37, float(np.float32(1) / np.float32(3)), 0.9, 1.0):
+        t = torch.tensor(tv, dtype=torch.float32)
+        for gam in ((0.2, 0.3), (1.0, 2.0), (-0.5, 0.0)):
+            s = _stage(_lib.IDFF_FIELD_MOMENTUM, 2, tv, 0.2, gam)
+            kind = 0 if tv == 0 else (1 if tv == 1 else 2)
+            assert s[1] == kind and s[0] == t.item()
+            st2 = (0.2 * torch.sqrt(t * (1 - t))) ** 2                         # Autograd_example_order2.py:47
+            a = torch.sqrt(1 - (gam[0] + gam[1]) * st2)                        # :73
+            assert s[2] == a.item() and s[3] == (1 - t).item()
+            one = torch.ones(())
+            c1 = 0.5 * (2 * gam[0] - 1) * one * st2 / (0.2 ** 2)               # :74 with grad == 1
+            c2 = gam[1] * one * st2 / (0.2 ** 2)                               # :75
+            assert s[4] == c1.item() and s[5] == c2.item() and s[6] == 0.0
+        s = _stage(_lib.IDFF_FIELD_MD, 2, tv, 0.5, (0.2, 1.25), end_div=0.3)
+        st2 = (0.5 ** 2) * t * (1 - t)                                          # MD_simulation.py:502
+        assert s[2] == torch.sqrt(1 - st2).item()                               # :523
+        assert s[4] == (-(0.5 * (2 * 0.2 - 1) * torch.ones(()) * st2 / 0.5 ** 2)).item()
+        assert s[5] == (-(1.25 * torch.ones(()) * st2 / 0.5 ** 2)).item()
+        assert s[7] == np.float32(0.3)
+        s = _stage(_lib.IDFF_FIELD_SCOREHEAD, 1, tv, 0.2, (0.3, 0.7))
+        st2 = (0.2 * torch.sqrt(t * (1 - t))) ** 2
+        assert s[2] == torch.sqrt(1 - (0.3 + 0.7) * st2).item()
+        assert s[4] == (0.5 * (2 * 0.3 - 1) * torch.ones(()) * st2).item()
+        assert s[5] == (0.7 * torch.ones(()) * st2).item()

@@ -1,0 +1,143 @@
+"""-m gpu: the fused samplers (whole RK4 / SRK solve in one launch) against trajectories produced by the reference's
+field code under the restated torchdiffeq / torchsde schemes.
+
+Accumulated-drift contract (SURVEY.md section 7 "kink chaos"): the fp32 reference itself differs from its fp64 twin by
+max 7e-5..5e-4 / median ~1e-6 over a solve (order 2) because SELU' and SELU'' jump at 0, and isolated order-3
+particles by up to 0.2.  So the bound is stated on the median and the 99.9th percentile; the max is reported."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from gpu_common import assert_field_close, drift_report, packed
+from idff_b200 import _lib, fields, sampler
+from make_golden_consts import GAMMAS2, GAMMAS3
+
+pytestmark = pytest.mark.gpu
+
+IMPLS = [_lib.IDFF_IMPL_GENERIC, _lib.IDFF_IMPL_AUTO]
+
+
+def _check_drift(got, ref32, ref64, what, med=2e-5, p999=2e-3):
+    r32, r64 = drift_report(got, ref32), drift_report(got, ref64)
+    base = drift_report(ref32, ref64)
+    print(f"{what}: vs fp32 ref {r32} | vs fp64 ref {r64} | fp32 ref vs fp64 ref {base}")
+    assert r32["median"] <= med and r64["median"] <= med, what
+    assert r32["p999"] <= max(p999, 4 * base["p999"]), what
+    assert r64["p999"] <= max(p999, 4 * base["p999"]), what
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("which", ["checkerboard", "8gaussians"])
+def test_rk4_order2_vs_golden(cuda_device, which, impl):
+    g = load_golden("traj2d")
+    x0 = torch.tensor(g["x0"]).to(cuda_device)
+    pw = packed(which, cuda_device)
+    for nfe in (2, 3, 5, 10):
+        for gi, gam in enumerate(GAMMAS2[:4]):
+            key = f"{which}_o2_nfe{nfe}_g{gi}"
+            if key not in g.files:
+                continue
+            m = fields.CustomNetModel(pw, 0.2, *gam)
+            m.impl = impl
+            ts = torch.linspace(0, 1, nfe + 1)
+            traj = sampler.odeint(m, x0, ts, rtol=1e-5, atol=1e-5, method="rk4")
+            assert traj.shape == (nfe + 1, x0.shape[0], 2)
+            assert torch.equal(traj[0], x0)
+            final = sampler.sample_rk4(m, x0, ts)
+            assert torch.equal(final, traj[-1])
+            ref = g[key]
+            ref_final = ref[-1] if ref.ndim == 3 else ref
+            _check_drift(final.cpu().numpy(), ref_final, g[key + "_f64"], f"{key} impl={impl}")
+            if ref.ndim == 3:
+                # first interval only: one rk4 step, no accumulated kink divergence yet
+                assert drift_report(traj[1].cpu().numpy(), ref[1])["median"] <= 1e-5
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_rk4_order3_and_cfm_vs_golden(cuda_device, impl):
+    g = load_golden("traj2d")
+    x0 = torch.tensor(g["x0"]).to(cuda_device)
+    pw = packed("checkerboard", cuda_device)
+    for nfe in (2, 5):
+        for gi, gam in enumerate(GAMMAS3[:2]):
+            key = f"checkerboard_o3_nfe{nfe}_g{gi}"
+            m = fields.CustomNetModelOrder3(pw, 0.2, *gam)
+            m.impl = impl
+            final = sampler.sample_rk4(m, x0, torch.linspace(0, 1, nfe + 1))
+            _check_drift(final.cpu().numpy(), g[key], g[key + "_f64"], f"{key} impl={impl}", med=5e-5, p999=0.05)
+    c = fields.CFMModel(pw)
+    c.impl = impl
+    final = sampler.sample_rk4(c, x0, torch.linspace(0, 1, 6))
+    assert drift_report(final.cpu().numpy(), g["checkerboard_cfm_nfe5"])["max"] <= 1e-4
+
+
+def test_rk4_scorehead_vs_golden(cuda_device):
+    g = load_golden("scorehead")
+    x0 = torch.tensor(load_golden("traj2d")["x0"][:256]).to(cuda_device)
+    pw = packed("scorehead", cuda_device)
+    for gi, gam in enumerate(g["gammas"]):
+        m = fields.CustomNetModelScoreHead(pw, 0.2, float(gam[0]), float(gam[1]))
+        final = sampler.sample_rk4(m, x0, torch.linspace(0, 1, 6))
+        r = drift_report(final.cpu().numpy(), g[f"traj_nfe5_g{gi}"])
+        assert r["median"] <= 1e-5 and r["p999"] <= 1e-3, r
+
+
+def test_host_stepped_odeint_equals_fused(cuda_device):
+    """Any callable can be stepped on the host with forward(t, x); it must agree with the one-launch solve."""
+    pw = packed("8gaussians", cuda_device)
+    m = fields.CustomNetModel(pw, 0.2, 0.2, 0.2)
+    x0 = torch.tensor(load_golden("traj2d")["x0"][:300]).to(cuda_device)
+    ts = torch.linspace(0, 1, 4)
+    fused = sampler.odeint(m, x0, ts, method="rk4")
+    stepped = sampler.odeint(lambda t, x: m(t, x), x0, ts, method="rk4")
+    r = drift_report(fused.cpu().numpy(), stepped.cpu().numpy())
+    assert r["median"] <= 2e-6 and r["p999"] <= 1e-3, r
+
+
+def test_rk4_properties_at_scale(cuda_device):
+    """N = 2^20 particles (BASELINE configs[1] lower end): particles are independent, so any sub-batch reproduces the
+    whole bit-for-bit (this is what makes the multi-GPU sharding exact); a long grid crosses the per-launch interval
+    limit and must equal the same grid solved in two calls."""
+    pw = packed("checkerboard", cuda_device)
+    m = fields.CustomNetModel(pw, 0.2, 0.2, 0.2)
+    g = torch.Generator(device=cuda_device).manual_seed(5)
+    x0 = torch.randn(1 << 20, 2, device=cuda_device, generator=g) / 1.5
+    ts = torch.linspace(0, 1, 3)
+    whole = sampler.sample_rk4(m, x0, ts)
+    assert torch.isfinite(whole).all()
+    lo, hi = 777, 777 + 100003
+    assert torch.equal(sampler.sample_rk4(m, x0[lo:hi], ts), whole[lo:hi])
+    assert torch.equal(sampler.sample_rk4(m, x0[:5], ts), whole[:5])
+    assert sampler.sample_rk4(m, x0[:0], ts).shape == (0, 2)
+    # degenerate grids
+    assert torch.equal(sampler.sample_rk4(m, x0[:64], torch.tensor([0.0])), x0[:64])
+    long_ts = torch.linspace(0, 1, 131)                      # 130 intervals > 96 per launch
+    a = sampler.sample_rk4(m, x0[:512], long_ts)
+    mid = sampler.sample_rk4(m, x0[:512], long_ts[:97])
+    b = sampler.sample_rk4(m, mid, long_ts[96:])
+    assert torch.equal(a, b)
+    with pytest.raises(_lib.IdffError):
+        sampler.sample_rk4(m, x0[:8], torch.tensor([0.0, 0.5, 0.5, 1.0]))
+
+
+def test_sde_srk_and_euler_vs_golden(cuda_device):
+    g = load_golden("md")
+    y = torch.tensor(g["y"]).to(cuda_device)
+    pw = packed("polyala", cuda_device)
+    sde = fields.SDE_cal(pw, input_dim=46, sigma=0.5, init_ind=3, max_length=200, dt=0.3, gamma1=0.2, gamma2=5.0 / 4)
+    ts = torch.tensor(g["ts"])
+    I_k, I_k0 = torch.tensor(g["I_k"]).to(cuda_device), torch.tensor(g["I_k0"]).to(cuda_device)
+    assert sampler.sde_num_steps(ts, 0.3) == I_k.shape[0] == 4
+    out = sampler.sdeint(sde, y, ts, dt=0.3, method="srk", bm=(I_k, I_k0))
+    assert out.shape == (3, 64, 46) and torch.equal(out[0], y)
+    # values are O(100) degrees; 1e-5 relative per step over 4 steps x 3 drift evaluations
+    for i in (1, 2):
+        assert_field_close(out[i].cpu().numpy(), g["srk"][i], 1e-4, f"srk ts[{i}]")
+    eul = sampler.sdeint(sde, y, ts, dt=0.3, method="euler", bm=(I_k, None))
+    for i in (1, 2):
+        assert_field_close(eul[i].cpu().numpy(), g["euler"][i], 1e-4, f"euler ts[{i}]")
+    # noise drawn on the device when not injected: finite, right shape, differs between draws
+    a = sampler.sdeint(sde, y, ts, dt=0.3)
+    b = sampler.sdeint(sde, y, ts, dt=0.3)
+    assert a.shape == (3, 64, 46) and torch.isfinite(a).all() and not torch.equal(a, b)

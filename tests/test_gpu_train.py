@@ -1,0 +1,162 @@
+"""-m gpu: path sample (bit-exact), lambda, losses and their gradients, through the public Python API (ctypes ->
+C-ABI -> sm_100a kernels), against the golden vectors produced by the reference's own code and the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+import idff_oracle as O
+from conftest import load_golden
+from idff_b200 import _lib, losses
+from idff_b200.torchcfm import conditional_flow_matching as cfm
+from idff_b200.torchcfm import conditional_flow_matching_dynamic as cfmd
+
+pytestmark = pytest.mark.gpu
+
+
+def _matcher(key, sigma):
+    dyn = key.startswith("dyn")
+    mod = cfmd if dyn else cfm
+    if "_Exact_" in key:
+        return cfm.ExactOptimalTransportConditionalFlowMatcher(sigma)
+    return mod.ConditionalFlowMatcher(sigma)
+
+
+def test_path_sample_bit_exact_vs_reference_golden(cuda_device):
+    g = load_golden("path")
+    keys = sorted({k.rsplit("_", 1)[0] for k in g.files if k.endswith("_xt")})
+    assert len(keys) >= 12
+    for k in keys:
+        sigma = float(k.rsplit("_s", 1)[1])
+        FM = _matcher(k, sigma)
+        x0, x1, t, eps = (torch.tensor(g[f"{k}_{n}"]).to(cuda_device) for n in ("x0", "x1", "t", "eps"))
+        FM.sample_noise_like = lambda x, e=eps: e             # inject the reference's noise draw
+        t2, xt, ut, eps2 = FM.sample_location_and_conditional_flow(x0, x1, t=t, return_noise=True)
+        np.testing.assert_array_equal(xt.cpu().numpy(), g[k + "_xt"], err_msg=k)
+        np.testing.assert_array_equal(ut.cpu().numpy(), g[k + "_ut"], err_msg=k)
+        assert t2 is t and eps2 is eps
+        np.testing.assert_array_equal(FM.sample_xt(x0, x1, t, eps).cpu().numpy(), g[k + "_xt"])
+        lam = FM.compute_lambda(t).cpu().numpy()
+        ref = np.broadcast_to(np.asarray(g[k + "_lambda"], dtype=np.float32), lam.shape)
+        np.testing.assert_allclose(lam, ref, rtol=2e-7, atol=0)
+
+
+def test_draw_order_t_then_eps(cuda_device):
+    """t comes from the CPU generator (torch.rand) BEFORE eps = randn_like(x0) on x0's device (reference :184,:187)."""
+    FM = cfm.ExactOptimalTransportConditionalFlowMatcher(sigma=0.5)
+    x0 = torch.randn(64, 46, device=cuda_device)
+    x1 = torch.randn(64, 46, device=cuda_device)
+    torch.manual_seed(123)
+    t, xt, ut, eps = FM.sample_location_and_conditional_flow(x0, x1, return_noise=True)
+    torch.manual_seed(123)
+    t_ref = torch.rand(64)
+    eps_ref = torch.randn_like(x0)
+    assert torch.equal(t.cpu(), t_ref) and torch.equal(eps, eps_ref)
+    assert FM.x0 is x0 and FM.x1 is x1
+    xt_ref, ut_ref = O.path_sample(x0.cpu(), x1.cpu(), t.cpu(), eps.cpu(), 0.5, True)
+    assert torch.equal(xt.cpu(), xt_ref) and torch.equal(ut.cpu(), ut_ref)
+    out = FM.guided_sample_location_and_conditional_flow(x0, x1, y0="a", y1="b")
+    assert len(out) == 5 and out[3] == "a" and out[4] == "b"
+    with pytest.raises(AssertionError):
+        FM.sample_location_and_conditional_flow(x0, x1, t=torch.rand(3, device=cuda_device))
+
+
+@pytest.mark.parametrize("B,D", [(0, 2), (1, 1), (3, 5), (257, 3), (1000, 46), (4096, 2)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_path_sample_ragged_and_gather(cuda_device, B, D, mode):
+    g = torch.Generator().manual_seed(B * 100 + D)
+    x0, x1, eps = (torch.randn(B, D, generator=g) for _ in range(3))
+    t = torch.rand(B, generator=g)
+    sigma = 0.3
+    xt, ut = cfm._path_sample(x0.to(cuda_device), x1.to(cuda_device), t.to(cuda_device), eps.to(cuda_device), sigma, mode)
+    xr, ur = O.path_sample(x0, x1, t, eps, sigma, bool(mode))
+    assert torch.equal(xt.cpu(), xr) and torch.equal(ut.cpu(), ur)
+    if B > 1:
+        i = torch.randint(0, B, (B,), generator=g)
+        j = torch.randint(0, B, (B,), generator=g)
+        xt, ut = cfm._path_sample(x0.to(cuda_device), x1.to(cuda_device), t.to(cuda_device), eps.to(cuda_device), sigma,
+                                  mode, idx0=i.to(cuda_device), idx1=j.to(cuda_device))
+        xr, ur = O.path_sample(x0[i], x1[j], t, eps, sigma, bool(mode))
+        assert torch.equal(xt.cpu(), xr) and torch.equal(ut.cpu(), ur)
+
+
+def test_dynamic_matcher_repairs_with_plan(cuda_device):
+    class FixedPlan:
+        def sample_map_indices(self, a, b):
+            n = a.shape[0]
+            return torch.arange(n - 1, -1, -1, device=a.device), torch.arange(n, device=a.device).roll(1)
+    FM = cfmd.ExactOptimalTransportConditionalFlowMatcher(sigma=0.1, ot_sampler=FixedPlan())
+    x0 = torch.randn(33, 4, device=cuda_device)
+    x1 = torch.randn(33, 4, device=cuda_device)
+    t, xt, ut, eps = FM.sample_location_and_conditional_flow(x0, x1, return_noise=True)
+    i, j = FixedPlan().sample_map_indices(x0, x1)
+    xr, ur = O.path_sample(x0[i].cpu(), x1[j].cpu(), t.cpu(), eps.cpu(), 0.1, True)
+    assert torch.equal(xt.cpu(), xr) and torch.equal(ut.cpu(), ur)
+    assert torch.equal(FM.x1, x1[j])
+    lam = FM.compute_lambda(t)
+    np.testing.assert_allclose(lam.cpu().numpy(), O.compute_lambda(t.cpu(), 0.1, True, True).numpy(), rtol=2e-7)
+
+
+def test_path_sample_full_size_properties(cuda_device):
+    """B = 2^24, D = 2 (BASELINE.md workload): ut is exactly x1 - x0; sigma = 0 gives the deterministic interpolant;
+    the kernel is linear in eps; chunks of the batch reproduce the whole bit-for-bit."""
+    B, D = 1 << 24, 2
+    g = torch.Generator(device=cuda_device).manual_seed(7)
+    x0 = torch.randn(B, D, device=cuda_device, generator=g)
+    x1 = torch.randn(B, D, device=cuda_device, generator=g)
+    eps = torch.randn(B, D, device=cuda_device, generator=g)
+    t = torch.rand(B, device=cuda_device, generator=g)
+    xt, ut = cfm._path_sample(x0, x1, t, eps, 0.0, 1)
+    assert torch.equal(ut, x1 - x0)
+    mu = t[:, None] * x1 + (1 - t[:, None]) * x0
+    assert torch.equal(xt, mu + 0.0 * eps)
+    xt2, _ = cfm._path_sample(x0, x1, t, eps, 0.5, 0)
+    assert torch.equal(xt2, mu + 0.5 * eps)
+    lo, hi = 12345, 12345 + (1 << 20) + 3
+    xt3, _ = cfm._path_sample(x0[lo:hi], x1[lo:hi], t[lo:hi], eps[lo:hi], 0.5, 0)
+    assert torch.equal(xt3, xt2[lo:hi])
+
+
+def test_path_sample_rejects_cpu_tensors():
+    FM = cfm.ConditionalFlowMatcher(0.1)
+    with pytest.raises(_lib.IdffError):
+        FM.sample_location_and_conditional_flow(torch.randn(4, 2), torch.randn(4, 2))
+
+
+@pytest.mark.parametrize("k", ["B256_D2", "B10_D46", "B1000_D2"])
+def test_losses_and_gradients_vs_golden(cuda_device, k):
+    g = load_golden("loss")
+    dev = cuda_device
+    vt, st, x0, x1, t, xt = (torch.tensor(g[f"{k}_{n}"]).to(dev) for n in ("vt", "st", "x0", "x1", "t", "xt"))
+    # tolerance: 1e-6 relative on the loss (fp64 block sums vs torch's fp32 pairwise mean), 2e-6 on gradients
+    v = vt.clone().requires_grad_(True)
+    l = losses.flow_loss(v, x1, t)
+    l.backward()
+    assert l.item() == pytest.approx(float(g[f"{k}_flow"]), rel=1e-6)
+    np.testing.assert_allclose(v.grad.cpu().numpy(), g[f"{k}_flow_gvt"], rtol=2e-6, atol=1e-12)
+    s = st.clone().requires_grad_(True)
+    l = losses.score_loss(s, xt, x1, x0, t, 0.2)
+    (l * 3.0).backward()
+    assert l.item() == pytest.approx(float(g[f"{k}_score"]), rel=2e-6)
+    np.testing.assert_allclose(s.grad.cpu().numpy() / 3.0, g[f"{k}_score_gst"], rtol=5e-6, atol=1e-9)
+    v = (vt * 100).clone().requires_grad_(True)
+    l = losses.md_periodic_loss(v, x1 * 90)
+    l.backward()
+    assert l.item() == pytest.approx(float(g[f"{k}_md"]), rel=1e-6)
+    np.testing.assert_allclose(v.grad.cpu().numpy(), g[f"{k}_md_gvt"], rtol=2e-6, atol=1e-9)
+    # no-grad call: value only, repeated calls reuse the scratch deterministically
+    with torch.no_grad():
+        a = losses.flow_loss(vt, x1, t).item()
+        b = losses.flow_loss(vt, x1, t).item()
+    assert a == b == pytest.approx(float(g[f"{k}_flow"]), rel=1e-6)
+
+
+def test_loss_large_batch_matches_fp64(cuda_device):
+    B, D = 1 << 22, 2
+    g = torch.Generator(device=cuda_device).manual_seed(3)
+    vt = torch.randn(B, D, device=cuda_device, generator=g)
+    x1 = torch.randn(B, D, device=cuda_device, generator=g)
+    t = torch.rand(B, device=cuda_device, generator=g)
+    got = losses.flow_loss(vt, x1, t).item()
+    w = 1.0 / (np.float32(1.01) - t.double()[:, None])
+    ref = ((w * (vt.double() - x1.double())) ** 2).mean().item()
+    assert got == pytest.approx(ref, rel=2e-6)
