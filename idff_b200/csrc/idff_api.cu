@@ -20,8 +20,10 @@ int generic_sample_sde(const idff_weights_t* w, const idff_field_params_t* p, co
 bool fused_supports(const idff_weights_t* w, const idff_field_params_t* p);
 int fused_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, const float* d_x0, const Stage* stages,
                      const float* dts, int n_iv, float* d_out_final, float* d_out_traj, int64_t N, void* stream);
-int fused_field_eval(const idff_weights_t* w, const idff_field_params_t* p, float t, const float* d_x, float* d_out,
-                     int64_t N, void* stream);
+int fused_field_eval(const idff_weights_t* w, const idff_field_params_t* p, float t, const float* d_x,
+                     const float* d_x0, float* d_out, int64_t N, void* stream);
+int fused_sample_sde(const idff_weights_t* w, const idff_field_params_t* p, const SdeTable& tab, const float* d_y0,
+                     const float* d_Ik, const float* d_Ik0, float* d_out, int64_t N, void* stream);
 
 struct DeviceGuard {
   int prev = -1;
@@ -82,7 +84,7 @@ extern "C" int idff_field_eval(const idff_weights_t* w, const idff_field_params_
       set_error("idff_field_eval: the fused kernel does not support this shape/variant");
       return IDFF_EUNSUPPORTED;
     }
-    return fused_field_eval(w, p, t, d_x, d_out, N, stream);
+    return fused_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
   }
   return generic_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
 }
@@ -213,5 +215,13 @@ extern "C" int idff_sample_sde(const idff_weights_t* w, const idff_field_params_
     if (tab.emit_step[e] < 0)
       IDFF_CUDA(cudaMemcpyAsync(d_out + (size_t)tab.emit_out[e] * N * p->dim, d_y0, (size_t)N * p->dim * sizeof(float),
                                 cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  const bool want_fused = p->impl == IDFF_IMPL_FUSED || (p->impl == IDFF_IMPL_AUTO && fused_supports(w, p));
+  if (want_fused) {
+    if (!fused_supports(w, p)) {
+      set_error("idff_sample_sde: the fused kernel does not support this shape/variant");
+      return IDFF_EUNSUPPORTED;
+    }
+    return fused_sample_sde(w, p, tab, d_y0, d_I_k, d_I_k0, d_out, N, stream);
+  }
   return generic_sample_sde(w, p, tab, d_y0, d_I_k, d_I_k0, d_out, N, stream);
 }

@@ -56,6 +56,14 @@ struct NetView {
   const float* b3;    // [dout]
   const float* u3;    // [w]  sum_k W3[k][n]   : adjoint seed of phi = sum_k out_k
   const float* zd1;   // [w]  sum_{d<D} W0[n][d] : tangent of z1 along d = (1,..,1)  (D = din - 1)
+  // column-permuted copies for the fused kernel (w in {128, 256}; null otherwise).  Physical column p of a row
+  // holds logical unit perm(p) = l + 32*(4h + jj) with p = 128h + 4l + jj, so that lane l of a warp reads its
+  // units {l, l+32, ...} with conflict-free 128-bit loads and writes them back with unit-stride addresses.
+  const float* fwt1;  // [w][w]  fwt1[k][p] = W1[perm(p)][k]   forward,  layer 2
+  const float* fwt2;  // [w][w]  fwt2[k][p] = W2[perm(p)][k]   forward,  layer 3
+  const float* fw2r;  // [w][w]  fw2r[n][p] = W2[n][perm(p)]   reverse,  layer 3 -> 2
+  const float* fw1r;  // [w][w]  fw1r[n][p] = W1[n][perm(p)]   reverse,  layer 2 -> 1
+  const float* w0n;   // [w][din-1]  W0[n][d], d < D            reverse,  layer 1 -> x  (wide-D path)
 };
 
 }  // namespace idff
@@ -67,6 +75,8 @@ struct idff_weights {
   int emb_rows, emb_dim;
   float* d_blob;        // single allocation holding every array above
   size_t blob_floats;
+  float* d_stash;       // order-3 fused sampler: per-thread derivative stash (allocated on first use)
+  size_t stash_bytes;
 };
 
 namespace idff {

@@ -105,6 +105,10 @@ extern "C" int idff_weights_create(const float* const* h_W, const float* const* 
   const size_t o_w1 = take((size_t)w * w), o_w2 = take((size_t)w * w), o_w3 = take((size_t)dout * w);
   const size_t o_wt3 = take((size_t)w * dout), o_b0 = take((size_t)n_tidx * w), o_b1 = take(w), o_b2 = take(w);
   const size_t o_b3 = take(dout), o_u3 = take(w), o_zd1 = take(w);
+  const bool fused_layout = (w == 128 || w == 256);
+  const size_t o_fwt1 = fused_layout ? take((size_t)w * w) : 0, o_fwt2 = fused_layout ? take((size_t)w * w) : 0;
+  const size_t o_fw2r = fused_layout ? take((size_t)w * w) : 0, o_fw1r = fused_layout ? take((size_t)w * w) : 0;
+  const size_t o_w0n = take((size_t)w * (din > 1 ? din - 1 : 1));
   std::vector<float> blob(off, 0.0f);
 
   const float *W0 = h_W[0], *W1 = h_W[1], *W2 = h_W[2], *W3 = h_W[3];
@@ -139,6 +143,20 @@ extern "C" int idff_weights_create(const float* const* h_W, const float* const* 
     blob[o_zd1 + n] = (float)z;
   }
 
+  if (fused_layout) {
+    auto perm = [](int p) { const int h = p / 128, l = (p % 128) / 4, jj = p % 4; return l + 32 * (4 * h + jj); };
+    for (int r = 0; r < w; ++r)
+      for (int p = 0; p < w; ++p) {
+        const int q = perm(p);
+        blob[o_fwt1 + (size_t)r * w + p] = W1[(size_t)q * w + r];
+        blob[o_fwt2 + (size_t)r * w + p] = W2[(size_t)q * w + r];
+        blob[o_fw2r + (size_t)r * w + p] = W2[(size_t)r * w + q];
+        blob[o_fw1r + (size_t)r * w + p] = W1[(size_t)r * w + q];
+      }
+  }
+  for (int n = 0; n < w; ++n)
+    for (int d = 0; d < din - 1; ++d) blob[o_w0n + (size_t)n * (din - 1) + d] = W0[(size_t)n * din_total + d];
+
   int prev = 0;
   IDFF_CUDA(cudaGetDevice(&prev));
   IDFF_CUDA(cudaSetDevice(device));
@@ -169,6 +187,10 @@ extern "C" int idff_weights_create(const float* const* h_W, const float* const* 
   v.w1 = d_blob + o_w1; v.w2 = d_blob + o_w2; v.w3 = d_blob + o_w3; v.wt3 = d_blob + o_wt3;
   v.b0 = d_blob + o_b0; v.b1 = d_blob + o_b1; v.b2 = d_blob + o_b2; v.b3 = d_blob + o_b3;
   v.u3 = d_blob + o_u3; v.zd1 = d_blob + o_zd1;
+  v.fwt1 = fused_layout ? d_blob + o_fwt1 : nullptr; v.fwt2 = fused_layout ? d_blob + o_fwt2 : nullptr;
+  v.fw2r = fused_layout ? d_blob + o_fw2r : nullptr; v.fw1r = fused_layout ? d_blob + o_fw1r : nullptr;
+  v.w0n = d_blob + o_w0n;
+  h->d_stash = nullptr; h->stash_bytes = 0;
   *out = h;
   return IDFF_OK;
 }
@@ -176,6 +198,7 @@ extern "C" int idff_weights_create(const float* const* h_W, const float* const* 
 extern "C" int idff_weights_destroy(idff_weights_t* w) {
   if (!w) return IDFF_OK;
   cudaFree(w->d_blob);
+  if (w->d_stash) cudaFree(w->d_stash);
   delete w;
   return IDFF_OK;
 }

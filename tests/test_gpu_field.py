@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from conftest import load_golden
-from gpu_common import assert_field_close, packed
+from gpu_common import assert_field_close, assert_field_vs_refs, packed
 from idff_b200 import _lib, fields
 from idff_b200.torchcfm.models.models import MLP, MLP_Embedding
 from make_golden_consts import FIELD_TIMES, GAMMAS2, GAMMAS3
@@ -27,14 +27,15 @@ def test_field2d_order2_order3(cuda_device, which, impl):
         m.impl = impl
         for ti, tv in enumerate(FIELD_TIMES):
             out = m(torch.tensor(tv, dtype=torch.float32), x).cpu().numpy()
-            worst = max(worst, assert_field_close(out, g[f"{which}_o2_g{gi}"][ti], 1e-5, f"o2 g{gi} t={tv}"))
-            assert_field_close(out, g[f"{which}_o2_g{gi}_f64"][ti], 1e-5, f"o2 g{gi} t={tv} vs fp64")
+            worst = max(worst, assert_field_vs_refs(out, g[f"{which}_o2_g{gi}"][ti], g[f"{which}_o2_g{gi}_f64"][ti],
+                                                    1e-5, f"o2 g{gi} t={tv}"))
     for gi, gam in enumerate(GAMMAS3):
         m = fields.CustomNetModelOrder3(pw, 0.2, *gam)
         m.impl = impl
         for ti, tv in enumerate(FIELD_TIMES):
             out = m(torch.tensor(tv, dtype=torch.float32), x).cpu().numpy()
-            worst = max(worst, assert_field_close(out, g[f"{which}_o3_g{gi}"][ti], 2e-5, f"o3 g{gi} t={tv}"))
+            worst = max(worst, assert_field_vs_refs(out, g[f"{which}_o3_g{gi}"][ti], g[f"{which}_o3_g{gi}_f64"][ti],
+                                                    1e-5, f"o3 g{gi} t={tv}"))
     print(f"[{which} impl={impl}] worst per-eval error / max|f| = {worst:.2e}")
 
 
@@ -87,13 +88,15 @@ def test_scorehead_and_cfm_fields(cuda_device):
     assert f1.shape == x.shape and torch.isfinite(f1).all()
 
 
-def test_md_field_with_folded_embedding(cuda_device):
+@pytest.mark.parametrize("impl", IMPLS)
+def test_md_field_with_folded_embedding(cuda_device, impl):
     g = load_golden("md")
     y = torch.tensor(g["y"]).to(cuda_device)
     pw = packed("polyala", cuda_device)
     for ii in g["init_inds"]:
         sde = fields.SDE_cal(pw, input_dim=46, sigma=0.5, init_ind=int(ii), max_length=200, dt=0.3, gamma1=0.2,
                              gamma2=5.0 / (1 + int(ii)))
+        sde.impl = impl
         assert sde.noise_type == "diagonal" and sde.sde_type == "ito"
         for ti, tv in enumerate((0.0, 0.3, 0.6, 1.0)):
             t = torch.tensor(tv)

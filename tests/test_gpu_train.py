@@ -52,7 +52,7 @@ def test_draw_order_t_then_eps(cuda_device):
     eps_ref = torch.randn_like(x0)
     assert torch.equal(t.cpu(), t_ref) and torch.equal(eps, eps_ref)
     assert FM.x0 is x0 and FM.x1 is x1
-    xt_ref, ut_ref = O.path_sample(x0.cpu(), x1.cpu(), t.cpu(), eps.cpu(), 0.5, True)
+    xt_ref, ut_ref = O.path_sample(x0.cpu(), x1.cpu(), t.cpu(), eps.cpu(), 0.5, True, ieee_sqrt=True)
     assert torch.equal(xt.cpu(), xt_ref) and torch.equal(ut.cpu(), ut_ref)
     out = FM.guided_sample_location_and_conditional_flow(x0, x1, y0="a", y1="b")
     assert len(out) == 5 and out[3] == "a" and out[4] == "b"
@@ -68,14 +68,15 @@ def test_path_sample_ragged_and_gather(cuda_device, B, D, mode):
     t = torch.rand(B, generator=g)
     sigma = 0.3
     xt, ut = cfm._path_sample(x0.to(cuda_device), x1.to(cuda_device), t.to(cuda_device), eps.to(cuda_device), sigma, mode)
-    xr, ur = O.path_sample(x0, x1, t, eps, sigma, bool(mode))
+    # IEEE sqrt: torch's CPU sqrt (MKL VML) is 1 ulp off in ~0.6% of entries above a few hundred elements
+    xr, ur = O.path_sample(x0, x1, t, eps, sigma, bool(mode), ieee_sqrt=True)
     assert torch.equal(xt.cpu(), xr) and torch.equal(ut.cpu(), ur)
     if B > 1:
         i = torch.randint(0, B, (B,), generator=g)
         j = torch.randint(0, B, (B,), generator=g)
         xt, ut = cfm._path_sample(x0.to(cuda_device), x1.to(cuda_device), t.to(cuda_device), eps.to(cuda_device), sigma,
                                   mode, idx0=i.to(cuda_device), idx1=j.to(cuda_device))
-        xr, ur = O.path_sample(x0[i], x1[j], t, eps, sigma, bool(mode))
+        xr, ur = O.path_sample(x0[i], x1[j], t, eps, sigma, bool(mode), ieee_sqrt=True)
         assert torch.equal(xt.cpu(), xr) and torch.equal(ut.cpu(), ur)
 
 
@@ -89,7 +90,7 @@ def test_dynamic_matcher_repairs_with_plan(cuda_device):
     x1 = torch.randn(33, 4, device=cuda_device)
     t, xt, ut, eps = FM.sample_location_and_conditional_flow(x0, x1, return_noise=True)
     i, j = FixedPlan().sample_map_indices(x0, x1)
-    xr, ur = O.path_sample(x0[i].cpu(), x1[j].cpu(), t.cpu(), eps.cpu(), 0.1, True)
+    xr, ur = O.path_sample(x0[i].cpu(), x1[j].cpu(), t.cpu(), eps.cpu(), 0.1, True, ieee_sqrt=True)
     assert torch.equal(xt.cpu(), xr) and torch.equal(ut.cpu(), ur)
     assert torch.equal(FM.x1, x1[j])
     lam = FM.compute_lambda(t)
@@ -114,6 +115,9 @@ def test_path_sample_full_size_properties(cuda_device):
     lo, hi = 12345, 12345 + (1 << 20) + 3
     xt3, _ = cfm._path_sample(x0[lo:hi], x1[lo:hi], t[lo:hi], eps[lo:hi], 0.5, 0)
     assert torch.equal(xt3, xt2[lo:hi])
+    # ExactOT sigma_t against the same expression evaluated by torch on the GPU (IEEE sqrt, separate kernels)
+    xt4, _ = cfm._path_sample(x0, x1, t, eps, 0.3, 1)
+    assert torch.equal(xt4, mu + (0.3 * torch.sqrt(t * (1 - t)))[:, None] * eps)
 
 
 def test_path_sample_rejects_cpu_tensors():
@@ -142,7 +146,9 @@ def test_losses_and_gradients_vs_golden(cuda_device, k):
     l = losses.md_periodic_loss(v, x1 * 90)
     l.backward()
     assert l.item() == pytest.approx(float(g[f"{k}_md"]), rel=1e-6)
-    np.testing.assert_allclose(v.grad.cpu().numpy(), g[f"{k}_md_gvt"], rtol=2e-6, atol=1e-9)
+    # the +-360 terms cancel in the gradient: absolute tolerance relative to the largest entry
+    gm = g[f"{k}_md_gvt"]
+    np.testing.assert_allclose(v.grad.cpu().numpy(), gm, rtol=2e-6, atol=2e-7 * np.abs(gm).max())
     # no-grad call: value only, repeated calls reuse the scratch deterministically
     with torch.no_grad():
         a = losses.flow_loss(vt, x1, t).item()
