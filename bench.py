@@ -298,16 +298,20 @@ def aux_measurements(dev, pw, model, peaks):
     by = (5 * D + 1) * 4 * B
     aux["path_sample"] = {"rows_per_s": B / s, "GBps": by / s / 1e9, "frac_hbm": by / s / 1e9 / peaks["hbm_gbs"],
                           "shape": [B, D], "bound": "hbm", "bytes_per_row": (5 * D + 1) * 4}
-    vt = torch.randn(B, D, device=dev, generator=g).requires_grad_(True)
-
-    def loss_fb():
-        losses.flow_loss(vt, x1, t).backward()
-    s = timeit(loss_fb)
+    vt = torch.randn(B, D, device=dev, generator=g)
+    s = timeit(lambda: losses._run(0, vt, x1, None, None, t, 0.0, True))
     by = (3 * D + 1) * 4 * B
     aux["flow_loss_fwd_bwd"] = {"rows_per_s": B / s, "GBps": by / s / 1e9, "frac_hbm": by / s / 1e9 / peaks["hbm_gbs"],
                                 "shape": [B, D], "bound": "hbm", "bytes_per_row": (3 * D + 1) * 4,
-                                "note": "includes torch's grad*g multiply of the autograd wrapper"}
-    del x0, x1, eps, vt, t
+                                "note": "one pass: loss value + d loss/d vt (idff_loss)"}
+    vg = vt.clone().requires_grad_(True)
+
+    def loss_fb():
+        vg.grad = None
+        losses.flow_loss(vg, x1, t).backward()
+    s = timeit(loss_fb)
+    aux["flow_loss_autograd"] = {"rows_per_s": B / s, "note": "through the torch.autograd wrapper (adds grad*g)"}
+    del x0, x1, eps, vt, vg, t
     n = 32768
     a = torch.randn(n, 2, device=dev, generator=g)
     b = torch.randn(n, 2, device=dev, generator=g)

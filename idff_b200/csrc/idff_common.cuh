@@ -125,13 +125,11 @@ constexpr float kSeluLA = 1.0507009873554805f * 1.6732632423543772f;
 // equal E = alpha*scale*exp(x) and vanish on the positive branch.  `code` packs both: code < 0 -> positive
 // branch (s' = lambda, E = 0), else s' = E = code.
 __device__ __forceinline__ float selu_fwd(float z, float& code) {
-  if (z <= 0.0f) {
-    float e = expf(z);
-    code = kSeluLA * e;
-    return (e - 1.0f) * kSeluLA;
-  }
-  code = -1.0f;
-  return z * kSeluLambda;
+  // branch-free (a warp holds units on both sides of the kink): exp of min(z, 0), then select.  !(z <= 0) keeps NaN.
+  const float e = expf(fminf(z, 0.0f));
+  const bool pos = !(z <= 0.0f);
+  code = pos ? -1.0f : kSeluLA * e;
+  return pos ? z * kSeluLambda : (e - 1.0f) * kSeluLA;
 }
 __device__ __forceinline__ float selu_val(float z) {
   return z <= 0.0f ? (expf(z) - 1.0f) * kSeluLA : z * kSeluLambda;

@@ -14,6 +14,7 @@ struct MmdJob {
   const float* a;   // rows [a_begin, a_end) of this set ...
   const float* b;   // ... against all nb rows of this set
   long a_begin, a_end, nb;
+  int symmetric;   // a == b and the rows cover the whole set: evaluate only the upper block triangle
 };
 struct MmdJobs {
   MmdJob job[3];
@@ -43,13 +44,16 @@ __device__ __forceinline__ void block_accumulate(double v, double* dst) {
 
 // ---- small D (<= 4): A points in registers, B chunk broadcast from shared memory --------------------------------
 constexpr int kSmallRA = 2;        // A rows per thread
-constexpr int kSmallBC = 2048;     // B rows per CTA
+constexpr int kSmallBC = 256 * kSmallRA;   // B rows per CTA (= A rows per CTA: square blocks, so symmetry is per block)
 template <int D>
 __global__ void __launch_bounds__(256) k_mmd_small(const __grid_constant__ MmdJobs jobs, double* __restrict__ sums) {
   const MmdJob& jb = jobs.job[blockIdx.z];
   const long a0 = jb.a_begin + (long)blockIdx.x * (256 * kSmallRA);
   const long b0 = (long)blockIdx.y * kSmallBC;
   if (a0 >= jb.a_end || b0 >= jb.nb) return;
+  // K(a,b) = K(b,a): blocks below the diagonal are skipped, blocks above it count twice
+  if (jb.symmetric && blockIdx.y < blockIdx.x) return;
+  const double weight = (jb.symmetric && blockIdx.y > blockIdx.x) ? 2.0 : 1.0;
   __shared__ __align__(16) float bs[kSmallBC * D];
   const long bcnt = jb.nb - b0 < kSmallBC ? jb.nb - b0 : kSmallBC;
   for (long i = threadIdx.x; i < bcnt * D; i += 256) bs[i] = jb.b[b0 * D + i] * jobs.scale;
@@ -89,7 +93,7 @@ __global__ void __launch_bounds__(256) k_mmd_small(const __grid_constant__ MmdJo
     for (int r = 0; r < kSmallRA; ++r)
       if (valid[r]) tot += (double)acc[r];
   }
-  block_accumulate(tot, sums + blockIdx.z);
+  block_accumulate(tot * weight, sums + blockIdx.z);
 }
 
 // ---- any D: 64 x 64 pair tile per iteration, 4 x 4 pairs per thread, coordinates staged in chunks of 16 ---------
@@ -158,9 +162,10 @@ extern "C" int idff_mmd_rbf(const float* d_x, int64_t N, const float* d_y, int64
   IDFF_CHECK_ARG(0 <= x_row_begin && x_row_begin <= x_row_end && x_row_end <= N, "idff_mmd_rbf: bad x row range");
   IDFF_CHECK_ARG(0 <= y_row_begin && y_row_begin <= y_row_end && y_row_end <= M, "idff_mmd_rbf: bad y row range");
   MmdJobs jobs;
-  jobs.job[0] = {d_x, d_x, (long)x_row_begin, (long)x_row_end, (long)N};
-  jobs.job[1] = {d_y, d_y, (long)y_row_begin, (long)y_row_end, (long)M};
-  jobs.job[2] = {d_x, d_y, (long)x_row_begin, (long)x_row_end, (long)M};
+  const bool small = D <= 4;   // the symmetric shortcut is implemented by the small-D kernel
+  jobs.job[0] = {d_x, d_x, (long)x_row_begin, (long)x_row_end, (long)N, small && x_row_begin == 0 && x_row_end == N};
+  jobs.job[1] = {d_y, d_y, (long)y_row_begin, (long)y_row_end, (long)M, small && y_row_begin == 0 && y_row_end == M};
+  jobs.job[2] = {d_x, d_y, (long)x_row_begin, (long)x_row_end, (long)M, 0};
   jobs.scale = (float)sqrt(1.4426950408889634 / (2.0 * (double)sigma_k * (double)sigma_k));
   jobs.D = D;
   const long amax = (x_row_end - x_row_begin) > (y_row_end - y_row_begin) ? (x_row_end - x_row_begin) : (y_row_end - y_row_begin);

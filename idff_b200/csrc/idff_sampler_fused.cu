@@ -60,6 +60,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(s32(b)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(s32(b)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)),
                "l"(src), "r"(bytes), "r"(s32(bar))
@@ -139,6 +165,7 @@ struct Warp {
   int lane, ctid, D, dout, variant, reverse;
   int stage;
   uint32_t phase;
+  bool ready;   // the current chunk's full barrier was already observed complete
 
   __device__ __forceinline__ int dim() const { return DT > 0 ? DT : D; }
 
@@ -151,11 +178,15 @@ struct Warp {
       for (int j = 0; j < CT; ++j) acc[r][j] = 0.0f;
 #pragma unroll 1
     for (int ch = 0; ch < Geo<W>::NCHUNK; ++ch) {
-      mbar_wait(&full[stage], phase);
+      if (!ready) mbar_wait(&full[stage], phase);
       const float* Bs = stages + stage * Geo<W>::CHUNK + lane * 4;
       const float* As = A + ch * KC * RW;
+      const int nstage = stage + 1 == NSTAGE ? 0 : stage + 1;
+      const uint32_t nphase = stage + 1 == NSTAGE ? phase ^ 1u : phase;
 #pragma unroll
       for (int kk = 0; kk < KC; ++kk) {
+        // probe the next chunk's barrier in the middle of this one so its latency hides behind the FMAs
+        if (kk == KC / 2) ready = mbar_test_wait(&full[nstage], nphase);
         float b[CT], a[NJA * 4];
 #pragma unroll
         for (int h = 0; h < CT / 4; ++h) {
@@ -517,7 +548,7 @@ k_fused(const __grid_constant__ FParams P, const __grid_constant__ Rk4Table rk, 
           for (int gi = 0; gi < ng; ++gi) {
             const float* src = gi == 0 ? P.net.fwt1 : (gi == 1 ? P.net.fwt2 : (gi == 2 ? P.net.fw2r : P.net.fw1r));
             for (int ch = 0; ch < G::NCHUNK; ++ch) {
-              mbar_wait(&empty[stage], phase ^ 1u);
+              while (!mbar_try_wait(&empty[stage], phase ^ 1u)) __nanosleep(128);   // do not steal issue slots
               mbar_arrive_expect_tx(&full[stage], G::CHUNK * 4);
               tma_load_1d(smem + L.stages + stage * G::CHUNK, src + (size_t)ch * G::CHUNK, G::CHUNK * 4, &full[stage]);
               if (++stage == G::NSTAGE) { stage = 0; phase ^= 1u; }
@@ -544,7 +575,7 @@ k_fused(const __grid_constant__ FParams P, const __grid_constant__ Rk4Table rk, 
   wp.y = stt; wp.k1 = stt + L.sd; wp.k2 = stt + 2 * L.sd; wp.k3 = stt + 3 * L.sd; wp.xs = stt + 4 * L.sd;
   wp.fb = stt + 5 * L.sd; wp.x0c = stt + 6 * L.sd; wp.pred = stt + 7 * L.sd; wp.g = stt + 8 * L.sd;
   wp.lane = lane; wp.ctid = tid; wp.D = D; wp.dout = dout; wp.variant = P.variant; wp.reverse = P.reverse;
-  wp.stage = 0; wp.phase = 0;
+  wp.stage = 0; wp.phase = 0; wp.ready = false;
   const int Dd = wp.dim();
   const float third = (float)(1.0 / 3.0);
 

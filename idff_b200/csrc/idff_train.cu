@@ -102,9 +102,41 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 }
 
 // kind 0: flow loss; 1: score loss; 2: periodic MD loss.  One pass computes the loss terms and, when asked,
-// the gradient wrt the network output `a`.  Partial sums are fp64 per block, combined in block order by the
-// last block to finish (deterministic).
+// the gradient wrt the network output `a`.  VEC = 4: 128-bit loads/stores of 4 consecutive elements (rows are
+// recovered from the flat index); VEC = 1: ragged / unaligned.  Partial sums are fp64 per block, combined in block
+// order by the last block to finish (deterministic).
 template <int KIND>
+__device__ __forceinline__ void loss_elem(float av, float b1, float x0v, float xtv, float tv, float sigma0_sq,
+                                          float gk, float& s0, float& s1, float& s2, float& gout) {
+  if (KIND == 0) {
+    // mean(((1/(1e-2+1-t)) * (vt - x1))**2)           Autograd_example_order2.py:105
+    const float wgt = __fdiv_rn(1.0f, __fsub_rn(1.01f, tv));
+    const float r = __fmul_rn(wgt, __fsub_rn(av, b1));
+    s0 += __fmul_rn(r, r);
+    gout = 2.0f * r * wgt * gk;
+  } else if (KIND == 1) {
+    // mean((st - logp)**2), logp per example_order1_with_prediction_head.py:42-50
+    const float omt = __fsub_rn(1.0f, tv);
+    const float mu = __fadd_rn(__fmul_rn(tv, b1), __fmul_rn(omt, x0v));
+    const float s2v = __fadd_rn(__fmul_rn(__fmul_rn(sigma0_sq, tv), omt), 1e-4f);
+    const float diff = __fsub_rn(xtv, mu);
+    const float lp = __fmul_rn(-0.5f, __fadd_rn(logf(__fmul_rn(6.283185307179586f, s2v)),
+                                                __fdiv_rn(__fmul_rn(diff, diff), s2v)));
+    const float r = __fsub_rn(av, lp);
+    s0 += __fmul_rn(r, r);
+    gout = 2.0f * r * gk;
+  } else {
+    // mean((vt-x1)^2) + mean((vt-(x1+360))^2) + mean((vt-(x1-360))^2)     MD_simulation.py:137-141
+    const float r0 = __fsub_rn(av, b1), r1 = __fsub_rn(av, __fadd_rn(b1, 360.0f)),
+                r2 = __fsub_rn(av, __fsub_rn(b1, 360.0f));
+    s0 += __fmul_rn(r0, r0);
+    s1 += __fmul_rn(r1, r1);
+    s2 += __fmul_rn(r2, r2);
+    gout = 2.0f * (r0 + r1 + r2) * gk;
+  }
+}
+
+template <int KIND, int VEC>
 __global__ void __launch_bounds__(256) k_loss(const float* __restrict__ a, const float* __restrict__ x1,
                                               const float* __restrict__ x0, const float* __restrict__ xt,
                                               const float* __restrict__ t, float sigma0_sq, float gscale,
@@ -112,44 +144,55 @@ __global__ void __launch_bounds__(256) k_loss(const float* __restrict__ a, const
                                               LossScratch* __restrict__ sc) {
   __shared__ double sh[8];
   __shared__ bool last;
-  const float inv_n = (float)(1.0 / (double)n);
+  const float gk = (float)(1.0 / (double)n) * gscale;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f;
   double d0 = 0.0, d1 = 0.0, d2 = 0.0;
-  int cnt = 0;
   const long stride = (long)gridDim.x * blockDim.x;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const long row = i / D;
-    const float av = a[i], b1 = x1[i];
-    if (KIND == 0) {
-      // mean(((1/(1e-2+1-t)) * (vt - x1))**2)           Autograd_example_order2.py:105
-      const float wgt = __fdiv_rn(1.0f, __fsub_rn(1.01f, __ldg(t + row)));
-      const float r = __fmul_rn(wgt, __fsub_rn(av, b1));
-      s0 += __fmul_rn(r, r);
-      if (grad) grad[i] = 2.0f * r * wgt * inv_n * gscale;
-    } else if (KIND == 1) {
-      // mean((st - logp)**2), logp per example_order1_with_prediction_head.py:42-50
-      const float tv = __ldg(t + row), omt = __fsub_rn(1.0f, tv);
-      const float mu = __fadd_rn(__fmul_rn(tv, b1), __fmul_rn(omt, x0[i]));
-      const float s2v = __fadd_rn(__fmul_rn(__fmul_rn(sigma0_sq, tv), omt), 1e-4f);
-      const float diff = __fsub_rn(xt[i], mu);
-      const float lp = __fmul_rn(-0.5f, __fadd_rn(logf(__fmul_rn(6.283185307179586f, s2v)),
-                                                  __fdiv_rn(__fmul_rn(diff, diff), s2v)));
-      const float r = __fsub_rn(av, lp);
-      s0 += __fmul_rn(r, r);
-      if (grad) grad[i] = 2.0f * r * inv_n * gscale;
-    } else {
-      // mean((vt-x1)^2) + mean((vt-(x1+360))^2) + mean((vt-(x1-360))^2)     MD_simulation.py:137-141
-      const float r0 = __fsub_rn(av, b1), r1 = __fsub_rn(av, __fadd_rn(b1, 360.0f)),
-                  r2 = __fsub_rn(av, __fsub_rn(b1, 360.0f));
-      s0 += __fmul_rn(r0, r0);
-      s1 += __fmul_rn(r1, r1);
-      s2 += __fmul_rn(r2, r2);
-      if (grad) grad[i] = 2.0f * (r0 + r1 + r2) * inv_n * gscale;
+  if (VEC == 4) {
+    const long n4 = n >> 2;
+    const float4 *a4 = reinterpret_cast<const float4*>(a), *x14 = reinterpret_cast<const float4*>(x1),
+                 *x04 = reinterpret_cast<const float4*>(x0), *xt4 = reinterpret_cast<const float4*>(xt);
+    float4* g4 = reinterpret_cast<float4*>(grad);
+    int cnt = 0;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const float4 av = __ldcs(a4 + i), bv = __ldcs(x14 + i);
+      float4 x0v = make_float4(0.f, 0.f, 0.f, 0.f), xtv = x0v;
+      if (KIND == 1) { x0v = __ldcs(x04 + i); xtv = __ldcs(xt4 + i); }
+      float tv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (KIND != 2) {
+        const long e0 = 4 * i;
+        long row = e0 / D, rem = e0 - row * D;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          tv[q] = __ldg(t + row);
+          if (++rem == D) { rem = 0; ++row; }
+        }
+      }
+      float4 go;
+      loss_elem<KIND>(av.x, bv.x, x0v.x, xtv.x, tv[0], sigma0_sq, gk, s0, s1, s2, go.x);
+      loss_elem<KIND>(av.y, bv.y, x0v.y, xtv.y, tv[1], sigma0_sq, gk, s0, s1, s2, go.y);
+      loss_elem<KIND>(av.z, bv.z, x0v.z, xtv.z, tv[2], sigma0_sq, gk, s0, s1, s2, go.z);
+      loss_elem<KIND>(av.w, bv.w, x0v.w, xtv.w, tv[3], sigma0_sq, gk, s0, s1, s2, go.w);
+      if (grad) __stcs(g4 + i, go);
+      if (++cnt == 2) {   // flush the short fp32 runs (8 terms) into fp64
+        d0 += s0; d1 += s1; d2 += s2;
+        s0 = s1 = s2 = 0.f;
+        cnt = 0;
+      }
     }
-    if (++cnt == 8) {   // flush the short fp32 runs into fp64
-      d0 += s0; d1 += s1; d2 += s2;
-      s0 = s1 = s2 = 0.f;
-      cnt = 0;
+  } else {
+    int cnt = 0;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      const long row = i / D;
+      float go;
+      loss_elem<KIND>(a[i], x1[i], KIND == 1 ? x0[i] : 0.f, KIND == 1 ? xt[i] : 0.f, KIND != 2 ? __ldg(t + row) : 0.f,
+                      sigma0_sq, gk, s0, s1, s2, go);
+      if (grad) grad[i] = go;
+      if (++cnt == 8) {
+        d0 += s0; d1 += s1; d2 += s2;
+        s0 = s1 = s2 = 0.f;
+        cnt = 0;
+      }
     }
   }
   d0 += s0; d1 += s1; d2 += s2;
@@ -248,13 +291,20 @@ extern "C" int idff_loss(int32_t kind, const float* d_a, const float* d_x1, cons
   int dev = 0;
   IDFF_CUDA(cudaGetDevice(&dev));
   const long n = (long)B * (long)D;
-  int grid = stream_grid(n, 256, dev, 4);
+  auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool vec = (n % 4 == 0) && al16(d_a) && al16(d_x1) && al16(d_x0) && al16(d_xt) && al16(d_grad);
+  int grid = stream_grid(vec ? n / 4 : n, 256, dev, 8);
   if (grid > kLossMaxBlocks) grid = kLossMaxBlocks;
   LossScratch* sc = reinterpret_cast<LossScratch*>(d_scratch);
   cudaStream_t s = (cudaStream_t)stream;
-  if (kind == 0) k_loss<0><<<grid, 256, 0, s>>>(d_a, d_x1, d_x0, d_xt, d_t, sigma0_sq, grad_scale, d_loss, d_grad, n, (long)D, sc);
-  else if (kind == 1) k_loss<1><<<grid, 256, 0, s>>>(d_a, d_x1, d_x0, d_xt, d_t, sigma0_sq, grad_scale, d_loss, d_grad, n, (long)D, sc);
-  else k_loss<2><<<grid, 256, 0, s>>>(d_a, d_x1, d_x0, d_xt, d_t, sigma0_sq, grad_scale, d_loss, d_grad, n, (long)D, sc);
+#define IDFF_LOSS_LAUNCH(K, V) \
+  k_loss<K, V><<<grid, 256, 0, s>>>(d_a, d_x1, d_x0, d_xt, d_t, sigma0_sq, grad_scale, d_loss, d_grad, n, (long)D, sc)
+  if (vec) {
+    if (kind == 0) IDFF_LOSS_LAUNCH(0, 4); else if (kind == 1) IDFF_LOSS_LAUNCH(1, 4); else IDFF_LOSS_LAUNCH(2, 4);
+  } else {
+    if (kind == 0) IDFF_LOSS_LAUNCH(0, 1); else if (kind == 1) IDFF_LOSS_LAUNCH(1, 1); else IDFF_LOSS_LAUNCH(2, 1);
+  }
+#undef IDFF_LOSS_LAUNCH
   IDFF_CUDA(cudaGetLastError());
   count_launch();
   return IDFF_OK;

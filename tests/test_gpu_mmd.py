@@ -46,8 +46,8 @@ def test_mmd_ragged_shapes_and_row_split(cuda_device, N, Mm, D):
     cut_x, cut_y = N // 3, (2 * Mm) // 3
     s1 = M.mmd_partial_sums(xs, ys, sig, (0, cut_x), (0, cut_y)).cpu().numpy()
     s2 = M.mmd_partial_sums(xs, ys, sig, (cut_x, N), (cut_y, Mm)).cpu().numpy()
-    # (D <= 4 sums each row in a fixed order; the tiled kernel groups 4x4 pairs in fp32 before going to fp64)
-    np.testing.assert_allclose(s1 + s2, s, rtol=1e-12 if D <= 4 else 1e-6)
+    # (the full-set call uses the symmetric block shortcut, the row blocks do not: fp32 run grouping differs)
+    np.testing.assert_allclose(s1 + s2, s, rtol=1e-6)
 
 
 def test_mmd_large_sets(cuda_device):
