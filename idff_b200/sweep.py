@@ -1,0 +1,49 @@
+"""gamma sweeps by MMD -- the caller of the sampler hot path in the reference:
+
+    find_best_gammas_mmd               2D_examples/Autograd_example_order2.py:281-303   (8x8 tuples)
+    the 10^3-tuple order-3 sweep       2D_examples/Autograd_example_order3.py:288-314
+
+Every tuple is one fused-sampler launch plus one MMD launch, all queued on the current stream; the kernel sums stay
+on the device and are read back once at the end (the reference synchronises on `.item()` twice per field call)."""
+from __future__ import annotations
+
+import itertools
+
+import torch
+
+from . import fields, mmd, sampler
+
+
+def sweep_mmd(base_model, x0, true_samples, gamma_tuples, nfe, sigma=0.2, sigma_kernel=1.0, impl=0):
+    """MMD(true_samples, odeint(field(gammas), x0, linspace(0,1,nfe+1))[-1]) for every tuple -> list of floats."""
+    t_span = torch.linspace(0, 1, nfe + 1)
+    true_samples = torch.as_tensor(true_samples, dtype=torch.float32, device=x0.device)
+    N, M = true_samples.shape[0], x0.shape[0]
+    sums = []
+    out = torch.empty_like(x0)
+    for g in gamma_tuples:
+        if len(g) == 2:
+            model = fields.CustomNetModel(base_model, sigma=sigma, gamma1=g[0], gamma2=g[1])
+        elif len(g) == 3:
+            model = fields.CustomNetModelOrder3(base_model, sigma=sigma, gamma1=g[0], gamma2=g[1], gamma3=g[2])
+        else:
+            raise ValueError(f"gamma tuple must have 2 or 3 entries, got {g}")
+        model.impl = impl
+        sampler.sample_rk4(model, x0, t_span, out=out)
+        sums.append(mmd.mmd_partial_sums(true_samples, out, sigma_kernel))
+    vals = torch.stack([mmd.mmd_from_sums(s, N, M) for s in sums]).cpu().tolist()     # the only synchronisation
+    return vals
+
+
+def find_best_gammas_mmd(base_model, x0, true_samples, gamma_range=(0.0, 0.5, 1.0, 2.0), nfe=20, sigma=0.2,
+                         sigma_kernel=1.0, order=2, verbose=False):
+    """Same contract as the reference: -> (best_gamma_tuple, [((g1, g2[, g3]), mmd), ...]) in product order."""
+    tuples = list(itertools.product(gamma_range, repeat=order))
+    vals = sweep_mmd(base_model, x0, true_samples, tuples, nfe, sigma, sigma_kernel)
+    results = list(zip(tuples, vals))
+    best = min(results, key=lambda r: r[1])
+    if verbose:
+        for g, v in results:
+            print(f"gammas={g} -> MMD: {v:.5f}")
+        print(f"best: {best[0]} with MMD={best[1]:.5f}")
+    return best[0], results

@@ -1,0 +1,53 @@
+#include <cstdio>
+#include <cuda_runtime.h>
+__device__ __forceinline__ void ffma2(float2& d, float2 a, float2 b) {
+  unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d), aa = *reinterpret_cast<unsigned long long*>(&a), bb = *reinterpret_cast<unsigned long long*>(&b);
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(bb));
+  d = *reinterpret_cast<float2*>(&dd);
+}
+// ORDER 0: row outer (a reused), 1: col outer (b pair reused), 2: a as pair along rows (acc pairs along rows, b scalar broadcast)
+template <int RM, int CN2, int ORDER>
+__global__ void k(float* out, long long* cyc, int iters, float x) {
+  float2 acc[RM][CN2], a[RM], b[CN2];
+  for (int i = 0; i < RM; ++i) { a[i].x = x + i + threadIdx.x; a[i].y = a[i].x; }
+  for (int j = 0; j < CN2; ++j) { b[j].x = x * j - threadIdx.x; b[j].y = b[j].x + 1.f; }
+  for (int i = 0; i < RM; ++i) for (int j = 0; j < CN2; ++j) acc[i][j] = make_float2(0.f, 0.f);
+  __syncthreads();
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (ORDER == 0) {
+#pragma unroll
+        for (int i = 0; i < RM; ++i)
+#pragma unroll
+          for (int j = 0; j < CN2; ++j) ffma2(acc[i][j], a[i], b[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < CN2; ++j)
+#pragma unroll
+          for (int i = 0; i < RM; ++i) ffma2(acc[i][j], a[i], b[j]);
+      }
+      a[u % RM].x += 1e-9f; a[u % RM].y = a[u % RM].x; b[u % CN2].x -= 1e-9f;
+    }
+  }
+  long long t1 = clock64();
+  float s = 0; for (int i = 0; i < RM; ++i) for (int j = 0; j < CN2; ++j) s += acc[i][j].x + acc[i][j].y;
+  if (s == 12345.f) out[0] = s;
+  if (threadIdx.x == 0 && blockIdx.x == 0) cyc[0] = t1 - t0;
+}
+template <int RM, int CN2, int ORDER> void run(float* d, long long* dc) {
+  for (int nw : {8}) {
+    int iters = 4000;
+    k<RM, CN2, ORDER><<<148, 32 * nw>>>(d, dc, 100, 1.f); cudaDeviceSynchronize();
+    k<RM, CN2, ORDER><<<148, 32 * nw>>>(d, dc, iters, 1.f); cudaError_t e = cudaDeviceSynchronize();
+    long long c; cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost);
+    double fma = (double)iters * 8 * RM * CN2 * 2 * 32 * nw;
+    printf("FFMA2 tile %dx%d order %d warps/SM %2d: %.1f FMA/clk/SM %s\n", RM, 2 * CN2, ORDER, nw, fma / (double)c, cudaGetErrorString(e));
+  }
+}
+int main() {
+  float* d; cudaMalloc(&d, 4); long long* dc; cudaMalloc(&dc, 8);
+  run<8, 4, 0>(d, dc); run<8, 4, 1>(d, dc); run<8, 2, 0>(d, dc); run<8, 2, 1>(d, dc); run<16, 2, 0>(d, dc); run<16, 2, 1>(d, dc); run<4, 8, 0>(d, dc); run<4, 8, 1>(d, dc); run<8, 8, 0>(d, dc); run<8,8,1>(d,dc); run<2, 8, 1>(d, dc); run<16,4,1>(d,dc);
+  return 0;
+}

@@ -1,0 +1,74 @@
+"""-m gpu: the callers either side of the sampler: gamma sweep by MMD and the PolyALA
+autoregressive generator, against the oracle run the way the reference scripts run them."""
+import numpy as np
+import pytest
+import torch
+
+import idff_oracle as O
+from conftest import golden_layers, load_golden
+from gpu_common import assert_field_close, packed
+from idff_b200 import md, sweep
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gamma_sweep_matches_oracle_loop(cuda_device):
+    """find_best_gammas_mmd (Autograd_example_order2.py:281-303): same tuple order, same MMD values, same winner."""
+    layers, _ = golden_layers("checkerboard")
+    g = load_golden("mmd")
+    true_s = torch.tensor(g["true_checkerboard"])
+    x0 = torch.tensor(load_golden("traj2d")["x0"])
+    grid = [0.0, 0.2, 1.0]
+    best, results = sweep.find_best_gammas_mmd(packed("checkerboard", cuda_device), x0.to(cuda_device),
+                                               true_s.to(cuda_device), gamma_range=grid, nfe=2, sigma=0.2,
+                                               sigma_kernel=1.0, order=2)
+    assert [r[0] for r in results] == [(a, b) for a in grid for b in grid]
+    ref = []
+    for (g1, g2) in [r[0] for r in results]:
+        fin = O.odeint_rk4(O.Field2D(layers, 0.2, (g1, g2), 2), x0, torch.linspace(0, 1, 3))[-1]
+        ref.append(O.mmd_rbf_fp64_direct(true_s, fin, 1.0))
+    got = np.array([r[1] for r in results])
+    np.testing.assert_allclose(got, np.array(ref), rtol=2e-3, atol=2e-6)     # MMD of slightly drifted samples
+    assert best == results[int(np.argmin(got))][0]
+    assert abs(got[int(np.argmin(ref))] - got.min()) < 1e-5
+    # order-3 tuples go through the order-3 field
+    _, r3 = sweep.find_best_gammas_mmd(packed("checkerboard", cuda_device), x0.to(cuda_device), true_s.to(cuda_device),
+                                       gamma_range=[0.0, 0.2], nfe=2, order=3)
+    assert len(r3) == 8 and all(np.isfinite(v) for _, v in r3)
+    assert r3[0][1] == pytest.approx(results[0][1], abs=1e-6)              # (0,0,0) == (0,0)
+
+
+def test_md_autoregressive_generation_vs_oracle(cuda_device):
+    """generate_trajectories (MD_simulation.py:197-213) for 6 frames, 5 trajectories, injected Brownian increments."""
+    layers, emb = golden_layers("polyala")
+    K, D, T, NFE, dt = 5, 46, 6, 3, 0.3
+    gen = torch.Generator().manual_seed(0)
+    x_init = torch.randn(K, D, generator=gen)
+    ts = torch.linspace(0, 1, NFE)
+    grid = O.sde_step_grid(ts, dt)
+    h = torch.tensor(np.diff(np.array(grid, dtype=np.float32)))
+    ns = len(h)
+    noises = []
+    for _ in range(T):
+        ik = torch.randn(ns, K, D, generator=gen) * h.sqrt()[:, None, None]
+        ik0 = 0.5 * h[:, None, None] * ik + torch.randn(ns, K, D, generator=gen) * (h ** 1.5)[:, None, None] / np.sqrt(12.0)
+        noises.append((ik, ik0))
+    # oracle: the reference's loop, frame by frame
+    ref = []
+    x1 = x_init
+    for t_idx in range(T):
+        sde = O.FieldMD(layers, emb, D, sigma=0.5, init_ind=t_idx, dt=dt, gamma1=0.2, gamma2=5.0 / (1 + t_idx))
+        x1 = O.sdeint_srk(sde, x1, ts, dt, noises[t_idx][0], noises[t_idx][1])[-1]
+        ref.append(x1)
+    ref = torch.stack(ref).numpy()
+    got = md.generate_trajectories(packed("polyala", cuda_device), K, D, T, NFE, sigma=0.5, gamma1=0.2, gamma2=5.0, dt=dt,
+                                   device=cuda_device, x_init=x_init.to(cuda_device),
+                                   noise=lambda t_idx, n: (noises[t_idx][0].to(cuda_device), noises[t_idx][1].to(cuda_device)))
+    assert got.shape == (T, K, D)
+    for t_idx in range(T):
+        # each frame compounds the previous frames' round-off: 1e-4 of the frame's scale
+        assert_field_close(got[t_idx].cpu().numpy(), ref[t_idx], 1e-4, f"frame {t_idx}")
+    m = md.compute_metrics(got, torch.tensor(ref.mean(1)))
+    assert m["RMSE"] < 1e-2 * max(1.0, np.abs(ref).max()) and m["CC"] > 0.999
+    one = md.generate_onestep(packed("polyala", cuda_device), K, D, T, 3, 0.5, x_init.to(cuda_device), gamma1=0.2, gamma2=5.0)
+    assert one.shape == (3, K, D) and torch.isfinite(one).all()
