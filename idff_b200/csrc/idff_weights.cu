@@ -109,6 +109,10 @@ extern "C" int idff_weights_create(const float* const* h_W, const float* const* 
   const size_t o_fwt1 = fused_layout ? take((size_t)w * w) : 0, o_fwt2 = fused_layout ? take((size_t)w * w) : 0;
   const size_t o_fw2r = fused_layout ? take((size_t)w * w) : 0, o_fw1r = fused_layout ? take((size_t)w * w) : 0;
   const size_t o_w0n = take((size_t)w * (din > 1 ? din - 1 : 1));
+  const bool tc_layout = (w == 256);
+  const size_t tc_floats = (size_t)4 * 2 * 8 * 2 * 128 * 32;
+  off = (off + 255) & ~size_t(255);   // 1 KB alignment of the tile images
+  const size_t o_tc = tc_layout ? take(tc_floats) : 0;
   std::vector<float> blob(off, 0.0f);
 
   const float *W0 = h_W[0], *W1 = h_W[1], *W2 = h_W[2], *W3 = h_W[3];
@@ -154,6 +158,32 @@ extern "C" int idff_weights_create(const float* const* h_W, const float* const* 
         blob[o_fw1r + (size_t)r * w + p] = W1[(size_t)r * w + q];
       }
   }
+  if (tc_layout) {
+    auto rn_tf32 = [](float x) {
+      uint32_t u;
+      memcpy(&u, &x, 4);
+      u += 0x1000u;
+      u &= 0xFFFFE000u;
+      memcpy(&x, &u, 4);
+      return x;
+    };
+    for (int g = 0; g < 4; ++g)
+      for (int mt = 0; mt < 2; ++mt)
+        for (int kb = 0; kb < 8; ++kb) {
+          float* hi = &blob[o_tc + ((((size_t)g * 2 + mt) * 8 + kb) * 2 + 0) * 4096];
+          float* lo = hi + 4096;
+          for (int r = 0; r < 128; ++r)
+            for (int kk = 0; kk < 32; ++kk) {
+              const int row = mt * 128 + r, col = kb * 32 + kk;   // D[row][.] = sum_col A[row][col] * act[.][col]
+              const float v = g == 0 ? W1[(size_t)row * w + col] : g == 1 ? W2[(size_t)row * w + col]
+                            : g == 2 ? W2[(size_t)col * w + row] : W1[(size_t)col * w + row];
+              const float h = rn_tf32(v);
+              const size_t o = (size_t)r * 32 + ((((kk >> 2) ^ (r & 7)) << 2) | (kk & 3));
+              hi[o] = h;
+              lo[o] = rn_tf32(v - h);
+            }
+        }
+  }
   for (int n = 0; n < w; ++n)
     for (int d = 0; d < din - 1; ++d) blob[o_w0n + (size_t)n * (din - 1) + d] = W0[(size_t)n * din_total + d];
 
@@ -190,6 +220,7 @@ extern "C" int idff_weights_create(const float* const* h_W, const float* const* 
   v.fwt1 = fused_layout ? d_blob + o_fwt1 : nullptr; v.fwt2 = fused_layout ? d_blob + o_fwt2 : nullptr;
   v.fw2r = fused_layout ? d_blob + o_fw2r : nullptr; v.fw1r = fused_layout ? d_blob + o_fw1r : nullptr;
   v.w0n = d_blob + o_w0n;
+  v.tc_tiles = tc_layout ? d_blob + o_tc : nullptr;
   h->d_stash = nullptr; h->stash_bytes = 0;
   *out = h;
   return IDFF_OK;

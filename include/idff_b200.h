@@ -40,6 +40,7 @@ extern "C" {
 #define IDFF_IMPL_AUTO 0
 #define IDFF_IMPL_GENERIC 1 /* any width / dimension: one thread per hidden unit, weights from L2 */
 #define IDFF_IMPL_FUSED 2   /* persistent warp-tiled kernel, weights streamed by TMA bulk copies */
+#define IDFF_IMPL_TENSOR 3  /* tcgen05 3xTF32 kernel (width 256, dim 2, order <= 2): accumulators in TMEM */
 
 typedef struct idff_weights idff_weights_t; /* opaque: packed device copies of one 4-layer SELU MLP */
 
