@@ -169,7 +169,7 @@ def run_ours(args):
 
     pw = PackedWeights.from_npz(os.path.join(GOLDEN, "weights_checkerboard.npz"), device=dev)
     model = fields.CustomNetModel(pw, SIGMA, *GAMMAS)
-    model.impl = {"auto": 0, "generic": 1, "fused": 2}[args.kernel]
+    model.impl = {"auto": 0, "generic": 1, "fused": 2, "tensor": 3}[args.kernel]
     shard = launcher.ShardedSampler(model, 2, dev, base_seed=1000)
     x0 = shard.x0(n_total)
     ts = torch.linspace(0, 1, nfe + 1)
@@ -245,14 +245,27 @@ def run_ours(args):
         flops = P * flops_per_particle_solve(nfe)
         achieved = flops / (k_ms * 1e-3) / 1e12
         fma_peak = 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
-        roofline = {"bound": "fma", "kernel": "idff sampler (whole rk4 solve, one launch)", "achieved": achieved,
-                    "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved / fma_peak, "traffic": None,
-                    "peak_source": "fp32 FFMA issue peak 148 SM x 128 lanes x 2 x clocks.max.sm "
-                                   f"({peak_src} sm_max_mhz); MEASURED_PEAKS.json holds no fp32 figure. fp32 results at "
-                                   "1e-5 rule out single-pass TF32/BF16 tensor MMA",
-                    "algorithmic_flops_per_launch": flops, "kernel_ms": k_ms,
-                    "kernel_share_of_step": k_ms * args.steps / total_ms,
-                    "frac_of_bf16_tensor_peak": achieved / peaks.get("bf16_tflops", 1590.0)}
+        bf16 = peaks.get("bf16_tflops", 1590.0)
+        if args.kernel in ("auto", "tensor"):
+            # tcgen05 kind::tf32, three MMAs per product (3xTF32): algorithmic fp32 FLOP peak = tf32 dense / 3
+            tpeak = bf16 / 2.0 / 3.0
+            roofline = {"bound": "tensor", "kernel": "k_tc: tcgen05 3xTF32 sampler (whole rk4 solve, one launch)",
+                        "achieved": achieved, "peak": tpeak, "unit": "TFLOP/s", "frac": achieved / tpeak, "traffic": None,
+                        "peak_source": f"{peak_src} bf16 dense {bf16:.0f} TFLOP/s (MEASURED_PEAKS.json, burst) / 2 (tf32 rate) / 3 "
+                                       "(hi*hi + lo*hi + hi*lo passes); the kernel is bound by the shared-memory operand reads of "
+                                       "the M=128 x N=64 x K=8 MMAs (profiles/README.md), not by the tensor pipe",
+                        "algorithmic_flops_per_launch": flops, "kernel_ms": k_ms,
+                        "kernel_share_of_step": k_ms * args.steps / total_ms,
+                        "executed_tensor_tflops": 3.0 * achieved, "frac_of_bf16_tensor_peak": 3.0 * achieved / bf16,
+                        "frac_of_fp32_fma_peak": achieved / fma_peak}
+        else:
+            roofline = {"bound": "fma", "kernel": "idff sampler (whole rk4 solve, one launch)", "achieved": achieved,
+                        "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved / fma_peak, "traffic": None,
+                        "peak_source": "fp32 FFMA issue peak 148 SM x 128 lanes x 2 x clocks.max.sm "
+                                       f"({peak_src} sm_max_mhz); MEASURED_PEAKS.json holds no fp32 figure",
+                        "algorithmic_flops_per_launch": flops, "kernel_ms": k_ms,
+                        "kernel_share_of_step": k_ms * args.steps / total_ms,
+                        "frac_of_bf16_tensor_peak": achieved / bf16}
         aux = aux_measurements(dev, pw, model, peaks) if not args.no_aux else {}
         cpu_rate, cpu_per, cores, _ = cpu_reference_rate(args.cpu_particles, nfe, runs=5) if not args.no_cpu else (None, None, 0, [])
         line = {"metric": "idff_particle_steps_per_sec", "value": value, "unit": "particle-steps/s", "n_gpus": ws,
@@ -318,13 +331,17 @@ def aux_measurements(dev, pw, model, peaks):
     s = timeit(lambda: mmd_partial_sums(a, b, 1.0))
     aux["mmd_rbf"] = {"pairs_per_s": 3.0 * n * n / s, "shape": [n, n, 2], "bound": "mufu.ex2",
                       "frac_ex2_peak": 3.0 * n * n / s / (148 * 16 * peaks.get("sm_max_mhz", 1965.0) * 1e6)}
-    sweep = {}
+    from idff_b200 import fields
     xs = torch.randn(1 << 21, 2, device=dev, generator=g) / 1.5
-    for nfe in (2, 5, 10):
-        ts = torch.linspace(0, 1, nfe + 1)
-        s = timeit(lambda: sampler.sample_rk4(model, xs, ts), reps=2, warm=1)
-        sweep[str(nfe)] = xs.shape[0] * 4 * nfe / s
-    aux["sampler_nfe_sweep_particle_steps_per_s"] = sweep
+    for name, impl in (("fma_ffma2", 2), ("tensor_3xtf32", 3)):
+        m2 = fields.CustomNetModel(pw, SIGMA, *GAMMAS)
+        m2.impl = impl
+        sweep = {}
+        for nfe in (2, 5, 10):
+            ts = torch.linspace(0, 1, nfe + 1)
+            s = timeit(lambda: sampler.sample_rk4(m2, xs, ts), reps=2, warm=1)
+            sweep[str(nfe)] = xs.shape[0] * 4 * nfe / s
+        aux[f"sampler_{name}_nfe_sweep_particle_steps_per_s"] = sweep
     return aux
 
 
@@ -336,7 +353,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--particles", type=int, default=1 << 24, help="particles per GPU")
     ap.add_argument("--nfe", type=int, default=2)
-    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fused"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fused", "tensor"])
     ap.add_argument("--cpu-particles", type=int, default=65536)
     ap.add_argument("--no-aux", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -38,6 +38,7 @@ SIGNATURES = {
                                       C.POINTER(_vp)]),
     "idff_weights_destroy": (C.c_int, [_vp]),
     "idff_stage_scalars": (C.c_int, [_PP, _f32, _vp]),
+    "idff_debug_tensor_stamps": (C.c_int, [_vp]),
     "idff_mlp_forward": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp]),
     "idff_field_eval": (C.c_int, [_vp, _PP, _f32, _vp, _vp, _vp, _i64, _vp]),
     "idff_sample_rk4": (C.c_int, [_vp, _PP, _vp, _vp, _i32, _vp, _vp, _i64, _vp]),

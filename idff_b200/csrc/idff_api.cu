@@ -32,6 +32,8 @@ int tensor_field_eval(const idff_weights_t* w, const idff_field_params_t* p, flo
 int tensor_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, const float* d_x0, const Stage* stages,
                       const float* dts, int n_iv, float* d_out_final, float* d_out_traj, int64_t N, void* stream);
 
+int tensor_debug_stamps(long long* h_out, int n);
+
 struct DeviceGuard {
   int prev = -1;
   bool ok = true;
@@ -58,6 +60,11 @@ static std::vector<float> sde_grid(const float* ts, int n_ts, float dt) {
 }  // namespace idff
 
 using namespace idff;
+
+extern "C" int idff_debug_tensor_stamps(int64_t* h_out32) {
+  IDFF_CHECK_ARG(h_out32, "idff_debug_tensor_stamps: null pointer");
+  return tensor_debug_stamps(reinterpret_cast<long long*>(h_out32), 32);
+}
 
 extern "C" int idff_stage_scalars(const idff_field_params_t* p, float t, float* h_out8) {
   IDFF_CHECK_ARG(p && h_out8, "idff_stage_scalars: null pointer");
@@ -86,7 +93,8 @@ extern "C" int idff_field_eval(const idff_weights_t* w, const idff_field_params_
   IDFF_CHECK_ARG(N > 0 && d_x && d_out, "idff_field_eval: null pointer or negative N");
   IDFF_CHECK_ARG(p->variant != IDFF_FIELD_CFM || t == 0.0f || d_x0, "idff_field_eval: the CFM field needs x0 (captured at t == 0) when t != 0");
   DeviceGuard g(w->device);
-  if (p->impl == IDFF_IMPL_TENSOR) return tensor_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
+  if (p->impl == IDFF_IMPL_TENSOR || (p->impl == IDFF_IMPL_AUTO && tensor_supports(w, p) && N >= 4096))
+    return tensor_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
   if (p->impl == IDFF_IMPL_FUSED || (p->impl == IDFF_IMPL_AUTO && fused_supports(w, p))) {
     if (!fused_supports(w, p)) {
       set_error("idff_field_eval: the fused kernel does not support this shape/variant");
@@ -132,7 +140,7 @@ extern "C" int idff_sample_rk4(const idff_weights_t* w, const idff_field_params_
     make_stage(*p, tc, &st[4 * i + 2]);
     make_stage(*p, t1, &st[4 * i + 3]);
   }
-  if (p->impl == IDFF_IMPL_TENSOR)
+  if (p->impl == IDFF_IMPL_TENSOR || (p->impl == IDFF_IMPL_AUTO && tensor_supports(w, p)))
     return tensor_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream);
   const bool want_fused = p->impl == IDFF_IMPL_FUSED || (p->impl == IDFF_IMPL_AUTO && fused_supports(w, p));
   if (want_fused) {

@@ -16,6 +16,8 @@
 // unit n: the SELU jet / adjoint algebra is thread-local, per-unit constants are scalars.  Reductions over units
 // (x1hat = W3 a3, grad_x = W0^T P1) are a shuffle reduce-scatter.  Warp roles: 4 epilogue warps, 1 TMA producer, 1 MMA
 // issuer (single elected thread); mbarriers between them, named barriers among the epilogue warps.
+#include <cstdlib>
+
 #include "idff_common.cuh"
 
 namespace idff {
@@ -26,13 +28,15 @@ namespace tc {
 constexpr int W = 256;
 constexpr int NP = 32;                   // particles per CTA
 constexpr int NCOL = 64;                 // MMA N: 2 jets x 32 particles
-constexpr int NSTAGE = 2;                // weight ring depth
+constexpr int NSTAGE = 3;                // weight ring depth (bytes in flight hide the ~1000-cycle L2->SM latency)
 constexpr int TILE_BYTES = 32768;        // hi (16 KB) + lo (16 KB) image of one [128 x 32] weight tile
 constexpr int ACT_BYTES = NCOL * W * 4;  // one copy (hi or lo) of the B operand: 8 k-blocks x [64 x 128 B]
-constexpr int NE = 256;                  // epilogue threads: warps 0..3 own m-tile 0, warps 4..7 m-tile 1 (lane quarter = warp % 4)
-constexpr int NTHREADS = 320;            // + producer warp 8 + MMA warp 9
+constexpr int NE = 512;                  // epilogue threads: warp w -> lane quarter w%4, m-tile (w/4)%2, particle half w/8
+constexpr int NEW = NE / 32;             // epilogue warps
+constexpr int NTHREADS = NE + 64;        // + producer warp 16 + MMA warp 17
 constexpr int TMEM_COLS = 512;
-constexpr int COL_MAIN = 0, COL_CORR = 64, COL_MT = 128, COL_STASH = 256;   // + mt * COL_MT / + mt * 64
+// per m-tile: two main accumulators (even / odd k-blocks: halves the number of truncating accumulation steps) + corr
+constexpr int COL_MAIN = 0, COL_MAIN2 = 64, COL_CORR = 128, COL_MT = 192, COL_STASH = 384;   // + mt * COL_MT / + mt * 64
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
@@ -58,17 +62,37 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
   }
 }
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* b, uint32_t parity) {
-  while (!mbar_try_wait(b, parity)) __nanosleep(64);
+  while (!mbar_try_wait(b, parity)) __nanosleep(256);
 }
 __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)),
                "l"(src), "r"(bytes), "r"(s32(bar))
                : "memory");
 }
+// each CTA of a pair loads one half (hi or lo) of every weight tile and multicasts it to both CTAs: halves the L2 reads
+__device__ __forceinline__ void tma_load_1d_mc(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(s32(dst)),
+      "l"(src), "r"(bytes), "r"(s32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(s32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void ebar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // epilogue warps only
+__device__ __forceinline__ void ebar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // epilogue warps only
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (8-row groups 1024 B apart)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -103,6 +127,16 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       IDFF_I8(v, 8), IDFF_I8(v, 16), IDFF_I8(v, 24), "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : IDFF_R8(v, 0), IDFF_R8(v, 8)
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};" ::IDFF_I8(v, 0),
+               IDFF_I8(v, 8), "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -111,6 +145,9 @@ __device__ __forceinline__ float rn_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
 }
+
+// phase timestamps (clock64) of CTA 0, first tile, evaluation 1 (an interior one): diagnostic only
+__device__ long long g_tc_stamps[32];
 
 struct TParams {
   NetView net;
@@ -122,16 +159,16 @@ struct TParams {
   float* traj;
 };
 
-struct Smem {   // byte offsets from the 1024-aligned dynamic base
+struct Smem {   // byte offsets from the dynamic base, which must be 1024-byte aligned (checked at kernel entry)
   static constexpr int act_hi = 0;
   static constexpr int act_lo = ACT_BYTES;
   static constexpr int ring = 2 * ACT_BYTES;
-  static constexpr int misc = ring + NSTAGE * TILE_BYTES;   // floats from here
-  // misc floats: w0 [256][4] (w0x0, w0x1, w0t, b0), vecs b1,b2,u3,zd1 [4][256], w3 [2][256], red [2][8][64], state [6][64]
-  static constexpr int f_w0 = 0, f_vec = 1024, f_w3 = 2048, f_red = 2560, f_state = 3584, f_end = 3584 + 12 * 32;
+  static constexpr int misc = ring + NSTAGE * TILE_BYTES;   // floats: red [16 warps][32], xs [64]
+  static constexpr int f_red = 0, f_xs = NEW * 32, f_end = NEW * 32 + 64;
   static constexpr int bars = misc + f_end * 4;
   static constexpr int total = bars + 128;
 };
+static_assert(Smem::total <= 232448, "shared memory budget");
 
 // element (col, k) of the B operand: byte offset inside one copy
 __device__ __forceinline__ uint32_t act_off(int col, int k) {
@@ -152,11 +189,24 @@ __device__ __forceinline__ void warp_reduce_scatter64(float (&v)[64], int lane) 
   }
 }
 
+// same for 32 partial sums: lane L ends with the total of v[L]
+__device__ __forceinline__ void warp_reduce_scatter32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16, cnt = 16; off >= 1; off >>= 1, cnt >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < cnt; ++i) {
+      const float send = up ? v[i] : v[i + cnt];
+      const float keep = up ? v[i + cnt] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, const __grid_constant__ Stage one) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // SWIZZLE_128B operands need a 1024-byte aligned base: align by hand (the launch reserves the slack)
-  unsigned char* smem = smem_raw + ((1024u - (s32(smem_raw) & 1023u)) & 1023u);
+  extern __shared__ __align__(1024) unsigned char smem[];
+  if ((s32(smem) & 1023u) != 0u) return;   // SWIZZLE_128B operands need a 1024-byte aligned base (host checks the result)
   float* misc = reinterpret_cast<float*>(smem + Smem::misc);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
   uint64_t* full = bars;                 // [NSTAGE]  TMA -> MMA
@@ -169,76 +219,71 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], 2);   // both CTAs of the pair must have consumed a slot before either half is overwritten
     }
     mbar_init(acc_full, 1);
     mbar_init(b_ready, NE);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {
+  if (warp == NEW + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  // resident small operands
-  for (int n = tid; n < W; n += NTHREADS) {
-    misc[Smem::f_w0 + 4 * n + 0] = P.net.wt0[0 * W + n];
-    misc[Smem::f_w0 + 4 * n + 1] = P.net.wt0[1 * W + n];
-    misc[Smem::f_w0 + 4 * n + 2] = P.net.wt0[2 * W + n];
-    misc[Smem::f_w0 + 4 * n + 3] = P.net.b0[(size_t)P.tidx * W + n];
-    misc[Smem::f_vec + 0 * W + n] = P.net.b1[n];
-    misc[Smem::f_vec + 1 * W + n] = P.net.b2[n];
-    misc[Smem::f_vec + 2 * W + n] = P.net.u3[n];
-    misc[Smem::f_vec + 3 * W + n] = P.net.zd1[n];
-    misc[Smem::f_w3 + 0 * W + n] = P.net.w3[0 * W + n];
-    misc[Smem::f_w3 + 1 * W + n] = P.net.w3[1 * W + n];
   }
   // jet-1 columns are read by the MMAs of boundary evaluations too: start from finite values
   for (int i = tid; i < 2 * ACT_BYTES / 4; i += NTHREADS) reinterpret_cast<float*>(smem)[i] = 0.0f;
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();   // barrier inits visible to the peer before any remote complete_tx / commit arrives
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const uint32_t crank = cluster_ctarank();
+  // both CTAs of a pair walk the same number of tiles (the ring couples them); surplus tiles are all-padding
+  const long n_tiles = (P.N + NP - 1) / NP;
+  const long n_iter = (n_tiles + gridDim.x - 1) / gridDim.x;
 
   const int n_eval = P.mode == 0 ? 1 : 4 * rk.n_iv;
   auto stage_of = [&](int e) -> const Stage& { return P.mode == 0 ? one : rk.st[e]; };
   auto heavy_of = [&](const Stage& st) { return st.kind == 2 && P.reverse; };
 
-  if (warp == 8) {
+  if (warp == NEW) {
     // ===== TMA producer: weight tile images of every layer pass, in consumption order
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long tile = blockIdx.x; tile * NP < P.N; tile += gridDim.x)
+      for (long it = 0; it < n_iter; ++it)
         for (int e = 0; e < n_eval; ++e) {
           const int ng = heavy_of(stage_of(e)) ? 4 : 2;
           for (int g = 0; g < ng; ++g)
             for (int t = 0; t < 16; ++t) {   // (m-tile, k-block) pairs of gemm g are contiguous
               mbar_wait_sleep(&empty[stage], phase ^ 1u);
               mbar_arrive_expect_tx(&full[stage], TILE_BYTES);
-              tma_load_1d(smem + Smem::ring + stage * TILE_BYTES,
-                          reinterpret_cast<const unsigned char*>(P.net.tc_tiles) + ((size_t)g * 16 + t) * TILE_BYTES, TILE_BYTES,
-                          &full[stage]);
+              tma_load_1d_mc(smem + Smem::ring + stage * TILE_BYTES + crank * (TILE_BYTES / 2),
+                             reinterpret_cast<const unsigned char*>(P.net.tc_tiles) + ((size_t)g * 16 + t) * TILE_BYTES +
+                                 crank * (TILE_BYTES / 2),
+                             TILE_BYTES / 2, &full[stage], (uint16_t)3);
               if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
             }
         }
     }
-  } else if (warp == 9) {
+  } else if (warp == NEW + 1) {
     // ===== MMA issuer (one thread)
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t bhi = s32(smem + Smem::act_hi), blo = s32(smem + Smem::act_lo);
       int stage = 0;
       uint32_t phase = 0, bphase = 0;
-      for (long tile = blockIdx.x; tile * NP < P.N; tile += gridDim.x)
+      for (long it = 0; it < n_iter; ++it)
         for (int e = 0; e < n_eval; ++e) {
           const int ng = heavy_of(stage_of(e)) ? 4 : 2;
           for (int g = 0; g < ng; ++g) {
             mbar_wait(b_ready, bphase);
             bphase ^= 1u;
             tc_fence_after();
+            const bool mstamp = blockIdx.x == 0 && it == 0 && e == 1;
+            if (mstamp) g_tc_stamps[16 + 2 * g] = clock64();
             for (int mt = 0; mt < 2; ++mt) {
-              const uint32_t d_main = tmem + mt * COL_MT + COL_MAIN, d_corr = tmem + mt * COL_MT + COL_CORR;
+              const uint32_t d_main0 = tmem + mt * COL_MT + COL_MAIN, d_corr = tmem + mt * COL_MT + COL_CORR;
               for (int kb = 0; kb < 8; ++kb) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
@@ -247,42 +292,47 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
                 for (int ks = 0; ks < 4; ++ks) {
                   const uint64_t a_hi = make_desc(whi + ks * 32), a_lo = make_desc(wlo + ks * 32);
                   const uint64_t b_hi = make_desc(bhi + kb * (NCOL * 128) + ks * 32), b_lo = make_desc(blo + kb * (NCOL * 128) + ks * 32);
-                  mma_tf32(d_main, a_hi, b_hi, idesc, (kb | ks) != 0);
+                  mma_tf32(d_main0 + (kb & 1) * (COL_MAIN2 - COL_MAIN), a_hi, b_hi, idesc, ((kb >> 1) | ks) != 0);
                   mma_tf32(d_corr, a_lo, b_hi, idesc, (kb | ks) != 0);
                   mma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
                 }
-                mma_commit(&empty[stage]);   // the ring slot is free once these MMAs have read it
+                mma_commit_mc(&empty[stage], (uint16_t)3);   // frees the slot in both CTAs once these MMAs have read it
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
               }
             }
             mma_commit(acc_full);
+            if (mstamp) g_tc_stamps[17 + 2 * g] = clock64();
           }
         }
     }
   } else {
-    // ===== epilogue warps: warp w owns m-tile w / 4 and TMEM lanes 32 (w % 4) ..: thread <-> one hidden unit n
-    const int mt = warp >> 2;
+    // ===== epilogue warps: thread <-> (hidden unit n, half h of the CTA's particles)
+    const int mt = (warp >> 2) & 1, h = warp >> 3;
     const int n = mt * 128 + (warp & 3) * 32 + lane;
-    float* red = misc + Smem::f_red;       // [2][8 warps][64]
-    float* stt = misc + Smem::f_state;     // [6][64]: y, k1, k2, k3, xs, x0c
-    float *sy = stt, *sk1 = stt + 64, *sk2 = stt + 128, *sk3 = stt + 192, *sxs = stt + 256, *sx0 = stt + 320;
-    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + mt * COL_MT;
-    const uint32_t stash_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + COL_STASH + mt * 64;
+    constexpr int HP = NP / 2;             // particles per thread
+    const int p0 = h * HP;
+    float* red = misc + Smem::f_red;       // [16 warps][32]
+    float* sxs = misc + Smem::f_xs;        // stage input of the 32 particles, [p][2]
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + mt * COL_MT + p0;
+    const uint32_t stash_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + COL_STASH + mt * 64 + p0;
     uint32_t aphase = 0;
     const float third = (float)(1.0 / 3.0);
-    const float wx0 = misc[Smem::f_w0 + 4 * n + 0], wx1 = misc[Smem::f_w0 + 4 * n + 1], wtt = misc[Smem::f_w0 + 4 * n + 2],
-                bb0 = misc[Smem::f_w0 + 4 * n + 3], bb1 = misc[Smem::f_vec + 0 * W + n], bb2 = misc[Smem::f_vec + 1 * W + n],
-                uu3 = misc[Smem::f_vec + 2 * W + n], zz1 = misc[Smem::f_vec + 3 * W + n], w30 = misc[Smem::f_w3 + 0 * W + n],
-                w31 = misc[Smem::f_w3 + 1 * W + n];
+    const float wx0 = __ldg(P.net.wt0 + 0 * W + n), wx1 = __ldg(P.net.wt0 + 1 * W + n), wtt = __ldg(P.net.wt0 + 2 * W + n),
+                bb0 = __ldg(P.net.b0 + (size_t)P.tidx * W + n), bb1 = __ldg(P.net.b1 + n), bb2 = __ldg(P.net.b2 + n),
+                uu3 = __ldg(P.net.u3 + n), zz1 = __ldg(P.net.zd1 + n), w30 = __ldg(P.net.w3 + 0 * W + n),
+                w31 = __ldg(P.net.w3 + 1 * W + n);
+    // integrator state of particle `lane`, held by warp 0 (y, k1, k2, k3, x0 of the CFM field: 2 components each)
+    float sy[2] = {0.f, 0.f}, sk1[2] = {0.f, 0.f}, sk2[2] = {0.f, 0.f}, sk3[2] = {0.f, 0.f}, sx0[2] = {0.f, 0.f};
+    float pr_tot[2] = {0.f, 0.f};
     // this unit's k position inside the B operand: k-block, 16-byte chunk, word
     unsigned char* ahi = smem + Smem::act_hi + (n >> 5) * (NCOL * 128) + ((n & 3) << 2);
     unsigned char* alo = ahi + ACT_BYTES;
     const int kchunk = (n >> 2) & 7;
     auto put = [&](int col, float v) {
       const uint32_t o = (uint32_t)(col * 128 + ((kchunk ^ (col & 7)) << 4));
-      const float h = rn_tf32(v);
-      *reinterpret_cast<float*>(ahi + o) = h;
-      *reinterpret_cast<float*>(alo + o) = v - h;
+      const float hv = rn_tf32(v);
+      *reinterpret_cast<float*>(ahi + o) = hv;
+      *reinterpret_cast<float*>(alo + o) = v - hv;
     };
     // after writing the B operand: make it visible to the tensor core and hand over to the MMA thread
     auto publish = [&]() {
@@ -290,36 +340,42 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
       tc_fence_before();
       mbar_arrive(b_ready);
     };
-    // z = main + corr, columns [c0, c0+32) of this thread's lane
-    auto load_acc = [&](int c0, float (&z)[32]) {
-      uint32_t m[32], c[32];
-      tmem_ld32(lane_base + COL_MAIN + c0, m);
-      tmem_ld32(lane_base + COL_CORR + c0, c);
+    // z = main + corr of this thread's unit: jet j, particles p0 .. p0+15
+    auto load_acc = [&](int j, float (&z)[HP]) {
+      uint32_t m[HP], m2[HP], c[HP];
+      tmem_ld16(lane_base + COL_MAIN + j * NP, m);
+      tmem_ld16(lane_base + COL_MAIN2 + j * NP, m2);
+      tmem_ld16(lane_base + COL_CORR + j * NP, c);
       tmem_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) z[i] = __uint_as_float(m[i]) + __uint_as_float(c[i]);
+      for (int i = 0; i < HP; ++i) z[i] = (__uint_as_float(m[i]) + __uint_as_float(m2[i])) + __uint_as_float(c[i]);
     };
 
-    for (long tile = blockIdx.x; tile * NP < P.N; tile += gridDim.x) {
-      const long base = tile * NP;
-      if (tid < 64) {
-        const int p = tid >> 1, d = tid & 1;
-        const long row = base + p;
-        const float v = row < P.N ? P.x_in[row * 2 + d] : 0.0f;
-        sy[tid] = v;
-        sxs[tid] = v;
-        if (P.mode == 0 && P.variant == IDFF_FIELD_CFM && P.x0_cfm) sx0[tid] = row < P.N ? P.x0_cfm[row * 2 + d] : 0.0f;
+    for (long it = 0; it < n_iter; ++it) {
+      const long base = (blockIdx.x + it * gridDim.x) * NP;   // may lie beyond N: an all-padding tile
+      if (warp == 0) {
+        const long row = base + lane;
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          const float v = row < P.N ? P.x_in[row * 2 + d] : 0.0f;
+          sy[d] = v;
+          sxs[2 * lane + d] = v;
+          if (P.mode == 0 && P.variant == IDFF_FIELD_CFM && P.x0_cfm) sx0[d] = row < P.N ? P.x0_cfm[row * 2 + d] : 0.0f;
+        }
       }
       ebar();
 #pragma unroll 1
       for (int ev = 0; ev < n_eval; ++ev) {
         const Stage& st = stage_of(ev);
         const bool heavy = heavy_of(st);
+        const bool stamp = blockIdx.x == 0 && it == 0 && ev == 1 && tid == 0;
+        if (stamp) g_tc_stamps[0] = clock64();
         // ---- layer 1 (K = 3, computed directly): a1 and, for interior evaluations, a1' = s'(z1) * (W0 d)
         {
           const float zb = fmaf(wtt, st.t, bb0);
-#pragma unroll 8
-          for (int p = 0; p < NP; ++p) {
+#pragma unroll
+          for (int i = 0; i < HP; ++i) {
+            const int p = p0 + i;
             const float z = fmaf(wx1, sxs[2 * p + 1], fmaf(wx0, sxs[2 * p], zb));
             float code, s1, E;
             const float a = selu_fwd(z, code);
@@ -329,164 +385,195 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
           }
         }
         publish();
-        float part[64];
+        if (stamp) g_tc_stamps[1] = clock64();
+        float part[32];
         // ---- gemm 0: layer 2 forward
-        mbar_wait(acc_full, aphase); aphase ^= 1u; tc_fence_after();
+        mbar_wait_sleep(acc_full, aphase); aphase ^= 1u; tc_fence_after();
+        if (stamp) g_tc_stamps[2] = clock64();
         {
-          float z[32], zd[32];
+          float z[HP], zd[HP];
           load_acc(0, z);
-          if (heavy) load_acc(32, zd);
-          uint32_t st_code[32];
+          if (heavy) load_acc(1, zd);
+          uint32_t st_code[HP];
 #pragma unroll
-          for (int p = 0; p < NP; ++p) {
+          for (int i = 0; i < HP; ++i) {
             float code, s1, E;
-            const float a = selu_fwd(z[p] + bb1, code);
+            const float a = selu_fwd(z[i] + bb1, code);
             selu_decode(code, s1, E);
-            st_code[p] = __float_as_uint(code);
-            put(p, a);
-            if (heavy) put(NP + p, s1 * zd[p]);
+            st_code[i] = __float_as_uint(code);
+            put(p0 + i, a);
+            if (heavy) put(NP + p0 + i, s1 * zd[i]);
           }
           if (heavy) {
-            uint32_t st_zd[32];
+            uint32_t st_zd[HP];
 #pragma unroll
-            for (int p = 0; p < NP; ++p) st_zd[p] = __float_as_uint(zd[p]);
-            tmem_st32(stash_base, st_code);
-            tmem_st32(stash_base + 32, st_zd);
+            for (int i = 0; i < HP; ++i) st_zd[i] = __float_as_uint(zd[i]);
+            tmem_st16(stash_base, st_code);
+            tmem_st16(stash_base + NP, st_zd);
             tmem_wait_st();
           }
         }
         publish();
+        if (stamp) g_tc_stamps[3] = clock64();
         // ---- gemm 1: layer 3 forward; x1hat partials; adjoint seeds
-        mbar_wait(acc_full, aphase); aphase ^= 1u; tc_fence_after();
+        mbar_wait_sleep(acc_full, aphase); aphase ^= 1u; tc_fence_after();
+        if (stamp) g_tc_stamps[4] = clock64();
         {
-          float z[32], zd[32];
+          float z[HP], zd[HP];
           load_acc(0, z);
-          if (heavy) load_acc(32, zd);
+          if (heavy) load_acc(1, zd);
           const float A0 = st.c[0] * uu3, A1 = st.c[1] * uu3;
 #pragma unroll
-          for (int p = 0; p < NP; ++p) {
+          for (int i = 0; i < HP; ++i) {
             float code, s1, E;
-            const float a = selu_fwd(z[p] + bb2, code);
+            const float a = selu_fwd(z[i] + bb2, code);
             selu_decode(code, s1, E);
-            part[2 * p] = a * w30;
-            part[2 * p + 1] = a * w31;
+            part[2 * i] = a * w30;
+            part[2 * i + 1] = a * w31;
             if (heavy) {
-              put(p, fmaf(A1 * E, zd[p], A0 * s1));   // adjoint of z3
-              put(NP + p, A1 * s1);                   // adjoint of z3'
+              put(p0 + i, fmaf(A1 * E, zd[i], A0 * s1));   // adjoint of z3
+              put(NP + p0 + i, A1 * s1);                   // adjoint of z3'
             }
           }
         }
         if (heavy) publish();
-        warp_reduce_scatter64(part, lane);
-        red[warp * 64 + 2 * lane] = part[0];
-        red[warp * 64 + 2 * lane + 1] = part[1];
+        if (stamp) g_tc_stamps[5] = clock64();
+        warp_reduce_scatter32(part, lane);
+        red[warp * 32 + lane] = part[0];
+        ebar();
+        if (warp == 0) {   // x1hat of particle `lane`: fixed summation order over the 8 warps of its half
+          const int hh = lane >> 4, q = (lane & 15) * 2;
+#pragma unroll
+          for (int d = 0; d < 2; ++d) {
+            float acc = __ldg(P.net.b3 + d);
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) acc += red[(hh * 8 + w8) * 32 + q + d];
+            pr_tot[d] = acc;
+          }
+        }
+        if (stamp) g_tc_stamps[6] = clock64();
+        float gg[2] = {0.f, 0.f};
         if (heavy) {
           // ---- gemm 2: reverse, layer 3 -> 2
-          mbar_wait(acc_full, aphase); aphase ^= 1u; tc_fence_after();
+          mbar_wait_sleep(acc_full, aphase); aphase ^= 1u; tc_fence_after();
+          if (stamp) g_tc_stamps[7] = clock64();
           {
-            float a0[32], a1[32];
+            float a0[HP], a1[HP];
             load_acc(0, a0);
-            load_acc(32, a1);
-            uint32_t cd[32], zdu[32];
-            tmem_ld32(stash_base, cd);
-            tmem_ld32(stash_base + 32, zdu);
+            load_acc(1, a1);
+            uint32_t cd[HP], zdu[HP];
+            tmem_ld16(stash_base, cd);
+            tmem_ld16(stash_base + NP, zdu);
             tmem_wait_ld();
 #pragma unroll
-            for (int p = 0; p < NP; ++p) {
+            for (int i = 0; i < HP; ++i) {
               float s1, E;
-              selu_decode(__uint_as_float(cd[p]), s1, E);
-              put(p, fmaf(a1[p] * E, __uint_as_float(zdu[p]), a0[p] * s1));
-              put(NP + p, a1[p] * s1);
+              selu_decode(__uint_as_float(cd[i]), s1, E);
+              put(p0 + i, fmaf(a1[i] * E, __uint_as_float(zdu[i]), a0[i] * s1));
+              put(NP + p0 + i, a1[i] * s1);
             }
           }
           publish();
+          if (stamp) g_tc_stamps[8] = clock64();
           // ---- gemm 3: reverse, layer 2 -> 1 -> x
-          mbar_wait(acc_full, aphase); aphase ^= 1u; tc_fence_after();
+          mbar_wait_sleep(acc_full, aphase); aphase ^= 1u; tc_fence_after();
+          if (stamp) g_tc_stamps[9] = clock64();
           {
-            float a0[32], a1[32];
+            float a0[HP], a1[HP];
             load_acc(0, a0);
-            load_acc(32, a1);
+            load_acc(1, a1);
             const float zb = fmaf(wtt, st.t, bb0);
 #pragma unroll
-            for (int p = 0; p < NP; ++p) {
+            for (int i = 0; i < HP; ++i) {
+              const int p = p0 + i;
               const float z = fmaf(wx1, sxs[2 * p + 1], fmaf(wx0, sxs[2 * p], zb));
               float code, s1, E;
               (void)selu_fwd(z, code);
               selu_decode(code, s1, E);
-              const float P1 = fmaf(a1[p] * E, zz1, a0[p] * s1);
-              part[2 * p] = P1 * wx0;
-              part[2 * p + 1] = P1 * wx1;
+              const float P1 = fmaf(a1[i] * E, zz1, a0[i] * s1);
+              part[2 * i] = P1 * wx0;
+              part[2 * i + 1] = P1 * wx1;
             }
           }
-          warp_reduce_scatter64(part, lane);
-          red[512 + warp * 64 + 2 * lane] = part[0];
-          red[512 + warp * 64 + 2 * lane + 1] = part[1];
+          warp_reduce_scatter32(part, lane);
+          red[warp * 32 + lane] = part[0];
+          if (stamp) g_tc_stamps[10] = clock64();
+          ebar();
+          if (warp == 0) {
+            const int hh = lane >> 4, q = (lane & 15) * 2;
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+              float acc = 0.0f;
+#pragma unroll
+              for (int w8 = 0; w8 < 8; ++w8) acc += red[(hh * 8 + w8) * 32 + q + d];
+              gg[d] = acc;
+            }
+          }
         }
-        ebar();
+        if (stamp) g_tc_stamps[11] = clock64();
         // ---- combine + integrator stage update: warp 0, lane = particle
         if (warp == 0) {
-          const int p = lane;
-          const long row = base + p;
+          const long row = base + lane;
 #pragma unroll
           for (int d = 0; d < 2; ++d) {
-            const int o = 2 * p + d;
-            float pr = __ldg(P.net.b3 + d), gg = 0.0f;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) pr += red[q * 64 + o];
-            if (heavy) {
-#pragma unroll
-              for (int q = 0; q < 8; ++q) gg += red[512 + q * 64 + o];
-            }
-            const float x = sxs[o];
+            const float pr = pr_tot[d];
+            const float x = sxs[2 * lane + d];
             float f;
             if (P.variant == IDFF_FIELD_CFM) {
-              if (st.kind == 0) sx0[o] = x;
-              f = __fsub_rn(pr, sx0[o]);
+              if (st.kind == 0) sx0[d] = x;
+              f = __fsub_rn(pr, sx0[d]);
             } else {
               const float diff = __fsub_rn(pr, x);
               if (st.kind == 0) f = diff;
               else if (st.kind == 1) f = __fdiv_rn(diff, st.end_div);
               else {
                 f = __fdiv_rn(__fmul_rn(st.a, diff), st.den);
-                if (heavy) f = __fadd_rn(f, gg);
+                if (heavy) f = __fadd_rn(f, gg[d]);
               }
             }
             if (P.mode == 0) {
               if (row < P.N) P.out[row * 2 + d] = f;
             } else {
               const int iv = ev >> 2, sg = ev & 3;
-              const float dt = rk.dt[iv], y = sy[o];
+              const float dt = rk.dt[iv], y = sy[d];
               float xn;
               if (sg == 0) {
-                sk1[o] = f;
+                sk1[d] = f;
                 xn = __fadd_rn(y, __fmul_rn(__fmul_rn(dt, f), third));
               } else if (sg == 1) {
-                sk2[o] = f;
-                xn = __fadd_rn(y, __fmul_rn(dt, __fsub_rn(f, __fmul_rn(sk1[o], third))));
+                sk2[d] = f;
+                xn = __fadd_rn(y, __fmul_rn(dt, __fsub_rn(f, __fmul_rn(sk1[d], third))));
               } else if (sg == 2) {
-                sk3[o] = f;
-                xn = __fadd_rn(y, __fmul_rn(dt, __fadd_rn(__fsub_rn(sk1[o], sk2[o]), f)));
+                sk3[d] = f;
+                xn = __fadd_rn(y, __fmul_rn(dt, __fadd_rn(__fsub_rn(sk1[d], sk2[d]), f)));
               } else {
-                const float sum = __fadd_rn(__fadd_rn(sk1[o], __fmul_rn(3.0f, __fadd_rn(sk2[o], sk3[o]))), f);
+                const float sum = __fadd_rn(__fadd_rn(sk1[d], __fmul_rn(3.0f, __fadd_rn(sk2[d], sk3[d]))), f);
                 xn = __fadd_rn(y, __fmul_rn(__fmul_rn(sum, dt), 0.125f));
-                sy[o] = xn;
+                sy[d] = xn;
                 if (P.traj != nullptr && row < P.N) P.traj[((size_t)(iv + 1) * P.N + row) * 2 + d] = xn;
                 if (ev == n_eval - 1 && row < P.N) P.out[row * 2 + d] = xn;
               }
-              sxs[o] = xn;
+              sxs[2 * lane + d] = xn;
             }
           }
         }
         ebar();
+        if (stamp) g_tc_stamps[12] = clock64();
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+  cluster_sync_all();   // the peer may still be multicasting into this CTA's ring / arriving on its barriers
+  if (warp == NEW + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
 }
 
 }  // namespace tc
+
+int tensor_debug_stamps(long long* h_out, int n) {
+  IDFF_CUDA(cudaMemcpyFromSymbol(h_out, tc::g_tc_stamps, sizeof(long long) * (n < 32 ? n : 32)));
+  return IDFF_OK;
+}
 
 bool tensor_supports(const idff_weights_t* w, const idff_field_params_t* p) {
   const NetView& v = w->v;
@@ -506,14 +593,28 @@ static int launch_tc(const idff_weights_t* w, const idff_field_params_t* p, tc::
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
   const long tiles = (P.N + tc::NP - 1) / tc::NP;
-  const int grid = (int)(tiles < sms ? tiles : sms);
+  int grid = (int)(tiles < sms ? tiles : sms);
+  grid = (grid + 1) & ~1;   // CTA pairs
   static thread_local Rk4Table rk0;
   static thread_local Stage one0;
   const Rk4Table& rkr = rk ? *rk : rk0;
   const Stage& oner = one ? *one : one0;
-  const int smem = tc::Smem::total + 1024;
+  const int smem = tc::Smem::total;
   IDFF_CUDA(cudaFuncSetAttribute(tc::k_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  tc::k_tc<<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(P, rkr, oner);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(tc::NTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  IDFF_CUDA(cudaLaunchKernelEx(&cfg, tc::k_tc, P, rkr, oner));
   IDFF_CUDA(cudaGetLastError());
   count_launch();
   return IDFF_OK;

@@ -86,6 +86,11 @@ int idff_field_eval(const idff_weights_t* w, const idff_field_params_t* p, float
  * 1-t, c1, c2, c3, end_div}.  Needs no GPU. */
 int idff_stage_scalars(const idff_field_params_t* p, float t, float* h_out8);
 
+/* Diagnostic: clock64 phase timestamps of the last IDFF_IMPL_TENSOR launch (CTA 0, first tile, 2nd evaluation):
+ * [0..12] epilogue warp 0 (layer-1 start, publish, accumulator-ready / publish of every layer pass, reductions,
+ * stage update), [16+2g], [17+2g] MMA issue start / commit of layer pass g.  h_out32: 32 int64 on the host. */
+int idff_debug_tensor_stamps(int64_t* h_out32);
+
 /* ---- a8 + a3..a6 fused: torchdiffeq.odeint(model, x0, t_grid, method='rk4') (3/8 rule, grid == t_grid;
  * call sites Autograd_example_order2.py:167,213,291).  h_t_grid: n_grid fp32 times on the host.
  * d_out_final [N][dim] = traj[-1]; d_out_traj (optional) [n_grid][N][dim] = the whole traj. */
