@@ -30,13 +30,15 @@ constexpr int NP = 32;                   // particles per CTA
 constexpr int NCOL = 64;                 // MMA N: 2 jets x 32 particles
 constexpr int NSTAGE = 3;                // weight ring depth (bytes in flight hide the ~1000-cycle L2->SM latency)
 constexpr int TILE_BYTES = 32768;        // hi (16 KB) + lo (16 KB) image of one [128 x 32] weight tile
-constexpr int ACT_BYTES = NCOL * W * 4;  // one copy (hi or lo) of the B operand: 8 k-blocks x [64 x 128 B]
+constexpr int KB_BYTES = 2 * NCOL * 128;  // B operand of one k-block: rows 0..63 = hi copy, rows 64..127 = lo copy (16 KB)
+constexpr int ACT_BYTES = 8 * KB_BYTES;   // whole B operand: 8 k-blocks
 constexpr int NE = 512;                  // epilogue threads: warp w -> lane quarter w%4, m-tile (w/4)%2, particle half w/8
 constexpr int NEW = NE / 32;             // epilogue warps
 constexpr int NTHREADS = NE + 64;        // + producer warp 16 + MMA warp 17
 constexpr int TMEM_COLS = 512;
-// per m-tile: two main accumulators (even / odd k-blocks: halves the number of truncating accumulation steps) + corr
-constexpr int COL_MAIN = 0, COL_MAIN2 = 64, COL_CORR = 128, COL_MT = 192, COL_STASH = 384;   // + mt * COL_MT / + mt * 64
+// accumulator sets (shared by the two m-tiles, which run back to back): set s = k-block parity, [main 64 | corr 64];
+// two sets halve the number of truncating accumulation steps per accumulator.  Stash: 64 columns per m-tile.
+constexpr int COL_SET = 128, COL_CORR = 64, COL_STASH = 256;
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
@@ -160,9 +162,8 @@ struct TParams {
 };
 
 struct Smem {   // byte offsets from the dynamic base, which must be 1024-byte aligned (checked at kernel entry)
-  static constexpr int act_hi = 0;
-  static constexpr int act_lo = ACT_BYTES;
-  static constexpr int ring = 2 * ACT_BYTES;
+  static constexpr int act = 0;
+  static constexpr int ring = ACT_BYTES;
   static constexpr int misc = ring + NSTAGE * TILE_BYTES;   // floats: red [16 warps][32], xs [64]
   static constexpr int f_red = 0, f_xs = NEW * 32, f_end = NEW * 32 + 64;
   static constexpr int bars = misc + f_end * 4;
@@ -211,9 +212,10 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
   uint64_t* full = bars;                 // [NSTAGE]  TMA -> MMA
   uint64_t* empty = bars + NSTAGE;       // [NSTAGE]  MMA -> TMA
-  uint64_t* acc_full = bars + 2 * NSTAGE;   // MMA -> epilogue: the accumulators of one layer pass are complete
-  uint64_t* b_ready = acc_full + 1;         // epilogue -> MMA: the B operand of the next layer pass is written
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 2);
+  uint64_t* acc_full = bars + 2 * NSTAGE;   // [2] MMA -> epilogue: the accumulators of m-tile mt are complete
+  uint64_t* b_ready = acc_full + 2;         // epilogue -> MMA: the B operand of the next layer pass is written
+  uint64_t* tmem_free = acc_full + 3;       // m-tile-0 epilogue threads -> MMA: accumulators read, m-tile 1 may overwrite
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
@@ -221,8 +223,10 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 2);   // both CTAs of the pair must have consumed a slot before either half is overwritten
     }
-    mbar_init(acc_full, 1);
+    mbar_init(&acc_full[0], 1);
+    mbar_init(&acc_full[1], 1);
     mbar_init(b_ready, NE);
+    mbar_init(tmem_free, NE / 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == NEW + 1) {
@@ -230,7 +234,7 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   // jet-1 columns are read by the MMAs of boundary evaluations too: start from finite values
-  for (int i = tid; i < 2 * ACT_BYTES / 4; i += NTHREADS) reinterpret_cast<float*>(smem)[i] = 0.0f;
+  for (int i = tid; i < ACT_BYTES / 4; i += NTHREADS) reinterpret_cast<float*>(smem)[i] = 0.0f;
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -269,10 +273,11 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
   } else if (warp == NEW + 1) {
     // ===== MMA issuer (one thread)
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t bhi = s32(smem + Smem::act_hi), blo = s32(smem + Smem::act_lo);
+      const uint32_t idesc_w = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * NCOL >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc_n = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t bop = s32(smem + Smem::act);
       int stage = 0;
-      uint32_t phase = 0, bphase = 0;
+      uint32_t phase = 0, bphase = 0, fphase = 0;
       for (long it = 0; it < n_iter; ++it)
         for (int e = 0; e < n_eval; ++e) {
           const int ng = heavy_of(stage_of(e)) ? 4 : 2;
@@ -283,24 +288,29 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
             const bool mstamp = blockIdx.x == 0 && it == 0 && e == 1;
             if (mstamp) g_tc_stamps[16 + 2 * g] = clock64();
             for (int mt = 0; mt < 2; ++mt) {
-              const uint32_t d_main0 = tmem + mt * COL_MT + COL_MAIN, d_corr = tmem + mt * COL_MT + COL_CORR;
+              if (mt == 1) {   // the accumulator sets are reused: m-tile 0 must have been read out
+                mbar_wait(tmem_free, fphase);
+                fphase ^= 1u;
+                tc_fence_after();
+              }
               for (int kb = 0; kb < 8; ++kb) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 const uint32_t whi = s32(smem + Smem::ring + stage * TILE_BYTES), wlo = whi + 16384;
+                const uint32_t dset = tmem + (kb & 1) * COL_SET;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                   const uint64_t a_hi = make_desc(whi + ks * 32), a_lo = make_desc(wlo + ks * 32);
-                  const uint64_t b_hi = make_desc(bhi + kb * (NCOL * 128) + ks * 32), b_lo = make_desc(blo + kb * (NCOL * 128) + ks * 32);
-                  mma_tf32(d_main0 + (kb & 1) * (COL_MAIN2 - COL_MAIN), a_hi, b_hi, idesc, ((kb >> 1) | ks) != 0);
-                  mma_tf32(d_corr, a_lo, b_hi, idesc, (kb | ks) != 0);
-                  mma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
+                  const uint64_t b_w = make_desc(bop + kb * KB_BYTES + ks * 32);   // 128 rows: hi copy then lo copy
+                  // [main | corr] += W_hi * [X_hi ; X_lo]   (one N = 128 MMA reads W_hi once), then corr += W_lo * X_hi
+                  mma_tf32(dset, a_hi, b_w, idesc_w, ((kb >> 1) | ks) != 0);
+                  mma_tf32(dset + COL_CORR, a_lo, b_w, idesc_n, 1u);
                 }
                 mma_commit_mc(&empty[stage], (uint16_t)3);   // frees the slot in both CTAs once these MMAs have read it
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
               }
+              mma_commit(&acc_full[mt]);
             }
-            mma_commit(acc_full);
             if (mstamp) g_tc_stamps[17 + 2 * g] = clock64();
           }
         }
@@ -313,9 +323,9 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
     const int p0 = h * HP;
     float* red = misc + Smem::f_red;       // [16 warps][32]
     float* sxs = misc + Smem::f_xs;        // stage input of the 32 particles, [p][2]
-    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + mt * COL_MT + p0;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + p0;
     const uint32_t stash_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + COL_STASH + mt * 64 + p0;
-    uint32_t aphase = 0;
+    uint32_t aphase0 = 0, aphase1 = 0;
     const float third = (float)(1.0 / 3.0);
     const float wx0 = __ldg(P.net.wt0 + 0 * W + n), wx1 = __ldg(P.net.wt0 + 1 * W + n), wtt = __ldg(P.net.wt0 + 2 * W + n),
                 bb0 = __ldg(P.net.b0 + (size_t)P.tidx * W + n), bb1 = __ldg(P.net.b1 + n), bb2 = __ldg(P.net.b2 + n),
@@ -325,8 +335,8 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
     float sy[2] = {0.f, 0.f}, sk1[2] = {0.f, 0.f}, sk2[2] = {0.f, 0.f}, sk3[2] = {0.f, 0.f}, sx0[2] = {0.f, 0.f};
     float pr_tot[2] = {0.f, 0.f};
     // this unit's k position inside the B operand: k-block, 16-byte chunk, word
-    unsigned char* ahi = smem + Smem::act_hi + (n >> 5) * (NCOL * 128) + ((n & 3) << 2);
-    unsigned char* alo = ahi + ACT_BYTES;
+    unsigned char* ahi = smem + Smem::act + (n >> 5) * KB_BYTES + ((n & 3) << 2);
+    unsigned char* alo = ahi + NCOL * 128;
     const int kchunk = (n >> 2) & 7;
     auto put = [&](int col, float v) {
       const uint32_t o = (uint32_t)(col * 128 + ((kchunk ^ (col & 7)) << 4));
@@ -340,15 +350,31 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
       tc_fence_before();
       mbar_arrive(b_ready);
     };
-    // z = main + corr of this thread's unit: jet j, particles p0 .. p0+15
+    // z = sum of the two accumulator sets (main + corr each) of this thread's unit: jet j, particles p0 .. p0+15
     auto load_acc = [&](int j, float (&z)[HP]) {
-      uint32_t m[HP], m2[HP], c[HP];
-      tmem_ld16(lane_base + COL_MAIN + j * NP, m);
-      tmem_ld16(lane_base + COL_MAIN2 + j * NP, m2);
-      tmem_ld16(lane_base + COL_CORR + j * NP, c);
+      uint32_t m0[HP], c0[HP], m1[HP], c1[HP];
+      tmem_ld16(lane_base + j * NP, m0);
+      tmem_ld16(lane_base + COL_CORR + j * NP, c0);
+      tmem_ld16(lane_base + COL_SET + j * NP, m1);
+      tmem_ld16(lane_base + COL_SET + COL_CORR + j * NP, c1);
       tmem_wait_ld();
 #pragma unroll
-      for (int i = 0; i < HP; ++i) z[i] = (__uint_as_float(m[i]) + __uint_as_float(m2[i])) + __uint_as_float(c[i]);
+      for (int i = 0; i < HP; ++i)
+        z[i] = (__uint_as_float(m0[i]) + __uint_as_float(m1[i])) + (__uint_as_float(c0[i]) + __uint_as_float(c1[i]));
+    };
+    // accumulators of this thread's m-tile complete
+    auto wait_acc = [&]() {
+      if (mt == 0) { mbar_wait_sleep(&acc_full[0], aphase0); aphase0 ^= 1u; }
+      else { mbar_wait_sleep(&acc_full[1], aphase1); aphase1 ^= 1u; }
+      tc_fence_after();
+    };
+    // m-tile 0: accumulators are in registers -> m-tile 1 may overwrite them
+    auto release_acc = [&]() {
+      if (mt == 0) { tc_fence_before(); mbar_arrive(tmem_free); }
+    };
+    // the B operand may be rewritten once every MMA of the layer pass has read it (= m-tile 1 complete)
+    auto wait_operand_free = [&]() {
+      if (mt == 0) { mbar_wait_sleep(&acc_full[1], aphase1); aphase1 ^= 1u; }
     };
 
     for (long it = 0; it < n_iter; ++it) {
@@ -388,21 +414,21 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
         if (stamp) g_tc_stamps[1] = clock64();
         float part[32];
         // ---- gemm 0: layer 2 forward
-        mbar_wait_sleep(acc_full, aphase); aphase ^= 1u; tc_fence_after();
+        wait_acc();
         if (stamp) g_tc_stamps[2] = clock64();
         {
-          float z[HP], zd[HP];
+          float z[HP], zd[HP], o0[HP], o1[HP];
           load_acc(0, z);
           if (heavy) load_acc(1, zd);
+          release_acc();
           uint32_t st_code[HP];
 #pragma unroll
           for (int i = 0; i < HP; ++i) {
             float code, s1, E;
-            const float a = selu_fwd(z[i] + bb1, code);
+            o0[i] = selu_fwd(z[i] + bb1, code);
             selu_decode(code, s1, E);
             st_code[i] = __float_as_uint(code);
-            put(p0 + i, a);
-            if (heavy) put(NP + p0 + i, s1 * zd[i]);
+            o1[i] = heavy ? s1 * zd[i] : 0.0f;
           }
           if (heavy) {
             uint32_t st_zd[HP];
@@ -412,16 +438,23 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
             tmem_st16(stash_base + NP, st_zd);
             tmem_wait_st();
           }
+          wait_operand_free();
+#pragma unroll
+          for (int i = 0; i < HP; ++i) {
+            put(p0 + i, o0[i]);
+            if (heavy) put(NP + p0 + i, o1[i]);
+          }
         }
         publish();
         if (stamp) g_tc_stamps[3] = clock64();
         // ---- gemm 1: layer 3 forward; x1hat partials; adjoint seeds
-        mbar_wait_sleep(acc_full, aphase); aphase ^= 1u; tc_fence_after();
+        wait_acc();
         if (stamp) g_tc_stamps[4] = clock64();
         {
-          float z[HP], zd[HP];
+          float z[HP], zd[HP], o0[HP], o1[HP];
           load_acc(0, z);
           if (heavy) load_acc(1, zd);
+          release_acc();
           const float A0 = st.c[0] * uu3, A1 = st.c[1] * uu3;
 #pragma unroll
           for (int i = 0; i < HP; ++i) {
@@ -430,9 +463,15 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
             selu_decode(code, s1, E);
             part[2 * i] = a * w30;
             part[2 * i + 1] = a * w31;
-            if (heavy) {
-              put(p0 + i, fmaf(A1 * E, zd[i], A0 * s1));   // adjoint of z3
-              put(NP + p0 + i, A1 * s1);                   // adjoint of z3'
+            o0[i] = heavy ? fmaf(A1 * E, zd[i], A0 * s1) : 0.0f;   // adjoint of z3
+            o1[i] = A1 * s1;                                        // adjoint of z3'
+          }
+          wait_operand_free();
+          if (heavy) {
+#pragma unroll
+            for (int i = 0; i < HP; ++i) {
+              put(p0 + i, o0[i]);
+              put(NP + p0 + i, o1[i]);
             }
           }
         }
@@ -455,12 +494,13 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
         float gg[2] = {0.f, 0.f};
         if (heavy) {
           // ---- gemm 2: reverse, layer 3 -> 2
-          mbar_wait_sleep(acc_full, aphase); aphase ^= 1u; tc_fence_after();
+          wait_acc();
           if (stamp) g_tc_stamps[7] = clock64();
           {
-            float a0[HP], a1[HP];
+            float a0[HP], a1[HP], o0[HP], o1[HP];
             load_acc(0, a0);
             load_acc(1, a1);
+            release_acc();
             uint32_t cd[HP], zdu[HP];
             tmem_ld16(stash_base, cd);
             tmem_ld16(stash_base + NP, zdu);
@@ -469,19 +509,26 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
             for (int i = 0; i < HP; ++i) {
               float s1, E;
               selu_decode(__uint_as_float(cd[i]), s1, E);
-              put(p0 + i, fmaf(a1[i] * E, __uint_as_float(zdu[i]), a0[i] * s1));
-              put(NP + p0 + i, a1[i] * s1);
+              o0[i] = fmaf(a1[i] * E, __uint_as_float(zdu[i]), a0[i] * s1);
+              o1[i] = a1[i] * s1;
+            }
+            wait_operand_free();
+#pragma unroll
+            for (int i = 0; i < HP; ++i) {
+              put(p0 + i, o0[i]);
+              put(NP + p0 + i, o1[i]);
             }
           }
           publish();
           if (stamp) g_tc_stamps[8] = clock64();
           // ---- gemm 3: reverse, layer 2 -> 1 -> x
-          mbar_wait_sleep(acc_full, aphase); aphase ^= 1u; tc_fence_after();
+          wait_acc();
           if (stamp) g_tc_stamps[9] = clock64();
           {
             float a0[HP], a1[HP];
             load_acc(0, a0);
             load_acc(1, a1);
+            release_acc();
             const float zb = fmaf(wtt, st.t, bb0);
 #pragma unroll
             for (int i = 0; i < HP; ++i) {
@@ -494,6 +541,7 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
               part[2 * i] = P1 * wx0;
               part[2 * i + 1] = P1 * wx1;
             }
+            wait_operand_free();   // keeps the barrier phases of both m-tile groups in step
           }
           warp_reduce_scatter32(part, lane);
           red[warp * 32 + lane] = part[0];
