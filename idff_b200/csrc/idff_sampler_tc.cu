@@ -213,9 +213,13 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
   uint64_t* full = bars;                 // [NSTAGE]  TMA -> MMA
   uint64_t* empty = bars + NSTAGE;       // [NSTAGE]  MMA -> TMA
   uint64_t* acc_full = bars + 2 * NSTAGE;   // [2] MMA -> epilogue: the accumulators of m-tile mt are complete
-  uint64_t* b_ready = acc_full + 2;         // epilogue -> MMA: the B operand of the next layer pass is written
-  uint64_t* tmem_free = acc_full + 3;       // m-tile-0 epilogue threads -> MMA: accumulators read, m-tile 1 may overwrite
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
+  // epilogue -> MMA.  b_ready_lo: k-blocks 0..3 of the next layer pass are written (m-tile-0 threads) AND the m-tile-1
+  // threads have read their accumulators out; b_ready_hi: k-blocks 4..7 are written (m-tile-1 threads).  The next pass
+  // starts on k-blocks 0..3 while the m-tile-1 epilogue is still computing.
+  uint64_t* b_ready_lo = acc_full + 2;
+  uint64_t* b_ready_hi = acc_full + 3;
+  uint64_t* tmem_free = acc_full + 4;       // m-tile-0 epilogue threads -> MMA: accumulators read, m-tile 1 may overwrite
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 5);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
@@ -225,7 +229,8 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
     }
     mbar_init(&acc_full[0], 1);
     mbar_init(&acc_full[1], 1);
-    mbar_init(b_ready, NE);
+    mbar_init(b_ready_lo, NE);
+    mbar_init(b_ready_hi, NE / 2);
     mbar_init(tmem_free, NE / 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -277,12 +282,12 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
       const uint32_t idesc_n = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t bop = s32(smem + Smem::act);
       int stage = 0;
-      uint32_t phase = 0, bphase = 0, fphase = 0;
+      uint32_t phase = 0, bphase = 0, hphase = 0, fphase = 0;
       for (long it = 0; it < n_iter; ++it)
         for (int e = 0; e < n_eval; ++e) {
           const int ng = heavy_of(stage_of(e)) ? 4 : 2;
           for (int g = 0; g < ng; ++g) {
-            mbar_wait(b_ready, bphase);
+            mbar_wait(b_ready_lo, bphase);
             bphase ^= 1u;
             tc_fence_after();
             const bool mstamp = blockIdx.x == 0 && it == 0 && e == 1;
@@ -294,6 +299,11 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
                 tc_fence_after();
               }
               for (int kb = 0; kb < 8; ++kb) {
+                if (mt == 0 && kb == 4) {   // the upper half of K comes from the m-tile-1 epilogue threads
+                  mbar_wait(b_ready_hi, hphase);
+                  hphase ^= 1u;
+                  tc_fence_after();
+                }
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 const uint32_t whi = s32(smem + Smem::ring + stage * TILE_BYTES), wlo = whi + 16384;
@@ -348,7 +358,7 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
     auto publish = [&]() {
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(b_ready);
+      mbar_arrive(mt == 0 ? b_ready_lo : b_ready_hi);
     };
     // z = sum of the two accumulator sets (main + corr each) of this thread's unit: jet j, particles p0 .. p0+15
     auto load_acc = [&](int j, float (&z)[HP]) {
@@ -365,18 +375,20 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
     // accumulators of this thread's m-tile complete
     auto wait_acc = [&]() {
       if (mt == 0) { mbar_wait_sleep(&acc_full[0], aphase0); aphase0 ^= 1u; }
-      else { mbar_wait_sleep(&acc_full[1], aphase1); aphase1 ^= 1u; }
+      else { mbar_wait(&acc_full[1], aphase1); aphase1 ^= 1u; }
       tc_fence_after();
     };
-    // m-tile 0: accumulators are in registers -> m-tile 1 may overwrite them
+    // accumulators are in registers: m-tile 0 -> m-tile 1 may overwrite them; m-tile 1 -> the next layer pass may
     auto release_acc = [&]() {
-      if (mt == 0) { tc_fence_before(); mbar_arrive(tmem_free); }
+      tc_fence_before();
+      mbar_arrive(mt == 0 ? tmem_free : b_ready_lo);
     };
     // the B operand may be rewritten once every MMA of the layer pass has read it (= m-tile 1 complete)
     auto wait_operand_free = [&]() {
-      if (mt == 0) { mbar_wait_sleep(&acc_full[1], aphase1); aphase1 ^= 1u; }
+      if (mt == 0) { mbar_wait(&acc_full[1], aphase1); aphase1 ^= 1u; }   // on the critical path: no back-off
     };
 
+    if (mt == 1) mbar_arrive(b_ready_lo);   // nothing to read out before the very first layer pass
     for (long it = 0; it < n_iter; ++it) {
       const long base = (blockIdx.x + it * gridDim.x) * NP;   // may lie beyond N: an all-padding tile
       if (warp == 0) {
