@@ -1,5 +1,5 @@
 import sys, os, time, ctypes as C
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, ROOT + "/oracle", ROOT + "/tests"]
 import numpy as np, torch
 from gpu_common import packed
