@@ -34,6 +34,13 @@ int tensor_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, con
 
 int tensor_debug_stamps(long long* h_out, int n);
 
+// idff_sampler_wide.cu
+bool wide_supports(const idff_weights_t* w, const idff_field_params_t* p);
+int wide_field_eval(const idff_weights_t* w, const idff_field_params_t* p, float t, const float* d_x, const float* d_x0,
+                    float* d_out, int64_t N, void* stream);
+int wide_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, const float* d_x0, const Stage* stages,
+                    const float* dts, int n_iv, float* d_out_final, float* d_out_traj, int64_t N, void* stream);
+
 struct DeviceGuard {
   int prev = -1;
   bool ok = true;
@@ -93,6 +100,8 @@ extern "C" int idff_field_eval(const idff_weights_t* w, const idff_field_params_
   IDFF_CHECK_ARG(N > 0 && d_x && d_out, "idff_field_eval: null pointer or negative N");
   IDFF_CHECK_ARG(p->variant != IDFF_FIELD_CFM || t == 0.0f || d_x0, "idff_field_eval: the CFM field needs x0 (captured at t == 0) when t != 0");
   DeviceGuard g(w->device);
+  if ((p->impl == IDFF_IMPL_TENSOR || p->impl == IDFF_IMPL_AUTO) && wide_supports(w, p) && (p->impl == IDFF_IMPL_TENSOR || N >= 2048))
+    return wide_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
   if (p->impl == IDFF_IMPL_TENSOR || (p->impl == IDFF_IMPL_AUTO && tensor_supports(w, p) && N >= 4096))
     return tensor_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
   if (p->impl == IDFF_IMPL_FUSED || (p->impl == IDFF_IMPL_AUTO && fused_supports(w, p))) {
@@ -140,6 +149,8 @@ extern "C" int idff_sample_rk4(const idff_weights_t* w, const idff_field_params_
     make_stage(*p, tc, &st[4 * i + 2]);
     make_stage(*p, t1, &st[4 * i + 3]);
   }
+  if ((p->impl == IDFF_IMPL_TENSOR || p->impl == IDFF_IMPL_AUTO) && wide_supports(w, p) && (p->impl == IDFF_IMPL_TENSOR || N >= 2048))
+    return wide_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream);
   if (p->impl == IDFF_IMPL_TENSOR || (p->impl == IDFF_IMPL_AUTO && tensor_supports(w, p)))
     return tensor_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream);
   const bool want_fused = p->impl == IDFF_IMPL_FUSED || (p->impl == IDFF_IMPL_AUTO && fused_supports(w, p));

@@ -64,7 +64,8 @@ struct NetView {
   const float* fw2r;  // [w][w]  fw2r[n][p] = W2[n][perm(p)]   reverse,  layer 3 -> 2
   const float* fw1r;  // [w][w]  fw1r[n][p] = W1[n][perm(p)]   reverse,  layer 2 -> 1
   const float* w0n;   // [w][din-1]  W0[n][d], d < D            reverse,  layer 1 -> x  (wide-D path)
-  // tcgen05 operand tiles (w == 256): [gemm 0..3][m-tile 0..1][k-block 0..7][hi, lo][128 rows x 32 tf32], each tile a
+  // tcgen05 operand tiles (w % 128 == 0, 3 -> w -> w -> w -> 2 networks): [gemm 0..3][m-tile < w/128][k-block < w/32][hi, lo]
+  // [128 rows x 32 tf32], each tile a
   // 16 KB shared-memory image in the canonical K-major SWIZZLE_128B layout (row r at r*128 B, 16-byte chunk c stored at
   // chunk c ^ (r & 7)), so one cp.async.bulk lands it ready for the UMMA descriptor.  gemm 0: W1 (rows = out units),
   // 1: W2, 2: W2^T, 3: W1^T.  hi = rn_tf32(w), lo = rn_tf32(w - hi)  (3xTF32 split).

@@ -109,8 +109,9 @@ extern "C" int idff_weights_create(const float* const* h_W, const float* const* 
   const size_t o_fwt1 = fused_layout ? take((size_t)w * w) : 0, o_fwt2 = fused_layout ? take((size_t)w * w) : 0;
   const size_t o_fw2r = fused_layout ? take((size_t)w * w) : 0, o_fw1r = fused_layout ? take((size_t)w * w) : 0;
   const size_t o_w0n = take((size_t)w * (din > 1 ? din - 1 : 1));
-  const bool tc_layout = (w == 256);
-  const size_t tc_floats = (size_t)4 * 2 * 8 * 2 * 128 * 32;
+  const bool tc_layout = (w % 128 == 0) && w >= 256 && w <= 2048 && din == 3 && dout == 2;
+  const int tc_mt = w / 128, tc_kb = w / 32;
+  const size_t tc_floats = (size_t)4 * tc_mt * tc_kb * 2 * 128 * 32;
   off = (off + 255) & ~size_t(255);   // 1 KB alignment of the tile images
   const size_t o_tc = tc_layout ? take(tc_floats) : 0;
   std::vector<float> blob(off, 0.0f);
@@ -168,9 +169,9 @@ extern "C" int idff_weights_create(const float* const* h_W, const float* const* 
       return x;
     };
     for (int g = 0; g < 4; ++g)
-      for (int mt = 0; mt < 2; ++mt)
-        for (int kb = 0; kb < 8; ++kb) {
-          float* hi = &blob[o_tc + ((((size_t)g * 2 + mt) * 8 + kb) * 2 + 0) * 4096];
+      for (int mt = 0; mt < tc_mt; ++mt)
+        for (int kb = 0; kb < tc_kb; ++kb) {
+          float* hi = &blob[o_tc + ((((size_t)g * tc_mt + mt) * tc_kb + kb) * 2 + 0) * 4096];
           float* lo = hi + 4096;
           for (int r = 0; r < 128; ++r)
             for (int kk = 0; kk < 32; ++kk) {
