@@ -345,24 +345,26 @@ def aux_measurements(dev, pw, model, peaks):
     # ---- other BASELINE configs, measured briefly (reported, not the headline)
     try:
         from idff_b200.weights import PackedWeights
-        # C3: order-3 field, wide MLP (default nn.Linear init, seed 0) -> generic kernel (one thread per hidden unit)
+        # C3: order-3 field, wide MLP (default nn.Linear init, seed 0) -> layer-by-layer tcgen05 3xTF32 engine
         torch.manual_seed(0)
         from idff_b200.torchcfm.models.models import MLP
         for wide in (1024,):
             net = MLP(dim=2, w=wide, time_varying=True)
             pww = PackedWeights.from_module(net, device=dev)
             m3 = fields.CustomNetModelOrder3(pww, SIGMA, 0.2, 0.2, 0.2)
-            xw = torch.randn(1 << 15, 2, device=dev, generator=g) / 1.5
+            xw = torch.randn(1 << 17, 2, device=dev, generator=g) / 1.5
             ts = torch.linspace(0, 1, 3)
             s = timeit(lambda: sampler.sample_rk4(m3, xw, ts), reps=2, warm=1)
             F = 3 * wide + 2 * wide * wide + wide * 2
-            aux[f"c3_order3_w{wide}_generic"] = {"particle_steps_per_s": xw.shape[0] * 8 / s,
+            aux[f"c3_order3_w{wide}_layered_tcgen05"] = {"particle_steps_per_s": xw.shape[0] * 8 / s,
                                                  "algorithmic_tflops": xw.shape[0] * 2.0 * F * (6 * 6 + 2) / s / 1e12,
                                                  "particles": xw.shape[0], "nfe": 2}
-        # C2 order 3 at w = 256 (FFMA2 kernel, three jets)
-        m3 = fields.CustomNetModelOrder3(pw, SIGMA, 0.2, 0.2, 0.2)
-        s = timeit(lambda: sampler.sample_rk4(m3, xs, torch.linspace(0, 1, 3)), reps=2, warm=1)
-        aux["order3_w256_ffma2"] = {"particle_steps_per_s": xs.shape[0] * 8 / s}
+        # C2 order 3 at w = 256: FFMA2 kernel vs the layered tcgen05 engine (AUTO picks the latter for large batches)
+        for name, impl in (("ffma2", 2), ("layered_tcgen05", 4)):
+            m3 = fields.CustomNetModelOrder3(pw, SIGMA, 0.2, 0.2, 0.2)
+            m3.impl = impl
+            s = timeit(lambda: sampler.sample_rk4(m3, xs, torch.linspace(0, 1, 3)), reps=2, warm=1)
+            aux[f"order3_w256_{name}"] = {"particle_steps_per_s": xs.shape[0] * 8 / s}
         # C4: PolyALA SDE_cal (47-128-128-128-46, folded embedding), srk, ts = linspace(0,1,3), dt = 0.3
         pwm = PackedWeights.from_npz(os.path.join(GOLDEN, "weights_polyala.npz"), device=dev)
         sde = fields.SDE_cal(pwm, input_dim=46, sigma=0.5, init_ind=3, max_length=200, dt=0.3, gamma1=0.2, gamma2=1.25)

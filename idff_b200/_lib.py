@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libidff_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 IDFF_FIELD_MOMENTUM, IDFF_FIELD_SCOREHEAD, IDFF_FIELD_CFM, IDFF_FIELD_MD = 0, 1, 2, 3
-IDFF_IMPL_AUTO, IDFF_IMPL_GENERIC, IDFF_IMPL_FUSED, IDFF_IMPL_TENSOR = 0, 1, 2, 3
+IDFF_IMPL_AUTO, IDFF_IMPL_GENERIC, IDFF_IMPL_FUSED, IDFF_IMPL_TENSOR, IDFF_IMPL_LAYERED = 0, 1, 2, 3, 4
 
 
 class IdffError(RuntimeError):

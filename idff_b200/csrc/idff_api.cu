@@ -100,6 +100,7 @@ extern "C" int idff_field_eval(const idff_weights_t* w, const idff_field_params_
   IDFF_CHECK_ARG(N > 0 && d_x && d_out, "idff_field_eval: null pointer or negative N");
   IDFF_CHECK_ARG(p->variant != IDFF_FIELD_CFM || t == 0.0f || d_x0, "idff_field_eval: the CFM field needs x0 (captured at t == 0) when t != 0");
   DeviceGuard g(w->device);
+  if (p->impl == IDFF_IMPL_LAYERED) return wide_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
   if ((p->impl == IDFF_IMPL_TENSOR || p->impl == IDFF_IMPL_AUTO) && wide_supports(w, p) && (p->impl == IDFF_IMPL_TENSOR || N >= 2048))
     return wide_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
   if (p->impl == IDFF_IMPL_TENSOR || (p->impl == IDFF_IMPL_AUTO && tensor_supports(w, p) && N >= 4096))
@@ -148,6 +149,15 @@ extern "C" int idff_sample_rk4(const idff_weights_t* w, const idff_field_params_
     make_stage(*p, tb, &st[4 * i + 1]);
     make_stage(*p, tc, &st[4 * i + 2]);
     make_stage(*p, t1, &st[4 * i + 3]);
+  }
+  if (p->impl == IDFF_IMPL_LAYERED)
+    return wide_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream);
+  if (p->impl == IDFF_IMPL_AUTO && w->v.w == 256 && N >= 16384 && !tensor_supports(w, p)) {
+    // three jets do not fit the fused tensor kernel; measured: layered tcgen05 engine 60 M vs FFMA2 kernel 48 M steps/s
+    idff_field_params_t q = *p;
+    q.impl = IDFF_IMPL_LAYERED;
+    if (wide_supports(w, &q))
+      return wide_sample_rk4(w, &q, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream);
   }
   if ((p->impl == IDFF_IMPL_TENSOR || p->impl == IDFF_IMPL_AUTO) && wide_supports(w, p) && (p->impl == IDFF_IMPL_TENSOR || N >= 2048))
     return wide_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream);

@@ -479,7 +479,8 @@ __global__ void k_wide_update(const __grid_constant__ UParams U) {
 // ---- host side ---------------------------------------------------------------------------------------------------------------
 bool wide_supports(const idff_weights_t* w, const idff_field_params_t* p) {
   const NetView& v = w->v;
-  if (v.tc_tiles == nullptr || v.w < 512 || p->dim != 2 || v.din != 3 || v.dout != 2) return false;
+  const int min_w = p->impl == IDFF_IMPL_LAYERED ? 256 : 512;   // at 256 the fused kernel is the default
+  if (v.tc_tiles == nullptr || v.w < min_w || p->dim != 2 || v.din != 3 || v.dout != 2) return false;
   return p->variant == IDFF_FIELD_MOMENTUM || p->variant == IDFF_FIELD_CFM;
 }
 

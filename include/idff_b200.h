@@ -40,7 +40,8 @@ extern "C" {
 #define IDFF_IMPL_AUTO 0
 #define IDFF_IMPL_GENERIC 1 /* any width / dimension: one thread per hidden unit, weights from L2 */
 #define IDFF_IMPL_FUSED 2   /* persistent warp-tiled kernel, weights streamed by TMA bulk copies */
-#define IDFF_IMPL_TENSOR 3  /* tcgen05 3xTF32 kernel (width 256, dim 2, order <= 2): accumulators in TMEM */
+#define IDFF_IMPL_TENSOR 3  /* tcgen05 3xTF32: fused kernel (width 256, dim 2, order <= 2) or the layered engine (width >= 512) */
+#define IDFF_IMPL_LAYERED 4 /* force the layer-by-layer tcgen05 engine (width >= 256, dim 2, orders 1..3) */
 
 typedef struct idff_weights idff_weights_t; /* opaque: packed device copies of one 4-layer SELU MLP */
 

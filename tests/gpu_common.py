@@ -32,14 +32,15 @@ def assert_field_close(got, ref, tol=1e-5, what=""):
 
 
 def assert_field_vs_refs(got, ref32, ref64, tol=1e-5, what=""):
-    """Per-evaluation contract: within tol * max|f| of the reference's fp32 result -- or, where the reference's own
-    fp32 rounding exceeds that (the t == 1 branch divides by 1e-2 and amplifies the MLP's fp32 round-off x100), within
-    2x the reference's fp32<->fp64 gap of it AND at least as close to the fp64 value as the reference itself."""
+    """Per-evaluation contract: within tol * max|f| of the reference's fp32 result and of its fp64 twin -- or, where
+    the reference's own fp32 rounding exceeds that (the t == 1 branch divides by 1e-2 and amplifies the MLP's fp32
+    round-off x100), about as close to the fp64 value as the reference itself (1.25 x its fp32<->fp64 gap), hence within
+    gap + 1.25 gap of the fp32 reference (triangle inequality)."""
     got, ref32, ref64 = (np.asarray(a, dtype=np.float64) for a in (got, ref32, ref64))
     scale = max(1.0, float(np.abs(ref32).max()))
     gap = float(np.abs(ref32 - ref64).max())
     e32 = float(np.abs(got - ref32).max())
     e64 = float(np.abs(got - ref64).max())
-    assert e32 <= max(tol * scale, 2.0 * gap), f"{what}: |got-ref32| {e32:.3e} (tol {tol * scale:.3e}, ref gap {gap:.3e})"
+    assert e32 <= max(tol * scale, 2.25 * gap), f"{what}: |got-ref32| {e32:.3e} (tol {tol * scale:.3e}, ref gap {gap:.3e})"
     assert e64 <= max(tol * scale, 1.25 * gap), f"{what}: |got-ref64| {e64:.3e} (tol {tol * scale:.3e}, ref gap {gap:.3e})"
     return e32 / scale

@@ -12,7 +12,7 @@ from make_golden_consts import FIELD_TIMES, GAMMAS2, GAMMAS3
 
 pytestmark = pytest.mark.gpu
 
-IMPLS = [_lib.IDFF_IMPL_GENERIC, _lib.IDFF_IMPL_FUSED, _lib.IDFF_IMPL_TENSOR, _lib.IDFF_IMPL_AUTO]
+IMPLS = [_lib.IDFF_IMPL_GENERIC, _lib.IDFF_IMPL_FUSED, _lib.IDFF_IMPL_TENSOR, _lib.IDFF_IMPL_LAYERED, _lib.IDFF_IMPL_AUTO]
 
 
 @pytest.mark.parametrize("impl", IMPLS)

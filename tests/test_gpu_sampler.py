@@ -15,7 +15,7 @@ from make_golden_consts import GAMMAS2, GAMMAS3
 
 pytestmark = pytest.mark.gpu
 
-IMPLS = [_lib.IDFF_IMPL_GENERIC, _lib.IDFF_IMPL_FUSED, _lib.IDFF_IMPL_TENSOR, _lib.IDFF_IMPL_AUTO]
+IMPLS = [_lib.IDFF_IMPL_GENERIC, _lib.IDFF_IMPL_FUSED, _lib.IDFF_IMPL_TENSOR, _lib.IDFF_IMPL_LAYERED, _lib.IDFF_IMPL_AUTO]
 
 
 def _check_drift(got, ref32, ref64, what, med=2e-5, p999=2e-3):
