@@ -81,8 +81,9 @@ struct idff_weights {
   int emb_rows, emb_dim;
   float* d_blob;        // single allocation holding every array above
   size_t blob_floats;
-  float* d_stash;       // order-3 fused sampler: per-thread derivative stash (allocated on first use)
+  float* d_stash;       // scratch owned by the handle (order-3 stash of the fused kernel, buffers of the layered engine)
   size_t stash_bytes;
+  int tc_verified;      // bit 0 / 1: the first fused / layered tcgen05 launch on this handle was checked (alignment flag)
 };
 
 namespace idff {
@@ -99,6 +100,7 @@ struct Stage {
 };
 
 void make_stage(const idff_field_params_t& p, float t, Stage* out);
+
 
 
 // ---- launch tables (passed by value as __grid_constant__ kernel parameters; CUDA 12.1+ allows 32 KB) ---------

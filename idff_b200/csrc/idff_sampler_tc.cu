@@ -22,6 +22,21 @@
 
 namespace idff {
 void jets_needed(const idff_field_params_t& p, int* nj, int* reverse);
+// After the first launch on a handle: synchronise once and fail loudly if the kernel found its dynamic shared memory
+// misaligned for SWIZZLE_128B operands (it then returned without computing).
+__device__ int g_tc_misaligned = 0;
+static int verify_tc_launch(idff_weights_t* w, void* stream, int bit) {
+  if (w->tc_verified & bit) return IDFF_OK;
+  int flag = 0;
+  IDFF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  IDFF_CUDA(cudaMemcpyFromSymbol(&flag, g_tc_misaligned, sizeof(int)));
+  if (flag) {
+    set_error("tcgen05 kernel: dynamic shared memory is not 1024-byte aligned on this driver; use impl = IDFF_IMPL_FUSED");
+    return IDFF_EUNSUPPORTED;
+  }
+  w->tc_verified |= bit;
+  return IDFF_OK;
+}
 
 namespace tc {
 
@@ -207,7 +222,10 @@ __device__ __forceinline__ void warp_reduce_scatter32(float (&v)[32], int lane) 
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, const __grid_constant__ Stage one) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  if ((s32(smem) & 1023u) != 0u) return;   // SWIZZLE_128B operands need a 1024-byte aligned base (host checks the result)
+  if ((s32(smem) & 1023u) != 0u) {   // SWIZZLE_128B operands need a 1024-byte aligned base: report and do nothing
+    if (threadIdx.x == 0) g_tc_misaligned = 1;
+    return;
+  }   // SWIZZLE_128B operands need a 1024-byte aligned base (host checks the result)
   float* misc = reinterpret_cast<float*>(smem + Smem::misc);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
   uint64_t* full = bars;                 // [NSTAGE]  TMA -> MMA
@@ -677,7 +695,7 @@ static int launch_tc(const idff_weights_t* w, const idff_field_params_t* p, tc::
   IDFF_CUDA(cudaLaunchKernelEx(&cfg, tc::k_tc, P, rkr, oner));
   IDFF_CUDA(cudaGetLastError());
   count_launch();
-  return IDFF_OK;
+  return verify_tc_launch(const_cast<idff_weights_t*>(w), stream, 1);
 }
 
 static void fill_tparams(const idff_weights_t* w, const idff_field_params_t* p, int mode, int64_t N, tc::TParams* P) {

@@ -23,6 +23,21 @@
 
 namespace idff {
 void jets_needed(const idff_field_params_t& p, int* nj, int* reverse);
+// After the first launch on a handle: synchronise once and fail loudly if the kernel found its dynamic shared memory
+// misaligned for SWIZZLE_128B operands (it then returned without computing).
+__device__ int g_tc_misaligned = 0;
+static int verify_tc_launch(idff_weights_t* w, void* stream, int bit) {
+  if (w->tc_verified & bit) return IDFF_OK;
+  int flag = 0;
+  IDFF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  IDFF_CUDA(cudaMemcpyFromSymbol(&flag, g_tc_misaligned, sizeof(int)));
+  if (flag) {
+    set_error("tcgen05 kernel: dynamic shared memory is not 1024-byte aligned on this driver; use impl = IDFF_IMPL_FUSED");
+    return IDFF_EUNSUPPORTED;
+  }
+  w->tc_verified |= bit;
+  return IDFF_OK;
+}
 
 namespace wide {
 
@@ -188,7 +203,10 @@ template <int NJ>
 __global__ void __launch_bounds__(NTHREADS, 1) k_wide_layer(const __grid_constant__ WParams P) {
   constexpr int PPT = ppt_of(NJ), HP = PPT / 2;
   extern __shared__ __align__(1024) unsigned char smem[];
-  if ((s32(smem) & 1023u) != 0u) return;
+  if ((s32(smem) & 1023u) != 0u) {   // SWIZZLE_128B operands need a 1024-byte aligned base: report and do nothing
+    if (threadIdx.x == 0) g_tc_misaligned = 1;
+    return;
+  }
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + NSTAGE;
@@ -591,7 +609,7 @@ static int wide_run(const idff_weights_t* w, const idff_field_params_t* p, int m
     }
   }
   IDFF_CUDA(cudaGetLastError());
-  return IDFF_OK;
+  return verify_tc_launch(wm, stream, 2);
 }
 
 int wide_field_eval(const idff_weights_t* w, const idff_field_params_t* p, float t, const float* d_x, const float* d_x0,

@@ -222,7 +222,7 @@ extern "C" int idff_weights_create(const float* const* h_W, const float* const* 
   v.fw2r = fused_layout ? d_blob + o_fw2r : nullptr; v.fw1r = fused_layout ? d_blob + o_fw1r : nullptr;
   v.w0n = d_blob + o_w0n;
   v.tc_tiles = tc_layout ? d_blob + o_tc : nullptr;
-  h->d_stash = nullptr; h->stash_bytes = 0;
+  h->d_stash = nullptr; h->stash_bytes = 0; h->tc_verified = 0;
   *out = h;
   return IDFF_OK;
 }
