@@ -266,8 +266,10 @@ def run_ours(args):
                         "algorithmic_flops_per_launch": flops, "kernel_ms": k_ms,
                         "kernel_share_of_step": k_ms * args.steps / total_ms,
                         "frac_of_bf16_tensor_peak": achieved / bf16}
-        aux = aux_measurements(dev, pw, model, peaks) if not args.no_aux else {}
-        cpu_rate, cpu_per, cores, _ = cpu_reference_rate(args.cpu_particles, nfe, runs=5) if not args.no_cpu else (None, None, 0, [])
+        # secondary kernels and the CPU baseline are measured at N = 1 only (other ranks would idle in NCCL teardown)
+        aux = aux_measurements(dev, pw, model, peaks) if (not args.no_aux and ws == 1) else {}
+        cpu_rate, cpu_per, cores, _ = (cpu_reference_rate(args.cpu_particles, nfe, runs=5) if (not args.no_cpu and ws == 1)
+                                       else (None, None, 0, []))
         line = {"metric": "idff_particle_steps_per_sec", "value": value, "unit": "particle-steps/s", "n_gpus": ws,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
