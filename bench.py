@@ -344,6 +344,40 @@ def aux_measurements(dev, pw, model, peaks):
             s = timeit(lambda: sampler.sample_rk4(m2, xs, ts), reps=2, warm=1)
             sweep[str(nfe)] = xs.shape[0] * 4 * nfe / s
         aux[f"sampler_{name}_nfe_sweep_particle_steps_per_s"] = sweep
+    # ---- the reference's CPU path for the secondary kernels, timed beside them, small + large
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import idff_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+
+        def cpu_time(fn, reps=3):
+            fn()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            return (time.perf_counter() - t0) / reps
+
+        cpu = {"cores": os.cpu_count()}
+        for Bc in (256, 1 << 20):
+            a0, a1, ee = (torch.randn(Bc, 2) for _ in range(3))
+            tt = torch.rand(Bc)
+            cpu[f"path_sample_B{Bc}_rows_per_s"] = Bc / cpu_time(lambda: O.path_sample(a0, a1, tt, ee, 0.2, True))
+            cpu[f"flow_loss_fwd_B{Bc}_rows_per_s"] = Bc / cpu_time(lambda: O.flow_loss(a0, a1, tt))
+            d0, d1, de, dt_ = (v.to(dev) for v in (a0, a1, ee, tt))
+            sgpu = timeit(lambda: cfm._path_sample(d0, d1, dt_, de, 0.2, 1), reps=20, warm=3)
+            cpu[f"gpu_path_sample_B{Bc}_rows_per_s"] = Bc / sgpu
+        xa, xb = torch.randn(2048, 2), torch.randn(2048, 2)
+        cpu["mmd_2048_pairs_per_s"] = 3 * 2048 * 2048 / cpu_time(lambda: O.mmd_rbf(xa, xb))
+        da, db = xa.to(dev), xb.to(dev)
+        cpu["gpu_mmd_2048_pairs_per_s"] = 3 * 2048 * 2048 / timeit(lambda: mmd_partial_sums(da, db, 1.0), reps=20, warm=3)
+        wmd = np.load(os.path.join(GOLDEN, "weights_polyala.npz"))
+        lay = [(torch.tensor(wmd[f"W{i}"]), torch.tensor(wmd[f"b{i}"])) for i in range(4)]
+        fmd = O.FieldMD(lay, torch.tensor(wmd["emb"]), 46, sigma=0.5, init_ind=3, dt=0.3, gamma1=0.2, gamma2=1.25)
+        yk = torch.randn(4096, 46) * 60
+        cpu["sde_cal_f_K4096_evals_per_s"] = 4096 / cpu_time(lambda: fmd.f(torch.tensor(0.3), yk))
+        aux["reference_cpu_secondary"] = cpu
+    except Exception as exc:
+        aux["reference_cpu_secondary_error"] = repr(exc)
     # ---- other BASELINE configs, measured briefly (reported, not the headline)
     try:
         from idff_b200.weights import PackedWeights
