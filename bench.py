@@ -169,7 +169,7 @@ def run_ours(args):
 
     pw = PackedWeights.from_npz(os.path.join(GOLDEN, "weights_checkerboard.npz"), device=dev)
     model = fields.CustomNetModel(pw, SIGMA, *GAMMAS)
-    model.impl = {"auto": 0, "generic": 1, "fused": 2, "tensor": 3}[args.kernel]
+    model.impl = {"auto": 0, "generic": 1, "fused": 2, "tensor": 3, "tensor16": 5}[args.kernel]
     shard = launcher.ShardedSampler(model, 2, dev, base_seed=1000)
     x0 = shard.x0(n_total)
     ts = torch.linspace(0, 1, nfe + 1)
@@ -246,14 +246,25 @@ def run_ours(args):
         achieved = flops / (k_ms * 1e-3) / 1e12
         fma_peak = 148 * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
         bf16 = peaks.get("bf16_tflops", 1590.0)
-        if args.kernel in ("auto", "tensor"):
+        if args.kernel in ("auto", "tensor16"):
+            # tcgen05 kind::f16, three MMA products per algorithmic product (3xFP16 split): peak = fp16 dense / 3
+            tpeak = bf16 / 3.0
+            roofline = {"bound": "tensor", "kernel": "k_tc16: tcgen05 3xFP16 sampler (whole rk4 solve, one launch)",
+                        "achieved": achieved, "peak": tpeak, "unit": "TFLOP/s", "frac": achieved / tpeak, "traffic": None,
+                        "peak_source": f"{peak_src} bf16/fp16 dense {bf16:.0f} TFLOP/s (MEASURED_PEAKS.json, burst) / 3 "
+                                       "(hi*hi + hi*lo + lo*hi products); algorithmic FLOPs = 2F per MLP pass, 2n passes per "
+                                       "interior order-n evaluation (SURVEY.md section 8d)",
+                        "algorithmic_flops_per_launch": flops, "kernel_ms": k_ms,
+                        "kernel_share_of_step": k_ms * args.steps / total_ms,
+                        "executed_tensor_tflops": 3.0 * achieved, "frac_of_bf16_tensor_peak": 3.0 * achieved / bf16,
+                        "frac_of_fp32_fma_peak": achieved / fma_peak}
+        elif args.kernel == "tensor":
             # tcgen05 kind::tf32, three MMAs per product (3xTF32): algorithmic fp32 FLOP peak = tf32 dense / 3
             tpeak = bf16 / 2.0 / 3.0
             roofline = {"bound": "tensor", "kernel": "k_tc: tcgen05 3xTF32 sampler (whole rk4 solve, one launch)",
                         "achieved": achieved, "peak": tpeak, "unit": "TFLOP/s", "frac": achieved / tpeak, "traffic": None,
                         "peak_source": f"{peak_src} bf16 dense {bf16:.0f} TFLOP/s (MEASURED_PEAKS.json, burst) / 2 (tf32 rate) / 3 "
-                                       "(hi*hi + lo*hi + hi*lo passes); the kernel is bound by the shared-memory operand reads of "
-                                       "the M=128 x N=64 x K=8 MMAs (profiles/README.md), not by the tensor pipe",
+                                       "(hi*hi + lo*hi + hi*lo passes)",
                         "algorithmic_flops_per_launch": flops, "kernel_ms": k_ms,
                         "kernel_share_of_step": k_ms * args.steps / total_ms,
                         "executed_tensor_tflops": 3.0 * achieved, "frac_of_bf16_tensor_peak": 3.0 * achieved / bf16,
@@ -335,7 +346,7 @@ def aux_measurements(dev, pw, model, peaks):
                       "frac_ex2_peak": 3.0 * n * n / s / (148 * 16 * peaks.get("sm_max_mhz", 1965.0) * 1e6)}
     from idff_b200 import fields
     xs = torch.randn(1 << 21, 2, device=dev, generator=g) / 1.5
-    for name, impl in (("fma_ffma2", 2), ("tensor_3xtf32", 3)):
+    for name, impl in (("fma_ffma2", 2), ("tensor_3xtf32", 3), ("tensor_3xfp16", 5)):
         m2 = fields.CustomNetModel(pw, SIGMA, *GAMMAS)
         m2.impl = impl
         sweep = {}
@@ -426,7 +437,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--particles", type=int, default=1 << 24, help="particles per GPU")
     ap.add_argument("--nfe", type=int, default=2)
-    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fused", "tensor"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fused", "tensor", "tensor16"])
     ap.add_argument("--cpu-particles", type=int, default=65536)
     ap.add_argument("--no-aux", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

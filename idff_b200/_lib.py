@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libidff_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 IDFF_FIELD_MOMENTUM, IDFF_FIELD_SCOREHEAD, IDFF_FIELD_CFM, IDFF_FIELD_MD = 0, 1, 2, 3
-IDFF_IMPL_AUTO, IDFF_IMPL_GENERIC, IDFF_IMPL_FUSED, IDFF_IMPL_TENSOR, IDFF_IMPL_LAYERED = 0, 1, 2, 3, 4
+IDFF_IMPL_AUTO, IDFF_IMPL_GENERIC, IDFF_IMPL_FUSED, IDFF_IMPL_TENSOR, IDFF_IMPL_LAYERED, IDFF_IMPL_TENSOR16 = 0, 1, 2, 3, 4, 5
 
 
 class IdffError(RuntimeError):
@@ -39,6 +39,8 @@ SIGNATURES = {
     "idff_weights_destroy": (C.c_int, [_vp]),
     "idff_stage_scalars": (C.c_int, [_PP, _f32, _vp]),
     "idff_debug_tensor_stamps": (C.c_int, [_vp]),
+    "idff_debug_tensor16_stamps": (C.c_int, [_vp]),
+    "idff_tensor16_nonfinite": (C.c_int, [_vp]),
     "idff_mlp_forward": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp]),
     "idff_field_eval": (C.c_int, [_vp, _PP, _f32, _vp, _vp, _vp, _i64, _vp]),
     "idff_sample_rk4": (C.c_int, [_vp, _PP, _vp, _vp, _i32, _vp, _vp, _i64, _vp]),
@@ -97,6 +99,13 @@ def require_cuda(t: torch.Tensor, name: str):
         raise IdffError(f"{name} must be a CUDA tensor: idff_b200 has no CPU path")
     if t.dtype != torch.float32:
         raise IdffError(f"{name} must be float32, got {t.dtype}")
+
+
+def tensor16_nonfinite() -> int:
+    """Particle-evaluations of the 3xFP16 tensor kernel whose field value was not finite (fp16 operand overflow)."""
+    c = C.c_uint64(0)
+    check(lib().idff_tensor16_nonfinite(C.byref(c)), "idff_tensor16_nonfinite")
+    return int(c.value)
 
 
 def launch_count() -> int:

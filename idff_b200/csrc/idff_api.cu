@@ -34,6 +34,15 @@ int tensor_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, con
 
 int tensor_debug_stamps(long long* h_out, int n);
 
+// idff_sampler_tc16.cu
+bool tensor16_supports(const idff_weights_t* w, const idff_field_params_t* p);
+int tensor16_field_eval(const idff_weights_t* w, const idff_field_params_t* p, float t, const float* d_x, const float* d_x0,
+                        float* d_out, int64_t N, void* stream);
+int tensor16_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, const float* d_x0, const Stage* stages,
+                        const float* dts, int n_iv, float* d_out_final, float* d_out_traj, int64_t N, void* stream);
+int tensor16_debug_stamps(long long* h_out, int n);
+int tensor16_nonfinite(unsigned long long* h_out);
+
 // idff_sampler_wide.cu
 bool wide_supports(const idff_weights_t* w, const idff_field_params_t* p);
 int wide_field_eval(const idff_weights_t* w, const idff_field_params_t* p, float t, const float* d_x, const float* d_x0,
@@ -73,6 +82,19 @@ extern "C" int idff_debug_tensor_stamps(int64_t* h_out32) {
   return tensor_debug_stamps(reinterpret_cast<long long*>(h_out32), 32);
 }
 
+extern "C" int idff_debug_tensor16_stamps(int64_t* h_out32) {
+  IDFF_CHECK_ARG(h_out32, "idff_debug_tensor16_stamps: null pointer");
+  return tensor16_debug_stamps(reinterpret_cast<long long*>(h_out32), 32);
+}
+
+extern "C" int idff_tensor16_nonfinite(uint64_t* h_count) {
+  IDFF_CHECK_ARG(h_count, "idff_tensor16_nonfinite: null pointer");
+  unsigned long long c = 0;
+  int rc = tensor16_nonfinite(&c);
+  *h_count = (uint64_t)c;
+  return rc;
+}
+
 extern "C" int idff_stage_scalars(const idff_field_params_t* p, float t, float* h_out8) {
   IDFF_CHECK_ARG(p && h_out8, "idff_stage_scalars: null pointer");
   Stage s;
@@ -103,8 +125,9 @@ extern "C" int idff_field_eval(const idff_weights_t* w, const idff_field_params_
   if (p->impl == IDFF_IMPL_LAYERED) return wide_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
   if ((p->impl == IDFF_IMPL_TENSOR || p->impl == IDFF_IMPL_AUTO) && wide_supports(w, p) && (p->impl == IDFF_IMPL_TENSOR || N >= 2048))
     return wide_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
-  if (p->impl == IDFF_IMPL_TENSOR || (p->impl == IDFF_IMPL_AUTO && tensor_supports(w, p) && N >= 4096))
-    return tensor_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
+  if (p->impl == IDFF_IMPL_TENSOR16 || (p->impl == IDFF_IMPL_AUTO && tensor16_supports(w, p) && N >= 4096))
+    return tensor16_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
+  if (p->impl == IDFF_IMPL_TENSOR) return tensor_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
   if (p->impl == IDFF_IMPL_FUSED || (p->impl == IDFF_IMPL_AUTO && fused_supports(w, p))) {
     if (!fused_supports(w, p)) {
       set_error("idff_field_eval: the fused kernel does not support this shape/variant");
@@ -152,6 +175,8 @@ extern "C" int idff_sample_rk4(const idff_weights_t* w, const idff_field_params_
   }
   if (p->impl == IDFF_IMPL_LAYERED)
     return wide_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream);
+  if (p->impl == IDFF_IMPL_TENSOR16 || (p->impl == IDFF_IMPL_AUTO && tensor16_supports(w, p)))
+    return tensor16_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream);
   if (p->impl == IDFF_IMPL_AUTO && w->v.w == 256 && N >= 16384 && !tensor_supports(w, p)) {
     // three jets do not fit the fused tensor kernel; measured: layered tcgen05 engine 60 M vs FFMA2 kernel 48 M steps/s
     idff_field_params_t q = *p;
@@ -161,7 +186,7 @@ extern "C" int idff_sample_rk4(const idff_weights_t* w, const idff_field_params_
   }
   if ((p->impl == IDFF_IMPL_TENSOR || p->impl == IDFF_IMPL_AUTO) && wide_supports(w, p) && (p->impl == IDFF_IMPL_TENSOR || N >= 2048))
     return wide_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream);
-  if (p->impl == IDFF_IMPL_TENSOR || (p->impl == IDFF_IMPL_AUTO && tensor_supports(w, p)))
+  if (p->impl == IDFF_IMPL_TENSOR)
     return tensor_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream);
   const bool want_fused = p->impl == IDFF_IMPL_FUSED || (p->impl == IDFF_IMPL_AUTO && fused_supports(w, p));
   if (want_fused) {

@@ -70,6 +70,10 @@ struct NetView {
   // chunk c ^ (r & 7)), so one cp.async.bulk lands it ready for the UMMA descriptor.  gemm 0: W1 (rows = out units),
   // 1: W2, 2: W2^T, 3: W1^T.  hi = rn_tf32(w), lo = rn_tf32(w - hi)  (3xTF32 split).
   const float* tc_tiles;
+  // 3xFP16 operand tiles of the fused fp16 tensor kernel (w == 256 only): [gemm 0..3][m-tile 0..1][k-block 0..3][hi, lo']
+  // [128 rows x 64 fp16], each a 16 KB K-major SWIZZLE_128B image (row r at r*128 B, 16-byte chunk c = 8 halfs at chunk
+  // c ^ (r & 7)).  hi = fp16_rn(w), lo' = fp16_rn((w - hi) * 2^11).  Same gemm numbering as tc_tiles.
+  const float* tc16_tiles;
 };
 
 }  // namespace idff

@@ -1,0 +1,766 @@
+// Tensor-core IDFF sampler, 3xFP16 split (IDFF_IMPL_TENSOR16): hidden width 256, state dimension 2, up to two jets.
+//
+// Every w x w layer pass of the evaluation (forward jets and reverse sweep) runs on tcgen05.mma kind::f16 with fp32
+// accumulation in tensor memory.  An fp32 value v is carried as two fp16 numbers
+//     hi = fp16_rn(v),   lo' = fp16_rn((v - hi) * 2^11)
+// (the remainder is scaled back into the normal fp16 range, so 22 significant bits survive even for tiny v), and
+//     D = W_hi*X_hi  +  2^-11 * (W_hi*X_lo' + W_lo'*X_hi).
+// Measured on the part (profiles/microbench/tc_f16.cu): error 1.4e-7 .. 8.9e-7 of sum|terms| over K = 256 -- the level
+// of an fp32 FMA chain, better than 3xTF32 (1e-6) -- at twice the MACs per MMA instruction of kind::tf32.  fp16 has no
+// headroom above 65504: an activation, jet or adjoint beyond that turns into inf/NaN in that particle's own columns
+// only (columns never mix), so the particle's output is NaN -- loud, never silently wrong; such networks use
+// IDFF_IMPL_TENSOR (3xTF32) or IDFF_IMPL_FUSED (fp32 FMA).
+//
+// Formulation ("units on M"): D[unit][col] = sum_k W[unit][k] * X[col][k].
+//   * B operand = activations of the CTA's 64 particles, resident in shared memory (128 KB): per 64-wide k-block a
+//     256-row K-major SWIZZLE_128B tile, row = hl*128 + jet*64 + particle (hl 0 = hi, 1 = lo'); rewritten in place
+//     by the epilogue of every layer pass.
+//   * A operand = weights: 32 KB tile images [128 units x 64 k] hi | lo', pre-swizzled at handle creation, streamed by
+//     a TMA producer warp (cp.async.bulk multicast inside a CTA pair, each CTA loads one half), 3-stage ring.
+//   * per 16-wide k-step two MMAs, both at a shape the tensor core runs at full rate [measured: 128xNx16 costs 72.6
+//     cycles for any N <= 128 and 128.8 for N = 256]:
+//         [main | corr] += W_hi * [X_hi ; X_lo']      N = 256
+//                corr   += W_lo' * X_hi               N = 128
+//   * TMEM (512 columns): accumulators [main 128 | corr 128] shared by the two m-tiles, which run back to back, and
+//     the layer-2 derivative stash of the reverse sweep (2 x 128 columns).
+// A TMEM lane is one hidden unit, so the thread that reads lane n owns every jet of its particles for unit n: the SELU
+// jet / adjoint algebra is thread-local.  16 epilogue warps = 4 lane quarters x 4 particle quarters; every thread
+// serves m-tile 0 and then m-tile 1 of a pass.  The m-tile-0 epilogue computes while the m-tile-1 MMAs run, and the
+// next pass starts on k-blocks 0-1 (written by the m-tile-0 epilogue) while the m-tile-1 epilogue is still at work.
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+
+#include "idff_common.cuh"
+
+namespace idff {
+void jets_needed(const idff_field_params_t& p, int* nj, int* reverse);
+__device__ int g_tc16_misaligned = 0;
+__device__ unsigned long long g_tc16_nonfinite = 0;   // particle-evaluations whose field value was not finite
+
+namespace tch {
+
+constexpr int W = 256;
+constexpr int NP = 64;                    // particles per CTA
+constexpr int NROW = 256;                 // rows of the B operand: hl*128 + jet*64 + particle
+constexpr int NSTAGE = 3;                 // weight ring depth
+constexpr int TILE_BYTES = 32768;         // hi (16 KB) + lo' (16 KB) image of one [128 units x 64 k] fp16 weight tile
+constexpr int KB_BYTES = NROW * 128;      // B operand of one 64-wide k-block (32 KB)
+constexpr int NKB = W / 64;               // 4 k-blocks
+constexpr int ACT_BYTES = NKB * KB_BYTES;
+constexpr int NE = 512;                   // epilogue threads: warp w -> lane quarter w & 3, particle quarter w >> 2
+constexpr int NEW = NE / 32;
+constexpr int NTHREADS = NE + 64;         // + producer warp 16 + MMA warp 17
+constexpr int HP = 16;                    // particles per epilogue thread
+constexpr int TMEM_COLS = 512;
+constexpr int COL_CORR = 128, COL_STASH = 256;
+constexpr float LO_SCALE = 2048.0f, LO_INV = 1.0f / 2048.0f;
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}\n"
+      : "=r"(ok)
+      : "r"(s32(b)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  while (!mbar_try_wait(b, parity)) {
+  }
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* b, uint32_t parity) {
+  while (!mbar_try_wait(b, parity)) __nanosleep(128);
+}
+__device__ __forceinline__ void tma_load_1d_mc(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(s32(dst)),
+      "l"(src), "r"(bytes), "r"(s32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(s32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void ebar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // epilogue warps only
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+#define IDFF_R8(v, o) "=r"(v[o]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7])
+#define IDFF_I8(v, o) "r"(v[o]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3]), "r"(v[o + 4]), "r"(v[o + 5]), "r"(v[o + 6]), "r"(v[o + 7])
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : IDFF_R8(v, 0), IDFF_R8(v, 8)
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};" ::IDFF_I8(v, 0),
+               IDFF_I8(v, 8), "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// v0, v1 -> packed fp16 pairs: h2 = {lo half: hi(v0), hi half: hi(v1)}, l2 likewise for the scaled remainders
+__device__ __forceinline__ void split2(float v0, float v1, uint32_t& h2, uint32_t& l2) {
+  float f0, f1;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(v1), "f"(v0));
+  asm("{\n.reg .b16 a, b;\nmov.b32 {a, b}, %2;\ncvt.f32.f16 %0, a;\ncvt.f32.f16 %1, b;\n}\n" : "=f"(f0), "=f"(f1) : "r"(h2));
+  const float d0 = __fmul_rn(__fsub_rn(v0, f0), LO_SCALE), d1 = __fmul_rn(__fsub_rn(v1, f1), LO_SCALE);
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(l2) : "f"(d1), "f"(d0));
+}
+// low / high half of a packed pair to shared memory at [base + OFF]
+template <int OFF>
+__device__ __forceinline__ void st16_lo(uint32_t base, uint32_t packed) {
+  asm volatile("{\n.reg .b16 a, b;\nmov.b32 {a, b}, %1;\nst.shared.b16 [%0+%2], a;\n}\n" ::"r"(base), "r"(packed), "n"(OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void st16_hi(uint32_t base, uint32_t packed) {
+  asm volatile("{\n.reg .b16 a, b;\nmov.b32 {a, b}, %1;\nst.shared.b16 [%0+%2], b;\n}\n" ::"r"(base), "r"(packed), "n"(OFF) : "memory");
+}
+
+// phase timestamps (clock64) of CTA 0, first tile, evaluation 1 (an interior one): diagnostic only
+__device__ long long g_tc16_stamps[32];
+
+struct TParams {
+  NetView net;
+  int variant, D, tidx, reverse, mode;   // mode 0 eval, 1 rk4
+  long N;
+  const float* x_in;
+  const float* x0_cfm;
+  float* out;
+  float* traj;
+};
+
+struct Smem {   // byte offsets from the dynamic base, which must be 1024-byte aligned (checked at kernel entry)
+  static constexpr int act = 0;
+  static constexpr int ring = ACT_BYTES;
+  static constexpr int misc = ring + NSTAGE * TILE_BYTES;   // floats: red [16 warps][32], xs [64][2]
+  static constexpr int f_red = 0, f_xs = NEW * 32, f_end = NEW * 32 + 2 * NP;
+  static constexpr int bars = misc + f_end * 4;
+  static constexpr int total = bars + 128;
+};
+static_assert(Smem::total <= 232448, "shared memory budget");
+
+// reduce-scatter of 32 per-thread partial sums over the 32 lanes of a warp: lane L ends with the total of v[L]
+__device__ __forceinline__ void warp_reduce_scatter32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16, cnt = 16; off >= 1; off >>= 1, cnt >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < cnt; ++i) {
+      const float send = up ? v[i] : v[i + cnt];
+      const float keep = up ? v[i + cnt] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
+// the 16 particles of a thread: hi / lo' halves of jet 0 (and jet 1) into the B operand.  sw[c] = this unit's 16-byte
+// chunk address for rows with (row & 7) == c, already offset to the thread's first particle.
+template <bool TWO>
+__device__ __forceinline__ void put_all(const uint32_t (&sw)[8], const float (&v0)[HP], const float (&v1)[HP]) {
+#pragma unroll
+  for (int i = 0; i < HP; ++i) {
+    uint32_t h2, l2;
+    split2(v0[i], TWO ? v1[i] : 0.0f, h2, l2);
+    const uint32_t b = sw[i & 7] + (uint32_t)(i * 128);
+    st16_lo<0>(b, h2);
+    st16_lo<128 * 128>(b, l2);
+    if (TWO) {
+      st16_hi<64 * 128>(b, h2);
+      st16_hi<128 * 128 + 64 * 128>(b, l2);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, const __grid_constant__ Stage one) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  if ((s32(smem) & 1023u) != 0u) {   // SWIZZLE_128B operands need a 1024-byte aligned base: report and do nothing
+    if (threadIdx.x == 0) g_tc16_misaligned = 1;
+    return;
+  }
+  float* misc = reinterpret_cast<float*>(smem + Smem::misc);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
+  uint64_t* full = bars;                    // [NSTAGE]  TMA -> MMA
+  uint64_t* empty = bars + NSTAGE;          // [NSTAGE]  MMA -> TMA (both CTAs of the pair)
+  uint64_t* acc_full = bars + 2 * NSTAGE;   // MMA -> epilogue: the accumulators of the current m-tile are complete
+  uint64_t* acc_free = acc_full + 1;        // epilogue -> MMA: every thread has read its accumulators out
+  uint64_t* b_ready = acc_full + 2;         // [2] epilogue -> MMA: k-blocks 0-1 / 2-3 of the next pass are written
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 2);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_free, NE);
+    mbar_init(&b_ready[0], NE);
+    mbar_init(&b_ready[1], NE);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == NEW + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // jet-1 rows are read by the MMAs of boundary evaluations too: start from finite values
+  for (int i = tid; i < ACT_BYTES / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // barrier inits visible to the peer before any remote complete_tx / commit arrives
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t crank = cluster_ctarank();
+  // both CTAs of a pair walk the same number of tiles (the ring couples them); surplus tiles are all-padding
+  const long n_tiles = (P.N + NP - 1) / NP;
+  const long n_iter = (n_tiles + gridDim.x - 1) / gridDim.x;
+
+  const int n_eval = P.mode == 0 ? 1 : 4 * rk.n_iv;
+  auto stage_of = [&](int e) -> const Stage& { return P.mode == 0 ? one : rk.st[e]; };
+  auto heavy_of = [&](const Stage& st) { return st.kind == 2 && P.reverse; };
+
+  if (warp == NEW) {
+    // ===== TMA producer: weight tile images of every layer pass, in consumption order
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const unsigned char* tiles = reinterpret_cast<const unsigned char*>(P.net.tc16_tiles);
+      for (long it = 0; it < n_iter; ++it)
+        for (int e = 0; e < n_eval; ++e) {
+          const int ng = heavy_of(stage_of(e)) ? 4 : 2;
+          for (int g = 0; g < ng; ++g)
+            for (int t = 0; t < 2 * NKB; ++t) {   // (m-tile, k-block) tiles of gemm g are contiguous
+              mbar_wait_sleep(&empty[stage], phase ^ 1u);
+              mbar_arrive_expect_tx(&full[stage], TILE_BYTES);
+              tma_load_1d_mc(smem + Smem::ring + stage * TILE_BYTES + crank * (TILE_BYTES / 2),
+                             tiles + ((size_t)g * 2 * NKB + t) * TILE_BYTES + crank * (TILE_BYTES / 2), TILE_BYTES / 2,
+                             &full[stage], (uint16_t)3);
+              if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+            }
+        }
+    }
+  } else if (warp == NEW + 1) {
+    // ===== MMA issuer (one thread)
+    if (lane == 0) {
+      // kind::f16: D fp32 (bit 4), A = B = fp16 (format 0), K-major, N >> 3 at bit 17, M >> 4 at bit 24
+      const uint32_t idesc_256 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc_128 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t bop = s32(smem + Smem::act);
+      int stage = 0;
+      uint32_t phase = 0, fphase = 0, bphase0 = 0, bphase1 = 0;
+      for (long it = 0; it < n_iter; ++it)
+        for (int e = 0; e < n_eval; ++e) {
+          const int ng = heavy_of(stage_of(e)) ? 4 : 2;
+          for (int g = 0; g < ng; ++g) {
+            const bool mstamp = blockIdx.x == 0 && it == 0 && e == 1;
+            for (int mt = 0; mt < 2; ++mt) {
+              mbar_wait(acc_free, fphase);   // the previous m-tile's accumulators have been read out
+              fphase ^= 1u;
+              tc_fence_after();
+              for (int kb = 0; kb < NKB; ++kb) {
+                if (mt == 0 && kb == 0) {
+                  mbar_wait(&b_ready[0], bphase0);
+                  bphase0 ^= 1u;
+                  tc_fence_after();
+                  if (mstamp) g_tc16_stamps[16 + 2 * g] = clock64();
+                }
+                if (mt == 0 && kb == 2) {
+                  mbar_wait(&b_ready[1], bphase1);
+                  bphase1 ^= 1u;
+                  tc_fence_after();
+                }
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t whi = s32(smem + Smem::ring + stage * TILE_BYTES), wlo = whi + TILE_BYTES / 2;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  const uint64_t a_hi = make_desc(whi + ks * 32), a_lo = make_desc(wlo + ks * 32);
+                  const uint64_t b_w = make_desc(bop + kb * KB_BYTES + ks * 32);   // 256 rows: hi rows then lo' rows
+                  mma_f16(tmem, a_hi, b_w, idesc_256, (kb | ks) != 0);             // [main | corr] += W_hi * [X_hi ; X_lo']
+                  mma_f16(tmem + COL_CORR, a_lo, b_w, idesc_128, 1u);              // corr += W_lo' * X_hi
+                }
+                mma_commit_mc(&empty[stage], (uint16_t)3);   // frees the slot in both CTAs once these MMAs have read it
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+              }
+              mma_commit(acc_full);
+            }
+            if (mstamp) g_tc16_stamps[17 + 2 * g] = clock64();
+          }
+        }
+    }
+  } else {
+    // ===== epilogue warps: thread <-> (TMEM lane = hidden unit within the m-tile, 16 of the CTA's 64 particles)
+    const int q = warp & 3, pq = warp >> 2;
+    const int p0 = pq * HP;
+    float* red = misc + Smem::f_red;       // [16 warps][32]
+    float* sxs = misc + Smem::f_xs;        // stage input of the 64 particles, [p][2]
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + p0;
+    uint32_t aphase = 0;
+    const float third = (float)(1.0 / 3.0);
+    // integrator state of particle warp*32 + lane, held by warps 0 and 1 (2 components each)
+    float sy[2] = {0.f, 0.f}, sk1[2] = {0.f, 0.f}, sk2[2] = {0.f, 0.f}, sk3[2] = {0.f, 0.f}, sx0[2] = {0.f, 0.f};
+    float pr_tot[2] = {0.f, 0.f};
+    const int myp = (warp & 1) * 32 + lane;   // particle served by this thread in the integrator part (warps 0, 1)
+    // this thread's position inside a B-operand row for m-tile mt: k-block 2*mt + (q >> 1), 16-byte chunk, half
+    const uint32_t act_base = s32(smem + Smem::act) + (uint32_t)((q >> 1) * KB_BYTES + p0 * 128 + (lane & 7) * 2);
+    const uint32_t chunk = (uint32_t)((q & 1) * 4 + (lane >> 3));
+    auto make_sw = [&](int mt, uint32_t (&sw)[8]) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) sw[c] = act_base + (uint32_t)(mt * 2 * KB_BYTES) + ((chunk ^ (uint32_t)c) << 4);
+    };
+    // after writing one half of the B operand: make it visible to the tensor core and hand over to the MMA thread
+    auto publish = [&](int mt) {
+      fence_proxy_async();
+      mbar_arrive(&b_ready[mt]);
+    };
+    // z = main + 2^-11 * corr of this thread's unit: jet j, particles p0 .. p0+15
+    auto load_acc = [&](int j, float (&z)[HP]) {
+      uint32_t m[HP], c[HP];
+      tmem_ld16(lane_base + j * NP, m);
+      tmem_ld16(lane_base + COL_CORR + j * NP, c);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < HP; ++i) z[i] = fmaf(__uint_as_float(c[i]), LO_INV, __uint_as_float(m[i]));
+    };
+    auto wait_acc = [&]() {
+      mbar_wait(acc_full, aphase);
+      aphase ^= 1u;
+      tc_fence_after();
+    };
+    auto release_acc = [&]() {
+      tc_fence_before();
+      mbar_arrive(acc_free);
+    };
+
+    mbar_arrive(acc_free);   // nothing to read out before the very first m-tile
+    for (long it = 0; it < n_iter; ++it) {
+      const long base = (blockIdx.x + it * gridDim.x) * NP;   // may lie beyond N: an all-padding tile
+      if (warp < 2) {
+        const long row = base + myp;
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          const float v = row < P.N ? P.x_in[row * 2 + d] : 0.0f;
+          sy[d] = v;
+          sxs[2 * myp + d] = v;
+          if (P.mode == 0 && P.variant == IDFF_FIELD_CFM && P.x0_cfm) sx0[d] = row < P.N ? P.x0_cfm[row * 2 + d] : 0.0f;
+        }
+      }
+      ebar();
+#pragma unroll 1
+      for (int ev = 0; ev < n_eval; ++ev) {
+        const Stage& st = stage_of(ev);
+        const bool heavy = heavy_of(st);
+        const bool stamp = blockIdx.x == 0 && it == 0 && ev == 1 && tid == 0;
+        if (stamp) g_tc16_stamps[0] = clock64();
+        // ---- layer 1 (K = 3, computed directly): a1 and, for interior evaluations, a1' = s'(z1) * (W0 d).
+        // Every MMA of the previous evaluation is complete (this thread waited for its last accumulators).
+#pragma unroll 1
+        for (int mt = 0; mt < 2; ++mt) {
+          const int n = mt * 128 + q * 32 + lane;
+          const float wx0 = __ldg(P.net.wt0 + 0 * W + n), wx1 = __ldg(P.net.wt0 + 1 * W + n);
+          const float zb = fmaf(__ldg(P.net.wt0 + 2 * W + n), st.t, __ldg(P.net.b0 + (size_t)P.tidx * W + n));
+          const float zz1 = __ldg(P.net.zd1 + n);
+          float o0[HP], o1[HP];
+#pragma unroll
+          for (int i = 0; i < HP; ++i) {
+            const int p = p0 + i;
+            const float z = fmaf(wx1, sxs[2 * p + 1], fmaf(wx0, sxs[2 * p], zb));
+            float code, s1, E;
+            o0[i] = selu_fwd(z, code);
+            selu_decode(code, s1, E);
+            o1[i] = s1 * zz1;
+          }
+          uint32_t sw[8];
+          make_sw(mt, sw);
+          if (heavy) put_all<true>(sw, o0, o1);
+          else put_all<false>(sw, o0, o1);
+          publish(mt);
+        }
+        if (stamp) g_tc16_stamps[1] = clock64();
+        // ---- gemm 0: layer 2 forward
+#pragma unroll 1
+        for (int mt = 0; mt < 2; ++mt) {
+          const int n = mt * 128 + q * 32 + lane;
+          if (mt == 0) wait_acc();
+          if (stamp && mt == 0) g_tc16_stamps[2] = clock64();
+          float z[HP], zd[HP];
+          load_acc(0, z);
+          if (heavy) load_acc(1, zd);
+          release_acc();
+          const float bb1 = __ldg(P.net.b1 + n);
+          const uint32_t stash = lane_base + COL_STASH + mt * 128;
+          if (heavy) {   // stash z2' (raw) ...
+            uint32_t u[HP];
+#pragma unroll
+            for (int i = 0; i < HP; ++i) u[i] = __float_as_uint(zd[i]);
+            tmem_st16(stash + NP, u);
+          }
+          {
+            uint32_t u[HP];
+#pragma unroll
+            for (int i = 0; i < HP; ++i) {
+              float code, s1, E;
+              z[i] = selu_fwd(z[i] + bb1, code);     // a2
+              selu_decode(code, s1, E);
+              u[i] = __float_as_uint(code);
+              zd[i] = heavy ? s1 * zd[i] : 0.0f;     // a2'
+            }
+            if (heavy) {   // ... and the derivative code of z2
+              tmem_st16(stash, u);
+              tmem_wait_st();
+            }
+          }
+          if (mt == 0) wait_acc();   // m-tile 1 complete: every MMA of this pass has read the operand
+          uint32_t sw[8];
+          make_sw(mt, sw);
+          if (heavy) put_all<true>(sw, z, zd);
+          else put_all<false>(sw, z, zd);
+          publish(mt);
+        }
+        if (stamp) g_tc16_stamps[3] = clock64();
+        // ---- gemm 1: layer 3 forward; x1hat partial sums; adjoint seeds
+        {
+          float rsum = 0.0f;
+#pragma unroll 1
+          for (int mt = 0; mt < 2; ++mt) {
+            const int n = mt * 128 + q * 32 + lane;
+            if (mt == 0) wait_acc();
+            if (stamp && mt == 0) g_tc16_stamps[4] = clock64();
+            float z[HP], zd[HP];
+            load_acc(0, z);
+            if (heavy) load_acc(1, zd);
+            release_acc();
+            const float bb2 = __ldg(P.net.b2 + n), uu3 = __ldg(P.net.u3 + n);
+            {
+              const float w30 = __ldg(P.net.w3 + 0 * W + n), w31 = __ldg(P.net.w3 + 1 * W + n);
+              float part[32];
+#pragma unroll
+              for (int i = 0; i < HP; ++i) {
+                float code;
+                const float a = selu_fwd(z[i] + bb2, code);
+                part[2 * i] = a * w30;
+                part[2 * i + 1] = a * w31;
+                z[i] = code;
+              }
+              warp_reduce_scatter32(part, lane);
+              rsum += part[0];
+            }
+            if (heavy) {
+              const float A0 = st.c[0] * uu3, A1 = st.c[1] * uu3;
+#pragma unroll
+              for (int i = 0; i < HP; ++i) {
+                float s1, E;
+                selu_decode(z[i], s1, E);
+                z[i] = fmaf(A1 * E, zd[i], A0 * s1);   // adjoint of z3
+                zd[i] = A1 * s1;                        // adjoint of z3'
+              }
+            }
+            if (mt == 0) wait_acc();
+            if (heavy) {
+              uint32_t sw[8];
+              make_sw(mt, sw);
+              put_all<true>(sw, z, zd);
+              publish(mt);
+            }
+          }
+          red[warp * 32 + lane] = rsum;
+        }
+        if (stamp) g_tc16_stamps[5] = clock64();
+        ebar();
+        if (warp < 2) {   // x1hat of particle myp: fixed summation order over the 4 lane-quarter warps of its quarter
+          const int wq = (myp >> 4) * 4, e2 = (myp & 15) * 2;
+#pragma unroll
+          for (int d = 0; d < 2; ++d) {
+            float acc = __ldg(P.net.b3 + d);
+#pragma unroll
+            for (int w4 = 0; w4 < 4; ++w4) acc += red[(wq + w4) * 32 + e2 + d];
+            pr_tot[d] = acc;
+          }
+        }
+        if (stamp) g_tc16_stamps[6] = clock64();
+        float gg[2] = {0.f, 0.f};
+        if (heavy) {
+          // ---- gemm 2: reverse, layer 3 -> 2
+#pragma unroll 1
+          for (int mt = 0; mt < 2; ++mt) {
+            if (mt == 0) wait_acc();
+            if (stamp && mt == 0) g_tc16_stamps[7] = clock64();
+            float a0[HP], a1[HP];
+            load_acc(0, a0);
+            load_acc(1, a1);
+            release_acc();
+            {
+              const uint32_t stash = lane_base + COL_STASH + mt * 128;
+              uint32_t cd[HP], zdu[HP];
+              tmem_ld16(stash, cd);
+              tmem_ld16(stash + NP, zdu);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < HP; ++i) {
+                float s1, E;
+                selu_decode(__uint_as_float(cd[i]), s1, E);
+                a0[i] = fmaf(a1[i] * E, __uint_as_float(zdu[i]), a0[i] * s1);
+                a1[i] = a1[i] * s1;
+              }
+            }
+            if (mt == 0) wait_acc();
+            uint32_t sw[8];
+            make_sw(mt, sw);
+            put_all<true>(sw, a0, a1);
+            publish(mt);
+          }
+          if (stamp) g_tc16_stamps[8] = clock64();
+          // ---- gemm 3: reverse, layer 2 -> 1 -> x
+          float gsum = 0.0f;
+#pragma unroll 1
+          for (int mt = 0; mt < 2; ++mt) {
+            const int n = mt * 128 + q * 32 + lane;
+            if (mt == 0) wait_acc();
+            if (stamp && mt == 0) g_tc16_stamps[9] = clock64();
+            float a0[HP], a1[HP];
+            load_acc(0, a0);
+            load_acc(1, a1);
+            release_acc();
+            const float wx0 = __ldg(P.net.wt0 + 0 * W + n), wx1 = __ldg(P.net.wt0 + 1 * W + n);
+            const float zb = fmaf(__ldg(P.net.wt0 + 2 * W + n), st.t, __ldg(P.net.b0 + (size_t)P.tidx * W + n));
+            const float zz1 = __ldg(P.net.zd1 + n);
+            float part[32];
+#pragma unroll
+            for (int i = 0; i < HP; ++i) {
+              const int p = p0 + i;
+              const float z = fmaf(wx1, sxs[2 * p + 1], fmaf(wx0, sxs[2 * p], zb));
+              float code, s1, E;
+              (void)selu_fwd(z, code);
+              selu_decode(code, s1, E);
+              const float P1 = fmaf(a1[i] * E, zz1, a0[i] * s1);
+              part[2 * i] = P1 * wx0;
+              part[2 * i + 1] = P1 * wx1;
+            }
+            warp_reduce_scatter32(part, lane);
+            gsum += part[0];
+            if (mt == 0) wait_acc();   // keeps the barrier phase in step (m-tile 1 complete)
+          }
+          red[warp * 32 + lane] = gsum;
+          if (stamp) g_tc16_stamps[10] = clock64();
+          ebar();
+          if (warp < 2) {
+            const int wq = (myp >> 4) * 4, e2 = (myp & 15) * 2;
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+              float acc = 0.0f;
+#pragma unroll
+              for (int w4 = 0; w4 < 4; ++w4) acc += red[(wq + w4) * 32 + e2 + d];
+              gg[d] = acc;
+            }
+          }
+        }
+        if (stamp) g_tc16_stamps[11] = clock64();
+        // ---- combine + integrator stage update: warps 0 and 1, one particle per lane
+        if (warp < 2) {
+          const long row = base + myp;
+#pragma unroll
+          for (int d = 0; d < 2; ++d) {
+            const float pr = pr_tot[d];
+            const float x = sxs[2 * myp + d];
+            float f;
+            if (P.variant == IDFF_FIELD_CFM) {
+              if (st.kind == 0) sx0[d] = x;
+              f = __fsub_rn(pr, sx0[d]);
+            } else {
+              const float diff = __fsub_rn(pr, x);
+              if (st.kind == 0) f = diff;
+              else if (st.kind == 1) f = __fdiv_rn(diff, st.end_div);
+              else {
+                f = __fdiv_rn(__fmul_rn(st.a, diff), st.den);
+                if (heavy) f = __fadd_rn(f, gg[d]);
+              }
+            }
+            if (row < P.N && !(fabsf(f) <= 3.0e38f)) atomicAdd(&g_tc16_nonfinite, 1ull);
+            if (P.mode == 0) {
+              if (row < P.N) P.out[row * 2 + d] = f;
+            } else {
+              const int iv = ev >> 2, sg = ev & 3;
+              const float dt = rk.dt[iv], y = sy[d];
+              float xn;
+              if (sg == 0) {
+                sk1[d] = f;
+                xn = __fadd_rn(y, __fmul_rn(__fmul_rn(dt, f), third));
+              } else if (sg == 1) {
+                sk2[d] = f;
+                xn = __fadd_rn(y, __fmul_rn(dt, __fsub_rn(f, __fmul_rn(sk1[d], third))));
+              } else if (sg == 2) {
+                sk3[d] = f;
+                xn = __fadd_rn(y, __fmul_rn(dt, __fadd_rn(__fsub_rn(sk1[d], sk2[d]), f)));
+              } else {
+                const float sum = __fadd_rn(__fadd_rn(sk1[d], __fmul_rn(3.0f, __fadd_rn(sk2[d], sk3[d]))), f);
+                xn = __fadd_rn(y, __fmul_rn(__fmul_rn(sum, dt), 0.125f));
+                sy[d] = xn;
+                if (P.traj != nullptr && row < P.N) P.traj[((size_t)(iv + 1) * P.N + row) * 2 + d] = xn;
+                if (ev == n_eval - 1 && row < P.N) P.out[row * 2 + d] = xn;
+              }
+              sxs[2 * myp + d] = xn;
+            }
+          }
+        }
+        ebar();
+        if (stamp) g_tc16_stamps[12] = clock64();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer may still be multicasting into this CTA's ring / arriving on its barriers
+  if (warp == NEW + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+}
+
+}  // namespace tch
+
+int tensor16_debug_stamps(long long* h_out, int n) {
+  IDFF_CUDA(cudaMemcpyFromSymbol(h_out, tch::g_tc16_stamps, sizeof(long long) * (n < 32 ? n : 32)));
+  return IDFF_OK;
+}
+
+// number of particle-evaluations (summed over all launches of this process) whose field value came out non-finite
+int tensor16_nonfinite(unsigned long long* h_out) {
+  IDFF_CUDA(cudaMemcpyFromSymbol(h_out, g_tc16_nonfinite, sizeof(unsigned long long)));
+  return IDFF_OK;
+}
+
+bool tensor16_supports(const idff_weights_t* w, const idff_field_params_t* p) {
+  const NetView& v = w->v;
+  if (v.w != 256 || v.tc16_tiles == nullptr || p->dim != 2 || v.din != 3 || v.dout != 2) return false;
+  if (!(p->variant == IDFF_FIELD_MOMENTUM || p->variant == IDFF_FIELD_CFM)) return false;
+  int nj, rev;
+  jets_needed(*p, &nj, &rev);
+  return nj <= 2;
+}
+
+static int verify_tc16_launch(idff_weights_t* w, void* stream) {
+  if (w->tc_verified & 4) return IDFF_OK;
+  int flag = 0;
+  IDFF_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  IDFF_CUDA(cudaMemcpyFromSymbol(&flag, g_tc16_misaligned, sizeof(int)));
+  if (flag) {
+    set_error("tcgen05 kernel: dynamic shared memory is not 1024-byte aligned on this driver; use impl = IDFF_IMPL_FUSED");
+    return IDFF_EUNSUPPORTED;
+  }
+  w->tc_verified |= 4;
+  return IDFF_OK;
+}
+
+static int launch_tc16(const idff_weights_t* w, const idff_field_params_t* p, tch::TParams& P, const Rk4Table* rk,
+                       const Stage* one, void* stream) {
+  if (!tensor16_supports(w, p)) {
+    set_error("3xFP16 tensor-core sampler: needs a 3-256-256-256-2 network, dim 2, order <= 2 (momentum / CFM field)");
+    return IDFF_EUNSUPPORTED;
+  }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
+  const long tiles = (P.N + tch::NP - 1) / tch::NP;
+  int grid = (int)(tiles < sms ? tiles : sms);
+  grid = (grid + 1) & ~1;   // CTA pairs
+  static thread_local Rk4Table rk0;
+  static thread_local Stage one0;
+  const Rk4Table& rkr = rk ? *rk : rk0;
+  const Stage& oner = one ? *one : one0;
+  const int smem = tch::Smem::total;
+  IDFF_CUDA(cudaFuncSetAttribute(tch::k_tc16, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(tch::NTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  IDFF_CUDA(cudaLaunchKernelEx(&cfg, tch::k_tc16, P, rkr, oner));
+  IDFF_CUDA(cudaGetLastError());
+  count_launch();
+  return verify_tc16_launch(const_cast<idff_weights_t*>(w), stream);
+}
+
+static void fill_tparams16(const idff_weights_t* w, const idff_field_params_t* p, int mode, int64_t N, tch::TParams* P) {
+  memset(P, 0, sizeof(*P));
+  int nj, rev;
+  jets_needed(*p, &nj, &rev);
+  P->net = w->v;
+  P->variant = p->variant; P->D = p->dim; P->tidx = p->t_idx; P->reverse = rev; P->mode = mode;
+  P->N = (long)N;
+}
+
+int tensor16_field_eval(const idff_weights_t* w, const idff_field_params_t* p, float t, const float* d_x, const float* d_x0,
+                        float* d_out, int64_t N, void* stream) {
+  tch::TParams P;
+  fill_tparams16(w, p, 0, N, &P);
+  P.x_in = d_x; P.x0_cfm = d_x0; P.out = d_out;
+  Stage st;
+  make_stage(*p, t, &st);
+  return launch_tc16(w, p, P, nullptr, &st, stream);
+}
+
+int tensor16_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, const float* d_x0, const Stage* stages,
+                        const float* dts, int n_iv, float* d_out_final, float* d_out_traj, int64_t N, void* stream) {
+  static thread_local Rk4Table tab;
+  const float* src = d_x0;
+  for (int done = 0; done < n_iv; done += kMaxIntervals) {
+    const int cnt = n_iv - done < kMaxIntervals ? n_iv - done : kMaxIntervals;
+    tab.n_iv = cnt;
+    memcpy(tab.dt, dts + done, sizeof(float) * cnt);
+    memcpy(tab.st, stages + 4 * (size_t)done, sizeof(Stage) * 4 * cnt);
+    tch::TParams P;
+    fill_tparams16(w, p, 1, N, &P);
+    P.x_in = src; P.out = d_out_final;
+    P.traj = d_out_traj ? d_out_traj + (size_t)done * N * p->dim : nullptr;
+    int rc = launch_tc16(w, p, P, &tab, nullptr, stream);
+    if (rc) return rc;
+    src = d_out_final;
+  }
+  return IDFF_OK;
+}
+
+}  // namespace idff

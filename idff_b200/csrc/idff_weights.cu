@@ -4,6 +4,8 @@
 #include <atomic>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "idff_common.cuh"
 
 namespace idff {
@@ -114,6 +116,10 @@ extern "C" int idff_weights_create(const float* const* h_W, const float* const* 
   const size_t tc_floats = (size_t)4 * tc_mt * tc_kb * 2 * 128 * 32;
   off = (off + 255) & ~size_t(255);   // 1 KB alignment of the tile images
   const size_t o_tc = tc_layout ? take(tc_floats) : 0;
+  const bool tc16_layout = tc_layout && w == 256;
+  const size_t tc16_floats = (size_t)4 * 2 * 4 * 2 * 128 * 32;   // 4 gemms x 2 m-tiles x 4 k-blocks x (hi, lo') x 16 KB
+  off = (off + 255) & ~size_t(255);
+  const size_t o_tc16 = tc16_layout ? take(tc16_floats) : 0;
   std::vector<float> blob(off, 0.0f);
 
   const float *W0 = h_W[0], *W1 = h_W[1], *W2 = h_W[2], *W3 = h_W[3];
@@ -185,6 +191,25 @@ extern "C" int idff_weights_create(const float* const* h_W, const float* const* 
             }
         }
   }
+  if (tc16_layout) {
+    for (int g = 0; g < 4; ++g)
+      for (int mt = 0; mt < 2; ++mt)
+        for (int kb = 0; kb < 4; ++kb) {
+          uint16_t* hi = reinterpret_cast<uint16_t*>(&blob[o_tc16 + ((((size_t)g * 2 + mt) * 4 + kb) * 2 + 0) * 4096]);
+          uint16_t* lo = hi + 8192;
+          for (int r = 0; r < 128; ++r)
+            for (int kk = 0; kk < 64; ++kk) {
+              const int row = mt * 128 + r, col = kb * 64 + kk;   // D[row][.] = sum_col A[row][col] * act[.][col]
+              const float v = g == 0 ? W1[(size_t)row * w + col] : g == 1 ? W2[(size_t)row * w + col]
+                            : g == 2 ? W2[(size_t)col * w + row] : W1[(size_t)col * w + row];
+              const __half h = __float2half_rn(v);
+              const __half l = __float2half_rn((v - __half2float(h)) * 2048.0f);
+              const size_t o = (size_t)r * 64 + ((((kk >> 3) ^ (r & 7)) << 3) | (kk & 7));
+              memcpy(&hi[o], &h, 2);
+              memcpy(&lo[o], &l, 2);
+            }
+        }
+  }
   for (int n = 0; n < w; ++n)
     for (int d = 0; d < din - 1; ++d) blob[o_w0n + (size_t)n * (din - 1) + d] = W0[(size_t)n * din_total + d];
 
@@ -222,6 +247,7 @@ extern "C" int idff_weights_create(const float* const* h_W, const float* const* 
   v.fw2r = fused_layout ? d_blob + o_fw2r : nullptr; v.fw1r = fused_layout ? d_blob + o_fw1r : nullptr;
   v.w0n = d_blob + o_w0n;
   v.tc_tiles = tc_layout ? d_blob + o_tc : nullptr;
+  v.tc16_tiles = tc16_layout ? d_blob + o_tc16 : nullptr;
   h->d_stash = nullptr; h->stash_bytes = 0; h->tc_verified = 0;
   *out = h;
   return IDFF_OK;

@@ -42,6 +42,9 @@ extern "C" {
 #define IDFF_IMPL_FUSED 2   /* persistent warp-tiled kernel, weights streamed by TMA bulk copies */
 #define IDFF_IMPL_TENSOR 3  /* tcgen05 3xTF32: fused kernel (width 256, dim 2, order <= 2) or the layered engine (width >= 512) */
 #define IDFF_IMPL_LAYERED 4 /* force the layer-by-layer tcgen05 engine (width >= 256, dim 2, orders 1..3) */
+#define IDFF_IMPL_TENSOR16 5 /* tcgen05 3xFP16 fused kernel (width 256, dim 2, order <= 2): the default for that shape.
+                                Values beyond the fp16 range (|activation|, |jet|, |adjoint| > 65504) make that particle's
+                                output NaN and are counted by idff_tensor16_nonfinite(); use TENSOR or FUSED for such nets */
 
 typedef struct idff_weights idff_weights_t; /* opaque: packed device copies of one 4-layer SELU MLP */
 
@@ -91,6 +94,11 @@ int idff_stage_scalars(const idff_field_params_t* p, float t, float* h_out8);
  * [0..12] epilogue warp 0 (layer-1 start, publish, accumulator-ready / publish of every layer pass, reductions,
  * stage update), [16+2g], [17+2g] MMA issue start / commit of layer pass g.  h_out32: 32 int64 on the host. */
 int idff_debug_tensor_stamps(int64_t* h_out32);
+/* same for the last IDFF_IMPL_TENSOR16 launch */
+int idff_debug_tensor16_stamps(int64_t* h_out32);
+/* Diagnostic: particle-evaluations of IDFF_IMPL_TENSOR16 launches in this process whose field value was not finite
+ * (fp16 operand overflow or non-finite input); synchronises the device. */
+int idff_tensor16_nonfinite(uint64_t* h_count);
 
 /* ---- a8 + a3..a6 fused: torchdiffeq.odeint(model, x0, t_grid, method='rk4') (3/8 rule, grid == t_grid;
  * call sites Autograd_example_order2.py:167,213,291).  h_t_grid: n_grid fp32 times on the host.

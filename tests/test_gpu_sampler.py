@@ -15,7 +15,8 @@ from make_golden_consts import GAMMAS2, GAMMAS3
 
 pytestmark = pytest.mark.gpu
 
-IMPLS = [_lib.IDFF_IMPL_GENERIC, _lib.IDFF_IMPL_FUSED, _lib.IDFF_IMPL_TENSOR, _lib.IDFF_IMPL_LAYERED, _lib.IDFF_IMPL_AUTO]
+IMPLS = [_lib.IDFF_IMPL_GENERIC, _lib.IDFF_IMPL_FUSED, _lib.IDFF_IMPL_TENSOR, _lib.IDFF_IMPL_TENSOR16, _lib.IDFF_IMPL_LAYERED,
+         _lib.IDFF_IMPL_AUTO]
 
 
 def _check_drift(got, ref32, ref64, what, med=2e-5, p999=2e-3):
@@ -65,7 +66,7 @@ def test_rk4_order3_and_cfm_vs_golden(cuda_device, impl):
             key = f"checkerboard_o3_nfe{nfe}_g{gi}"
             m = fields.CustomNetModelOrder3(pw, 0.2, *gam)
             m.impl = impl
-            if impl == _lib.IDFF_IMPL_TENSOR and gam[2] != 0:
+            if impl in (_lib.IDFF_IMPL_TENSOR, _lib.IDFF_IMPL_TENSOR16) and gam[2] != 0:
                 with pytest.raises(_lib.IdffError):
                     sampler.sample_rk4(m, x0, torch.linspace(0, 1, nfe + 1))
                 continue
@@ -157,22 +158,25 @@ def test_fused_kernel_is_selected_and_agrees_with_generic(cuda_device):
     x0 = torch.tensor(load_golden("traj2d")["x0"]).to(cuda_device)
     ts = torch.linspace(0, 1, 3)
     outs = {}
-    for impl in (_lib.IDFF_IMPL_GENERIC, _lib.IDFF_IMPL_FUSED, _lib.IDFF_IMPL_TENSOR, _lib.IDFF_IMPL_AUTO):
+    for impl in (_lib.IDFF_IMPL_GENERIC, _lib.IDFF_IMPL_FUSED, _lib.IDFF_IMPL_TENSOR, _lib.IDFF_IMPL_TENSOR16, _lib.IDFF_IMPL_AUTO):
         m = fields.CustomNetModel(pw, 0.2, 0.2, 0.2)
         m.impl = impl
         outs[impl] = sampler.sample_rk4(m, x0, ts)
-    assert torch.equal(outs[_lib.IDFF_IMPL_TENSOR], outs[_lib.IDFF_IMPL_AUTO])     # AUTO = tcgen05 kernel on this shape
+    assert torch.equal(outs[_lib.IDFF_IMPL_TENSOR16], outs[_lib.IDFF_IMPL_AUTO])   # AUTO = tcgen05 3xFP16 kernel on this shape
+    r = drift_report(outs[_lib.IDFF_IMPL_TENSOR16].cpu().numpy(), outs[_lib.IDFF_IMPL_GENERIC].cpu().numpy())
+    assert r["median"] <= 2e-5 and r["p999"] <= 1e-3, r                            # 3xFP16, truncating accumulation
+    assert _lib.tensor16_nonfinite() == 0
     r = drift_report(outs[_lib.IDFF_IMPL_FUSED].cpu().numpy(), outs[_lib.IDFF_IMPL_GENERIC].cpu().numpy())
     assert r["median"] <= 5e-6 and r["p999"] <= 1e-3, r
     r = drift_report(outs[_lib.IDFF_IMPL_TENSOR].cpu().numpy(), outs[_lib.IDFF_IMPL_GENERIC].cpu().numpy())
     assert r["median"] <= 2e-5 and r["p999"] <= 1e-3, r                            # 3xTF32, truncating accumulation
     # ragged particle counts around the 32-particle tile / 148-CTA grid
-    for impl in (_lib.IDFF_IMPL_FUSED, _lib.IDFF_IMPL_TENSOR):
+    for impl in (_lib.IDFF_IMPL_FUSED, _lib.IDFF_IMPL_TENSOR, _lib.IDFF_IMPL_TENSOR16):
         m = fields.CustomNetModel(pw, 0.2, 0.2, 0.2)
         m.impl = impl
         big = torch.randn(148 * 32 * 2 + 17, 2, device=cuda_device) / 1.5
         whole = sampler.sample_rk4(m, big, ts)
-        for n in (1, 3, 31, 32, 33, 4735, 4737):
+        for n in (1, 3, 31, 32, 33, 63, 64, 65, 4735, 4737, 9473):
             assert torch.equal(sampler.sample_rk4(m, big[:n], ts), whole[:n])
     sh = fields.CustomNetModelScoreHead(packed("scorehead", cuda_device), 0.2, 0.2, 0.2)
     sh.impl = _lib.IDFF_IMPL_FUSED
