@@ -192,20 +192,42 @@ __device__ __forceinline__ void warp_reduce_scatter32(float (&v)[32], int lane) 
   }
 }
 
-// the 16 particles of a thread: hi / lo' halves of jet 0 (and jet 1) into the B operand.  sw[c] = this unit's 16-byte
-// chunk address for rows with (row & 7) == c, already offset to the thread's first particle.
+// SELU value a, first derivative s1 and E = every higher derivative at z (ATen: z <= 0 -> (exp(z) - 1) * LA, derivative
+// LA * exp(z); z > 0 -> lambda * z, lambda, 0).  exp through ex2.approx on z * log2(e): the same MUFU.EX2 CUDA's expf is
+// built on (2 ulp), without its range-reduction scaffolding; the extra input rounding is |z| * 2^-24 relative.
+__device__ __forceinline__ void selu_jet(float z, float& a, float& s1, float& E) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(z, 0.0f) * 1.4426950408889634f));
+  const bool pos = !(z <= 0.0f);   // keeps NaN on the linear branch
+  const float t = kSeluLA * e;
+  a = pos ? z * kSeluLambda : (e - 1.0f) * kSeluLA;
+  s1 = pos ? kSeluLambda : t;
+  E = pos ? 0.0f : t;
+}
+
+// same, returning the derivative code kept in the stash: LA * exp(z) (= s1 = E) on the exp branch, -1 on the linear one
+__device__ __forceinline__ void selu_jet_code(float z, float& a, float& s1, float& code) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(z, 0.0f) * 1.4426950408889634f));
+  const bool pos = !(z <= 0.0f);
+  const float t = kSeluLA * e;
+  a = pos ? z * kSeluLambda : (e - 1.0f) * kSeluLA;
+  s1 = pos ? kSeluLambda : t;
+  code = pos ? -1.0f : t;
+}
+
+// the 16 particles of a thread: packed hi / lo' halves of jet 0 (and jet 1) into the B operand.  sw[c] = this unit's
+// 16-byte chunk address for rows with (row & 7) == c, already offset to the thread's first particle.
 template <bool TWO>
-__device__ __forceinline__ void put_all(const uint32_t (&sw)[8], const float (&v0)[HP], const float (&v1)[HP]) {
+__device__ __forceinline__ void store_all(const uint32_t (&sw)[8], const uint32_t (&hh)[HP], const uint32_t (&ll)[HP]) {
 #pragma unroll
   for (int i = 0; i < HP; ++i) {
-    uint32_t h2, l2;
-    split2(v0[i], TWO ? v1[i] : 0.0f, h2, l2);
     const uint32_t b = sw[i & 7] + (uint32_t)(i * 128);
-    st16_lo<0>(b, h2);
-    st16_lo<128 * 128>(b, l2);
+    st16_lo<0>(b, hh[i]);
+    st16_lo<128 * 128>(b, ll[i]);
     if (TWO) {
-      st16_hi<64 * 128>(b, h2);
-      st16_hi<128 * 128 + 64 * 128>(b, l2);
+      st16_hi<64 * 128>(b, hh[i]);
+      st16_hi<128 * 128 + 64 * 128>(b, ll[i]);
     }
   }
 }
@@ -224,7 +246,8 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
   uint64_t* acc_full = bars + 2 * NSTAGE;   // MMA -> epilogue: the accumulators of the current m-tile are complete
   uint64_t* acc_free = acc_full + 1;        // epilogue -> MMA: every thread has read its accumulators out
   uint64_t* b_ready = acc_full + 2;         // [2] epilogue -> MMA: k-blocks 0-1 / 2-3 of the next pass are written
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
+  uint64_t* kfree = acc_full + 4;           // MMA -> epilogue: k-blocks 0-1 have been read by both m-tiles of this pass
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 5);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
@@ -233,6 +256,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
       mbar_init(&empty[s], 2);
     }
     mbar_init(acc_full, 1);
+    mbar_init(kfree, 1);
     mbar_init(acc_free, NE);
     mbar_init(&b_ready[0], NE);
     mbar_init(&b_ready[1], NE);
@@ -326,6 +350,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
                 }
                 mma_commit_mc(&empty[stage], (uint16_t)3);   // frees the slot in both CTAs once these MMAs have read it
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+                if (mt == 1 && kb == 1) mma_commit(kfree);   // the m-tile-0 epilogue may overwrite k-blocks 0-1
               }
               mma_commit(acc_full);
             }
@@ -384,6 +409,11 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
       aphase ^= 1u;
       tc_fence_after();
     };
+    uint32_t kphase = 0;
+    auto wait_kfree = [&]() {
+      mbar_wait(kfree, kphase);
+      kphase ^= 1u;
+    };
     auto release_acc = [&]() {
       tc_fence_before();
       mbar_arrive(acc_free);
@@ -417,20 +447,18 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
           const float wx0 = __ldg(P.net.wt0 + 0 * W + n), wx1 = __ldg(P.net.wt0 + 1 * W + n);
           const float zb = fmaf(__ldg(P.net.wt0 + 2 * W + n), st.t, __ldg(P.net.b0 + (size_t)P.tidx * W + n));
           const float zz1 = __ldg(P.net.zd1 + n);
-          float o0[HP], o1[HP];
+          uint32_t hh[HP], ll[HP];
 #pragma unroll
           for (int i = 0; i < HP; ++i) {
-            const int p = p0 + i;
-            const float z = fmaf(wx1, sxs[2 * p + 1], fmaf(wx0, sxs[2 * p], zb));
-            float code, s1, E;
-            o0[i] = selu_fwd(z, code);
-            selu_decode(code, s1, E);
-            o1[i] = s1 * zz1;
+            const float2 xp = *reinterpret_cast<const float2*>(sxs + 2 * (p0 + i));
+            float a, s1, E;
+            selu_jet(fmaf(wx1, xp.y, fmaf(wx0, xp.x, zb)), a, s1, E);
+            split2(a, s1 * zz1, hh[i], ll[i]);
           }
           uint32_t sw[8];
           make_sw(mt, sw);
-          if (heavy) put_all<true>(sw, o0, o1);
-          else put_all<false>(sw, o0, o1);
+          if (heavy) store_all<true>(sw, hh, ll);
+          else store_all<false>(sw, hh, ll);
           publish(mt);
         }
         if (stamp) g_tc16_stamps[1] = clock64();
@@ -438,7 +466,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
 #pragma unroll 1
         for (int mt = 0; mt < 2; ++mt) {
           const int n = mt * 128 + q * 32 + lane;
-          if (mt == 0) wait_acc();
+          wait_acc();
           if (stamp && mt == 0) g_tc16_stamps[2] = clock64();
           float z[HP], zd[HP];
           if (heavy) {
@@ -450,32 +478,34 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
           release_acc();
           const float bb1 = __ldg(P.net.b1 + n);
           const uint32_t stash = lane_base + COL_STASH + mt * 128;
-          if (heavy) {   // stash z2' (raw) ...
+          uint32_t hh[HP], ll[HP];
+          if (heavy) {   // stash z2' (raw) and the derivative code of z2
             uint32_t u[HP];
 #pragma unroll
             for (int i = 0; i < HP; ++i) u[i] = __float_as_uint(zd[i]);
             tmem_st16(stash + NP, u);
-          }
-          {
-            uint32_t u[HP];
 #pragma unroll
             for (int i = 0; i < HP; ++i) {
-              float code, s1, E;
-              z[i] = selu_fwd(z[i] + bb1, code);     // a2
-              selu_decode(code, s1, E);
+              float a, s1, code;
+              selu_jet_code(z[i] + bb1, a, s1, code);
               u[i] = __float_as_uint(code);
-              zd[i] = heavy ? s1 * zd[i] : 0.0f;     // a2'
+              split2(a, s1 * zd[i], hh[i], ll[i]);
             }
-            if (heavy) {   // ... and the derivative code of z2
-              tmem_st16(stash, u);
-              tmem_wait_st();
+            tmem_st16(stash, u);
+            tmem_wait_st();
+          } else {
+#pragma unroll
+            for (int i = 0; i < HP; ++i) {
+              float a, s1, E;
+              selu_jet(z[i] + bb1, a, s1, E);
+              split2(a, 0.0f, hh[i], ll[i]);
             }
           }
-          if (mt == 0) wait_acc();   // m-tile 1 complete: every MMA of this pass has read the operand
+          if (mt == 0) wait_kfree();   // k-blocks 0-1 have been read by every MMA of this pass
           uint32_t sw[8];
           make_sw(mt, sw);
-          if (heavy) put_all<true>(sw, z, zd);
-          else put_all<false>(sw, z, zd);
+          if (heavy) store_all<true>(sw, hh, ll);
+          else store_all<false>(sw, hh, ll);
           publish(mt);
         }
         if (stamp) g_tc16_stamps[3] = clock64();
@@ -485,7 +515,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
 #pragma unroll 1
           for (int mt = 0; mt < 2; ++mt) {
             const int n = mt * 128 + q * 32 + lane;
-            if (mt == 0) wait_acc();
+            wait_acc();
             if (stamp && mt == 0) g_tc16_stamps[4] = clock64();
             float z[HP], zd[HP];
             if (heavy) {
@@ -496,36 +526,35 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
             }
             release_acc();
             const float bb2 = __ldg(P.net.b2 + n), uu3 = __ldg(P.net.u3 + n);
+            const float w30 = __ldg(P.net.w3 + 0 * W + n), w31 = __ldg(P.net.w3 + 1 * W + n);
+            const float A0 = st.c[0] * uu3, A1 = st.c[1] * uu3;
             {
-              const float w30 = __ldg(P.net.w3 + 0 * W + n), w31 = __ldg(P.net.w3 + 1 * W + n);
               float part[32];
 #pragma unroll
               for (int i = 0; i < HP; ++i) {
-                float code;
-                const float a = selu_fwd(z[i] + bb2, code);
+                float a, s1, E;
+                selu_jet(z[i] + bb2, a, s1, E);
                 part[2 * i] = a * w30;
                 part[2 * i + 1] = a * w31;
-                z[i] = code;
+                if (heavy) {   // adjoints of z3 and z3', in place
+                  z[i] = fmaf(A1 * E, zd[i], A0 * s1);
+                  zd[i] = A1 * s1;
+                }
               }
               warp_reduce_scatter32(part, lane);
               rsum += part[0];
             }
             if (heavy) {
-              const float A0 = st.c[0] * uu3, A1 = st.c[1] * uu3;
+              uint32_t hh[HP], ll[HP];
 #pragma unroll
-              for (int i = 0; i < HP; ++i) {
-                float s1, E;
-                selu_decode(z[i], s1, E);
-                z[i] = fmaf(A1 * E, zd[i], A0 * s1);   // adjoint of z3
-                zd[i] = A1 * s1;                        // adjoint of z3'
-              }
-            }
-            if (mt == 0) wait_acc();
-            if (heavy) {
+              for (int i = 0; i < HP; ++i) split2(z[i], zd[i], hh[i], ll[i]);
+              if (mt == 0) wait_kfree();
               uint32_t sw[8];
               make_sw(mt, sw);
-              put_all<true>(sw, z, zd);
+              store_all<true>(sw, hh, ll);
               publish(mt);
+            } else if (mt == 0) {
+              wait_kfree();
             }
           }
           red[warp * 32 + lane] = rsum;
@@ -548,12 +577,13 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
           // ---- gemm 2: reverse, layer 3 -> 2
 #pragma unroll 1
           for (int mt = 0; mt < 2; ++mt) {
-            if (mt == 0) wait_acc();
+            wait_acc();
             if (stamp && mt == 0) g_tc16_stamps[7] = clock64();
             float a0[HP], a1[HP];
             load_acc(0, a0);
             load_acc(1, a1);
             release_acc();
+            uint32_t hh[HP], ll[HP];
             {
               const uint32_t stash = lane_base + COL_STASH + mt * 128;
               uint32_t cd[HP], zdu[HP];
@@ -562,16 +592,15 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
               tmem_wait_ld();
 #pragma unroll
               for (int i = 0; i < HP; ++i) {
-                float s1, E;
-                selu_decode(__uint_as_float(cd[i]), s1, E);
-                a0[i] = fmaf(a1[i] * E, __uint_as_float(zdu[i]), a0[i] * s1);
-                a1[i] = a1[i] * s1;
+                const float code = __uint_as_float(cd[i]);
+                const float s1 = code < 0.0f ? kSeluLambda : code, E = code < 0.0f ? 0.0f : code;
+                split2(fmaf(a1[i] * E, __uint_as_float(zdu[i]), a0[i] * s1), a1[i] * s1, hh[i], ll[i]);
               }
             }
-            if (mt == 0) wait_acc();
+            if (mt == 0) wait_kfree();
             uint32_t sw[8];
             make_sw(mt, sw);
-            put_all<true>(sw, a0, a1);
+            store_all<true>(sw, hh, ll);
             publish(mt);
           }
           if (stamp) g_tc16_stamps[8] = clock64();
@@ -580,7 +609,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
 #pragma unroll 1
           for (int mt = 0; mt < 2; ++mt) {
             const int n = mt * 128 + q * 32 + lane;
-            if (mt == 0) wait_acc();
+            wait_acc();
             if (stamp && mt == 0) g_tc16_stamps[9] = clock64();
             float a0[HP], a1[HP];
             load_acc(0, a0);
@@ -592,18 +621,16 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
             float part[32];
 #pragma unroll
             for (int i = 0; i < HP; ++i) {
-              const int p = p0 + i;
-              const float z = fmaf(wx1, sxs[2 * p + 1], fmaf(wx0, sxs[2 * p], zb));
-              float code, s1, E;
-              (void)selu_fwd(z, code);
-              selu_decode(code, s1, E);
+              const float2 xp = *reinterpret_cast<const float2*>(sxs + 2 * (p0 + i));
+              float a, s1, E;
+              selu_jet(fmaf(wx1, xp.y, fmaf(wx0, xp.x, zb)), a, s1, E);
               const float P1 = fmaf(a1[i] * E, zz1, a0[i] * s1);
               part[2 * i] = P1 * wx0;
               part[2 * i + 1] = P1 * wx1;
             }
             warp_reduce_scatter32(part, lane);
             gsum += part[0];
-            if (mt == 0) wait_acc();   // keeps the barrier phase in step (m-tile 1 complete)
+            if (mt == 0) wait_kfree();   // keeps the barrier phase in step
           }
           red[warp * 32 + lane] = gsum;
           if (stamp) g_tc16_stamps[10] = clock64();
