@@ -12,9 +12,9 @@
 // IDFF_IMPL_TENSOR (3xTF32) or IDFF_IMPL_FUSED (fp32 FMA).
 //
 // Formulation ("units on M"): D[unit][col] = sum_k W[unit][k] * X[col][k].
-//   * B operand = activations of the CTA's 64 particles, resident in shared memory (128 KB): per 64-wide k-block a
-//     256-row K-major SWIZZLE_128B tile, row = hl*128 + jet*64 + particle (hl 0 = hi, 1 = lo'); rewritten in place
-//     by the epilogue of every layer pass.
+//   * B operand = activations of the CTA's 64 particles, resident in shared memory (128 KB): per 32-wide k-block a
+//     256-row K-major SWIZZLE_64B tile (64-byte rows), row = hl*128 + jet*64 + particle (hl 0 = hi, 1 = lo');
+//     rewritten in place by the epilogue of every layer pass with conflict-free 64-bit stores (4 units each).
 //   * A operand = weights: 32 KB tile images [128 units x 64 k] hi | lo', pre-swizzled at handle creation, streamed by
 //     a TMA producer warp (cp.async.bulk multicast inside a CTA pair, each CTA loads one half), 3-stage ring.
 //   * per 16-wide k-step two MMAs, both at a shape the tensor core runs at full rate [measured: 128xNx16 costs 72.6
@@ -23,9 +23,12 @@
 //                corr   += W_lo' * X_hi               N = 128
 //   * TMEM (512 columns): accumulators [main 128 | corr 128] shared by the two m-tiles, which run back to back, and
 //     the layer-2 derivative stash of the reverse sweep (2 x 128 columns).
-// A TMEM lane is one hidden unit, so the thread that reads lane n owns every jet of its particles for unit n: the SELU
-// jet / adjoint algebra is thread-local.  16 epilogue warps = 4 lane quarters x 4 particle quarters; every thread
-// serves m-tile 0 and then m-tile 1 of a pass.  The m-tile-0 epilogue computes while the m-tile-1 MMAs run, and the
+// A TMEM lane is one hidden unit.  The epilogue reads the accumulators with tcgen05.ld.16x128b: thread T of a warp gets
+// lanes {g, g+8, g+16, g+24} (g = T/4) of its lane quarter and columns {T%4 + 4r}; the weight-tile rows are permuted at
+// handle creation so that these four lanes are four CONSECUTIVE units 4g..4g+3, i.e. one 8-byte group of the next
+// pass's K-major operand row.  A thread therefore owns every jet of 4 units x 4 particles: the SELU jet / adjoint
+// algebra is thread-local, and sums over units are 3 in-thread adds + a 3-step shuffle.  16 epilogue warps = 4 lane
+// quarters x 4 particle quarters; every thread serves m-tile 0 and then m-tile 1 of a pass.  The m-tile-0 epilogue computes while the m-tile-1 MMAs run, and the
 // next pass starts on k-blocks 0-1 (written by the m-tile-0 epilogue) while the m-tile-1 epilogue is still at work.
 #include <cuda_fp16.h>
 
@@ -45,9 +48,9 @@ constexpr int NP = 64;                    // particles per CTA
 constexpr int NROW = 256;                 // rows of the B operand: hl*128 + jet*64 + particle
 constexpr int NSTAGE = 3;                 // weight ring depth
 constexpr int TILE_BYTES = 32768;         // hi (16 KB) + lo' (16 KB) image of one [128 units x 64 k] fp16 weight tile
-constexpr int KB_BYTES = NROW * 128;      // B operand of one 64-wide k-block (32 KB)
-constexpr int NKB = W / 64;               // 4 k-blocks
-constexpr int ACT_BYTES = NKB * KB_BYTES;
+constexpr int KB_BYTES = NROW * 64;       // B operand of one 32-wide k-block: 256 rows x 64 B (16 KB)
+constexpr int NKB = W / 64;               // 4 weight k-blocks of 64 (= 8 operand k-blocks of 32)
+constexpr int ACT_BYTES = (W / 32) * KB_BYTES;
 constexpr int NE = 512;                   // epilogue threads: warp w -> lane quarter w & 3, particle quarter w >> 2
 constexpr int NEW = NE / 32;
 constexpr int NTHREADS = NE + 64;         // + producer warp 16 + MMA warp 17
@@ -114,6 +117,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
 }
+// K-major SWIZZLE_64B (64-byte rows, 8-row groups 512 B apart): the activation operand
+__device__ __forceinline__ uint64_t make_desc64(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)4 << 61);
+}
 __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
@@ -145,14 +153,21 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t& h2, uint32_
   const float d0 = __fmul_rn(__fsub_rn(v0, f0), LO_SCALE), d1 = __fmul_rn(__fsub_rn(v1, f1), LO_SCALE);
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(l2) : "f"(d1), "f"(d0));
 }
-// low / high half of a packed pair to shared memory at [base + OFF]
-template <int OFF>
-__device__ __forceinline__ void st16_lo(uint32_t base, uint32_t packed) {
-  asm volatile("{\n.reg .b16 a, b;\nmov.b32 {a, b}, %1;\nst.shared.b16 [%0+%2], a;\n}\n" ::"r"(base), "r"(packed), "n"(OFF) : "memory");
+// tcgen05.ld/st.16x128b.x4: 16 TMEM lanes x 16 columns; thread T: register 2r + h <-> lane T/4 + 8h, column 4r + T%4
+// [layout verified on the part: profiles/microbench/tmem_shapes.cu]
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.16x128b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.16x128b.x4.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::"r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(taddr)
+               : "memory");
 }
 template <int OFF>
-__device__ __forceinline__ void st16_hi(uint32_t base, uint32_t packed) {
-  asm volatile("{\n.reg .b16 a, b;\nmov.b32 {a, b}, %1;\nst.shared.b16 [%0+%2], b;\n}\n" ::"r"(base), "r"(packed), "n"(OFF) : "memory");
+__device__ __forceinline__ void st64(uint32_t base, uint32_t w0, uint32_t w1) {
+  asm volatile("st.shared.v2.b32 [%0+%3], {%1, %2};" ::"r"(base), "r"(w0), "r"(w1), "n"(OFF) : "memory");
 }
 
 // phase timestamps (clock64) of CTA 0, first tile, evaluation 1 (an interior one): diagnostic only
@@ -216,21 +231,29 @@ __device__ __forceinline__ void selu_jet_code(float z, float& a, float& s1, floa
   code = pos ? -1.0f : t;
 }
 
-// the 16 particles of a thread: packed hi / lo' halves of jet 0 (and jet 1) into the B operand.  sw[c] = this unit's
-// 16-byte chunk address for rows with (row & 7) == c, already offset to the thread's first particle.
-template <bool TWO>
-__device__ __forceinline__ void store_all(const uint32_t (&sw)[8], const uint32_t (&hh)[HP], const uint32_t (&ll)[HP]) {
+// A thread's 16 values of one jet are indexed e = 8*ld + 2*r + h: unit 2*ld + h (of its 4 consecutive units), particle
+// r (of its 4).  pack_jet: hi / lo' fp16 words of the unit pairs (0,1) and (2,3) for each particle: hw[2r + ld].
+__device__ __forceinline__ void pack_jet(const float (&v)[HP], uint32_t (&hw)[8], uint32_t (&lw)[8]) {
 #pragma unroll
-  for (int i = 0; i < HP; ++i) {
-    const uint32_t b = sw[i & 7] + (uint32_t)(i * 128);
-    st16_lo<0>(b, hh[i]);
-    st16_lo<128 * 128>(b, ll[i]);
-    if (TWO) {
-      st16_hi<64 * 128>(b, hh[i]);
-      st16_hi<128 * 128 + 64 * 128>(b, ll[i]);
-    }
+  for (int ld = 0; ld < 2; ++ld)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) split2(v[8 * ld + 2 * r], v[8 * ld + 2 * r + 1], hw[2 * r + ld], lw[2 * r + ld]);
+}
+// 8-byte stores of one jet (JET) into the thread's four particle rows: hi rows at +0, lo' rows 128 rows further.
+// sa[0] / sa[1] = swizzled address of the thread's 8-byte group for even / odd r, first particle, jet 0, hi.
+template <int JET>
+__device__ __forceinline__ void store_jet(const uint32_t (&sa)[2], const uint32_t (&hw)[8], const uint32_t (&lw)[8]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    // (r & 1) is a compile-time constant after unrolling
+    if (r == 0) { st64<JET * 4096 + 0 * 256>(sa[0], hw[0], hw[1]); st64<8192 + JET * 4096 + 0 * 256>(sa[0], lw[0], lw[1]); }
+    if (r == 1) { st64<JET * 4096 + 1 * 256>(sa[1], hw[2], hw[3]); st64<8192 + JET * 4096 + 1 * 256>(sa[1], lw[2], lw[3]); }
+    if (r == 2) { st64<JET * 4096 + 2 * 256>(sa[0], hw[4], hw[5]); st64<8192 + JET * 4096 + 2 * 256>(sa[0], lw[4], lw[5]); }
+    if (r == 3) { st64<JET * 4096 + 3 * 256>(sa[1], hw[6], hw[7]); st64<8192 + JET * 4096 + 3 * 256>(sa[1], lw[6], lw[7]); }
   }
 }
+// per-unit constant c[0..3] of the thread's four units for element e
+#define IDFF_UC(c, e) ((((e) >> 3) * 2 + ((e) & 1)) == 0 ? (c).x : (((e) >> 3) * 2 + ((e) & 1)) == 1 ? (c).y : (((e) >> 3) * 2 + ((e) & 1)) == 2 ? (c).z : (c).w)
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, const __grid_constant__ Stage one) {
@@ -316,31 +339,42 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
         for (int e = 0; e < n_eval; ++e) {
           const bool heavy = heavy_of(stage_of(e));
           const int ng = heavy ? 4 : 2;
+          if (blockIdx.x == 0 && it == 0 && e == 1)
+            for (int i = 24; i < 29; ++i) g_tc16_stamps[i] = 0;
           for (int g = 0; g < ng; ++g) {
             const bool mstamp = blockIdx.x == 0 && it == 0 && e == 1;
             for (int mt = 0; mt < 2; ++mt) {
+              long long c0 = mstamp ? clock64() : 0;
               mbar_wait(acc_free, fphase);   // the previous m-tile's accumulators have been read out
               fphase ^= 1u;
               tc_fence_after();
+              if (mstamp) g_tc16_stamps[24 + mt] += clock64() - c0;
               for (int kb = 0; kb < NKB; ++kb) {
                 if (mt == 0 && kb == 0) {
+                  c0 = mstamp ? clock64() : 0;
                   mbar_wait(&b_ready[0], bphase0);
                   bphase0 ^= 1u;
                   tc_fence_after();
                   if (mstamp) g_tc16_stamps[16 + 2 * g] = clock64();
+                  if (mstamp) g_tc16_stamps[26] += clock64() - c0;
                 }
                 if (mt == 0 && kb == 2) {
+                  c0 = mstamp ? clock64() : 0;
                   mbar_wait(&b_ready[1], bphase1);
                   bphase1 ^= 1u;
                   tc_fence_after();
+                  if (mstamp) g_tc16_stamps[27] += clock64() - c0;
                 }
+                c0 = mstamp ? clock64() : 0;
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
+                if (mstamp) g_tc16_stamps[28] += clock64() - c0;
                 const uint32_t whi = s32(smem + Smem::ring + stage * TILE_BYTES), wlo = whi + TILE_BYTES / 2;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                   const uint64_t a_hi = make_desc(whi + ks * 32), a_lo = make_desc(wlo + ks * 32);
-                  const uint64_t b_w = make_desc(bop + kb * KB_BYTES + ks * 32);   // 256 rows: hi rows then lo' rows
+                  // operand k-block (32 wide) 2*kb + ks/2, 32-byte half ks%2 of its 64-byte rows; 256 rows: hi then lo'
+                  const uint64_t b_w = make_desc64(bop + (2 * kb + (ks >> 1)) * KB_BYTES + (ks & 1) * 32);
                   // boundary evaluations (no stash in use) split the K sum over two accumulator sets by k-block parity:
                   // half as many truncating accumulation steps where the t == 1 branch amplifies the error x100
                   const uint32_t dset = tmem + (heavy ? 0u : (uint32_t)((kb & 1) * COL_STASH));
@@ -359,35 +393,46 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
         }
     }
   } else {
-    // ===== epilogue warps: thread <-> (TMEM lane = hidden unit within the m-tile, 16 of the CTA's 64 particles)
+    // ===== epilogue warps: thread <-> 4 consecutive hidden units x 4 particles (see the header comment)
     const int q = warp & 3, pq = warp >> 2;
     const int p0 = pq * HP;
+    const int g = lane >> 2, c4 = lane & 3;
     float* red = misc + Smem::f_red;       // [16 warps][32]
     float* sxs = misc + Smem::f_xs;        // stage input of the 64 particles, [p][2]
-    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + p0;
-    uint32_t aphase = 0;
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + p0;   // + (16 << 16) for the upper 16 lanes
+    uint32_t aphase = 0, kphase = 0;
     const float third = (float)(1.0 / 3.0);
     // integrator state of particle warp*32 + lane, held by warps 0 and 1 (2 components each)
     float sy[2] = {0.f, 0.f}, sk1[2] = {0.f, 0.f}, sk2[2] = {0.f, 0.f}, sk3[2] = {0.f, 0.f}, sx0[2] = {0.f, 0.f};
     float pr_tot[2] = {0.f, 0.f};
     const int myp = (warp & 1) * 32 + lane;   // particle served by this thread in the integrator part (warps 0, 1)
-    // this thread's position inside a B-operand row for m-tile mt: k-block 2*mt + (q >> 1), 16-byte chunk, half
-    const uint32_t act_base = s32(smem + Smem::act) + (uint32_t)((q >> 1) * KB_BYTES + p0 * 128 + (lane & 7) * 2);
-    const uint32_t chunk = (uint32_t)((q & 1) * 4 + (lane >> 3));
-    auto make_sw = [&](int mt, uint32_t (&sw)[8]) {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) sw[c] = act_base + (uint32_t)(mt * 2 * KB_BYTES) + ((chunk ^ (uint32_t)c) << 4);
+    // where red[] holds the totals of particle myp: warps 4*(myp/16) .. +3, lane (2*(c/4) + d)*4 + c%4 with c = myp%16
+    const int red_w = (myp >> 4) * 4, red_l = ((myp & 15) >> 2) * 8 + (myp & 3);
+    // this thread's 8-byte group inside the operand rows of its particles p0 + 4r + c4: operand k-block mt*4 + q, 16-byte
+    // chunk (g >> 1) ^ ((row >> 1) & 3) [SWIZZLE_64B], half g & 1.  (row >> 1) & 3 = ((r & 1) << 1) | (c4 >> 1).
+    uint32_t sa0[2];
+    {
+      const uint32_t b0 = s32(smem + Smem::act) + (uint32_t)(q * KB_BYTES + (p0 + c4) * 64 + (g & 1) * 8);
+      const uint32_t ce = (uint32_t)((g >> 1) ^ (c4 >> 1));
+      sa0[0] = b0 + (ce << 4);
+      sa0[1] = b0 + ((ce ^ 2u) << 4);
+    }
+    auto make_sa = [&](int mt, uint32_t (&sa)[2]) {
+      sa[0] = sa0[0] + (uint32_t)(mt * 4 * KB_BYTES);
+      sa[1] = sa0[1] + (uint32_t)(mt * 4 * KB_BYTES);
     };
     // after writing one half of the B operand: make it visible to the tensor core and hand over to the MMA thread
     auto publish = [&](int mt) {
       fence_proxy_async();
       mbar_arrive(&b_ready[mt]);
     };
-    // z = main + 2^-11 * corr of this thread's unit: jet j, particles p0 .. p0+15
+    // z = main + 2^-11 * corr, jet j, element e = 8*ld + 2*r + h
     auto load_acc = [&](int j, float (&z)[HP]) {
       uint32_t m[HP], c[HP];
-      tmem_ld16(lane_base + j * NP, m);
-      tmem_ld16(lane_base + COL_CORR + j * NP, c);
+      tmem_ld8(lane_base + j * NP, m);
+      tmem_ld8(lane_base + (16u << 16) + j * NP, m + 8);
+      tmem_ld8(lane_base + COL_CORR + j * NP, c);
+      tmem_ld8(lane_base + (16u << 16) + COL_CORR + j * NP, c + 8);
       tmem_wait_ld();
 #pragma unroll
       for (int i = 0; i < HP; ++i) z[i] = fmaf(__uint_as_float(c[i]), LO_INV, __uint_as_float(m[i]));
@@ -395,10 +440,14 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
     // boundary evaluations: jet 0 summed over the two accumulator sets
     auto load_acc2 = [&](float (&z)[HP]) {
       uint32_t m0[HP], c0[HP], m1[HP], c1[HP];
-      tmem_ld16(lane_base, m0);
-      tmem_ld16(lane_base + COL_CORR, c0);
-      tmem_ld16(lane_base + COL_STASH, m1);
-      tmem_ld16(lane_base + COL_STASH + COL_CORR, c1);
+      tmem_ld8(lane_base, m0);
+      tmem_ld8(lane_base + (16u << 16), m0 + 8);
+      tmem_ld8(lane_base + COL_CORR, c0);
+      tmem_ld8(lane_base + (16u << 16) + COL_CORR, c0 + 8);
+      tmem_ld8(lane_base + COL_STASH, m1);
+      tmem_ld8(lane_base + (16u << 16) + COL_STASH, m1 + 8);
+      tmem_ld8(lane_base + COL_STASH + COL_CORR, c1);
+      tmem_ld8(lane_base + (16u << 16) + COL_STASH + COL_CORR, c1 + 8);
       tmem_wait_ld();
 #pragma unroll
       for (int i = 0; i < HP; ++i)
@@ -409,7 +458,6 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
       aphase ^= 1u;
       tc_fence_after();
     };
-    uint32_t kphase = 0;
     auto wait_kfree = [&]() {
       mbar_wait(kfree, kphase);
       kphase ^= 1u;
@@ -417,6 +465,20 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
     auto release_acc = [&]() {
       tc_fence_before();
       mbar_arrive(acc_free);
+    };
+    // sum over the thread's 4 units, then over the 8 threads that share its particles: v[2r + d] -> lane g keeps v[g]
+    auto reduce_units = [&](float (&v)[8]) -> float {
+#pragma unroll
+      for (int off = 16, cnt = 4; off >= 4; off >>= 1, cnt >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < cnt; ++i) {
+          const float send = up ? v[i] : v[i + cnt];
+          const float keep = up ? v[i + cnt] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      return v[0];
     };
 
     mbar_arrive(acc_free);   // nothing to read out before the very first m-tile
@@ -443,29 +505,39 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
         // Every MMA of the previous evaluation is complete (this thread waited for its last accumulators).
 #pragma unroll 1
         for (int mt = 0; mt < 2; ++mt) {
-          const int n = mt * 128 + q * 32 + lane;
-          const float wx0 = __ldg(P.net.wt0 + 0 * W + n), wx1 = __ldg(P.net.wt0 + 1 * W + n);
-          const float zb = fmaf(__ldg(P.net.wt0 + 2 * W + n), st.t, __ldg(P.net.b0 + (size_t)P.tidx * W + n));
-          const float zz1 = __ldg(P.net.zd1 + n);
-          uint32_t hh[HP], ll[HP];
+          const int n0 = mt * 128 + q * 32 + 4 * g;
+          float2 xp[4];
 #pragma unroll
-          for (int i = 0; i < HP; ++i) {
-            const float2 xp = *reinterpret_cast<const float2*>(sxs + 2 * (p0 + i));
-            float a, s1, E;
-            selu_jet(fmaf(wx1, xp.y, fmaf(wx0, xp.x, zb)), a, s1, E);
-            split2(a, s1 * zz1, hh[i], ll[i]);
+          for (int r = 0; r < 4; ++r) xp[r] = *reinterpret_cast<const float2*>(sxs + 2 * (p0 + 4 * r + c4));
+          const float4 wx0 = __ldg(reinterpret_cast<const float4*>(P.net.wt0 + 0 * W + n0));
+          const float4 wx1 = __ldg(reinterpret_cast<const float4*>(P.net.wt0 + 1 * W + n0));
+          const float4 wtt = __ldg(reinterpret_cast<const float4*>(P.net.wt0 + 2 * W + n0));
+          const float4 bb0 = __ldg(reinterpret_cast<const float4*>(P.net.b0 + (size_t)P.tidx * W + n0));
+          const float4 zz1 = __ldg(reinterpret_cast<const float4*>(P.net.zd1 + n0));
+          float v0[HP], v1[HP];
+#pragma unroll
+          for (int e = 0; e < HP; ++e) {
+            const int r = (e >> 1) & 3;
+            const float zb = fmaf(IDFF_UC(wtt, e), st.t, IDFF_UC(bb0, e));
+            float s1, E;
+            selu_jet(fmaf(IDFF_UC(wx1, e), xp[r].y, fmaf(IDFF_UC(wx0, e), xp[r].x, zb)), v0[e], s1, E);
+            v1[e] = s1 * IDFF_UC(zz1, e);
           }
-          uint32_t sw[8];
-          make_sw(mt, sw);
-          if (heavy) store_all<true>(sw, hh, ll);
-          else store_all<false>(sw, hh, ll);
+          uint32_t sa[2], hw[8], lw[8];
+          make_sa(mt, sa);
+          pack_jet(v0, hw, lw);
+          store_jet<0>(sa, hw, lw);
+          if (heavy) {
+            pack_jet(v1, hw, lw);
+            store_jet<1>(sa, hw, lw);
+          }
           publish(mt);
         }
         if (stamp) g_tc16_stamps[1] = clock64();
         // ---- gemm 0: layer 2 forward
 #pragma unroll 1
         for (int mt = 0; mt < 2; ++mt) {
-          const int n = mt * 128 + q * 32 + lane;
+          const int n0 = mt * 128 + q * 32 + 4 * g;
           wait_acc();
           if (stamp && mt == 0) g_tc16_stamps[2] = clock64();
           float z[HP], zd[HP];
@@ -476,36 +548,40 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
             load_acc2(z);
           }
           release_acc();
-          const float bb1 = __ldg(P.net.b1 + n);
+          const float4 bb1 = __ldg(reinterpret_cast<const float4*>(P.net.b1 + n0));
           const uint32_t stash = lane_base + COL_STASH + mt * 128;
-          uint32_t hh[HP], ll[HP];
+          uint32_t h0[8], l0[8], h1[8], l1[8];
           if (heavy) {   // stash z2' (raw) and the derivative code of z2
             uint32_t u[HP];
 #pragma unroll
-            for (int i = 0; i < HP; ++i) u[i] = __float_as_uint(zd[i]);
-            tmem_st16(stash + NP, u);
+            for (int e = 0; e < HP; ++e) u[e] = __float_as_uint(zd[e]);
+            tmem_st8(stash + NP, u);
+            tmem_st8(stash + (16u << 16) + NP, u + 8);
 #pragma unroll
-            for (int i = 0; i < HP; ++i) {
-              float a, s1, code;
-              selu_jet_code(z[i] + bb1, a, s1, code);
-              u[i] = __float_as_uint(code);
-              split2(a, s1 * zd[i], hh[i], ll[i]);
+            for (int e = 0; e < HP; ++e) {
+              float s1, code;
+              selu_jet_code(z[e] + IDFF_UC(bb1, e), z[e], s1, code);
+              u[e] = __float_as_uint(code);
+              zd[e] = s1 * zd[e];
             }
-            tmem_st16(stash, u);
+            tmem_st8(stash, u);
+            tmem_st8(stash + (16u << 16), u + 8);
             tmem_wait_st();
+            pack_jet(z, h0, l0);
+            pack_jet(zd, h1, l1);
           } else {
 #pragma unroll
-            for (int i = 0; i < HP; ++i) {
-              float a, s1, E;
-              selu_jet(z[i] + bb1, a, s1, E);
-              split2(a, 0.0f, hh[i], ll[i]);
+            for (int e = 0; e < HP; ++e) {
+              float s1, E;
+              selu_jet(z[e] + IDFF_UC(bb1, e), z[e], s1, E);
             }
+            pack_jet(z, h0, l0);
           }
           if (mt == 0) wait_kfree();   // k-blocks 0-1 have been read by every MMA of this pass
-          uint32_t sw[8];
-          make_sw(mt, sw);
-          if (heavy) store_all<true>(sw, hh, ll);
-          else store_all<false>(sw, hh, ll);
+          uint32_t sa[2];
+          make_sa(mt, sa);
+          store_jet<0>(sa, h0, l0);
+          if (heavy) store_jet<1>(sa, h1, l1);
           publish(mt);
         }
         if (stamp) g_tc16_stamps[3] = clock64();
@@ -514,7 +590,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
           float rsum = 0.0f;
 #pragma unroll 1
           for (int mt = 0; mt < 2; ++mt) {
-            const int n = mt * 128 + q * 32 + lane;
+            const int n0 = mt * 128 + q * 32 + 4 * g;
             wait_acc();
             if (stamp && mt == 0) g_tc16_stamps[4] = clock64();
             float z[HP], zd[HP];
@@ -525,33 +601,38 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
               load_acc2(z);
             }
             release_acc();
-            const float bb2 = __ldg(P.net.b2 + n), uu3 = __ldg(P.net.u3 + n);
-            const float w30 = __ldg(P.net.w3 + 0 * W + n), w31 = __ldg(P.net.w3 + 1 * W + n);
-            const float A0 = st.c[0] * uu3, A1 = st.c[1] * uu3;
-            {
-              float part[32];
+            const float4 bb2 = __ldg(reinterpret_cast<const float4*>(P.net.b2 + n0));
+            const float4 uu3 = __ldg(reinterpret_cast<const float4*>(P.net.u3 + n0));
+            const float4 w30 = __ldg(reinterpret_cast<const float4*>(P.net.w3 + 0 * W + n0));
+            const float4 w31 = __ldg(reinterpret_cast<const float4*>(P.net.w3 + 1 * W + n0));
+            float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-              for (int i = 0; i < HP; ++i) {
-                float a, s1, E;
-                selu_jet(z[i] + bb2, a, s1, E);
-                part[2 * i] = a * w30;
-                part[2 * i + 1] = a * w31;
-                if (heavy) {   // adjoints of z3 and z3', in place
-                  z[i] = fmaf(A1 * E, zd[i], A0 * s1);
-                  zd[i] = A1 * s1;
+            for (int ld = 0; ld < 2; ++ld)       // fixed summation order over the thread's units 0, 1, 2, 3
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                  const int e = 8 * ld + 2 * r + h;
+                  float a, s1, E;
+                  selu_jet(z[e] + IDFF_UC(bb2, e), a, s1, E);
+                  part[2 * r] += a * IDFF_UC(w30, e);
+                  part[2 * r + 1] += a * IDFF_UC(w31, e);
+                  if (heavy) {   // adjoints of z3 and z3', in place
+                    const float A0 = st.c[0] * IDFF_UC(uu3, e), A1 = st.c[1] * IDFF_UC(uu3, e);
+                    z[e] = fmaf(A1 * E, zd[e], A0 * s1);
+                    zd[e] = A1 * s1;
+                  }
                 }
-              }
-              warp_reduce_scatter32(part, lane);
-              rsum += part[0];
-            }
+            rsum += reduce_units(part);
             if (heavy) {
-              uint32_t hh[HP], ll[HP];
-#pragma unroll
-              for (int i = 0; i < HP; ++i) split2(z[i], zd[i], hh[i], ll[i]);
+              uint32_t h0[8], l0[8], h1[8], l1[8];
+              pack_jet(z, h0, l0);
+              pack_jet(zd, h1, l1);
               if (mt == 0) wait_kfree();
-              uint32_t sw[8];
-              make_sw(mt, sw);
-              store_all<true>(sw, hh, ll);
+              uint32_t sa[2];
+              make_sa(mt, sa);
+              store_jet<0>(sa, h0, l0);
+              store_jet<1>(sa, h1, l1);
               publish(mt);
             } else if (mt == 0) {
               wait_kfree();
@@ -562,12 +643,11 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
         if (stamp) g_tc16_stamps[5] = clock64();
         ebar();
         if (warp < 2) {   // x1hat of particle myp: fixed summation order over the 4 lane-quarter warps of its quarter
-          const int wq = (myp >> 4) * 4, e2 = (myp & 15) * 2;
 #pragma unroll
           for (int d = 0; d < 2; ++d) {
             float acc = __ldg(P.net.b3 + d);
 #pragma unroll
-            for (int w4 = 0; w4 < 4; ++w4) acc += red[(wq + w4) * 32 + e2 + d];
+            for (int w4 = 0; w4 < 4; ++w4) acc += red[(red_w + w4) * 32 + red_l + 4 * d];
             pr_tot[d] = acc;
           }
         }
@@ -583,24 +663,30 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
             load_acc(0, a0);
             load_acc(1, a1);
             release_acc();
-            uint32_t hh[HP], ll[HP];
             {
               const uint32_t stash = lane_base + COL_STASH + mt * 128;
               uint32_t cd[HP], zdu[HP];
-              tmem_ld16(stash, cd);
-              tmem_ld16(stash + NP, zdu);
+              tmem_ld8(stash, cd);
+              tmem_ld8(stash + (16u << 16), cd + 8);
+              tmem_ld8(stash + NP, zdu);
+              tmem_ld8(stash + (16u << 16) + NP, zdu + 8);
               tmem_wait_ld();
 #pragma unroll
-              for (int i = 0; i < HP; ++i) {
-                const float code = __uint_as_float(cd[i]);
+              for (int e = 0; e < HP; ++e) {
+                const float code = __uint_as_float(cd[e]);
                 const float s1 = code < 0.0f ? kSeluLambda : code, E = code < 0.0f ? 0.0f : code;
-                split2(fmaf(a1[i] * E, __uint_as_float(zdu[i]), a0[i] * s1), a1[i] * s1, hh[i], ll[i]);
+                a0[e] = fmaf(a1[e] * E, __uint_as_float(zdu[e]), a0[e] * s1);
+                a1[e] = a1[e] * s1;
               }
             }
+            uint32_t h0[8], l0[8], h1[8], l1[8];
+            pack_jet(a0, h0, l0);
+            pack_jet(a1, h1, l1);
             if (mt == 0) wait_kfree();
-            uint32_t sw[8];
-            make_sw(mt, sw);
-            store_all<true>(sw, hh, ll);
+            uint32_t sa[2];
+            make_sa(mt, sa);
+            store_jet<0>(sa, h0, l0);
+            store_jet<1>(sa, h1, l1);
             publish(mt);
           }
           if (stamp) g_tc16_stamps[8] = clock64();
@@ -608,40 +694,48 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
           float gsum = 0.0f;
 #pragma unroll 1
           for (int mt = 0; mt < 2; ++mt) {
-            const int n = mt * 128 + q * 32 + lane;
+            const int n0 = mt * 128 + q * 32 + 4 * g;
             wait_acc();
             if (stamp && mt == 0) g_tc16_stamps[9] = clock64();
             float a0[HP], a1[HP];
             load_acc(0, a0);
             load_acc(1, a1);
             release_acc();
-            const float wx0 = __ldg(P.net.wt0 + 0 * W + n), wx1 = __ldg(P.net.wt0 + 1 * W + n);
-            const float zb = fmaf(__ldg(P.net.wt0 + 2 * W + n), st.t, __ldg(P.net.b0 + (size_t)P.tidx * W + n));
-            const float zz1 = __ldg(P.net.zd1 + n);
-            float part[32];
+            const float4 wx0 = __ldg(reinterpret_cast<const float4*>(P.net.wt0 + 0 * W + n0));
+            const float4 wx1 = __ldg(reinterpret_cast<const float4*>(P.net.wt0 + 1 * W + n0));
+            const float4 wtt = __ldg(reinterpret_cast<const float4*>(P.net.wt0 + 2 * W + n0));
+            const float4 bb0 = __ldg(reinterpret_cast<const float4*>(P.net.b0 + (size_t)P.tidx * W + n0));
+            const float4 zz1 = __ldg(reinterpret_cast<const float4*>(P.net.zd1 + n0));
+            float2 xp[4];
 #pragma unroll
-            for (int i = 0; i < HP; ++i) {
-              const float2 xp = *reinterpret_cast<const float2*>(sxs + 2 * (p0 + i));
-              float a, s1, E;
-              selu_jet(fmaf(wx1, xp.y, fmaf(wx0, xp.x, zb)), a, s1, E);
-              const float P1 = fmaf(a1[i] * E, zz1, a0[i] * s1);
-              part[2 * i] = P1 * wx0;
-              part[2 * i + 1] = P1 * wx1;
-            }
-            warp_reduce_scatter32(part, lane);
-            gsum += part[0];
+            for (int r = 0; r < 4; ++r) xp[r] = *reinterpret_cast<const float2*>(sxs + 2 * (p0 + 4 * r + c4));
+            float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ld = 0; ld < 2; ++ld)
+#pragma unroll
+              for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                  const int e = 8 * ld + 2 * r + h;
+                  const float zb = fmaf(IDFF_UC(wtt, e), st.t, IDFF_UC(bb0, e));
+                  float a, s1, E;
+                  selu_jet(fmaf(IDFF_UC(wx1, e), xp[r].y, fmaf(IDFF_UC(wx0, e), xp[r].x, zb)), a, s1, E);
+                  const float P1 = fmaf(a1[e] * E, IDFF_UC(zz1, e), a0[e] * s1);
+                  part[2 * r] += P1 * IDFF_UC(wx0, e);
+                  part[2 * r + 1] += P1 * IDFF_UC(wx1, e);
+                }
+            gsum += reduce_units(part);
             if (mt == 0) wait_kfree();   // keeps the barrier phase in step
           }
           red[warp * 32 + lane] = gsum;
           if (stamp) g_tc16_stamps[10] = clock64();
           ebar();
           if (warp < 2) {
-            const int wq = (myp >> 4) * 4, e2 = (myp & 15) * 2;
 #pragma unroll
             for (int d = 0; d < 2; ++d) {
               float acc = 0.0f;
 #pragma unroll
-              for (int w4 = 0; w4 < 4; ++w4) acc += red[(wq + w4) * 32 + e2 + d];
+              for (int w4 = 0; w4 < 4; ++w4) acc += red[(red_w + w4) * 32 + red_l + 4 * d];
               gg[d] = acc;
             }
           }

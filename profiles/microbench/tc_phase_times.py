@@ -17,3 +17,5 @@ buf = (C.c_int64 * 32)(); _lib.check((_lib.lib().idff_debug_tensor16_stamps if I
 names = ["L1 start", "L1 done+publish", "acc0 ready", "epi0 done+publish", "acc1 ready", "epi1 done+publish", "reduce1 done", "acc2 ready", "epi2 done+publish", "acc3 ready", "epi3+reduce done", "ebar", "update+ebar"]
 for i in range(1, 13): print(f"  E: {names[i]:22s} +{s[i]-s[i-1]:7d}   (t={s[i]-s[0]})")
 for g in range(4): print(f"  MMA gemm {g}: start t={s[16+2*g]-s[0]:7d}  issue-done t={s[17+2*g]-s[0]:7d}  issue {s[17+2*g]-s[16+2*g]}")
+
+if IMPL == 5: print(f"  MMA thread waits over the evaluation: acc_free(mt0) {s[24]}  acc_free(mt1) {s[25]}  b_ready[0] {s[26]}  b_ready[1] {s[27]}  weight ring {s[28]}")
