@@ -73,7 +73,7 @@ struct NetView {
   // 3xFP16 operand tiles of the fused fp16 tensor kernel (w == 256 only): [gemm 0..3][m-tile 0..1][k-block 0..3][hi, lo']
   // [128 rows x 64 fp16], each a 16 KB K-major SWIZZLE_128B image (row r at r*128 B, 16-byte chunk c = 8 halfs at chunk
   // c ^ (r & 7)).  hi = fp16_rn(w), lo' = fp16_rn((w - hi) * 2^11).  Same gemm numbering as tc_tiles.  Tile row r holds
-  // unit (r & ~31) + 4*(r & 7) + ((r >> 3) & 3) of the m-tile (see idff_sampler_tc16.cu).
+  // unit (r & ~31) + 4*slot(r & 7) + ((r >> 3) & 3) of the m-tile (see idff_sampler_tc16.cu).
   const float* tc16_tiles;
 };
 

@@ -25,8 +25,8 @@
 //     the layer-2 derivative stash of the reverse sweep (2 x 128 columns).
 // A TMEM lane is one hidden unit.  The epilogue reads the accumulators with tcgen05.ld.16x128b: thread T of a warp gets
 // lanes {g, g+8, g+16, g+24} (g = T/4) of its lane quarter and columns {T%4 + 4r}; the weight-tile rows are permuted at
-// handle creation so that these four lanes are four CONSECUTIVE units 4g..4g+3, i.e. one 8-byte group of the next
-// pass's K-major operand row.  A thread therefore owns every jet of 4 units x 4 particles: the SELU jet / adjoint
+// handle creation so that these four lanes are four CONSECUTIVE units 4s..4s+3 (s = slot(g), a fixed permutation of
+// 0..7 chosen for bank-conflict-free stores), i.e. one 8-byte group of the next pass's K-major operand row.  A thread therefore owns every jet of 4 units x 4 particles: the SELU jet / adjoint
 // algebra is thread-local, and sums over units are 3 in-thread adds + a 3-step shuffle.  16 epilogue warps = 4 lane
 // quarters x 4 particle quarters; every thread serves m-tile 0 and then m-tile 1 of a pass.  The m-tile-0 epilogue computes while the m-tile-1 MMAs run, and the
 // next pass starts on k-blocks 0-1 (written by the m-tile-0 epilogue) while the m-tile-1 epilogue is still at work.
@@ -397,6 +397,10 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
     const int q = warp & 3, pq = warp >> 2;
     const int p0 = pq * HP;
     const int g = lane >> 2, c4 = lane & 3;
+    // 8-byte slot of this thread's 4 units inside the 64-byte operand row of its lane quarter.  Not g itself: a 64-bit
+    // store is served per half-warp (g = 0..3 | 4..7, 4 particle rows each); rows c4 and c4 + 2 fall on the same banks
+    // and the SWIZZLE_64B XOR between them is one 16-byte chunk, so a half-warp must own chunks {0, 2} or {1, 3}.
+    const int slot = (g & 1) | (((g >> 1) & 1) << 2) | ((g >> 2) << 1);
     float* red = misc + Smem::f_red;       // [16 warps][32]
     float* sxs = misc + Smem::f_xs;        // stage input of the 64 particles, [p][2]
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + p0;   // + (16 << 16) for the upper 16 lanes
@@ -409,11 +413,11 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
     // where red[] holds the totals of particle myp: warps 4*(myp/16) .. +3, lane (2*(c/4) + d)*4 + c%4 with c = myp%16
     const int red_w = (myp >> 4) * 4, red_l = ((myp & 15) >> 2) * 8 + (myp & 3);
     // this thread's 8-byte group inside the operand rows of its particles p0 + 4r + c4: operand k-block mt*4 + q, 16-byte
-    // chunk (g >> 1) ^ ((row >> 1) & 3) [SWIZZLE_64B], half g & 1.  (row >> 1) & 3 = ((r & 1) << 1) | (c4 >> 1).
+    // chunk (slot >> 1) ^ ((row >> 1) & 3) [SWIZZLE_64B], half slot & 1.  (row >> 1) & 3 = ((r & 1) << 1) | (c4 >> 1).
     uint32_t sa0[2];
     {
-      const uint32_t b0 = s32(smem + Smem::act) + (uint32_t)(q * KB_BYTES + (p0 + c4) * 64 + (g & 1) * 8);
-      const uint32_t ce = (uint32_t)((g >> 1) ^ (c4 >> 1));
+      const uint32_t b0 = s32(smem + Smem::act) + (uint32_t)(q * KB_BYTES + (p0 + c4) * 64 + (slot & 1) * 8);
+      const uint32_t ce = (uint32_t)((slot >> 1) ^ (c4 >> 1));
       sa0[0] = b0 + (ce << 4);
       sa0[1] = b0 + ((ce ^ 2u) << 4);
     }
@@ -505,7 +509,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
         // Every MMA of the previous evaluation is complete (this thread waited for its last accumulators).
 #pragma unroll 1
         for (int mt = 0; mt < 2; ++mt) {
-          const int n0 = mt * 128 + q * 32 + 4 * g;
+          const int n0 = mt * 128 + q * 32 + 4 * slot;
           float2 xp[4];
 #pragma unroll
           for (int r = 0; r < 4; ++r) xp[r] = *reinterpret_cast<const float2*>(sxs + 2 * (p0 + 4 * r + c4));
@@ -537,7 +541,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
         // ---- gemm 0: layer 2 forward
 #pragma unroll 1
         for (int mt = 0; mt < 2; ++mt) {
-          const int n0 = mt * 128 + q * 32 + 4 * g;
+          const int n0 = mt * 128 + q * 32 + 4 * slot;
           wait_acc();
           if (stamp && mt == 0) g_tc16_stamps[2] = clock64();
           float z[HP], zd[HP];
@@ -590,7 +594,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
           float rsum = 0.0f;
 #pragma unroll 1
           for (int mt = 0; mt < 2; ++mt) {
-            const int n0 = mt * 128 + q * 32 + 4 * g;
+            const int n0 = mt * 128 + q * 32 + 4 * slot;
             wait_acc();
             if (stamp && mt == 0) g_tc16_stamps[4] = clock64();
             float z[HP], zd[HP];
@@ -694,7 +698,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
           float gsum = 0.0f;
 #pragma unroll 1
           for (int mt = 0; mt < 2; ++mt) {
-            const int n0 = mt * 128 + q * 32 + 4 * g;
+            const int n0 = mt * 128 + q * 32 + 4 * slot;
             wait_acc();
             if (stamp && mt == 0) g_tc16_stamps[9] = clock64();
             float a0[HP], a1[HP];

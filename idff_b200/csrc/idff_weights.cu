@@ -199,9 +199,11 @@ extern "C" int idff_weights_create(const float* const* h_W, const float* const* 
           uint16_t* lo = hi + 8192;
           for (int r = 0; r < 128; ++r)
             for (int kk = 0; kk < 64; ++kk) {
-              // tile row r = TMEM lane: lanes {g, g+8, g+16, g+24} of a 32-lane quarter hold units 4g..4g+3 (the four
-              // lanes one thread reads with tcgen05.ld.16x128b), so a thread writes 4 consecutive k of the next operand
-              const int unit = (r & ~31) + 4 * (r & 7) + ((r >> 3) & 3);
+              // tile row r = TMEM lane: lanes {g, g+8, g+16, g+24} of a 32-lane quarter hold units 4s..4s+3, s = slot(g)
+              // (the four lanes one thread reads with tcgen05.ld.16x128b), so a thread writes 4 consecutive k of the
+              // next operand; slot() is the bank-conflict-free order of idff_sampler_tc16.cu
+              const int gq = r & 7, slot = (gq & 1) | (((gq >> 1) & 1) << 2) | ((gq >> 2) << 1);
+              const int unit = (r & ~31) + 4 * slot + ((r >> 3) & 3);
               const int row = mt * 128 + unit, col = kb * 64 + kk;   // D[row][.] = sum_col A[row][col] * act[.][col]
               const float v = g == 0 ? W1[(size_t)row * w + col] : g == 1 ? W2[(size_t)row * w + col]
                             : g == 2 ? W2[(size_t)col * w + row] : W1[(size_t)col * w + row];
