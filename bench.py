@@ -389,6 +389,56 @@ def aux_measurements(dev, pw, model, peaks):
         aux["reference_cpu_secondary"] = cpu
     except Exception as exc:
         aux["reference_cpu_secondary_error"] = repr(exc)
+    # ---- training side (BASELINE metric: "train samples/s"): the reference's 2-D training step at its batch size (256,
+    # launch-bound) and at 2^16, eager vs one CUDA-graph replay per step; the reference's step on the host cores beside it
+    try:
+        from idff_b200 import train
+        from idff_b200.torchcfm.models.models import MLP
+        tr_out = {}
+        for Bt in (256, 1 << 16):
+            torch.manual_seed(0)
+            net = MLP(dim=2, w=256, time_varying=True).to(dev)
+            FMt = cfm.ExactOptimalTransportConditionalFlowMatcher(sigma=0.0)
+            opt = torch.optim.AdamW(net.parameters(), lr=2e-4)
+
+            def eager_step():
+                x1 = train.checkerboard_device(Bt, dev)
+                train.flow_train_step(net, opt, FMt, torch.randn_like(x1), x1, t=torch.rand(Bt, device=dev))
+            s_e = timeit(eager_step, reps=50, warm=5)
+            gt = train.GraphedFlowTrainer(net, batch_size=Bt)
+            s_g = timeit(gt.step, reps=200, warm=5)
+            tr_out[f"B{Bt}"] = {"eager_samples_per_s": Bt / s_e, "graph_samples_per_s": Bt / s_g,
+                                "eager_us_per_step": s_e * 1e6, "graph_us_per_step": s_g * 1e6}
+        # the reference's own step on the CPU (torch CPU, all host threads), B = 256
+        torch.manual_seed(0)
+        netc = MLP(dim=2, w=256, time_varying=True)
+        optc = torch.optim.AdamW(netc.parameters(), lr=2e-4)
+        import idff_oracle as O2
+        from idff_b200.torchcfm.utils import sample_checkerboard as host_checkerboard
+
+        def cpu_step():
+            optc.zero_grad()
+            x1 = host_checkerboard(256)
+            x0 = torch.randn_like(x1)
+            t = torch.rand(256)
+            eps = torch.randn_like(x0)
+            xt, _ = O2.path_sample(x0, x1, t, eps, 0.0, True)
+            vt = netc.net(torch.cat([xt, t[:, None]], dim=-1))
+            loss = torch.mean(((1 / (1e-2 + 1 - t[:, None])) * (vt - x1)) ** 2)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(netc.parameters(), 1)
+            optc.step()
+        torch.set_num_threads(os.cpu_count() or 1)
+        for _ in range(5):
+            cpu_step()
+        t0 = time.perf_counter()
+        for _ in range(100):
+            cpu_step()
+        s_c = (time.perf_counter() - t0) / 100
+        tr_out["reference_cpu_B256"] = {"samples_per_s": 256 / s_c, "us_per_step": s_c * 1e6, "cores": os.cpu_count()}
+        aux["train_step"] = tr_out
+    except Exception as exc:
+        aux["train_step_error"] = repr(exc)
     # ---- other BASELINE configs, measured briefly (reported, not the headline)
     try:
         from idff_b200.weights import PackedWeights
