@@ -163,6 +163,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if ws > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"      # stdout carries exactly one JSON line: no NCCL version banner
         dist.init_process_group("nccl", device_id=dev)
     P, nfe = args.particles, args.nfe
     n_total = P * ws
