@@ -40,6 +40,8 @@ int tensor16_field_eval(const idff_weights_t* w, const idff_field_params_t* p, f
                         float* d_out, int64_t N, void* stream);
 int tensor16_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, const float* d_x0, const Stage* stages,
                         const float* dts, int n_iv, float* d_out_final, float* d_out_traj, int64_t N, void* stream);
+int tensor16_sample_rk4_sweep(const idff_weights_t* w, const idff_field_params_t* params, int n_sets, const float* d_x0,
+                              const Stage* stages, const float* dts, int n_iv, float* d_out, int64_t N, void* stream);
 int tensor16_debug_stamps(long long* h_out, int n);
 int tensor16_nonfinite(unsigned long long* h_out);
 
@@ -197,6 +199,56 @@ extern "C" int idff_sample_rk4(const idff_weights_t* w, const idff_field_params_
     return fused_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream);
   }
   return generic_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream);
+}
+
+extern "C" int idff_sample_rk4_sweep(const idff_weights_t* w, const idff_field_params_t* params, int32_t n_sets,
+                                     const float* d_x0, const float* h_t_grid, int32_t n_grid, float* d_out, int64_t N,
+                                     void* stream) {
+  IDFF_CHECK_ARG(params && n_sets >= 1 && n_sets <= 100000, "idff_sample_rk4_sweep: bad parameter-set array (n_sets=%d)", n_sets);
+  for (int g = 0; g < n_sets; ++g) {
+    int rc = check_field_args(w, &params[g], "idff_sample_rk4_sweep");
+    if (rc) return rc;
+    IDFF_CHECK_ARG(params[g].variant != IDFF_FIELD_MD, "idff_sample_rk4_sweep: the MD field is an SDE drift");
+    IDFF_CHECK_ARG(params[g].dim == params[0].dim, "idff_sample_rk4_sweep: parameter sets differ in dim");
+  }
+  IDFF_CHECK_ARG(h_t_grid && n_grid >= 1 && n_grid <= 100000, "idff_sample_rk4_sweep: bad time grid (n_grid=%d)", n_grid);
+  for (int i = 1; i < n_grid; ++i)
+    IDFF_CHECK_ARG(h_t_grid[i] > h_t_grid[i - 1], "idff_sample_rk4_sweep: t_grid must be strictly increasing");
+  if (N == 0) return IDFF_OK;
+  IDFF_CHECK_ARG(N > 0 && d_x0 && d_out, "idff_sample_rk4_sweep: null pointer or negative N");
+  const int n_iv = n_grid - 1;
+  const size_t set_floats = (size_t)N * params[0].dim;
+  // one launch when every set is served by the 3xFP16 tensor kernel; otherwise one fused launch per set
+  bool batched = n_iv >= 1 && n_iv <= kMaxSweepIntervals;
+  for (int g = 0; g < n_sets && batched; ++g)
+    batched = (params[g].impl == IDFF_IMPL_AUTO || params[g].impl == IDFF_IMPL_TENSOR16) && tensor16_supports(w, &params[g]) &&
+              params[g].variant == params[0].variant && params[g].t_idx == params[0].t_idx;
+  if (!batched) {
+    for (int g = 0; g < n_sets; ++g) {
+      int rc = idff_sample_rk4(w, &params[g], d_x0, h_t_grid, n_grid, d_out + (size_t)g * set_floats, nullptr, N, stream);
+      if (rc) return rc;
+    }
+    return IDFF_OK;
+  }
+  DeviceGuard guard(w->device);
+  std::vector<Stage> st((size_t)n_sets * 4 * n_iv);
+  std::vector<float> dts(n_iv);
+  const float third = (float)(1.0 / 3.0), two_thirds = (float)(2.0 / 3.0);
+  for (int i = 0; i < n_iv; ++i) {   // stage times as in idff_sample_rk4 (torchdiffeq rk4_alt_step_func)
+    const float t0 = h_t_grid[i], t1 = h_t_grid[i + 1];
+    volatile float dt = t1 - t0;
+    volatile float a = dt * third, b = dt * two_thirds;
+    volatile float tb = t0 + a, tc = t0 + b;
+    dts[i] = dt;
+    for (int g = 0; g < n_sets; ++g) {
+      Stage* s4 = &st[((size_t)g * n_iv + i) * 4];
+      make_stage(params[g], t0, &s4[0]);
+      make_stage(params[g], tb, &s4[1]);
+      make_stage(params[g], tc, &s4[2]);
+      make_stage(params[g], t1, &s4[3]);
+    }
+  }
+  return tensor16_sample_rk4_sweep(w, params, n_sets, d_x0, st.data(), dts.data(), n_iv, d_out, N, stream);
 }
 
 extern "C" int idff_sde_num_steps(const float* h_ts, int32_t n_ts, float dt) {

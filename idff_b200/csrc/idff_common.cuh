@@ -89,6 +89,8 @@ struct idff_weights {
   float* d_stash;       // scratch owned by the handle (order-3 stash of the fused kernel, buffers of the layered engine)
   size_t stash_bytes;
   int tc_verified;      // bit 0 / 1: the first fused / layered tcgen05 launch on this handle was checked (alignment flag)
+  void* d_sweep;        // device copy of the SweepTab array of the last idff_sample_rk4_sweep call
+  size_t sweep_bytes;
 };
 
 namespace idff {
@@ -114,6 +116,15 @@ struct Rk4Table {
   int n_iv;
   float dt[kMaxIntervals];
   Stage st[4 * kMaxIntervals];
+};
+
+// gamma sweeps (idff_sample_rk4_sweep): one table per parameter set, in global memory
+constexpr int kMaxSweepIntervals = 32;
+struct SweepTab {
+  int reverse;   // jets_needed(): whether this set's interior evaluations run the reverse sweep
+  int pad[3];
+  float dt[kMaxSweepIntervals];
+  Stage st[4 * kMaxSweepIntervals];
 };
 
 constexpr int kMaxSdeSteps = 48;

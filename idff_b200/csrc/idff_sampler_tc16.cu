@@ -33,6 +33,7 @@
 #include <cuda_fp16.h>
 
 #include <cstdlib>
+#include <vector>
 
 #include "idff_common.cuh"
 
@@ -175,7 +176,10 @@ __device__ long long g_tc16_stamps[32];
 
 struct TParams {
   NetView net;
-  int variant, D, tidx, reverse, mode;   // mode 0 eval, 1 rk4
+  int variant, D, tidx, reverse, mode;   // mode 0 eval, 1 rk4, 2 rk4 sweep over n_sets parameter sets (same x0, same grid)
+  int n_sets, sweep_n_iv;
+  long tiles_per_set;                    // sweep: even, so both CTAs of a pair always work on the same set
+  const SweepTab* tabs;                  // sweep: [n_sets] in global memory
   long N;
   const float* x_in;
   const float* x0_cfm;
@@ -299,12 +303,19 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
   const uint32_t tmem = *tmem_slot;
   const uint32_t crank = cluster_ctarank();
   // both CTAs of a pair walk the same number of tiles (the ring couples them); surplus tiles are all-padding
-  const long n_tiles = (P.N + NP - 1) / NP;
+  const long tiles_per_set = P.mode == 2 ? P.tiles_per_set : (P.N + NP - 1) / NP;
+  const long n_tiles = P.mode == 2 ? tiles_per_set * P.n_sets : tiles_per_set;
   const long n_iter = (n_tiles + gridDim.x - 1) / gridDim.x;
 
-  const int n_eval = P.mode == 0 ? 1 : 4 * rk.n_iv;
-  auto stage_of = [&](int e) -> const Stage& { return P.mode == 0 ? one : rk.st[e]; };
-  auto heavy_of = [&](const Stage& st) { return st.kind == 2 && P.reverse; };
+  const int n_eval = P.mode == 0 ? 1 : (P.mode == 1 ? 4 * rk.n_iv : 4 * P.sweep_n_iv);
+  // parameter set of iteration `it` of this CTA (0 outside sweeps); surplus tiles run the last set on padding
+  auto set_of = [&](long it) -> int {
+    if (P.mode != 2) return 0;
+    const long g = (blockIdx.x + it * gridDim.x) / tiles_per_set;
+    return (int)(g < P.n_sets ? g : P.n_sets - 1);
+  };
+  auto stage_of = [&](int e, int g) -> const Stage& { return P.mode == 0 ? one : (P.mode == 1 ? rk.st[e] : P.tabs[g].st[e]); };
+  auto heavy_of = [&](const Stage& st, int g) { return st.kind == 2 && (P.mode == 2 ? P.tabs[g].reverse : P.reverse) != 0; };
 
   if (warp == NEW) {
     // ===== TMA producer: weight tile images of every layer pass, in consumption order
@@ -314,7 +325,8 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
       const unsigned char* tiles = reinterpret_cast<const unsigned char*>(P.net.tc16_tiles);
       for (long it = 0; it < n_iter; ++it)
         for (int e = 0; e < n_eval; ++e) {
-          const int ng = heavy_of(stage_of(e)) ? 4 : 2;
+          const int gs = set_of(it);
+          const int ng = heavy_of(stage_of(e, gs), gs) ? 4 : 2;
           for (int g = 0; g < ng; ++g)
             for (int t = 0; t < 2 * NKB; ++t) {   // (m-tile, k-block) tiles of gemm g are contiguous
               mbar_wait_sleep(&empty[stage], phase ^ 1u);
@@ -337,7 +349,8 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
       uint32_t phase = 0, fphase = 0, bphase0 = 0, bphase1 = 0;
       for (long it = 0; it < n_iter; ++it)
         for (int e = 0; e < n_eval; ++e) {
-          const bool heavy = heavy_of(stage_of(e));
+          const int gs = set_of(it);
+          const bool heavy = heavy_of(stage_of(e, gs), gs);
           const int ng = heavy ? 4 : 2;
           if (blockIdx.x == 0 && it == 0 && e == 1)
             for (int i = 24; i < 29; ++i) g_tc16_stamps[i] = 0;
@@ -487,7 +500,11 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
 
     mbar_arrive(acc_free);   // nothing to read out before the very first m-tile
     for (long it = 0; it < n_iter; ++it) {
-      const long base = (blockIdx.x + it * gridDim.x) * NP;   // may lie beyond N: an all-padding tile
+      const long tile = blockIdx.x + it * gridDim.x;
+      const int gs = set_of(it);
+      // first particle of the tile; may lie beyond N: an all-padding tile
+      const long base = (P.mode == 2 ? (tile < n_tiles ? tile - (long)gs * tiles_per_set : tiles_per_set) : tile) * NP;
+      float* const out_set = P.out + (P.mode == 2 ? (size_t)gs * P.N * 2 : (size_t)0);
       if (warp < 2) {
         const long row = base + myp;
 #pragma unroll
@@ -501,8 +518,8 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
       ebar();
 #pragma unroll 1
       for (int ev = 0; ev < n_eval; ++ev) {
-        const Stage& st = stage_of(ev);
-        const bool heavy = heavy_of(st);
+        const Stage& st = stage_of(ev, gs);
+        const bool heavy = heavy_of(st, gs);
         const bool stamp = blockIdx.x == 0 && it == 0 && ev == 1 && tid == 0;
         if (stamp) g_tc16_stamps[0] = clock64();
         // ---- layer 1 (K = 3, computed directly): a1 and, for interior evaluations, a1' = s'(z1) * (W0 d).
@@ -767,10 +784,10 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
             }
             if (row < P.N && !(fabsf(f) <= 3.0e38f)) atomicAdd(&g_tc16_nonfinite, 1ull);
             if (P.mode == 0) {
-              if (row < P.N) P.out[row * 2 + d] = f;
+              if (row < P.N) out_set[row * 2 + d] = f;
             } else {
               const int iv = ev >> 2, sg = ev & 3;
-              const float dt = rk.dt[iv], y = sy[d];
+              const float dt = P.mode == 2 ? P.tabs[gs].dt[iv] : rk.dt[iv], y = sy[d];
               float xn;
               if (sg == 0) {
                 sk1[d] = f;
@@ -786,7 +803,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
                 xn = __fadd_rn(y, __fmul_rn(__fmul_rn(sum, dt), 0.125f));
                 sy[d] = xn;
                 if (P.traj != nullptr && row < P.N) P.traj[((size_t)(iv + 1) * P.N + row) * 2 + d] = xn;
-                if (ev == n_eval - 1 && row < P.N) P.out[row * 2 + d] = xn;
+                if (ev == n_eval - 1 && row < P.N) out_set[row * 2 + d] = xn;
               }
               sxs[2 * myp + d] = xn;
             }
@@ -846,7 +863,7 @@ static int launch_tc16(const idff_weights_t* w, const idff_field_params_t* p, tc
   }
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
-  const long tiles = (P.N + tch::NP - 1) / tch::NP;
+  const long tiles = P.mode == 2 ? P.tiles_per_set * P.n_sets : (P.N + tch::NP - 1) / tch::NP;
   int grid = (int)(tiles < sms ? tiles : sms);
   grid = (grid + 1) & ~1;   // CTA pairs
   static thread_local Rk4Table rk0;
@@ -891,6 +908,49 @@ int tensor16_field_eval(const idff_weights_t* w, const idff_field_params_t* p, f
   Stage st;
   make_stage(*p, t, &st);
   return launch_tc16(w, p, P, nullptr, &st, stream);
+}
+
+// One launch for n_sets parameter sets over the same x0 and grid (the gamma sweeps of the 2-D scripts).
+int tensor16_sample_rk4_sweep(const idff_weights_t* w, const idff_field_params_t* params, int n_sets, const float* d_x0,
+                              const Stage* stages, const float* dts, int n_iv, float* d_out, int64_t N, void* stream) {
+  if (n_iv > kMaxSweepIntervals) {
+    set_error("3xFP16 sweep: %d intervals exceed the per-launch table (%d)", n_iv, kMaxSweepIntervals);
+    return IDFF_EUNSUPPORTED;
+  }
+  idff_weights_t* wm = const_cast<idff_weights_t*>(w);
+  const size_t bytes = sizeof(SweepTab) * (size_t)n_sets;
+  if (wm->sweep_bytes < bytes) {
+    if (wm->d_sweep) cudaFree(wm->d_sweep);
+    wm->d_sweep = nullptr;
+    wm->sweep_bytes = 0;
+    IDFF_CUDA(cudaMalloc(&wm->d_sweep, bytes));
+    wm->sweep_bytes = bytes;
+  }
+  static thread_local std::vector<SweepTab> host;
+  host.assign((size_t)n_sets, SweepTab());
+  for (int g = 0; g < n_sets; ++g) {
+    if (!tensor16_supports(w, &params[g])) {
+      set_error("3xFP16 sweep: parameter set %d is not served by this kernel", g);
+      return IDFF_EUNSUPPORTED;
+    }
+    int nj, rev;
+    jets_needed(params[g], &nj, &rev);
+    memset(&host[g], 0, sizeof(SweepTab));
+    host[g].reverse = rev;
+    memcpy(host[g].dt, dts, sizeof(float) * n_iv);
+    memcpy(host[g].st, stages + (size_t)g * 4 * n_iv, sizeof(Stage) * 4 * n_iv);
+  }
+  // pageable source: the runtime stages the copy before returning, `host` may be reused by the next call
+  IDFF_CUDA(cudaMemcpyAsync(wm->d_sweep, host.data(), bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  tch::TParams P;
+  fill_tparams16(w, &params[0], 2, N, &P);
+  P.n_sets = n_sets;
+  P.sweep_n_iv = n_iv;
+  const long tiles = ((long)N + tch::NP - 1) / tch::NP;
+  P.tiles_per_set = (tiles + 1) & ~1L;
+  P.tabs = reinterpret_cast<const SweepTab*>(wm->d_sweep);
+  P.x_in = d_x0; P.out = d_out;
+  return launch_tc16(w, &params[0], P, nullptr, nullptr, stream);
 }
 
 int tensor16_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, const float* d_x0, const Stage* stages,

@@ -254,6 +254,7 @@ extern "C" int idff_weights_create(const float* const* h_W, const float* const* 
   v.tc_tiles = tc_layout ? d_blob + o_tc : nullptr;
   v.tc16_tiles = tc16_layout ? d_blob + o_tc16 : nullptr;
   h->d_stash = nullptr; h->stash_bytes = 0; h->tc_verified = 0;
+  h->d_sweep = nullptr; h->sweep_bytes = 0;
   *out = h;
   return IDFF_OK;
 }
@@ -262,6 +263,7 @@ extern "C" int idff_weights_destroy(idff_weights_t* w) {
   if (!w) return IDFF_OK;
   cudaFree(w->d_blob);
   if (w->d_stash) cudaFree(w->d_stash);
+  if (w->d_sweep) cudaFree(w->d_sweep);
   delete w;
   return IDFF_OK;
 }

@@ -39,6 +39,33 @@ def sample_rk4(model: _FieldBase, x0, t_span, return_traj=False, out=None):
     return traj if return_traj else final
 
 
+def sample_rk4_sweep(models, x0, t_span, out=None):
+    """The same x0 and grid solved under every field of `models` (wrappers around ONE packed network that differ in
+    gammas / order / sigma): -> (len(models), N, D) = traj[-1] per field.  One launch for the whole sweep where the
+    3xFP16 tensor kernel serves the fields (idff_sample_rk4_sweep), identical to per-field sample_rk4 calls."""
+    if len(models) == 0:
+        raise _lib.IdffError("sample_rk4_sweep: no fields given")
+    _lib.require_cuda(x0, "x0")
+    if x0.dim() != 2:
+        raise _lib.IdffError(f"x0 must be (N, D), got {tuple(x0.shape)}")
+    x0c = x0.detach().contiguous()
+    tg = np.ascontiguousarray(t_span.detach().cpu().numpy() if torch.is_tensor(t_span) else np.asarray(t_span),
+                              dtype=np.float32)
+    N, D = x0c.shape
+    pw = models[0]._packed(x0c.device)
+    for m in models[1:]:
+        if m._packed(x0c.device) is not pw:
+            raise _lib.IdffError("sample_rk4_sweep: every field must wrap the same packed network")
+    params = (_lib.FieldParams * len(models))(*[m.field_params(D) for m in models])
+    res = out if out is not None else torch.empty((len(models), N, D), device=x0c.device, dtype=torch.float32)
+    if tuple(res.shape) != (len(models), N, D) or not res.is_contiguous():
+        raise _lib.IdffError(f"out must be a contiguous {(len(models), N, D)} tensor")
+    _lib.check(_lib.lib().idff_sample_rk4_sweep(pw.handle, C.cast(params, C.c_void_p), len(models), _lib.ptr(x0c),
+                                                tg.ctypes.data_as(C.c_void_p), len(tg), _lib.ptr(res), N,
+                                                _lib.stream_of(x0c)), "idff_sample_rk4_sweep")
+    return res
+
+
 def odeint(func, y0, t, rtol=None, atol=None, method="rk4", options=None):
     """torchdiffeq.odeint for the fixed-grid 'rk4' method (rtol/atol are ignored by that solver). -> (len(t), *y0.shape)"""
     del rtol, atol, options

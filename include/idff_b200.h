@@ -107,6 +107,15 @@ int idff_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, const
                     const float* h_t_grid, int32_t n_grid, float* d_out_final, float* d_out_traj, int64_t N,
                     void* stream);
 
+/* ---- the gamma sweeps that call the sampler (find_best_gammas_mmd, Autograd_example_order2.py:281-303,
+ * 8x8 tuples; Autograd_example_order3.py:288-314, 10^3 tuples): the same x0 [N][dim] and t grid solved under n_sets
+ * parameter sets (params[g]: same variant and dim, any gammas / order / sigma).  d_out [n_sets][N][dim] = traj[-1] of every
+ * set.  One launch for all sets where the 3xFP16 tensor kernel serves them (the reference's 2048 particles fill 32 of 148
+ * SMs per tuple; 64 tuples fill the machine), otherwise one fused launch per set -- results are identical to calling
+ * idff_sample_rk4 per set either way. */
+int idff_sample_rk4_sweep(const idff_weights_t* w, const idff_field_params_t* params, int32_t n_sets, const float* d_x0,
+                          const float* h_t_grid, int32_t n_grid, float* d_out, int64_t N, void* stream);
+
 /* ---- a8 + a7 fused: torchsde.sdeint(sde, y0, ts, dt) for SDE_cal (MD_simulation.py:209,228); method 0 = srk
  * (torchsde default for ito/diagonal), 1 = euler.  Brownian increments are injected: d_I_k, d_I_k0
  * [n_steps][N][dim] with n_steps = idff_sde_num_steps(h_ts, n_ts, dt); d_I_k0 may be NULL for euler.

@@ -72,3 +72,47 @@ def test_md_autoregressive_generation_vs_oracle(cuda_device):
     assert m["RMSE"] < 1e-2 * max(1.0, np.abs(ref).max()) and m["CC"] > 0.999
     one = md.generate_onestep(packed("polyala", cuda_device), K, D, T, 3, 0.5, x_init.to(cuda_device), gamma1=0.2, gamma2=5.0)
     assert one.shape == (3, K, D) and torch.isfinite(one).all()
+
+
+def test_batched_sweep_equals_per_field_solves(cuda_device):
+    """idff_sample_rk4_sweep: one launch for many gamma tuples (mixed: with / without reverse sweep, order-1-like sets)
+    returns bit-for-bit what one idff_sample_rk4 call per tuple returns, for ragged particle counts and odd tile counts."""
+    import time
+
+    from idff_b200 import _lib, fields, sampler
+    pw = packed("checkerboard", cuda_device)
+    tuples = [(0.0, 0.0), (0.5, 0.0), (0.2, 0.0), (0.2, 0.2), (1.0, 2.0), (0.5, 0.3), (-0.5, 0.3)]
+    models = [fields.CustomNetModel(pw, 0.2, *g) for g in tuples]
+    for n in (2048 + 17, 64, 1, 4097):
+        x0 = torch.randn(n, 2, device=cuda_device, generator=torch.Generator(device=cuda_device).manual_seed(n)) / 1.5
+        for nfe in (2, 5):
+            ts = torch.linspace(0, 1, nfe + 1)
+            before = _lib.launch_count()
+            got = sampler.sample_rk4_sweep(models, x0, ts)
+            assert _lib.launch_count() == before + 1                       # ONE launch for the whole sweep
+            assert got.shape == (len(tuples), n, 2)
+            for k, m in enumerate(models):
+                assert torch.equal(got[k], sampler.sample_rk4(m, x0, ts)), (n, nfe, tuples[k])
+    # sets the tensor kernel does not serve (order 3 with gamma3 != 0) fall back to one launch per set, same results
+    m3 = [fields.CustomNetModelOrder3(pw, 0.2, 0.2, 0.2, g3) for g3 in (0.0, 0.2)]
+    x0 = torch.randn(512, 2, device=cuda_device) / 1.5
+    got = sampler.sample_rk4_sweep(m3, x0, torch.linspace(0, 1, 3))
+    for k, m in enumerate(m3):
+        assert torch.equal(got[k], sampler.sample_rk4(m, x0, torch.linspace(0, 1, 3)))
+    # the reference's sweep shape: 8 x 8 tuples, 2048 particles, nfe = 2 -- batched vs launch-per-tuple timing (reported)
+    grid8 = [0.0, 0.1, 0.2, 0.3, 0.5, 0.7, 1.0, 2.0]
+    ms = [fields.CustomNetModel(pw, 0.2, a, b) for a in grid8 for b in grid8]
+    x0 = torch.randn(2048, 2, device=cuda_device) / 1.5
+    ts = torch.linspace(0, 1, 3)
+    sampler.sample_rk4_sweep(ms, x0, ts)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sampler.sample_rk4_sweep(ms, x0, ts)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    for m in ms:
+        sampler.sample_rk4(m, x0, ts)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    print(f"64-tuple sweep, 2048 particles, nfe 2: batched {1e3 * (t1 - t0):.2f} ms, per tuple {1e3 * (t2 - t1):.2f} ms")
+    assert (t1 - t0) < (t2 - t1)
