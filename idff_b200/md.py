@@ -1,7 +1,9 @@
 """PolyALA autoregressive generation (TrajectoryGenerator.generate_trajectories / generate_onestep,
 timeseris_example/MD_simulation.py:197-230): T sequential SDE solves, each starting from the previous frame, each
 with its own embedding row (init_ind = t_idx) and gamma2/(1+t_idx).  Every frame is ONE launch of the fused SDE
-sampler over all trajectories; frames never leave the device (the reference round-trips through numpy every frame)."""
+sampler over all trajectories; frames never leave the device (the reference round-trips through numpy every frame).
+`GraphedGenerator` captures the whole T-frame chain (noise draws included) once as a CUDA graph: at the reference's 5
+trajectories the chain is T launch-bound solves, and a replay is one `cudaGraphLaunch`."""
 from __future__ import annotations
 
 import torch
@@ -29,6 +31,40 @@ def generate_trajectories(model, num_trajectories, data_dim, max_length, nfe, si
         traj = sampler.sdeint(sde, x1, ts, dt=dt, method=method, bm=bm, generator=generator)
         y_hat[t_idx] = traj[-1]
     return y_hat
+
+
+class GraphedGenerator:
+    """generate_trajectories captured as one CUDA graph.
+
+    gen = GraphedGenerator(model, K, D, T, nfe, sigma, gamma1, gamma2, dt); y_hat = gen.generate(x_init)
+    Every replay draws fresh Brownian increments on the device (graph-safe Philox offsets) unless `noise` tensors are
+    given at construction: noise = (I_k, I_k0), each (T, n_steps, K, D), read by the captured solves."""
+
+    def __init__(self, model, num_trajectories, data_dim, max_length, nfe, sigma, gamma1=1.0, gamma2=10.0, dt=0.3,
+                 device="cuda", method="srk", noise=None, warmup=1):
+        self.device = torch.device(device)
+        self.x_init = torch.zeros((num_trajectories, data_dim), device=self.device, dtype=torch.float32)
+        self._noise = noise
+        kw = dict(device=self.device, x_init=self.x_init, method=method,
+                  noise=(lambda t_idx, n: (noise[0][t_idx], noise[1][t_idx])) if noise is not None else None)
+        args = (model, num_trajectories, data_dim, max_length, nfe, sigma, gamma1, gamma2, dt)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):          # allocations, stash buffers and first-launch checks happen here
+                generate_trajectories(*args, **kw)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.y_hat = generate_trajectories(*args, **kw)
+
+    def generate(self, x_init=None) -> torch.Tensor:
+        """-> y_hat (T, K, D); the tensor is overwritten by the next call."""
+        if x_init is not None:
+            self.x_init.copy_(x_init)
+        self.graph.replay()
+        return self.y_hat
 
 
 def generate_onestep(model, num_trajectories, data_dim, max_length, nfe, sigma, x_prev, gamma1=1.0, gamma2=10.0,

@@ -102,13 +102,16 @@ def brownian_increments(n_steps, ts, dt, shape, device, generator=None):
     grid = [np.float32(tg[0])]
     while grid[-1] < tg[-1]:
         grid.append(min(np.float32(grid[-1] + np.float32(dt)), np.float32(tg[-1])))
-    h = torch.tensor(np.diff(np.array(grid, dtype=np.float32)), device=device)
+    h = np.diff(np.array(grid, dtype=np.float32))
     assert len(h) == n_steps
-    z1 = torch.randn((n_steps,) + tuple(shape), device=device, generator=generator)
-    z2 = torch.randn((n_steps,) + tuple(shape), device=device, generator=generator)
-    hs = h.view(-1, *([1] * len(shape)))
-    I_k = z1 * hs.sqrt()
-    I_k0 = 0.5 * hs * I_k + z2 * (hs ** 1.5) / math.sqrt(12.0)
+    I_k = torch.randn((n_steps,) + tuple(shape), device=device, generator=generator)
+    I_k0 = torch.randn((n_steps,) + tuple(shape), device=device, generator=generator)
+    # per-step scalings with host scalars (fp32 like the tensors): no host-to-device copy, so the draw can be captured
+    # in a CUDA graph
+    for s_ in range(n_steps):
+        hs = np.float32(h[s_])
+        I_k[s_].mul_(float(np.sqrt(hs)))
+        I_k0[s_].mul_(float(hs ** np.float32(1.5)) / math.sqrt(12.0)).add_(I_k[s_], alpha=float(np.float32(0.5) * hs))
     return I_k, I_k0
 
 

@@ -116,3 +116,41 @@ def test_batched_sweep_equals_per_field_solves(cuda_device):
     t2 = time.perf_counter()
     print(f"64-tuple sweep, 2048 particles, nfe 2: batched {1e3 * (t1 - t0):.2f} ms, per tuple {1e3 * (t2 - t1):.2f} ms")
     assert (t1 - t0) < (t2 - t1)
+
+
+def test_md_generation_as_cuda_graph(cuda_device):
+    """The T-frame autoregressive chain captured as one CUDA graph replays bit-for-bit what the eager loop computes
+    (injected Brownian increments), and draws fresh noise on every replay when none is injected."""
+    import time
+    K, D, T, NFE, dt = 5, 46, 6, 3, 0.3
+    pw = packed("polyala", cuda_device)
+    ts = torch.linspace(0, 1, NFE)
+    from idff_b200 import sampler
+    ns = sampler.sde_num_steps(ts, dt)
+    g = torch.Generator(device=cuda_device).manual_seed(3)
+    ik = torch.randn(T, ns, K, D, device=cuda_device, generator=g) * 0.5
+    ik0 = torch.randn(T, ns, K, D, device=cuda_device, generator=g) * 0.1
+    x_init = torch.randn(K, D, device=cuda_device, generator=g)
+    eager = md.generate_trajectories(pw, K, D, T, NFE, sigma=0.5, gamma1=0.2, gamma2=5.0, dt=dt, device=cuda_device,
+                                     x_init=x_init, noise=lambda t_idx, n: (ik[t_idx], ik0[t_idx]))
+    gen = md.GraphedGenerator(pw, K, D, T, NFE, sigma=0.5, gamma1=0.2, gamma2=5.0, dt=dt, device=cuda_device, noise=(ik, ik0))
+    assert torch.isfinite(eager).all()
+    assert torch.equal(gen.generate(x_init), eager)
+    assert torch.equal(gen.generate(x_init * 0.5), md.generate_trajectories(
+        pw, K, D, T, NFE, sigma=0.5, gamma1=0.2, gamma2=5.0, dt=dt, device=cuda_device, x_init=x_init * 0.5,
+        noise=lambda t_idx, n: (ik[t_idx], ik0[t_idx])))
+    fresh = md.GraphedGenerator(pw, K, D, T, NFE, sigma=0.5, gamma1=0.2, gamma2=5.0, dt=dt, device=cuda_device)
+    a = fresh.generate(x_init).clone()
+    b = fresh.generate(x_init).clone()
+    assert torch.isfinite(a).all() and torch.isfinite(b).all() and not torch.equal(a, b)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        fresh.generate(x_init)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    for _ in range(5):
+        md.generate_trajectories(pw, K, D, T, NFE, sigma=0.5, gamma1=0.2, gamma2=5.0, dt=dt, device=cuda_device, x_init=x_init)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    print(f"PolyALA chain, {T} frames x {K} trajectories: graph {1e3 * (t1 - t0) / 5:.2f} ms, eager {1e3 * (t2 - t1) / 5:.2f} ms")
