@@ -125,6 +125,11 @@ extern "C" int idff_field_eval(const idff_weights_t* w, const idff_field_params_
   IDFF_CHECK_ARG(p->variant != IDFF_FIELD_CFM || t == 0.0f || d_x0, "idff_field_eval: the CFM field needs x0 (captured at t == 0) when t != 0");
   DeviceGuard g(w->device);
   if (p->impl == IDFF_IMPL_LAYERED) return wide_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
+  if (p->impl == IDFF_IMPL_AUTO && w->v.w == 256 && N >= 2048 && !tensor16_supports(w, p)) {
+    idff_field_params_t q = *p;   // order 3 at width 256: the layered 3xFP16 engine (see idff_sample_rk4)
+    q.impl = IDFF_IMPL_LAYERED;
+    if (wide_supports(w, &q)) return wide_field_eval(w, &q, t, d_x, d_x0, d_out, N, stream);
+  }
   if ((p->impl == IDFF_IMPL_TENSOR || p->impl == IDFF_IMPL_AUTO) && wide_supports(w, p) && (p->impl == IDFF_IMPL_TENSOR || N >= 2048))
     return wide_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
   if (p->impl == IDFF_IMPL_TENSOR16 || (p->impl == IDFF_IMPL_AUTO && tensor16_supports(w, p) && N >= 4096))
@@ -179,8 +184,9 @@ extern "C" int idff_sample_rk4(const idff_weights_t* w, const idff_field_params_
     return wide_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream);
   if (p->impl == IDFF_IMPL_TENSOR16 || (p->impl == IDFF_IMPL_AUTO && tensor16_supports(w, p)))
     return tensor16_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream);
-  if (p->impl == IDFF_IMPL_AUTO && w->v.w == 256 && N >= 16384 && !tensor_supports(w, p)) {
-    // three jets do not fit the fused tensor kernel; measured: layered tcgen05 engine 60 M vs FFMA2 kernel 48 M steps/s
+  if (p->impl == IDFF_IMPL_AUTO && w->v.w == 256 && N >= 2048 && !tensor16_supports(w, p)) {
+    // three jets do not fit the fused tensor kernel; measured: layered 3xFP16 engine 35 / 81 / 120-135 M particle-steps/s
+    // at N = 2048 / 8192 / >= 32768 vs 20 / 41 / 48 M for the FFMA2 kernel
     idff_field_params_t q = *p;
     q.impl = IDFF_IMPL_LAYERED;
     if (wide_supports(w, &q))

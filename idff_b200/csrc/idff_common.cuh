@@ -64,7 +64,7 @@ struct NetView {
   const float* fw2r;  // [w][w]  fw2r[n][p] = W2[n][perm(p)]   reverse,  layer 3 -> 2
   const float* fw1r;  // [w][w]  fw1r[n][p] = W1[n][perm(p)]   reverse,  layer 2 -> 1
   const float* w0n;   // [w][din-1]  W0[n][d], d < D            reverse,  layer 1 -> x  (wide-D path)
-  // tcgen05 operand tiles (w % 128 == 0, 3 -> w -> w -> w -> 2 networks): [gemm 0..3][m-tile < w/128][k-block < w/32][hi, lo]
+  // tcgen05 3xTF32 operand tiles of k_tc (w == 256, 3 -> w -> w -> w -> 2 networks): [gemm 0..3][m-tile < w/128][k-block < w/32][hi, lo]
   // [128 rows x 32 tf32], each tile a
   // 16 KB shared-memory image in the canonical K-major SWIZZLE_128B layout (row r at r*128 B, 16-byte chunk c stored at
   // chunk c ^ (r & 7)), so one cp.async.bulk lands it ready for the UMMA descriptor.  gemm 0: W1 (rows = out units),
@@ -75,6 +75,9 @@ struct NetView {
   // c ^ (r & 7)).  hi = fp16_rn(w), lo' = fp16_rn((w - hi) * 2^11).  Same gemm numbering as tc_tiles.  Tile row r holds
   // unit (r & ~31) + 4*slot(r & 7) + ((r >> 3) & 3) of the m-tile (see idff_sampler_tc16.cu).
   const float* tc16_tiles;
+  // 3xFP16 operand tiles of the layered engine (w % 128 == 0, 256..2048): [gemm 0..3][m-tile < w/128][k-block < w/64][hi, lo']
+  // [128 rows x 64 fp16], same images as tc16_tiles but with the rows in natural unit order (tile row r = unit r).
+  const float* tcw16_tiles;
 };
 
 }  // namespace idff

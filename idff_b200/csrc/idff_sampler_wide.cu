@@ -1,22 +1,27 @@
-// Layer-by-layer tensor-core IDFF sampler for WIDE networks (3 -> w -> w -> w -> 2, w a multiple of 128, 512..2048):
+// Layer-by-layer tensor-core IDFF sampler for WIDE networks (3 -> w -> w -> w -> 2, w a multiple of 128, 256..2048):
 // BASELINE.json configs[2] (order-3 field, large-width MLP).  Activations of a w >= 512 layer do not fit on chip, so
-// every layer pass is a persistent tcgen05 3xTF32 GEMM over activations that live in global memory (L2/HBM) already in
-// the tensor core's operand format; the SELU jet / adjoint algebra is the epilogue of that GEMM.
+// every layer pass is a persistent tcgen05 3xFP16 GEMM (kind::f16, fp32 accumulation in TMEM; the split of
+// idff_sampler_tc16.cu: v = hi + 2^-11 lo', D = W_hi X_hi + 2^-11 (W_hi X_lo' + W_lo' X_hi)) over activations that live in
+// global memory (L2/HBM) already in the tensor core's operand format; the SELU jet / adjoint algebra is the epilogue.
 //
-//   D[unit][col] = sum_k W[unit][k] * X[col][k]          col = jet*PPT + particle, 64 columns per column tile
+//   D[unit][col] = sum_k W[unit][k] * X[col][k]          col = jet*PPT + particle, 128 columns per column tile
 //
-//   * X operand in global memory: per (column tile, 32-wide k-block) a 16 KB image of a K-major SWIZZLE_128B tile,
-//     rows 0..63 the hi copy, rows 64..127 the lo copy -- one cp.async.bulk per stage lands it next to the 32 KB (hi|lo)
-//     weight tile; [main | corr] += W_hi*[X_hi;X_lo] (N = 128 MMA), corr += W_lo*X_hi (N = 64 MMA), as in k_tc.
+//   * X operand in global memory: per (column tile, 64-wide k-block) a 32 KB image of a K-major SWIZZLE_128B tile,
+//     rows 0..127 the hi copy, rows 128..255 the lo' copy -- one cp.async.bulk per stage lands it next to the 32 KB
+//     (hi|lo') weight tile; [main | corr] += W_hi*[X_hi;X_lo'] (N = 256 MMA), corr += W_lo'*X_hi (N = 128 MMA): the two
+//     shapes the tensor core runs at full rate [measured, profiles/microbench/tc_f16.cu].
 //   * work items (column tile, m-tile) are spread over persistent CTAs; accumulators are double buffered in TMEM
-//     (2 buffers x 2 k-parity sets x [main 64 | corr 64] = 512 columns), so the epilogue of item i overlaps the MMAs
-//     of item i+1; 4-stage TMA ring of 48 KB stages.
-//   * epilogue thread <-> (hidden unit, half of the tile's particles): reads its TMEM lane, applies the layer's jet or
-//     adjoint formulas and writes the next layer's operand straight into the global tile images (128 B per warp store),
-//     the layer-2 derivative stash, or per-(m-tile, lane-quarter) partial sums of the two small layers
+//     (2 buffers x [main 128 | corr 128] = 512 columns), so the epilogue of item i overlaps the MMAs of item i+1;
+//     3-stage TMA ring of 64 KB stages.
+//   * epilogue thread <-> (hidden unit, quarter of the tile's particles): reads its TMEM lane, applies the layer's jet
+//     or adjoint formulas and writes the next layer's operand straight into the global tile images (64 B per warp
+//     store), the layer-2 derivative stash, or per-(m-tile, lane-quarter) partial sums of the two small layers
 //     (x1hat = W3 a3, grad_x = W0^T P1), which the update kernel adds in a fixed order.
 // One call = chunks of particles x (1 + 2|4 + 1) launches per field evaluation; the particle state, the stash and the
-// operand buffers are scratch owned by the weights handle.
+// operand buffers are scratch owned by the weights handle.  As in k_tc16, values beyond the fp16 range turn that
+// particle's output into NaN (columns never mix); IDFF_IMPL_GENERIC serves such networks.
+#include <cuda_fp16.h>
+
 #include <algorithm>
 
 #include "idff_common.cuh"
@@ -41,15 +46,17 @@ static int verify_tc_launch(idff_weights_t* w, void* stream, int bit) {
 
 namespace wide {
 
-constexpr int NCOL = 64;                 // columns per column tile (jets x particles, padded)
-constexpr int XT_BYTES = 2 * NCOL * 128; // one k-block of the X operand: hi rows then lo rows (16 KB)
-constexpr int WT_BYTES = 32768;          // one (hi|lo) weight tile
+constexpr int NCOL = 128;                // columns per column tile (jets x particles, padded)
+constexpr int XT_BYTES = 2 * NCOL * 128; // one 64-wide k-block of the X operand: hi rows then lo' rows (32 KB)
+constexpr int WT_BYTES = 32768;          // one (hi|lo') weight tile [128 units x 64 k] fp16
 constexpr int STAGE_BYTES = WT_BYTES + XT_BYTES;
-constexpr int NSTAGE = 4;
-constexpr int NEW = 8;                   // epilogue warps: lane quarter = w % 4, particle half = w / 4
+constexpr int NSTAGE = 3;
+constexpr int NEW = 16;                  // epilogue warps: lane quarter = w % 4, particle quarter = w / 4
+constexpr int NPART = NEW / 4;
 constexpr int NE = NEW * 32;
 constexpr int NTHREADS = NE + 64;        // + producer warp + MMA warp
-constexpr int COL_SET = 128, COL_CORR = 64, COL_BUF = 256;
+constexpr int COL_CORR = 128, COL_BUF = 256;
+constexpr float LO_SCALE = 2048.0f, LO_INV = 1.0f / 2048.0f;
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
@@ -88,10 +95,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
 }
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -104,19 +111,32 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ float rn_tf32(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
 
 // ---- layouts ----------------------------------------------------------------------------------------------------------
 // NJ jets -> PPT particles per column tile; column of (jet j, particle p) = j*PPT + p; columns >= NJ*PPT are padding.
-__host__ __device__ constexpr int ppt_of(int nj) { return nj == 1 ? 64 : (nj == 2 ? 32 : 16); }
+__host__ __device__ constexpr int ppt_of(int nj) { return nj == 1 ? 128 : (nj == 2 ? 64 : 32); }
 
-// byte offset of element (col, k) inside the X operand of one column tile (KB k-blocks of XT_BYTES)
+// byte offset of fp16 element (col, k) inside the X operand of one column tile (KB k-blocks of XT_BYTES)
 __device__ __forceinline__ size_t xt_off(int col, int k, int lo) {
-  return (size_t)(k >> 5) * XT_BYTES + (size_t)(lo * NCOL + col) * 128 + ((((k >> 2) & 7) ^ (col & 7)) << 4) + ((k & 3) << 2);
+  return (size_t)(k >> 6) * XT_BYTES + (size_t)(lo * NCOL + col) * 128 + ((((k >> 3) & 7) ^ (col & 7)) << 4) + ((k & 7) << 1);
+}
+// hi / lo' halves of v for column col, unit k
+__device__ __forceinline__ void put16(unsigned char* xt, int col, int k, float v) {
+  const __half h = __float2half_rn(v);
+  const __half l = __float2half_rn(__fmul_rn(__fsub_rn(v, __half2float(h)), LO_SCALE));
+  *reinterpret_cast<__half*>(xt + xt_off(col, k, 0)) = h;
+  *reinterpret_cast<__half*>(xt + xt_off(col, k, 1)) = l;
+}
+
+// Boundary evaluations (t = 0, t = 1: one jet) of a field with >= 2 jets: the jet-1 column slot is free, so the K sum is
+// split over the two slots by k-block parity -- unit k's value goes to slot (k / 64) % 2, an exact zero to the other.
+// Adding exact zeros costs no rounding, so each accumulator sees half as many truncating accumulation steps where the
+// t = 1 branch amplifies the network's error x100.
+template <int PPT>
+__device__ __forceinline__ void put_light(unsigned char* xt, int p, int k, float v) {
+  const int odd = (k >> 6) & 1;
+  put16(xt, p, k, odd ? 0.0f : v);
+  put16(xt, PPT + p, k, odd ? v : 0.0f);
 }
 
 struct WParams {
@@ -129,8 +149,8 @@ struct WParams {
   Stage st;
   const unsigned char* xin;    // X operand in  [ctile][KB][XT_BYTES]
   unsigned char* xout;         // X operand out
-  float* stash;                // [ctile][MT][2 halves][NJ*HP][128]
-  float* part;                 // [ctile][MT][4 quarters][2 halves][2*HP]   partial sums of a small layer
+  float* stash;                // [ctile][MT][NPART][NJ*HP][128]
+  float* part;                 // [ctile][MT][4 lane quarters][NPART][2*HP]   partial sums of a small layer
   const float* xs;             // [P][2] stage input (layer-1 recompute in the last reverse pass)
 };
 
@@ -187,12 +207,11 @@ __global__ void __launch_bounds__(256) k_wide_l1(const __grid_constant__ WParams
       const float a = selu_fwd(z, code);
       selu_decode(code, s1, E);
       float vals[3] = {a, s1 * zd, E * zd * zd};
+      if (NJ >= 2 && !P.heavy) {
+        put_light<PPT>(xt, p, n, vals[0]);
+      } else {
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        const float v = (j == 0 || P.heavy) ? vals[j] : 0.0f;
-        const float h = rn_tf32(v);
-        *reinterpret_cast<float*>(xt + xt_off(j * PPT + p, n, 0)) = h;
-        *reinterpret_cast<float*>(xt + xt_off(j * PPT + p, n, 1)) = v - h;
+        for (int j = 0; j < NJ; ++j) put16(xt, j * PPT + p, n, (j == 0 || P.heavy) ? vals[j] : 0.0f);
       }
     }
   }
@@ -201,7 +220,7 @@ __global__ void __launch_bounds__(256) k_wide_l1(const __grid_constant__ WParams
 // ---- one layer pass -------------------------------------------------------------------------------------------------------
 template <int NJ>
 __global__ void __launch_bounds__(NTHREADS, 1) k_wide_layer(const __grid_constant__ WParams P) {
-  constexpr int PPT = ppt_of(NJ), HP = PPT / 2;
+  constexpr int PPT = ppt_of(NJ), HP = PPT / NPART;
   extern __shared__ __align__(1024) unsigned char smem[];
   if ((s32(smem) & 1023u) != 0u) {   // SWIZZLE_128B operands need a 1024-byte aligned base: report and do nothing
     if (threadIdx.x == 0) g_tc_misaligned = 1;
@@ -229,7 +248,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_wide_layer(const __grid_constan
   const uint32_t tmem = *tmem_slot;
   const int MT = P.MT, KB = P.KB;
   const long n_items = (long)P.n_ctiles * MT;
-  const unsigned char* wt = reinterpret_cast<const unsigned char*>(P.net.tc_tiles) + (size_t)P.gemm * MT * KB * WT_BYTES;
+  const unsigned char* wt = reinterpret_cast<const unsigned char*>(P.net.tcw16_tiles) + (size_t)P.gemm * MT * KB * WT_BYTES;
 
   if (warp == NEW) {
     if (lane == 0) {
@@ -249,8 +268,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_wide_layer(const __grid_constan
     }
   } else if (warp == NEW + 1) {
     if (lane == 0) {
-      const uint32_t idesc_w = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * NCOL >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t idesc_n = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // kind::f16: D fp32 (bit 4), A = B = fp16 (format 0), K-major, N >> 3 at bit 17, M >> 4 at bit 24
+      const uint32_t idesc_w = (1u << 4) | ((uint32_t)(2 * NCOL >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc_n = (1u << 4) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       int stage = 0, q = 0;
       uint32_t phase = 0, ephase[2] = {0, 0};
       for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -261,12 +281,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_wide_layer(const __grid_constan
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t whi = s32(smem + stage * STAGE_BYTES), wlo = whi + 16384, xop = whi + WT_BYTES;
-          const uint32_t dset = tmem + q * COL_BUF + (kb & 1) * COL_SET;
+          const uint32_t dset = tmem + q * COL_BUF;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t a_hi = make_desc(whi + ks * 32), a_lo = make_desc(wlo + ks * 32), b_w = make_desc(xop + ks * 32);
-            mma_tf32(dset, a_hi, b_w, idesc_w, ((kb >> 1) | ks) != 0);
-            mma_tf32(dset + COL_CORR, a_lo, b_w, idesc_n, 1u);
+            mma_f16(dset, a_hi, b_w, idesc_w, (kb | ks) != 0);   // [main | corr] += W_hi * [X_hi ; X_lo']
+            mma_f16(dset + COL_CORR, a_lo, b_w, idesc_n, 1u);    // corr += W_lo' * X_hi
           }
           mma_commit(&empty[stage]);
           if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
@@ -295,28 +315,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_wide_layer(const __grid_constan
         if (j == 0 || P.heavy) {
 #pragma unroll
           for (int c8 = 0; c8 < HP / 8; ++c8) {
-            uint32_t m0[8], c0[8], m1[8], c1[8];
+            uint32_t m0[8], c0[8];
             const int col = j * PPT + p0 + c8 * 8;
             tmem_ld8(lane_base + col, m0);
             tmem_ld8(lane_base + COL_CORR + col, c0);
-            tmem_ld8(lane_base + COL_SET + col, m1);
-            tmem_ld8(lane_base + COL_SET + COL_CORR + col, c1);
             tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              acc[j][c8 * 8 + i] = (__uint_as_float(m0[i]) + __uint_as_float(m1[i])) + (__uint_as_float(c0[i]) + __uint_as_float(c1[i]));
+            for (int i = 0; i < 8; ++i) acc[j][c8 * 8 + i] = fmaf(__uint_as_float(c0[i]), LO_INV, __uint_as_float(m0[i]));
           }
         } else {
 #pragma unroll
           for (int i = 0; i < HP; ++i) acc[j][i] = 0.0f;
         }
+      if (NJ >= 2 && !P.heavy) {
+        // boundary evaluation: the K sum was split by k-block parity over the jet-0 / jet-1 column slots (see put_light)
+#pragma unroll
+        for (int c8 = 0; c8 < HP / 8; ++c8) {
+          uint32_t m1[8], c1[8];
+          const int col = PPT + p0 + c8 * 8;
+          tmem_ld8(lane_base + col, m1);
+          tmem_ld8(lane_base + COL_CORR + col, c1);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[0][c8 * 8 + i] += fmaf(__uint_as_float(c1[i]), LO_INV, __uint_as_float(m1[i]));
+        }
+      }
       tc_fence_before();
       mbar_arrive(&acc_empty[q]);
       q ^= 1;
 
       unsigned char* xt = P.xout + (size_t)ct * KB * XT_BYTES;
-      float* stash = P.stash + ((((size_t)ct * MT + mt) * 2 + h) * (NJ * HP)) * 128 + lq * 32 + lane;
-      float* part = P.part + ((((size_t)ct * MT + mt) * 4 + lq) * 2 + h) * (2 * HP);
+      float* stash = P.stash + ((((size_t)ct * MT + mt) * NPART + h) * (NJ * HP)) * 128 + lq * 32 + lane;
+      float* part = P.part + ((((size_t)ct * MT + mt) * 4 + lq) * NPART + h) * (2 * HP);
       if (P.gemm == 0) {
         // layer 2 forward: activations of all jets, derivative stash
         const float bb = __ldg(P.net.b1 + n);
@@ -333,13 +363,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_wide_layer(const __grid_constan
             if (NJ >= 2) stash[((NJ >= 2 ? 1 : 0) * HP + i) * 128] = acc[NJ >= 2 ? 1 : 0][i];
             if (NJ >= 3) stash[((NJ >= 3 ? 2 : 0) * HP + i) * 128] = acc[NJ >= 3 ? 2 : 0][i];
           }
+          if (NJ >= 2 && !P.heavy) {
+            put_light<PPT>(xt, p0 + i, n, vals[0]);
+          } else {
 #pragma unroll
-          for (int j = 0; j < NJ; ++j)
-            if (j == 0 || P.heavy) {
-              const float hv = rn_tf32(vals[j]);
-              *reinterpret_cast<float*>(xt + xt_off(j * PPT + p0 + i, n, 0)) = hv;
-              *reinterpret_cast<float*>(xt + xt_off(j * PPT + p0 + i, n, 1)) = vals[j] - hv;
-            }
+            for (int j = 0; j < NJ; ++j)
+              if (j == 0 || P.heavy) put16(xt, j * PPT + p0 + i, n, vals[j]);
+          }
         }
       } else if (P.gemm == 1) {
         // layer 3 forward: x1hat partial sums, adjoint seeds of c1*phi + c2*D_d phi + c3*D_d^2 phi
@@ -364,9 +394,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_wide_layer(const __grid_constan
             vals[2] = A2 * s1;
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
-              const float hv = rn_tf32(vals[j]);
-              *reinterpret_cast<float*>(xt + xt_off(j * PPT + p0 + i, n, 0)) = hv;
-              *reinterpret_cast<float*>(xt + xt_off(j * PPT + p0 + i, n, 1)) = vals[j] - hv;
+              put16(xt, j * PPT + p0 + i, n, vals[j]);
             }
           }
         }
@@ -389,9 +417,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_wide_layer(const __grid_constan
           vals[2] = A2 * s1;
 #pragma unroll
           for (int j = 0; j < NJ; ++j) {
-            const float hv = rn_tf32(vals[j]);
-            *reinterpret_cast<float*>(xt + xt_off(j * PPT + p0 + i, n, 0)) = hv;
-            *reinterpret_cast<float*>(xt + xt_off(j * PPT + p0 + i, n, 1)) = vals[j] - hv;
+            put16(xt, j * PPT + p0 + i, n, vals[j]);
           }
         }
       } else {
@@ -427,13 +453,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_wide_layer(const __grid_constan
 // ---- sum the partials of a small layer over (m-tile, lane quarter) in a fixed order ----------------------------------------
 template <int NJ>
 __global__ void k_wide_sum(const __grid_constant__ WParams P, float* __restrict__ dst) {
-  constexpr int PPT = ppt_of(NJ), HP = PPT / 2;
+  constexpr int PPT = ppt_of(NJ), HP = PPT / NPART;
   for (long o = (long)blockIdx.x * blockDim.x + threadIdx.x; o < P.P * 2; o += (long)gridDim.x * blockDim.x) {
     const long row = o >> 1;
     const int d = (int)(o & 1), ct = (int)(row / PPT), p = (int)(row - (long)ct * PPT), h = p / HP, pl = p - h * HP;
     float s = 0.0f;
     for (int mt = 0; mt < P.MT; ++mt)
-      for (int lq = 0; lq < 4; ++lq) s += P.part[((((size_t)ct * P.MT + mt) * 4 + lq) * 2 + h) * (2 * HP) + 2 * pl + d];
+      for (int lq = 0; lq < 4; ++lq) s += P.part[((((size_t)ct * P.MT + mt) * 4 + lq) * NPART + h) * (2 * HP) + 2 * pl + d];
     dst[o] = s;
   }
 }
@@ -498,7 +524,7 @@ __global__ void k_wide_update(const __grid_constant__ UParams U) {
 bool wide_supports(const idff_weights_t* w, const idff_field_params_t* p) {
   const NetView& v = w->v;
   const int min_w = p->impl == IDFF_IMPL_LAYERED ? 256 : 512;   // at 256 the fused kernel is the default
-  if (v.tc_tiles == nullptr || v.w < min_w || p->dim != 2 || v.din != 3 || v.dout != 2) return false;
+  if (v.tcw16_tiles == nullptr || v.w < min_w || p->dim != 2 || v.din != 3 || v.dout != 2) return false;
   return p->variant == IDFF_FIELD_MOMENTUM || p->variant == IDFF_FIELD_CFM;
 }
 
@@ -511,16 +537,19 @@ static int wide_run(const idff_weights_t* w, const idff_field_params_t* p, int m
                     const Stage* stages, const float* dts, int n_eval, float* d_out, float* d_traj, int64_t N, void* stream) {
   using namespace wide;
   if (!wide_supports(w, p)) {
-    set_error("wide tensor-core sampler: needs a 3-w-w-w-2 network with w in {512..2048} (multiple of 128), dim 2");
+    set_error("wide tensor-core sampler: needs a 3-w-w-w-2 network with w in {256..2048} (multiple of 128), dim 2");
     return IDFF_EUNSUPPORTED;
   }
   cudaStream_t s = (cudaStream_t)stream;
   int nj, rev;
   jets_needed(*p, &nj, &rev);
   const NetView& v = w->v;
-  const int W = v.w, MT = W / 128, KB = W / 32, PPT = ppt_of(nj), HP = PPT / 2;
+  const int W = v.w, MT = W / 128, KB = W / 64, PPT = ppt_of(nj), HP = PPT / NPART;
   // chunk of particles whose scratch stays around 3 GB
-  const size_t per_ctile = (size_t)2 * KB * XT_BYTES + (size_t)MT * 2 * nj * HP * 128 * 4 + (size_t)MT * 4 * 2 * 2 * HP * 4;
+  // boundary evaluations of a one-jet field run in the two-jet tile geometry (64 particles per tile) so that they too
+  // have a free column slot for the split-K accumulation (put_light): twice the column tiles for those evaluations
+  const int nj_light = nj < 2 ? 2 : nj, xmul = ppt_of(nj) / ppt_of(nj_light);
+  const size_t per_ctile = (size_t)2 * xmul * KB * XT_BYTES + (size_t)MT * NPART * nj * HP * 128 * 4 + (size_t)MT * 4 * NPART * 2 * HP * 4;
   long chunk_ctiles = (long)std::max<size_t>(1, ((size_t)3 << 30) / per_ctile);
   const long total_ctiles = (N + PPT - 1) / PPT;
   if (chunk_ctiles > total_ctiles) chunk_ctiles = total_ctiles;
@@ -537,10 +566,10 @@ static int wide_run(const idff_weights_t* w, const idff_field_params_t* p, int m
   WideScratch sc;
   {
     unsigned char* b = reinterpret_cast<unsigned char*>(wm->d_stash);
-    sc.xa = b; b += (size_t)chunk_ctiles * KB * XT_BYTES;
-    sc.xb = b; b += (size_t)chunk_ctiles * KB * XT_BYTES;
-    sc.stash = reinterpret_cast<float*>(b); b += (size_t)chunk_ctiles * MT * 2 * nj * HP * 128 * 4;
-    sc.part = reinterpret_cast<float*>(b); b += (size_t)chunk_ctiles * MT * 4 * 2 * 2 * HP * 4;
+    sc.xa = b; b += (size_t)chunk_ctiles * xmul * KB * XT_BYTES;
+    sc.xb = b; b += (size_t)chunk_ctiles * xmul * KB * XT_BYTES;
+    sc.stash = reinterpret_cast<float*>(b); b += (size_t)chunk_ctiles * MT * NPART * nj * HP * 128 * 4;
+    sc.part = reinterpret_cast<float*>(b); b += (size_t)chunk_ctiles * MT * 4 * NPART * 2 * HP * 4;
     float* f = reinterpret_cast<float*>(b);
     const size_t n2 = (size_t)chunkP * 2;
     sc.pred = f; sc.grad = f + n2; sc.y = f + 2 * n2; sc.k1 = f + 3 * n2; sc.k2 = f + 4 * n2; sc.k3 = f + 5 * n2;
@@ -553,7 +582,9 @@ static int wide_run(const idff_weights_t* w, const idff_field_params_t* p, int m
     IDFF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     return IDFF_OK;
   };
-  int rc = nj == 1 ? set_attr(k_wide_layer<1>) : (nj == 2 ? set_attr(k_wide_layer<2>) : set_attr(k_wide_layer<3>));
+  int rc = set_attr(k_wide_layer<1>);
+  if (!rc) rc = set_attr(k_wide_layer<2>);
+  if (!rc) rc = set_attr(k_wide_layer<3>);
   if (rc) return rc;
 
   for (long c0 = 0; c0 < total_ctiles; c0 += chunk_ctiles) {
@@ -567,31 +598,33 @@ static int wide_run(const idff_weights_t* w, const idff_field_params_t* p, int m
     for (int e = 0; e < n_eval; ++e) {
       const Stage& st = stages[e];
       const int heavy = (st.kind == 2 && rev) ? 1 : 0;
+      const int njk = heavy ? nj : nj_light, PPTk = ppt_of(njk);
+      const long nctk = (Pn + PPTk - 1) / PPTk;
       WParams P;
       memset(&P, 0, sizeof(P));
-      P.net = v; P.w = W; P.MT = MT; P.KB = KB; P.nj = nj; P.ppt = PPT; P.n_ctiles = (int)nct; P.P = Pn; P.heavy = heavy;
+      P.net = v; P.w = W; P.MT = MT; P.KB = KB; P.nj = njk; P.ppt = PPTk; P.n_ctiles = (int)nctk; P.P = Pn; P.heavy = heavy;
       P.st = st; P.stash = sc.stash; P.part = sc.part; P.xs = sc.xs;
-      const int ew_grid = (int)std::min<long>((nct * W + 255) / 256, (long)sms * 8);
+      const int ew_grid = (int)std::min<long>((nctk * W + 255) / 256, (long)sms * 8);
       P.xout = sc.xa;
-      if (nj == 1) k_wide_l1<1><<<ew_grid, 256, 0, s>>>(P);
-      else if (nj == 2) k_wide_l1<2><<<ew_grid, 256, 0, s>>>(P);
+      if (njk == 1) k_wide_l1<1><<<ew_grid, 256, 0, s>>>(P);
+      else if (njk == 2) k_wide_l1<2><<<ew_grid, 256, 0, s>>>(P);
       else k_wide_l1<3><<<ew_grid, 256, 0, s>>>(P);
       count_launch();
       const int ng = heavy ? 4 : 2;
-      const int lgrid = (int)std::min<long>(nct * MT, (long)sms);
+      const int lgrid = (int)std::min<long>(nctk * MT, (long)sms);
       for (int g = 0; g < ng; ++g) {
         P.gemm = g;
         P.xin = (g & 1) ? sc.xb : sc.xa;
         P.xout = (g & 1) ? sc.xa : sc.xb;
-        if (nj == 1) k_wide_layer<1><<<lgrid, NTHREADS, smem, s>>>(P);
-        else if (nj == 2) k_wide_layer<2><<<lgrid, NTHREADS, smem, s>>>(P);
+        if (njk == 1) k_wide_layer<1><<<lgrid, NTHREADS, smem, s>>>(P);
+        else if (njk == 2) k_wide_layer<2><<<lgrid, NTHREADS, smem, s>>>(P);
         else k_wide_layer<3><<<lgrid, NTHREADS, smem, s>>>(P);
         count_launch();
         if (g == 1 || g == 3) {
           float* dst = g == 1 ? sc.pred : sc.grad;
           const int sg_grid = (int)std::min<long>((Pn * 2 + 255) / 256, (long)sms * 8);
-          if (nj == 1) k_wide_sum<1><<<sg_grid, 256, 0, s>>>(P, dst);
-          else if (nj == 2) k_wide_sum<2><<<sg_grid, 256, 0, s>>>(P, dst);
+          if (njk == 1) k_wide_sum<1><<<sg_grid, 256, 0, s>>>(P, dst);
+          else if (njk == 2) k_wide_sum<2><<<sg_grid, 256, 0, s>>>(P, dst);
           else k_wide_sum<3><<<sg_grid, 256, 0, s>>>(P, dst);
           count_launch();
         }

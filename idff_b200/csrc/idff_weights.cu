@@ -111,11 +111,16 @@ extern "C" int idff_weights_create(const float* const* h_W, const float* const* 
   const size_t o_fwt1 = fused_layout ? take((size_t)w * w) : 0, o_fwt2 = fused_layout ? take((size_t)w * w) : 0;
   const size_t o_fw2r = fused_layout ? take((size_t)w * w) : 0, o_fw1r = fused_layout ? take((size_t)w * w) : 0;
   const size_t o_w0n = take((size_t)w * (din > 1 ? din - 1 : 1));
-  const bool tc_layout = (w % 128 == 0) && w >= 256 && w <= 2048 && din == 3 && dout == 2;
+  const bool wide_layout = (w % 128 == 0) && w >= 256 && w <= 2048 && din == 3 && dout == 2;   // layered fp16 engine
+  const bool tc_layout = wide_layout && w == 256;                                               // k_tc (3xTF32)
   const int tc_mt = w / 128, tc_kb = w / 32;
   const size_t tc_floats = (size_t)4 * tc_mt * tc_kb * 2 * 128 * 32;
   off = (off + 255) & ~size_t(255);   // 1 KB alignment of the tile images
   const size_t o_tc = tc_layout ? take(tc_floats) : 0;
+  const int tw_mt = w / 128, tw_kb = w / 64;
+  const size_t tw_floats = (size_t)4 * tw_mt * tw_kb * 2 * 4096;   // 16 KB (4096 floats) per hi / lo' image
+  off = (off + 255) & ~size_t(255);
+  const size_t o_tw = wide_layout ? take(tw_floats) : 0;
   const bool tc16_layout = tc_layout && w == 256;
   const size_t tc16_floats = (size_t)4 * 2 * 4 * 2 * 128 * 32;   // 4 gemms x 2 m-tiles x 4 k-blocks x (hi, lo') x 16 KB
   off = (off + 255) & ~size_t(255);
@@ -191,6 +196,25 @@ extern "C" int idff_weights_create(const float* const* h_W, const float* const* 
             }
         }
   }
+  if (wide_layout) {
+    for (int g = 0; g < 4; ++g)
+      for (int mt = 0; mt < tw_mt; ++mt)
+        for (int kb = 0; kb < tw_kb; ++kb) {
+          uint16_t* hi = reinterpret_cast<uint16_t*>(&blob[o_tw + ((((size_t)g * tw_mt + mt) * tw_kb + kb) * 2 + 0) * 4096]);
+          uint16_t* lo = hi + 8192;
+          for (int r = 0; r < 128; ++r)
+            for (int kk = 0; kk < 64; ++kk) {
+              const int row = mt * 128 + r, col = kb * 64 + kk;   // D[row][.] = sum_col A[row][col] * act[.][col]
+              const float v = g == 0 ? W1[(size_t)row * w + col] : g == 1 ? W2[(size_t)row * w + col]
+                            : g == 2 ? W2[(size_t)col * w + row] : W1[(size_t)col * w + row];
+              const __half h = __float2half_rn(v);
+              const __half l = __float2half_rn((v - __half2float(h)) * 2048.0f);
+              const size_t o = (size_t)r * 64 + ((((kk >> 3) ^ (r & 7)) << 3) | (kk & 7));
+              memcpy(&hi[o], &h, 2);
+              memcpy(&lo[o], &l, 2);
+            }
+        }
+  }
   if (tc16_layout) {
     for (int g = 0; g < 4; ++g)
       for (int mt = 0; mt < 2; ++mt)
@@ -253,6 +277,7 @@ extern "C" int idff_weights_create(const float* const* h_W, const float* const* 
   v.w0n = d_blob + o_w0n;
   v.tc_tiles = tc_layout ? d_blob + o_tc : nullptr;
   v.tc16_tiles = tc16_layout ? d_blob + o_tc16 : nullptr;
+  v.tcw16_tiles = wide_layout ? d_blob + o_tw : nullptr;
   h->d_stash = nullptr; h->stash_bytes = 0; h->tc_verified = 0;
   h->d_sweep = nullptr; h->sweep_bytes = 0;
   *out = h;

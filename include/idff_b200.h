@@ -40,8 +40,8 @@ extern "C" {
 #define IDFF_IMPL_AUTO 0
 #define IDFF_IMPL_GENERIC 1 /* any width / dimension: one thread per hidden unit, weights from L2 */
 #define IDFF_IMPL_FUSED 2   /* persistent warp-tiled kernel, weights streamed by TMA bulk copies */
-#define IDFF_IMPL_TENSOR 3  /* tcgen05 3xTF32: fused kernel (width 256, dim 2, order <= 2) or the layered engine (width >= 512) */
-#define IDFF_IMPL_LAYERED 4 /* force the layer-by-layer tcgen05 engine (width >= 256, dim 2, orders 1..3) */
+#define IDFF_IMPL_TENSOR 3  /* tcgen05: fused 3xTF32 kernel (width 256, dim 2, order <= 2) or the layered 3xFP16 engine (width >= 512) */
+#define IDFF_IMPL_LAYERED 4 /* force the layer-by-layer tcgen05 3xFP16 engine (width >= 256, dim 2, orders 1..3) */
 #define IDFF_IMPL_TENSOR16 5 /* tcgen05 3xFP16 fused kernel (width 256, dim 2, order <= 2): the default for that shape.
                                 Values beyond the fp16 range (|activation|, |jet|, |adjoint| > 65504) make that particle's
                                 output NaN and are counted by idff_tensor16_nonfinite(); use TENSOR or FUSED for such nets */
