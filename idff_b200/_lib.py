@@ -9,7 +9,7 @@ import subprocess
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libidff_b200.so")
+LIB_PATH = os.environ.get("IDFF_B200_LIB") or os.path.join(_HERE, "lib", "libidff_b200.so")   # override: A/B experiments
 CSRC = os.path.join(_HERE, "csrc")
 
 IDFF_FIELD_MOMENTUM, IDFF_FIELD_SCOREHEAD, IDFF_FIELD_CFM, IDFF_FIELD_MD = 0, 1, 2, 3

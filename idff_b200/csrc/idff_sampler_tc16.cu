@@ -22,7 +22,9 @@
 //         [main | corr] += W_hi * [X_hi ; X_lo']      N = 256
 //                corr   += W_lo' * X_hi               N = 128
 //   * TMEM (512 columns): accumulators [main 128 | corr 128] shared by the two m-tiles, which run back to back, and
-//     the layer-2 derivative stash of the reverse sweep (2 x 128 columns).
+//     the layer-2 derivative stash of the reverse sweep (2 x 128 columns).  Boundary evaluations (t = 0, t = 1: one jet,
+//     no reverse sweep) keep [X_hi ; X_lo'] in operand rows 0..127, run N = 128 / N = 64 MMAs and split the K sum over
+//     two accumulator sets by k-block parity: half as many truncating accumulation steps where t = 1 amplifies x100.
 // A TMEM lane is one hidden unit.  The epilogue reads the accumulators with tcgen05.ld.16x128b: thread T of a warp gets
 // lanes {g, g+8, g+16, g+24} (g = T/4) of its lane quarter and columns {T%4 + 4r}; the weight-tile rows are permuted at
 // handle creation so that these four lanes are four CONSECUTIVE units 4s..4s+3 (s = slot(g), a fixed permutation of
@@ -99,6 +101,12 @@ __device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
 }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -245,15 +253,17 @@ __device__ __forceinline__ void pack_jet(const float (&v)[HP], uint32_t (&hw)[8]
 }
 // 8-byte stores of one jet (JET) into the thread's four particle rows: hi rows at +0, lo' rows 128 rows further.
 // sa[0] / sa[1] = swizzled address of the thread's 8-byte group for even / odd r, first particle, jet 0, hi.
-template <int JET>
+// LO = byte offset of the lo' rows: 128 rows (8192 B) in interior evaluations; 64 rows in boundary evaluations, which
+// carry one jet and keep [X_hi ; X_lo'] in rows 0..127 so that their MMAs are N = 128 / N = 64.
+template <int JET, int LO = 8192>
 __device__ __forceinline__ void store_jet(const uint32_t (&sa)[2], const uint32_t (&hw)[8], const uint32_t (&lw)[8]) {
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     // (r & 1) is a compile-time constant after unrolling
-    if (r == 0) { st64<JET * 4096 + 0 * 256>(sa[0], hw[0], hw[1]); st64<8192 + JET * 4096 + 0 * 256>(sa[0], lw[0], lw[1]); }
-    if (r == 1) { st64<JET * 4096 + 1 * 256>(sa[1], hw[2], hw[3]); st64<8192 + JET * 4096 + 1 * 256>(sa[1], lw[2], lw[3]); }
-    if (r == 2) { st64<JET * 4096 + 2 * 256>(sa[0], hw[4], hw[5]); st64<8192 + JET * 4096 + 2 * 256>(sa[0], lw[4], lw[5]); }
-    if (r == 3) { st64<JET * 4096 + 3 * 256>(sa[1], hw[6], hw[7]); st64<8192 + JET * 4096 + 3 * 256>(sa[1], lw[6], lw[7]); }
+    if (r == 0) { st64<JET * 4096 + 0 * 256>(sa[0], hw[0], hw[1]); st64<LO + JET * 4096 + 0 * 256>(sa[0], lw[0], lw[1]); }
+    if (r == 1) { st64<JET * 4096 + 1 * 256>(sa[1], hw[2], hw[3]); st64<LO + JET * 4096 + 1 * 256>(sa[1], lw[2], lw[3]); }
+    if (r == 2) { st64<JET * 4096 + 2 * 256>(sa[0], hw[4], hw[5]); st64<LO + JET * 4096 + 2 * 256>(sa[0], lw[4], lw[5]); }
+    if (r == 3) { st64<JET * 4096 + 3 * 256>(sa[1], hw[6], hw[7]); st64<LO + JET * 4096 + 3 * 256>(sa[1], lw[6], lw[7]); }
   }
 }
 // per-unit constant c[0..3] of the thread's four units for element e
@@ -318,33 +328,45 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
   auto heavy_of = [&](const Stage& st, int g) { return st.kind == 2 && (P.mode == 2 ? P.tabs[g].reverse : P.reverse) != 0; };
 
   if (warp == NEW) {
-    // ===== TMA producer: weight tile images of every layer pass, in consumption order
-    if (lane == 0) {
+    // ===== TMA producer: weight tile images of every layer pass, in consumption order.  Whole warp in uniform control
+    // flow (addresses in uniform registers), one elected lane issues; no back-off on the slot wait: the ring is only
+    // three stages deep and a late refill stalls the tensor pipe
+    {
+      const bool leader = elect_one();
       int stage = 0;
       uint32_t phase = 0;
-      const unsigned char* tiles = reinterpret_cast<const unsigned char*>(P.net.tc16_tiles);
+      const unsigned char* tiles = reinterpret_cast<const unsigned char*>(P.net.tc16_tiles) + crank * (TILE_BYTES / 2);
+      unsigned char* const ring = smem + Smem::ring + crank * (TILE_BYTES / 2);
       for (long it = 0; it < n_iter; ++it)
         for (int e = 0; e < n_eval; ++e) {
           const int gs = set_of(it);
           const int ng = heavy_of(stage_of(e, gs), gs) ? 4 : 2;
           for (int g = 0; g < ng; ++g)
             for (int t = 0; t < 2 * NKB; ++t) {   // (m-tile, k-block) tiles of gemm g are contiguous
-              mbar_wait_sleep(&empty[stage], phase ^ 1u);
-              mbar_arrive_expect_tx(&full[stage], TILE_BYTES);
-              tma_load_1d_mc(smem + Smem::ring + stage * TILE_BYTES + crank * (TILE_BYTES / 2),
-                             tiles + ((size_t)g * 2 * NKB + t) * TILE_BYTES + crank * (TILE_BYTES / 2), TILE_BYTES / 2,
-                             &full[stage], (uint16_t)3);
+              mbar_wait(&empty[stage], phase ^ 1u);
+              if (leader) {
+                mbar_arrive_expect_tx(&full[stage], TILE_BYTES);
+                tma_load_1d_mc(ring + stage * TILE_BYTES, tiles + ((size_t)g * 2 * NKB + t) * TILE_BYTES, TILE_BYTES / 2,
+                               &full[stage], (uint16_t)3);
+              }
+              __syncwarp();
               if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
             }
         }
     }
   } else if (warp == NEW + 1) {
-    // ===== MMA issuer (one thread)
-    if (lane == 0) {
+    // ===== MMA issuer.  The whole warp walks the schedule in uniform control flow, so descriptors, TMEM addresses and
+    // barrier phases live in uniform registers and each tcgen05.mma costs a handful of instructions; one elected lane
+    // issues.  (Issued from an `if (lane == 0)` region every UTCHMMA was preceded by an ELECT / 7 x R2UR.BROADCAST /
+    // BRA.U.ANY loop and the issuing thread, not the tensor pipe, set the pace of a layer pass.)
+    {
       // kind::f16: D fp32 (bit 4), A = B = fp16 (format 0), K-major, N >> 3 at bit 17, M >> 4 at bit 24
       const uint32_t idesc_256 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t idesc_128 = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc_64 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t bop = s32(smem + Smem::act);
+      const uint32_t ring0 = s32(smem + Smem::ring);
+      const bool leader = elect_one();
       int stage = 0;
       uint32_t phase = 0, fphase = 0, bphase0 = 0, bphase1 = 0;
       for (long it = 0; it < n_iter; ++it)
@@ -352,10 +374,10 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
           const int gs = set_of(it);
           const bool heavy = heavy_of(stage_of(e, gs), gs);
           const int ng = heavy ? 4 : 2;
-          if (blockIdx.x == 0 && it == 0 && e == 1)
+          const bool mstamp = blockIdx.x == 0 && it == 0 && e == 1 && lane == 0;
+          if (mstamp)
             for (int i = 24; i < 29; ++i) g_tc16_stamps[i] = 0;
           for (int g = 0; g < ng; ++g) {
-            const bool mstamp = blockIdx.x == 0 && it == 0 && e == 1;
             for (int mt = 0; mt < 2; ++mt) {
               long long c0 = mstamp ? clock64() : 0;
               mbar_wait(acc_free, fphase);   // the previous m-tile's accumulators have been read out
@@ -382,24 +404,32 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 if (mstamp) g_tc16_stamps[28] += clock64() - c0;
-                const uint32_t whi = s32(smem + Smem::ring + stage * TILE_BYTES), wlo = whi + TILE_BYTES / 2;
+                // interior evaluation: [main | corr] += W_hi * [X_hi ; X_lo'] (N = 256), corr += W_lo' * X_hi (N = 128).
+                // boundary evaluation (one jet): rows 0..63 hold X_hi, rows 64..127 X_lo' (the jet-1 hi slot is free), so the
+                // two MMAs are N = 128 and N = 64; accumulator set (kb & 1): [main 64 | corr 64] at columns 128 * (kb & 1)
+                const uint32_t d1 = tmem + (heavy ? 0u : (uint32_t)((kb & 1) * 128)), d2 = d1 + (heavy ? 128u : 64u);
+                const uint32_t i1 = heavy ? idesc_256 : idesc_128, i2 = heavy ? idesc_128 : idesc_64;
+                const uint32_t first = (uint32_t)(heavy ? kb : (kb >> 1));
+                // descriptors advance by 32 bytes (2 address units) per 16-wide k-step; the operand k-block (32 wide) is
+                // 2*kb + ks/2, its 32-byte half ks%2
+                const uint64_t a_hi0 = make_desc(ring0 + (uint32_t)(stage * TILE_BYTES));
+                const uint64_t a_lo0 = make_desc(ring0 + (uint32_t)(stage * TILE_BYTES + TILE_BYTES / 2));
+                const uint64_t b_0 = make_desc64(bop + (uint32_t)(2 * kb * KB_BYTES));
+                if (leader) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  const uint64_t a_hi = make_desc(whi + ks * 32), a_lo = make_desc(wlo + ks * 32);
-                  // operand k-block (32 wide) 2*kb + ks/2, 32-byte half ks%2 of its 64-byte rows; 256 rows: hi then lo'
-                  const uint64_t b_w = make_desc64(bop + (2 * kb + (ks >> 1)) * KB_BYTES + (ks & 1) * 32);
-                  // boundary evaluations (no stash in use) split the K sum over two accumulator sets by k-block parity:
-                  // half as many truncating accumulation steps where the t == 1 branch amplifies the error x100
-                  const uint32_t dset = tmem + (heavy ? 0u : (uint32_t)((kb & 1) * COL_STASH));
-                  const uint32_t acc = heavy ? (uint32_t)((kb | ks) != 0) : (uint32_t)(((kb >> 1) | ks) != 0);
-                  mma_f16(dset, a_hi, b_w, idesc_256, acc);                // [main | corr] += W_hi * [X_hi ; X_lo']
-                  mma_f16(dset + COL_CORR, a_lo, b_w, idesc_128, 1u);      // corr += W_lo' * X_hi
+                  for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t boff = (uint64_t)(((ks >> 1) * KB_BYTES + (ks & 1) * 32) >> 4);
+                    mma_f16(d1, a_hi0 + (uint64_t)(2 * ks), b_0 + boff, i1, (first | (uint32_t)ks) != 0u);
+                    mma_f16(d2, a_lo0 + (uint64_t)(2 * ks), b_0 + boff, i2, 1u);
+                  }
+                  mma_commit_mc(&empty[stage], (uint16_t)3);   // frees the slot in both CTAs once these MMAs have read it
+                  if (mt == 1 && kb == 1) mma_commit(kfree);   // the m-tile-0 epilogue may overwrite k-blocks 0-1
                 }
-                mma_commit_mc(&empty[stage], (uint16_t)3);   // frees the slot in both CTAs once these MMAs have read it
+                __syncwarp();
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
-                if (mt == 1 && kb == 1) mma_commit(kfree);   // the m-tile-0 epilogue may overwrite k-blocks 0-1
               }
-              mma_commit(acc_full);
+              if (leader) mma_commit(acc_full);
+              __syncwarp();
             }
             if (mstamp) g_tc16_stamps[17 + 2 * g] = clock64();
           }
@@ -454,17 +484,17 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
 #pragma unroll
       for (int i = 0; i < HP; ++i) z[i] = fmaf(__uint_as_float(c[i]), LO_INV, __uint_as_float(m[i]));
     };
-    // boundary evaluations: jet 0 summed over the two accumulator sets
+    // boundary evaluations: jet 0 summed over the two accumulator sets [main 64 | corr 64] at columns 0 and 128
     auto load_acc2 = [&](float (&z)[HP]) {
       uint32_t m0[HP], c0[HP], m1[HP], c1[HP];
       tmem_ld8(lane_base, m0);
       tmem_ld8(lane_base + (16u << 16), m0 + 8);
-      tmem_ld8(lane_base + COL_CORR, c0);
-      tmem_ld8(lane_base + (16u << 16) + COL_CORR, c0 + 8);
-      tmem_ld8(lane_base + COL_STASH, m1);
-      tmem_ld8(lane_base + (16u << 16) + COL_STASH, m1 + 8);
-      tmem_ld8(lane_base + COL_STASH + COL_CORR, c1);
-      tmem_ld8(lane_base + (16u << 16) + COL_STASH + COL_CORR, c1 + 8);
+      tmem_ld8(lane_base + 64, c0);
+      tmem_ld8(lane_base + (16u << 16) + 64, c0 + 8);
+      tmem_ld8(lane_base + 128, m1);
+      tmem_ld8(lane_base + (16u << 16) + 128, m1 + 8);
+      tmem_ld8(lane_base + 192, c1);
+      tmem_ld8(lane_base + (16u << 16) + 192, c1 + 8);
       tmem_wait_ld();
 #pragma unroll
       for (int i = 0; i < HP; ++i)
@@ -547,10 +577,12 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
           uint32_t sa[2], hw[8], lw[8];
           make_sa(mt, sa);
           pack_jet(v0, hw, lw);
-          store_jet<0>(sa, hw, lw);
           if (heavy) {
+            store_jet<0>(sa, hw, lw);
             pack_jet(v1, hw, lw);
             store_jet<1>(sa, hw, lw);
+          } else {
+            store_jet<0, 4096>(sa, hw, lw);
           }
           publish(mt);
         }
@@ -601,8 +633,12 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
           if (mt == 0) wait_kfree();   // k-blocks 0-1 have been read by every MMA of this pass
           uint32_t sa[2];
           make_sa(mt, sa);
-          store_jet<0>(sa, h0, l0);
-          if (heavy) store_jet<1>(sa, h1, l1);
+          if (heavy) {
+            store_jet<0>(sa, h0, l0);
+            store_jet<1>(sa, h1, l1);
+          } else {
+            store_jet<0, 4096>(sa, h0, l0);
+          }
           publish(mt);
         }
         if (stamp) g_tc16_stamps[3] = clock64();
