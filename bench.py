@@ -249,12 +249,19 @@ def run_ours(args):
         bf16 = peaks.get("bf16_tflops", 1590.0)
         if args.kernel in ("auto", "tensor16"):
             # tcgen05 kind::f16, three MMA products per algorithmic product (3xFP16 split): peak = fp16 dense / 3
-            tpeak = bf16 / 3.0
+            # a launch of >= 100 ms repeated back to back runs under the 1000 W power cap like the driver's sustained GEMM
+            # loop: that figure is the denominator then (B200_PROFILING.md), the burst one for short launches
+            sustained = peaks.get("bf16_tflops_sustained")
+            long_step = k_ms >= 100.0 and sustained is not None
+            dense = sustained if long_step else bf16
+            tpeak = dense / 3.0
             roofline = {"bound": "tensor", "kernel": "k_tc16: tcgen05 3xFP16 sampler (whole rk4 solve, one launch)",
                         "achieved": achieved, "peak": tpeak, "unit": "TFLOP/s", "frac": achieved / tpeak, "traffic": None,
-                        "peak_source": f"{peak_src} bf16/fp16 dense {bf16:.0f} TFLOP/s (MEASURED_PEAKS.json, burst) / 3 "
-                                       "(hi*hi + hi*lo + lo*hi products); algorithmic FLOPs = 2F per MLP pass, 2n passes per "
-                                       "interior order-n evaluation (SURVEY.md section 8d)",
+                        "frac_of_burst_peak": achieved / (bf16 / 3.0),
+                        "peak_source": f"{peak_src} bf16/fp16 dense {dense:.0f} TFLOP/s (MEASURED_PEAKS.json, "
+                                       f"{'sustained: ' + format(k_ms, '.0f') + ' ms launches back to back under the power cap' if long_step else 'burst'}"
+                                       f"; burst {bf16:.0f}) / 3 (hi*hi + hi*lo + lo*hi products); algorithmic FLOPs = 2F per "
+                                       "MLP pass, 2n passes per interior order-n evaluation (SURVEY.md section 8d)",
                         "algorithmic_flops_per_launch": flops, "kernel_ms": k_ms,
                         "kernel_share_of_step": k_ms * args.steps / total_ms,
                         "executed_tensor_tflops": 3.0 * achieved, "frac_of_bf16_tensor_peak": 3.0 * achieved / bf16,

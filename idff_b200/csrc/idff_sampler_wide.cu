@@ -89,6 +89,12 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(s32(bar))
                : "memory");
 }
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -251,49 +257,61 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_wide_layer(const __grid_constan
   const unsigned char* wt = reinterpret_cast<const unsigned char*>(P.net.tcw16_tiles) + (size_t)P.gemm * MT * KB * WT_BYTES;
 
   if (warp == NEW) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int ct = (int)(item / MT), mt = (int)(item - (long)ct * MT);
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait_sleep(&empty[stage], phase ^ 1u);
+    // TMA producer: whole warp in uniform control flow, one elected lane issues (operands in uniform registers)
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int ct = (int)(item / MT), mt = (int)(item - (long)ct * MT);
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1u);
+        if (leader) {
           mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
           unsigned char* dst = smem + stage * STAGE_BYTES;
           tma_load_1d(dst, wt + ((size_t)mt * KB + kb) * WT_BYTES, WT_BYTES, &full[stage]);
           tma_load_1d(dst + WT_BYTES, P.xin + ((size_t)ct * KB + kb) * XT_BYTES, XT_BYTES, &full[stage]);
-          if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == NEW + 1) {
-    if (lane == 0) {
-      // kind::f16: D fp32 (bit 4), A = B = fp16 (format 0), K-major, N >> 3 at bit 17, M >> 4 at bit 24
-      const uint32_t idesc_w = (1u << 4) | ((uint32_t)(2 * NCOL >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t idesc_n = (1u << 4) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      int stage = 0, q = 0;
-      uint32_t phase = 0, ephase[2] = {0, 0};
-      for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
-        mbar_wait(&acc_empty[q], ephase[q] ^ 1u);   // the epilogue has read this accumulator buffer out
-        ephase[q] ^= 1u;
+    // MMA issuer: whole warp in uniform control flow, one elected lane issues -- descriptors and TMEM addresses stay in
+    // uniform registers, a tcgen05.mma costs a few instructions (from an `if (lane == 0)` region each one is preceded by
+    // an ELECT / R2UR.BROADCAST loop and the issuing thread, not the tensor pipe, sets the pace)
+    // kind::f16: D fp32 (bit 4), A = B = fp16 (format 0), K-major, N >> 3 at bit 17, M >> 4 at bit 24
+    const uint32_t idesc_w = (1u << 4) | ((uint32_t)(2 * NCOL >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc_n = (1u << 4) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const bool leader = elect_one();
+    const uint32_t ring0 = s32(smem);
+    int stage = 0, q = 0;
+    uint32_t phase = 0, ephase0 = 0, ephase1 = 0;
+    for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
+      // the epilogue has read this accumulator buffer out
+      if (q == 0) { mbar_wait(&acc_empty[0], ephase0 ^ 1u); ephase0 ^= 1u; }
+      else { mbar_wait(&acc_empty[1], ephase1 ^ 1u); ephase1 ^= 1u; }
+      tc_fence_after();
+      const uint32_t dset = tmem + q * COL_BUF;
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t whi = s32(smem + stage * STAGE_BYTES), wlo = whi + 16384, xop = whi + WT_BYTES;
-          const uint32_t dset = tmem + q * COL_BUF;
+        const uint64_t a_hi0 = make_desc(ring0 + (uint32_t)(stage * STAGE_BYTES));
+        const uint64_t a_lo0 = make_desc(ring0 + (uint32_t)(stage * STAGE_BYTES + 16384));
+        const uint64_t b_0 = make_desc(ring0 + (uint32_t)(stage * STAGE_BYTES + WT_BYTES));
+        if (leader) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t a_hi = make_desc(whi + ks * 32), a_lo = make_desc(wlo + ks * 32), b_w = make_desc(xop + ks * 32);
-            mma_f16(dset, a_hi, b_w, idesc_w, (kb | ks) != 0);   // [main | corr] += W_hi * [X_hi ; X_lo']
-            mma_f16(dset + COL_CORR, a_lo, b_w, idesc_n, 1u);    // corr += W_lo' * X_hi
+          for (int ks = 0; ks < 4; ++ks) {   // descriptors advance by 32 bytes (2 address units) per 16-wide k-step
+            mma_f16(dset, a_hi0 + (uint64_t)(2 * ks), b_0 + (uint64_t)(2 * ks), idesc_w, (uint32_t)((kb | ks) != 0));   // [main | corr] += W_hi * [X_hi ; X_lo']
+            mma_f16(dset + COL_CORR, a_lo0 + (uint64_t)(2 * ks), b_0 + (uint64_t)(2 * ks), idesc_n, 1u);                // corr += W_lo' * X_hi
           }
           mma_commit(&empty[stage]);
-          if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
         }
-        mma_commit(&acc_full[q]);
-        q ^= 1;
+        __syncwarp();
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
       }
+      if (leader) mma_commit(&acc_full[q]);
+      __syncwarp();
+      q ^= 1;
     }
   } else {
     // ===== epilogue warps
