@@ -294,11 +294,15 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
         }
     }
   } else if (warp == NEW + 1) {
-    // ===== MMA issuer (one thread)
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp walks the schedule in uniform control flow (descriptors and TMEM addresses in
+    // uniform registers), one elected lane issues -- see idff_sampler_tc16.cu
+    {
       const uint32_t idesc_w = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * NCOL >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t idesc_n = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t bop = s32(smem + Smem::act);
+      const uint32_t bop = s32(smem + Smem::act), ring0 = s32(smem + Smem::ring);
+      uint32_t el;
+      asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(el));
+      const bool leader = el != 0;
       int stage = 0;
       uint32_t phase = 0, bphase = 0, hphase = 0, fphase = 0;
       for (long it = 0; it < n_iter; ++it)
@@ -308,7 +312,7 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
             mbar_wait(b_ready_lo, bphase);
             bphase ^= 1u;
             tc_fence_after();
-            const bool mstamp = blockIdx.x == 0 && it == 0 && e == 1;
+            const bool mstamp = blockIdx.x == 0 && it == 0 && e == 1 && lane == 0;
             if (mstamp) g_tc_stamps[16 + 2 * g] = clock64();
             for (int mt = 0; mt < 2; ++mt) {
               if (mt == 1) {   // the accumulator sets are reused: m-tile 0 must have been read out
@@ -324,20 +328,24 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
                 }
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
-                const uint32_t whi = s32(smem + Smem::ring + stage * TILE_BYTES), wlo = whi + 16384;
+                const uint64_t a_hi0 = make_desc(ring0 + (uint32_t)(stage * TILE_BYTES));
+                const uint64_t a_lo0 = make_desc(ring0 + (uint32_t)(stage * TILE_BYTES + 16384));
+                const uint64_t b_0 = make_desc(bop + (uint32_t)(kb * KB_BYTES));   // 128 rows: hi copy then lo copy
                 const uint32_t dset = tmem + (kb & 1) * COL_SET;
+                if (leader) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  const uint64_t a_hi = make_desc(whi + ks * 32), a_lo = make_desc(wlo + ks * 32);
-                  const uint64_t b_w = make_desc(bop + kb * KB_BYTES + ks * 32);   // 128 rows: hi copy then lo copy
-                  // [main | corr] += W_hi * [X_hi ; X_lo]   (one N = 128 MMA reads W_hi once), then corr += W_lo * X_hi
-                  mma_tf32(dset, a_hi, b_w, idesc_w, ((kb >> 1) | ks) != 0);
-                  mma_tf32(dset + COL_CORR, a_lo, b_w, idesc_n, 1u);
+                  for (int ks = 0; ks < 4; ++ks) {
+                    // [main | corr] += W_hi * [X_hi ; X_lo]   (one N = 128 MMA reads W_hi once), then corr += W_lo * X_hi
+                    mma_tf32(dset, a_hi0 + (uint64_t)(2 * ks), b_0 + (uint64_t)(2 * ks), idesc_w, ((kb >> 1) | ks) != 0);
+                    mma_tf32(dset + COL_CORR, a_lo0 + (uint64_t)(2 * ks), b_0 + (uint64_t)(2 * ks), idesc_n, 1u);
+                  }
+                  mma_commit_mc(&empty[stage], (uint16_t)3);   // frees the slot in both CTAs once these MMAs have read it
                 }
-                mma_commit_mc(&empty[stage], (uint16_t)3);   // frees the slot in both CTAs once these MMAs have read it
+                __syncwarp();
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
               }
-              mma_commit(&acc_full[mt]);
+              if (leader) mma_commit(&acc_full[mt]);
+              __syncwarp();
             }
             if (mstamp) g_tc_stamps[17 + 2 * g] = clock64();
           }
