@@ -407,6 +407,28 @@ def aux_measurements(dev, pw, model, peaks):
         aux["reference_cpu_secondary"] = cpu
     except Exception as exc:
         aux["reference_cpu_secondary_error"] = repr(exc)
+    # ---- the caller of the sampler: find_best_gammas_mmd, 8 x 8 tuples, 2048 particles, nfe = 2
+    try:
+        from idff_b200 import sweep as sweep_mod
+        import idff_oracle as O3
+        grid8 = [0.0, 0.1, 0.2, 0.3, 0.5, 0.7, 1.0, 2.0]
+        xs2k = torch.randn(2048, 2, device=dev, generator=g) / 1.5
+        np.random.seed(1)
+        from idff_b200.torchcfm.utils import sample_checkerboard as host_cb
+        true2k = host_cb(2048).to(dev)
+        s_sw = timeit(lambda: sweep_mod.find_best_gammas_mmd(pw, xs2k, true2k, gamma_range=grid8, nfe=2, sigma=0.2,
+                                                             sigma_kernel=1.0, order=2), reps=5, warm=2)
+        lay = load_layers()
+        xc, tc_ = xs2k.cpu(), true2k.cpu()
+        t0 = time.perf_counter()
+        for gam in ((0.0, 0.0), (0.2, 0.2), (1.0, 2.0), (0.5, 0.0)):
+            fin = O3.odeint_rk4(O3.Field2D(lay, 0.2, gam, 2), xc, torch.linspace(0, 1, 3))[-1]
+            O3.mmd_rbf(tc_, fin)
+        s_cpu = (time.perf_counter() - t0) / 4 * 64
+        aux["gamma_sweep_8x8_N2048_nfe2"] = {"ms": s_sw * 1e3, "launches": 2, "reference_cpu_ms": s_cpu * 1e3,
+                                             "reference_cpu_note": "4 of the 64 tuples timed on the host cores, x16"}
+    except Exception as exc:
+        aux["gamma_sweep_error"] = repr(exc)
     # ---- training side (BASELINE metric: "train samples/s"): the reference's 2-D training step at its batch size (256,
     # launch-bound) and at 2^16, eager vs one CUDA-graph replay per step; the reference's step on the host cores beside it
     try:

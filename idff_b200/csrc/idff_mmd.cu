@@ -46,8 +46,7 @@ __device__ __forceinline__ void block_accumulate(double v, double* dst) {
 constexpr int kSmallRA = 2;        // A rows per thread
 constexpr int kSmallBC = 256 * kSmallRA;   // B rows per CTA (= A rows per CTA: square blocks, so symmetry is per block)
 template <int D>
-__global__ void __launch_bounds__(256) k_mmd_small(const __grid_constant__ MmdJobs jobs, double* __restrict__ sums) {
-  const MmdJob& jb = jobs.job[blockIdx.z];
+__device__ __forceinline__ void mmd_small_body(const MmdJob& jb, const float scale, double* __restrict__ dst) {
   const long a0 = jb.a_begin + (long)blockIdx.x * (256 * kSmallRA);
   const long b0 = (long)blockIdx.y * kSmallBC;
   if (a0 >= jb.a_end || b0 >= jb.nb) return;
@@ -56,7 +55,7 @@ __global__ void __launch_bounds__(256) k_mmd_small(const __grid_constant__ MmdJo
   const double weight = (jb.symmetric && blockIdx.y > blockIdx.x) ? 2.0 : 1.0;
   __shared__ __align__(16) float bs[kSmallBC * D];
   const long bcnt = jb.nb - b0 < kSmallBC ? jb.nb - b0 : kSmallBC;
-  for (long i = threadIdx.x; i < bcnt * D; i += 256) bs[i] = jb.b[b0 * D + i] * jobs.scale;
+  for (long i = threadIdx.x; i < bcnt * D; i += 256) bs[i] = jb.b[b0 * D + i] * scale;
   float av[kSmallRA][D];
   bool valid[kSmallRA];
 #pragma unroll
@@ -64,7 +63,7 @@ __global__ void __launch_bounds__(256) k_mmd_small(const __grid_constant__ MmdJo
     const long row = a0 + threadIdx.x + (long)r * 256;
     valid[r] = row < jb.a_end;
 #pragma unroll
-    for (int d = 0; d < D; ++d) av[r][d] = valid[r] ? jb.a[row * D + d] * jobs.scale : 0.0f;
+    for (int d = 0; d < D; ++d) av[r][d] = valid[r] ? jb.a[row * D + d] * scale : 0.0f;
   }
   __syncthreads();
   double tot = 0.0;
@@ -93,7 +92,27 @@ __global__ void __launch_bounds__(256) k_mmd_small(const __grid_constant__ MmdJo
     for (int r = 0; r < kSmallRA; ++r)
       if (valid[r]) tot += (double)acc[r];
   }
-  block_accumulate(tot * weight, sums + blockIdx.z);
+  block_accumulate(tot * weight, dst);
+}
+template <int D>
+__global__ void __launch_bounds__(256) k_mmd_small(const __grid_constant__ MmdJobs jobs, double* __restrict__ sums) {
+  mmd_small_body<D>(jobs.job[blockIdx.z], jobs.scale, sums + blockIdx.z);
+}
+// gamma sweeps: one fixed set x [N][D] against G generated sets y_g [M][D] (contiguous).  blockIdx.z = 0: (x, x);
+// 1 + 2g: (y_g, y_g); 2 + 2g: (x, y_g).  sums[blockIdx.z] receives the pair sum.
+template <int D>
+__global__ void __launch_bounds__(256) k_mmd_small_sweep(const float* __restrict__ x, long N, const float* __restrict__ y, long M,
+                                                         float scale, double* __restrict__ sums) {
+  const int z = blockIdx.z;
+  MmdJob jb;
+  if (z == 0) {
+    jb = {x, x, 0, N, N, 1};
+  } else {
+    const float* yg = y + (size_t)((z - 1) >> 1) * (size_t)M * D;
+    if ((z - 1) & 1) jb = {x, yg, 0, N, M, 0};
+    else jb = {yg, yg, 0, M, M, 1};
+  }
+  mmd_small_body<D>(jb, scale, sums + z);
 }
 
 // ---- any D: 64 x 64 pair tile per iteration, 4 x 4 pairs per thread, coordinates staged in chunks of 16 ---------
@@ -185,6 +204,33 @@ extern "C" int idff_mmd_rbf(const float* d_x, int64_t N, const float* d_y, int64
     dim3 grid((unsigned)((amax + 63) / 64), (unsigned)((bmax + kBigBC - 1) / kBigBC), 3);
     IDFF_CHECK_ARG(grid.y <= 65535, "idff_mmd_rbf: set too large (%ld rows)", bmax);
     k_mmd_big<<<grid, 256, 0, s>>>(jobs, d_sums);
+  }
+  IDFF_CUDA(cudaGetLastError());
+  count_launch();
+  return IDFF_OK;
+}
+
+extern "C" int idff_mmd_rbf_sweep(const float* d_x, int64_t N, const float* d_y, int64_t M, int32_t n_sets, int32_t D,
+                                  float sigma_k, double* d_sums, void* stream) {
+  IDFF_CHECK_ARG(d_x && d_y && d_sums, "idff_mmd_rbf_sweep: null pointer");
+  IDFF_CHECK_ARG(N >= 1 && M >= 1 && n_sets >= 1 && n_sets <= 32767, "idff_mmd_rbf_sweep: bad sizes (N=%lld M=%lld sets=%d)",
+                 (long long)N, (long long)M, n_sets);
+  IDFF_CHECK_ARG(sigma_k > 0.0f, "idff_mmd_rbf_sweep: sigma_k must be positive");
+  if (D < 1 || D > 4) {
+    set_error("idff_mmd_rbf_sweep: D = %d (the batched kernel serves D <= 4; call idff_mmd_rbf per set)", D);
+    return IDFF_EUNSUPPORTED;
+  }
+  const float scale = (float)sqrt(1.4426950408889634 / (2.0 * (double)sigma_k * (double)sigma_k));
+  const long amax = N > M ? N : M;
+  dim3 grid((unsigned)((amax + 256 * kSmallRA - 1) / (256 * kSmallRA)), (unsigned)((amax + kSmallBC - 1) / kSmallBC),
+            (unsigned)(1 + 2 * n_sets));
+  IDFF_CHECK_ARG(grid.y <= 65535, "idff_mmd_rbf_sweep: set too large (%ld rows)", amax);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (D) {
+    case 1: k_mmd_small_sweep<1><<<grid, 256, 0, s>>>(d_x, (long)N, d_y, (long)M, scale, d_sums); break;
+    case 2: k_mmd_small_sweep<2><<<grid, 256, 0, s>>>(d_x, (long)N, d_y, (long)M, scale, d_sums); break;
+    case 3: k_mmd_small_sweep<3><<<grid, 256, 0, s>>>(d_x, (long)N, d_y, (long)M, scale, d_sums); break;
+    default: k_mmd_small_sweep<4><<<grid, 256, 0, s>>>(d_x, (long)N, d_y, (long)M, scale, d_sums); break;
   }
   IDFF_CUDA(cudaGetLastError());
   count_launch();

@@ -29,6 +29,25 @@ def mmd_from_sums(sums, N, M):
     return sums[0] / (float(N) * N) + sums[1] / (float(M) * M) - 2.0 * sums[2] / (float(N) * M)
 
 
+def mmd_sweep(x, ys, sigma=1.0):
+    """MMD(x, ys[g]) for every generated set of a sweep: x (N, D), ys (G, M, D) -> fp64 tensor (G,) on the device.
+    One launch for all sets when D <= 4 (idff_mmd_rbf_sweep; Kxx is evaluated once), else one launch per set."""
+    _lib.require_cuda(x, "x")
+    _lib.require_cuda(ys, "ys")
+    x = x.detach().contiguous()
+    ys = ys.detach().contiguous()
+    if x.dim() != 2 or ys.dim() != 3 or x.shape[1] != ys.shape[2]:
+        raise _lib.IdffError(f"x {tuple(x.shape)} must be (N, D) and ys {tuple(ys.shape)} (G, M, D)")
+    N, D = x.shape
+    G, M = ys.shape[0], ys.shape[1]
+    if D > 4:
+        return torch.stack([mmd_from_sums(mmd_partial_sums(x, ys[g], sigma), N, M) for g in range(G)])
+    sums = torch.zeros(1 + 2 * G, device=x.device, dtype=torch.float64)
+    _lib.check(_lib.lib().idff_mmd_rbf_sweep(_lib.ptr(x), N, _lib.ptr(ys), M, G, D, float(sigma), _lib.ptr(sums),
+                                             _lib.stream_of(x)), "idff_mmd_rbf_sweep")
+    return sums[0] / (float(N) * N) + sums[1::2] / (float(M) * M) - 2.0 * sums[2::2] / (float(N) * M)
+
+
 def compute_mmd_rbf(x, y, sigma=1.0):
     """mean(Kxx) + mean(Kyy) - 2 mean(Kxy), K = exp(-|a-b|^2/(2 sigma^2)); returns a Python float."""
     if not torch.is_tensor(x):

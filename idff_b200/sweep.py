@@ -4,8 +4,8 @@
     the 10^3-tuple order-3 sweep       2D_examples/Autograd_example_order3.py:288-314
 
 All tuples of a sweep are solved by ONE sampler launch (idff_sample_rk4_sweep: the reference's 2048 particles fill 32 of
-148 SMs per tuple, 64 tuples fill the machine), followed by one MMD launch per tuple on the same stream; the kernel sums
-stay on the device and are read back once at the end (the reference synchronises on `.item()` twice per field call)."""
+148 SMs per tuple, 64 tuples fill the machine), followed by ONE MMD launch for all tuples (idff_mmd_rbf_sweep; Kxx of the
+fixed sample set is evaluated once); the values stay on the device and are read back once at the end (the reference synchronises on `.item()` twice per field call)."""
 from __future__ import annotations
 
 import itertools
@@ -31,16 +31,13 @@ def sweep_mmd(base_model, x0, true_samples, gamma_tuples, nfe, sigma=0.2, sigma_
     The solves of `chunk` tuples at a time go out as ONE sampler launch (idff_sample_rk4_sweep)."""
     t_span = torch.linspace(0, 1, nfe + 1)
     true_samples = torch.as_tensor(true_samples, dtype=torch.float32, device=x0.device)
-    N, M = true_samples.shape[0], x0.shape[0]
     gamma_tuples = list(gamma_tuples)
-    sums = []
+    vals = []
     for lo in range(0, len(gamma_tuples), chunk):
         models = [_field_for(base_model, g, sigma, impl) for g in gamma_tuples[lo:lo + chunk]]
-        outs = sampler.sample_rk4_sweep(models, x0, t_span)
-        for k in range(len(models)):
-            sums.append(mmd.mmd_partial_sums(true_samples, outs[k], sigma_kernel))
-    vals = torch.stack([mmd.mmd_from_sums(s, N, M) for s in sums]).cpu().tolist()     # the only synchronisation
-    return vals
+        outs = sampler.sample_rk4_sweep(models, x0, t_span)            # one sampler launch ...
+        vals.append(mmd.mmd_sweep(true_samples, outs, sigma_kernel))   # ... and one MMD launch per chunk of tuples
+    return torch.cat(vals).cpu().tolist()                              # the only synchronisation
 
 
 def find_best_gammas_mmd(base_model, x0, true_samples, gamma_range=(0.0, 0.5, 1.0, 2.0), nfe=20, sigma=0.2,

@@ -159,6 +159,13 @@ int idff_mmd_rbf(const float* d_x, int64_t N, const float* d_y, int64_t M, int32
                  double* d_sums, int64_t x_row_begin, int64_t x_row_end, int64_t y_row_begin, int64_t y_row_end,
                  void* stream);
 
+/* The MMD half of a gamma sweep (find_best_gammas_mmd, Autograd_example_order2.py:293-295): one fixed sample set d_x [N][D]
+ * against n_sets generated sets d_y [n_sets][M][D] (the output of idff_sample_rk4_sweep) in ONE launch, D <= 4.
+ * d_sums [1 + 2 n_sets] fp64, zeroed by the caller: [0] = sum Kxx, [1 + 2g] = sum Kyy of set g, [2 + 2g] = sum Kxy of set g;
+ * MMD_g = sums[0]/N^2 + sums[1+2g]/M^2 - 2 sums[2+2g]/(N M). */
+int idff_mmd_rbf_sweep(const float* d_x, int64_t N, const float* d_y, int64_t M, int32_t n_sets, int32_t D, float sigma_k,
+                       double* d_sums, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,6 +116,15 @@ def test_batched_sweep_equals_per_field_solves(cuda_device):
     t2 = time.perf_counter()
     print(f"64-tuple sweep, 2048 particles, nfe 2: batched {1e3 * (t1 - t0):.2f} ms, per tuple {1e3 * (t2 - t1):.2f} ms")
     assert (t1 - t0) < (t2 - t1)
+    # the whole caller (solves + MMD of every tuple + argmin), as the reference script runs it
+    true_s = torch.tensor(load_golden("mmd")["true_checkerboard"]).to(cuda_device)
+    sweep.find_best_gammas_mmd(pw, x0, true_s, gamma_range=grid8, nfe=2, sigma=0.2, sigma_kernel=1.0, order=2)
+    torch.cuda.synchronize()
+    t3 = time.perf_counter()
+    best, res = sweep.find_best_gammas_mmd(pw, x0, true_s, gamma_range=grid8, nfe=2, sigma=0.2, sigma_kernel=1.0, order=2)
+    t4 = time.perf_counter()
+    print(f"find_best_gammas_mmd, 8 x 8 tuples: {1e3 * (t4 - t3):.2f} ms end to end (2 launches), best {best}")
+    assert len(res) == 64 and all(np.isfinite(v) for _, v in res)
 
 
 def test_md_generation_as_cuda_graph(cuda_device):

@@ -57,3 +57,24 @@ def test_mmd_large_sets(cuda_device):
     sx, sy, sxy = O.mmd_partial_sums_fp64(x, y, 1.0)
     ref = sx / 16384 ** 2 + sy / 16384 ** 2 - 2 * sxy / 16384 ** 2
     _close(M.compute_mmd_rbf(x.to(cuda_device), y.to(cuda_device), 1.0), ref)
+
+
+def test_mmd_sweep_equals_per_set_evaluation(cuda_device):
+    """idff_mmd_rbf_sweep: one launch for G generated sets against one fixed set == G single evaluations."""
+    from idff_b200 import _lib
+    from idff_b200.mmd import mmd_from_sums, mmd_partial_sums, mmd_sweep
+    g = torch.Generator(device=cuda_device).manual_seed(11)
+    for (N, M, G, D) in ((2048, 2048, 5, 2), (1000, 333, 3, 2), (64, 700, 2, 4)):
+        x = torch.randn(N, D, device=cuda_device, generator=g)
+        ys = torch.randn(G, M, D, device=cuda_device, generator=g) * 1.3 + 0.2
+        before = _lib.launch_count()
+        got = mmd_sweep(x, ys, 1.0)
+        assert _lib.launch_count() == before + 1 and got.shape == (G,) and got.dtype == torch.float64
+        ref = torch.stack([mmd_from_sums(mmd_partial_sums(x, ys[k], 1.0), N, M) for k in range(G)])
+        np.testing.assert_allclose(got.cpu().numpy(), ref.cpu().numpy(), rtol=1e-10, atol=1e-14)
+    # D > 4 falls back to one launch per set
+    x = torch.randn(100, 46, device=cuda_device, generator=g) * 30
+    ys = torch.randn(3, 50, 46, device=cuda_device, generator=g) * 30
+    got = mmd_sweep(x, ys, 1.0)
+    ref = torch.stack([mmd_from_sums(mmd_partial_sums(x, ys[k], 1.0), 100, 50) for k in range(3)])
+    np.testing.assert_allclose(got.cpu().numpy(), ref.cpu().numpy(), rtol=1e-10, atol=1e-14)
