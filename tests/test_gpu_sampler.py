@@ -184,3 +184,35 @@ def test_fused_kernel_is_selected_and_agrees_with_generic(cuda_device):
     sh.impl = _lib.IDFF_IMPL_FUSED
     with pytest.raises(_lib.IdffError):
         sampler.sample_rk4(sh, x0[:8], ts)
+
+
+def test_tensor16_full_size_properties_and_range_guard(cuda_device):
+    """BASELINE-size batch through the default (3xFP16 tensor) sampler: particles are independent, so any slice of a
+    4 M-particle solve is reproduced bit-for-bit by solving the slice alone; trajectories end where sample_rk4 ends.
+    Operands beyond the fp16 range make THAT particle's output non-finite (never silently wrong) and are counted."""
+    pw = packed("checkerboard", cuda_device)
+    m = fields.CustomNetModel(pw, 0.2, 0.2, 0.2)                      # AUTO -> k_tc16
+    n = 1 << 22
+    x0 = torch.randn(n, 2, device=cuda_device, generator=torch.Generator(device=cuda_device).manual_seed(9)) / 1.5
+    ts = torch.linspace(0, 1, 3)
+    whole = sampler.sample_rk4(m, x0, ts)
+    assert torch.isfinite(whole).all()
+    for lo, hi in ((0, 4097), (1 << 21, (1 << 21) + 64), (n - 12345, n)):
+        assert torch.equal(sampler.sample_rk4(m, x0[lo:hi], ts), whole[lo:hi])
+    traj = sampler.odeint(m, x0[:70000], ts, method="rk4")
+    assert torch.equal(traj[-1], whole[:70000]) and torch.equal(traj[0], x0[:70000])
+    # the distribution moved toward the checkerboard support (|x| <= 4): a sanity property of the shipped model
+    assert (whole.abs() < 6).float().mean().item() > 0.99
+    # range guard
+    before = _lib.tensor16_nonfinite()
+    bad = x0[:128].clone()
+    bad[5] = 3.0e6                                                   # layer-1 pre-activations far beyond 65504
+    out = sampler.sample_rk4(m, bad, ts)
+    assert not torch.isfinite(out[5]).all()
+    keep = torch.ones(128, dtype=torch.bool, device=cuda_device)
+    keep[5] = False
+    assert torch.equal(out[keep], whole[:128][keep])                 # the other particles of the tile are untouched
+    assert _lib.tensor16_nonfinite() > before
+    mf = fields.CustomNetModel(pw, 0.2, 0.2, 0.2)
+    mf.impl = _lib.IDFF_IMPL_FUSED                                   # the fp32 kernel serves such inputs
+    assert torch.isfinite(sampler.sample_rk4(mf, bad, ts)).all()
