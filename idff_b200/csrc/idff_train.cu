@@ -18,25 +18,72 @@ __device__ __forceinline__ void path_elem(float x0, float x1, float t, float st,
   ut = __fsub_rn(x1, x0);
 }
 
-// Vectorised path: no gather, (B*D) % 4 == 0 and 16-byte aligned pointers.  Each thread owns 4 consecutive
-// elements per iteration; rows are recovered from the flat index (D is arbitrary).
-__global__ void __launch_bounds__(256) k_path_sample_vec(const float4* __restrict__ x0, const float4* __restrict__ x1,
-                                                         const float* __restrict__ t, const float4* __restrict__ eps,
-                                                         float sigma, int mode, float4* __restrict__ xt,
-                                                         float4* __restrict__ ut, long n4, long D) {
-  const long stride = (long)gridDim.x * blockDim.x;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const float4 a = __ldcs(x0 + i), b = __ldcs(x1 + i);
-    const float4 e = eps ? __ldcs(eps + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+// Times of the 4 consecutive flat elements 4i .. 4i+3 (row = element / D).  DM = 1, 2: D == 1 / 2, one aligned vector load
+// (equal rows share a register, so the per-row scalars -- sigma_t, the loss weight -- are computed once per row);
+// DM = 4: D % 4 == 0, the four elements lie in one row; DM = 0: any D, 32-bit division (the host picks DM = 0 only when
+// the flat index fits 32 bits, DM = -1 otherwise: 64-bit division).
+template <int DM>
+__device__ __forceinline__ void load_t4(const float* __restrict__ t, long i, long D, float (&tv)[4]) {
+  if (DM == 1) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(t) + i);
+    tv[0] = v.x; tv[1] = v.y; tv[2] = v.z; tv[3] = v.w;
+  } else if (DM == 2) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(t) + i);
+    tv[0] = v.x; tv[1] = v.x; tv[2] = v.y; tv[3] = v.y;
+  } else if (DM == 4) {
+    const float v = __ldg(t + (unsigned)i / (unsigned)(D >> 2));
+    tv[0] = v; tv[1] = v; tv[2] = v; tv[3] = v;
+  } else if (DM == 0) {
+    const unsigned e0 = 4u * (unsigned)i, Du = (unsigned)D;
+    unsigned row = e0 / Du, rem = e0 - row * Du;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      tv[q] = __ldg(t + row);
+      if (++rem == Du) { rem = 0; ++row; }
+    }
+  } else {
     const long e0 = 4 * i;
-    long row = e0 / D;
-    long rem = e0 - row * D;
-    float tv[4];
+    long row = e0 / D, rem = e0 - row * D;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       tv[q] = __ldg(t + row);
       if (++rem == D) { rem = 0; ++row; }
     }
+  }
+}
+// host side: which load_t4 variant serves (t, D, n4)
+static int pick_dm(const void* t, long D, long n4) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(t);
+  if (n4 >= (1L << 30)) return -1;
+  if (D == 1 && (a & 15) == 0) return 1;
+  if (D == 2 && (a & 7) == 0) return 2;
+  if (D % 4 == 0) return 4;
+  return 0;
+}
+
+// Vectorised path: no gather, (B*D) % 4 == 0 and 16-byte aligned pointers.  Each thread owns 4 consecutive
+// elements per iteration; rows are recovered from the flat index (D is arbitrary).
+template <int DM>
+__global__ void __launch_bounds__(256, 6) k_path_sample_vec(const float4* __restrict__ x0, const float4* __restrict__ x1,
+                                                            const float* __restrict__ t, const float4* __restrict__ eps,
+                                                            float sigma, int mode, float4* __restrict__ xt,
+                                                            float4* __restrict__ ut, long n4, long D) {
+  const long stride = (long)gridDim.x * blockDim.x;
+  // two independent 128-bit groups per thread and iteration: twice the loads in flight
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += 2 * stride) {
+    const long i2 = i + stride;
+    const bool two = i2 < n4;
+    const float4 a = __ldcs(x0 + i), b = __ldcs(x1 + i);
+    const float4 e = eps ? __ldcs(eps + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 a2 = a, b2 = b, e2 = e;
+    if (two) {
+      a2 = __ldcs(x0 + i2);
+      b2 = __ldcs(x1 + i2);
+      if (eps) e2 = __ldcs(eps + i2);
+    }
+    float tv[4], tw[4];
+    load_t4<DM>(t, i, D, tv);
+    if (two) load_t4<DM>(t, i2, D, tw);
     float4 o, u;
     path_elem(a.x, b.x, tv[0], sigma_t_of(tv[0], sigma, mode), e.x, o.x, u.x);
     path_elem(a.y, b.y, tv[1], sigma_t_of(tv[1], sigma, mode), e.y, o.y, u.y);
@@ -44,6 +91,14 @@ __global__ void __launch_bounds__(256) k_path_sample_vec(const float4* __restric
     path_elem(a.w, b.w, tv[3], sigma_t_of(tv[3], sigma, mode), e.w, o.w, u.w);
     __stcs(xt + i, o);
     if (ut) __stcs(ut + i, u);
+    if (two) {
+      path_elem(a2.x, b2.x, tw[0], sigma_t_of(tw[0], sigma, mode), e2.x, o.x, u.x);
+      path_elem(a2.y, b2.y, tw[1], sigma_t_of(tw[1], sigma, mode), e2.y, o.y, u.y);
+      path_elem(a2.z, b2.z, tw[2], sigma_t_of(tw[2], sigma, mode), e2.z, o.z, u.z);
+      path_elem(a2.w, b2.w, tw[3], sigma_t_of(tw[3], sigma, mode), e2.w, o.w, u.w);
+      __stcs(xt + i2, o);
+      if (ut) __stcs(ut + i2, u);
+    }
   }
 }
 
@@ -136,8 +191,8 @@ __device__ __forceinline__ void loss_elem(float av, float b1, float x0v, float x
   }
 }
 
-template <int KIND, int VEC>
-__global__ void __launch_bounds__(256) k_loss(const float* __restrict__ a, const float* __restrict__ x1,
+template <int KIND, int VEC, int DM>
+__global__ void __launch_bounds__(256, 6) k_loss(const float* __restrict__ a, const float* __restrict__ x1,
                                               const float* __restrict__ x0, const float* __restrict__ xt,
                                               const float* __restrict__ t, float sigma0_sq, float gscale,
                                               float* __restrict__ loss, float* __restrict__ grad, long n, long D,
@@ -159,15 +214,7 @@ __global__ void __launch_bounds__(256) k_loss(const float* __restrict__ a, const
       float4 x0v = make_float4(0.f, 0.f, 0.f, 0.f), xtv = x0v;
       if (KIND == 1) { x0v = __ldcs(x04 + i); xtv = __ldcs(xt4 + i); }
       float tv[4] = {0.f, 0.f, 0.f, 0.f};
-      if (KIND != 2) {
-        const long e0 = 4 * i;
-        long row = e0 / D, rem = e0 - row * D;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          tv[q] = __ldg(t + row);
-          if (++rem == D) { rem = 0; ++row; }
-        }
-      }
+      if (KIND != 2) load_t4<DM>(t, i, D, tv);
       float4 go;
       loss_elem<KIND>(av.x, bv.x, x0v.x, xtv.x, tv[0], sigma0_sq, gk, s0, s1, s2, go.x);
       loss_elem<KIND>(av.y, bv.y, x0v.y, xtv.y, tv[1], sigma0_sq, gk, s0, s1, s2, go.y);
@@ -251,11 +298,16 @@ extern "C" int idff_path_sample(const float* d_x0, const float* d_x1, const floa
   const bool vec = !d_idx0 && !d_idx1 && (n % 4 == 0) && al16(d_x0) && al16(d_x1) && al16(d_eps) && al16(d_xt) && al16(d_ut);
   if (vec) {
     const long n4 = n / 4;
-    const int grid = stream_grid(n4, 256, dev, 8);
-    k_path_sample_vec<<<grid, 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(d_x0), reinterpret_cast<const float4*>(d_x1), d_t,
-        reinterpret_cast<const float4*>(d_eps), sigma, sigma_mode, reinterpret_cast<float4*>(d_xt),
-        reinterpret_cast<float4*>(d_ut), n4, (long)D);
+    const int grid = stream_grid((n4 + 1) / 2, 256, dev, 6);
+    const int dm = pick_dm(d_t, (long)D, n4);
+#define IDFF_PS_LAUNCH(DM)                                                                                   \
+  k_path_sample_vec<DM><<<grid, 256, 0, (cudaStream_t)stream>>>(                                             \
+      reinterpret_cast<const float4*>(d_x0), reinterpret_cast<const float4*>(d_x1), d_t,                     \
+      reinterpret_cast<const float4*>(d_eps), sigma, sigma_mode, reinterpret_cast<float4*>(d_xt),            \
+      reinterpret_cast<float4*>(d_ut), n4, (long)D)
+    if (dm == 1) IDFF_PS_LAUNCH(1); else if (dm == 2) IDFF_PS_LAUNCH(2); else if (dm == 4) IDFF_PS_LAUNCH(4);
+    else if (dm == 0) IDFF_PS_LAUNCH(0); else IDFF_PS_LAUNCH(-1);
+#undef IDFF_PS_LAUNCH
   } else {
     const int grid = stream_grid(n, 256, dev, 8);
     k_path_sample_gather<<<grid, 256, 0, (cudaStream_t)stream>>>(d_x0, d_x1, d_t, d_eps, d_idx0, d_idx1, sigma,
@@ -293,17 +345,25 @@ extern "C" int idff_loss(int32_t kind, const float* d_a, const float* d_x1, cons
   const long n = (long)B * (long)D;
   auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const bool vec = (n % 4 == 0) && al16(d_a) && al16(d_x1) && al16(d_x0) && al16(d_xt) && al16(d_grad);
-  int grid = stream_grid(vec ? n / 4 : n, 256, dev, 8);
+  int grid = stream_grid(vec ? n / 4 : n, 256, dev, 6);
   if (grid > kLossMaxBlocks) grid = kLossMaxBlocks;
   LossScratch* sc = reinterpret_cast<LossScratch*>(d_scratch);
   cudaStream_t s = (cudaStream_t)stream;
-#define IDFF_LOSS_LAUNCH(K, V) \
-  k_loss<K, V><<<grid, 256, 0, s>>>(d_a, d_x1, d_x0, d_xt, d_t, sigma0_sq, grad_scale, d_loss, d_grad, n, (long)D, sc)
+  const int dm = (vec && kind != 2) ? pick_dm(d_t, (long)D, n / 4) : -1;
+#define IDFF_LOSS_LAUNCH(K, V, DM) \
+  k_loss<K, V, DM><<<grid, 256, 0, s>>>(d_a, d_x1, d_x0, d_xt, d_t, sigma0_sq, grad_scale, d_loss, d_grad, n, (long)D, sc)
+#define IDFF_LOSS_DM(K)                                                                                       \
+  do {                                                                                                        \
+    if (dm == 1) IDFF_LOSS_LAUNCH(K, 4, 1); else if (dm == 2) IDFF_LOSS_LAUNCH(K, 4, 2);                      \
+    else if (dm == 4) IDFF_LOSS_LAUNCH(K, 4, 4); else if (dm == 0) IDFF_LOSS_LAUNCH(K, 4, 0);                 \
+    else IDFF_LOSS_LAUNCH(K, 4, -1);                                                                          \
+  } while (0)
   if (vec) {
-    if (kind == 0) IDFF_LOSS_LAUNCH(0, 4); else if (kind == 1) IDFF_LOSS_LAUNCH(1, 4); else IDFF_LOSS_LAUNCH(2, 4);
+    if (kind == 0) IDFF_LOSS_DM(0); else if (kind == 1) IDFF_LOSS_DM(1); else IDFF_LOSS_LAUNCH(2, 4, -1);
   } else {
-    if (kind == 0) IDFF_LOSS_LAUNCH(0, 1); else if (kind == 1) IDFF_LOSS_LAUNCH(1, 1); else IDFF_LOSS_LAUNCH(2, 1);
+    if (kind == 0) IDFF_LOSS_LAUNCH(0, 1, -1); else if (kind == 1) IDFF_LOSS_LAUNCH(1, 1, -1); else IDFF_LOSS_LAUNCH(2, 1, -1);
   }
+#undef IDFF_LOSS_DM
 #undef IDFF_LOSS_LAUNCH
   IDFF_CUDA(cudaGetLastError());
   count_launch();
