@@ -32,12 +32,10 @@
 // algebra is thread-local, and sums over units are 3 in-thread adds + a 3-step shuffle.  16 epilogue warps = 4 lane
 // quarters x 4 particle quarters; every thread serves m-tile 0 and then m-tile 1 of a pass.  The m-tile-0 epilogue computes while the m-tile-1 MMAs run, and the
 // next pass starts on k-blocks 0-1 (written by the m-tile-0 epilogue) while the m-tile-1 epilogue is still at work.
-#include <cuda_fp16.h>
-
 #include <cstdlib>
 #include <vector>
 
-#include "idff_common.cuh"
+#include "idff_tcgen05.cuh"
 
 namespace idff {
 void jets_needed(const idff_field_params_t& p, int* nj, int* reverse);
@@ -60,124 +58,8 @@ constexpr int NTHREADS = NE + 64;         // + producer warp 16 + MMA warp 17
 constexpr int HP = 16;                    // particles per epilogue thread
 constexpr int TMEM_COLS = 512;
 constexpr int COL_CORR = 128, COL_STASH = 256;
-constexpr float LO_SCALE = 2048.0f, LO_INV = 1.0f / 2048.0f;
 
-__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}\n"
-      : "=r"(ok)
-      : "r"(s32(b)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
-  while (!mbar_try_wait(b, parity)) {
-  }
-}
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* b, uint32_t parity) {
-  while (!mbar_try_wait(b, parity)) __nanosleep(128);
-}
-__device__ __forceinline__ void tma_load_1d_mc(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(s32(dst)),
-      "l"(src), "r"(bytes), "r"(s32(bar)), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(s32(bar)),
-               "h"(mask)
-               : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
-}
-// one lane of a converged warp
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void ebar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // epilogue warps only
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (8-row groups 1024 B apart)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)2 << 61);
-}
-// K-major SWIZZLE_64B (64-byte rows, 8-row groups 512 B apart): the activation operand
-__device__ __forceinline__ uint64_t make_desc64(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)4 << 61);
-}
-__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
-      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-#define IDFF_R8(v, o) "=r"(v[o]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7])
-#define IDFF_I8(v, o) "r"(v[o]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3]), "r"(v[o + 4]), "r"(v[o + 5]), "r"(v[o + 6]), "r"(v[o + 7])
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-               : IDFF_R8(v, 0), IDFF_R8(v, 8)
-               : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};" ::IDFF_I8(v, 0),
-               IDFF_I8(v, 8), "r"(taddr)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// v0, v1 -> packed fp16 pairs: h2 = {lo half: hi(v0), hi half: hi(v1)}, l2 likewise for the scaled remainders
-__device__ __forceinline__ void split2(float v0, float v1, uint32_t& h2, uint32_t& l2) {
-  float f0, f1;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(v1), "f"(v0));
-  asm("{\n.reg .b16 a, b;\nmov.b32 {a, b}, %2;\ncvt.f32.f16 %0, a;\ncvt.f32.f16 %1, b;\n}\n" : "=f"(f0), "=f"(f1) : "r"(h2));
-  const float d0 = __fmul_rn(__fsub_rn(v0, f0), LO_SCALE), d1 = __fmul_rn(__fsub_rn(v1, f1), LO_SCALE);
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(l2) : "f"(d1), "f"(d0));
-}
-// tcgen05.ld/st.16x128b.x4: 16 TMEM lanes x 16 columns; thread T: register 2r + h <-> lane T/4 + 8h, column 4r + T%4
-// [layout verified on the part: profiles/microbench/tmem_shapes.cu]
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
-  asm volatile("tcgen05.ld.sync.aligned.16x128b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
-  asm volatile("tcgen05.st.sync.aligned.16x128b.x4.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::"r"(v[0]), "r"(v[1]), "r"(v[2]),
-               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(taddr)
-               : "memory");
-}
-template <int OFF>
-__device__ __forceinline__ void st64(uint32_t base, uint32_t w0, uint32_t w1) {
-  asm volatile("st.shared.v2.b32 [%0+%3], {%1, %2};" ::"r"(base), "r"(w0), "r"(w1), "n"(OFF) : "memory");
-}
+using namespace tcg;
 
 // phase timestamps (clock64) of CTA 0, first tile, evaluation 1 (an interior one): diagnostic only
 __device__ long long g_tc16_stamps[32];
@@ -204,44 +86,6 @@ struct Smem {   // byte offsets from the dynamic base, which must be 1024-byte a
   static constexpr int total = bars + 128;
 };
 static_assert(Smem::total <= 232448, "shared memory budget");
-
-// reduce-scatter of 32 per-thread partial sums over the 32 lanes of a warp: lane L ends with the total of v[L]
-__device__ __forceinline__ void warp_reduce_scatter32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int off = 16, cnt = 16; off >= 1; off >>= 1, cnt >>= 1) {
-    const bool up = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < cnt; ++i) {
-      const float send = up ? v[i] : v[i + cnt];
-      const float keep = up ? v[i + cnt] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-}
-
-// SELU value a, first derivative s1 and E = every higher derivative at z (ATen: z <= 0 -> (exp(z) - 1) * LA, derivative
-// LA * exp(z); z > 0 -> lambda * z, lambda, 0).  exp through ex2.approx on z * log2(e): the same MUFU.EX2 CUDA's expf is
-// built on (2 ulp), without its range-reduction scaffolding; the extra input rounding is |z| * 2^-24 relative.
-__device__ __forceinline__ void selu_jet(float z, float& a, float& s1, float& E) {
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(z, 0.0f) * 1.4426950408889634f));
-  const bool pos = !(z <= 0.0f);   // keeps NaN on the linear branch
-  const float t = kSeluLA * e;
-  a = pos ? z * kSeluLambda : (e - 1.0f) * kSeluLA;
-  s1 = pos ? kSeluLambda : t;
-  E = pos ? 0.0f : t;
-}
-
-// same, returning the derivative code kept in the stash: LA * exp(z) (= s1 = E) on the exp branch, -1 on the linear one
-__device__ __forceinline__ void selu_jet_code(float z, float& a, float& s1, float& code) {
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(z, 0.0f) * 1.4426950408889634f));
-  const bool pos = !(z <= 0.0f);
-  const float t = kSeluLA * e;
-  a = pos ? z * kSeluLambda : (e - 1.0f) * kSeluLA;
-  s1 = pos ? kSeluLambda : t;
-  code = pos ? -1.0f : t;
-}
 
 // A thread's 16 values of one jet are indexed e = 8*ld + 2*r + h: unit 2*ld + h (of its 4 consecutive units), particle
 // r (of its 4).  pack_jet: hi / lo' fp16 words of the unit pairs (0,1) and (2,3) for each particle: hw[2r + ld].
