@@ -20,6 +20,12 @@ class IdffError(RuntimeError):
     pass
 
 
+class AdamW(C.Structure):
+    """idff_adamw_t: torch.optim.AdamW's hyper-parameters + the clip_grad_norm_ threshold."""
+    _fields_ = [("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+                ("weight_decay", C.c_double), ("max_grad_norm", C.c_double)]
+
+
 class FieldParams(C.Structure):
     _fields_ = [("variant", C.c_int32), ("order", C.c_int32), ("dim", C.c_int32), ("t_idx", C.c_int32),
                 ("impl", C.c_int32), ("reserved", C.c_int32), ("sigma", C.c_double), ("gamma", C.c_double * 3),
@@ -53,6 +59,11 @@ SIGNATURES = {
     "idff_loss": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp, _i64, _i64, _vp, _vp]),
     "idff_mmd_rbf": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _f32, _vp, _i64, _i64, _i64, _i64, _vp]),
     "idff_mmd_rbf_sweep": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _f32, _vp, _vp]),
+    "idff_train_flow_state_floats": (C.c_int64, []),
+    "idff_train_flow_offsets": (C.c_int, [_vp]),
+    "idff_train_flow_init": (C.c_int, [_vp, _vp]),
+    "idff_train_flow_steps": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _i32, C.POINTER(AdamW), _i64, _vp, _vp,
+                                        _vp, _vp]),
 }
 
 _lib = None

@@ -10,13 +10,19 @@ CUDA graph.
 At the reference's batch size (256) this step is ~60 tiny kernels and purely launch-bound, so `GraphedFlowTrainer`
 captures it once -- data draw, path-sample kernel, MLP forward/backward, loss kernel, clipping and a capturable AdamW
 -- and replays it with one `cudaGraphLaunch` per step.  `flow_train_step` is the same step in eager form with the
-random draws passed in (used by the parity test against the reference's formula).  The MLP's own GEMMs stay in
-torch: training the network is SURVEY.md section 8(f) row 3, not the sampler hot path."""
+random draws passed in (used by the parity test against the reference's formula).
+
+`FusedFlowTrainer` goes one step further for the network the 2-D scripts train (MLP 3-256-256-256-2, flow loss): the
+whole step -- path sample, forward, loss, backward, gradient-norm clipping, AdamW -- is ONE hand-written persistent
+kernel (`idff_train_flow_steps`, csrc/idff_trainer.cu) that runs many consecutive steps per launch; no torch kernel
+is involved and the model's parameters are views of the kernel's state buffer.  SURVEY.md section 8(f) row 3."""
 from __future__ import annotations
+
+import ctypes as C
 
 import torch
 
-from . import losses
+from . import _lib, losses
 from .torchcfm import conditional_flow_matching as cfm
 
 
@@ -80,3 +86,98 @@ class GraphedFlowTrainer:
         self.graph.replay()
         self.steps += 1
         return self.loss
+
+
+class FusedFlowTrainer:
+    """The reference's 2-D training loop (Autograd_example_order2.py:89-112) on `idff_train_flow_steps`.
+
+    model: torchcfm MLP(dim=2, w=256, time_varying=True) on a CUDA device.  Its parameters are re-pointed at the
+    kernel's state buffer, so the module (forward, state_dict, PackedWeights.from_module) always sees the trained weights.
+        tr = FusedFlowTrainer(model, batch_size=256)
+        losses = tr.steps(x0, x1, t, eps)          # [S][B][2], [S][B][2], [S][B], [S][B][2] (eps optional) -> [S] losses
+        losses = tr.run(n_steps)                   # draws checkerboard / normal / uniform samples on the device first
+    """
+
+    def __init__(self, model: torch.nn.Module, batch_size: int = 256, sigma: float = 0.0, lr: float = 2e-4,
+                 betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2, clip: float = 1.0,
+                 data=checkerboard_device, exact_ot_sigma: bool = True):
+        L = _lib.lib()
+        params = [p for p in model.parameters()]
+        shapes = [tuple(p.shape) for p in params]
+        if shapes != [(256, 3), (256,), (256, 256), (256,), (256, 256), (256,), (2, 256), (2,)]:
+            raise _lib.IdffError(f"FusedFlowTrainer serves MLP(dim=2, w=256, time_varying=True) only, got {shapes}; "
+                                 "use GraphedFlowTrainer for other networks")
+        self.device = params[0].device
+        if self.device.type != "cuda":
+            raise _lib.IdffError("FusedFlowTrainer needs a CUDA device: idff_b200 has no CPU path")
+        self.B = int(batch_size)
+        off = (C.c_int64 * 12)()
+        _lib.check(L.idff_train_flow_offsets(off), "idff_train_flow_offsets")
+        self.offsets = [int(v) for v in off]
+        self.n_params = self.offsets[8]
+        self.state = torch.zeros(int(L.idff_train_flow_state_floats()), device=self.device, dtype=torch.float32)
+        base = self.offsets[9]
+        with torch.no_grad():
+            for p, o in zip(params, self.offsets[:8]):
+                view = self.state[base + o: base + o + p.numel()].view(p.shape)
+                view.copy_(p)
+                p.data = view
+        self.model = model
+        self.opt = _lib.AdamW(lr, betas[0], betas[1], eps, weight_decay, clip)
+        self.sigma, self.sigma_mode = float(sigma), 1 if exact_ot_sigma else 0   # ExactOT matcher: sigma*sqrt(t(1-t))
+        self.data = data
+        self.steps_done = 0
+        self.sync_params()
+
+    def sync_params(self):
+        """Rebuild the kernel's transposed weight copies after the parameters were written from outside."""
+        _lib.check(_lib.lib().idff_train_flow_init(_lib.ptr(self.state), _lib.stream_of(self.state)), "idff_train_flow_init")
+
+    def _block(self, name):   # parameter-block shaped views: "param", "exp_avg", "exp_avg_sq"
+        base = self.offsets[{"param": 9, "exp_avg": 10, "exp_avg_sq": 11}[name]]
+        return self.state[base: base + self.n_params]
+
+    def named_block(self, name):
+        """The 8 tensors (nn.Linear layout) of the parameter / exp_avg / exp_avg_sq block."""
+        flat, shapes = self._block(name), [(256, 3), (256,), (256, 256), (256,), (256, 256), (256,), (2, 256), (2,)]
+        out = []
+        for o, sh in zip(self.offsets[:8], shapes):
+            n = 1
+            for v in sh:
+                n *= v
+            out.append(flat[o: o + n].view(sh))
+        return out
+
+    def steps(self, x0, x1, t, eps=None, return_gnorm: bool = False, grad_dump: torch.Tensor | None = None):
+        for name, v in (("x0", x0), ("x1", x1), ("t", t)) + ((("eps", eps),) if eps is not None else ()):
+            _lib.require_cuda(v, name)
+            if not v.is_contiguous():
+                raise _lib.IdffError(f"{name} must be contiguous")
+        if x0.dim() == 2:
+            x0, x1, t = x0[None], x1[None], t[None]
+            eps = eps[None] if eps is not None else None
+        S, B = int(t.shape[0]), int(t.shape[1])
+        if tuple(x0.shape) != (S, B, 2) or tuple(x1.shape) != (S, B, 2) or (eps is not None and tuple(eps.shape) != (S, B, 2)):
+            raise _lib.IdffError(f"expected x0, x1[, eps] of shape ({S}, {B}, 2)")
+        loss = torch.empty(S, device=self.device, dtype=torch.float32)
+        gnorm = torch.empty(S, device=self.device, dtype=torch.float32) if return_gnorm else None
+        _lib.check(_lib.lib().idff_train_flow_steps(
+            _lib.ptr(self.state), _lib.ptr(x0), _lib.ptr(x1), _lib.ptr(t), _lib.ptr(eps), S, B, self.sigma, self.sigma_mode,
+            C.byref(self.opt), self.steps_done, _lib.ptr(loss), _lib.ptr(gnorm), _lib.ptr(grad_dump),
+            _lib.stream_of(self.state)), "idff_train_flow_steps")
+        self.steps_done += S
+        for p in self.model.parameters():      # the kernel wrote them in place: invalidate caches keyed on _version
+            torch.autograd.graph.increment_version(p)
+        return (loss, gnorm) if return_gnorm else loss
+
+    def draw(self, n_steps: int):
+        """Device draws for n_steps steps: x1 ~ data, x0 = randn_like, t ~ U(0,1) (order2.py:92-95; t on the device)."""
+        x1 = self.data(n_steps * self.B, self.device).view(n_steps, self.B, 2).contiguous()
+        x0 = torch.randn_like(x1)
+        t = torch.rand(n_steps, self.B, device=self.device)
+        eps = torch.randn_like(x1) if self.sigma != 0.0 else None
+        return x0, x1, t, eps
+
+    def run(self, n_steps: int) -> torch.Tensor:
+        x0, x1, t, eps = self.draw(n_steps)
+        return self.steps(x0, x1, t, eps)

@@ -166,6 +166,36 @@ int idff_mmd_rbf(const float* d_x, int64_t N, const float* d_y, int64_t M, int32
 int idff_mmd_rbf_sweep(const float* d_x, int64_t N, const float* d_y, int64_t M, int32_t n_sets, int32_t D, float sigma_k,
                        double* d_sums, void* stream);
 
+/* ---- the 2-D training step (Autograd_example_order2.py:89-112 = Autograd_example_order3.py:90-109)
+ *   t, xt, ut, eps = FM.sample_location_and_conditional_flow(x0, x1)   (path sample, conditional_flow_matching.py:153-193)
+ *   vt = base_model(cat[xt, t])                                         (MLP 3-256-256-256-2, models.py:4-21)
+ *   loss = mean(((1/(1e-2+1-t)) * (vt - FM.x1))**2); loss.backward()    (:105, :109)
+ *   clip_grad_norm_(params, max_grad_norm); AdamW.step()                (:110-112)
+ * as ONE persistent cooperative kernel that runs n_steps consecutive steps per launch: path sample, forward, loss,
+ * backward, gradient-norm clipping and the AdamW update, no torch kernel in between.
+ * The caller owns the state: d_state = idff_train_flow_state_floats() fp32 (16-byte aligned), zero-initialised, holding
+ * parameters, AdamW moments and scratch.  idff_train_flow_offsets fills h_out12 = {offset of 0.weight [256][3], 0.bias,
+ * 2.weight [256][256], 2.bias, 4.weight, 4.bias, 6.weight [2][256], 6.bias within a parameter block, parameter count,
+ * state offset of the parameter block, of exp_avg, of exp_avg_sq} (floats; tensors in nn.Linear's own layout, so torch
+ * parameters can be views of the state).  After writing the parameters call idff_train_flow_init (builds the transposed
+ * forward copies); call it again whenever the parameters are changed from outside.
+ * Inputs of step s: d_x0, d_x1, d_eps [n_steps][B][2] (d_eps may be NULL: sigma_t * eps = 0), d_t [n_steps][B].
+ * B: multiple of 4 in [4, IDFF_TRAIN_MAX_BATCH].  steps_done: optimizer steps taken before this call (AdamW bias
+ * correction).  max_grad_norm <= 0 disables clipping.  Outputs (each optional): d_loss [n_steps], d_gnorm [n_steps] (total
+ * gradient norm before clipping), d_grad_dump [parameter count] (unclipped gradient of the last step, parameter-block
+ * layout).  Other networks / losses train through torch (idff_b200/train.py GraphedFlowTrainer). */
+#define IDFF_TRAIN_MAX_BATCH 512
+typedef struct idff_adamw {
+  double lr, beta1, beta2, eps, weight_decay; /* torch.optim.AdamW defaults: 1e-3 (the scripts use 2e-4), 0.9, 0.999, 1e-8, 1e-2 */
+  double max_grad_norm;                       /* clip_grad_norm_ threshold: 1 (Autograd_example_order2.py:111) */
+} idff_adamw_t;
+int64_t idff_train_flow_state_floats(void);
+int idff_train_flow_offsets(int64_t* h_out12);
+int idff_train_flow_init(float* d_state, void* stream);
+int idff_train_flow_steps(float* d_state, const float* d_x0, const float* d_x1, const float* d_t, const float* d_eps,
+                          int32_t n_steps, int32_t B, float sigma, int32_t sigma_mode, const idff_adamw_t* opt,
+                          int64_t steps_done, float* d_loss, float* d_gnorm, float* d_grad_dump, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -348,6 +348,41 @@ def flow_loss(vt, x1, t):
     return torch.mean(((1 / (1e-2 + 1 - t[:, None])) * (vt - x1)) ** 2)
 
 
+def train_steps_2d(layers, x0, x1, t, eps, sigma=0.0, lr=2e-4, clip=1.0, return_grads=False):
+    """The 2-D training loop, Autograd_example_order2.py:89-112 (= Autograd_example_order3.py:90-109), with the random
+    draws passed in: x0, x1, eps [S][B][2], t [S][B].  MLP(dim=2, w=256, time_varying=True) as nn.Sequential of the given
+    layers, AdamW(lr) with torch defaults (:80), ExactOT matcher sigma (:81, OT pairing off), clip_grad_norm_(1) (:111).
+    Returns (per-step losses, per-step total gradient norms, final layers[, unclipped gradients of the last step])."""
+    dt = layers[0][0].dtype
+    mods = []
+    for i, (W, b) in enumerate(layers):
+        lin = torch.nn.Linear(W.shape[1], W.shape[0]).to(dt)
+        with torch.no_grad():
+            lin.weight.copy_(W)
+            lin.bias.copy_(b)
+        mods.append(lin)
+        if i + 1 < len(layers):
+            mods.append(torch.nn.SELU())
+    net = torch.nn.Sequential(*mods)                                              # models.py:9-18
+    optimizer = torch.optim.AdamW(net.parameters(), lr=lr)                        # order2.py:80
+    losses, norms, grads = [], [], None
+    for s in range(t.shape[0]):
+        optimizer.zero_grad()                                                     # :91
+        xt, ut = path_sample(x0[s], x1[s], t[s], eps[s] if eps is not None else torch.zeros_like(x0[s]), sigma, True,
+                             ieee_sqrt=True)                                      # :95
+        vt = net(torch.cat([xt, t[s][:, None]], dim=-1))                          # :98
+        loss = flow_loss(vt, x1[s], t[s])                                         # :105
+        loss.backward()                                                           # :109
+        if return_grads and s == t.shape[0] - 1:
+            grads = [p.grad.detach().clone() for p in net.parameters()]
+        norms.append(float(torch.nn.utils.clip_grad_norm_(net.parameters(), clip)))   # :111
+        optimizer.step()                                                          # :112
+        losses.append(float(loss.detach()))
+    out_layers = [(mods[2 * i].weight.detach().clone(), mods[2 * i].bias.detach().clone()) for i in range(4)]
+    res = (losses, norms, out_layers)
+    return res + (grads,) if return_grads else res
+
+
 def log_prob_xt_given_x1_dimwise(x_t, x_1, x_0, t, sigma0_sq):
     """example_order1_with_prediction_head.py:26-51."""
     if t.ndim == 1:

@@ -1,0 +1,29 @@
+"""Rate of the fused training kernel (idff_train_flow_steps): us/step and samples/s at the reference's batch (256) and others,
+S steps per launch, inputs pre-drawn on the device (and, separately, including the device draws)."""
+import os, sys, time
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
+import torch
+from idff_b200 import train
+from idff_b200.torchcfm.models.models import MLP
+
+dev = torch.device("cuda:0")
+for B in (256, 64, 512):
+    torch.manual_seed(0)
+    tr = train.FusedFlowTrainer(MLP(dim=2, w=256, time_varying=True).to(dev), batch_size=B)
+    for S in (1, 64, 1024):
+        x0, x1, t, eps = tr.draw(S)
+        tr.steps(x0, x1, t)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            tr.steps(x0, x1, t)
+        e1.record(); torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / (reps * S)
+        e0.record()
+        for _ in range(reps):
+            tr.run(S)
+        e1.record(); torch.cuda.synchronize()
+        us2 = e0.elapsed_time(e1) * 1e3 / (reps * S)
+        print(f"B={B} S={S}: {us:.2f} us/step = {B / us:.2f} M samples/s (pre-drawn); {us2:.2f} us/step incl. draws", flush=True)

@@ -1,0 +1,152 @@
+"""-m gpu: the fused training kernel (idff_train_flow_steps) against the reference's training loop
+(Autograd_example_order2.py:89-112) run by the CPU oracle on the same weights and draws: per-step losses, gradient norms,
+gradients, and the parameters / AdamW moments after a run of steps."""
+import numpy as np
+import pytest
+import torch
+
+import idff_oracle as O
+from idff_b200 import _lib, train
+
+pytestmark = pytest.mark.gpu
+
+LR = 2e-4
+
+
+def _fresh_mlp(device, seed=0):
+    from idff_b200.torchcfm.models.models import MLP
+    torch.manual_seed(seed)
+    return MLP(dim=2, w=256, time_varying=True).to(device)
+
+
+def _layers_of(model, dtype=torch.float32):
+    ps = [p.detach().cpu().to(dtype).clone() for p in model.parameters()]
+    return [(ps[2 * i], ps[2 * i + 1]) for i in range(4)]
+
+
+def _draws(S, B, seed, sigma):
+    g = torch.Generator().manual_seed(seed)
+    x1 = torch.as_tensor(O.checkerboard(S * B), dtype=torch.float32).view(S, B, 2) if hasattr(O, "checkerboard") else None
+    x0 = torch.randn(S, B, 2, generator=g)
+    t = torch.rand(S, B, generator=g)
+    eps = torch.randn(S, B, 2, generator=g) if sigma != 0 else None
+    return x0, x1.contiguous(), t, eps
+
+
+@pytest.mark.parametrize("B,sigma", [(256, 0.0), (64, 0.5), (512, 0.0), (4, 0.0)])
+def test_one_step_gradients_loss_and_update(cuda_device, B, sigma):
+    """One step: unclipped gradients within 1e-5 * max|g| per tensor of autograd's, loss and gradient norm to 2e-6
+    relative, AdamW's first update (~lr * sign(g)) to 1e-3 * lr wherever |g| is above the fp32 noise floor."""
+    np.random.seed(3)
+    dev = cuda_device
+    model = _fresh_mlp(dev, seed=B)
+    layers = _layers_of(model)
+    x0, x1, t, eps = _draws(1, B, 11, sigma)
+    losses_r, norms_r, after_r, grads_r = O.train_steps_2d(layers, x0, x1, t, eps, sigma=sigma, lr=LR, return_grads=True)
+    tr = train.FusedFlowTrainer(model, batch_size=B, sigma=sigma, lr=LR)
+    dump = torch.zeros(tr.n_params, device=dev)
+    before = _lib.launch_count()
+    loss, gnorm = tr.steps(x0.to(dev), x1.to(dev), t.to(dev), eps.to(dev) if eps is not None else None, return_gnorm=True,
+                           grad_dump=dump)
+    assert _lib.launch_count() - before == 1
+    assert loss.item() == pytest.approx(losses_r[0], rel=2e-6)
+    assert gnorm.item() == pytest.approx(norms_r[0], rel=2e-6)
+    shapes = [tuple(p.shape) for p in model.parameters()]
+    for o, sh, gr in zip(tr.offsets[:8], shapes, grads_r):
+        got = dump[o: o + gr.numel()].view(sh).cpu().numpy()
+        ref = gr.numpy()
+        assert np.abs(got - ref).max() <= 1e-5 * max(np.abs(ref).max(), 1e-12), (sh, np.abs(got - ref).max(), np.abs(ref).max())
+    coef = min(1.0, 1.0 / (norms_r[0] + 1e-6))
+    flat_r = torch.cat([torch.cat([W.reshape(-1), b.reshape(-1)]) for W, b in after_r]).numpy()
+    flat_g = torch.cat([g.reshape(-1) for g in grads_r]).numpy() * coef
+    flat_o = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).cpu().numpy()
+    d = np.abs(flat_o - flat_r)
+    solid = np.abs(flat_g) > 1e-6        # m/(sqrt(v)+1e-8) is insensitive to fp32 noise in g there
+    assert d[solid].max() <= 1e-3 * LR, d[solid].max()
+    assert d.max() <= 2 * LR
+
+
+def test_many_steps_track_the_reference(cuda_device):
+    """40 consecutive steps in ONE launch: losses within 1e-4 relative of the reference loop at every step (fp32 noise
+    compounds through AdamW's normalised update), parameters within a few lr; median parameter difference << lr."""
+    np.random.seed(4)
+    dev = cuda_device
+    S, B = 40, 256
+    model = _fresh_mlp(dev, seed=7)
+    layers = _layers_of(model)
+    x0, x1, t, eps = _draws(S, B, 21, 0.0)
+    losses_r, norms_r, after_r = O.train_steps_2d(layers, x0, x1, t, eps, sigma=0.0, lr=LR)
+    tr = train.FusedFlowTrainer(model, batch_size=B, lr=LR)
+    before = _lib.launch_count()
+    loss, gnorm = tr.steps(x0.to(dev), x1.to(dev), t.to(dev), return_gnorm=True)
+    assert _lib.launch_count() - before == 1 and tr.steps_done == S
+    np.testing.assert_allclose(loss.cpu().numpy(), np.array(losses_r, dtype=np.float32), rtol=1e-4)
+    np.testing.assert_allclose(gnorm.cpu().numpy(), np.array(norms_r, dtype=np.float32), rtol=1e-3)
+    flat_r = torch.cat([torch.cat([W.reshape(-1), b.reshape(-1)]) for W, b in after_r]).numpy()
+    flat_o = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).cpu().numpy()
+    d = np.abs(flat_o - flat_r)
+    moved = np.abs(flat_r - torch.cat([torch.cat([W.reshape(-1), b.reshape(-1)]) for W, b in layers]).numpy())
+    print(f"after {S} steps: median|dp| {np.median(d):.2e} p99.9 {np.quantile(d, 0.999):.2e} max {d.max():.2e}; "
+          f"median movement {np.median(moved):.2e}")
+    assert np.median(d) <= 1e-2 * LR and np.quantile(d, 0.999) <= LR and d.max() <= 5 * LR
+    assert np.median(moved) > 10 * np.median(d)
+
+
+def test_split_launches_are_bit_identical_and_deterministic(cuda_device):
+    """20 steps in one launch == 12 + 8 steps in two launches == a second run, bit for bit (fixed reduction orders;
+    steps_done carries the AdamW bias correction across launches)."""
+    np.random.seed(5)
+    dev = cuda_device
+    S, B = 20, 128
+    x0, x1, t, eps = (v.to(dev) if v is not None else None for v in _draws(S, B, 31, 0.5))
+    outs = []
+    for split in ((S,), (12, 8), (S,)):
+        model = _fresh_mlp(dev, seed=9)
+        tr = train.FusedFlowTrainer(model, batch_size=B, sigma=0.5, lr=LR)
+        ls, a = [], 0
+        for n in split:
+            ls.append(tr.steps(x0[a:a + n].contiguous(), x1[a:a + n].contiguous(), t[a:a + n].contiguous(),
+                               eps[a:a + n].contiguous()))
+            a += n
+        outs.append((torch.cat(ls).cpu(), tr.state[: 3 * tr.offsets[10]].cpu().clone()))
+    for l, st in outs[1:]:
+        assert torch.equal(l, outs[0][0]) and torch.equal(st, outs[0][1])
+
+
+def test_model_aliases_state_and_feeds_the_sampler(cuda_device):
+    """The torch module's parameters are views of the kernel state: after training, module forward, state_dict and the
+    sampler's packed weights all see the trained network; the loss goes down on the checkerboard."""
+    from idff_b200 import fields, sampler
+    from idff_b200.weights import PackedWeights
+    dev = cuda_device
+    model = _fresh_mlp(dev, seed=2)
+    w_before = model.net[0].weight.detach().clone()
+    tr = train.FusedFlowTrainer(model, batch_size=256, lr=2e-3)
+    first = tr.run(50).cpu().numpy()
+    tr.run(1500)
+    last = tr.run(50).cpu().numpy()
+    assert np.isfinite(first).all() and np.isfinite(last).all()
+    assert last.mean() < 0.7 * first.mean(), (first.mean(), last.mean())
+    assert not torch.equal(w_before, model.net[0].weight.detach())
+    assert model.net[0].weight.data_ptr() == tr.state.data_ptr() + 4 * (tr.offsets[9] + tr.offsets[0])
+    x = torch.randn(64, 2, device=dev)
+    tt = torch.full((64, 1), 0.3, device=dev)
+    ref = O.mlp_forward(_layers_of(model), torch.cat([x, tt], 1).cpu())
+    np.testing.assert_allclose(model(torch.cat([x, tt], 1)).detach().cpu().numpy(), ref.numpy(), rtol=1e-4, atol=1e-5)
+    pw = PackedWeights.from_module(model, device=dev)
+    f = fields.CustomNetModel(pw, 0.2, 0.2, 0.0)
+    out = sampler.sample_rk4(f, x, torch.linspace(0, 1, 3))
+    assert torch.isfinite(out).all()
+
+
+def test_rejects_unsupported_shapes(cuda_device):
+    dev = cuda_device
+    tr = train.FusedFlowTrainer(_fresh_mlp(dev), batch_size=256)
+    for B in (6, 1024, 2):
+        with pytest.raises(_lib.IdffError):
+            tr.steps(torch.zeros(1, B, 2, device=dev), torch.zeros(1, B, 2, device=dev), torch.zeros(1, B, device=dev))
+    with pytest.raises(_lib.IdffError):
+        tr.steps(torch.zeros(1, 8, 2), torch.zeros(1, 8, 2), torch.zeros(1, 8))          # CPU tensors: no fallback
+    from idff_b200.torchcfm.models.models import MLP
+    with pytest.raises(_lib.IdffError):
+        train.FusedFlowTrainer(MLP(dim=2, w=128, time_varying=True).to(dev))
