@@ -449,6 +449,29 @@ def aux_measurements(dev, pw, model, peaks):
             s_g = timeit(gt.step, reps=200, warm=5)
             tr_out[f"B{Bt}"] = {"eager_samples_per_s": Bt / s_e, "graph_samples_per_s": Bt / s_g,
                                 "eager_us_per_step": s_e * 1e6, "graph_us_per_step": s_g * 1e6}
+        # the fused training kernel (idff_train_flow_steps): the whole step -- path sample, MLP forward, loss, backward, clip,
+        # AdamW -- for 1024 consecutive steps in ONE launch.  "incl_draws" also counts the torch RNG kernels that draw the
+        # 1024 batches (x1 checkerboard, x0, t) on the device; "e2e" adds pinned host inputs -> device and the losses back.
+        for Bt in (256, 512):
+            torch.manual_seed(0)
+            ft = train.FusedFlowTrainer(MLP(dim=2, w=256, time_varying=True).to(dev), batch_size=Bt)
+            S = 1024
+            x0d, x1d, td, _ = ft.draw(S)
+            s_k = timeit(lambda: ft.steps(x0d, x1d, td), reps=5, warm=2) / S
+            s_d = timeit(lambda: ft.run(S), reps=5, warm=2) / S
+            hx0, hx1, ht = (v.cpu().pin_memory() for v in (x0d, x1d, td))
+            hl = torch.empty(S).pin_memory()
+
+            def fused_e2e():
+                hl.copy_(ft.steps(hx0.to(dev, non_blocking=True), hx1.to(dev, non_blocking=True),
+                                  ht.to(dev, non_blocking=True)), non_blocking=True)
+            s_h = timeit(fused_e2e, reps=5, warm=2) / S
+            tr_out[f"B{Bt}"] = dict(tr_out.get(f"B{Bt}", {}), **{
+                "fused_samples_per_s": Bt / s_k, "fused_us_per_step": s_k * 1e6,
+                "fused_incl_draws_samples_per_s": Bt / s_d, "fused_e2e_host_inputs_samples_per_s": Bt / s_h,
+                "fused_steps_per_launch": S,
+                "fused_note": "one persistent cooperative kernel; rows phase streams 1 MB of weights per step per CTA "
+                              "through a TMA ring (per-SM L2 ingest bound), 3 grid barriers per step"})
         # the reference's own step on the CPU (torch CPU, all host threads), B = 256
         torch.manual_seed(0)
         netc = MLP(dim=2, w=256, time_varying=True)

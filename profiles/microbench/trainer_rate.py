@@ -27,3 +27,19 @@ for B in (256, 64, 512):
         e1.record(); torch.cuda.synchronize()
         us2 = e0.elapsed_time(e1) * 1e3 / (reps * S)
         print(f"B={B} S={S}: {us:.2f} us/step = {B / us:.2f} M samples/s (pre-drawn); {us2:.2f} us/step incl. draws", flush=True)
+
+# phase stamps (clock64 per CTA) of the last step of a 64-step launch at B = 256
+import ctypes as C
+import numpy as np
+from idff_b200 import _lib
+torch.manual_seed(0)
+tr = train.FusedFlowTrainer(MLP(dim=2, w=256, time_varying=True).to(dev), batch_size=256)
+x0, x1, t, eps = tr.draw(64)
+tr.steps(x0, x1, t); torch.cuda.synchronize()
+buf = (C.c_int64 * (148 * 8))()
+_lib.check(_lib.lib().idff_debug_train_stamps(buf, 148), "stamps")
+st = np.array(buf[:], dtype=np.int64).reshape(148, 8)
+d = np.diff(st[:, :7], axis=1)
+names = ["rows phase", "barrier 1 wait", "wgrad job", "barrier 2 wait", "adamw", "barrier 3 wait"]
+for lo, hi, what in ((0, 64, "row CTAs (also tiles)"), (64, 128, "tile-only CTAs"), (128, 144, "thin jobs"), (144, 145, "db3/loss"), (145, 148, "idle")):
+    print(what, {n: int(np.median(d[lo:hi, i])) for i, n in enumerate(names)}, "total", int(np.median(st[lo:hi, 6] - st[lo:hi, 0])))
