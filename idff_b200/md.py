@@ -77,12 +77,21 @@ def generate_onestep(model, num_trajectories, data_dim, max_length, nfe, sigma, 
 
 
 def compute_metrics(y_hat, dataset):
-    """CC / RMSE / MAE between the trajectory mean and the data (MD_simulation.py:275-295), on the device."""
-    mean = y_hat.mean(dim=1)
-    data = torch.as_tensor(dataset, dtype=torch.float32, device=y_hat.device)
-    err = mean - data
-    rmse = torch.sqrt((err ** 2).mean())
-    mae = err.abs().mean()
-    a, b = mean.flatten() - mean.mean(), data.flatten() - data.mean()
-    cc = (a * b).sum() / torch.sqrt((a * a).sum() * (b * b).sum())
-    return {"CC": float(cc), "RMSE": float(rmse), "MAE": float(mae)}
+    """TrajectoryGenerator.compute_metrics (MD_simulation.py:275-295) without leaving the device: per (trajectory,
+    dimension) Pearson CC, RMSE and MAE of the generated series against the data over the T frames, then mean and std
+    (ddof = 0) over the K * D series.  y_hat (T, K, D) CUDA tensor, dataset (T, D).  NaN frames are skipped by RMSE / MAE
+    (nanmean) and poison CC, as in the reference.  The old keys CC / RMSE / MAE are the *_mean values."""
+    if not y_hat.is_cuda:
+        raise RuntimeError("compute_metrics needs a CUDA tensor: idff_b200 has no CPU path")
+    y = y_hat.to(torch.float64)
+    d = torch.as_tensor(dataset, device=y_hat.device).to(torch.float64)[:, None, :]
+    err = y - d
+    rmse = torch.sqrt(torch.nanmean(err * err, dim=0))
+    mae = torch.nanmean(err.abs(), dim=0)
+    ya, da = y - y.mean(dim=0, keepdim=True), d - d.mean(dim=0, keepdim=True)
+    cc = (ya * da).sum(0) / torch.sqrt((ya * ya).sum(0) * (da * da).sum(0))
+    stats = torch.stack([cc.mean(), cc.std(unbiased=False), rmse.mean(), rmse.std(unbiased=False), mae.mean(),
+                         mae.std(unbiased=False)]).tolist()          # one device -> host copy
+    out = dict(zip(("CC_mean", "CC_std", "RMSE_mean", "RMSE_std", "MAE_mean", "MAE_std"), stats))
+    out.update(CC=out["CC_mean"], RMSE=out["RMSE_mean"], MAE=out["MAE_mean"])
+    return out

@@ -405,6 +405,21 @@ def md_periodic_loss(vt, x1):
             + torch.mean((vt - (x1 - 360)) ** 2))
 
 
+def md_compute_metrics(y_hat, dataset):
+    """TrajectoryGenerator.compute_metrics (MD_simulation.py:275-295): per (trajectory, dimension) Pearson CC, RMSE and MAE
+    of the generated series against the data over the T frames, then mean / std (ddof = 0) over the K*D series.
+    y_hat (T, K, D), dataset (T, D) numpy."""
+    y_hat, dataset = np.asarray(y_hat), np.asarray(dataset)
+    cc, rmse, mae = [], [], []
+    for ii in range(y_hat.shape[1]):
+        for jj in range(y_hat.shape[2]):
+            cc.append(np.corrcoef(y_hat[:, ii, jj], dataset[:, jj])[0, 1])                  # :282
+            rmse.append(np.sqrt(np.nanmean((y_hat[:, ii, jj] - dataset[:, jj]) ** 2)))      # :284
+            mae.append(np.nanmean(np.abs(y_hat[:, ii, jj] - dataset[:, jj])))               # :286
+    return {"CC_mean": np.mean(cc), "CC_std": np.std(cc), "RMSE_mean": np.mean(rmse), "RMSE_std": np.std(rmse),
+            "MAE_mean": np.mean(mae), "MAE_std": np.std(mae)}
+
+
 # --------------------------------------------------------------------------------------
 # a13 : RBF-kernel MMD
 # --------------------------------------------------------------------------------------

@@ -242,9 +242,27 @@ def main():
     mm["mmd_md_unit_f64"] = O.mmd_rbf_fp64_direct(a2, b2, sigma=3.0)
     np.savez(os.path.join(OUT, "mmd.npz"), **mm)
 
+    golden_metrics()
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"wrote {len(os.listdir(OUT))} files, {tot / 1e6:.2f} MB -> {OUT}")
 
 
+def golden_metrics():
+    """TrajectoryGenerator.compute_metrics (MD_simulation.py:275-295) executed on a seeded PolyALA-shaped case."""
+    import types
+    fn = R.script_method(R.MD, "TrajectoryGenerator", "compute_metrics")
+    g = torch.Generator().manual_seed(7)
+    T, K, D = 200, 5, 46
+    data = 180 * torch.sin(torch.cumsum(torch.randn(T, D, generator=g) * 0.05, 0) + torch.rand(D, generator=g) * 6.28)
+    y_hat = data[:, None, :] + 10 * torch.randn(T, K, D, generator=g)
+    res = fn(types.SimpleNamespace(dataset=data), y_hat.numpy())
+    out = {"dataset": data.numpy(), "y_hat": y_hat.numpy()}
+    out.update({k: np.float64(v) for k, v in res.items()})
+    np.savez(os.path.join(OUT, "metrics.npz"), **out)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "metrics":
+        golden_metrics()
+    else:
+        main()

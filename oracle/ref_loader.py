@@ -95,6 +95,24 @@ def script_symbols(relpath: str, names, extra_ns=None):
     return {n: ns[n] for n in names}
 
 
+def script_method(relpath: str, class_name: str, method_name: str, extra_ns=None):
+    """Compile + exec ONE method of a class defined in a reference script as a plain function (first argument `self`):
+    for classes whose constructor cannot run here (TrajectoryGenerator loads an unshipped dataset)."""
+    path = os.path.join(REF_ROOT, relpath)
+    with open(path, "r") as fh:
+        tree = ast.parse(fh.read(), filename=path)
+    ns = {"torch": torch, "np": np, "math": math, "__name__": "idff_ref_slice"}
+    if extra_ns:
+        ns.update(extra_ns)
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == class_name:
+            for sub in node.body:
+                if isinstance(sub, ast.FunctionDef) and sub.name == method_name:
+                    exec(compile(ast.Module(body=[sub], type_ignores=[]), path, "exec"), ns)
+                    return ns[method_name]
+    raise KeyError(f"{relpath}: {class_name}.{method_name} not found")
+
+
 ORDER2 = "2D_examples/Autograd_example_order2.py"
 ORDER3 = "2D_examples/Autograd_example_order3.py"
 ORDER1 = "2D_examples/example_order1_with_prediction_head.py"

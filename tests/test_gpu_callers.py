@@ -163,3 +163,22 @@ def test_md_generation_as_cuda_graph(cuda_device):
     torch.cuda.synchronize()
     t2 = time.perf_counter()
     print(f"PolyALA chain, {T} frames x {K} trajectories: graph {1e3 * (t1 - t0) / 5:.2f} ms, eager {1e3 * (t2 - t1) / 5:.2f} ms")
+
+
+def test_md_compute_metrics_matches_reference_golden(cuda_device):
+    """compute_metrics (MD_simulation.py:275-295) on the device against the values the reference's own method produced:
+    CC in fp64 (np.corrcoef promotes), RMSE / MAE within fp32 rounding of the reference's fp32 nanmean."""
+    from conftest import load_golden
+    from idff_b200 import md
+    g = load_golden("metrics")
+    m = md.compute_metrics(torch.tensor(g["y_hat"]).to(cuda_device), torch.tensor(g["dataset"]))
+    for k in ("CC_mean", "CC_std"):
+        assert m[k] == pytest.approx(float(g[k]), rel=1e-6), k
+    for k in ("RMSE_mean", "RMSE_std", "MAE_mean", "MAE_std"):
+        assert m[k] == pytest.approx(float(g[k]), rel=1e-5), k
+    y = torch.tensor(g["y_hat"]).to(cuda_device)
+    y[3, 1, 2] = float("nan")
+    m2 = md.compute_metrics(y, torch.tensor(g["dataset"]))
+    assert np.isnan(m2["CC_mean"]) and np.isfinite(m2["RMSE_mean"]) and np.isfinite(m2["MAE_mean"])
+    with pytest.raises(RuntimeError):
+        md.compute_metrics(torch.tensor(g["y_hat"]), torch.tensor(g["dataset"]))

@@ -138,3 +138,12 @@ def test_jet_formulation_equals_nested_autograd():
             out = torch.sqrt(1 - sum(gam) * st2) * (pred - x) / (1 - t) + gsum
             ref = f(t, x)
             assert (out - ref).abs().max().item() < 1e-11 * max(1.0, ref.abs().max().item())
+
+
+def test_md_metrics_match_golden():
+    """TrajectoryGenerator.compute_metrics (MD_simulation.py:275-295): the oracle restatement equals the values the
+    reference's own method produced (tests/golden/metrics.npz, written by oracle/make_golden.py metrics)."""
+    g = load_golden("metrics")
+    r = O.md_compute_metrics(g["y_hat"], g["dataset"])
+    for k in ("CC_mean", "CC_std", "RMSE_mean", "RMSE_std", "MAE_mean", "MAE_std"):
+        assert float(r[k]) == float(g[k]), k

@@ -60,3 +60,16 @@ def test_mmd_bit_exact():
     f = R.script_symbols(R.ORDER2, ["compute_mmd_rbf"])["compute_mmd_rbf"]
     a, b = torch.randn(500, 2), torch.randn(700, 2) + 0.5
     assert f(a, b, sigma=1.0) == pytest.approx(O.mmd_rbf(a, b, 1.0), rel=1e-6)
+
+
+def test_md_metrics_equal_reference_method():
+    import types
+    fn = R.script_method(R.MD, "TrajectoryGenerator", "compute_metrics")
+    g = torch.Generator().manual_seed(3)
+    data = 100 * torch.randn(50, 7, generator=g)
+    y = data[:, None, :] + 5 * torch.randn(50, 3, 7, generator=g)
+    ref = fn(types.SimpleNamespace(dataset=data), y.numpy())
+    got = O.md_compute_metrics(y.numpy(), data.numpy())
+    assert set(ref) == set(got)
+    for k in ref:
+        assert float(ref[k]) == float(got[k]), k
