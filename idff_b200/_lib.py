@@ -63,6 +63,7 @@ SIGNATURES = {
     "idff_train_flow_offsets": (C.c_int, [_vp]),
     "idff_train_flow_init": (C.c_int, [_vp, _vp]),
     "idff_debug_train_stamps": (C.c_int, [_vp, _i32]),
+    "idff_debug_train_pair_mode": (C.c_int, [_i32]),
     "idff_train_flow_steps": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _i32, C.POINTER(AdamW), _i64, _vp, _vp,
                                         _vp, _vp]),
 }

@@ -47,6 +47,9 @@ int tensor16_nonfinite(unsigned long long* h_out);
 
 // idff_sampler_wide.cu
 bool wide_supports(const idff_weights_t* w, const idff_field_params_t* p);
+bool wide_sweep_supports(const idff_weights_t* w, const idff_field_params_t* params, int n_sets, int64_t N);
+int wide_sample_rk4_sweep(const idff_weights_t* w, const idff_field_params_t* params, int n_sets, const float* d_x0,
+                          const Stage* stages, const float* dts, int n_iv, float* d_out, int64_t N, void* stream);
 int wide_field_eval(const idff_weights_t* w, const idff_field_params_t* p, float t, const float* d_x, const float* d_x0,
                     float* d_out, int64_t N, void* stream);
 int wide_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, const float* d_x0, const Stage* stages,
@@ -145,6 +148,19 @@ extern "C" int idff_field_eval(const idff_weights_t* w, const idff_field_params_
   return generic_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
 }
 
+// Would idff_sample_rk4 hand (p, N) to the layered tcgen05 engine?  (mirrors its dispatch; *q = p with the impl that engine expects)
+static bool routes_to_wide(const idff_weights_t* w, const idff_field_params_t* p, int64_t N, idff_field_params_t* q) {
+  *q = *p;
+  if (p->impl == IDFF_IMPL_LAYERED) return wide_supports(w, p);
+  if (p->impl == IDFF_IMPL_TENSOR16 || (p->impl == IDFF_IMPL_AUTO && tensor16_supports(w, p))) return false;
+  if (p->impl == IDFF_IMPL_AUTO && w->v.w == 256 && N >= 2048) {
+    q->impl = IDFF_IMPL_LAYERED;
+    if (wide_supports(w, q)) return true;
+    q->impl = p->impl;
+  }
+  return (p->impl == IDFF_IMPL_TENSOR || p->impl == IDFF_IMPL_AUTO) && wide_supports(w, p) && (p->impl == IDFF_IMPL_TENSOR || N >= 2048);
+}
+
 extern "C" int idff_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, const float* d_x0,
                                const float* h_t_grid, int32_t n_grid, float* d_out_final, float* d_out_traj, int64_t N,
                                void* stream) {
@@ -229,7 +245,15 @@ extern "C" int idff_sample_rk4_sweep(const idff_weights_t* w, const idff_field_p
   for (int g = 0; g < n_sets && batched; ++g)
     batched = (params[g].impl == IDFF_IMPL_AUTO || params[g].impl == IDFF_IMPL_TENSOR16) && tensor16_supports(w, &params[g]) &&
               params[g].variant == params[0].variant && params[g].t_idx == params[0].t_idx;
-  if (!batched) {
+  // order 3 / wide networks: one batch on the layered engine when that engine would serve every set anyway
+  std::vector<idff_field_params_t> wp;
+  bool wide_batched = !batched && n_iv >= 1 && N % 128 == 0 && n_sets >= 2;
+  if (wide_batched) {
+    wp.resize(n_sets);
+    for (int g = 0; g < n_sets && wide_batched; ++g) wide_batched = routes_to_wide(w, &params[g], N, &wp[g]);
+    wide_batched = wide_batched && wide_sweep_supports(w, wp.data(), n_sets, N);
+  }
+  if (!batched && !wide_batched) {
     for (int g = 0; g < n_sets; ++g) {
       int rc = idff_sample_rk4(w, &params[g], d_x0, h_t_grid, n_grid, d_out + (size_t)g * set_floats, nullptr, N, stream);
       if (rc) return rc;
@@ -254,6 +278,7 @@ extern "C" int idff_sample_rk4_sweep(const idff_weights_t* w, const idff_field_p
       make_stage(params[g], t1, &s4[3]);
     }
   }
+  if (wide_batched) return wide_sample_rk4_sweep(w, wp.data(), n_sets, d_x0, st.data(), dts.data(), n_iv, d_out, N, stream);
   return tensor16_sample_rk4_sweep(w, params, n_sets, d_x0, st.data(), dts.data(), n_iv, d_out, N, stream);
 }
 

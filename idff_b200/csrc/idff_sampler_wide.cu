@@ -23,6 +23,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "idff_common.cuh"
 
@@ -158,6 +159,10 @@ struct WParams {
   float* stash;                // [ctile][MT][NPART][NJ*HP][128]
   float* part;                 // [ctile][MT][4 lane quarters][NPART][2*HP]   partial sums of a small layer
   const float* xs;             // [P][2] stage input (layer-1 recompute in the last reverse pass)
+  // gamma sweeps: particle row r of the whole batch belongs to parameter set r / set_rows (set_rows is a multiple of every
+  // column-tile size, so a column tile never straddles two sets); coef [n_sets][4] = {c1, c2, c3, a} of this evaluation
+  const float* coef;
+  long set_rows, row0;
 };
 
 template <int NV>
@@ -393,7 +398,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_wide_layer(const __grid_constan
         // layer 3 forward: x1hat partial sums, adjoint seeds of c1*phi + c2*D_d phi + c3*D_d^2 phi
         const float bb = __ldg(P.net.b2 + n), u = __ldg(P.net.u3 + n);
         const float w30 = __ldg(P.net.w3 + n), w31 = __ldg(P.net.w3 + w + n);
-        const float A0 = P.st.c[0] * u, A1 = P.st.c[1] * u, A2 = P.st.c[2] * u;
+        float c0 = P.st.c[0], c1 = P.st.c[1], c2 = P.st.c[2];
+        if (P.coef) {
+          const float4 cf = __ldg(reinterpret_cast<const float4*>(P.coef) + (P.row0 + (long)ct * PPT) / P.set_rows);
+          c0 = cf.x; c1 = cf.y; c2 = cf.z;
+        }
+        const float A0 = c0 * u, A1 = c1 * u, A2 = c2 * u;
         float pv[2 * HP];
 #pragma unroll
         for (int i = 0; i < HP; ++i) {
@@ -491,6 +501,8 @@ struct UParams {
   const float *pred, *grad, *b3;
   float *y, *k1, *k2, *k3, *xs, *x0c;
   float *out, *traj_row;   // global outputs (already offset to this chunk)
+  const float* coef;       // gamma sweeps: [n_sets][4] = {c1, c2, c3, a} of this evaluation, set = (row0 + row) / set_rows
+  long set_rows;
 };
 __global__ void k_wide_update(const __grid_constant__ UParams U) {
   const float third = (float)(1.0 / 3.0);
@@ -506,7 +518,8 @@ __global__ void k_wide_update(const __grid_constant__ UParams U) {
       if (U.st.kind == 0) f = diff;
       else if (U.st.kind == 1) f = __fdiv_rn(diff, U.st.end_div);
       else {
-        f = __fdiv_rn(__fmul_rn(U.st.a, diff), U.st.den);
+        const float a = U.coef ? __ldg(U.coef + 4 * ((U.row0 + (o >> 1)) / U.set_rows) + 3) : U.st.a;
+        f = __fdiv_rn(__fmul_rn(a, diff), U.st.den);
         if (U.heavy) f = __fadd_rn(f, U.grad[o]);
       }
     }
@@ -552,7 +565,8 @@ struct WideScratch {
 };
 
 static int wide_run(const idff_weights_t* w, const idff_field_params_t* p, int mode, const float* d_x, const float* d_x0,
-                    const Stage* stages, const float* dts, int n_eval, float* d_out, float* d_traj, int64_t N, void* stream) {
+                    const Stage* stages, const float* dts, int n_eval, float* d_out, float* d_traj, int64_t N, void* stream,
+                    const float* d_coef = nullptr, int n_sets = 1, long set_rows = 0) {
   using namespace wide;
   if (!wide_supports(w, p)) {
     set_error("wide tensor-core sampler: needs a 3-w-w-w-2 network with w in {256..2048} (multiple of 128), dim 2");
@@ -622,6 +636,7 @@ static int wide_run(const idff_weights_t* w, const idff_field_params_t* p, int m
       memset(&P, 0, sizeof(P));
       P.net = v; P.w = W; P.MT = MT; P.KB = KB; P.nj = njk; P.ppt = PPTk; P.n_ctiles = (int)nctk; P.P = Pn; P.heavy = heavy;
       P.st = st; P.stash = sc.stash; P.part = sc.part; P.xs = sc.xs;
+      P.coef = d_coef ? d_coef + (size_t)e * n_sets * 4 : nullptr; P.set_rows = set_rows; P.row0 = row0;
       const int ew_grid = (int)std::min<long>((nctk * W + 255) / 256, (long)sms * 8);
       P.xout = sc.xa;
       if (njk == 1) k_wide_l1<1><<<ew_grid, 256, 0, s>>>(P);
@@ -652,6 +667,7 @@ static int wide_run(const idff_weights_t* w, const idff_field_params_t* p, int m
       U.P = Pn; U.N_total = N; U.row0 = row0; U.variant = p->variant; U.mode = mode; U.sg = e & 3; U.heavy = heavy;
       U.last = (e == n_eval - 1); U.dt = mode == 1 ? dts[e >> 2] : 0.0f; U.st = st;
       U.pred = sc.pred; U.grad = sc.grad; U.b3 = v.b3;
+      U.coef = P.coef; U.set_rows = set_rows;
       U.y = sc.y; U.k1 = sc.k1; U.k2 = sc.k2; U.k3 = sc.k3; U.xs = sc.xs; U.x0c = sc.x0c;
       U.out = d_out + row0 * 2;
       U.traj_row = (mode == 1 && d_traj && (e & 3) == 3) ? d_traj + ((size_t)((e >> 2) + 1) * N + row0) * 2 : nullptr;
@@ -673,6 +689,61 @@ int wide_field_eval(const idff_weights_t* w, const idff_field_params_t* p, float
 int wide_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, const float* d_x0, const Stage* stages,
                     const float* dts, int n_iv, float* d_out_final, float* d_out_traj, int64_t N, void* stream) {
   return wide_run(w, p, 1, d_x0, nullptr, stages, dts, 4 * n_iv, d_out_final, d_out_traj, N, stream);
+}
+
+// idff_sample_rk4_sweep on the layered engine: n_sets parameter sets (same variant, same jets_needed, same t grid, sigma
+// and end_div -- only the folded gamma coefficients and a = sqrt(1 - Gamma sigma_t^2) differ) over the same x0, solved as ONE
+// batch of n_sets * N particles: d_out [n_sets][N][2] first receives n_sets copies of x0 and is then integrated in place, the
+// kernels look the per-set coefficients up by particle row.  N must be a multiple of 128 (the largest column tile), so that
+// a column tile never straddles two sets.  Per particle the arithmetic is that of wide_sample_rk4 with the set's parameters.
+__global__ void k_wide_replicate(const float2* __restrict__ x0, float2* __restrict__ out, long N, long total) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) out[i] = x0[i % N];
+}
+
+bool wide_sweep_supports(const idff_weights_t* w, const idff_field_params_t* params, int n_sets, int64_t N) {
+  if (N % 128 != 0 || n_sets < 2) return false;
+  int nj0, rev0;
+  jets_needed(params[0], &nj0, &rev0);
+  for (int g = 0; g < n_sets; ++g) {
+    const idff_field_params_t& q = params[g];
+    int nj, rev;
+    jets_needed(q, &nj, &rev);
+    if (!wide_supports(w, &q) || q.variant != IDFF_FIELD_MOMENTUM || q.variant != params[0].variant || nj != nj0 || rev != rev0 ||
+        q.sigma != params[0].sigma || q.end_div != params[0].end_div || q.order != params[0].order)
+      return false;
+  }
+  return true;
+}
+
+int wide_sample_rk4_sweep(const idff_weights_t* w, const idff_field_params_t* params, int n_sets, const float* d_x0,
+                          const Stage* stages /*[n_sets][4 n_iv]*/, const float* dts, int n_iv, float* d_out, int64_t N,
+                          void* stream) {
+  const int n_eval = 4 * n_iv;
+  std::vector<float> coef((size_t)n_eval * n_sets * 4);
+  for (int e = 0; e < n_eval; ++e)
+    for (int g = 0; g < n_sets; ++g) {
+      const Stage& st = stages[(size_t)g * n_eval + e];
+      float* c = &coef[((size_t)e * n_sets + g) * 4];
+      c[0] = st.c[0]; c[1] = st.c[1]; c[2] = st.c[2]; c[3] = st.a;
+    }
+  idff_weights_t* wm = const_cast<idff_weights_t*>(w);
+  const size_t bytes = coef.size() * sizeof(float);
+  if (wm->sweep_bytes < bytes) {
+    if (wm->d_sweep) cudaFree(wm->d_sweep);
+    wm->d_sweep = nullptr;
+    wm->sweep_bytes = 0;
+    IDFF_CUDA(cudaMalloc(&wm->d_sweep, bytes));
+    wm->sweep_bytes = bytes;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  IDFF_CUDA(cudaMemcpyAsync(wm->d_sweep, coef.data(), bytes, cudaMemcpyHostToDevice, s));
+  IDFF_CUDA(cudaStreamSynchronize(s));   // `coef` is pageable host memory that dies with this call
+  const long total = (long)n_sets * N;
+  k_wide_replicate<<<(int)std::min<long>((total + 255) / 256, 148 * 8), 256, 0, s>>>(
+      reinterpret_cast<const float2*>(d_x0), reinterpret_cast<float2*>(d_out), (long)N, total);
+  count_launch();
+  return wide_run(w, &params[0], 1, d_out, nullptr, stages, dts, n_eval, d_out, nullptr, total, stream,
+                  reinterpret_cast<const float*>(wm->d_sweep), n_sets, (long)N);
 }
 
 }  // namespace idff

@@ -9,20 +9,24 @@
 // At the reference's batch (256) this is 0.2 GFLOP: launch- and latency-bound on any GPU (60 torch kernels, 290 us even as
 // a CUDA graph).  Here `n_steps` consecutive steps run inside one launch; a step is three phases separated by a grid
 // barrier (monotonic counter, one red.release per CTA; the launch is cooperative so all CTAs are co-resident):
-//   A  rows:    B/4 CTAs own 4 batch rows each and run path sample -> forward -> loss -> backward-data for their rows
-//               with no cross-CTA traffic.  The four 256x256 weight matrices of the step (W1^T, W2^T, W2, W1: 1 MB, L2
-//               resident) stream through a 4 x 32 KB shared-memory ring filled by a producer warp with TMA bulk copies
-//               (cp.async.bulk + mbarrier complete_tx), running ahead across layer boundaries; a consumer thread owns
-//               4 units x 4 rows over one eighth of K (128-bit conflict-free weight reads, broadcast activation reads),
-//               the 8 K-slices are summed in a fixed order.  Activations and the pre-activation gradients dZ go to global
-//               memory (L2-resident, 1.5 MB).  The producer warp also prefetches the next step's input rows.
+//   A  rows:    B/4 CTAs own 4 batch rows each: path sample -> forward -> loss -> backward-data for those rows, no cross-CTA
+//               traffic.  The four 256x256 weight matrices of the step (W1^T, W2^T, W2, W1: 1 MB, L2 resident) stream
+//               through a 4 x 32 KB shared-memory ring filled by a producer warp with TMA bulk copies (cp.async.bulk +
+//               mbarrier complete_tx), running ahead across layer boundaries.  A consumer thread owns 4 units x 4 rows over
+//               one K-slice (128-bit conflict-free weight reads, broadcast activation reads); slices are summed in a fixed
+//               order.  Activations and the pre-activation gradients dZ go to global memory (L2-resident, 1.5 MB).  The
+//               producer warp also prefetches the next step's input rows.  (An opt-in variant runs a row group on a CTA
+//               PAIR -- cluster of 2, each CTA streaming / computing half of the units, activation halves exchanged
+//               through distributed shared memory with a cluster-scope mbarrier per layer: measured slower, kept as a
+//               diagnostic)
 //   B  weights: 145 jobs, one per CTA: 2 x 64 tiles (32 x 32) of dW1 / dW2 = dZ^T A (K = batch, operands staged in shared
 //               memory, 4 x 4 outputs per thread over one eighth of K), 8 + 8 jobs for the thin layers, one for db3 and the
 //               loss value.  A gradient never leaves the CTA that owns its parameter; only the CTA's sum of squares goes
 //               to global memory.  The owner's P / exp_avg / exp_avg_sq loads are issued before the barrier.
 //   C  update:  every CTA adds the partial sums of squares in the same fixed order (-> identical clip coefficient), then
-//               each thread applies clip + AdamW (torch's op order) to the parameters it owns; the transposed forward
-//               copies of W1 / W2 are refreshed through a shared-memory transpose (coalesced stores).
+//               each thread applies clip + AdamW (torch's op order) to the parameters it owns; the streaming copies of
+//               W1 / W2 (forward = transposed, backward = as stored, each split into output-unit halves) are refreshed,
+//               the transposed ones through a shared-memory transpose (coalesced stores).
 // Every reduction has a fixed order: results are bit-reproducible run to run.
 #include <cmath>
 
@@ -31,29 +35,32 @@
 namespace idff {
 namespace trn {
 
-constexpr int W = 256, DIN = 3, DOUT = 2, R = 4, NC = 512, NT = NC + 32, MAXB = IDFF_TRAIN_MAX_BATCH;
+constexpr int W = 256, DIN = 3, DOUT = 2, RMIN = 4, RMAX = 4, NC = 512, NT = NC + 32, MAXB = IDFF_TRAIN_MAX_BATCH;
 constexpr int oW0 = 0, ob0 = oW0 + W * DIN, oW1 = ob0 + W, ob1 = oW1 + W * W, oW2 = ob1 + W, ob2 = oW2 + W * W,
               oW3 = ob2 + W, ob3 = oW3 + DOUT * W, NP = ob3 + DOUT;
 constexpr int NPP = (NP + 63) / 64 * 64;
 constexpr int JOB_W0 = 128, JOB_W3 = 136, JOB_B3 = 144, N_JOBS = 145;
 constexpr int MAX_GRID = 256;
-constexpr int NS = 4, CH_ROWS = 32, CH_FLOATS = CH_ROWS * W, CH_BYTES = CH_FLOATS * 4, CH_PER_PASS = W / CH_ROWS,
-              CH_PER_STEP = 4 * CH_PER_PASS;
-static_assert(CH_PER_STEP % NS == 0, "ring phase bookkeeping");
+constexpr int NSMAX = 8, CH_ROWS = 32, CH_FLOATS = CH_ROWS * W, CH_PER_PASS = W / CH_ROWS, CH_PER_STEP = 4 * CH_PER_PASS;
+constexpr int HALF = W * 128;          // floats of one output-unit half of a streaming copy: [256 reduce rows][128 units]
+constexpr int HCH = CH_ROWS * 128;     // floats of one half-chunk (32 rows x 128 units = 16 KB)
+static_assert(CH_PER_STEP % NSMAX == 0, "ring phase bookkeeping");
 
 // clock64 phase stamps of the last step of the last launch, per CTA: diagnostic only (idff_debug_train_stamps)
 __device__ long long g_train_stamps[256][8];
 
 // offsets (floats) into the caller-owned state buffer
-constexpr size_t sP = 0, sM = sP + NPP, sV = sM + NPP, sWT1 = sV + NPP, sWT2 = sWT1 + W * W, sIN = sWT2 + W * W,
+// streaming copies [2 halves][256][128]: F_l[h][k][jj] = W_l[128 h + jj][k] (forward), B_l[h][j][kk] = W_l[j][128 h + kk] (backward)
+constexpr size_t sP = 0, sM = sP + NPP, sV = sM + NPP, sF1 = sV + NPP, sF2 = sF1 + W * W, sB1 = sF2 + W * W, sB2 = sB1 + W * W,
+                 sIN = sB2 + W * W,
                  sA1 = sIN + (size_t)MAXB * 4, sA2 = sA1 + (size_t)MAXB * W, sA3 = sA2 + (size_t)MAXB * W,
                  sZ1 = sA3 + (size_t)MAXB * W, sZ2 = sZ1 + (size_t)MAXB * W, sZ3 = sZ2 + (size_t)MAXB * W,
                  sDO = sZ3 + (size_t)MAXB * W, sLP = sDO + (size_t)MAXB * DOUT, sNP = sLP + MAX_GRID, sBAR = sNP + MAX_GRID,
                  sTOTAL = sBAR + 64;
 
 // dynamic shared memory (floats).  Phase A: ring | act | part | raw | in4 | dout | lterm.  Phases B / C alias it.
-constexpr int mRING = 0, mACT = mRING + NS * CH_FLOATS, mPART = mACT + R * W, mRAW = mPART + 8 * R * W, mIN4 = mRAW + 2 * R * 8,
-              mDOUT = mIN4 + R * 4, mLT = mDOUT + R * DOUT, mTOTAL = mLT + 8;
+constexpr int mRING = 0, mACT = mRING + 4 * CH_FLOATS, mPART = mACT + 2 * RMAX * W, mRAW = mPART + 2048 * RMAX,
+              mIN4 = mRAW + 2 * RMAX * 8, mDOUT = mIN4 + RMAX * 4, mLT = mDOUT + RMAX * DOUT, mTOTAL = mLT + RMAX * DOUT;
 constexpr int mDZS = 0, mAS = mDZS + 256 * 32, mRED = mAS + 256 * 32, mREDB = mRED + 8 * 16 * 64, mPT = mREDB + 16 * 32,
               mBTOTAL = mPT + 32 * 33;
 static_assert(mBTOTAL <= mRAW, "phase B scratch must not overlap the input prefetch buffer");
@@ -100,6 +107,37 @@ __device__ __forceinline__ void fence_async_global() { asm volatile("fence.proxy
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }      // the 16 consumer warps
 __device__ __forceinline__ void fullsync() { asm volatile("bar.sync 0, 544;" ::: "memory"); }   // + the producer warp
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared::cta pointer of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(s32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n.reg .pred P1;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}\n"
+        : "=r"(ok)
+        : "r"(s32(b)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
 __device__ __forceinline__ float sigma_t_of(float t, float sigma, int mode) {
   if (mode == 0) return sigma;
   return __fmul_rn(sigma, __fsqrt_rn(__fmul_rn(t, __fsub_rn(1.0f, t))));   // conditional_flow_matching.py:231-233
@@ -122,52 +160,82 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& epoch, boo
 
 __device__ __forceinline__ float selu_d1(float code) { return code < 0.0f ? kSeluLambda : code; }
 
-// One 256 x 256 layer pass over the ring: thread (ks, u4) accumulates units 4 u4 .. 4 u4 + 3 of the CTA's 4 rows over the
-// k rows {32 c + 4 ks + i} of every chunk c, then the 8 K-slices meet in `part`.
+// Per-CTA geometry of the rows phase.  CL = 1: the CTA computes all 256 units of its R rows; CL = 2: 128 of them.
+template <int CL, int R>
+struct Geo {
+  static constexpr int UPC = W / CL;          // output units per CTA
+  static constexpr int NU4 = UPC / 4;         // threads across units (4 units each)
+  static constexpr int KSL = NC / NU4;        // K-slices: 8 / 16
+  static constexpr int RPS = CH_ROWS / KSL;   // k rows of a chunk per slice: 4 / 2
+  static constexpr int NQ = R * UPC / NC;     // outputs (row, unit) finalised per thread
+  static constexpr int CHF = CH_FLOATS / CL;  // floats of one ring chunk
+  static constexpr int NS = 4 * CL;           // ring stages (128 KB either way)
+};
+
+// One 256 x 256 layer pass over the ring: thread (ks, u4) accumulates units 4 u4 .. 4 u4 + 3 (of this CTA's units) of the 4 rows
+// over the k rows {32 c + RPS ks + i} of every chunk c, then the K-slices meet in `part` [KSL][R][UPC].
+template <int CL, int R>
 __device__ __forceinline__ void gemm_ring(const float* ring, const float* act, float* part, uint64_t* full, uint64_t* empty,
                                           uint32_t& cc, int ks, int u4, int lane) {
+  using G = Geo<CL, R>;
   float acc[R][4];
 #pragma unroll
   for (int r = 0; r < R; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
+  const int woff = (u4 >> 5) * HCH + (G::RPS * ks) * 128 + 4 * (u4 & 31);   // [half][32 rows][128 units] within a chunk
 #pragma unroll 1
   for (int c = 0; c < CH_PER_PASS; ++c) {
-    const uint32_t stage = cc % NS;
-    mbar_wait(&full[stage], (cc / NS) & 1);
-    const float* wb = ring + stage * CH_FLOATS + (4 * ks) * W + 4 * u4;
-    float4 av[R];
+    const uint32_t stage = cc % G::NS;
+#ifndef IDFF_TRN_NOTMA   // (diagnostic builds: -DIDFF_TRN_NOTMA = compute on whatever is in the ring, -DIDFF_TRN_NOFMA = stream only)
+    mbar_wait(&full[stage], (cc / G::NS) & 1);
+#endif
+    const float* wb = ring + stage * G::CHF + woff;
+#ifndef IDFF_TRN_NOFMA
+    float av[R][G::RPS];
 #pragma unroll
-    for (int r = 0; r < R; ++r) av[r] = *reinterpret_cast<const float4*>(act + r * W + c * CH_ROWS + 4 * ks);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 w = *reinterpret_cast<const float4*>(wb + i * W);
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const float x = i == 0 ? av[r].x : i == 1 ? av[r].y : i == 2 ? av[r].z : av[r].w;
-        acc[r][0] = fmaf(x, w.x, acc[r][0]);
-        acc[r][1] = fmaf(x, w.y, acc[r][1]);
-        acc[r][2] = fmaf(x, w.z, acc[r][2]);
-        acc[r][3] = fmaf(x, w.w, acc[r][3]);
+    for (int r = 0; r < R; ++r) {
+      if (G::RPS == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(act + r * W + c * CH_ROWS + 4 * ks);
+        av[r][0] = v.x; av[r][1] = v.y; av[r][G::RPS - 2] = v.z; av[r][G::RPS - 1] = v.w;
+      } else {
+        const float2 v = *reinterpret_cast<const float2*>(act + r * W + c * CH_ROWS + 2 * ks);
+        av[r][0] = v.x; av[r][1] = v.y;
       }
     }
+#pragma unroll
+    for (int i = 0; i < G::RPS; ++i) {
+      const float4 w = *reinterpret_cast<const float4*>(wb + i * 128);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        acc[r][0] = fmaf(av[r][i], w.x, acc[r][0]);
+        acc[r][1] = fmaf(av[r][i], w.y, acc[r][1]);
+        acc[r][2] = fmaf(av[r][i], w.z, acc[r][2]);
+        acc[r][3] = fmaf(av[r][i], w.w, acc[r][3]);
+      }
+    }
+#endif
     __syncwarp();
+#ifndef IDFF_TRN_NOTMA
     if (lane == 0) mbar_arrive(&empty[stage]);
+#endif
     ++cc;
   }
 #pragma unroll
   for (int r = 0; r < R; ++r)
-    *reinterpret_cast<float4*>(part + (ks * R + r) * W + 4 * u4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    *reinterpret_cast<float4*>(part + (ks * R + r) * G::UPC + 4 * u4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
 }
 
-__device__ __forceinline__ float part_sum(const float* part, int r, int j) {
-  float z = part[r * W + j];
+template <int CL, int R>
+__device__ __forceinline__ float part_sum(const float* part, int r, int jl) {
+  using G = Geo<CL, R>;
+  float z = part[r * G::UPC + jl];
 #pragma unroll
-  for (int k = 1; k < 8; ++k) z += part[(k * R + r) * W + j];
+  for (int k = 1; k < G::KSL; ++k) z += part[(k * R + r) * G::UPC + jl];
   return z;
 }
 
 // raw input rows of one step -> shared memory: {x0[0], x0[1], x1[0], x1[1], eps[0], eps[1], t, 0}
-__device__ __forceinline__ void load_raw(const Args& a, int s, int row_in_cta, int cta, float* raw) {
-  const size_t row = (size_t)s * a.B + cta * R + row_in_cta;
+__device__ __forceinline__ void load_raw(const Args& a, int s, int row_in_cta, int row0, int R, float* raw) {
+  const size_t row = (size_t)s * a.B + row0 + row_in_cta;
   const float2 x0 = *reinterpret_cast<const float2*>(a.x0 + row * 2), x1 = *reinterpret_cast<const float2*>(a.x1 + row * 2);
   const float2 e = a.eps ? *reinterpret_cast<const float2*>(a.eps + row * 2) : make_float2(0.f, 0.f);
   float* o = raw + ((s & 1) * R + row_in_cta) * 8;
@@ -175,24 +243,52 @@ __device__ __forceinline__ void load_raw(const Args& a, int s, int row_in_cta, i
   *reinterpret_cast<float4*>(o + 4) = make_float4(e.x, e.y, a.t[row], 0.f);
 }
 
-// ---- phase A (consumer warps): path sample, forward, loss, backward-data for rows [4 cta, 4 cta + 4) ----------------------
-__device__ void phase_rows(const Args& a, int s, float* smem, int cta, uint64_t* full, uint64_t* empty, uint32_t& cc) {
+// ---- phase A (consumer warps): path sample, forward, loss, backward-data for the 4 rows of this CTA (pair) ------------------
+template <int CL, int R>
+__device__ void phase_rows(const Args& a, int s, float* smem, int grp, uint32_t rank, uint64_t* full, uint64_t* empty,
+                           uint64_t* actbar, uint32_t& aph, uint32_t& cc) {
+  using G = Geo<CL, R>;
   const float* ring = smem + mRING;
-  float* act = smem + mACT;       // [R][W]
-  float* part = smem + mPART;     // [8][R][W]
+  float* actb = smem + mACT;      // [2][R][W]: layer n reads buffer n & 1 and writes the other one
+  float* part = smem + mPART;     // [KSL][R][UPC]
   const float* raw = smem + mRAW + (s & 1) * R * 8;
   float* in4 = smem + mIN4;       // [R][4]   xt0, xt1, t, 1
   float* dout = smem + mDOUT;     // [R][2]
   float* lterm = smem + mLT;      // [R*DOUT]
-  const int tid = threadIdx.x, h = tid >> 8, j = tid & 255, lane = tid & 31, warp = tid >> 5;
-  const int ks = tid >> 6, u4 = tid & 63;
-  const int row0 = cta * R;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ks = tid / G::NU4, u4 = tid % G::NU4;
+  const int row0 = grp * R;
   const float* P = a.S + sP;
+  const uint32_t peer_act = CL == 2 ? mapa(actb, rank ^ 1) : 0, peer_bar = CL == 2 ? mapa(actbar, rank ^ 1) : 0;
 
-  // this thread's share of the thin layers and biases: issued now, needed later
-  const float w00 = __ldcg(P + oW0 + j * 3), w01 = __ldcg(P + oW0 + j * 3 + 1), w02 = __ldcg(P + oW0 + j * 3 + 2);
-  const float bias0 = __ldcg(P + ob0 + j), bias1 = __ldcg(P + ob1 + j), bias2 = __ldcg(P + ob2 + j);
-  const float w30 = __ldcg(P + oW3 + j), w31 = __ldcg(P + oW3 + W + j);
+  // the (row, unit) outputs this thread finalises in every layer, and its share of the thin layers / biases (issued now)
+  int orow[G::NQ], oj[G::NQ], ojl[G::NQ];
+  float w00[G::NQ], w01[G::NQ], w02[G::NQ], bias0[G::NQ], bias1[G::NQ], bias2[G::NQ], w30[G::NQ], w31[G::NQ];
+#pragma unroll
+  for (int q = 0; q < G::NQ; ++q) {
+    const int o = tid + q * NC;
+    orow[q] = o / G::UPC; ojl[q] = o % G::UPC; oj[q] = (int)rank * G::UPC + ojl[q];
+    const int j = oj[q];
+    w00[q] = __ldcg(P + oW0 + j * 3); w01[q] = __ldcg(P + oW0 + j * 3 + 1); w02[q] = __ldcg(P + oW0 + j * 3 + 2);
+    bias0[q] = __ldcg(P + ob0 + j); bias1[q] = __ldcg(P + ob1 + j); bias2[q] = __ldcg(P + ob2 + j);
+    w30[q] = __ldcg(P + oW3 + j); w31[q] = __ldcg(P + oW3 + W + j);
+  }
+  // publish one value of the next layer's input: own copy + (pair) the peer's copy through distributed shared memory
+  auto put = [&](int buf, int r, int j, float v) {
+    actb[(buf * R + r) * W + j] = v;
+    if (CL == 2) st_cluster(peer_act + ((buf * R + r) * W + j) * 4, v);
+  };
+  // all 256 units of the next layer's input are in place in this CTA (and, pair, this CTA's half in the peer)
+  auto layer_sync = [&]() {
+    if (CL == 1) {
+      csync();
+    } else {
+      __syncwarp();
+      if (lane == 0) { mbar_arrive_cluster(s32(actbar)); mbar_arrive_cluster(peer_bar); }
+      mbar_wait_cluster(actbar, aph);
+      aph ^= 1;
+    }
+  };
 
   if (tid < R) {   // K2 inlined: xt = t*x1 + (1-t)*x0 + sigma_t*eps   (conditional_flow_matching.py:98-123, no contraction)
     const float4 q0 = *reinterpret_cast<const float4*>(raw + tid * 8), q1 = *reinterpret_cast<const float4*>(raw + tid * 8 + 4);
@@ -203,48 +299,45 @@ __device__ void phase_rows(const Args& a, int s, float* smem, int cta, uint64_t*
     const float xt1 = __fadd_rn(__fadd_rn(__fmul_rn(t, q0.w), __fmul_rn(omt, q0.y)), __fmul_rn(st, q1.y));
     const float4 v = make_float4(xt0, xt1, t, 1.0f);
     *reinterpret_cast<float4*>(in4 + tid * 4) = v;
-    *reinterpret_cast<float4*>(a.S + sIN + (size_t)(row0 + tid) * 4) = v;
+    if (rank == 0) *reinterpret_cast<float4*>(a.S + sIN + (size_t)(row0 + tid) * 4) = v;
   }
   csync();
 
-  float code1[2], code2[2], code3[2];
+  float code1[G::NQ], code2[G::NQ], code3[G::NQ];
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {   // layer 1 (K = 3)
-    const int r = 2 * h + q;
-    const float z = fmaf(in4[r * 4 + 2], w02, fmaf(in4[r * 4 + 1], w01, fmaf(in4[r * 4], w00, bias0)));
+  for (int q = 0; q < G::NQ; ++q) {   // layer 1 (K = 3) -> buffer 0
+    const int r = orow[q];
+    const float z = fmaf(in4[r * 4 + 2], w02[q], fmaf(in4[r * 4 + 1], w01[q], fmaf(in4[r * 4], w00[q], bias0[q])));
     const float av = selu_fwd(z, code1[q]);
-    act[r * W + j] = av;
-    a.S[sA1 + (size_t)(row0 + r) * W + j] = av;
+    put(0, r, oj[q], av);
+    a.S[sA1 + (size_t)(row0 + r) * W + oj[q]] = av;
   }
-  csync();
+  layer_sync();
 
 #pragma unroll 1
-  for (int l = 0; l < 2; ++l) {   // layers 2, 3: ring passes 0 (W1^T), 1 (W2^T)
-    gemm_ring(ring, act, part, full, empty, cc, ks, u4, lane);
+  for (int l = 0; l < 2; ++l) {   // layers 2, 3: ring passes 0 (W1^T), 1 (W2^T); reads buffer l, writes buffer l ^ 1
+    gemm_ring<CL, R>(ring, actb + l * R * W, part, full, empty, cc, ks, u4, lane);
     csync();
-    const float b = l ? bias2 : bias1;
     float* Aout = a.S + (l ? sA3 : sA2);
-    float avs[2];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int r = 2 * h + q;
-      const float z = part_sum(part, r, j) + b;
+    for (int q = 0; q < G::NQ; ++q) {
+      const int r = orow[q];
+      const float z = part_sum<CL, R>(part, r, ojl[q]) + (l ? bias2[q] : bias1[q]);
       float c;
-      avs[q] = selu_fwd(z, c);
+      const float av = selu_fwd(z, c);
       if (l) code3[q] = c; else code2[q] = c;
-      Aout[(size_t)(row0 + r) * W + j] = avs[q];
+      put(l ^ 1, r, oj[q], av);
+      Aout[(size_t)(row0 + r) * W + oj[q]] = av;
     }
-    act[(2 * h) * W + j] = avs[0];       // every gemm_ring read of act happened before the csync above
-    act[(2 * h + 1) * W + j] = avs[1];
-    csync();
+    layer_sync();
   }
 
-  // output layer + loss (Autograd_example_order2.py:105) + d loss / d vt
+  // output layer + loss (Autograd_example_order2.py:105) + d loss / d vt; a3 is in buffer 0 (both CTAs of a pair compute it)
   if (warp < R * DOUT) {
     const int r = warp >> 1, o = warp & 1;
     float sum = 0.0f;
 #pragma unroll
-    for (int i = 0; i < W / 32; ++i) sum = fmaf(act[r * W + lane + 32 * i], __ldcg(P + oW3 + o * W + lane + 32 * i), sum);
+    for (int i = 0; i < W / 32; ++i) sum = fmaf(actb[r * W + lane + 32 * i], __ldcg(P + oW3 + o * W + lane + 32 * i), sum);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
     if (lane == 0) {
@@ -257,39 +350,37 @@ __device__ void phase_rows(const Args& a, int s, float* smem, int cta, uint64_t*
       const float gk = 1.0f / (float)(a.B * DOUT);
       const float d = 2.0f * rr * wgt * gk;
       dout[r * DOUT + o] = d;
-      a.S[sDO + (size_t)(row0 + r) * DOUT + o] = d;
+      if (rank == 0) a.S[sDO + (size_t)(row0 + r) * DOUT + o] = d;
     }
   }
   csync();
-  if (tid == 0) {
+  if (tid == 0 && rank == 0) {
     float ls = 0.0f;
 #pragma unroll
     for (int i = 0; i < R * DOUT; ++i) ls += lterm[i];
-    a.S[sLP + cta] = ls;
+    a.S[sLP + grp] = ls;
   }
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {   // dZ3 = (dOut W3) * selu'(z3)
-    const int r = 2 * h + q;
-    const float dz = fmaf(dout[r * 2 + 1], w31, dout[r * 2] * w30) * selu_d1(code3[q]);
-    act[r * W + j] = dz;
-    a.S[sZ3 + (size_t)(row0 + r) * W + j] = dz;
+  for (int q = 0; q < G::NQ; ++q) {   // dZ3 = (dOut W3) * selu'(z3) -> buffer 1
+    const int r = orow[q];
+    const float dz = fmaf(dout[r * 2 + 1], w31[q], dout[r * 2] * w30[q]) * selu_d1(code3[q]);
+    put(1, r, oj[q], dz);
+    a.S[sZ3 + (size_t)(row0 + r) * W + oj[q]] = dz;
   }
-  csync();
+  layer_sync();
 #pragma unroll 1
   for (int l = 0; l < 2; ++l) {   // dZ2 = (dZ3 W2) * selu'(z2), dZ1 = (dZ2 W1) * selu'(z1): ring passes 2 (W2), 3 (W1)
-    gemm_ring(ring, act, part, full, empty, cc, ks, u4, lane);
+    gemm_ring<CL, R>(ring, actb + (l ^ 1) * R * W, part, full, empty, cc, ks, u4, lane);
     csync();
     float* Zout = a.S + (l ? sZ1 : sZ2);
-    float dzs[2];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int r = 2 * h + q;
-      dzs[q] = part_sum(part, r, j) * selu_d1(l ? code1[q] : code2[q]);
-      Zout[(size_t)(row0 + r) * W + j] = dzs[q];
+    for (int q = 0; q < G::NQ; ++q) {
+      const int r = orow[q];
+      const float dz = part_sum<CL, R>(part, r, ojl[q]) * selu_d1(l ? code1[q] : code2[q]);
+      if (l == 0) put(0, r, oj[q], dz);
+      Zout[(size_t)(row0 + r) * W + oj[q]] = dz;
     }
-    act[(2 * h) * W + j] = dzs[0];
-    act[(2 * h + 1) * W + j] = dzs[1];
-    csync();
+    if (l == 0) layer_sync();
   }
 }
 
@@ -297,7 +388,7 @@ __device__ void phase_rows(const Args& a, int s, float* smem, int cta, uint64_t*
 struct Owned {
   float g[4];
   int idx[4];
-  int wt_off;   // tile jobs: state offset of WT[kb*32][jb*32] (the 32 x 32 transposed block of this CTA), else -1
+  int tile;     // tile jobs: the job index (layer, jb, kb) whose streaming copies this CTA refreshes, else -1
 };
 
 // ---- phase B ---------------------------------------------------------------------------------------------------------------
@@ -378,7 +469,7 @@ __device__ void job_tile(const Args& a, int job, float* smem, Owned& own) {
     own.g[0] = g0; own.g[1] = g1;
     own.idx[0] = oW + (jb * 32 + j) * W + kb * 32 + 2 * kp;
     own.idx[1] = own.idx[0] + 1;
-    own.wt_off = (int)(m ? sWT2 : sWT1) + (kb * 32) * W + jb * 32;
+    own.tile = job;
     if (kb == 0 && kp == 0) {
       float b = 0.f;
 #pragma unroll
@@ -418,40 +509,56 @@ __device__ void job_thin(const Args& a, const float* X, const float* Y, int q, f
   }
 }
 
+template <int CL, int R>
 __global__ void __launch_bounds__(NT, 1) k_train_flow(const Args a) {
+  using G = Geo<CL, R>;
+  constexpr int NS = G::NS;
   extern __shared__ __align__(128) float smem[];
-  __shared__ __align__(8) uint64_t full[NS], empty[NS];
+  __shared__ __align__(8) uint64_t full[NSMAX], empty[NSMAX], actbar[1];
   __shared__ double sred[NC / 32];
   __shared__ float s_coef, s_step_size, s_bc2_sqrt;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, cta = blockIdx.x;
-  const int nA = a.B / R;
-  const bool row_cta = cta < nA;
+  const uint32_t rank = CL == 2 ? cluster_ctarank() : 0;
+  const int grp = cta / CL;              // row group: the CTA (pair) that owns batch rows [4 grp, 4 grp + 4)
+  const bool row_cta = grp < a.B / R;
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], NC / 32); }
+    mbar_init(&actbar[0], 2 * (NC / 32));   // pair: one arrival per consumer warp of both CTAs per layer
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (row_cta && tid < R) load_raw(a, 0, tid, cta, smem + mRAW);
+  if (row_cta && tid < R) load_raw(a, 0, tid, grp * R, R, smem + mRAW);
   __syncthreads();
-  uint32_t cc = 0;   // ring chunks issued (producer) / consumed (consumers): the same sequence on both sides
+  if (CL == 2) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
+  uint32_t cc = 0;    // ring chunks issued (producer) / consumed (consumers): the same sequence on both sides
+  uint32_t aph = 0;   // phase of actbar
 
   if (warp == NC / 32) {
-    // ---- producer warp: streams the step's four weight matrices through the ring, prefetches the next step's inputs ----
+    // ---- producer warp: streams this CTA's share of the step's four weight matrices through the ring (pair: the half that
+    // produces its 128 output units; single: both halves), and prefetches the next step's input rows ----
     for (int s = 0; s < a.n_steps; ++s) {
       if (s > 0) fullsync();   // weights of step s are final (the consumers passed the closing grid barrier of step s - 1)
       if (!row_cta) continue;
+#ifndef IDFF_TRN_NOTMA
       if (lane == 0) {
         fence_async_global();
-        const float* src[4] = {a.S + sWT1, a.S + sWT2, a.S + sP + oW2, a.S + sP + oW1};
+        const float* src[4] = {a.S + sF1, a.S + sF2, a.S + sB2, a.S + sB1};
 #pragma unroll 1
         for (int c = 0; c < CH_PER_STEP; ++c, ++cc) {
           const uint32_t stage = cc % NS;
           if (cc >= NS) mbar_wait(&empty[stage], ((cc / NS) - 1) & 1);
-          mbar_arrive_expect_tx(&full[stage], CH_BYTES);
-          tma_load_1d(smem + mRING + stage * CH_FLOATS, src[c / CH_PER_PASS] + (size_t)(c % CH_PER_PASS) * CH_FLOATS, CH_BYTES,
-                      &full[stage]);
+          mbar_arrive_expect_tx(&full[stage], G::CHF * 4);
+          const float* m = src[c / CH_PER_PASS] + (size_t)(c % CH_PER_PASS) * HCH;
+          float* dst = smem + mRING + stage * G::CHF;
+          if (CL == 2) {
+            tma_load_1d(dst, m + (size_t)rank * HALF, HCH * 4, &full[stage]);
+          } else {
+            tma_load_1d(dst, m, HCH * 4, &full[stage]);
+            tma_load_1d(dst + HCH, m + HALF, HCH * 4, &full[stage]);
+          }
         }
       }
-      if (s + 1 < a.n_steps && lane < R) load_raw(a, s + 1, lane, cta, smem + mRAW);
+#endif
+      if (s + 1 < a.n_steps && lane < R) load_raw(a, s + 1, lane, grp * R, R, smem + mRAW);
     }
     return;
   }
@@ -467,7 +574,7 @@ __global__ void __launch_bounds__(NT, 1) k_train_flow(const Args a) {
   for (int s = 0; s < a.n_steps; ++s) {
     const bool stamp = tid == 0 && s == a.n_steps - 1;
     if (stamp) g_train_stamps[cta][0] = clock64();
-    if (row_cta) phase_rows(a, s, smem, cta, full, empty, cc);
+    if (row_cta) phase_rows<CL, R>(a, s, smem, grp, rank, full, empty, actbar, aph, cc);
     if (stamp) g_train_stamps[cta][1] = clock64();
     grid_barrier(bar, epoch, false);
     if (stamp) g_train_stamps[cta][2] = clock64();
@@ -475,7 +582,7 @@ __global__ void __launch_bounds__(NT, 1) k_train_flow(const Args a) {
     Owned own;
 #pragma unroll
     for (int i = 0; i < 4; ++i) { own.g[i] = 0.0f; own.idx[i] = -1; }
-    own.wt_off = -1;
+    own.tile = -1;
     if (cta < JOB_W0) {
       job_tile(a, cta, smem, own);
     } else if (cta < JOB_W3) {   // dW0, db0 for units [32 q, 32 q + 32)
@@ -506,7 +613,7 @@ __global__ void __launch_bounds__(NT, 1) k_train_flow(const Args a) {
         if (lane == 0) { own.g[0] = sum; own.idx[0] = ob3 + warp; }
       } else if (warp == 2) {
         double sum = 0.0;
-        for (int c = lane; c < nA; c += 32) sum += (double)__ldcg(a.S + sLP + c);
+        for (int c = lane; c < a.B / R; c += 32) sum += (double)__ldcg(a.S + sLP + c);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
         if (lane == 0 && a.loss_out) a.loss_out[s] = (float)(sum / (double)(a.B * DOUT));
@@ -575,14 +682,18 @@ __global__ void __launch_bounds__(NT, 1) k_train_flow(const Args a) {
         pn[i] = p - step_size * (mm / denom);
         P[ix] = pn[i]; M[ix] = mm; V[ix] = v2;
       }
-      if (own.wt_off >= 0) {   // W^T copy of the tile through shared memory: rows of 32 consecutive j per k
+      if (own.tile >= 0) {   // streaming copies of this 32 x 32 tile: backward (as stored) and forward (transposed via smem)
+        const int m = own.tile >> 6, jb = (own.tile >> 3) & 7, kb = own.tile & 7;
+        float* Bc = a.S + (m ? sB2 : sB1) + (size_t)(kb >> 2) * HALF + (kb & 3) * 32;   // B[h][j][kk], kk = k - 128 h
+        float* Fc = a.S + (m ? sF2 : sF1) + (size_t)(jb >> 2) * HALF + (jb & 3) * 32;   // F[h][k][jj], jj = j - 128 h
         float* pt = smem + mPT;
         const int j = tid >> 4, kp = tid & 15;
+        *reinterpret_cast<float2*>(Bc + (jb * 32 + j) * 128 + 2 * kp) = make_float2(pn[0], pn[1]);
         pt[(2 * kp) * 33 + j] = pn[0];
         pt[(2 * kp + 1) * 33 + j] = pn[1];
         csync();
         const int k = tid >> 4, j2 = (tid & 15) * 2;
-        *reinterpret_cast<float2*>(a.S + own.wt_off + k * W + j2) = make_float2(pt[k * 33 + j2], pt[k * 33 + j2 + 1]);
+        *reinterpret_cast<float2*>(Fc + (kb * 32 + k) * 128 + j2) = make_float2(pt[k * 33 + j2], pt[k * 33 + j2 + 1]);
       }
       fence_async_global();   // the next step's TMA reads (async proxy) of these generic-proxy writes
     }
@@ -592,12 +703,14 @@ __global__ void __launch_bounds__(NT, 1) k_train_flow(const Args a) {
   }
 }
 
-__global__ void k_train_init(float* S) {   // WT[k][j] = W[j][k] for layers 2 and 3
+__global__ void k_train_init(float* S) {   // streaming copies of layers 2 and 3 from the parameter block
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < W * W) {
-    const int k = i / W, j = i % W;
-    S[sWT1 + i] = S[sP + oW1 + j * W + k];
-    S[sWT2 + i] = S[sP + oW2 + j * W + k];
+    const int j = i / W, k = i % W;   // W_l[j][k]
+    const float w1 = S[sP + oW1 + i], w2 = S[sP + oW2 + i];
+    const size_t f = (size_t)(j >> 7) * HALF + k * 128 + (j & 127), b = (size_t)(k >> 7) * HALF + j * 128 + (k & 127);
+    S[sF1 + f] = w1; S[sF2 + f] = w2;
+    S[sB1 + b] = w1; S[sB2 + b] = w2;
   }
 }
 
@@ -613,6 +726,12 @@ extern "C" int idff_train_flow_offsets(int64_t* h_out12) {
   IDFF_CHECK_ARG(h_out12, "idff_train_flow_offsets: null pointer");
   const int64_t v[12] = {oW0, ob0, oW1, ob1, oW2, ob2, oW3, ob3, NP, (int64_t)sP, (int64_t)sM, (int64_t)sV};
   for (int i = 0; i < 12; ++i) h_out12[i] = v[i];
+  return IDFF_OK;
+}
+
+static int g_pair_mode = 0;   // diagnostic: 1 = run a row group on a CTA pair where possible (idff_debug_train_pair_mode)
+extern "C" int idff_debug_train_pair_mode(int32_t on) {
+  g_pair_mode = on ? 1 : 0;
   return IDFF_OK;
 }
 
@@ -639,7 +758,7 @@ extern "C" int idff_train_flow_steps(float* d_state, const float* d_x0, const fl
   IDFF_CHECK_ARG(((reinterpret_cast<uintptr_t>(d_x0) | reinterpret_cast<uintptr_t>(d_x1) | reinterpret_cast<uintptr_t>(d_eps)) & 7) == 0,
                  "idff_train_flow_steps: x0, x1, eps must be 8-byte aligned");
   IDFF_CHECK_ARG(n_steps >= 0 && n_steps <= (1 << 20), "idff_train_flow_steps: n_steps %d outside [0, 2^20]", n_steps);
-  IDFF_CHECK_ARG(B >= R && B <= MAXB && B % R == 0, "idff_train_flow_steps: batch %d must be a multiple of %d in [%d, %d]", B, R, R, MAXB);
+  IDFF_CHECK_ARG(B >= RMIN && B <= MAXB && B % RMIN == 0, "idff_train_flow_steps: batch %d must be a multiple of %d in [%d, %d]", B, RMIN, RMIN, MAXB);
   IDFF_CHECK_ARG(sigma_mode == 0 || sigma_mode == 1, "idff_train_flow_steps: sigma_mode %d", sigma_mode);
   IDFF_CHECK_ARG(steps_done >= 0, "idff_train_flow_steps: steps_done < 0");
   if (n_steps == 0) return IDFF_OK;
@@ -651,10 +770,11 @@ extern "C" int idff_train_flow_steps(float* d_state, const float* d_x0, const fl
     set_error("idff_train_flow_steps: needs cooperative launch and >= %d SMs (device has %d)", N_JOBS, sms);
     return IDFF_EUNSUPPORTED;
   }
-  const int grid = sms < MAX_GRID ? sms : MAX_GRID;
+  int grid = sms < MAX_GRID ? sms : MAX_GRID;
   static bool attr_set = false;
   if (!attr_set) {
-    IDFF_CUDA(cudaFuncSetAttribute(k_train_flow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    IDFF_CUDA(cudaFuncSetAttribute(k_train_flow<1, RMIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    IDFF_CUDA(cudaFuncSetAttribute(k_train_flow<2, RMIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     attr_set = true;
   }
   Args a;
@@ -670,8 +790,35 @@ extern "C" int idff_train_flow_steps(float* d_state, const float* d_x0, const fl
   a.b1pow = std::pow(opt->beta1, (double)steps_done); a.b2pow = std::pow(opt->beta2, (double)steps_done);
   cudaStream_t st = (cudaStream_t)stream;
   IDFF_CUDA(cudaMemsetAsync(d_state + sBAR, 0, 64 * sizeof(float), st));
-  void* kargs[] = {&a};
-  IDFF_CUDA(cudaLaunchCooperativeKernel((const void*)k_train_flow, dim3(grid), dim3(NT), kargs, kSmemBytes, st));
+  // one CTA per 4 rows by default.  Opt-in (idff_debug_train_pair_mode): a CTA pair (cluster of 2) per 4 rows, each CTA streaming
+  // and computing half of the units -- measured SLOWER (27 vs 25 us/step at B = 256): the five cluster-scope activation
+  // exchanges per step cost more than the halved weight stream and FMA work save
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  int pairs = 0;
+  const int grid2 = grid & ~1;
+  if (g_pair_mode && 2 * (B / RMIN) <= grid2 && grid2 >= N_JOBS) {
+    cfg.gridDim = dim3(grid2);
+    cfg.numAttrs = 2;
+    int ncl = 0;
+    if (cudaOccupancyMaxActiveClusters(&ncl, k_train_flow<2, RMIN>, &cfg) == cudaSuccess && 2 * ncl >= grid2) pairs = 1;
+    else (void)cudaGetLastError();
+  }
+  if (pairs) {
+    IDFF_CUDA(cudaLaunchKernelEx(&cfg, k_train_flow<2, RMIN>, a));
+  } else {
+    cfg.gridDim = dim3(grid);
+    cfg.numAttrs = 1;
+    IDFF_CUDA(cudaLaunchKernelEx(&cfg, k_train_flow<1, RMIN>, a));
+  }
   count_launch();
   return IDFF_OK;
 }

@@ -195,6 +195,10 @@ int idff_train_flow_init(float* d_state, void* stream);
 /* Diagnostic: clock64 stamps of the last step of the last idff_train_flow_steps launch, h_out [n_ctas][8]: per CTA
  * {step start, rows phase done, barrier 1 passed, weight-gradient job done, barrier 2 passed, AdamW done, barrier 3 passed, 0}. */
 int idff_debug_train_stamps(int64_t* h_out, int32_t n_ctas);
+/* Diagnostic: on != 0 makes idff_train_flow_steps run every group of 4 batch rows on a CTA pair (cluster of 2 that splits the
+ * units, activation halves exchanged through distributed shared memory; B <= 296) instead of one CTA.  Measured slower; the
+ * two modes sum the K-slices of a layer in different (fixed) orders, so they agree to fp32 rounding, not bit for bit. */
+int idff_debug_train_pair_mode(int32_t on);
 int idff_train_flow_steps(float* d_state, const float* d_x0, const float* d_x1, const float* d_t, const float* d_eps,
                           int32_t n_steps, int32_t B, float sigma, int32_t sigma_mode, const idff_adamw_t* opt,
                           int64_t steps_done, float* d_loss, float* d_gnorm, float* d_grad_dump, void* stream);

@@ -6,8 +6,12 @@ import torch
 from idff_b200 import train
 from idff_b200.torchcfm.models.models import MLP
 
+import ctypes as C
+from idff_b200 import _lib
 dev = torch.device("cuda:0")
-for B in (256, 64, 512):
+for B, pair in ((256, 0), (256, 1), (64, 0), (512, 0)):
+    _lib.lib().idff_debug_train_pair_mode(pair)
+    print("mode:", "CTA pair per 4 rows (opt-in)" if pair and B <= 296 else "one CTA per 4 rows (default)", flush=True)
     torch.manual_seed(0)
     tr = train.FusedFlowTrainer(MLP(dim=2, w=256, time_varying=True).to(dev), batch_size=B)
     for S in (1, 64, 1024):
@@ -29,9 +33,8 @@ for B in (256, 64, 512):
         print(f"B={B} S={S}: {us:.2f} us/step = {B / us:.2f} M samples/s (pre-drawn); {us2:.2f} us/step incl. draws", flush=True)
 
 # phase stamps (clock64 per CTA) of the last step of a 64-step launch at B = 256
-import ctypes as C
 import numpy as np
-from idff_b200 import _lib
+_lib.lib().idff_debug_train_pair_mode(0)
 torch.manual_seed(0)
 tr = train.FusedFlowTrainer(MLP(dim=2, w=256, time_varying=True).to(dev), batch_size=256)
 x0, x1, t, eps = tr.draw(64)
