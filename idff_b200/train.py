@@ -88,6 +88,56 @@ class GraphedFlowTrainer:
         return self.loss
 
 
+def md_train_step(model, optimizer, FM, dataset, index_sel, t=None):
+    """One PolyALA training step (TrajectoryGenerator.train_model, MD_simulation.py:126-144) on given frame indices:
+    x0 = dataset[idx - 1], x1 = dataset[idx]; path sample (idff_path_sample); vt = model(cat[xt, t], idx) (torch);
+    periodic loss (idff_loss kind 2, value + gradient in one pass); Adam.  Returns the loss (0-d device tensor)."""
+    optimizer.zero_grad(set_to_none=False)
+    x0, x1 = dataset[index_sel - 1], dataset[index_sel]                                    # :129-130
+    t, xt, ut, eps = FM.sample_location_and_conditional_flow(x0, x1, t=t, return_noise=True)   # :132
+    vt = model(torch.cat([xt, t[:, None]], dim=-1), index_sel)                                 # :135
+    loss = losses.md_periodic_loss(vt, x1)                                                      # :137-141
+    loss.backward()
+    optimizer.step()
+    return loss.detach()
+
+
+class GraphedMDTrainer:
+    """`md_train_step` with on-device index / time draws captured as one CUDA graph (the reference's batch is 10:
+    ~70 launch-bound kernels per step).  dataset: (T, D) CUDA tensor; model: MLP_Embedding(dim=D, w, time_embed=T,
+    time_varying=True); optimizer: torch.optim.Adam with defaults (MD_simulation.py:119), sigma :121."""
+
+    def __init__(self, model: torch.nn.Module, dataset: torch.Tensor, batch_size: int = 10, sigma: float = 0.5, warmup: int = 3):
+        if not dataset.is_cuda:
+            raise RuntimeError("GraphedMDTrainer needs a CUDA data set: idff_b200 has no CPU path")
+        self.model, self.dataset, self.B = model, dataset, int(batch_size)
+        self.device = dataset.device
+        self.FM = cfm.ExactOptimalTransportConditionalFlowMatcher(sigma=sigma)
+        self.optimizer = torch.optim.Adam(model.parameters(), capturable=True)
+        self.loss = torch.zeros((), device=self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._eager()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._eager()
+        self.steps = 0
+
+    def _eager(self):
+        idx = torch.randint(1, self.dataset.shape[0], (self.B,), device=self.device)      # :128
+        t = torch.rand(self.B, device=self.device)
+        self.loss.copy_(md_train_step(self.model, self.optimizer, self.FM, self.dataset, idx, t=t))
+
+    def step(self) -> torch.Tensor:
+        self.graph.replay()
+        self.steps += 1
+        return self.loss
+
+
 class FusedFlowTrainer:
     """The reference's 2-D training loop (Autograd_example_order2.py:89-112) on `idff_train_flow_steps`.
 

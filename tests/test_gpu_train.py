@@ -221,3 +221,55 @@ def test_graphed_trainer_replays_and_learns(cuda_device):
     assert tr.steps == 440 and all(np.isfinite(first + last))
     assert np.mean(last) < 0.7 * np.mean(first), (np.mean(first), np.mean(last))
     assert any(not torch.equal(a, b.detach()) for a, b in zip(before, model.parameters()))
+
+
+def test_md_train_step_matches_reference_formula(cuda_device):
+    """One step of TrajectoryGenerator.train_model (MD_simulation.py:126-144) through the kernels (path sample, periodic loss
+    value + gradient) against the same step written with the reference's torch expressions: loss and Adam-updated parameters."""
+    from idff_b200 import train
+    from idff_b200.torchcfm.models.models import MLP_Embedding
+    dev = cuda_device
+    T, D, B = 200, 46, 10
+    g = torch.Generator().manual_seed(3)
+    data = (180 * torch.sin(torch.cumsum(torch.randn(T, D, generator=g) * 0.05, 0))).to(dev)
+    idx = torch.randint(1, T, (B,), generator=g).to(dev)
+    t = torch.rand(B, generator=g).to(dev)
+    torch.manual_seed(0)
+    ours = MLP_Embedding(dim=D, w=128, time_embed=T, time_varying=True).to(dev)
+    torch.manual_seed(0)
+    ref = MLP_Embedding(dim=D, w=128, time_embed=T, time_varying=True).to(dev)
+    FM = cfm.ExactOptimalTransportConditionalFlowMatcher(sigma=0.5)
+    eps = torch.randn(B, D, generator=g).to(dev)
+    FM.sample_noise_like = lambda x, e=eps: e
+    opt_o, opt_r = torch.optim.Adam(ours.parameters()), torch.optim.Adam(ref.parameters())
+    loss_o = train.md_train_step(ours, opt_o, FM, data, idx, t=t)
+    opt_r.zero_grad()
+    x0, x1 = data[idx - 1], data[idx]
+    st = 0.5 * torch.sqrt(t * (1 - t))
+    xt = t[:, None] * x1 + (1 - t[:, None]) * x0 + st[:, None] * eps
+    vt = ref.net(torch.cat([xt, t[:, None], ref.time_index_embedding(idx)], dim=-1))
+    loss_r = torch.mean((vt - x1) ** 2) + torch.mean((vt - (x1 + 360)) ** 2) + torch.mean((vt - (x1 - 360)) ** 2)
+    loss_r.backward()
+    opt_r.step()
+    assert loss_o.item() == pytest.approx(loss_r.item(), rel=2e-6)
+    for po, pr in zip(ours.parameters(), ref.parameters()):
+        # Adam's first step moves a weight by lr * g / (|g| + 1e-8): fp32 noise in a near-zero gradient can flip it
+        d = np.abs(po.detach().cpu().numpy() - pr.detach().cpu().numpy()).reshape(-1)
+        assert np.quantile(d, 0.999) <= 2e-6 and d.max() <= 2.1e-3, (d.max(), np.quantile(d, 0.999))
+
+
+def test_graphed_md_trainer_learns(cuda_device):
+    from idff_b200 import train
+    from idff_b200.torchcfm.models.models import MLP_Embedding
+    dev = cuda_device
+    T, D = 200, 46
+    g = torch.Generator().manual_seed(4)
+    data = (180 * torch.sin(torch.cumsum(torch.randn(T, D, generator=g) * 0.05, 0))).to(dev)
+    torch.manual_seed(1)
+    model = MLP_Embedding(dim=D, w=128, time_embed=T, time_varying=True).to(dev)
+    tr = train.GraphedMDTrainer(model, data, batch_size=10, sigma=0.5)
+    first = [tr.step().item() for _ in range(20)]
+    for _ in range(600):
+        tr.step()
+    last = [tr.step().item() for _ in range(20)]
+    assert np.isfinite(first + last).all() and np.mean(last) < np.mean(first), (np.mean(first), np.mean(last))
