@@ -1,7 +1,8 @@
 """The `_dynamic` flavour of the matchers (torchcfm/conditional_flow_matching_dynamic.py): identical to
 conditional_flow_matching.py except that (a) compute_lambda returns 2*sigma_t/(sigma^2+1e-8) (:213-214) and
 (b) the ExactOT matcher re-pairs the batch with the minibatch-OT plan before sampling (:268).  The re-pairing is
-an index gather fused into the path-sample kernel; the plan itself comes from an OTPlanSampler (host side)."""
+an index gather fused into the path-sample kernel; the plan comes from an OTPlanSampler -- on CUDA tensors the exact
+assignment kernel idff_ot_assign, index pairs drawn on the device (no host round trip)."""
 from typing import Union
 
 import torch

@@ -1,9 +1,37 @@
-"""Minibatch OT coupling (torchcfm/optimal_transport.py:11-142).  OUT OF the hot path: the reference solves the
-plan with POT's CPU network simplex at batch size 256; only its output -- the index pairs (i, j) -- feeds the
-path-sample kernel (as a fused gather).  POT is not installed here, so the exact plan for the uniform, equal-size
-marginals the reference uses is obtained with scipy's assignment solver on the host."""
+"""Minibatch OT coupling (torchcfm/optimal_transport.py:11-142).
+
+The reference computes the exact plan between two minibatches of equal size with uniform marginals on the host (POT's
+network simplex, `pot.emd`, batch 256) and samples index pairs from it with numpy.  For those marginals the exact plan is
+1/n times a permutation matrix, so the coupling is an assignment problem.  On CUDA tensors it is solved where the data lives
+(`idff_ot_assign`: exact shortest-augmenting-path assignment in fp64, one launch) and the index pairs are drawn on the device:
+no host round trip, graph-capturable, and they feed `idff_path_sample` as fused gather indices.  `get_map` / `sample_map`
+keep the reference's host-side signatures (numpy plan in, numpy indices out; POT is not installed here, so the plan comes
+from scipy's assignment solver)."""
+import ctypes as C
+
 import numpy as np
 import torch
+
+from .. import _lib
+
+
+def ot_assign(x0: torch.Tensor, x1: torch.Tensor, return_cost: bool = False):
+    """perm (n,) int64 on the device with plan[i][perm[i]] = 1/n for the exact uniform-marginal plan of (x0, x1) under the
+    squared-Euclidean cost (optimal_transport.py:59-94 for equal batch sizes); optionally the plan's total cost (fp64)."""
+    _lib.require_cuda(x0, "x0")
+    _lib.require_cuda(x1, "x1")
+    if x0.shape[0] != x1.shape[0]:
+        raise _lib.IdffError("ot_assign needs equal batch sizes (the reference's uniform-marginal minibatch plan)")
+    a = x0.detach().reshape(x0.shape[0], -1).contiguous()
+    b = x1.detach().reshape(x1.shape[0], -1).contiguous()
+    if a.shape[1] != b.shape[1]:
+        raise _lib.IdffError(f"x0 and x1 differ in dimension: {a.shape[1]} vs {b.shape[1]}")
+    n, D = a.shape
+    perm = torch.empty(n, dtype=torch.int64, device=a.device)
+    cost = torch.zeros((), dtype=torch.float64, device=a.device) if return_cost else None
+    _lib.check(_lib.lib().idff_ot_assign(_lib.ptr(a), _lib.ptr(b), n, D, _lib.ptr(perm), _lib.ptr(cost), _lib.stream_of(a)),
+               "idff_ot_assign")
+    return (perm, cost) if return_cost else perm
 
 
 class OTPlanSampler:
@@ -13,7 +41,7 @@ class OTPlanSampler:
         self.method = method
 
     def get_map(self, x0, x1):
-        """Uniform-marginal exact plan, as a (B0, B1) numpy array (reference :59-94)."""
+        """Uniform-marginal exact plan, as a (B0, B1) numpy array (reference :59-94) -- host side, for API compatibility."""
         from scipy.optimize import linear_sum_assignment
         a = x0.reshape(x0.shape[0], -1).double()
         b = x1.reshape(x1.shape[0], -1).double()
@@ -32,10 +60,15 @@ class OTPlanSampler:
         choices = np.random.choice(pi.shape[0] * pi.shape[1], p=p, size=batch_size, replace=replace)
         return np.divmod(choices, pi.shape[1])
 
-    def sample_map_indices(self, x0, x1):
+    def sample_map_indices(self, x0, x1, generator=None):
+        """(i, j) int64 index tensors on x0's device, distributed as the reference's sample_map(get_map(x0, x1), B): i uniform
+        with replacement, j = perm[i].  CUDA inputs: assignment and draw on the device (torch's generator, not numpy's)."""
+        if x0.is_cuda:
+            perm = ot_assign(x0, x1)
+            i = torch.randint(0, x0.shape[0], (x0.shape[0],), device=x0.device, generator=generator)
+            return i, perm[i]
         i, j = self.sample_map(self.get_map(x0, x1), x0.shape[0])
-        dev = x0.device
-        return (torch.as_tensor(i, dtype=torch.int64, device=dev), torch.as_tensor(j, dtype=torch.int64, device=dev))
+        return torch.as_tensor(i, dtype=torch.int64), torch.as_tensor(j, dtype=torch.int64)
 
     def sample_plan(self, x0, x1, replace=True):
         i, j = self.sample_map_indices(x0, x1)

@@ -203,6 +203,14 @@ int idff_train_flow_steps(float* d_state, const float* d_x0, const float* d_x1, 
                           int32_t n_steps, int32_t B, float sigma, int32_t sigma_mode, const idff_adamw_t* opt,
                           int64_t steps_done, float* d_loss, float* d_gnorm, float* d_grad_dump, void* stream);
 
+/* ---- OTPlanSampler.get_map for the reference's use (torchcfm/optimal_transport.py:59-94: uniform marginals over
+ * two minibatches of EQUAL size n, squared-Euclidean cost, exact plan from pot.emd -- POT's network simplex, un-vendored).  The
+ * exact plan of uniform equal-size marginals is 1/n times a permutation matrix, so the plan is returned as the permutation:
+ * d_perm [n] int64, plan[i][perm[i]] = 1/n; sample_plan (:120-142) then draws i uniformly and pairs x0[i] with x1[perm[i]]
+ * (the gather inputs d_idx0 / d_idx1 of idff_path_sample).  d_x0, d_x1 [n][D] fp32; n <= 1024; d_cost (optional): the plan's
+ * total cost sum_i |x0[i] - x1[perm[i]]|^2 in fp64.  Exact shortest-augmenting-path assignment in fp64, one launch. */
+int idff_ot_assign(const float* d_x0, const float* d_x1, int32_t n, int32_t D, int64_t* d_perm, double* d_cost, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -405,6 +405,21 @@ def md_periodic_loss(vt, x1):
             + torch.mean((vt - (x1 - 360)) ** 2))
 
 
+def ot_exact_permutation(x0, x1):
+    """OTPlanSampler.get_map (optimal_transport.py:59-94) for equal batch sizes: pot.emd(unif, unif, cdist^2) -- POT (un-vendored,
+    unpinned in requirements.txt:10) solves the transport LP with the network simplex; with uniform equal-size marginals its
+    optimum is 1/n times a permutation matrix, obtained here with scipy's assignment solver on the fp64 cost of the fp32
+    points.  Returns (perm, total cost): plan[i][perm[i]] = 1/n.  PARITY UNPINNED against POT itself (not installed)."""
+    from scipy.optimize import linear_sum_assignment
+    a = torch.as_tensor(x0).reshape(len(x0), -1).double()
+    b = torch.as_tensor(x1).reshape(len(x1), -1).double()
+    M = ((a[:, None, :] - b[None, :, :]) ** 2).sum(-1).numpy()
+    r, c = linear_sum_assignment(M)
+    perm = np.empty(len(r), dtype=np.int64)
+    perm[r] = c
+    return perm, float(M[r, c].sum())
+
+
 def md_compute_metrics(y_hat, dataset):
     """TrajectoryGenerator.compute_metrics (MD_simulation.py:275-295): per (trajectory, dimension) Pearson CC, RMSE and MAE
     of the generated series against the data over the T frames, then mean / std (ddof = 0) over the K*D series.

@@ -1,0 +1,67 @@
+"""-m gpu: the device OT coupling (idff_ot_assign) against the oracle (scipy's exact assignment on the fp64
+cost, the restatement of pot.emd for uniform equal-size marginals, optimal_transport.py:59-94)."""
+import numpy as np
+import pytest
+import torch
+
+import idff_oracle as O
+from idff_b200 import _lib
+from idff_b200.torchcfm import optimal_transport as ot
+from idff_b200.torchcfm import conditional_flow_matching_dynamic as cfmd
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,D", [(1, 2), (2, 2), (10, 46), (64, 2), (256, 2), (257, 3), (512, 2), (1024, 2)])
+def test_assignment_is_the_exact_plan(cuda_device, n, D):
+    g = torch.Generator().manual_seed(100 * n + D)
+    x0 = torch.randn(n, D, generator=g)
+    x1 = torch.randn(n, D, generator=g) * 1.5 + 0.3
+    perm_ref, cost_ref = O.ot_exact_permutation(x0, x1)
+    before = _lib.launch_count()
+    perm, cost = ot.ot_assign(x0.to(cuda_device), x1.to(cuda_device), return_cost=True)
+    assert _lib.launch_count() - before == 1
+    perm = perm.cpu().numpy()
+    assert sorted(perm.tolist()) == list(range(n))                        # a permutation: plan = P / n has uniform marginals
+    assert cost.item() == pytest.approx(cost_ref, rel=1e-12, abs=1e-12)   # the same optimum ...
+    np.testing.assert_array_equal(perm, perm_ref)                         # ... and (generic data: unique) the same plan
+
+
+def test_ties_and_degenerate_inputs(cuda_device):
+    """Duplicate points (many optimal plans): any optimal permutation is acceptable, the cost must be the optimum."""
+    x0 = torch.tensor([[0.0, 0.0]] * 8 + [[1.0, 1.0]] * 8)
+    x1 = torch.tensor([[1.0, 1.0]] * 8 + [[0.0, 0.0]] * 8)
+    perm, cost = ot.ot_assign(x0.to(cuda_device), x1.to(cuda_device), return_cost=True)
+    assert sorted(perm.cpu().tolist()) == list(range(16)) and cost.item() == 0.0
+    x = torch.randn(33, 2)
+    perm, cost = ot.ot_assign(x.to(cuda_device), x.to(cuda_device), return_cost=True)
+    assert perm.cpu().tolist() == list(range(33)) and cost.item() == 0.0
+    with pytest.raises(_lib.IdffError):
+        ot.ot_assign(torch.zeros(2000, 2, device=cuda_device), torch.zeros(2000, 2, device=cuda_device))
+    with pytest.raises(_lib.IdffError):
+        ot.ot_assign(torch.zeros(4, 2), torch.zeros(4, 2))                # CPU tensors: no fallback
+
+
+def test_dynamic_matcher_couples_on_the_device(cuda_device):
+    """conditional_flow_matching_dynamic.py:268: x0, x1 = ot_sampler.sample_plan(x0, x1) -- pairs follow the exact plan
+    (every drawn pair (i, j) has j = perm[i]), i is uniform, and the path sample uses the re-paired rows."""
+    dev = cuda_device
+    B = 256
+    g = torch.Generator().manual_seed(9)
+    x0 = torch.randn(B, 2, generator=g).to(dev)
+    x1 = (torch.randn(B, 2, generator=g) + 2.0).to(dev)
+    perm_ref, _ = O.ot_exact_permutation(x0.cpu(), x1.cpu())
+    i, j = ot.OTPlanSampler().sample_map_indices(x0, x1)
+    assert i.is_cuda and j.is_cuda and i.dtype == torch.int64
+    np.testing.assert_array_equal(j.cpu().numpy(), perm_ref[i.cpu().numpy()])
+    assert 0.45 * B < len(set(i.cpu().tolist())) <= B                     # with replacement: ~63 % distinct
+    FM = cfmd.ExactOptimalTransportConditionalFlowMatcher(sigma=0.0)
+    t, xt, ut = FM.sample_location_and_conditional_flow(x0, x1)
+    # sigma = 0: xt - t * ut = x0[i] and xt + (1 - t) * ut = x1[perm[i]] for the drawn i: every row of (FM.x0, FM.x1) is a plan pair
+    a, b = FM.x0.cpu().numpy(), FM.x1.cpu().numpy()
+    x0n, x1n = x0.cpu().numpy(), x1.cpu().numpy()
+    for r in range(0, B, 17):
+        src = np.where((x0n == a[r]).all(1))[0]
+        assert len(src) >= 1 and (x1n[perm_ref[src[0]]] == b[r]).all()
+    # transport cost of the coupled pairs is lower than the independent pairing's
+    assert ((FM.x0 - FM.x1) ** 2).sum(1).mean().item() < ((x0 - x1) ** 2).sum(1).mean().item()
