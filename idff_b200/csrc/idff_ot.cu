@@ -8,9 +8,10 @@
 // assignment is solved where the data lives, so the dynamic matcher's step needs no host round trip and can be graph-captured.
 //
 // Algorithm: shortest augmenting paths with dual variables (Jonker-Volgenant / the Hungarian method in its O(n^3) form), fp64,
-// exact.  One CTA, one thread per column: a thread keeps its column's tentative distance, visited flag and dual v in registers;
-// every search step is one relaxation of all columns against the row just reached (cost recomputed from the coordinates, never
-// materialised) plus one block-wide argmin (warp shuffles + one shared-memory exchange, one barrier per step).
+// exact, after a greedy column-reduction start.  One CTA, one thread per column: a thread keeps its column's tentative distance,
+// visited flag and dual v in registers; every search step is one relaxation of all columns against the row just reached (cost
+// recomputed from the coordinates, never materialised) plus one block-wide argmin (warp shuffles, one shared-memory exchange,
+// one barrier per step).
 #include "idff_common.cuh"
 
 namespace idff {
@@ -21,26 +22,34 @@ constexpr int MAXN = 1024;
 struct Best {
   double val;
   int col;    // column index (MAXN: none)
-  int row;    // row4col[col]
+  int pad;
 };
 
-__device__ __forceinline__ bool better(double v, int r, int c, double bv, int br, int bc) {
-  // lowest distance; on ties an unassigned column (it ends the search), then the lowest index
-  if (v != bv) return v < bv;
-  const int fa = r < 0 ? 0 : 1, fb = br < 0 ? 0 : 1;
-  if (fa != fb) return fa < fb;
-  return c < bc;
+// (distance, column) order: lowest distance, then lowest column index -- any minimal column is a valid next Dijkstra vertex
+__device__ __forceinline__ bool better(double v, int c, double bv, int bc) { return v < bv || (v == bv && c < bc); }
+
+__device__ __forceinline__ void warp_argmin(double& bv, int& bc) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+    const int oc = __shfl_xor_sync(0xffffffffu, bc, off);
+    if (better(ov, oc, bv, bc)) { bv = ov; bc = oc; }
+  }
 }
 
+// DFIX > 0: D == DFIX, both point sets are staged on chip (x1[j] in registers, x0 in shared memory); DFIX == 0: any D, read
+// through L1.
 template <int DFIX>
 __global__ void __launch_bounds__(MAXN, 1) k_ot_assign(const float* __restrict__ x0, const float* __restrict__ x1, int n, int D,
                                                        int64_t* __restrict__ perm, double* __restrict__ cost_out) {
   extern __shared__ __align__(16) unsigned char smraw[];
   double* u = reinterpret_cast<double*>(smraw);                    // [n] row duals
-  int* col4row = reinterpret_cast<int*>(u + n);                     // [n]
+  Best* wbest = reinterpret_cast<Best*>(u + n);                     // [2][32]
+  int* col4row = reinterpret_cast<int*>(wbest + 64);                // [n]
   int* row4col = col4row + n;                                        // [n]
   int* path = row4col + n;                                           // [n]
-  Best* wbest = reinterpret_cast<Best*>(path + n + (n & 1));        // [2][32]
+  int* claim = path + n;                                             // [n] greedy start: lowest column that wants row i
+  float* x0s = reinterpret_cast<float*>(claim + n);                 // [n][DFIX]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = (blockDim.x + 31) >> 5;
   const int j = tid;
   const bool has = j < n;
@@ -49,15 +58,18 @@ __global__ void __launch_bounds__(MAXN, 1) k_ot_assign(const float* __restrict__
   float x1r[DFIX > 0 ? DFIX : 1];
   if (DFIX > 0 && has) {
 #pragma unroll
-    for (int d = 0; d < DFIX; ++d) x1r[d] = x1[(size_t)j * DFIX + d];
+    for (int d = 0; d < DFIX; ++d) {
+      x1r[d] = x1[(size_t)j * DFIX + d];
+      x0s[j * DFIX + d] = x0[(size_t)j * DFIX + d];
+    }
   }
   if (has) {
     u[j] = 0.0;
     col4row[j] = -1;
     row4col[j] = -1;
     path[j] = -1;
+    claim[j] = MAXN;
   }
-  double v = 0.0;
   __syncthreads();
 
   auto cost = [&](int i) -> double {
@@ -65,7 +77,7 @@ __global__ void __launch_bounds__(MAXN, 1) k_ot_assign(const float* __restrict__
     if (DFIX > 0) {
 #pragma unroll
       for (int d = 0; d < DFIX; ++d) {
-        const double df = (double)x0[(size_t)i * DFIX + d] - (double)x1r[d];
+        const double df = (double)x0s[i * DFIX + d] - (double)x1r[d];
         c = fma(df, df, c);
       }
     } else {
@@ -77,11 +89,32 @@ __global__ void __launch_bounds__(MAXN, 1) k_ot_assign(const float* __restrict__
     return c;
   };
 
+  // Greedy start (column reduction): v[j] = min_i c(i, j) with u = 0 is dual feasible and makes every column's cheapest edge
+  // tight; a row takes the lowest column that wants it.  Only the rows left without a column need an augmenting path.
+  double v = 0.0;
+  int want = -1;
+  if (has) {
+    double best = INF;
+    for (int i = 0; i < n; ++i) {
+      const double c = cost(i);
+      if (c < best) { best = c; want = i; }
+    }
+    v = best;
+    atomicMin(&claim[want], j);
+  }
+  __syncthreads();
+  if (has && claim[want] == j) {
+    row4col[j] = want;
+    col4row[want] = j;
+  }
+  __syncthreads();
+
   int it = 0;
   for (int cur = 0; cur < n; ++cur) {
+    if (col4row[cur] >= 0) continue;   // matched by the greedy start (uniform across the block)
     double shortest = INF;
     bool visited = false;
-    int my_row = has ? row4col[j] : -1;
+    const int my_row = has ? row4col[j] : -1;
     int i = cur, sink = -1;
     double min_val = 0.0;
     while (sink < 0) {
@@ -92,26 +125,20 @@ __global__ void __launch_bounds__(MAXN, 1) k_ot_assign(const float* __restrict__
           path[j] = i;
         }
       }
-      // block argmin over the unvisited columns
+      // block argmin over the unvisited columns: warp shuffles, one shared-memory exchange, one barrier
       double bv = (has && !visited) ? shortest : INF;
-      int bc = (has && !visited) ? j : MAXN, br = my_row;
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
-        const int oc = __shfl_xor_sync(0xffffffffu, bc, off), orow = __shfl_xor_sync(0xffffffffu, br, off);
-        if (better(ov, orow, oc, bv, br, bc)) { bv = ov; bc = oc; br = orow; }
-      }
+      int bc = (has && !visited) ? j : MAXN;
+      warp_argmin(bv, bc);
       Best* slot = wbest + (it & 1) * 32;
-      if (lane == 0) { slot[warp].val = bv; slot[warp].col = bc; slot[warp].row = br; }
+      if (lane == 0) { slot[warp].val = bv; slot[warp].col = bc; }
       __syncthreads();
-      bv = slot[0].val; bc = slot[0].col; br = slot[0].row;
-      for (int w = 1; w < nwarps; ++w) {
-        const Best o = slot[w];
-        if (better(o.val, o.row, o.col, bv, br, bc)) { bv = o.val; bc = o.col; br = o.row; }
-      }
+      bv = lane < nwarps ? slot[lane].val : INF;
+      bc = lane < nwarps ? slot[lane].col : MAXN;
+      warp_argmin(bv, bc);
       ++it;
       min_val = bv;
       if (j == bc) visited = true;
+      const int br = row4col[bc];
       if (br < 0) sink = bc; else i = br;
     }
     // dual update (uses the assignment as it was during the search)
@@ -121,7 +148,7 @@ __global__ void __launch_bounds__(MAXN, 1) k_ot_assign(const float* __restrict__
       v -= delta;
     }
     if (tid == 0) u[cur] += min_val;
-    __syncthreads();   // path[] complete, u[] updated
+    __syncthreads();   // path[] complete, u[] updated, every thread has read row4col[] for this search
     if (tid == 0) {    // augment along the path
       int jj = sink;
       while (true) {
@@ -152,7 +179,7 @@ __global__ void __launch_bounds__(MAXN, 1) k_ot_assign(const float* __restrict__
   }
 }
 
-static size_t smem_bytes(int n) { return (size_t)n * 8 + (size_t)(3 * n + (n & 1)) * 4 + 2 * 32 * sizeof(Best) + 16; }
+static size_t smem_bytes(int n, int dfix) { return (size_t)n * 8 + 64 * sizeof(Best) + (size_t)4 * n * 4 + (size_t)n * dfix * 4 + 16; }
 
 }  // namespace ot
 }  // namespace idff
@@ -166,7 +193,7 @@ extern "C" int idff_ot_assign(const float* d_x0, const float* d_x1, int32_t n, i
   if (n == 0) return IDFF_OK;
   IDFF_CHECK_ARG(d_x0 && d_x1 && d_perm, "idff_ot_assign: null pointer");
   const int threads = ((n + 31) / 32) * 32;
-  const size_t sm = ot::smem_bytes(n);
+  const size_t sm = ot::smem_bytes(n, D == 2 ? 2 : 0);
   cudaStream_t s = (cudaStream_t)stream;
   if (D == 2) ot::k_ot_assign<2><<<1, threads, sm, s>>>(d_x0, d_x1, n, D, d_perm, d_cost);
   else ot::k_ot_assign<0><<<1, threads, sm, s>>>(d_x0, d_x1, n, D, d_perm, d_cost);
