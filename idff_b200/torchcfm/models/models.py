@@ -1,51 +1,51 @@
 """The two networks of the hot path with the reference's constructor signatures, attribute names and
 state_dict keys (torchcfm/models/models.py:4-21 MLP, :23-42 MLP_Embedding), so the shipped checkpoints load.
 
-Under autograd (training) the layers run as ordinary torch modules -- training the MLP itself is outside the
-hot path built here.  Under torch.no_grad() on a CUDA tensor the forward is one launch of the B200 MLP kernel
-(idff_mlp_forward); MLP_Embedding takes that route when every row shares one time index, which is how the
-generator calls it (MD_simulation.py:501)."""
+Under autograd (training) the layers run as ordinary torch modules (or, for the 2-D MLP, inside the fused training
+kernel, whose state the parameters alias).  Under torch.no_grad() on a CUDA tensor the forward is one launch of the
+B200 MLP kernel (idff_mlp_forward); MLP_Embedding takes that route when every row shares one time index, which is how
+the generator calls it (MD_simulation.py:501)."""
 import torch
+from torch import nn
 
 from .. import _backend as B
 
 
-class MLP(torch.nn.Module):
+def _selu_stack(n_in: int, width: int, n_out: int) -> nn.Sequential:
+    """Linear-SELU x3 -> Linear; module indices 0, 2, 4, 6 hold the Linear layers (the checkpoints' `net.N.weight` keys)."""
+    sizes = [n_in, width, width, width]
+    layers = []
+    for a, b in zip(sizes[:-1], sizes[1:]):
+        layers += [nn.Linear(a, b), nn.SELU()]
+    layers.append(nn.Linear(width, n_out))
+    return nn.Sequential(*layers)
+
+
+class MLP(nn.Module):
+    """x = cat[state, t] (time_varying) -> net(x)."""
+
     def __init__(self, dim, out_dim=None, w=64, time_varying=False):
         super().__init__()
         self.time_varying = time_varying
-        if out_dim is None:
-            out_dim = dim
-        self.net = torch.nn.Sequential(
-            torch.nn.Linear(dim + (1 if time_varying else 0), w), torch.nn.SELU(),
-            torch.nn.Linear(w, w), torch.nn.SELU(),
-            torch.nn.Linear(w, w), torch.nn.SELU(),
-            torch.nn.Linear(w, out_dim))
+        self.net = _selu_stack(dim + int(bool(time_varying)), w, dim if out_dim is None else out_dim)
 
     def forward(self, x):
-        if B.use_kernel(self, x):
-            return B.mlp_forward(self, x, 0)
-        return self.net(x)
+        return B.mlp_forward(self, x, 0) if B.use_kernel(self, x) else self.net(x)
 
 
-class MLP_Embedding(torch.nn.Module):
+class MLP_Embedding(nn.Module):
+    """x = cat[state, t], ti = frame index -> net(cat[x, Embedding[ti]])."""
+
     def __init__(self, dim, out_dim=None, w=64, time_embed=100, time_varying=False):
         super().__init__()
         self.time_varying = time_varying
-        if out_dim is None:
-            out_dim = dim
-        self.time_index_embedding = torch.nn.Embedding(time_embed, w)
-        self.net = torch.nn.Sequential(
-            torch.nn.Linear(dim + w + (1 if time_varying else 0), w), torch.nn.SELU(),
-            torch.nn.Linear(w, w), torch.nn.SELU(),
-            torch.nn.Linear(w, w), torch.nn.SELU(),
-            torch.nn.Linear(w, out_dim))
+        self.time_index_embedding = nn.Embedding(time_embed, w)
+        self.net = _selu_stack(dim + w + int(bool(time_varying)), w, dim if out_dim is None else out_dim)
 
     def forward(self, x, ti):
         if B.use_kernel(self, x) and ti.numel() > 0:
-            idx = ti.reshape(-1).long()
-            first = int(idx[0])
-            if bool((idx == first).all()):
-                return B.mlp_forward(self, x, first)
-        emb = self.time_index_embedding(ti.long()).squeeze()
-        return self.net(torch.cat([x, emb], dim=-1))
+            frames = ti.reshape(-1).long()
+            f0 = int(frames[0])
+            if bool((frames == f0).all()):      # one frame for the whole batch: folded into the layer-0 bias table
+                return B.mlp_forward(self, x, f0)
+        return self.net(torch.cat([x, self.time_index_embedding(ti.long()).squeeze()], dim=-1))
