@@ -509,6 +509,21 @@ def aux_measurements(dev, pw, model, peaks):
         aux["train_step"] = tr_out
     except Exception as exc:
         aux["train_step_error"] = repr(exc)
+    # ---- PolyALA generation at the reference's shape (MD_simulation.py:197-213: 200 frames, 5 trajectories, NFE 3, dt 0.3):
+    # one launch of the chain kernel vs one fused SDE launch per frame (noise draws included in both)
+    try:
+        from idff_b200 import md as md_mod
+        from idff_b200.weights import PackedWeights as _PW
+        pwm = _PW.from_npz(np.load(os.path.join(ROOT, "tests", "golden", "weights_polyala.npz")), device=dev)
+        xi = torch.randn(5, 46, device=dev)
+        kwm = dict(sigma=0.5, gamma1=0.2, gamma2=5.0, dt=0.3, device=dev, x_init=xi)
+        s_chain = timeit(lambda: md_mod.generate_trajectories(pwm, 5, 46, 200, 3, chain=True, **kwm), reps=3, warm=1)
+        s_frame = timeit(lambda: md_mod.generate_trajectories(pwm, 5, 46, 200, 3, chain=False, **kwm), reps=2, warm=1)
+        aux["polyala_generation_T200_K5"] = {"chain_kernel_ms": s_chain * 1e3, "launch_per_frame_ms": s_frame * 1e3,
+                                             "launches": {"chain": 1, "per_frame": 200},
+                                             "particle_steps": 200 * 5 * 12}
+    except Exception as exc:
+        aux["polyala_generation_error"] = repr(exc)
     # ---- other BASELINE configs, measured briefly (reported, not the headline)
     try:
         from idff_b200.weights import PackedWeights

@@ -282,31 +282,10 @@ extern "C" int idff_sample_rk4_sweep(const idff_weights_t* w, const idff_field_p
   return tensor16_sample_rk4_sweep(w, params, n_sets, d_x0, st.data(), dts.data(), n_iv, d_out, N, stream);
 }
 
-extern "C" int idff_sde_num_steps(const float* h_ts, int32_t n_ts, float dt) {
-  IDFF_CHECK_ARG(h_ts && n_ts >= 1 && dt > 0.0f, "idff_sde_num_steps: bad argument");
-  return (int)sde_grid(h_ts, n_ts, dt).size() - 1;
-}
-
-extern "C" int idff_sample_sde(const idff_weights_t* w, const idff_field_params_t* p, const float* d_y0,
-                               const float* h_ts, int32_t n_ts, float dt, int32_t method, const float* d_I_k,
-                               const float* d_I_k0, float* d_out, int64_t N, void* stream) {
-  int rc = check_field_args(w, p, "idff_sample_sde");
-  if (rc) return rc;
-  IDFF_CHECK_ARG(p->variant == IDFF_FIELD_MD, "idff_sample_sde: only the MD field (SDE_cal) has a diffusion term");
-  IDFF_CHECK_ARG(h_ts && n_ts >= 1 && dt > 0.0f, "idff_sample_sde: bad ts/dt");
-  IDFF_CHECK_ARG(method == 0 || method == 1, "idff_sample_sde: method %d (0 srk, 1 euler)", method);
-  for (int i = 1; i < n_ts; ++i) IDFF_CHECK_ARG(h_ts[i] >= h_ts[i - 1], "idff_sample_sde: ts must be non-decreasing");
-  if (N == 0) return IDFF_OK;
-  IDFF_CHECK_ARG(N > 0 && d_y0 && d_out, "idff_sample_sde: null pointer or negative N");
-  const std::vector<float> grid = sde_grid(h_ts, n_ts, dt);
+// torchsde's fixed-step grid, the drift stage scalars, g values and output interpolation weights of one sdeint call
+static void build_sde_table(const idff_field_params_t* p, const float* h_ts, int n_ts, int method, const std::vector<float>& grid,
+                            SdeTable& tab) {
   const int n_steps = (int)grid.size() - 1;
-  IDFF_CHECK_ARG(n_steps == 0 || d_I_k, "idff_sample_sde: Brownian increments d_I_k are required");
-  IDFF_CHECK_ARG(n_steps == 0 || method == 1 || d_I_k0, "idff_sample_sde: srk needs the space-time Levy term d_I_k0");
-  if (n_steps > kMaxSdeSteps || n_ts - 1 > kMaxSdeEmit) {
-    set_error("idff_sample_sde: %d steps / %d outputs exceed the per-call limits (%d / %d)", n_steps, n_ts - 1, kMaxSdeSteps, kMaxSdeEmit);
-    return IDFF_EUNSUPPORTED;
-  }
-  static thread_local SdeTable tab;
   memset(&tab, 0, sizeof(tab));
   tab.n_steps = n_steps;
   tab.method = method;
@@ -356,6 +335,35 @@ extern "C" int idff_sample_sde(const idff_weights_t* w, const idff_field_params_
     ++ne;
   }
   tab.n_emit = ne;
+}
+
+extern "C" int idff_sde_num_steps(const float* h_ts, int32_t n_ts, float dt) {
+  IDFF_CHECK_ARG(h_ts && n_ts >= 1 && dt > 0.0f, "idff_sde_num_steps: bad argument");
+  return (int)sde_grid(h_ts, n_ts, dt).size() - 1;
+}
+
+extern "C" int idff_sample_sde(const idff_weights_t* w, const idff_field_params_t* p, const float* d_y0,
+                               const float* h_ts, int32_t n_ts, float dt, int32_t method, const float* d_I_k,
+                               const float* d_I_k0, float* d_out, int64_t N, void* stream) {
+  int rc = check_field_args(w, p, "idff_sample_sde");
+  if (rc) return rc;
+  IDFF_CHECK_ARG(p->variant == IDFF_FIELD_MD, "idff_sample_sde: only the MD field (SDE_cal) has a diffusion term");
+  IDFF_CHECK_ARG(h_ts && n_ts >= 1 && dt > 0.0f, "idff_sample_sde: bad ts/dt");
+  IDFF_CHECK_ARG(method == 0 || method == 1, "idff_sample_sde: method %d (0 srk, 1 euler)", method);
+  for (int i = 1; i < n_ts; ++i) IDFF_CHECK_ARG(h_ts[i] >= h_ts[i - 1], "idff_sample_sde: ts must be non-decreasing");
+  if (N == 0) return IDFF_OK;
+  IDFF_CHECK_ARG(N > 0 && d_y0 && d_out, "idff_sample_sde: null pointer or negative N");
+  const std::vector<float> grid = sde_grid(h_ts, n_ts, dt);
+  const int n_steps = (int)grid.size() - 1;
+  IDFF_CHECK_ARG(n_steps == 0 || d_I_k, "idff_sample_sde: Brownian increments d_I_k are required");
+  IDFF_CHECK_ARG(n_steps == 0 || method == 1 || d_I_k0, "idff_sample_sde: srk needs the space-time Levy term d_I_k0");
+  if (n_steps > kMaxSdeSteps || n_ts - 1 > kMaxSdeEmit) {
+    set_error("idff_sample_sde: %d steps / %d outputs exceed the per-call limits (%d / %d)", n_steps, n_ts - 1, kMaxSdeSteps, kMaxSdeEmit);
+    return IDFF_EUNSUPPORTED;
+  }
+  static thread_local SdeTable tab;
+  build_sde_table(p, h_ts, n_ts, method, grid, tab);
+  const int ne = tab.n_emit;
   DeviceGuard g(w->device);
   // outputs requested at ts[0] itself (emit_step == -1) are y0
   for (int e = 0; e < ne; ++e)
@@ -371,4 +379,52 @@ extern "C" int idff_sample_sde(const idff_weights_t* w, const idff_field_params_
     return fused_sample_sde(w, p, tab, d_y0, d_I_k, d_I_k0, d_out, N, stream);
   }
   return generic_sample_sde(w, p, tab, d_y0, d_I_k, d_I_k0, d_out, N, stream);
+}
+
+// ---- the autoregressive PolyALA generator in one launch ------------------------------------------------
+namespace idff {
+bool md_chain_supports(const idff_weights_t* w, const idff_field_params_t* p, int64_t K);
+int md_chain_run(const idff_weights_t* w, const idff_field_params_t* p, int n_frames, const SdeTable& tab0, const Stage* stages,
+                 const float* d_x_init, const float* d_I_k, const float* d_I_k0, float* d_y_hat, int64_t K, void* stream);
+}
+
+extern "C" int idff_md_generate(const idff_weights_t* w, const idff_field_params_t* p, int32_t n_frames, const float* d_x_init,
+                                const float* h_ts, int32_t n_ts, float dt, int32_t method, const float* d_I_k,
+                                const float* d_I_k0, float* d_y_hat, int64_t K, void* stream) {
+  int rc = check_field_args(w, p, "idff_md_generate");
+  if (rc) return rc;
+  IDFF_CHECK_ARG(p->variant == IDFF_FIELD_MD, "idff_md_generate: the generator integrates SDE_cal (variant IDFF_FIELD_MD)");
+  IDFF_CHECK_ARG(n_frames >= 1 && n_frames <= w->v.n_tidx, "idff_md_generate: %d frames, the embedding has %d rows", n_frames,
+                 w->v.n_tidx);
+  IDFF_CHECK_ARG(h_ts && n_ts >= 2 && dt > 0.0f, "idff_md_generate: bad ts/dt");
+  IDFF_CHECK_ARG(method == 0 || method == 1, "idff_md_generate: method %d (0 srk, 1 euler)", method);
+  for (int i = 1; i < n_ts; ++i) IDFF_CHECK_ARG(h_ts[i] >= h_ts[i - 1], "idff_md_generate: ts must be non-decreasing");
+  IDFF_CHECK_ARG(h_ts[n_ts - 1] > h_ts[0], "idff_md_generate: empty time span");
+  if (K == 0) return IDFF_OK;
+  IDFF_CHECK_ARG(K > 0 && d_x_init && d_y_hat && d_I_k && (method == 1 || d_I_k0), "idff_md_generate: null pointer or negative K");
+  const std::vector<float> grid = sde_grid(h_ts, n_ts, dt);
+  const int n_steps = (int)grid.size() - 1;
+  if (n_steps > kMaxSdeSteps || n_ts - 1 > kMaxSdeEmit) {
+    set_error("idff_md_generate: %d steps / %d outputs exceed the per-call limits (%d / %d)", n_steps, n_ts - 1, kMaxSdeSteps, kMaxSdeEmit);
+    return IDFF_EUNSUPPORTED;
+  }
+  if (!md_chain_supports(w, p, K)) {
+    set_error("idff_md_generate: needs a width-128 network with at most 64 state dimensions and at most 592 trajectories; "
+              "use one idff_sample_sde call per frame otherwise");
+    return IDFF_EUNSUPPORTED;
+  }
+  // frame f: init_ind = f, gamma2 / (1 + f)   (MD_simulation.py:201); everything else is shared by the frames
+  static thread_local SdeTable tab0, tabf;
+  std::vector<Stage> stages((size_t)n_frames * n_steps * 3);
+  for (int f = 0; f < n_frames; ++f) {
+    idff_field_params_t q = *p;
+    q.t_idx = f;
+    q.gamma[1] = p->gamma[1] / (double)(1 + f);
+    SdeTable& t = f == 0 ? tab0 : tabf;
+    build_sde_table(&q, h_ts, n_ts, method, grid, t);
+    for (int s = 0; s < n_steps; ++s)
+      for (int g = 0; g < 3; ++g) stages[((size_t)f * n_steps + s) * 3 + g] = t.st[s][g];
+  }
+  DeviceGuard guard(w->device);
+  return md_chain_run(w, p, n_frames, tab0, stages.data(), d_x_init, d_I_k, d_I_k0, d_y_hat, K, stream);
 }

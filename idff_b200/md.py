@@ -1,21 +1,77 @@
 """PolyALA autoregressive generation (TrajectoryGenerator.generate_trajectories / generate_onestep,
 timeseris_example/MD_simulation.py:197-230): T sequential SDE solves, each starting from the previous frame, each
-with its own embedding row (init_ind = t_idx) and gamma2/(1+t_idx).  Every frame is ONE launch of the fused SDE
-sampler over all trajectories; frames never leave the device (the reference round-trips through numpy every frame).
-`GraphedGenerator` captures the whole T-frame chain (noise draws included) once as a CUDA graph: at the reference's 5
-trajectories the chain is T launch-bound solves, and a replay is one `cudaGraphLaunch`."""
+with its own embedding row (init_ind = t_idx) and gamma2/(1+t_idx).
+
+`generate_trajectories` runs the whole chain in ONE launch of the chain kernel (`idff_md_generate`: one CTA per 4
+trajectories, network resident in shared memory) when it serves the shape -- the latency regime of the reference, which
+generates 5 trajectories -- and otherwise one launch of the fused SDE sampler per frame over all trajectories; frames never
+leave the device (the reference round-trips through numpy every frame).  `GraphedGenerator` captures the per-frame path
+(noise draws included) once as a CUDA graph."""
 from __future__ import annotations
 
+import ctypes as C
+
+import numpy as np
 import torch
 
-from . import fields, sampler
+from . import _lib, fields, sampler
+
+
+def chain_serves(model, num_trajectories, data_dim, device) -> bool:
+    """Does the one-launch chain kernel serve this generation? (hidden width 128, D <= 63, at most 592 trajectories)"""
+    pw = fields.SDE_cal(model, input_dim=data_dim, device=device)._packed(torch.device(device))
+    return pw.dims[1] == 128 and data_dim <= 63 and pw.dims[0] - pw.emb_dim == data_dim + 1 and 1 <= num_trajectories <= 592
+
+
+def generate_trajectories_chain(model, num_trajectories, data_dim, max_length, nfe, sigma, gamma1=1.0, gamma2=10.0, dt=0.3,
+                                device="cuda", x_init=None, generator=None, method="srk", noise=None):
+    """generate_trajectories (MD_simulation.py:197-213) as ONE kernel launch (idff_md_generate).
+    noise: optional (I_k, I_k0) tensors of shape (max_length, n_steps, K, D); drawn on the device otherwise."""
+    device = torch.device(device)
+    K, D, T = int(num_trajectories), int(data_dim), int(max_length)
+    ts = torch.linspace(0, 1, int(nfe)).numpy().astype(np.float32)
+    n_steps = sampler.sde_num_steps(ts, dt)
+    if noise is None:
+        I_k, I_k0 = sampler.brownian_increments(n_steps, ts, dt, (T, K, D), device, generator)   # (n_steps, T, K, D)
+        I_k, I_k0 = I_k.transpose(0, 1).contiguous(), I_k0.transpose(0, 1).contiguous()
+    else:
+        I_k, I_k0 = noise
+        I_k = I_k.contiguous()
+        I_k0 = None if I_k0 is None else I_k0.contiguous()
+    if tuple(I_k.shape) != (T, n_steps, K, D):
+        raise _lib.IdffError(f"I_k must be {(T, n_steps, K, D)}, got {tuple(I_k.shape)}")
+    if x_init is None:
+        x_init = torch.randn((K, D), device=device, generator=generator)
+    _lib.require_cuda(x_init, "x_init")
+    x_init = x_init.detach().contiguous()
+    sde = fields.SDE_cal(model, input_dim=D, gamma1=gamma1, gamma2=gamma2, init_ind=0, max_length=T, dt=dt, sigma=sigma,
+                         device=device)
+    pw = sde._packed(device)
+    p = sde.field_params(D)
+    y_hat = torch.empty((T, K, D), device=device, dtype=torch.float32)
+    meth = {"srk": 0, "euler": 1}[method]
+    _lib.check(_lib.lib().idff_md_generate(pw.handle, C.byref(p), T, _lib.ptr(x_init), ts.ctypes.data_as(C.c_void_p), len(ts),
+                                           float(dt), meth, _lib.ptr(I_k), _lib.ptr(I_k0), _lib.ptr(y_hat), K,
+                                           _lib.stream_of(x_init)), "idff_md_generate")
+    return y_hat
 
 
 def generate_trajectories(model, num_trajectories, data_dim, max_length, nfe, sigma, gamma1=1.0, gamma2=10.0, dt=0.3,
-                          device="cuda", x_init=None, generator=None, method="srk", noise=None):
+                          device="cuda", x_init=None, generator=None, method="srk", noise=None, chain=None):
     """-> y_hat (max_length, num_trajectories, data_dim) on `device`.
-    noise: optional callable (t_idx, n_steps) -> (I_k, I_k0) to inject Brownian increments (parity tests)."""
+    noise: optional callable (t_idx, n_steps) -> (I_k, I_k0) to inject Brownian increments (parity tests).
+    chain: True / False forces / forbids the one-launch chain kernel; None = use it where it serves the shape."""
     device = torch.device(device)
+    if chain is None:
+        chain = chain_serves(model, num_trajectories, data_dim, device)
+    if chain:
+        nz = None
+        if noise is not None:
+            n_steps = sampler.sde_num_steps(torch.linspace(0, 1, int(nfe)), dt)
+            pairs = [noise(t_idx, n_steps) for t_idx in range(max_length)]
+            nz = (torch.stack([a for a, _ in pairs]), None if pairs[0][1] is None else torch.stack([b for _, b in pairs]))
+        return generate_trajectories_chain(model, num_trajectories, data_dim, max_length, nfe, sigma, gamma1, gamma2, dt,
+                                           device, x_init, generator, method, nz)
     y_hat = torch.empty((max_length, num_trajectories, data_dim), device=device, dtype=torch.float32)
     ts = torch.linspace(0, 1, int(nfe))
     n_steps = sampler.sde_num_steps(ts, dt)
@@ -45,7 +101,7 @@ class GraphedGenerator:
         self.device = torch.device(device)
         self.x_init = torch.zeros((num_trajectories, data_dim), device=self.device, dtype=torch.float32)
         self._noise = noise
-        kw = dict(device=self.device, x_init=self.x_init, method=method,
+        kw = dict(device=self.device, x_init=self.x_init, method=method, chain=False,
                   noise=(lambda t_idx, n: (noise[0][t_idx], noise[1][t_idx])) if noise is not None else None)
         args = (model, num_trajectories, data_dim, max_length, nfe, sigma, gamma1, gamma2, dt)
         side = torch.cuda.Stream(device=self.device)

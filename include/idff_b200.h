@@ -211,6 +211,18 @@ int idff_train_flow_steps(float* d_state, const float* d_x0, const float* d_x1, 
  * total cost sum_i |x0[i] - x1[perm[i]]|^2 in fp64.  Exact shortest-augmenting-path assignment in fp64, one launch. */
 int idff_ot_assign(const float* d_x0, const float* d_x1, int32_t n, int32_t D, int64_t* d_perm, double* d_cost, void* stream);
 
+/* ---- TrajectoryGenerator.generate_trajectories, timeseris_example/MD_simulation.py:197-213 -- n_frames
+ * sequential solves  x1 = sdeint(SDE_cal(model, gamma2 = gamma2 / (1 + f), init_ind = f, dt, ...), x1, ts, dt)[-1],  f = 0 ..
+ * n_frames - 1, each starting from the previous frame's result -- in ONE launch: one CTA owns 4 trajectories for the whole
+ * chain, the network stays in shared memory.  p: variant IDFF_FIELD_MD with the BASE gamma2 in gamma[1] (divided by 1 + f per
+ * frame here, as :201 does) and end_div = dt; t_idx is ignored (frame f uses embedding row f).  d_x_init [K][D];
+ * d_I_k, d_I_k0 [n_frames][n_steps][K][D] Brownian increments per frame (n_steps = idff_sde_num_steps; d_I_k0 may be NULL for
+ * euler); d_y_hat [n_frames][K][D] = traj[-1] of every frame.  Serves hidden width 128, D <= 63, K <= 592 (the latency regime:
+ * the reference generates 5 trajectories); IDFF_EUNSUPPORTED otherwise -- use one idff_sample_sde call per frame there. */
+int idff_md_generate(const idff_weights_t* w, const idff_field_params_t* p, int32_t n_frames, const float* d_x_init,
+                     const float* h_ts, int32_t n_ts, float dt, int32_t method, const float* d_I_k, const float* d_I_k0,
+                     float* d_y_hat, int64_t K, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

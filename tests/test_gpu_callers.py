@@ -7,7 +7,7 @@ import torch
 import idff_oracle as O
 from conftest import golden_layers, load_golden
 from gpu_common import assert_field_close, packed
-from idff_b200 import md, sweep
+from idff_b200 import _lib, md, sweep
 
 pytestmark = pytest.mark.gpu
 
@@ -61,13 +61,16 @@ def test_md_autoregressive_generation_vs_oracle(cuda_device):
         x1 = O.sdeint_srk(sde, x1, ts, dt, noises[t_idx][0], noises[t_idx][1])[-1]
         ref.append(x1)
     ref = torch.stack(ref).numpy()
-    got = md.generate_trajectories(packed("polyala", cuda_device), K, D, T, NFE, sigma=0.5, gamma1=0.2, gamma2=5.0, dt=dt,
-                                   device=cuda_device, x_init=x_init.to(cuda_device),
-                                   noise=lambda t_idx, n: (noises[t_idx][0].to(cuda_device), noises[t_idx][1].to(cuda_device)))
-    assert got.shape == (T, K, D)
-    for t_idx in range(T):
-        # each frame compounds the previous frames' round-off: 1e-4 of the frame's scale
-        assert_field_close(got[t_idx].cpu().numpy(), ref[t_idx], 1e-4, f"frame {t_idx}")
+    for chain in (True, False):     # the one-launch chain kernel (idff_md_generate) and the launch-per-frame path
+        before = _lib.launch_count()
+        got = md.generate_trajectories(packed("polyala", cuda_device), K, D, T, NFE, sigma=0.5, gamma1=0.2, gamma2=5.0, dt=dt,
+                                       device=cuda_device, x_init=x_init.to(cuda_device), chain=chain,
+                                       noise=lambda t_idx, n: (noises[t_idx][0].to(cuda_device), noises[t_idx][1].to(cuda_device)))
+        assert _lib.launch_count() - before == (1 if chain else T)
+        assert got.shape == (T, K, D)
+        for t_idx in range(T):
+            # each frame compounds the previous frames' round-off: 1e-4 of the frame's scale
+            assert_field_close(got[t_idx].cpu().numpy(), ref[t_idx], 1e-4, f"frame {t_idx} chain={chain}")
     m = md.compute_metrics(got, torch.tensor(ref.mean(1)))          # MD_simulation.py:275-295 against a stand-in data set
     mo = O.md_compute_metrics(ref, ref.mean(1))
     for k in mo:
@@ -143,12 +146,12 @@ def test_md_generation_as_cuda_graph(cuda_device):
     ik0 = torch.randn(T, ns, K, D, device=cuda_device, generator=g) * 0.1
     x_init = torch.randn(K, D, device=cuda_device, generator=g)
     eager = md.generate_trajectories(pw, K, D, T, NFE, sigma=0.5, gamma1=0.2, gamma2=5.0, dt=dt, device=cuda_device,
-                                     x_init=x_init, noise=lambda t_idx, n: (ik[t_idx], ik0[t_idx]))
+                                     x_init=x_init, chain=False, noise=lambda t_idx, n: (ik[t_idx], ik0[t_idx]))
     gen = md.GraphedGenerator(pw, K, D, T, NFE, sigma=0.5, gamma1=0.2, gamma2=5.0, dt=dt, device=cuda_device, noise=(ik, ik0))
     assert torch.isfinite(eager).all()
     assert torch.equal(gen.generate(x_init), eager)
     assert torch.equal(gen.generate(x_init * 0.5), md.generate_trajectories(
-        pw, K, D, T, NFE, sigma=0.5, gamma1=0.2, gamma2=5.0, dt=dt, device=cuda_device, x_init=x_init * 0.5,
+        pw, K, D, T, NFE, sigma=0.5, gamma1=0.2, gamma2=5.0, dt=dt, device=cuda_device, x_init=x_init * 0.5, chain=False,
         noise=lambda t_idx, n: (ik[t_idx], ik0[t_idx])))
     fresh = md.GraphedGenerator(pw, K, D, T, NFE, sigma=0.5, gamma1=0.2, gamma2=5.0, dt=dt, device=cuda_device)
     a = fresh.generate(x_init).clone()
@@ -161,10 +164,64 @@ def test_md_generation_as_cuda_graph(cuda_device):
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     for _ in range(5):
-        md.generate_trajectories(pw, K, D, T, NFE, sigma=0.5, gamma1=0.2, gamma2=5.0, dt=dt, device=cuda_device, x_init=x_init)
+        md.generate_trajectories(pw, K, D, T, NFE, sigma=0.5, gamma1=0.2, gamma2=5.0, dt=dt, device=cuda_device, x_init=x_init,
+                                 chain=False)
     torch.cuda.synchronize()
     t2 = time.perf_counter()
     print(f"PolyALA chain, {T} frames x {K} trajectories: graph {1e3 * (t1 - t0) / 5:.2f} ms, eager {1e3 * (t2 - t1) / 5:.2f} ms")
+
+
+def test_md_chain_kernel_full_length(cuda_device):
+    """The reference's generation shape (T = 200 frames, 5 trajectories, NFE 3, dt 0.3) in ONE launch against the launch-per-frame
+    path on the same injected noise: the two differ only in summation order, and the frame-to-frame map is contractive enough
+    that the difference stays at round-off level over the whole chain.  Also K = 9 (three CTAs, ragged) and euler."""
+    import time
+
+    from idff_b200 import sampler as sampler_mod
+    pw = packed("polyala", cuda_device)
+    D, T, NFE, dt = 46, 200, 3, 0.3
+    g = torch.Generator(device=cuda_device).manual_seed(11)
+    n_steps = 4
+    for K, method in ((5, "srk"), (9, "srk"), (5, "euler")):
+        x_init = torch.randn(K, D, device=cuda_device, generator=g)        # MD_simulation.py:203
+        ik = torch.randn(T, n_steps, K, D, device=cuda_device, generator=g) * 0.5
+        ik0 = torch.randn(T, n_steps, K, D, device=cuda_device, generator=g) * 0.05
+        kw = dict(sigma=0.5, gamma1=0.2, gamma2=5.0, dt=dt, device=cuda_device, x_init=x_init, method=method,
+                  noise=lambda t_idx, n: (ik[t_idx], ik0[t_idx]))
+        before = _lib.launch_count()
+        one = md.generate_trajectories(pw, K, D, T, NFE, chain=True, **kw)
+        assert _lib.launch_count() - before == 1
+        per = md.generate_trajectories(pw, K, D, T, NFE, chain=False, **kw)
+        assert torch.isfinite(one).all()
+        d = (one - per).abs()
+        scale = per.abs().max().item()
+        print(f"K={K} {method}: chain vs per-frame over {T} frames: median|d| {d.median().item():.2e} max {d.max().item():.2e} (scale {scale:.1f})")
+        assert d.median().item() <= 1e-4 * scale and d.max().item() <= 1e-2 * scale
+    # many CTAs (K = 301: 76 CTAs, the last one ragged), short chain, drawn noise of the right law
+    K, Ts = 301, 8
+    x_init = torch.randn(K, D, device=cuda_device, generator=g)
+    ik, ik0 = sampler_mod.brownian_increments(n_steps, torch.linspace(0, 1, NFE), dt, (Ts, K, D), cuda_device, g)
+    ik, ik0 = ik.transpose(0, 1).contiguous(), ik0.transpose(0, 1).contiguous()
+    kw = dict(sigma=0.5, gamma1=0.2, gamma2=5.0, dt=dt, device=cuda_device, x_init=x_init,
+              noise=lambda t_idx, n: (ik[t_idx], ik0[t_idx]))
+    one = md.generate_trajectories(pw, K, D, Ts, NFE, chain=True, **kw)
+    per = md.generate_trajectories(pw, K, D, Ts, NFE, chain=False, **kw)
+    assert torch.isfinite(one).all() and (one - per).abs().max().item() <= 1e-4 * per.abs().max().item()
+    x_init = torch.randn(5, D, device=cuda_device, generator=g)
+    md.generate_trajectories(pw, 5, D, T, NFE, sigma=0.5, gamma1=0.2, gamma2=5.0, dt=dt, device=cuda_device, x_init=x_init)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        md.generate_trajectories(pw, 5, D, T, NFE, sigma=0.5, gamma1=0.2, gamma2=5.0, dt=dt, device=cuda_device, x_init=x_init)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    md.generate_trajectories(pw, 5, D, T, NFE, sigma=0.5, gamma1=0.2, gamma2=5.0, dt=dt, device=cuda_device, x_init=x_init, chain=False)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    print(f"PolyALA generation, 200 frames x 5 trajectories: chain kernel {1e3 * (t1 - t0) / 3:.1f} ms (incl. noise draws), "
+          f"launch per frame {1e3 * (t2 - t1):.1f} ms")
+    with pytest.raises(_lib.IdffError):
+        md.generate_trajectories(pw, 1000, D, 4, NFE, sigma=0.5, dt=dt, device=cuda_device, chain=True)
 
 
 def test_md_compute_metrics_matches_reference_golden(cuda_device):
