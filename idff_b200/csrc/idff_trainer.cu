@@ -754,6 +754,8 @@ extern "C" int idff_train_flow_steps(float* d_state, const float* d_x0, const fl
                                      const idff_adamw_t* opt, int64_t steps_done, float* d_loss, float* d_gnorm,
                                      float* d_grad_dump, void* stream) {
   IDFF_CHECK_ARG(d_state && (reinterpret_cast<uintptr_t>(d_state) & 15) == 0, "idff_train_flow_steps: state must be a 16-byte aligned device pointer");
+  IDFF_CHECK_ARG(n_steps >= 0 && n_steps <= (1 << 20), "idff_train_flow_steps: n_steps %d outside [0, 2^20]", n_steps);
+  if (n_steps == 0) return IDFF_OK;
   IDFF_CHECK_ARG(d_x0 && d_x1 && d_t && opt, "idff_train_flow_steps: null pointer");
   IDFF_CHECK_ARG(((reinterpret_cast<uintptr_t>(d_x0) | reinterpret_cast<uintptr_t>(d_x1) | reinterpret_cast<uintptr_t>(d_eps)) & 7) == 0,
                  "idff_train_flow_steps: x0, x1, eps must be 8-byte aligned");

@@ -22,6 +22,9 @@ def ot_assign(x0: torch.Tensor, x1: torch.Tensor, return_cost: bool = False):
     _lib.require_cuda(x1, "x1")
     if x0.shape[0] != x1.shape[0]:
         raise _lib.IdffError("ot_assign needs equal batch sizes (the reference's uniform-marginal minibatch plan)")
+    if x0.shape[0] == 0:
+        return (torch.empty(0, dtype=torch.int64, device=x0.device), torch.zeros((), dtype=torch.float64, device=x0.device)) \
+            if return_cost else torch.empty(0, dtype=torch.int64, device=x0.device)
     a = x0.detach().reshape(x0.shape[0], -1).contiguous()
     b = x1.detach().reshape(x1.shape[0], -1).contiguous()
     if a.shape[1] != b.shape[1]:

@@ -288,3 +288,39 @@ def test_order3_sweep_batched_on_layered_engine(cuda_device):
     t2 = time.perf_counter()
     print(f"125-tuple order-3 sweep, 2048 particles, nfe 2: batched {1e3 * (t1 - t0):.2f} ms, per tuple {1e3 * (t2 - t1):.2f} ms")
     assert (t1 - t0) < (t2 - t1)
+
+
+def test_new_entry_points_edge_cases(cuda_device):
+    """Empty and degenerate inputs of the round's later entry points: zero steps / rows are no-ops, bad shapes raise."""
+    import ctypes as C
+
+    from idff_b200 import train
+    from idff_b200.torchcfm import optimal_transport as ot
+    from idff_b200.torchcfm.models.models import MLP
+    dev = cuda_device
+    L = _lib.lib()
+    # idff_ot_assign: n = 0 is a no-op; D mismatch and unequal batches raise
+    assert ot.ot_assign(torch.zeros(0, 2, device=dev), torch.zeros(0, 2, device=dev)).numel() == 0
+    with pytest.raises(_lib.IdffError):
+        ot.ot_assign(torch.zeros(4, 2, device=dev), torch.zeros(5, 2, device=dev))
+    with pytest.raises(_lib.IdffError):
+        ot.ot_assign(torch.zeros(4, 2, device=dev), torch.zeros(4, 3, device=dev))
+    # idff_train_flow_steps: zero steps leave the state untouched
+    tr = train.FusedFlowTrainer(MLP(dim=2, w=256, time_varying=True).to(dev), batch_size=8)
+    before = tr.state.clone()
+    out = tr.steps(torch.zeros(0, 8, 2, device=dev), torch.zeros(0, 8, 2, device=dev), torch.zeros(0, 8, device=dev))
+    assert out.numel() == 0 and torch.equal(before, tr.state) and tr.steps_done == 0
+    # idff_md_generate: K = 0 is a no-op; more frames than embedding rows is an error
+    pw = packed("polyala", dev)
+    y = md.generate_trajectories_chain(pw, 0, 46, 4, 3, sigma=0.5, dt=0.3, device=dev, x_init=torch.zeros(0, 46, device=dev),
+                                       noise=(torch.zeros(4, 4, 0, 46, device=dev), torch.zeros(4, 4, 0, 46, device=dev)))
+    assert tuple(y.shape) == (4, 0, 46)
+    with pytest.raises(_lib.IdffError):
+        md.generate_trajectories_chain(pw, 2, 46, 201, 3, sigma=0.5, dt=0.3, device=dev)
+    # the sweep entry point with a single set and with N = 0
+    from idff_b200 import fields, sampler
+    m3 = fields.CustomNetModelOrder3(packed("checkerboard", dev), 0.2, 0.2, 0.2, 0.2)
+    x0 = torch.randn(2048, 2, device=dev)
+    ts = torch.linspace(0, 1, 3)
+    assert torch.equal(sampler.sample_rk4_sweep([m3], x0, ts)[0], sampler.sample_rk4(m3, x0, ts))
+    assert sampler.sample_rk4_sweep([m3, m3], x0[:0], ts).shape == (2, 0, 2)
