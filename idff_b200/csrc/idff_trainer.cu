@@ -283,10 +283,14 @@ __device__ void phase_rows(const Args& a, int s, float* smem, int grp, uint32_t 
     if (CL == 1) {
       csync();
     } else {
-      __syncwarp();
-      if (lane == 0) { mbar_arrive_cluster(s32(actbar)); mbar_arrive_cluster(peer_bar); }
-      mbar_wait_cluster(actbar, aph);
+      csync();   // every local and remote write of this CTA's threads is ordered before thread 0's release
+      if (tid == 0) {
+        mbar_arrive_cluster(s32(actbar));
+        mbar_arrive_cluster(peer_bar);
+        mbar_wait_cluster(actbar, aph);   // one poller per CTA: 512 spinning threads slow the hand-over down
+      }
       aph ^= 1;
+      csync();
     }
   };
 
@@ -523,7 +527,7 @@ __global__ void __launch_bounds__(NT, 1) k_train_flow(const Args a) {
   const bool row_cta = grp < a.B / R;
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], NC / 32); }
-    mbar_init(&actbar[0], 2 * (NC / 32));   // pair: one arrival per consumer warp of both CTAs per layer
+    mbar_init(&actbar[0], 2);   // pair: one arrival per CTA per layer
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (row_cta && tid < R) load_raw(a, 0, tid, grp * R, R, smem + mRAW);
