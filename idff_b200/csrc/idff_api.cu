@@ -384,6 +384,7 @@ extern "C" int idff_sample_sde(const idff_weights_t* w, const idff_field_params_
 // ---- the autoregressive PolyALA generator in one launch ------------------------------------------------
 namespace idff {
 bool md_chain_supports(const idff_weights_t* w, const idff_field_params_t* p, int64_t K);
+void md_chain_set_fma(int on);
 int md_chain_run(const idff_weights_t* w, const idff_field_params_t* p, int n_frames, const SdeTable& tab0, const Stage* stages,
                  const float* d_x_init, const float* d_I_k, const float* d_I_k0, float* d_y_hat, int64_t K, void* stream);
 }
@@ -427,4 +428,9 @@ extern "C" int idff_md_generate(const idff_weights_t* w, const idff_field_params
   }
   DeviceGuard guard(w->device);
   return md_chain_run(w, p, n_frames, tab0, stages.data(), d_x_init, d_I_k, d_I_k0, d_y_hat, K, stream);
+}
+
+extern "C" int idff_debug_md_chain_fma(int32_t on) {
+  md_chain_set_fma(on);
+  return IDFF_OK;
 }

@@ -5,11 +5,12 @@
 // of 12 drift evaluations each at 5 trajectories: pure latency.  The throughput kernel (idff_sampler_fused.cu) needs 0.5 ms per
 // frame whatever the trajectory count, because one warp owns a particle group for the whole solve.  Here one CTA owns 4
 // trajectories for the whole CHAIN and all 512 threads cooperate on every layer:
-//   * the network lives in shared memory for the whole launch (W1, W2 as stored, rows padded to 129 floats so that both the
-//     forward product (thread = output unit, walks its row) and the reverse product (thread = input unit, walks a column) are
-//     bank-conflict free from ONE copy; W0^T and W3 padded likewise): 220 KB, loaded once;
-//   * a layer pass is a skinny GEMM with thread = hidden unit, the K sum split over the four quarters of the CTA; Taylor jets and
-//     the reverse sweep as in idff_field_generic.cuh (the SELU derivative data stays in the registers of the unit's thread);
+//   * the network lives in shared memory for the whole launch (W1, W2 once, as stored, with a padded row pitch so that the
+//     forward product and the reverse product -- the transposed read of the same copy -- are (nearly) bank-conflict free;
+//     W0^T and W3 likewise): 220 KB, loaded once;
+//   * a layer pass is a skinny GEMM, 128 units x 8 columns (4 trajectories x 2 jets): one N = 8 tile of mma.sync.m16n8k8 with
+//     the 3 x tf32 split (default, eval_mma), or fp32 FMAs with thread = hidden unit (eval, diagnostic); Taylor jets and the
+//     reverse sweep as in idff_field_generic.cuh (the SELU derivative data stays in the registers of the unit's thread);
 //   * the SRK / Euler update, the per-frame layer-0 bias (folded embedding row) and stage scalars (gamma2 / (1 + frame)) and the
 //     hand-over of frame f's result to frame f + 1 all happen inside the kernel.
 #include "idff_field_generic.cuh"
@@ -19,7 +20,8 @@ void jets_needed(const idff_field_params_t& p, int* nj, int* reverse);
 
 namespace chain {
 
-constexpr int W = 128, LD = 129, PB = 4, NT = 512, KS = NT / W, DMAX = 64;   // KS: K-slices of a layer pass
+constexpr int W = 128, LD = 129, LDM = 132, PB = 4, NT = 512, KS = NT / W, DMAX = 64;   // KS: K-slices of a layer pass (FMA path)
+// LD / LDM: shared-memory row pitch of the weight matrices for the FMA path (bank = row + col) / the mma.sync path (bank = 4 row + col)
 
 struct Args {
   int n_frames, n_steps, method, D, din, din_pad, dout, reverse;
@@ -37,17 +39,19 @@ struct Smem {
   Stage* st;
 };
 constexpr int kStateFloats = PB * DMAX;
-__host__ __device__ inline size_t smem_floats(int din_pad, int dout) {
-  return 2 * W * LD + (size_t)(din_pad * LD + 3) / 4 * 4 + (size_t)(dout * LD + 3) / 4 * 4 + 4 * W + DMAX + (2 + KS - 1) * W * 2 * PB + 2 * NT + 8 * kStateFloats;
+// rows0 / rows3: rows of the W0^T / W3 images (the mma.sync path rounds them up to 16 and zero-fills); ld: row pitch
+__host__ __device__ inline size_t smem_floats(int rows0, int rows3, int ld) {
+  return 2 * W * ld + (size_t)(rows0 * ld + 3) / 4 * 4 + (size_t)(rows3 * ld + 3) / 4 * 4 + 4 * W + DMAX +
+         (2 + KS - 1) * W * 2 * PB + 2 * NT + 8 * kStateFloats;
 }
-inline size_t smem_bytes(int din_pad, int dout) { return smem_floats(din_pad, dout) * 4 + kMaxSdeSteps * 3 * sizeof(Stage); }
+inline size_t smem_bytes(int rows0, int rows3, int ld) { return smem_floats(rows0, rows3, ld) * 4 + kMaxSdeSteps * 3 * sizeof(Stage); }
 
-__device__ __forceinline__ Smem carve(float* m, int din_pad, int dout) {
+__device__ __forceinline__ Smem carve(float* m, int rows0, int rows3, int ld) {
   Smem s;
-  s.W1 = m; m += W * LD;
-  s.W2 = m; m += W * LD;
-  s.wt0 = m; m += (din_pad * LD + 3) / 4 * 4;   // keep every region 16-byte aligned
-  s.w3 = m; m += (dout * LD + 3) / 4 * 4;
+  s.W1 = m; m += W * ld;
+  s.W2 = m; m += W * ld;
+  s.wt0 = m; m += (rows0 * ld + 3) / 4 * 4;   // keep every region 16-byte aligned
+  s.w3 = m; m += (rows3 * ld + 3) / 4 * 4;
   s.b0 = m; m += W; s.b1 = m; m += W; s.b2 = m; m += W; s.u3 = m; m += W;
   s.b3 = m; m += DMAX;
   s.actA = m; m += W * 2 * PB; s.actB = m; m += W * 2 * PB; s.part = m; m += (KS - 1) * W * 2 * PB;
@@ -228,21 +232,214 @@ __device__ __forceinline__ void eval(const Smem& s, const Args& A, const Stage& 
   __syncthreads();
 }
 
-template <int NJ>
+
+// ---- the same evaluation on mma.sync.m16n8k8 (tf32 x 3: hi*hi + lo*hi + hi*lo, fp32 accumulate) --------------------------------
+// A layer pass is C[128 units][8 columns] = W[128][128] X[128][8], column = 2 * trajectory + jet: exactly one N = 8 MMA tile, so
+// the 16 warps are 8 unit tiles x 2 K halves.  The weights are read from shared memory once per pass (A fragments: 4 loads of 1
+// wavefront per k-step at row pitch 132) instead of once per warp and k with broadcast activation loads: 3 x fewer shared-memory
+// wavefronts and 3 x fewer instructions than the FMA path.  tcgen05 does not pay here: an N = 8 tile costs it the same ~70
+// cycles per instruction as N = 128.  The C fragment gives a thread (unit g, trajectory t) and (unit g + 8, trajectory t) with
+// both jets, so the SELU jet algebra and the reverse sweep's derivative data stay thread-local as in the other kernels.
+// v = hi + lo with hi = v truncated to tf32 (what the tensor core reads of an fp32 register anyway) and lo = v - hi, exact in
+// fp32; the hardware truncates lo to tf32 in turn (relative error 2^-10 of a term that is 2^-10 of v).  Two instructions per
+// element: cvt.rna.tf32 is emulated on this part with a dozen.
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(v) & 0xffffe000u;
+  lo = __float_as_uint(v - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// c += A X over k-steps [ks0, ks0 + nks): A[m][k] = Wm[m * LDM + k] (TRANS = false) or Wm[k * LDM + m] (TRANS = true), m = m0 + ...
+template <bool TRANS>
+__device__ __forceinline__ void mma_pass(const float* Wm, const float* X, int m0, int ks0, int nks, int g, int t, float (&c)[4]) {
+  // three independent accumulation chains (lo*hi, hi*lo, hi*hi): an mma.sync depends on its accumulator, so one chain of
+  // 3 * nks instructions would be latency-bound
+  float c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (int ks = ks0; ks < ks0 + nks; ++ks) {
+    const int k0 = 8 * ks;
+    float af[4];
+    if (!TRANS) {
+      const float* r0 = Wm + (m0 + g) * LDM + k0 + t;
+      af[0] = r0[0]; af[1] = r0[8 * LDM]; af[2] = r0[4]; af[3] = r0[8 * LDM + 4];
+    } else {
+      const float* r0 = Wm + (k0 + t) * LDM + m0 + g;
+      af[0] = r0[0]; af[1] = r0[8]; af[2] = r0[4 * LDM]; af[3] = r0[4 * LDM + 8];
+    }
+    const float bf0 = X[(k0 + t) * 8 + g], bf1 = X[(k0 + t + 4) * 8 + g];
+    uint32_t ah[4], al[4], bh0, bl0, bh1, bl1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_tf32(af[i], ah[i], al[i]);
+    split_tf32(bf0, bh0, bl0);
+    split_tf32(bf1, bh1, bl1);
+    mma_tf32(c1, al, bh0, bh1);
+    mma_tf32(c2, ah, bl0, bl1);
+    mma_tf32(c, ah, bh0, bh1);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] += c1[i] + c2[i];
+}
+
+template <bool REV>
+__device__ __forceinline__ void eval_mma(const Smem& s, const Args& A, const Stage& st, bool jets) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int mt = warp & 7, kh = warp >> 3, m0 = 16 * mt;
+  const int D = A.D, rows0 = (A.din_pad + 15) & ~15;
+  // layer-0 input: X[k][2 p + jet]; jet 0 = [x, t], jet 1 = d = (1..1, 0); rows >= din are zero
+  for (int i = tid; i < rows0 * 8; i += NT) {
+    const int k = i >> 3, r = i & 7, p = r >> 1, j = r & 1;
+    float v = 0.0f;
+    if (k < A.din) v = j == 0 ? (k < D ? s.xs[p * D + k] : st.t) : ((jets && k < D) ? 1.0f : 0.0f);
+    s.actA[i] = v;
+  }
+  __syncthreads();
+
+  float saved[3][REV ? 4 : 1];   // per layer: (code, z') of (unit m0 + g, trajectory t) and of (unit m0 + g + 8, t); kh == 0 warps
+  float* ain = s.actA;
+  float* aout = s.actB;
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    if (l == 0) mma_pass<true>(s.wt0, ain, m0, kh * (rows0 / 16), rows0 / 16, g, t, c);
+    else mma_pass<false>(l == 1 ? s.W1 : s.W2, ain, m0, kh * 8, 8, g, t, c);
+    if (kh == 1) {
+      *reinterpret_cast<float2*>(s.part + (m0 + g) * 8 + 2 * t) = make_float2(c[0], c[1]);
+      *reinterpret_cast<float2*>(s.part + (m0 + g + 8) * 8 + 2 * t) = make_float2(c[2], c[3]);
+    }
+    __syncthreads();
+    if (kh == 0) {
+      const float* bias = l == 0 ? s.b0 : (l == 1 ? s.b1 : s.b2);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int n = m0 + g + 8 * q;
+        const float2 o = *reinterpret_cast<const float2*>(s.part + n * 8 + 2 * t);
+        const float z = c[2 * q] + o.x + bias[n], zd = c[2 * q + 1] + o.y;
+        float code, s1, E;
+        const float a = selu_fwd(z, code);
+        selu_decode(code, s1, E);
+        if (REV) { saved[l][2 * q] = code; saved[l][2 * q + 1] = zd; }
+        *reinterpret_cast<float2*>(aout + n * 8 + 2 * t) = make_float2(a, s1 * zd);
+      }
+    }
+    __syncthreads();
+    float* tmp = ain; ain = aout; aout = tmp;
+  }
+
+  // output layer (jet-0 columns): pred[p][d] = b3[d] + sum_n W3[d][n] a3[n][p]; unit tiles 0 .. ceil(dout / 16) - 1
+  {
+    const int ntile = (A.dout + 15) >> 4;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    if (mt < ntile) {
+      mma_pass<false>(s.w3, ain, m0, kh * 8, 8, g, t, c);
+      if (kh == 1) {
+        s.opart[(m0 + g) * 4 + t] = c[0];
+        s.opart[(m0 + g + 8) * 4 + t] = c[2];
+      }
+    }
+    __syncthreads();
+    if (mt < ntile && kh == 0) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int d = m0 + g + 8 * q;
+        if (d < A.dout) s.pred[t * A.dout + d] = (c[2 * q] + s.opart[d * 4 + t]) + s.b3[d];
+      }
+    }
+  }
+  __syncthreads();
+
+  if (REV) {
+    if (kh == 0) {   // seeds: adjoints of (a3, a3') are c1 * u3[n], c2 * u3[n]
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int n = m0 + g + 8 * q;
+        const float u = s.u3[n];
+        float P, Q, Rr;
+        adjoint_unit<2>(saved[2][2 * q], saved[2][2 * q + 1], 0.0f, st.c[0] * u, st.c[1] * u, 0.0f, P, Q, Rr);
+        *reinterpret_cast<float2*>(aout + n * 8 + 2 * t) = make_float2(P, Q);
+      }
+    }
+    __syncthreads();
+    { float* tmp = ain; ain = aout; aout = tmp; }
+#pragma unroll
+    for (int l = 1; l >= 0; --l) {
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_pass<true>(l == 1 ? s.W2 : s.W1, ain, m0, kh * 8, 8, g, t, c);   // adjoint of a_l[k] = sum_j W[j][k] P_{l+1}[j]
+      if (kh == 1) {
+        *reinterpret_cast<float2*>(s.part + (m0 + g) * 8 + 2 * t) = make_float2(c[0], c[1]);
+        *reinterpret_cast<float2*>(s.part + (m0 + g + 8) * 8 + 2 * t) = make_float2(c[2], c[3]);
+      }
+      __syncthreads();
+      if (kh == 0) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int n = m0 + g + 8 * q;
+          const float2 o = *reinterpret_cast<const float2*>(s.part + n * 8 + 2 * t);
+          float P, Q, Rr;
+          adjoint_unit<2>(saved[l][2 * q], saved[l][2 * q + 1], 0.0f, c[2 * q] + o.x, c[2 * q + 1] + o.y, 0.0f, P, Q, Rr);
+          *reinterpret_cast<float2*>(aout + n * 8 + 2 * t) = make_float2(P, l == 1 ? Q : 0.0f);
+        }
+      }
+      __syncthreads();
+      float* tmp = ain; ain = aout; aout = tmp;
+    }
+    // gradient wrt x: g[p][d] = sum_n W0^T[d][n] P1[n][p]   (rows d of the W0^T image; jet-0 columns)
+    {
+      const int ntile = (D + 15) >> 4;
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+      if (mt < ntile) {
+        mma_pass<false>(s.wt0, ain, m0, kh * 8, 8, g, t, c);
+        if (kh == 1) {
+          s.opart[(m0 + g) * 4 + t] = c[0];
+          s.opart[(m0 + g + 8) * 4 + t] = c[2];
+        }
+      }
+      __syncthreads();
+      if (mt < ntile && kh == 0) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int d = m0 + g + 8 * q;
+          if (d < D) s.gout[t * D + d] = c[2 * q] + s.opart[d * 4 + t];
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  if (tid < PB * D) {   // combine, as in eval()
+    const int p = tid / D, d = tid - p * D;
+    const float diff = __fsub_rn(s.pred[p * A.dout + d], s.xs[tid]);
+    float f;
+    if (st.kind == 0) f = diff;
+    else if (st.kind == 1) f = __fdiv_rn(diff, st.end_div);
+    else {
+      f = __fdiv_rn(__fmul_rn(st.a, diff), st.den);
+      if (REV) f = __fadd_rn(f, s.gout[tid]);
+    }
+    s.fs[tid] = f;
+  }
+  __syncthreads();
+}
+
+template <int NJ, bool MMA>
 __global__ void __launch_bounds__(NT, 1) k_md_chain(NetView net, const __grid_constant__ Args A) {
   extern __shared__ __align__(16) float smem[];
-  const Smem s = carve(smem, A.din_pad, A.dout);
+  constexpr int ld = MMA ? LDM : LD;
+  const int rows0 = MMA ? ((A.din_pad + 15) & ~15) : A.din_pad, rows3 = MMA ? ((A.dout + 15) & ~15) : A.dout;
+  const Smem s = carve(smem, rows0, rows3, ld);
   const int tid = threadIdx.x, D = A.D;
   const long base = (long)blockIdx.x * PB;
 
-  // the network, once
+  // the network, once (rows beyond din_pad / dout of the padded images are zero)
   for (int i = tid; i < W * W; i += NT) {
     const int r = i >> 7, c = i & 127;
-    s.W1[r * LD + c] = __ldg(net.w1 + i);
-    s.W2[r * LD + c] = __ldg(net.w2 + i);
+    s.W1[r * ld + c] = __ldg(net.w1 + i);
+    s.W2[r * ld + c] = __ldg(net.w2 + i);
   }
-  for (int i = tid; i < A.din_pad * W; i += NT) s.wt0[(i >> 7) * LD + (i & 127)] = __ldg(net.wt0 + i);
-  for (int i = tid; i < A.dout * W; i += NT) s.w3[(i >> 7) * LD + (i & 127)] = __ldg(net.w3 + i);
+  for (int i = tid; i < rows0 * W; i += NT) s.wt0[(i >> 7) * ld + (i & 127)] = i < A.din_pad * W ? __ldg(net.wt0 + i) : 0.0f;
+  for (int i = tid; i < rows3 * W; i += NT) s.w3[(i >> 7) * ld + (i & 127)] = i < A.dout * W ? __ldg(net.w3 + i) : 0.0f;
   if (tid < W) { s.b1[tid] = __ldg(net.b1 + tid); s.b2[tid] = __ldg(net.b2 + tid); s.u3[tid] = __ldg(net.u3 + tid); }
   if (tid < A.dout) s.b3[tid] = __ldg(net.b3 + tid);
   for (int o = tid; o < PB * D; o += NT) {
@@ -269,8 +466,13 @@ __global__ void __launch_bounds__(NT, 1) k_md_chain(NetView net, const __grid_co
 #pragma unroll 1
       for (int sg = 0; sg < nstage; ++sg) {
         const Stage& st = s.st[stp * 3 + sg];
-        if (st.kind == 2 && A.reverse) eval<NJ, true>(s, A, st);
-        else eval<1, false>(s, A, st);
+        if (MMA) {
+          if (st.kind == 2 && A.reverse) eval_mma<true>(s, A, st, NJ >= 2);
+          else eval_mma<false>(s, A, st, false);
+        } else {
+          if (st.kind == 2 && A.reverse) eval<NJ, true>(s, A, st);
+          else eval<1, false>(s, A, st);
+        }
         // torchsde srk (Roessler SRI2, diagonal noise, state-independent g) / euler: same update as idff_generic_sde.cu
         for (int o = tid; o < PB * D; o += NT) {
           const long row = base + o / D;
@@ -334,6 +536,9 @@ __global__ void __launch_bounds__(NT, 1) k_md_chain(NetView net, const __grid_co
 
 }  // namespace chain
 
+static int g_chain_fma = 0;   // diagnostic: 1 = the FMA evaluator instead of the mma.sync one (idff_debug_md_chain_fma)
+void md_chain_set_fma(int on) { g_chain_fma = on ? 1 : 0; }
+
 bool md_chain_supports(const idff_weights_t* w, const idff_field_params_t* p, int64_t K) {
   const NetView& v = w->v;
   return p->variant == IDFF_FIELD_MD && v.w == chain::W && v.din == p->dim + 1 && v.din_pad <= chain::DMAX && v.dout <= chain::DMAX &&
@@ -370,18 +575,22 @@ int md_chain_run(const idff_weights_t* w, const idff_field_params_t* p, int n_fr
   A.stages = reinterpret_cast<const Stage*>(wm->d_sweep);
   A.x_init = d_x_init; A.Ik = d_I_k; A.Ik0 = d_I_k0; A.y_hat = d_y_hat; A.K = K;
   const int grid = (int)((K + PB - 1) / PB);
-  const size_t sm = smem_bytes(A.din_pad, A.dout);
+  const bool mma = g_chain_fma == 0;
+  const int rows0 = mma ? ((A.din_pad + 15) & ~15) : A.din_pad, rows3 = mma ? ((A.dout + 15) & ~15) : A.dout;
+  const size_t sm = smem_bytes(rows0, rows3, mma ? LDM : LD);
   if (sm > 232448) {
     set_error("idff_md_generate: %zu B of shared memory needed (limit 232448)", sm);
     return IDFF_EUNSUPPORTED;
   }
-  if (nj >= 2) {
-    IDFF_CUDA(cudaFuncSetAttribute(k_md_chain<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_md_chain<2><<<grid, NT, sm, s>>>(w->v, A);
-  } else {
-    IDFF_CUDA(cudaFuncSetAttribute(k_md_chain<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    k_md_chain<1><<<grid, NT, sm, s>>>(w->v, A);
-  }
+  auto launch = [&](auto kern) -> int {
+    IDFF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    kern<<<grid, NT, sm, s>>>(w->v, A);
+    return IDFF_OK;
+  };
+  int rc;
+  if (mma) rc = nj >= 2 ? launch(k_md_chain<2, true>) : launch(k_md_chain<1, true>);
+  else rc = nj >= 2 ? launch(k_md_chain<2, false>) : launch(k_md_chain<1, false>);
+  if (rc) return rc;
   IDFF_CUDA(cudaGetLastError());
   count_launch();
   return IDFF_OK;

@@ -219,6 +219,8 @@ int idff_ot_assign(const float* d_x0, const float* d_x1, int32_t n, int32_t D, i
  * d_I_k, d_I_k0 [n_frames][n_steps][K][D] Brownian increments per frame (n_steps = idff_sde_num_steps; d_I_k0 may be NULL for
  * euler); d_y_hat [n_frames][K][D] = traj[-1] of every frame.  Serves hidden width 128, D <= 63, K <= 592 (the latency regime:
  * the reference generates 5 trajectories); IDFF_EUNSUPPORTED otherwise -- use one idff_sample_sde call per frame there. */
+/* Diagnostic: on != 0 makes idff_md_generate evaluate the layers with the fp32 FMA loop instead of mma.sync (3 x tf32). */
+int idff_debug_md_chain_fma(int32_t on);
 int idff_md_generate(const idff_weights_t* w, const idff_field_params_t* p, int32_t n_frames, const float* d_x_init,
                      const float* h_ts, int32_t n_ts, float dt, int32_t method, const float* d_I_k, const float* d_I_k0,
                      float* d_y_hat, int64_t K, void* stream);

@@ -326,3 +326,26 @@ def test_new_entry_points_edge_cases(cuda_device):
     ts = torch.linspace(0, 1, 3)
     assert torch.equal(sampler.sample_rk4_sweep([m3], x0, ts)[0], sampler.sample_rk4(m3, x0, ts))
     assert sampler.sample_rk4_sweep([m3, m3], x0[:0], ts).shape == (2, 0, 2)
+
+
+def test_md_chain_fma_and_mma_evaluators_agree(cuda_device):
+    """idff_md_generate evaluates the layers on mma.sync (3 x tf32) by default; the fp32-FMA evaluator behind
+    idff_debug_md_chain_fma is the yardstick: the two stay within 1e-5 of the frame's scale over a 40-frame chain."""
+    pw = packed("polyala", cuda_device)
+    K, D, T, NFE, dt = 7, 46, 40, 3, 0.3
+    g = torch.Generator(device=cuda_device).manual_seed(3)
+    x_init = torch.randn(K, D, device=cuda_device, generator=g)
+    from idff_b200 import sampler as sampler_mod
+    ik, ik0 = sampler_mod.brownian_increments(4, torch.linspace(0, 1, NFE), dt, (T, K, D), cuda_device, g)
+    nz = (ik.transpose(0, 1).contiguous(), ik0.transpose(0, 1).contiguous())
+    out = []
+    for fma in (0, 1):
+        _lib.check(_lib.lib().idff_debug_md_chain_fma(fma), "chain_fma")
+        try:
+            out.append(md.generate_trajectories_chain(pw, K, D, T, NFE, sigma=0.5, gamma1=0.2, gamma2=5.0, dt=dt,
+                                                      device=cuda_device, x_init=x_init, noise=nz))
+        finally:
+            _lib.check(_lib.lib().idff_debug_md_chain_fma(0), "chain_fma")
+    d = (out[0] - out[1]).abs()
+    scale = out[1].abs().max().item()
+    assert torch.isfinite(out[0]).all() and d.max().item() <= 1e-5 * scale, (d.max().item(), scale)
