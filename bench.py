@@ -380,6 +380,29 @@ def aux_measurements(dev, pw, model, peaks):
             s = timeit(lambda: sampler.sample_rk4(m2, xs, ts), reps=2, warm=1)
             sweep[str(nfe)] = xs.shape[0] * 4 * nfe / s
         aux[f"sampler_{name}_nfe_sweep_particle_steps_per_s"] = sweep
+    # BASELINE configs[1]: "NFE 2-10, 1M-64M particles on 1 B200" -- the default sampler over particle counts (nfe = 2)
+    try:
+        m2 = fields.CustomNetModel(pw, SIGMA, *GAMMAS)
+        ts2 = torch.linspace(0, 1, 3)
+        nsweep = {}
+        for lg in (11, 16, 20, 22, 24, 26):
+            xn = torch.randn(1 << lg, 2, device=dev, generator=g) / 1.5
+            s = timeit(lambda: sampler.sample_rk4(m2, xn, ts2), reps=2 if lg >= 24 else 5, warm=1)
+            nsweep[f"2^{lg}"] = (1 << lg) * 8 / s
+            del xn
+        aux["sampler_default_particle_sweep_nfe2_particle_steps_per_s"] = nsweep
+    except Exception as exc:
+        aux["sampler_particle_sweep_error"] = repr(exc)
+    # the exact minibatch-OT coupling of the _dynamic matcher at the reference's batch (256) and PolyALA's (10)
+    try:
+        from idff_b200.torchcfm import optimal_transport as otm
+        ot_out = {}
+        for n_ot, d_ot in ((256, 2), (10, 46)):
+            xa, xb = torch.randn(n_ot, d_ot, device=dev, generator=g), torch.randn(n_ot, d_ot, device=dev, generator=g) + 1.0
+            ot_out[f"n{n_ot}_D{d_ot}_us"] = timeit(lambda: otm.ot_assign(xa, xb), reps=5, warm=1) * 1e6
+        aux["ot_assign"] = ot_out
+    except Exception as exc:
+        aux["ot_assign_error"] = repr(exc)
     # ---- the reference's CPU path for the secondary kernels, timed beside them, small + large
     try:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
