@@ -410,8 +410,8 @@ extern "C" int idff_md_generate(const idff_weights_t* w, const idff_field_params
     return IDFF_EUNSUPPORTED;
   }
   if (!md_chain_supports(w, p, K)) {
-    set_error("idff_md_generate: needs a width-128 network with at most 64 state dimensions and at most 592 trajectories; "
-              "use one idff_sample_sde call per frame otherwise");
+    set_error("idff_md_generate: needs a width-128 network with at most 63 state dimensions; use one idff_sample_sde call per "
+              "frame otherwise");
     return IDFF_EUNSUPPORTED;
   }
   // frame f: init_ind = f, gamma2 / (1 + f)   (MD_simulation.py:201); everything else is shared by the frames

@@ -430,7 +430,6 @@ __global__ void __launch_bounds__(NT, 1) k_md_chain(NetView net, const __grid_co
   const int rows0 = MMA ? ((A.din_pad + 15) & ~15) : A.din_pad, rows3 = MMA ? ((A.dout + 15) & ~15) : A.dout;
   const Smem s = carve(smem, rows0, rows3, ld);
   const int tid = threadIdx.x, D = A.D;
-  const long base = (long)blockIdx.x * PB;
 
   // the network, once (rows beyond din_pad / dout of the padded images are zero)
   for (int i = tid; i < W * W; i += NT) {
@@ -442,13 +441,17 @@ __global__ void __launch_bounds__(NT, 1) k_md_chain(NetView net, const __grid_co
   for (int i = tid; i < rows3 * W; i += NT) s.w3[(i >> 7) * ld + (i & 127)] = i < A.dout * W ? __ldg(net.w3 + i) : 0.0f;
   if (tid < W) { s.b1[tid] = __ldg(net.b1 + tid); s.b2[tid] = __ldg(net.b2 + tid); s.u3[tid] = __ldg(net.u3 + tid); }
   if (tid < A.dout) s.b3[tid] = __ldg(net.b3 + tid);
+
+  const int nstage = A.method == 1 ? 1 : 3;
+  const long ntiles = (A.K + PB - 1) / PB;
+  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {   // a CTA runs the whole chain of one group of 4, then the next
+  const long base = tile * PB;
+  __syncthreads();
   for (int o = tid; o < PB * D; o += NT) {
     const long row = base + o / D;
     s.y[o] = row < A.K ? A.x_init[row * D + (o % D)] : 0.0f;
   }
   __syncthreads();
-
-  const int nstage = A.method == 1 ? 1 : 3;
   for (int f = 0; f < A.n_frames; ++f) {
     // frame constants: folded layer-0 bias b0 + W0[:, D+1:] . emb[f], stage scalars with gamma2 / (1 + f)
     if (tid < W) s.b0[tid] = __ldg(net.b0 + (size_t)f * W + tid);
@@ -532,6 +535,7 @@ __global__ void __launch_bounds__(NT, 1) k_md_chain(NetView net, const __grid_co
     }
     __syncthreads();
   }
+  }
 }
 
 }  // namespace chain
@@ -542,7 +546,7 @@ void md_chain_set_fma(int on) { g_chain_fma = on ? 1 : 0; }
 bool md_chain_supports(const idff_weights_t* w, const idff_field_params_t* p, int64_t K) {
   const NetView& v = w->v;
   return p->variant == IDFF_FIELD_MD && v.w == chain::W && v.din == p->dim + 1 && v.din_pad <= chain::DMAX && v.dout <= chain::DMAX &&
-         v.dout >= p->dim && p->dim * chain::PB <= 256 && v.dout * chain::PB <= 256 && v.din_pad % chain::KS == 0 && K >= 1 && K <= 4 * 148;
+         v.dout >= p->dim && p->dim * chain::PB <= 256 && v.dout * chain::PB <= 256 && v.din_pad % chain::KS == 0 && K >= 1;
 }
 
 int md_chain_run(const idff_weights_t* w, const idff_field_params_t* p, int n_frames, const SdeTable& tab0, const Stage* stages,
@@ -574,7 +578,10 @@ int md_chain_run(const idff_weights_t* w, const idff_field_params_t* p, int n_fr
   A.w1 = tab0.n_emit > 0 ? tab0.emit_w1[tab0.n_emit - 1] : 1.0f;
   A.stages = reinterpret_cast<const Stage*>(wm->d_sweep);
   A.x_init = d_x_init; A.Ik = d_I_k; A.Ik0 = d_I_k0; A.y_hat = d_y_hat; A.K = K;
-  const int grid = (int)((K + PB - 1) / PB);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
+  const long tiles = (K + PB - 1) / PB;
+  const int grid = (int)(tiles < sms ? tiles : sms);
   const bool mma = g_chain_fma == 0;
   const int rows0 = mma ? ((A.din_pad + 15) & ~15) : A.din_pad, rows3 = mma ? ((A.dout + 15) & ~15) : A.dout;
   const size_t sm = smem_bytes(rows0, rows3, mma ? LDM : LD);

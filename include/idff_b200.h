@@ -217,8 +217,9 @@ int idff_ot_assign(const float* d_x0, const float* d_x1, int32_t n, int32_t D, i
  * chain, the network stays in shared memory.  p: variant IDFF_FIELD_MD with the BASE gamma2 in gamma[1] (divided by 1 + f per
  * frame here, as :201 does) and end_div = dt; t_idx is ignored (frame f uses embedding row f).  d_x_init [K][D];
  * d_I_k, d_I_k0 [n_frames][n_steps][K][D] Brownian increments per frame (n_steps = idff_sde_num_steps; d_I_k0 may be NULL for
- * euler); d_y_hat [n_frames][K][D] = traj[-1] of every frame.  Serves hidden width 128, D <= 63, K <= 592 (the latency regime:
- * the reference generates 5 trajectories); IDFF_EUNSUPPORTED otherwise -- use one idff_sample_sde call per frame there. */
+ * euler); d_y_hat [n_frames][K][D] = traj[-1] of every frame.  Serves hidden width 128, D <= 63 (IDFF_EUNSUPPORTED otherwise).  It is
+ * the latency path (the reference generates 5 trajectories): 592 trajectories run concurrently, more in waves; above a few
+ * thousand trajectories one idff_sample_sde call per frame (the throughput kernel) is faster. */
 /* Diagnostic: on != 0 makes idff_md_generate evaluate the layers with the fp32 FMA loop instead of mma.sync (3 x tf32). */
 int idff_debug_md_chain_fma(int32_t on);
 int idff_md_generate(const idff_weights_t* w, const idff_field_params_t* p, int32_t n_frames, const float* d_x_init,

@@ -9,8 +9,9 @@ pw = PackedWeights.from_npz(np.load(os.path.join(os.path.dirname(os.path.abspath
 K, D, T, NFE, dt = int(os.environ.get("K", 5)), 46, int(os.environ.get("T", 200)), 3, 0.3
 g = torch.Generator(device=dev).manual_seed(1)
 x_init = torch.randn(K, D, device=dev, generator=g)
-ik = torch.randn(T, 4, K, D, device=dev, generator=g) * 0.5
-ik0 = torch.randn(T, 4, K, D, device=dev, generator=g) * 0.05
+from idff_b200 import sampler
+ik, ik0 = sampler.brownian_increments(4, torch.linspace(0, 1, NFE), dt, (T, K, D), dev, g)     # (n_steps, T, K, D), the right law
+ik, ik0 = ik.transpose(0, 1).contiguous(), ik0.transpose(0, 1).contiguous()
 kw = dict(sigma=0.5, gamma1=0.2, gamma2=5.0, dt=dt, device=dev, x_init=x_init, noise=(ik, ik0))
 md.generate_trajectories_chain(pw, K, D, T, NFE, **kw)
 torch.cuda.synchronize()

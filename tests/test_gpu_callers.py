@@ -222,8 +222,15 @@ def test_md_chain_kernel_full_length(cuda_device):
     t2 = time.perf_counter()
     print(f"PolyALA generation, 200 frames x 5 trajectories: chain kernel {1e3 * (t1 - t0) / 3:.1f} ms (incl. noise draws), "
           f"launch per frame {1e3 * (t2 - t1):.1f} ms")
-    with pytest.raises(_lib.IdffError):
-        md.generate_trajectories(pw, 1000, D, 4, NFE, sigma=0.5, dt=dt, device=cuda_device, chain=True)
+    # more trajectories than one wave of CTAs (2 x 148 x 4 + 3): the CTAs loop over groups of 4
+    K2 = 2 * 592 + 3
+    x2 = torch.randn(K2, D, device=cuda_device, generator=g)
+    ik, ik0 = sampler_mod.brownian_increments(n_steps, torch.linspace(0, 1, NFE), dt, (3, K2, D), cuda_device, g)
+    nz = (ik.transpose(0, 1).contiguous(), ik0.transpose(0, 1).contiguous())
+    kw2 = dict(sigma=0.5, gamma1=0.2, gamma2=5.0, dt=dt, device=cuda_device, x_init=x2, noise=lambda t_idx, n: (nz[0][t_idx], nz[1][t_idx]))
+    a = md.generate_trajectories(pw, K2, D, 3, NFE, chain=True, **kw2)
+    b = md.generate_trajectories(pw, K2, D, 3, NFE, chain=False, **kw2)
+    assert torch.isfinite(a).all() and (a - b).abs().max().item() <= 1e-4 * b.abs().max().item()
 
 
 def test_md_compute_metrics_matches_reference_golden(cuda_device):
