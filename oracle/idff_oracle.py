@@ -16,7 +16,11 @@ Two third-party integrators are NOT in /root/reference and not installable here:
   * torchsde (imported MD_simulation.py:8, not in requirements.txt) `srk` for
     ito/diagonal (Roessler SRI2 tableau)      -> `sdeint_srk` below, Brownian
     increments injected (the reference's own BrownianInterval is entropy-seeded).
-For those two the parity is "unpinned" (anchored on the reference's call sites only).
+  * POT (requirements.txt:10, unpinned) `pot.emd` behind OTPlanSampler.get_map (optimal_transport.py:45,59-94)
+    -> `ot_exact_permutation` below: for the uniform equal-size marginals the reference uses, the LP optimum is the assignment
+    optimum, obtained with scipy's exact solver.
+For those three the parity is "unpinned" (anchored on the reference's call sites only).  The torch optimizer / clip calls of
+the training loop (`train_steps_2d`) and numpy's corrcoef / nanmean of `md_compute_metrics` ARE the reference's own calls.
 """
 from __future__ import annotations
 
