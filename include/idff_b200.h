@@ -11,8 +11,9 @@
  *   - pointers named d_* are DEVICE pointers owned by the caller (torch tensors), fp32 row-major unless
  *     stated; pointers named h_* are HOST pointers;  `stream` is a cudaStream_t passed as void*;
  *   - nothing is allocated per call; the only persistent allocation is the weights handle;
- *   - no global mutable state: handles are independent, calls on one handle may be issued from one host
- *     thread at a time.
+ *   - no global mutable state on the product path: handles are independent, calls on one handle may be issued
+ *     from one host thread at a time.  The idff_debug_* entry points are process-wide diagnostic switches /
+ *     read-outs (phase timestamps, alternative evaluators) for tests and profiling, not for production use.
  */
 #ifndef IDFF_B200_H
 #define IDFF_B200_H
