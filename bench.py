@@ -545,6 +545,24 @@ def aux_measurements(dev, pw, model, peaks):
         aux["polyala_generation_T200_K5"] = {"chain_kernel_ms": s_chain * 1e3, "launch_per_frame_ms": s_frame * 1e3,
                                              "launches": {"chain": 1, "per_frame": 200},
                                              "particle_steps": 200 * 5 * 12}
+        # the reference's loop on the host cores (oracle: SDE_cal.f with nested autograd under the restated srk), 4 frames x 50
+        import idff_oracle as O4
+        wz = np.load(os.path.join(ROOT, "tests", "golden", "weights_polyala.npz"))
+        lay4 = [(torch.tensor(wz[f"W{i}"]), torch.tensor(wz[f"b{i}"])) for i in range(4)]
+        emb4 = torch.tensor(wz["emb"])
+        ts4 = torch.linspace(0, 1, 3)
+        grid4 = O4.sde_step_grid(ts4, 0.3)
+        h4 = torch.tensor(np.diff(np.array(grid4, dtype=np.float32)))
+        xc = torch.randn(5, 46)
+        for f in range(5):
+            if f == 1:
+                t0 = time.perf_counter()     # frame 0 is the warm-up
+            ik = torch.randn(len(h4), 5, 46) * h4.sqrt()[:, None, None]
+            ik0 = 0.5 * h4[:, None, None] * ik
+            sde = O4.FieldMD(lay4, emb4, 46, sigma=0.5, init_ind=f, dt=0.3, gamma1=0.2, gamma2=5.0 / (1 + f))
+            xc = O4.sdeint_srk(sde, xc, ts4, 0.3, ik, ik0)[-1]
+        aux["polyala_generation_T200_K5"]["reference_cpu_ms"] = (time.perf_counter() - t0) / 4 * 200 * 1e3
+        aux["polyala_generation_T200_K5"]["reference_cpu_note"] = "4 frames timed on the host cores, x50"
     except Exception as exc:
         aux["polyala_generation_error"] = repr(exc)
     # ---- other BASELINE configs, measured briefly (reported, not the headline)
