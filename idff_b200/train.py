@@ -180,8 +180,10 @@ class FusedFlowTrainer:
         self.sync_params()
 
     def sync_params(self):
-        """Rebuild the kernel's transposed weight copies after the parameters were written from outside."""
+        """Rebuild the kernel's streaming weight copies after the parameters were written from outside (load_state_dict,
+        manual edits).  `steps` calls it by itself when a parameter's version counter moved since the last launch."""
         _lib.check(_lib.lib().idff_train_flow_init(_lib.ptr(self.state), _lib.stream_of(self.state)), "idff_train_flow_init")
+        self._versions = [p._version for p in self.model.parameters()]
 
     def _block(self, name):   # parameter-block shaped views: "param", "exp_avg", "exp_avg_sq"
         base = self.offsets[{"param": 9, "exp_avg": 10, "exp_avg_sq": 11}[name]]
@@ -209,6 +211,8 @@ class FusedFlowTrainer:
         S, B = int(t.shape[0]), int(t.shape[1])
         if tuple(x0.shape) != (S, B, 2) or tuple(x1.shape) != (S, B, 2) or (eps is not None and tuple(eps.shape) != (S, B, 2)):
             raise _lib.IdffError(f"expected x0, x1[, eps] of shape ({S}, {B}, 2)")
+        if [p._version for p in self.model.parameters()] != self._versions:
+            self.sync_params()                 # somebody wrote the parameters in place since the last launch
         loss = torch.empty(S, device=self.device, dtype=torch.float32)
         gnorm = torch.empty(S, device=self.device, dtype=torch.float32) if return_gnorm else None
         _lib.check(_lib.lib().idff_train_flow_steps(
@@ -218,6 +222,7 @@ class FusedFlowTrainer:
         self.steps_done += S
         for p in self.model.parameters():      # the kernel wrote them in place: invalidate caches keyed on _version
             torch.autograd.graph.increment_version(p)
+        self._versions = [p._version for p in self.model.parameters()]
         return (loss, gnorm) if return_gnorm else loss
 
     def draw(self, n_steps: int):

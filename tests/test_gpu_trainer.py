@@ -162,6 +162,26 @@ def test_model_aliases_state_and_feeds_the_sampler(cuda_device):
     assert torch.isfinite(out).all()
 
 
+def test_external_parameter_writes_are_picked_up(cuda_device):
+    """load_state_dict (an in-place copy into the aliased parameters) between launches: the next launch rebuilds the kernel's
+    streaming weight copies by itself and trains the loaded network -- identical to a trainer built on that network."""
+    np.random.seed(8)
+    dev = cuda_device
+    x0, x1, t, _ = (v.to(dev) if v is not None else None for v in _draws(3, 64, 51, 0.0))
+    donor = _fresh_mlp(dev, seed=21)
+    a = train.FusedFlowTrainer(_fresh_mlp(dev, seed=20), batch_size=64, lr=LR)
+    a.steps(x0, x1, t)                                   # some history on other weights ...
+    a.model.load_state_dict(donor.state_dict())          # ... then the weights are replaced from outside
+    a.state[a.offsets[10]: a.offsets[11] + a.n_params].zero_()               # fresh optimizer state (exp_avg, exp_avg_sq)
+    a.steps_done = 0
+    la = a.steps(x0, x1, t)
+    b = train.FusedFlowTrainer(_fresh_mlp(dev, seed=21), batch_size=64, lr=LR)
+    lb = b.steps(x0, x1, t)
+    assert torch.equal(la, lb)
+    for pa, pb in zip(a.model.parameters(), b.model.parameters()):
+        assert torch.equal(pa, pb)
+
+
 def test_rejects_unsupported_shapes(cuda_device):
     dev = cuda_device
     tr = train.FusedFlowTrainer(_fresh_mlp(dev), batch_size=256)
