@@ -7,7 +7,9 @@
 // (x0[i], x1[perm[i]]).  The reference ships the matrix to the host, solves it there (n = 256) and ships the plan back; here the
 // assignment is solved where the data lives, so the dynamic matcher's step needs no host round trip and can be graph-captured.
 //
-// Algorithm: shortest augmenting paths with dual variables (Jonker-Volgenant / the Hungarian method in its O(n^3) form), fp64,
+// Two kernels: shortest augmenting paths (below; n <= 64 and the yardstick) and an epsilon-scaling auction (further down; the
+// default above 64 rows).
+// Augmenting paths: shortest augmenting paths with dual variables (Jonker-Volgenant / the Hungarian method in its O(n^3) form), fp64,
 // exact, after a greedy column-reduction start.  One CTA, one thread per column: a thread keeps its column's tentative distance,
 // visited flag and dual v in registers; every search step is one relaxation of all columns against the row just reached (cost
 // recomputed from the coordinates, never materialised) plus one block-wide argmin (warp shuffles, one shared-memory exchange,
@@ -179,6 +181,218 @@ __global__ void __launch_bounds__(MAXN, 1) k_ot_assign(const float* __restrict__
   }
 }
 
+
+// ---- epsilon-scaling auction (Bertsekas), the default above 64 rows -----------------------------------------------------------
+// The augmenting-path search above is a chain of ~n^2 / 2 dependent block-wide argmins (10 ms at n = 256).  The auction is
+// parallel over the unassigned rows: in a round every unassigned row i (one warp each) scans all columns for its best and
+// second-best value -c(i, j) - p[j] and bids p[j1] + (w1 - w2) + eps on the best; every column takes its highest bid (ties: the
+// lowest row), its previous owner becomes unassigned.  Prices only rise; a phase ends when every row owns a column, and the
+// assignment then costs at most n * eps more than the optimum.  eps is scaled down by 6 from max(c) / 2 to max(c) * 2^-40, prices
+// carried over, so the final plan is the exact optimum whenever the optimum beats every other plan by more than n max(c) 2^-40
+// (2e-10 of the largest cost at n = 256: below the rounding of the cost sums themselves).  All arithmetic in fp64, costs
+// recomputed from the coordinates; every step is deterministic (ordered atomics only).
+template <int DFIX>
+__global__ void __launch_bounds__(512, 1) k_ot_auction(const float* __restrict__ x0, const float* __restrict__ x1, int n, int D,
+                                                       int64_t* __restrict__ perm, double* __restrict__ cost_out) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double* price = reinterpret_cast<double*>(smraw);                                // [n]
+  double* bidval = price + n;                                                      // [n] bid of row i this round
+  unsigned long long* maxbid = reinterpret_cast<unsigned long long*>(bidval + n);  // [n] highest bid on column j (bit pattern)
+  double* wred = reinterpret_cast<double*>(maxbid + n);                            // [32]
+  int* owner = reinterpret_cast<int*>(wred + 32);                                  // [n] row that owns column j, -1
+  int* mine = owner + n;                                                           // [n] column owned by row i, -1
+  int* winner = mine + n;                                                          // [n] lowest row among the highest bidders
+  int* bidcol = winner + n;                                                        // [n] column row i bid on this round
+  int* list = bidcol + n;                                                          // [n] unassigned rows, in row order
+  int* ccnt = list + n;                                                            // [32] unassigned rows per chunk of 32
+  float* xs0 = reinterpret_cast<float*>(ccnt + 32);                                // [n][DFIX]
+  float* xs1 = xs0 + (DFIX > 0 ? n * DFIX : 0);                                    // [n][DFIX]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;   // 16 warps
+  const int nchunk = (n + 31) >> 5;                                                // <= 32 chunks: 2 per warp
+
+  if (DFIX > 0)
+    for (int i = tid; i < n * DFIX; i += blockDim.x) { xs0[i] = x0[i]; xs1[i] = x1[i]; }
+  for (int j = tid; j < n; j += blockDim.x) { price[j] = 0.0; maxbid[j] = 0ull; winner[j] = 0x7fffffff; }
+  __syncthreads();
+  auto cost = [&](int i, int j) -> double {
+    double c = 0.0;
+    if (DFIX > 0) {
+#pragma unroll
+      for (int d = 0; d < DFIX; ++d) {
+        const double df = (double)xs0[i * DFIX + d] - (double)xs1[j * DFIX + d];
+        c = fma(df, df, c);
+      }
+    } else {
+      for (int d = 0; d < D; ++d) {
+        const double df = (double)x0[(size_t)i * D + d] - (double)x1[(size_t)j * D + d];
+        c = fma(df, df, c);
+      }
+    }
+    return c;
+  };
+  // largest cost: the epsilon scale
+  double cmax = 0.0;
+  for (int e = tid; e < n * n; e += blockDim.x) cmax = fmax(cmax, cost(e / n, e % n));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, off));
+  if (lane == 0) wred[warp] = cmax;
+  __syncthreads();
+  cmax = wred[0];
+  for (int w = 1; w < nwarps; ++w) cmax = fmax(cmax, wred[w]);
+  __syncthreads();
+  const double eps_final = fmax(cmax * 9.094947017729282e-13, 1e-300);   // max(c) 2^-40
+  double eps = fmax(cmax * 0.5, eps_final);
+  const long round_cap = 64L * n + 4096;   // non-finite inputs must not hang the device: give up on a phase after this many rounds
+
+  for (bool last = false; !last;) {
+    last = eps <= eps_final;
+    for (int i = tid; i < n; i += blockDim.x) { owner[i] = -1; mine[i] = -1; }
+    __syncthreads();
+    for (long round = 0; round < round_cap; ++round) {
+      // (1) the unassigned rows, compacted in row order (deterministic)
+      unsigned m2[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int c = warp + q * nwarps, i = c * 32 + lane;
+        m2[q] = __ballot_sync(0xffffffffu, c < nchunk && i < n && mine[i] < 0);
+        if (lane == 0 && c < 32) ccnt[c] = __popc(m2[q]);
+      }
+      __syncthreads();
+      int nun = 0;
+      for (int c = 0; c < nchunk; ++c) nun += ccnt[c];
+      if (nun == 0) break;   // uniform: every thread computed the same sum
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int c = warp + q * nwarps;
+        if (c < nchunk && ((m2[q] >> lane) & 1u)) {
+          int off = 0;
+          for (int cc = 0; cc < c; ++cc) off += ccnt[cc];
+          list[off + __popc(m2[q] & ((1u << lane) - 1u))] = c * 32 + lane;
+        }
+      }
+      __syncthreads();
+      if (nun == 1) {
+        // the common tail of a phase: ONE unassigned row.  Its bid displaces an owner, who is then the only unassigned row, and so
+        // on until a free column is taken: warp 0 walks that chain alone (same bids, no block barriers, no compaction)
+        if (warp == 0) {
+          int i = list[0];
+          for (long hop = 0; hop < round_cap; ++hop) {
+            double w1 = -1.0e300, w2 = -1.0e300;
+            int j1 = 0x7fffffff;
+            for (int j = lane; j < n; j += 32) {
+              const double v = -cost(i, j) - price[j];
+              if (v > w1) { w2 = w1; w1 = v; j1 = j; }
+              else if (v > w2) w2 = v;
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+              const double o1 = __shfl_xor_sync(0xffffffffu, w1, off), o2 = __shfl_xor_sync(0xffffffffu, w2, off);
+              const int oj = __shfl_xor_sync(0xffffffffu, j1, off);
+              if (o1 > w1 || (o1 == w1 && oj < j1)) { w2 = fmax(w1, o2); w1 = o1; j1 = oj; }
+              else w2 = fmax(w2, o1);
+            }
+            if (j1 >= n) { j1 = i; w2 = w1; }
+            const int prev = owner[j1];
+            __syncwarp();
+            if (lane == 0) {
+              price[j1] = price[j1] + (n > 1 ? w1 - w2 : 0.0) + eps;
+              owner[j1] = i;
+              mine[i] = j1;
+              if (prev >= 0) mine[prev] = -1;
+            }
+            __syncwarp();
+            if (prev < 0) break;
+            i = prev;
+          }
+        }
+        __syncthreads();
+        continue;
+      }
+      // (2) bids: one warp per unassigned row scans all columns for its best and second-best value
+      for (int u = warp; u < nun; u += nwarps) {
+        const int i = list[u];
+        double w1 = -1.0e300, w2 = -1.0e300;
+        int j1 = 0x7fffffff;
+        for (int j = lane; j < n; j += 32) {
+          const double v = -cost(i, j) - price[j];
+          if (v > w1) { w2 = w1; w1 = v; j1 = j; }
+          else if (v > w2) w2 = v;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const double o1 = __shfl_xor_sync(0xffffffffu, w1, off), o2 = __shfl_xor_sync(0xffffffffu, w2, off);
+          const int oj = __shfl_xor_sync(0xffffffffu, j1, off);
+          if (o1 > w1 || (o1 == w1 && oj < j1)) { w2 = fmax(w1, o2); w1 = o1; j1 = oj; }
+          else w2 = fmax(w2, o1);
+        }
+        if (lane == 0) {
+          if (j1 >= n) { j1 = i; w2 = w1; }   // nothing comparable (non-finite input): bid on the own index, no gap
+          const double bid = price[j1] + (n > 1 ? w1 - w2 : 0.0) + eps;
+          bidval[i] = bid;
+          bidcol[i] = j1;
+          atomicMax(&maxbid[j1], (unsigned long long)__double_as_longlong(bid));   // bids are positive: bit order = value order
+        }
+      }
+      __syncthreads();
+      // (3) the lowest row among a column's highest bidders wins
+      for (int u = tid; u < nun; u += blockDim.x) {
+        const int i = list[u], j1 = bidcol[i];
+        if ((unsigned long long)__double_as_longlong(bidval[i]) == maxbid[j1]) atomicMin(&winner[j1], i);
+      }
+      __syncthreads();
+      // (4) winners take their columns at the price they bid; the previous owner becomes unassigned
+      for (int u = tid; u < nun; u += blockDim.x) {
+        const int i = list[u], j1 = bidcol[i];
+        if (winner[j1] == i) {
+          const int prev = owner[j1];
+          if (prev >= 0) mine[prev] = -1;
+          owner[j1] = i;
+          mine[i] = j1;
+          price[j1] = bidval[i];
+        }
+      }
+      __syncthreads();
+      for (int u = tid; u < nun; u += blockDim.x) {
+        const int j1 = bidcol[list[u]];
+        maxbid[j1] = 0ull;
+        winner[j1] = 0x7fffffff;
+      }
+      __syncthreads();
+    }
+    eps = fmax(eps * (1.0 / 6.0), eps_final);
+  }
+  __syncthreads();
+  // rows left unassigned by the round cap (non-finite inputs only) take the free columns in order: still a permutation
+  if (tid == 0) {
+    int fj = 0;
+    for (int i = 0; i < n; ++i)
+      if (mine[i] < 0) {
+        while (owner[fj] >= 0) ++fj;
+        mine[i] = fj;
+        owner[fj] = i;
+      }
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) perm[i] = (int64_t)mine[i];
+  if (cost_out) {
+    double c = 0.0;
+    for (int i = tid; i < n; i += blockDim.x) c += cost(i, mine[i]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+    if (lane == 0) wred[warp] = c;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < nwarps; ++w) t += wred[w];
+      *cost_out = t;
+    }
+  }
+}
+
+static size_t auction_smem_bytes(int n, int dfix) {
+  return (size_t)n * 8 * 3 + 32 * 8 + (size_t)n * 4 * 5 + 32 * 4 + (size_t)2 * n * dfix * 4 + 16;
+}
+
 static size_t smem_bytes(int n, int dfix) { return (size_t)n * 8 + 64 * sizeof(Best) + (size_t)4 * n * 4 + (size_t)n * dfix * 4 + 16; }
 
 }  // namespace ot
@@ -186,17 +400,34 @@ static size_t smem_bytes(int n, int dfix) { return (size_t)n * 8 + 64 * sizeof(B
 
 using namespace idff;
 
+static int g_ot_sap = 0;   // diagnostic: 1 = always the augmenting-path kernel (idff_debug_ot_sap)
+extern "C" int idff_debug_ot_sap(int32_t on) {
+  g_ot_sap = on ? 1 : 0;
+  return IDFF_OK;
+}
+
 extern "C" int idff_ot_assign(const float* d_x0, const float* d_x1, int32_t n, int32_t D, int64_t* d_perm, double* d_cost,
                               void* stream) {
   IDFF_CHECK_ARG(n >= 0 && n <= ot::MAXN, "idff_ot_assign: n = %d outside [0, %d]", n, ot::MAXN);
   IDFF_CHECK_ARG(D >= 1, "idff_ot_assign: D = %d", D);
   if (n == 0) return IDFF_OK;
   IDFF_CHECK_ARG(d_x0 && d_x1 && d_perm, "idff_ot_assign: null pointer");
-  const int threads = ((n + 31) / 32) * 32;
-  const size_t sm = ot::smem_bytes(n, D == 2 ? 2 : 0);
   cudaStream_t s = (cudaStream_t)stream;
-  if (D == 2) ot::k_ot_assign<2><<<1, threads, sm, s>>>(d_x0, d_x1, n, D, d_perm, d_cost);
-  else ot::k_ot_assign<0><<<1, threads, sm, s>>>(d_x0, d_x1, n, D, d_perm, d_cost);
+  if (n > 64 && !g_ot_sap) {   // auction: parallel over the unassigned rows
+    const size_t sm = ot::auction_smem_bytes(n, D == 2 ? 2 : 0);
+    if (D == 2) {
+      IDFF_CUDA(cudaFuncSetAttribute(ot::k_ot_auction<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      ot::k_ot_auction<2><<<1, 512, sm, s>>>(d_x0, d_x1, n, D, d_perm, d_cost);
+    } else {
+      IDFF_CUDA(cudaFuncSetAttribute(ot::k_ot_auction<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      ot::k_ot_auction<0><<<1, 512, sm, s>>>(d_x0, d_x1, n, D, d_perm, d_cost);
+    }
+  } else {                     // augmenting paths: small problems, and the yardstick behind idff_debug_ot_sap
+    const int threads = ((n + 31) / 32) * 32;
+    const size_t sm = ot::smem_bytes(n, D == 2 ? 2 : 0);
+    if (D == 2) ot::k_ot_assign<2><<<1, threads, sm, s>>>(d_x0, d_x1, n, D, d_perm, d_cost);
+    else ot::k_ot_assign<0><<<1, threads, sm, s>>>(d_x0, d_x1, n, D, d_perm, d_cost);
+  }
   IDFF_CUDA(cudaGetLastError());
   count_launch();
   return IDFF_OK;

@@ -3,7 +3,7 @@
 The reference computes the exact plan between two minibatches of equal size with uniform marginals on the host (POT's
 network simplex, `pot.emd`, batch 256) and samples index pairs from it with numpy.  For those marginals the exact plan is
 1/n times a permutation matrix, so the coupling is an assignment problem.  On CUDA tensors it is solved where the data lives
-(`idff_ot_assign`: exact shortest-augmenting-path assignment in fp64, one launch) and the index pairs are drawn on the device:
+(`idff_ot_assign`: fp64 assignment in one launch -- augmenting paths for small batches, an epsilon-scaling auction above 64) and the index pairs are drawn on the device:
 no host round trip, graph-capturable, and they feed `idff_path_sample` as fused gather indices.  `get_map` / `sample_map`
 keep the reference's host-side signatures (numpy plan in, numpy indices out; POT is not installed here, so the plan comes
 from scipy's assignment solver)."""

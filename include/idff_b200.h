@@ -209,7 +209,11 @@ int idff_train_flow_steps(float* d_state, const float* d_x0, const float* d_x1, 
  * exact plan of uniform equal-size marginals is 1/n times a permutation matrix, so the plan is returned as the permutation:
  * d_perm [n] int64, plan[i][perm[i]] = 1/n; sample_plan (:120-142) then draws i uniformly and pairs x0[i] with x1[perm[i]]
  * (the gather inputs d_idx0 / d_idx1 of idff_path_sample).  d_x0, d_x1 [n][D] fp32; n <= 1024; d_cost (optional): the plan's
- * total cost sum_i |x0[i] - x1[perm[i]]|^2 in fp64.  Exact shortest-augmenting-path assignment in fp64, one launch. */
+ * total cost sum_i |x0[i] - x1[perm[i]]|^2 in fp64.  fp64 throughout, one launch: shortest augmenting paths for n <= 64, an
+ * epsilon-scaling auction above (eps down to max(c) 2^-40: the optimum unless another plan is within n max(c) 2^-40 of it). */
+/* Diagnostic: on != 0 makes idff_ot_assign use the augmenting-path kernel for every size (default: n <= 64 only; above that an
+ * epsilon-scaling auction, exact up to plans whose costs differ by less than n max(c) 2^-40). */
+int idff_debug_ot_sap(int32_t on);
 int idff_ot_assign(const float* d_x0, const float* d_x1, int32_t n, int32_t D, int64_t* d_perm, double* d_cost, void* stream);
 
 /* ---- TrajectoryGenerator.generate_trajectories, timeseris_example/MD_simulation.py:197-213 -- n_frames

@@ -27,15 +27,42 @@ def test_assignment_is_the_exact_plan(cuda_device, n, D):
     np.testing.assert_array_equal(perm, perm_ref)                         # ... and (generic data: unique) the same plan
 
 
+def test_auction_and_augmenting_path_kernels_agree(cuda_device):
+    """n > 64 runs the epsilon-scaling auction, n <= 64 (or idff_debug_ot_sap) the shortest-augmenting-path kernel: same
+    permutation and cost on generic data, for D = 2 and a wide D; non-finite inputs terminate and still return a permutation."""
+    g = torch.Generator().manual_seed(77)
+    for n, D in ((65, 2), (200, 2), (300, 7), (640, 2)):
+        x0 = torch.randn(n, D, generator=g).to(cuda_device)
+        x1 = (torch.randn(n, D, generator=g) * 0.7 - 0.4).to(cuda_device)
+        pa, ca = ot.ot_assign(x0, x1, return_cost=True)
+        _lib.check(_lib.lib().idff_debug_ot_sap(1), "ot_sap")
+        try:
+            ps, cs = ot.ot_assign(x0, x1, return_cost=True)
+        finally:
+            _lib.check(_lib.lib().idff_debug_ot_sap(0), "ot_sap")
+        assert torch.equal(pa, ps), (n, D)
+        assert ca.item() == pytest.approx(cs.item(), rel=1e-12)
+    x0 = torch.randn(100, 2, generator=g)
+    x0[3, 1] = float("nan")
+    x0[40, 0] = float("inf")
+    p = ot.ot_assign(x0.to(cuda_device), torch.randn(100, 2, generator=g).to(cuda_device))
+    assert sorted(p.cpu().tolist()) == list(range(100))
+
+
 def test_ties_and_degenerate_inputs(cuda_device):
     """Duplicate points (many optimal plans): any optimal permutation is acceptable, the cost must be the optimum."""
-    x0 = torch.tensor([[0.0, 0.0]] * 8 + [[1.0, 1.0]] * 8)
-    x1 = torch.tensor([[1.0, 1.0]] * 8 + [[0.0, 0.0]] * 8)
-    perm, cost = ot.ot_assign(x0.to(cuda_device), x1.to(cuda_device), return_cost=True)
-    assert sorted(perm.cpu().tolist()) == list(range(16)) and cost.item() == 0.0
-    x = torch.randn(33, 2)
-    perm, cost = ot.ot_assign(x.to(cuda_device), x.to(cuda_device), return_cost=True)
-    assert perm.cpu().tolist() == list(range(33)) and cost.item() == 0.0
+    for rep in (8, 48):                                  # 16 rows: augmenting paths; 96 rows: auction
+        x0 = torch.tensor([[0.0, 0.0]] * rep + [[1.0, 1.0]] * rep)
+        x1 = torch.tensor([[1.0, 1.0]] * rep + [[0.0, 0.0]] * rep)
+        perm, cost = ot.ot_assign(x0.to(cuda_device), x1.to(cuda_device), return_cost=True)
+        assert sorted(perm.cpu().tolist()) == list(range(2 * rep)) and cost.item() == 0.0
+    z = torch.zeros(80, 2, device=cuda_device)           # every plan is optimal
+    perm, cost = ot.ot_assign(z, z, return_cost=True)
+    assert sorted(perm.cpu().tolist()) == list(range(80)) and cost.item() == 0.0
+    for n in (33, 130):
+        x = torch.randn(n, 2)
+        perm, cost = ot.ot_assign(x.to(cuda_device), x.to(cuda_device), return_cost=True)
+        assert perm.cpu().tolist() == list(range(n)) and cost.item() == 0.0
     with pytest.raises(_lib.IdffError):
         ot.ot_assign(torch.zeros(2000, 2, device=cuda_device), torch.zeros(2000, 2, device=cuda_device))
     with pytest.raises(_lib.IdffError):
