@@ -204,11 +204,11 @@ __global__ void __launch_bounds__(512, 1) k_ot_auction(const float* __restrict__
   int* winner = mine + n;                                                          // [n] lowest row among the highest bidders
   int* bidcol = winner + n;                                                        // [n] column row i bid on this round
   int* list = bidcol + n;                                                          // [n] unassigned rows, in row order
-  int* ccnt = list + n;                                                            // [32] unassigned rows per chunk of 32
+  int* bidcol2 = list + n;                                                         // [n] the other list buffer
+  int* ccnt = bidcol2 + n;                                                         // [32] list lengths
   float* xs0 = reinterpret_cast<float*>(ccnt + 32);                                // [n][DFIX]
   float* xs1 = xs0 + (DFIX > 0 ? n * DFIX : 0);                                    // [n][DFIX]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;   // 16 warps
-  const int nchunk = (n + 31) >> 5;                                                // <= 32 chunks: 2 per warp
 
   if (DFIX > 0)
     for (int i = tid; i < n * DFIX; i += blockDim.x) { xs0[i] = x0[i]; xs1[i] = x1[i]; }
@@ -248,34 +248,24 @@ __global__ void __launch_bounds__(512, 1) k_ot_auction(const float* __restrict__
     last = eps <= eps_final;
     for (int i = tid; i < n; i += blockDim.x) { owner[i] = -1; mine[i] = -1; }
     __syncthreads();
+    // the unassigned rows of the next round are collected by the rows themselves (losing bidders, displaced owners) with an
+    // atomic counter: the list order varies from run to run, the result does not -- the bids of a round do not depend on each
+    // other and a column's winner is chosen by value, then by row index
+    for (int i = tid; i < n; i += blockDim.x) list[i] = i;
+    if (tid == 0) { ccnt[0] = n; ccnt[1] = 0; }
+    __syncthreads();
+    int cur = 0;   // ccnt[cur]: rows in list (this round), ccnt[cur ^ 1]: counter of the next round's list
+    int* lists[2] = {list, bidcol2};
     for (long round = 0; round < round_cap; ++round) {
-      // (1) the unassigned rows, compacted in row order (deterministic)
-      unsigned m2[2];
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int c = warp + q * nwarps, i = c * 32 + lane;
-        m2[q] = __ballot_sync(0xffffffffu, c < nchunk && i < n && mine[i] < 0);
-        if (lane == 0 && c < 32) ccnt[c] = __popc(m2[q]);
-      }
-      __syncthreads();
-      int nun = 0;
-      for (int c = 0; c < nchunk; ++c) nun += ccnt[c];
-      if (nun == 0) break;   // uniform: every thread computed the same sum
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int c = warp + q * nwarps;
-        if (c < nchunk && ((m2[q] >> lane) & 1u)) {
-          int off = 0;
-          for (int cc = 0; cc < c; ++cc) off += ccnt[cc];
-          list[off + __popc(m2[q] & ((1u << lane) - 1u))] = c * 32 + lane;
-        }
-      }
-      __syncthreads();
+      const int nun = ccnt[cur];
+      if (nun == 0) break;
+      const int* L = lists[cur];
+      int* Lnext = lists[cur ^ 1];
       if (nun == 1) {
         // the common tail of a phase: ONE unassigned row.  Its bid displaces an owner, who is then the only unassigned row, and so
-        // on until a free column is taken: warp 0 walks that chain alone (same bids, no block barriers, no compaction)
+        // on until a free column is taken: warp 0 walks that chain alone (same bids, no block barriers)
         if (warp == 0) {
-          int i = list[0];
+          int i = L[0];
           for (long hop = 0; hop < round_cap; ++hop) {
             double w1 = -1.0e300, w2 = -1.0e300;
             int j1 = 0x7fffffff;
@@ -304,13 +294,14 @@ __global__ void __launch_bounds__(512, 1) k_ot_auction(const float* __restrict__
             if (prev < 0) break;
             i = prev;
           }
+          if (lane == 0) { ccnt[cur] = 0; ccnt[cur ^ 1] = 0; }
         }
         __syncthreads();
-        continue;
+        continue;   // the next iteration sees an empty list and ends the phase (a capped chain leaves its row unassigned)
       }
-      // (2) bids: one warp per unassigned row scans all columns for its best and second-best value
+      // (1) bids: one warp per unassigned row scans all columns for its best and second-best value
       for (int u = warp; u < nun; u += nwarps) {
-        const int i = list[u];
+        const int i = L[u];
         double w1 = -1.0e300, w2 = -1.0e300;
         int j1 = 0x7fffffff;
         for (int j = lane; j < n; j += 32) {
@@ -333,30 +324,38 @@ __global__ void __launch_bounds__(512, 1) k_ot_auction(const float* __restrict__
           atomicMax(&maxbid[j1], (unsigned long long)__double_as_longlong(bid));   // bids are positive: bit order = value order
         }
       }
+      if (tid == 0) ccnt[cur ^ 1] = 0;
       __syncthreads();
-      // (3) the lowest row among a column's highest bidders wins
+      // (2) the lowest row among a column's highest bidders wins
       for (int u = tid; u < nun; u += blockDim.x) {
-        const int i = list[u], j1 = bidcol[i];
+        const int i = L[u], j1 = bidcol[i];
         if ((unsigned long long)__double_as_longlong(bidval[i]) == maxbid[j1]) atomicMin(&winner[j1], i);
       }
       __syncthreads();
-      // (4) winners take their columns at the price they bid; the previous owner becomes unassigned
+      // (3) winners take their columns at the price they bid and reset the column's bid state; losers and displaced owners
+      // enter the next round's list
       for (int u = tid; u < nun; u += blockDim.x) {
-        const int i = list[u], j1 = bidcol[i];
+        const int i = L[u], j1 = bidcol[i];
         if (winner[j1] == i) {
           const int prev = owner[j1];
-          if (prev >= 0) mine[prev] = -1;
+          if (prev >= 0) {
+            mine[prev] = -1;
+            Lnext[atomicAdd(&ccnt[cur ^ 1], 1)] = prev;
+          }
           owner[j1] = i;
           mine[i] = j1;
           price[j1] = bidval[i];
+        } else {
+          Lnext[atomicAdd(&ccnt[cur ^ 1], 1)] = i;
         }
       }
       __syncthreads();
-      for (int u = tid; u < nun; u += blockDim.x) {
-        const int j1 = bidcol[list[u]];
+      for (int u = tid; u < nun; u += blockDim.x) {   // (after every bidder has read winner[]: all bidders of a column write the same)
+        const int j1 = bidcol[L[u]];
         maxbid[j1] = 0ull;
         winner[j1] = 0x7fffffff;
       }
+      cur ^= 1;
       __syncthreads();
     }
     eps = fmax(eps * (1.0 / 6.0), eps_final);
@@ -390,7 +389,7 @@ __global__ void __launch_bounds__(512, 1) k_ot_auction(const float* __restrict__
 }
 
 static size_t auction_smem_bytes(int n, int dfix) {
-  return (size_t)n * 8 * 3 + 32 * 8 + (size_t)n * 4 * 5 + 32 * 4 + (size_t)2 * n * dfix * 4 + 16;
+  return (size_t)n * 8 * 3 + 32 * 8 + (size_t)n * 4 * 6 + 32 * 4 + (size_t)2 * n * dfix * 4 + 16;
 }
 
 static size_t smem_bytes(int n, int dfix) { return (size_t)n * 8 + 64 * sizeof(Best) + (size_t)4 * n * 4 + (size_t)n * dfix * 4 + 16; }
