@@ -254,7 +254,61 @@ extern "C" int idff_sample_rk4_sweep(const idff_weights_t* w, const idff_field_p
     wide_batched = wide_batched && wide_sweep_supports(w, wp.data(), n_sets, N);
   }
   if (!batched && !wide_batched) {
+    // Mixed sweep (the order-3 grid holds tuples with gamma3 == 0, which the fused tensor kernel serves, next to tuples that
+    // need three jets): split the sets into classes that batch -- class 0: fused tensor kernel; class 1 + 2 nj + rev: layered
+    // engine with that jet count -- solve every class of two or more sets as one batch into a staging buffer and scatter the
+    // rows to their slots; the rest one call per set.
+    std::vector<int> cls(n_sets, -1);
+    std::vector<std::vector<int>> members(8);
+    if (n_iv >= 1 && n_iv <= kMaxSweepIntervals) {
+      for (int g = 0; g < n_sets; ++g) {
+        const idff_field_params_t& q = params[g];
+        idff_field_params_t qq;
+        if ((q.impl == IDFF_IMPL_AUTO || q.impl == IDFF_IMPL_TENSOR16) && tensor16_supports(w, &q) && q.variant == params[0].variant &&
+            q.t_idx == params[0].t_idx) {
+          cls[g] = 0;
+        } else if (N % 128 == 0 && q.variant == IDFF_FIELD_MOMENTUM && routes_to_wide(w, &q, N, &qq)) {
+          int nj, rev;
+          jets_needed(q, &nj, &rev);
+          cls[g] = 1 + 2 * (nj - 1) + (rev ? 1 : 0);
+        }
+        if (cls[g] >= 0) members[cls[g]].push_back(g);
+      }
+    }
+    for (int c = 0; c < 8; ++c) {
+      const std::vector<int>& mem = members[c];
+      if (mem.size() < 2 || (int)mem.size() == n_sets) {   // (a class that is the whole sweep already failed to batch above)
+        for (int g : mem) cls[g] = -1;
+        continue;
+      }
+      std::vector<idff_field_params_t> sub(mem.size());
+      for (size_t k = 0; k < mem.size(); ++k) sub[k] = params[mem[k]];
+      idff_weights_t* wm = const_cast<idff_weights_t*>(w);
+      const size_t bytes = mem.size() * set_floats * sizeof(float);
+      {
+        DeviceGuard guard(w->device);
+        if (wm->sweep_out_bytes < bytes) {
+          if (wm->d_sweep_out) cudaFree(wm->d_sweep_out);
+          wm->d_sweep_out = nullptr;
+          wm->sweep_out_bytes = 0;
+          IDFF_CUDA(cudaMalloc(&wm->d_sweep_out, bytes));
+          wm->sweep_out_bytes = bytes;
+        }
+      }
+      int rc = idff_sample_rk4_sweep(w, sub.data(), (int)sub.size(), d_x0, h_t_grid, n_grid, wm->d_sweep_out, N, stream);
+      if (rc) return rc;
+      DeviceGuard guard(w->device);
+      size_t k = 0;
+      while (k < mem.size()) {   // scatter, runs of consecutive sets in one copy
+        size_t e = k + 1;
+        while (e < mem.size() && mem[e] == mem[e - 1] + 1) ++e;
+        IDFF_CUDA(cudaMemcpyAsync(d_out + (size_t)mem[k] * set_floats, wm->d_sweep_out + k * set_floats, (e - k) * set_floats * sizeof(float),
+                                  cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        k = e;
+      }
+    }
     for (int g = 0; g < n_sets; ++g) {
+      if (cls[g] >= 0) continue;
       int rc = idff_sample_rk4(w, &params[g], d_x0, h_t_grid, n_grid, d_out + (size_t)g * set_floats, nullptr, N, stream);
       if (rc) return rc;
     }

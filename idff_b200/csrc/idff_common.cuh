@@ -94,6 +94,8 @@ struct idff_weights {
   int tc_verified;      // bit 0 / 1: the first fused / layered tcgen05 launch on this handle was checked (alignment flag)
   void* d_sweep;        // device copy of the SweepTab array of the last idff_sample_rk4_sweep call
   size_t sweep_bytes;
+  float* d_sweep_out;   // staging buffer of a mixed gamma sweep (one class of sets at a time), grow-only
+  size_t sweep_out_bytes;
 };
 
 namespace idff {

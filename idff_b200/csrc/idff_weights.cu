@@ -280,6 +280,7 @@ extern "C" int idff_weights_create(const float* const* h_W, const float* const* 
   v.tcw16_tiles = wide_layout ? d_blob + o_tw : nullptr;
   h->d_stash = nullptr; h->stash_bytes = 0; h->tc_verified = 0;
   h->d_sweep = nullptr; h->sweep_bytes = 0;
+  h->d_sweep_out = nullptr; h->sweep_out_bytes = 0;
   *out = h;
   return IDFF_OK;
 }
@@ -289,6 +290,7 @@ extern "C" int idff_weights_destroy(idff_weights_t* w) {
   cudaFree(w->d_blob);
   if (w->d_stash) cudaFree(w->d_stash);
   if (w->d_sweep) cudaFree(w->d_sweep);
+  if (w->d_sweep_out) cudaFree(w->d_sweep_out);
   delete w;
   return IDFF_OK;
 }

@@ -112,8 +112,9 @@ int idff_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, const
  * 8x8 tuples; Autograd_example_order3.py:288-314, 10^3 tuples): the same x0 [N][dim] and t grid solved under n_sets
  * parameter sets (params[g]: same variant and dim, any gammas / order / sigma).  d_out [n_sets][N][dim] = traj[-1] of every
  * set.  One launch for all sets where the 3xFP16 tensor kernel serves them (the reference's 2048 particles fill 32 of 148
- * SMs per tuple; 64 tuples fill the machine), otherwise one fused launch per set -- results are identical to calling
- * idff_sample_rk4 per set either way. */
+ * SMs per tuple; 64 tuples fill the machine); sets that need three jets are solved as one batch on the layered engine (N a
+ * multiple of 128); a mixed sweep is split into such classes and the rows scattered to their slots; whatever remains takes one
+ * launch per set -- results are identical to calling idff_sample_rk4 per set in every case. */
 int idff_sample_rk4_sweep(const idff_weights_t* w, const idff_field_params_t* params, int32_t n_sets, const float* d_x0,
                           const float* h_t_grid, int32_t n_grid, float* d_out, int64_t N, void* stream);
 

@@ -276,6 +276,17 @@ def test_order3_sweep_batched_on_layered_engine(cuda_device):
         assert torch.equal(one, per[0])
         for k in range(len(tuples)):
             assert torch.equal(got[k], per[k]), (nfe, tuples[k])
+    # a mixed sweep (the reference's order-3 grid contains gamma3 == 0 tuples, which the fused tensor kernel serves): the sets
+    # are split into classes, each class solved as one batch and scattered to its slots -- still bit-identical per tuple
+    mixed = [(0.2, 0.2, 0.0), (0.2, 0.2, 0.2), (0.5, 0.0, 0.0), (0.0, 0.0, 0.1), (1.0, 2.0, 0.0), (0.3, 0.1, -0.2), (0.5, 0.0, 0.3)]
+    mm = [fields.CustomNetModelOrder3(pw, 0.2, *g) for g in mixed]
+    ts = torch.linspace(0, 1, 3)
+    per = [sampler.sample_rk4(m, x0, ts) for m in mm]
+    before = _lib.launch_count()
+    got = sampler.sample_rk4_sweep(mm, x0, ts)
+    assert _lib.launch_count() - before < sum(1 for _ in mm) * 20
+    for k in range(len(mixed)):
+        assert torch.equal(got[k], per[k]), mixed[k]
     # ragged N falls back to per-set solves, same results
     x1 = x0[:2048 - 64 + 3].contiguous()
     got = sampler.sample_rk4_sweep(models[:2], x1, torch.linspace(0, 1, 3))
