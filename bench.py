@@ -455,6 +455,12 @@ def aux_measurements(dev, pw, model, peaks):
             fin = O3.odeint_rk4(O3.Field2D(lay, 0.2, gam, 2), xc, torch.linspace(0, 1, 3))[-1]
             O3.mmd_rbf(tc_, fin)
         s_cpu = (time.perf_counter() - t0) / 4 * 64
+        # the order-3 script's sweep (Autograd_example_order3.py:288-314): 10 x 10 x 10 tuples
+        grid10 = [0.0, 0.1, 0.2, 0.3, 0.5, 0.7, 1.0, 1.5, 2.0, 3.0]
+        s_sw3 = timeit(lambda: sweep_mod.find_best_gammas_mmd(pw, xs2k, true2k, gamma_range=grid10, nfe=2, sigma=0.2,
+                                                              sigma_kernel=1.0, order=3), reps=2, warm=1)
+        aux["gamma_sweep_order3_10x10x10_N2048_nfe2"] = {"ms": s_sw3 * 1e3, "tuples": 1000,
+                                                         "particle_steps_per_s": 1000 * 2048 * 8 / s_sw3}
         aux["gamma_sweep_8x8_N2048_nfe2"] = {"ms": s_sw * 1e3, "launches": 2, "reference_cpu_ms": s_cpu * 1e3,
                                              "reference_cpu_note": "4 of the 64 tuples timed on the host cores, x16"}
     except Exception as exc:
