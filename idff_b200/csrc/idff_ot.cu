@@ -358,7 +358,10 @@ __global__ void __launch_bounds__(512, 1) k_ot_auction(const float* __restrict__
       cur ^= 1;
       __syncthreads();
     }
-    eps = fmax(eps * (1.0 / 6.0), eps_final);
+#ifndef IDFF_OT_THETA
+#define IDFF_OT_THETA 6.0
+#endif
+    eps = fmax(eps * (1.0 / IDFF_OT_THETA), eps_final);
   }
   __syncthreads();
   // rows left unassigned by the round cap (non-finite inputs only) take the free columns in order: still a permutation
