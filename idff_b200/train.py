@@ -47,15 +47,34 @@ def flow_train_step(model, optimizer, FM, x0, x1, t=None, clip: float = 1.0):
     return loss.detach()
 
 
+def scorehead_train_step(model, optimizer, FM, x0, x1, sigma0, t=None, clip: float = 1.0):
+    """One training step of the order-1 script with the score head (example_order1_with_prediction_head.py:111-137):
+    outs = model(cat[xt, xt, t]); vt, st = outs[:, :D], outs[:, D:]; loss = flow_loss(vt) + mean((st - logp)^2) with
+    logp = log_prob_xt_given_x1_dimwise(xt, x1, x0, t, sigma0) (:26-51, :126); clip; AdamW.  The path sample and both loss
+    terms (value + gradient, one pass each) are kernels; the MLP runs in torch.  Returns the loss (0-d device tensor)."""
+    optimizer.zero_grad(set_to_none=False)
+    t, xt, ut, eps = FM.sample_location_and_conditional_flow(x0, x1, t=t, return_noise=True)     # :116
+    outs = model(torch.cat([xt, xt, t[:, None]], dim=-1))                                         # :119
+    D = x1.shape[1]
+    vt, st = outs[:, :D].contiguous(), outs[:, D:].contiguous()                                   # :120-121
+    loss = losses.flow_loss(vt, FM.x1, t) + losses.score_loss(st, xt, FM.x1, FM.x0, t, sigma0)    # :126-132
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_(model.parameters(), clip)
+    optimizer.step()
+    return loss.detach()
+
+
 class GraphedFlowTrainer:
-    """Captures `flow_train_step` (with on-device data and time draws) into a CUDA graph.
+    """Captures `flow_train_step` (with on-device data and time draws) into a CUDA graph; `score_sigma` not None captures
+    `scorehead_train_step` instead (the order-1 script: MLP(dim=4, w=256, time_varying=True), AdamW lr 1e-3, sigma 0.2).
 
     trainer = GraphedFlowTrainer(model, batch_size=256); for _ in range(n): loss = trainer.step()
     `loss` is a device tensor that the next replay overwrites; read it with .item() only when needed."""
 
     def __init__(self, model: torch.nn.Module, batch_size: int = 256, sigma: float = 0.0, lr: float = 2e-4,
-                 clip: float = 1.0, data=checkerboard_device, device=None, warmup: int = 3):
+                 clip: float = 1.0, data=checkerboard_device, device=None, warmup: int = 3, score_sigma=None):
         self.model = model
+        self.score_sigma = score_sigma
         self.device = torch.device(device) if device is not None else next(model.parameters()).device
         if self.device.type != "cuda":
             raise RuntimeError("GraphedFlowTrainer needs a CUDA device: idff_b200 has no CPU path")
@@ -80,7 +99,11 @@ class GraphedFlowTrainer:
         x1 = self.data(self.B, self.device)
         x0 = torch.randn_like(x1)
         t = torch.rand(self.B, device=self.device)          # on the device: a host draw cannot be captured
-        self.loss.copy_(flow_train_step(self.model, self.optimizer, self.FM, x0, x1, t=t, clip=self.clip))
+        if self.score_sigma is None:
+            self.loss.copy_(flow_train_step(self.model, self.optimizer, self.FM, x0, x1, t=t, clip=self.clip))
+        else:
+            self.loss.copy_(scorehead_train_step(self.model, self.optimizer, self.FM, x0, x1, self.score_sigma, t=t,
+                                                 clip=self.clip))
 
     def step(self) -> torch.Tensor:
         self.graph.replay()
