@@ -193,3 +193,22 @@ def test_rejects_unsupported_shapes(cuda_device):
     from idff_b200.torchcfm.models.models import MLP
     with pytest.raises(_lib.IdffError):
         train.FusedFlowTrainer(MLP(dim=2, w=128, time_varying=True).to(dev))
+
+
+def test_eight_gaussians_device_sampler_and_training(cuda_device):
+    """BASELINE configs[0] (8gaussians): the on-device data draw has the reference's law (8 modes at radius 5, std 0.1**0.25)
+    and the fused trainer learns on it."""
+    x = train.eight_gaussians_device(200000, cuda_device).cpu()
+    rad = x.norm(dim=1)
+    assert abs(rad.mean().item() - 5.0) < 0.1
+    ang = torch.atan2(x[:, 1], x[:, 0])
+    mode = torch.round(ang / (np.pi / 4)) % 8
+    counts = torch.bincount(mode.long(), minlength=8).float() / len(x)
+    assert (counts - 0.125).abs().max().item() < 0.01
+    ref = O.eight_gaussians(200000)
+    assert abs(x.std(0).mean().item() - ref.std(0).mean().item()) < 0.05
+    tr = train.FusedFlowTrainer(_fresh_mlp(cuda_device, seed=5), batch_size=256, lr=2e-3, data=train.eight_gaussians_device)
+    first = tr.run(50).cpu().numpy()
+    tr.run(1500)
+    last = tr.run(50).cpu().numpy()
+    assert np.isfinite(last).all() and last.mean() < 0.7 * first.mean(), (first.mean(), last.mean())
