@@ -104,6 +104,7 @@ class GraphedFlowTrainer:
         with torch.cuda.graph(self.graph):
             self._eager()
         self.steps = 0
+        self._params = list(model.parameters())
 
     def _eager(self):
         x1 = self.data(self.B, self.device)
@@ -117,6 +118,9 @@ class GraphedFlowTrainer:
 
     def step(self) -> torch.Tensor:
         self.graph.replay()
+        # a graph replay writes the parameters without touching their version counters: bump them, so that caches keyed on
+        # _version (the sampler's packed weights, weights.packed_for) see the update
+        torch.autograd.graph.increment_version(self._params)
         self.steps += 1
         return self.loss
 
@@ -159,6 +163,7 @@ class GraphedMDTrainer:
         with torch.cuda.graph(self.graph):
             self._eager()
         self.steps = 0
+        self._params = list(model.parameters())
 
     def _eager(self):
         idx = torch.randint(1, self.dataset.shape[0], (self.B,), device=self.device)      # :128
@@ -167,6 +172,9 @@ class GraphedMDTrainer:
 
     def step(self) -> torch.Tensor:
         self.graph.replay()
+        # a graph replay writes the parameters without touching their version counters: bump them, so that caches keyed on
+        # _version (the sampler's packed weights, weights.packed_for) see the update
+        torch.autograd.graph.increment_version(self._params)
         self.steps += 1
         return self.loss
 
@@ -253,8 +261,7 @@ class FusedFlowTrainer:
             C.byref(self.opt), self.steps_done, _lib.ptr(loss), _lib.ptr(gnorm), _lib.ptr(grad_dump),
             _lib.stream_of(self.state)), "idff_train_flow_steps")
         self.steps_done += S
-        for p in self.model.parameters():      # the kernel wrote them in place: invalidate caches keyed on _version
-            torch.autograd.graph.increment_version(p)
+        torch.autograd.graph.increment_version(list(self.model.parameters()))   # the kernel wrote them in place
         self._versions = [p._version for p in self.model.parameters()]
         return (loss, gnorm) if return_gnorm else loss
 

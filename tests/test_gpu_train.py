@@ -314,3 +314,25 @@ def test_scorehead_train_step_matches_reference_formula(cuda_device):
         tr.step()
     last = [tr.step().item() for _ in range(20)]
     assert np.isfinite(first + last).all() and np.mean(last) < np.mean(first)
+
+
+def test_graph_trained_weights_reach_the_sampler(cuda_device):
+    """A CUDA-graph replay updates the parameters without touching their version counters; the trainers bump them, so the
+    sampler's packed-weights cache (keyed on data_ptr and _version) is rebuilt after further training."""
+    from idff_b200 import fields, sampler, train
+    from idff_b200.weights import packed_for
+    model = _fresh_mlp(cuda_device, seed=2)
+    tr = train.GraphedFlowTrainer(model, batch_size=256, lr=1e-2)
+    x0 = torch.randn(512, 2, device=cuda_device)
+    ts = torch.linspace(0, 1, 3)
+    f = fields.CustomNetModel(model, 0.2, 0.2, 0.0)
+    a = sampler.sample_rk4(f, x0, ts).clone()
+    pw_a = packed_for(model, cuda_device)
+    for _ in range(50):
+        tr.step()
+    b = sampler.sample_rk4(f, x0, ts)
+    assert packed_for(model, cuda_device) is not pw_a
+    assert not torch.equal(a, b)
+    ref = O.odeint_rk4(O.Field2D([(m.weight.detach().cpu(), m.bias.detach().cpu()) for m in model.net
+                                  if isinstance(m, torch.nn.Linear)], 0.2, (0.2, 0.0), 2), x0.cpu(), ts)[-1]
+    assert (b.cpu() - ref).abs().median().item() < 1e-4
