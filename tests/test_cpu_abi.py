@@ -80,3 +80,30 @@ def test_stage_scalars_follow_reference_op_order():
         assert s[2] == torch.sqrt(1 - (0.3 + 0.7) * st2).item()
         assert s[4] == (0.5 * (2 * 0.3 - 1) * torch.ones(()) * st2).item()
         assert s[5] == (0.7 * torch.ones(()) * st2).item()
+
+
+def test_new_entry_points_validate_without_a_gpu():
+    """The trainer's state layout matches nn.Linear's parameter shapes; the later entry points reject bad arguments and treat
+    empty work as a no-op before touching a device."""
+    L = _lib.lib()
+    off = (C.c_int64 * 12)()
+    assert L.idff_train_flow_offsets(off) == 0
+    o = list(off)
+    torch.manual_seed(0)
+    from idff_b200.torchcfm.models.models import MLP
+    sizes = [p.numel() for p in MLP(dim=2, w=256, time_varying=True).parameters()]
+    assert o[0] == 0 and [o[i + 1] - o[i] for i in range(7)] == sizes[:7] and o[8] == sum(sizes)
+    assert o[9] == 0 and o[10] >= o[8] and o[11] - o[10] == o[10] - o[9] and (o[10] * 4) % 16 == 0
+    assert L.idff_train_flow_state_floats() > o[11] + o[8]
+    assert L.idff_train_flow_offsets(None) == -1
+    opt = _lib.AdamW(2e-4, 0.9, 0.999, 1e-8, 1e-2, 1.0)
+    assert L.idff_train_flow_steps(None, None, None, None, None, 1, 256, 0.0, 1, C.byref(opt), 0, None, None, None, None) == -1
+    fake = C.c_void_p(4096)     # aligned, never dereferenced: validation happens first
+    assert L.idff_train_flow_steps(fake, None, None, None, None, 0, 256, 0.0, 1, C.byref(opt), 0, None, None, None, None) == 0
+    assert L.idff_train_flow_steps(fake, fake, fake, fake, None, 1, 6, 0.0, 1, C.byref(opt), 0, None, None, None, None) == -1
+    assert b"multiple of 4" in L.idff_last_error()
+    assert L.idff_train_flow_steps(fake, fake, fake, fake, None, 1, 1024, 0.0, 1, C.byref(opt), 0, None, None, None, None) == -1
+    assert L.idff_ot_assign(None, None, 0, 2, None, None, None) == 0
+    assert L.idff_ot_assign(None, None, 5000, 2, None, None, None) == -1
+    assert L.idff_ot_assign(None, None, 8, 2, None, None, None) == -1
+    assert L.idff_debug_train_stamps(None, 4) == -1
