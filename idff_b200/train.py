@@ -220,6 +220,12 @@ class FusedFlowTrainer:
         self.steps_done = 0
         self.sync_params()
 
+    def state_dict(self):
+        """model.state_dict() with every tensor cloned out of the kernel's state buffer -- what the reference saves when the
+        loss improves (Autograd_example_order2.py:115-117).  (The module's own state_dict() returns views of one 13 MB buffer,
+        which torch.save would write whole.)"""
+        return {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+
     def sync_params(self):
         """Rebuild the kernel's streaming weight copies after the parameters were written from outside (load_state_dict,
         manual edits).  `steps` calls it by itself when a parameter's version counter moved since the last launch."""

@@ -156,6 +156,11 @@ def test_model_aliases_state_and_feeds_the_sampler(cuda_device):
     tt = torch.full((64, 1), 0.3, device=dev)
     ref = O.mlp_forward(_layers_of(model), torch.cat([x, tt], 1).cpu())
     np.testing.assert_allclose(model(torch.cat([x, tt], 1)).detach().cpu().numpy(), ref.numpy(), rtol=1e-4, atol=1e-5)
+    sd = tr.state_dict()
+    assert set(sd) == set(model.state_dict()) and all(v.untyped_storage().nbytes() == v.numel() * 4 for v in sd.values())
+    fresh = _fresh_mlp(dev, seed=99)
+    fresh.load_state_dict(sd)                             # the checkpoint format of the reference (:116)
+    assert torch.equal(fresh.net[4].weight, model.net[4].weight)
     pw = PackedWeights.from_module(model, device=dev)
     f = fields.CustomNetModel(pw, 0.2, 0.2, 0.0)
     out = sampler.sample_rk4(f, x, torch.linspace(0, 1, 3))
