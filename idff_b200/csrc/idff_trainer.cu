@@ -35,7 +35,7 @@
 namespace idff {
 namespace trn {
 
-constexpr int W = 256, DIN = 3, DOUT = 2, RMIN = 4, RMAX = 4, NC = 512, NT = NC + 32, MAXB = IDFF_TRAIN_MAX_BATCH;
+constexpr int W = 256, DIN = 3, DOUT = 2, RMIN = 4, RMAX = 4, NC = 512, NT = NC + 32, MAXB = IDFF_TRAIN_MAX_BATCH;   // RMIN / RMAX: batch rows per row group (template R of the kernels; both 4 -- 8 rows per CTA pair was measured slower)
 constexpr int oW0 = 0, ob0 = oW0 + W * DIN, oW1 = ob0 + W, ob1 = oW1 + W * W, oW2 = ob1 + W, ob2 = oW2 + W * W,
               oW3 = ob2 + W, ob3 = oW3 + DOUT * W, NP = ob3 + DOUT;
 constexpr int NPP = (NP + 63) / 64 * 64;
