@@ -63,16 +63,20 @@ class OTPlanSampler:
         choices = np.random.choice(pi.shape[0] * pi.shape[1], p=p, size=batch_size, replace=replace)
         return np.divmod(choices, pi.shape[1])
 
-    def sample_map_indices(self, x0, x1, generator=None):
-        """(i, j) int64 index tensors on x0's device, distributed as the reference's sample_map(get_map(x0, x1), B): i uniform
-        with replacement, j = perm[i].  CUDA inputs: assignment and draw on the device (torch's generator, not numpy's)."""
+    def sample_map_indices(self, x0, x1, generator=None, replace=True):
+        """(i, j) int64 index tensors on x0's device, distributed as the reference's sample_map(get_map(x0, x1), B, replace):
+        the plan's support is the n pairs (i, perm[i]) with equal mass, so i is uniform with replacement (replace=True) or a
+        random permutation of all rows (replace=False), and j = perm[i].  CUDA inputs: assignment and draw on the device
+        (torch's generator, not numpy's)."""
         if x0.is_cuda:
             perm = ot_assign(x0, x1)
-            i = torch.randint(0, x0.shape[0], (x0.shape[0],), device=x0.device, generator=generator)
+            n = x0.shape[0]
+            i = (torch.randint(0, n, (n,), device=x0.device, generator=generator) if replace
+                 else torch.randperm(n, device=x0.device, generator=generator))
             return i, perm[i]
-        i, j = self.sample_map(self.get_map(x0, x1), x0.shape[0])
+        i, j = self.sample_map(self.get_map(x0, x1), x0.shape[0], replace=replace)
         return torch.as_tensor(i, dtype=torch.int64), torch.as_tensor(j, dtype=torch.int64)
 
     def sample_plan(self, x0, x1, replace=True):
-        i, j = self.sample_map_indices(x0, x1)
+        i, j = self.sample_map_indices(x0, x1, replace=replace)
         return x0[i], x1[j]

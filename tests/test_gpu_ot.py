@@ -82,6 +82,11 @@ def test_dynamic_matcher_couples_on_the_device(cuda_device):
     assert i.is_cuda and j.is_cuda and i.dtype == torch.int64
     np.testing.assert_array_equal(j.cpu().numpy(), perm_ref[i.cpu().numpy()])
     assert 0.45 * B < len(set(i.cpu().tolist())) <= B                     # with replacement: ~63 % distinct
+    i2, j2 = ot.OTPlanSampler().sample_map_indices(x0, x1, replace=False)  # without: every plan pair exactly once
+    assert sorted(i2.cpu().tolist()) == list(range(B))
+    np.testing.assert_array_equal(j2.cpu().numpy(), perm_ref[i2.cpu().numpy()])
+    a0, b0 = ot.OTPlanSampler().sample_plan(x0, x1, replace=False)
+    assert a0.shape == x0.shape and b0.shape == x1.shape
     FM = cfmd.ExactOptimalTransportConditionalFlowMatcher(sigma=0.0)
     t, xt, ut = FM.sample_location_and_conditional_flow(x0, x1)
     # sigma = 0: xt - t * ut = x0[i] and xt + (1 - t) * ut = x1[perm[i]] for the drawn i: every row of (FM.x0, FM.x1) is a plan pair
