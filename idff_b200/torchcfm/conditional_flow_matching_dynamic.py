@@ -41,3 +41,18 @@ class ExactOptimalTransportConditionalFlowMatcher(ConditionalFlowMatcher):
         if return_noise:
             return t, xt, ut, eps
         return t, xt, ut
+
+    def guided_sample_location_and_conditional_flow(self, x0, x1, y0=None, y1=None, t=None, return_noise=False):
+        """conditional_flow_matching_dynamic.py:273-315: the labels follow their rows through the OT re-pairing."""
+        i, j = self.ot_sampler.sample_map_indices(x0, x1)
+        if t is None:
+            t = torch.rand(x0.shape[0]).type_as(x0)
+        assert len(t) == x0.shape[0], "t has to have batch size dimension"
+        eps = self.sample_noise_like(x0)
+        xt, ut = _cfm._path_sample(x0, x1, t, eps, self.sigma, self._sigma_mode, idx0=i, idx1=j)
+        self.x0, self.x1 = x0[i], x1[j]
+        y0 = y0[i] if y0 is not None else None
+        y1 = y1[j] if y1 is not None else None
+        if return_noise:
+            return t, xt, ut, y0, y1, eps
+        return t, xt, ut, y0, y1

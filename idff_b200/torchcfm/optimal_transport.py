@@ -80,3 +80,8 @@ class OTPlanSampler:
     def sample_plan(self, x0, x1, replace=True):
         i, j = self.sample_map_indices(x0, x1, replace=replace)
         return x0[i], x1[j]
+
+    def sample_plan_with_labels(self, x0, x1, y0=None, y1=None, replace=True):
+        """(x0[i], x1[j], y0[i], y1[j]) for index pairs drawn from the plan (reference :144-179)."""
+        i, j = self.sample_map_indices(x0, x1, replace=replace)
+        return x0[i], x1[j], (y0[i] if y0 is not None else None), (y1[j] if y1 is not None else None)

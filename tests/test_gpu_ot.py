@@ -95,5 +95,14 @@ def test_dynamic_matcher_couples_on_the_device(cuda_device):
     for r in range(0, B, 17):
         src = np.where((x0n == a[r]).all(1))[0]
         assert len(src) >= 1 and (x1n[perm_ref[src[0]]] == b[r]).all()
+    # labels follow their rows through the re-pairing (guided variant, :273-315)
+    y0, y1 = torch.arange(B, device=dev), torch.arange(B, device=dev) + 1000
+    out = FM.guided_sample_location_and_conditional_flow(x0, x1, y0=y0, y1=y1, return_noise=True)
+    assert len(out) == 6
+    la, lb = out[3].cpu().numpy(), out[4].cpu().numpy() - 1000
+    np.testing.assert_array_equal(lb, perm_ref[la])
+    assert torch.equal(FM.x0, x0[out[3]]) and torch.equal(FM.x1, x1[out[4] - 1000])
+    xa, xb, ya, yb = ot.OTPlanSampler().sample_plan_with_labels(x0, x1, y0, None)
+    assert yb is None and torch.equal(xa, x0[ya])
     # transport cost of the coupled pairs is lower than the independent pairing's
     assert ((FM.x0 - FM.x1) ** 2).sum(1).mean().item() < ((x0 - x1) ** 2).sum(1).mean().item()
