@@ -14,7 +14,8 @@ import torch
 from .. import _lib
 
 __all__ = ["pad_t_like_x", "ConditionalFlowMatcher", "ExactOptimalTransportConditionalFlowMatcher",
-           "TargetConditionalFlowMatcher", "VariancePreservingConditionalFlowMatcher"]
+           "TargetConditionalFlowMatcher", "SchrodingerBridgeConditionalFlowMatcher",
+           "VariancePreservingConditionalFlowMatcher"]
 
 
 def pad_t_like_x(t, x):
@@ -148,6 +149,39 @@ class TargetConditionalFlowMatcher(ConditionalFlowMatcher):
         del x0
         tp = pad_t_like_x(t, x1)
         return (x1 - (1 - self.sigma) * xt) / (1 - (1 - self.sigma) * tp)
+
+
+class SchrodingerBridgeConditionalFlowMatcher(ConditionalFlowMatcher):
+    """SB-CFM (reference :391-547): sigma_t = sigma sqrt(t(1-t)) (the path-sample kernel's mode 1) and the conditional flow
+    (1-2t) / (2t(1-t) + 1e-8) (xt - mu_t) + x1 - x0.  In this reference file the OT re-pairing is commented out (:498, :533), so
+    the matcher pairs the batches as given.  No IDFF configuration uses it: the flow is plain torch ops on the kernel's xt."""
+    _sigma_mode = 1
+
+    def __init__(self, sigma: Union[float, int] = 1.0, ot_method="exact"):
+        if sigma <= 0:
+            raise ValueError(f"Sigma must be strictly positive, got {sigma}.")
+        if sigma < 1e-3:
+            import warnings
+            warnings.warn("Small sigma values may lead to numerical instability.")
+        super().__init__(sigma)
+        self.ot_method = ot_method
+        self.ot_sampler = None      # never consulted by the reference's code path
+
+    def compute_sigma_t(self, t):
+        return self.sigma * torch.sqrt(t * (1 - t))
+
+    def compute_conditional_flow(self, x0, x1, t, xt):
+        tp = pad_t_like_x(t, x0)
+        mu_t = self.compute_mu_t(x0, x1, t)
+        return (1 - 2 * tp) / (2 * tp * (1 - tp) + 1e-8) * (xt - mu_t) + x1 - x0
+
+    def guided_sample_location_and_conditional_flow(self, x0, x1, y0=None, y1=None, t=None, return_noise=False):
+        out = self.sample_location_and_conditional_flow(x0, x1, t, return_noise)
+        if return_noise:
+            t, xt, ut, eps = out
+            return t, xt, ut, y0, y1, eps
+        t, xt, ut = out
+        return t, xt, ut, y0, y1
 
 
 class VariancePreservingConditionalFlowMatcher(ConditionalFlowMatcher):

@@ -243,6 +243,7 @@ def main():
     np.savez(os.path.join(OUT, "mmd.npz"), **mm)
 
     golden_metrics()
+    golden_aux_matchers()
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"wrote {len(os.listdir(OUT))} files, {tot / 1e6:.2f} MB -> {OUT}")
 
@@ -261,8 +262,29 @@ def golden_metrics():
     np.savez(os.path.join(OUT, "metrics.npz"), **out)
 
 
+def golden_aux_matchers():
+    """The matchers no IDFF configuration uses (Target :315-388, SchrodingerBridge :391-547, VariancePreserving :550-608 of
+    torchcfm/conditional_flow_matching.py), executed on seeded inputs with the noise injected."""
+    cf = R.cfm(False)
+    g = torch.Generator().manual_seed(21)
+    out = {}
+    for B, D in ((64, 2), (10, 46)):
+        x0, x1, eps = (torch.randn(B, D, generator=g) for _ in range(3))
+        t = torch.rand(B, generator=g)
+        key = f"B{B}_D{D}"
+        out.update({f"{key}_x0": x0.numpy(), f"{key}_x1": x1.numpy(), f"{key}_eps": eps.numpy(), f"{key}_t": t.numpy()})
+        for name, FM in (("target", cf.TargetConditionalFlowMatcher(0.1)), ("sb", cf.SchrodingerBridgeConditionalFlowMatcher(0.5)),
+                         ("vp", cf.VariancePreservingConditionalFlowMatcher(0.2))):
+            FM.sample_noise_like = lambda x, e=eps: e
+            tt, xt, ut = FM.sample_location_and_conditional_flow(x0, x1, t=t)
+            out[f"{key}_{name}_xt"], out[f"{key}_{name}_ut"] = xt.numpy(), ut.numpy()
+    np.savez(os.path.join(OUT, "matchers.npz"), **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "metrics":
         golden_metrics()
+    elif len(sys.argv) > 1 and sys.argv[1] == "matchers":
+        golden_aux_matchers()
     else:
         main()

@@ -336,3 +336,21 @@ def test_graph_trained_weights_reach_the_sampler(cuda_device):
     ref = O.odeint_rk4(O.Field2D([(m.weight.detach().cpu(), m.bias.detach().cpu()) for m in model.net
                                   if isinstance(m, torch.nn.Linear)], 0.2, (0.2, 0.0), 2), x0.cpu(), ts)[-1]
     assert (b.cpu() - ref).abs().median().item() < 1e-4
+
+
+def test_aux_matchers_vs_reference_golden(cuda_device):
+    """Target / SchrodingerBridge / VariancePreserving matchers (no IDFF configuration uses them; plain torch ops around the
+    path-sample kernel) against outputs of the reference's own classes on the same inputs and injected noise."""
+    g = load_golden("matchers")
+    for key in ("B64_D2", "B10_D46"):
+        x0, x1, eps, t = (torch.tensor(g[f"{key}_{n}"]).to(cuda_device) for n in ("x0", "x1", "eps", "t"))
+        for name, FM in (("target", cfm.TargetConditionalFlowMatcher(0.1)), ("sb", cfm.SchrodingerBridgeConditionalFlowMatcher(0.5)),
+                         ("vp", cfm.VariancePreservingConditionalFlowMatcher(0.2))):
+            FM.sample_noise_like = lambda x, e=eps: e
+            t2, xt, ut = FM.sample_location_and_conditional_flow(x0, x1, t=t)
+            np.testing.assert_allclose(xt.cpu().numpy(), g[f"{key}_{name}_xt"], rtol=2e-6, atol=2e-6, err_msg=f"{key} {name} xt")
+            # the SB flow divides by 2 t (1 - t) + 1e-8: near t = 0 / 1 it amplifies the last-ulp differences of xt - mu_t
+            np.testing.assert_allclose(ut.cpu().numpy(), g[f"{key}_{name}_ut"], rtol=2e-4 if name == "sb" else 2e-6,
+                                       atol=2e-4 if name == "sb" else 2e-6, err_msg=f"{key} {name} ut")
+    with pytest.raises(ValueError):
+        cfm.SchrodingerBridgeConditionalFlowMatcher(0.0)
