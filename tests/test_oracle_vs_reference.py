@@ -73,3 +73,25 @@ def test_md_metrics_equal_reference_method():
     assert set(ref) == set(got)
     for k in ref:
         assert float(ref[k]) == float(got[k]), k
+
+
+def test_toy_samplers_equal_reference_functions():
+    """The host-side toy generators of the mirror (idff_b200/torchcfm/utils.py) against the reference's functions executed from
+    torchcfm/utils.py with the same RNG state."""
+    import numpy as np
+    from idff_b200.torchcfm import utils as U
+    ref_rng = np.random.RandomState(5)
+    f = R.script_symbols("torchcfm/utils.py", ["pinwheel", "spirals_2d", "checkerboard", "eight_normal_sample"],
+                         extra_ns={"rng": ref_rng})
+    U.rng = np.random.RandomState(5)
+    assert torch.equal(f["pinwheel"](250), U.pinwheel(250))
+    for name in ("spirals_2d", "checkerboard"):
+        np.random.seed(9)
+        a = f[name](300)
+        np.random.seed(9)
+        b = getattr(U, name)(300)
+        assert torch.equal(a, b), name
+    torch.manual_seed(4)
+    a = f["eight_normal_sample"](128, 2, scale=5, var=0.1)
+    torch.manual_seed(4)
+    assert torch.equal(a, U.eight_normal_sample(128, 2, scale=5, var=0.1))
