@@ -26,10 +26,11 @@ def _field_for(base_model, g, sigma, impl):
     return model
 
 
-def sweep_mmd(base_model, x0, true_samples, gamma_tuples, nfe, sigma=0.2, sigma_kernel=1.0, impl=0, chunk=256):
+def sweep_mmd(base_model, x0, true_samples, gamma_tuples, nfe, sigma=0.2, sigma_kernel=1.0, impl=0, chunk=256, t_span=None):
     """MMD(true_samples, odeint(field(gammas), x0, linspace(0,1,nfe+1))[-1]) for every tuple -> list of floats.
-    The solves of `chunk` tuples at a time go out as ONE sampler launch (idff_sample_rk4_sweep)."""
-    t_span = torch.linspace(0, 1, nfe + 1)
+    The solves of `chunk` tuples at a time go out as ONE sampler launch (idff_sample_rk4_sweep).  t_span overrides the grid."""
+    if t_span is None:
+        t_span = torch.linspace(0, 1, nfe + 1)
     true_samples = torch.as_tensor(true_samples, dtype=torch.float32, device=x0.device)
     gamma_tuples = list(gamma_tuples)
     vals = []
@@ -52,3 +53,19 @@ def find_best_gammas_mmd(base_model, x0, true_samples, gamma_range=(0.0, 0.5, 1.
             print(f"gammas={g} -> MMD: {v:.5f}")
         print(f"best: {best[0]} with MMD={best[1]:.5f}")
     return best[0], results
+
+
+def compute_mmd_for_gamma_configs(test_model, gamma_configs, x0, t_span, true_samples_tensor, sigma_model=0.2, sigma_kernel=1.0,
+                                  device=None, verbose=False):
+    """Same contract as the reference (2D_examples/Autograd_example_order3.py:376-425): for each (gamma1, gamma2, gamma3) wrap
+    `test_model` in the order-3 field, integrate x0 over t_span with rk4 and return [((g1, g2, g3), mmd), ...] -- here as one
+    batched sampler call and one MMD launch per 256 configurations instead of one solve per configuration."""
+    del device
+    cfgs = [tuple(g) for g in gamma_configs]
+    vals = sweep_mmd(test_model, x0, true_samples_tensor, cfgs, nfe=None, sigma=sigma_model, sigma_kernel=sigma_kernel,
+                     t_span=t_span)
+    results = list(zip(cfgs, vals))
+    if verbose:
+        for (g1, g2, g3), v in results:
+            print(f"gamma1={g1}, gamma2={g2}, gamma3={g3} -> MMD: {v:.5f}")
+    return results

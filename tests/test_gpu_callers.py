@@ -38,6 +38,23 @@ def test_gamma_sweep_matches_oracle_loop(cuda_device):
     assert r3[0][1] == pytest.approx(results[0][1], abs=1e-6)              # (0,0,0) == (0,0)
 
 
+def test_compute_mmd_for_gamma_configs(cuda_device):
+    """Autograd_example_order3.py:376-425: explicit (gamma1, gamma2, gamma3) list and t_span; equals per-configuration solves."""
+    from idff_b200 import fields, sampler
+    from idff_b200.mmd import compute_mmd_rbf
+    pw = packed("checkerboard", cuda_device)
+    g = torch.Generator(device=cuda_device).manual_seed(3)
+    x0 = torch.randn(2048, 2, device=cuda_device, generator=g) / 1.5
+    true_s = torch.tensor(load_golden("mmd")["true_checkerboard"]).to(cuda_device)
+    cfgs = [(0.0, 0.0, 0.0), (0.2, 0.2, 0.1), (1.0, 0.5, 0.0), (0.3, 0.0, 0.4)]
+    t_span = torch.linspace(0, 1, 4)
+    res = sweep.compute_mmd_for_gamma_configs(pw, cfgs, x0, t_span, true_s, sigma_model=0.2, sigma_kernel=1.0)
+    assert [c for c, _ in res] == cfgs
+    for c, v in res:
+        out = sampler.sample_rk4(fields.CustomNetModelOrder3(pw, 0.2, *c), x0, t_span)
+        assert v == pytest.approx(compute_mmd_rbf(true_s, out, 1.0), abs=2e-6)
+
+
 def test_md_autoregressive_generation_vs_oracle(cuda_device):
     """generate_trajectories (MD_simulation.py:197-213) for 6 frames, 5 trajectories, injected Brownian increments."""
     layers, emb = golden_layers("polyala")
