@@ -153,3 +153,29 @@ def compute_metrics(y_hat, dataset):
     out = dict(zip(("CC_mean", "CC_std", "RMSE_mean", "RMSE_std", "MAE_mean", "MAE_std"), stats))
     out.update(CC=out["CC_mean"], RMSE=out["RMSE_mean"], MAE=out["MAE_mean"])
     return out
+
+
+def evaluate_model(model, dataset, gamma1_values, gamma2_values, sigma_values, nfes, num_trajectories=5, dt=0.3,
+                   device="cuda", generator=None):
+    """TrajectoryGenerator.evaluate_model (MD_simulation.py:159-194) without the plots, the KDE-KL and the CSV: for every
+    (nfe, sigma, gamma1, gamma2) generate `num_trajectories` chains (one launch each), compute the reference's metrics and the
+    RBF-MMD (sigma_kernel = 1, :178) between all data frames and all generated frames.  -> list of dicts with the reference's
+    keys (CC_mean .. MAE_std, nfe, sigma, gamma1, gamma2, MMD), in the reference's loop order."""
+    from .mmd import compute_mmd_rbf
+    device = torch.device(device)
+    data = torch.as_tensor(dataset, dtype=torch.float32, device=device)
+    T, D = data.shape
+    results = []
+    for nfe in nfes:
+        for sigma in sigma_values:
+            for gamma1 in gamma1_values:
+                for gamma2 in gamma2_values:
+                    y_hat = generate_trajectories(model, num_trajectories, D, T, nfe, sigma, gamma1=gamma1, gamma2=gamma2, dt=dt,
+                                                  device=device, generator=generator)
+                    m = compute_metrics(y_hat, data)
+                    for k in ("CC", "RMSE", "MAE"):
+                        m.pop(k)
+                    m.update({"nfe": nfe, "sigma": sigma, "gamma1": gamma1, "gamma2": gamma2,
+                              "MMD": compute_mmd_rbf(data, y_hat.reshape(-1, D), 1.0)})
+                    results.append(m)
+    return results

@@ -384,3 +384,20 @@ def test_md_chain_fma_and_mma_evaluators_agree(cuda_device):
     d = (out[0] - out[1]).abs()
     scale = out[1].abs().max().item()
     assert torch.isfinite(out[0]).all() and d.max().item() <= 1e-5 * scale, (d.max().item(), scale)
+
+
+def test_md_evaluate_model_grid(cuda_device):
+    """evaluate_model (MD_simulation.py:159-194): one row per (nfe, sigma, gamma1, gamma2) in the reference's loop order with the
+    reference's metric keys; the MMD column equals the oracle's MMD of the same frames (data (T, D) vs all generated frames)."""
+    pw = packed("polyala", cuda_device)
+    g = torch.Generator().manual_seed(2)
+    T, D = 12, 46
+    data = 100 * torch.randn(T, D, generator=g)
+    rows = md.evaluate_model(pw, data, gamma1_values=[0.0, 0.2], gamma2_values=[1.0], sigma_values=[0.2, 0.5], nfes=[3],
+                             num_trajectories=5, device=cuda_device)
+    assert [(r["nfe"], r["sigma"], r["gamma1"], r["gamma2"]) for r in rows] == [(3, 0.2, 0.0, 1.0), (3, 0.2, 0.2, 1.0),
+                                                                                 (3, 0.5, 0.0, 1.0), (3, 0.5, 0.2, 1.0)]
+    keys = {"CC_mean", "CC_std", "RMSE_mean", "RMSE_std", "MAE_mean", "MAE_std", "nfe", "sigma", "gamma1", "gamma2", "MMD"}
+    assert all(set(r) == keys and np.isfinite(r["MMD"]) and np.isfinite(r["RMSE_mean"]) for r in rows)
+    # degree-valued frames with sigma_kernel = 1: the MMD is dominated by the diagonals, 1/T + 1/(5 T) (SURVEY.md section 5)
+    assert rows[0]["MMD"] == pytest.approx(1 / T + 1 / (5 * T), rel=0.05)
