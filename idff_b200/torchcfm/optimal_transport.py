@@ -85,3 +85,26 @@ class OTPlanSampler:
         """(x0[i], x1[j], y0[i], y1[j]) for index pairs drawn from the plan (reference :144-179)."""
         i, j = self.sample_map_indices(x0, x1, replace=replace)
         return x0[i], x1[j], (y0[i] if y0 is not None else None), (y1[j] if y1 is not None else None)
+
+
+def wasserstein(x0, x1, method=None, reg: float = 0.05, power: int = 2, **kwargs):
+    """Exact Wasserstein-`power` distance between two equally weighted batches of equal size (reference :214-263, pot.emd2).
+    power = 2 on CUDA tensors: one launch of the assignment kernel, sqrt(cost / n).  power = 1 (plain Euclidean cost) and CPU
+    tensors: scipy's exact assignment on the host.  Only the exact method is provided."""
+    del reg, kwargs
+    assert power == 1 or power == 2
+    if method not in (None, "exact"):
+        raise ValueError(f"only the exact method is provided (got {method!r})")
+    if x0.shape[0] != x1.shape[0]:
+        raise ValueError("equal batch sizes are required (uniform marginals reduce to an assignment)")
+    n = x0.shape[0]
+    if power == 2 and x0.is_cuda:
+        _, cost = ot_assign(x0, x1, return_cost=True)
+        return float(torch.sqrt(cost / n))
+    from scipy.optimize import linear_sum_assignment
+    M = torch.cdist(x0.reshape(n, -1).double(), x1.reshape(n, -1).double()).cpu().numpy()
+    if power == 2:
+        M = M ** 2
+    r, c = linear_sum_assignment(M)
+    ret = float(M[r, c].sum() / n)
+    return ret ** 0.5 if power == 2 else ret

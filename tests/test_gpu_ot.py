@@ -106,3 +106,18 @@ def test_dynamic_matcher_couples_on_the_device(cuda_device):
     assert yb is None and torch.equal(xa, x0[ya])
     # transport cost of the coupled pairs is lower than the independent pairing's
     assert ((FM.x0 - FM.x1) ** 2).sum(1).mean().item() < ((x0 - x1) ** 2).sum(1).mean().item()
+
+
+def test_wasserstein_distance(cuda_device):
+    """wasserstein(x0, x1, power) (optimal_transport.py:214-263): W2 from the assignment kernel, W1 on the host; both against
+    the oracle's exact plan."""
+    g = torch.Generator().manual_seed(12)
+    x0, x1 = torch.randn(200, 2, generator=g), torch.randn(200, 2, generator=g) + 1.5
+    _, cost = O.ot_exact_permutation(x0, x1)
+    w2 = ot.wasserstein(x0.to(cuda_device), x1.to(cuda_device), power=2)
+    assert w2 == pytest.approx(np.sqrt(cost / 200), rel=1e-9)
+    assert ot.wasserstein(x0, x1, power=2) == pytest.approx(w2, rel=1e-9)            # host path, same optimum
+    w1 = ot.wasserstein(x0.to(cuda_device), x1.to(cuda_device), power=1)
+    assert 0 < w1 <= w2 + 1e-9                                                        # W1 <= W2
+    with pytest.raises(ValueError):
+        ot.wasserstein(x0, x1, method="sinkhorn")
