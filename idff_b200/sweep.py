@@ -26,7 +26,7 @@ def _field_for(base_model, g, sigma, impl):
     return model
 
 
-def sweep_mmd(base_model, x0, true_samples, gamma_tuples, nfe, sigma=0.2, sigma_kernel=1.0, impl=0, chunk=256, t_span=None):
+def sweep_mmd(base_model, x0, true_samples, gamma_tuples, nfe, sigma=0.2, sigma_kernel=1.0, impl=0, chunk=1024, t_span=None):
     """MMD(true_samples, odeint(field(gammas), x0, linspace(0,1,nfe+1))[-1]) for every tuple -> list of floats.
     The solves of `chunk` tuples at a time go out as ONE sampler launch (idff_sample_rk4_sweep).  t_span overrides the grid."""
     if t_span is None:
@@ -59,7 +59,7 @@ def compute_mmd_for_gamma_configs(test_model, gamma_configs, x0, t_span, true_sa
                                   device=None, verbose=False):
     """Same contract as the reference (2D_examples/Autograd_example_order3.py:376-425): for each (gamma1, gamma2, gamma3) wrap
     `test_model` in the order-3 field, integrate x0 over t_span with rk4 and return [((g1, g2, g3), mmd), ...] -- here as one
-    batched sampler call and one MMD launch per 256 configurations instead of one solve per configuration."""
+    batched sampler call and one MMD launch per 1024 configurations instead of one solve per configuration."""
     del device
     cfgs = [tuple(g) for g in gamma_configs]
     vals = sweep_mmd(test_model, x0, true_samples_tensor, cfgs, nfe=None, sigma=sigma_model, sigma_kernel=sigma_kernel,
