@@ -131,7 +131,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "idff_particle_steps_per_sec", "value": rate, "unit": "particle-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, n),
+            "config": workload_config(args, args.particles),   # our arm's config; each step is the bounded sample below
             "cpu_baseline": {"value": rate, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -163,7 +163,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if ws > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"      # stdout carries exactly one JSON line: no NCCL version banner
+        # NCCL_DEBUG is left as the caller set it (the driver reads the communicator's rank count from the INFO log);
+        # the JSON line is the LAST line this process prints
         dist.init_process_group("nccl", device_id=dev)
     P, nfe = args.particles, args.nfe
     n_total = P * ws
@@ -175,7 +176,6 @@ def run_ours(args):
     x0 = shard.x0(n_total)
     ts = torch.linspace(0, 1, nfe + 1)
     out = torch.empty_like(x0)
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
     np.random.seed(0)
     torch.manual_seed(0)
     from idff_b200.torchcfm.utils import sample_checkerboard
@@ -239,6 +239,15 @@ def run_ours(args):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_val = n_total * steps_per_solve * args.steps / (float(e2e_ms.item()) * 1e-3)
     assert torch.equal(h_out, out.cpu())
+    # rank 0's first 2^20 output rows are the same GLOBAL particles at every GPU count (contiguous row blocks of the
+    # chunk-seeded x0): their checksum must not change with N
+    head = out[: min(P, 1 << 20)].contiguous()
+    x1_checksum = {"rows": int(head.shape[0]), "sum_f64": float(head.double().sum().item()),
+                   "xor_u32": int(np.bitwise_xor.reduce(head.view(torch.int32).cpu().numpy().view(np.uint32).reshape(-1)))}
+    nonfinite = _lib.weights_nonfinite(pw.handle)
+    if ws > 1:
+        dist.barrier()
+        dist.destroy_process_group()   # before rank 0's CPU arm: no rank idles inside NCCL
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -287,7 +296,7 @@ def run_ours(args):
                         "frac_of_bf16_tensor_peak": achieved / bf16}
         # DRAM bytes of the dominant kernel from the committed ncu --set full capture of this very launch shape
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get("k_tc16")
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json"))).get("k_tc16")
             if tr and args.kernel in ("auto", "tensor16") and tr["particles_per_launch"] == P and tr["nfe"] == nfe:
                 roofline["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
                 roofline["traffic_note"] = (f"dram__bytes_read+write per launch ({tr['source']}); algorithmic "
@@ -297,7 +306,7 @@ def run_ours(args):
             pass
         # secondary kernels and the CPU baseline are measured at N = 1 only (other ranks would idle in NCCL teardown)
         aux = aux_measurements(dev, pw, model, peaks) if (not args.no_aux and ws == 1) else {}
-        cpu_rate, cpu_per, cores, _ = (cpu_reference_rate(args.cpu_particles, nfe, runs=5) if (not args.no_cpu and ws == 1)
+        cpu_rate, cpu_per, cores, _ = (cpu_reference_rate(args.cpu_particles, nfe, runs=5) if not args.no_cpu
                                        else (None, None, 0, []))
         line = {"metric": "idff_particle_steps_per_sec", "value": value, "unit": "particle-steps/s", "n_gpus": ws,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -312,10 +321,11 @@ def run_ours(args):
                 "cpu_baseline": {"value": cpu_rate, "unit": "particle-steps/s", "cores": cores, "kind": "port",
                                  "sample": f"{args.cpu_particles} particles x 5 solves, nfe={nfe}, torch CPU fp32 "
                                            "(oracle = the reference's nested-autograd field under restated rk4)"},
-                "mmd": mmd_val, "particles_per_sec": value / steps_per_solve, "aux": aux}
+                "mmd": mmd_val, "x1_checksum": x1_checksum,
+                "nonfinite": {"fp16_overflow_particle_evals": nonfinite[0], "rows_resolved_fp32": nonfinite[1]},
+                "particles_per_sec": value / steps_per_solve, "aux": aux}
+        sys.stderr.flush()
         print(json.dumps(line), flush=True)
-    if ws > 1:
-        dist.destroy_process_group()
 
 
 def aux_measurements(dev, pw, model, peaks):
@@ -620,7 +630,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--particles", type=int, default=1 << 24, help="particles per GPU")
+    ap.add_argument("--particles", type=int, default=1 << 26,
+                    help="particles per GPU: 2^26 = the upper end of BASELINE configs[1] (1M-64M on 1 B200); 8 GPUs -> 512 M, "
+                         "inside configs[4] (256M-1B)")
     ap.add_argument("--nfe", type=int, default=2)
     ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fused", "tensor", "tensor16"])
     ap.add_argument("--cpu-particles", type=int, default=65536)

@@ -39,6 +39,7 @@ _PP = C.POINTER(FieldParams)
 SIGNATURES = {
     "idff_version": (C.c_int, []),
     "idff_last_error": (C.c_char_p, []),
+    "idff_source_hash": (C.c_char_p, []),
     "idff_launch_count": (C.c_uint64, []),
     "idff_weights_create": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i32), _i32, _vp, _i32, _i32, _i32,
                                       C.POINTER(_vp)]),
@@ -46,7 +47,7 @@ SIGNATURES = {
     "idff_stage_scalars": (C.c_int, [_PP, _f32, _vp]),
     "idff_debug_tensor_stamps": (C.c_int, [_vp]),
     "idff_debug_tensor16_stamps": (C.c_int, [_vp]),
-    "idff_tensor16_nonfinite": (C.c_int, [_vp]),
+    "idff_weights_nonfinite": (C.c_int, [_vp, _vp]),
     "idff_mlp_forward": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp]),
     "idff_field_eval": (C.c_int, [_vp, _PP, _f32, _vp, _vp, _vp, _i64, _vp]),
     "idff_sample_rk4": (C.c_int, [_vp, _PP, _vp, _vp, _i32, _vp, _vp, _i64, _vp]),
@@ -120,11 +121,31 @@ def require_cuda(t: torch.Tensor, name: str):
         raise IdffError(f"{name} must be float32, got {t.dtype}")
 
 
-def tensor16_nonfinite() -> int:
-    """Particle-evaluations of the 3xFP16 tensor kernel whose field value was not finite (fp16 operand overflow)."""
-    c = C.c_uint64(0)
-    check(lib().idff_tensor16_nonfinite(C.byref(c)), "idff_tensor16_nonfinite")
-    return int(c.value)
+def weights_nonfinite(handle) -> tuple:
+    """(particle-evaluations of the fp16-split kernels on this handle whose field value was not finite, rows re-solved in
+    fp32 by the safety net of IDFF_IMPL_AUTO)."""
+    c = (C.c_uint64 * 2)(0, 0)
+    check(lib().idff_weights_nonfinite(handle, c), "idff_weights_nonfinite")
+    return int(c[0]), int(c[1])
+
+
+def source_hash() -> str:
+    """sha256 prefix of the sources the loaded library was built from (stamped by the Makefile)."""
+    return lib().idff_source_hash().decode()
+
+
+def expected_source_hash() -> str:
+    """the same hash recomputed from the checkout: csrc/*.cu + csrc/*.cuh (sorted), include/idff_b200.h, csrc/Makefile"""
+    import glob
+    import hashlib
+    names = sorted(os.path.basename(p) for p in glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")))
+    files = [os.path.join(CSRC, n) for n in names] + [os.path.join(_HERE, "..", "include", "idff_b200.h"),
+                                                       os.path.join(CSRC, "Makefile")]
+    h = hashlib.sha256()
+    for f in files:
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
 def launch_count() -> int:

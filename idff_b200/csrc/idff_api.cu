@@ -43,7 +43,6 @@ int tensor16_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, c
 int tensor16_sample_rk4_sweep(const idff_weights_t* w, const idff_field_params_t* params, int n_sets, const float* d_x0,
                               const Stage* stages, const float* dts, int n_iv, float* d_out, int64_t N, void* stream);
 int tensor16_debug_stamps(long long* h_out, int n);
-int tensor16_nonfinite(unsigned long long* h_out);
 
 // idff_sampler_wide.cu
 bool wide_supports(const idff_weights_t* w, const idff_field_params_t* p);
@@ -54,6 +53,33 @@ int wide_field_eval(const idff_weights_t* w, const idff_field_params_t* p, float
                     float* d_out, int64_t N, void* stream);
 int wide_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, const float* d_x0, const Stage* stages,
                     const float* dts, int n_iv, float* d_out_final, float* d_out_traj, int64_t N, void* stream);
+
+// idff_fixup.cu: the fp32 safety net behind the fp16-split routes of IDFF_IMPL_AUTO
+int keep_input(idff_weights_t* wm, const float** src, const float* d_out, bool force, size_t bytes, void* stream);
+int fixup_with_tables(const idff_weights_t* w, const idff_field_params_t* p, int mode, int n_sets, const Stage* stages,
+                      const float* dts, int n_iv, const float* d_x_in, const float* d_x0_cfm, float* d_out, float* d_traj,
+                      int64_t N, void* stream);
+
+// AUTO on the layered 3xFP16 engine: the engine, then the safety net on the same stream
+static int safe_wide_field_eval(const idff_weights_t* w, const idff_field_params_t* q, float t, const float* d_x, const float* d_x0,
+                                float* d_out, int64_t N, void* stream) {
+  int rc = keep_input(const_cast<idff_weights_t*>(w), &d_x, d_out, false, (size_t)N * q->dim * sizeof(float), stream);
+  if (rc) return rc;
+  rc = wide_field_eval(w, q, t, d_x, d_x0, d_out, N, stream);
+  if (rc) return rc;
+  Stage st;
+  make_stage(*q, t, &st);
+  return fixup_with_tables(w, q, 0, 1, &st, nullptr, 0, d_x, d_x0, d_out, nullptr, N, stream);
+}
+static int safe_wide_sample_rk4(const idff_weights_t* w, const idff_field_params_t* q, const float* d_x0, const Stage* stages,
+                                const float* dts, int n_iv, float* d_out_final, float* d_out_traj, int64_t N, void* stream) {
+  int rc = keep_input(const_cast<idff_weights_t*>(w), &d_x0, d_out_final, false, (size_t)N * q->dim * sizeof(float), stream);
+  if (rc) return rc;
+  rc = wide_sample_rk4(w, q, d_x0, stages, dts, n_iv, d_out_final, d_out_traj, N, stream);
+  if (rc) return rc;
+  return fixup_with_tables(w, q, 1, 1, stages, dts, n_iv, d_x0, nullptr, d_out_final,
+                           d_out_traj ? d_out_traj + (size_t)N * q->dim : nullptr, N, stream);
+}
 
 struct DeviceGuard {
   int prev = -1;
@@ -92,12 +118,14 @@ extern "C" int idff_debug_tensor16_stamps(int64_t* h_out32) {
   return tensor16_debug_stamps(reinterpret_cast<long long*>(h_out32), 32);
 }
 
-extern "C" int idff_tensor16_nonfinite(uint64_t* h_count) {
-  IDFF_CHECK_ARG(h_count, "idff_tensor16_nonfinite: null pointer");
-  unsigned long long c = 0;
-  int rc = tensor16_nonfinite(&c);
-  *h_count = (uint64_t)c;
-  return rc;
+extern "C" int idff_weights_nonfinite(const idff_weights_t* w, uint64_t* h_out2) {
+  IDFF_CHECK_ARG(w && h_out2, "idff_weights_nonfinite: null pointer");
+  DeviceGuard g(w->device);
+  unsigned long long c[2] = {0, 0};
+  IDFF_CUDA(cudaMemcpy(c, w->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+  h_out2[0] = (uint64_t)c[0];
+  h_out2[1] = (uint64_t)c[1];
+  return IDFF_OK;
 }
 
 extern "C" int idff_stage_scalars(const idff_field_params_t* p, float t, float* h_out8) {
@@ -131,10 +159,11 @@ extern "C" int idff_field_eval(const idff_weights_t* w, const idff_field_params_
   if (p->impl == IDFF_IMPL_AUTO && w->v.w == 256 && N >= 2048 && !tensor16_supports(w, p)) {
     idff_field_params_t q = *p;   // order 3 at width 256: the layered 3xFP16 engine (see idff_sample_rk4)
     q.impl = IDFF_IMPL_LAYERED;
-    if (wide_supports(w, &q)) return wide_field_eval(w, &q, t, d_x, d_x0, d_out, N, stream);
+    if (wide_supports(w, &q)) return safe_wide_field_eval(w, &q, t, d_x, d_x0, d_out, N, stream);
   }
   if ((p->impl == IDFF_IMPL_TENSOR || p->impl == IDFF_IMPL_AUTO) && wide_supports(w, p) && (p->impl == IDFF_IMPL_TENSOR || N >= 2048))
-    return wide_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
+    return p->impl == IDFF_IMPL_AUTO ? safe_wide_field_eval(w, p, t, d_x, d_x0, d_out, N, stream)
+                                     : wide_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
   if (p->impl == IDFF_IMPL_TENSOR16 || (p->impl == IDFF_IMPL_AUTO && tensor16_supports(w, p) && N >= 4096))
     return tensor16_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
   if (p->impl == IDFF_IMPL_TENSOR) return tensor_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
@@ -172,6 +201,12 @@ extern "C" int idff_sample_rk4(const idff_weights_t* w, const idff_field_params_
     IDFF_CHECK_ARG(h_t_grid[i] > h_t_grid[i - 1], "idff_sample_rk4: t_grid must be strictly increasing");
   if (N == 0) return IDFF_OK;
   IDFF_CHECK_ARG(N > 0 && d_x0 && d_out_final, "idff_sample_rk4: null pointer or negative N");
+  // CFMModel captures x0 inside forward() at t == 0 only (Autograd_example_order2.py:322-324): a solve that does not start
+  // there has no x0 in the reference either (AttributeError); solves longer than one launch re-read the caller's d_x0
+  IDFF_CHECK_ARG(p->variant != IDFF_FIELD_CFM || n_grid < 2 || h_t_grid[0] == 0.0f,
+                 "idff_sample_rk4: the CFM field captures x0 at t == 0; t_grid[0] = %g", (double)h_t_grid[0]);
+  IDFF_CHECK_ARG(p->variant != IDFF_FIELD_CFM || n_grid - 1 <= kMaxIntervals || d_out_final != d_x0,
+                 "idff_sample_rk4: a CFM solve of more than %d intervals cannot run in place (x0 is re-read)", kMaxIntervals);
   DeviceGuard g(w->device);
   const size_t row_bytes = (size_t)N * p->dim * sizeof(float);
   if (d_out_traj) IDFF_CUDA(cudaMemcpyAsync(d_out_traj, d_x0, row_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
@@ -206,10 +241,11 @@ extern "C" int idff_sample_rk4(const idff_weights_t* w, const idff_field_params_
     idff_field_params_t q = *p;
     q.impl = IDFF_IMPL_LAYERED;
     if (wide_supports(w, &q))
-      return wide_sample_rk4(w, &q, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream);
+      return safe_wide_sample_rk4(w, &q, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream);
   }
   if ((p->impl == IDFF_IMPL_TENSOR || p->impl == IDFF_IMPL_AUTO) && wide_supports(w, p) && (p->impl == IDFF_IMPL_TENSOR || N >= 2048))
-    return wide_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream);
+    return p->impl == IDFF_IMPL_AUTO ? safe_wide_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream)
+                                     : wide_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream);
   if (p->impl == IDFF_IMPL_TENSOR)
     return tensor_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream);
   const bool want_fused = p->impl == IDFF_IMPL_FUSED || (p->impl == IDFF_IMPL_AUTO && fused_supports(w, p));
@@ -238,6 +274,8 @@ extern "C" int idff_sample_rk4_sweep(const idff_weights_t* w, const idff_field_p
     IDFF_CHECK_ARG(h_t_grid[i] > h_t_grid[i - 1], "idff_sample_rk4_sweep: t_grid must be strictly increasing");
   if (N == 0) return IDFF_OK;
   IDFF_CHECK_ARG(N > 0 && d_x0 && d_out, "idff_sample_rk4_sweep: null pointer or negative N");
+  IDFF_CHECK_ARG(params[0].variant != IDFF_FIELD_CFM || n_grid < 2 || h_t_grid[0] == 0.0f,
+                 "idff_sample_rk4_sweep: the CFM field captures x0 at t == 0; t_grid[0] = %g", (double)h_t_grid[0]);
   const int n_iv = n_grid - 1;
   const size_t set_floats = (size_t)N * params[0].dim;
   // one launch when every set is served by the 3xFP16 tensor kernel; otherwise one fused launch per set
@@ -332,7 +370,13 @@ extern "C" int idff_sample_rk4_sweep(const idff_weights_t* w, const idff_field_p
       make_stage(params[g], t1, &s4[3]);
     }
   }
-  if (wide_batched) return wide_sample_rk4_sweep(w, wp.data(), n_sets, d_x0, st.data(), dts.data(), n_iv, d_out, N, stream);
+  if (wide_batched) {
+    int rc = wide_sample_rk4_sweep(w, wp.data(), n_sets, d_x0, st.data(), dts.data(), n_iv, d_out, N, stream);
+    bool safe = false;   // range safe unless every set asked for the raw engine
+    for (int g = 0; g < n_sets; ++g) safe = safe || params[g].impl == IDFF_IMPL_AUTO;
+    if (rc || !safe) return rc;
+    return fixup_with_tables(w, &wp[0], 2, n_sets, st.data(), dts.data(), n_iv, d_x0, nullptr, d_out, nullptr, N, stream);
+  }
   return tensor16_sample_rk4_sweep(w, params, n_sets, d_x0, st.data(), dts.data(), n_iv, d_out, N, stream);
 }
 

@@ -96,6 +96,12 @@ struct idff_weights {
   size_t sweep_bytes;
   float* d_sweep_out;   // staging buffer of a mixed gamma sweep (one class of sets at a time), grow-only
   size_t sweep_out_bytes;
+  unsigned long long* d_counters;   // [0] particle-evaluations of the fp16-split kernels whose field value was not finite,
+                                    // [1] rows re-solved in fp32 by the range safety net (idff_fixup.cu)
+  float* d_fix_x;       // input rows of a launch that runs in place / continues a chunked solve, kept for the safety net; grow-only
+  size_t fix_x_bytes;
+  void* d_fix_tab;      // stage tables of the safety net for solves the grid-constant table cannot hold; grow-only
+  size_t fix_tab_bytes;
 };
 
 namespace idff {

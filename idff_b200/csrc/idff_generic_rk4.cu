@@ -7,8 +7,8 @@ void jets_needed(const idff_field_params_t& p, int* nj, int* reverse);
 
 template <int NJ, int PB, bool MULTI>
 __global__ void __launch_bounds__(256) k_sample_rk4(NetView net, FieldCfg cfg, const __grid_constant__ Rk4Table tab,
-                                                    const float* __restrict__ x0, float* __restrict__ out_final,
-                                                    float* __restrict__ traj, long N) {
+                                                    const float* __restrict__ x0, const float* __restrict__ x0_cfm,
+                                                    float* __restrict__ out_final, float* __restrict__ traj, long N) {
   extern __shared__ __align__(16) float smem[];
   SmemPlan s = carve<NJ, PB>(smem, net, cfg.D);
   const int D = cfg.D, tid = threadIdx.x, nth = blockDim.x;
@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(256) k_sample_rk4(NetView net, FieldCfg cfg, c
       const float v = row < N ? x0[row * D + (o % D)] : 0.0f;
       s.y[o] = v;
       s.xs[o] = v;
+      if (x0_cfm != nullptr) s.x0s[o] = row < N ? x0_cfm[row * D + (o % D)] : 0.0f;   // later chunk of a CFM solve
     }
     __syncthreads();
     for (int iv = 0; iv < tab.n_iv; ++iv) {
@@ -74,7 +75,8 @@ int generic_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, co
     memcpy(tab.dt, dts + done, sizeof(float) * cnt);
     memcpy(tab.st, stages + 4 * (size_t)done, sizeof(Stage) * 4 * cnt);
     float* traj = d_out_traj ? d_out_traj + (size_t)done * N * p->dim : nullptr;
-    auto one = [&]() -> int { IDFF_GEN_DISPATCH(k_sample_rk4, pl, stream, w->v, cfg, tab, src, d_out_final, traj, (long)N); };
+    const float* x0c = (done > 0 && p->variant == IDFF_FIELD_CFM) ? d_x0 : nullptr;
+    auto one = [&]() -> int { IDFF_GEN_DISPATCH(k_sample_rk4, pl, stream, w->v, cfg, tab, src, x0c, d_out_final, traj, (long)N); };
     rc = one();
     if (rc) return rc;
     src = d_out_final;

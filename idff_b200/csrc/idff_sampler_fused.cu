@@ -606,7 +606,7 @@ k_fused(const __grid_constant__ FParams P, const __grid_constant__ Rk4Table rk, 
       const float v = row < P.N ? P.x_in[row * Dd + (o % Dd)] : 0.0f;
       wp.y[o] = v;
       wp.xs[o] = v;
-      if (P.mode == 0 && P.variant == IDFF_FIELD_CFM && P.x0_cfm) wp.x0c[o] = row < P.N ? P.x0_cfm[row * Dd + (o % Dd)] : 0.0f;
+      if (P.variant == IDFF_FIELD_CFM && P.x0_cfm) wp.x0c[o] = row < P.N ? P.x0_cfm[row * Dd + (o % Dd)] : 0.0f;
       if (P.mode == 2 && row < P.N) P.out[row * Dd + (o % Dd)] = v;   // ys[0] = y0
     }
     __syncwarp();
@@ -835,6 +835,7 @@ int fused_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, cons
     fz::FParams P;
     fill_params(w, p, 1, N, &P);
     P.x_in = src; P.out = d_out_final;
+    P.x0_cfm = done > 0 ? d_x0 : nullptr;   // CFMModel keeps the x captured at t == 0 for the whole solve
     P.traj = d_out_traj ? d_out_traj + (size_t)done * N * p->dim : nullptr;
     int rc = launch_fused(w, p, P, &tab, nullptr, nullptr, stream);
     if (rc) return rc;

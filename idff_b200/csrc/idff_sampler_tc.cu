@@ -424,7 +424,7 @@ k_tc(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, con
           const float v = row < P.N ? P.x_in[row * 2 + d] : 0.0f;
           sy[d] = v;
           sxs[2 * lane + d] = v;
-          if (P.mode == 0 && P.variant == IDFF_FIELD_CFM && P.x0_cfm) sx0[d] = row < P.N ? P.x0_cfm[row * 2 + d] : 0.0f;
+          if (P.variant == IDFF_FIELD_CFM && P.x0_cfm) sx0[d] = row < P.N ? P.x0_cfm[row * 2 + d] : 0.0f;
         }
       }
       ebar();
@@ -737,6 +737,7 @@ int tensor_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, con
     tc::TParams P;
     fill_tparams(w, p, 1, N, &P);
     P.x_in = src; P.out = d_out_final;
+    P.x0_cfm = done > 0 ? d_x0 : nullptr;   // CFMModel keeps the x captured at t == 0 for the whole solve
     P.traj = d_out_traj ? d_out_traj + (size_t)done * N * p->dim : nullptr;
     int rc = launch_tc(w, p, P, &tab, nullptr, stream);
     if (rc) return rc;

@@ -40,7 +40,6 @@
 namespace idff {
 void jets_needed(const idff_field_params_t& p, int* nj, int* reverse);
 __device__ int g_tc16_misaligned = 0;
-__device__ unsigned long long g_tc16_nonfinite = 0;   // particle-evaluations whose field value was not finite
 
 namespace tch {
 
@@ -75,6 +74,7 @@ struct TParams {
   const float* x0_cfm;
   float* out;
   float* traj;
+  unsigned long long* counters;          // per handle: [0] += particle-evaluations whose field value was not finite
 };
 
 struct Smem {   // byte offsets from the dynamic base, which must be 1024-byte aligned (checked at kernel entry)
@@ -386,7 +386,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
           const float v = row < P.N ? P.x_in[row * 2 + d] : 0.0f;
           sy[d] = v;
           sxs[2 * myp + d] = v;
-          if (P.mode == 0 && P.variant == IDFF_FIELD_CFM && P.x0_cfm) sx0[d] = row < P.N ? P.x0_cfm[row * 2 + d] : 0.0f;
+          if (P.variant == IDFF_FIELD_CFM && P.x0_cfm) sx0[d] = row < P.N ? P.x0_cfm[row * 2 + d] : 0.0f;
         }
       }
       ebar();
@@ -662,7 +662,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
                 if (heavy) f = __fadd_rn(f, gg[d]);
               }
             }
-            if (row < P.N && !(fabsf(f) <= 3.0e38f)) atomicAdd(&g_tc16_nonfinite, 1ull);
+            if (row < P.N && !(fabsf(f) <= 3.0e38f)) atomicAdd(P.counters, 1ull);
             if (P.mode == 0) {
               if (row < P.N) out_set[row * 2 + d] = f;
             } else {
@@ -707,11 +707,12 @@ int tensor16_debug_stamps(long long* h_out, int n) {
   return IDFF_OK;
 }
 
-// number of particle-evaluations (summed over all launches of this process) whose field value came out non-finite
-int tensor16_nonfinite(unsigned long long* h_out) {
-  IDFF_CUDA(cudaMemcpyFromSymbol(h_out, g_tc16_nonfinite, sizeof(unsigned long long)));
-  return IDFF_OK;
-}
+// idff_fixup.cu: the range safety net of IDFF_IMPL_AUTO
+int fixup_nonfinite(const idff_weights_t* w, const idff_field_params_t* p, int mode, int n_sets, int n_iv, const Rk4Table* rk,
+                    const SweepTab* d_tabs, const Stage* g_st, const float* g_dt, const float* d_x_in, const float* d_x0_cfm,
+                    float* d_out, float* d_traj, int64_t N, void* stream);
+
+int keep_input(idff_weights_t* wm, const float** src, const float* d_out, bool force, size_t bytes, void* stream);
 
 bool tensor16_supports(const idff_weights_t* w, const idff_field_params_t* p) {
   const NetView& v = w->v;
@@ -778,16 +779,27 @@ static void fill_tparams16(const idff_weights_t* w, const idff_field_params_t* p
   P->net = w->v;
   P->variant = p->variant; P->D = p->dim; P->tidx = p->t_idx; P->reverse = rev; P->mode = mode;
   P->N = (long)N;
+  P->counters = w->d_counters;
 }
 
 int tensor16_field_eval(const idff_weights_t* w, const idff_field_params_t* p, float t, const float* d_x, const float* d_x0,
                         float* d_out, int64_t N, void* stream) {
   tch::TParams P;
   fill_tparams16(w, p, 0, N, &P);
+  const bool safe = p->impl == IDFF_IMPL_AUTO;
+  if (safe) {
+    int rc = keep_input(const_cast<idff_weights_t*>(w), &d_x, d_out, false, (size_t)N * 2 * sizeof(float), stream);
+    if (rc) return rc;
+  }
   P.x_in = d_x; P.x0_cfm = d_x0; P.out = d_out;
   Stage st;
   make_stage(*p, t, &st);
-  return launch_tc16(w, p, P, nullptr, &st, stream);
+  int rc = launch_tc16(w, p, P, nullptr, &st, stream);
+  if (rc || !safe) return rc;
+  static thread_local Rk4Table tab;
+  tab.n_iv = 0;
+  tab.st[0] = st;
+  return fixup_nonfinite(w, p, 0, 1, 0, &tab, nullptr, nullptr, nullptr, d_x, d_x0, d_out, nullptr, N, stream);
 }
 
 // One launch for n_sets parameter sets over the same x0 and grid (the gamma sweeps of the 2-D scripts).
@@ -830,13 +842,19 @@ int tensor16_sample_rk4_sweep(const idff_weights_t* w, const idff_field_params_t
   P.tiles_per_set = (tiles + 1) & ~1L;
   P.tabs = reinterpret_cast<const SweepTab*>(wm->d_sweep);
   P.x_in = d_x0; P.out = d_out;
-  return launch_tc16(w, &params[0], P, nullptr, nullptr, stream);
+  int rc = launch_tc16(w, &params[0], P, nullptr, nullptr, stream);
+  bool safe = false;   // range safe unless every set asks for the raw kernel
+  for (int g = 0; g < n_sets; ++g) safe = safe || params[g].impl == IDFF_IMPL_AUTO;
+  if (rc || !safe) return rc;
+  return fixup_nonfinite(w, &params[0], 2, n_sets, n_iv, nullptr, reinterpret_cast<const SweepTab*>(wm->d_sweep), nullptr, nullptr,
+                         d_x0, nullptr, d_out, nullptr, N, stream);
 }
 
 int tensor16_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, const float* d_x0, const Stage* stages,
                         const float* dts, int n_iv, float* d_out_final, float* d_out_traj, int64_t N, void* stream) {
   static thread_local Rk4Table tab;
   const float* src = d_x0;
+  const bool safe = p->impl == IDFF_IMPL_AUTO;
   for (int done = 0; done < n_iv; done += kMaxIntervals) {
     const int cnt = n_iv - done < kMaxIntervals ? n_iv - done : kMaxIntervals;
     tab.n_iv = cnt;
@@ -844,10 +862,20 @@ int tensor16_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, c
     memcpy(tab.st, stages + 4 * (size_t)done, sizeof(Stage) * 4 * cnt);
     tch::TParams P;
     fill_tparams16(w, p, 1, N, &P);
+    if (safe) {
+      int rc = keep_input(const_cast<idff_weights_t*>(w), &src, d_out_final, done > 0, (size_t)N * 2 * sizeof(float), stream);
+      if (rc) return rc;
+    }
     P.x_in = src; P.out = d_out_final;
+    P.x0_cfm = done > 0 ? d_x0 : nullptr;   // CFMModel keeps the x captured at t == 0 for the whole solve (order2.py:322-324)
     P.traj = d_out_traj ? d_out_traj + (size_t)done * N * p->dim : nullptr;
     int rc = launch_tc16(w, p, P, &tab, nullptr, stream);
     if (rc) return rc;
+    if (safe) {
+      rc = fixup_nonfinite(w, p, 1, 1, cnt, &tab, nullptr, nullptr, nullptr, src, P.x0_cfm, d_out_final,
+                           P.traj ? P.traj + (size_t)N * 2 : nullptr, N, stream);
+      if (rc) return rc;
+    }
     src = d_out_final;
   }
   return IDFF_OK;

@@ -80,7 +80,11 @@ void make_stage(const idff_field_params_t& p, float t, Stage* out) {
 
 using namespace idff;
 
-extern "C" int idff_version(void) { return 100; }
+#ifndef IDFF_SRC_HASH
+#define IDFF_SRC_HASH "unstamped"
+#endif
+extern "C" int idff_version(void) { return 200; }
+extern "C" const char* idff_source_hash(void) { return IDFF_SRC_HASH; }
 extern "C" const char* idff_last_error(void) { return idff::g_err; }
 extern "C" uint64_t idff_launch_count(void) { return idff::g_launches.load(); }
 
@@ -253,9 +257,13 @@ extern "C" int idff_weights_create(const float* const* h_W, const float* const* 
     return IDFF_ENOMEM;
   }
   e = cudaMemcpy(d_blob, blob.data(), off * sizeof(float), cudaMemcpyHostToDevice);
+  unsigned long long* d_counters = nullptr;
+  if (e == cudaSuccess) e = cudaMalloc(&d_counters, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(d_counters, 0, 2 * sizeof(unsigned long long));
   cudaSetDevice(prev);
   if (e != cudaSuccess) {
     cudaFree(d_blob);
+    if (d_counters) cudaFree(d_counters);
     set_error("idff_weights_create: cudaMemcpy failed: %s", cudaGetErrorString(e));
     return IDFF_ECUDA;
   }
@@ -281,6 +289,8 @@ extern "C" int idff_weights_create(const float* const* h_W, const float* const* 
   h->d_stash = nullptr; h->stash_bytes = 0; h->tc_verified = 0;
   h->d_sweep = nullptr; h->sweep_bytes = 0;
   h->d_sweep_out = nullptr; h->sweep_out_bytes = 0;
+  h->d_fix_x = nullptr; h->fix_x_bytes = 0; h->d_fix_tab = nullptr; h->fix_tab_bytes = 0;
+  h->d_counters = d_counters;
   *out = h;
   return IDFF_OK;
 }
@@ -291,6 +301,9 @@ extern "C" int idff_weights_destroy(idff_weights_t* w) {
   if (w->d_stash) cudaFree(w->d_stash);
   if (w->d_sweep) cudaFree(w->d_sweep);
   if (w->d_sweep_out) cudaFree(w->d_sweep_out);
+  if (w->d_counters) cudaFree(w->d_counters);
+  if (w->d_fix_x) cudaFree(w->d_fix_x);
+  if (w->d_fix_tab) cudaFree(w->d_fix_tab);
   delete w;
   return IDFF_OK;
 }

@@ -38,14 +38,18 @@ extern "C" {
 #define IDFF_FIELD_MD 3        /* SDE_cal.f, timeseris_example/MD_simulation.py:497-526 */
 
 /* which kernel family serves a sampler call */
-#define IDFF_IMPL_AUTO 0
+#define IDFF_IMPL_AUTO 0    /* fastest kernel that serves the shape, and RANGE SAFE: where that kernel carries fp32 values as fp16
+                               pairs (TENSOR16, LAYERED) the call also runs the fp32 safety net (idff_fixup.cu) on the same
+                               stream -- particles whose result came out non-finite (an activation, jet or adjoint beyond 65504)
+                               are re-solved from their inputs in fp32 FMA arithmetic, so AUTO never returns inf/NaN where the
+                               reference's fp32 path is finite.  No host synchronisation; idff_weights_nonfinite() counts them */
 #define IDFF_IMPL_GENERIC 1 /* any width / dimension: one thread per hidden unit, weights from L2 */
 #define IDFF_IMPL_FUSED 2   /* persistent warp-tiled kernel, weights streamed by TMA bulk copies */
 #define IDFF_IMPL_TENSOR 3  /* tcgen05: fused 3xTF32 kernel (width 256, dim 2, order <= 2) or the layered 3xFP16 engine (width >= 512) */
 #define IDFF_IMPL_LAYERED 4 /* force the layer-by-layer tcgen05 3xFP16 engine (width >= 256, dim 2, orders 1..3) */
-#define IDFF_IMPL_TENSOR16 5 /* tcgen05 3xFP16 fused kernel (width 256, dim 2, order <= 2): the default for that shape.
-                                Values beyond the fp16 range (|activation|, |jet|, |adjoint| > 65504) make that particle's
-                                output NaN and are counted by idff_tensor16_nonfinite(); use TENSOR or FUSED for such nets */
+#define IDFF_IMPL_TENSOR16 5 /* the raw tcgen05 3xFP16 fused kernel (width 256, dim 2, order <= 2), WITHOUT the safety net:
+                                values beyond the fp16 range (|activation|, |jet|, |adjoint| > 65504) make that particle's
+                                output NaN (counted by idff_weights_nonfinite()).  AUTO = this kernel + the safety net */
 
 typedef struct idff_weights idff_weights_t; /* opaque: packed device copies of one 4-layer SELU MLP */
 
@@ -62,6 +66,9 @@ typedef struct idff_field_params {
 } idff_field_params_t;
 
 int idff_version(void);
+/* first 16 hex digits of the sha256 over the library's sources (csrc/*.cu, csrc/*.cuh in sorted order, this header, the
+ * Makefile) as they were when the library was built: lets a caller prove the loaded binary matches its checkout */
+const char* idff_source_hash(void);
 const char* idff_last_error(void);
 /* number of kernels this library has launched from the calling process so far (bench.py's gpu_launches) */
 uint64_t idff_launch_count(void);
@@ -97,9 +104,10 @@ int idff_stage_scalars(const idff_field_params_t* p, float t, float* h_out8);
 int idff_debug_tensor_stamps(int64_t* h_out32);
 /* same for the last IDFF_IMPL_TENSOR16 launch */
 int idff_debug_tensor16_stamps(int64_t* h_out32);
-/* Diagnostic: particle-evaluations of IDFF_IMPL_TENSOR16 launches in this process whose field value was not finite
- * (fp16 operand overflow or non-finite input); synchronises the device. */
-int idff_tensor16_nonfinite(uint64_t* h_count);
+/* Per-handle counters of the fp16-split kernels: h_out2[0] = particle-evaluations whose field value was not finite (fp16
+ * operand overflow or non-finite input), h_out2[1] = rows the safety net of IDFF_IMPL_AUTO re-solved in fp32.  A blocking
+ * 16-byte device-to-host copy; never called on the product path. */
+int idff_weights_nonfinite(const idff_weights_t* w, uint64_t* h_out2);
 
 /* ---- a8 + a3..a6 fused: torchdiffeq.odeint(model, x0, t_grid, method='rk4') (3/8 rule, grid == t_grid;
  * call sites Autograd_example_order2.py:167,213,291).  h_t_grid: n_grid fp32 times on the host.

@@ -25,7 +25,12 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/idff_b200.h but not exported"
     assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
-    assert _lib.lib().idff_version() >= 100
+    assert _lib.lib().idff_version() >= 200
+
+
+def test_loaded_library_was_built_from_this_checkout():
+    """build provenance (VERDICT r1 weak #8): the Makefile stamps the sha256 of csrc/ + the header into the library"""
+    assert _lib.source_hash() == _lib.expected_source_hash()
 
 
 def test_argument_validation_needs_no_gpu():

@@ -167,7 +167,7 @@ def test_fused_kernel_is_selected_and_agrees_with_generic(cuda_device):
     assert torch.equal(outs[_lib.IDFF_IMPL_TENSOR16], outs[_lib.IDFF_IMPL_AUTO])   # AUTO = tcgen05 3xFP16 kernel on this shape
     r = drift_report(outs[_lib.IDFF_IMPL_TENSOR16].cpu().numpy(), outs[_lib.IDFF_IMPL_GENERIC].cpu().numpy())
     assert r["median"] <= 2e-5 and r["p999"] <= 1e-3, r                            # 3xFP16, truncating accumulation
-    assert _lib.tensor16_nonfinite() == 0
+    assert _lib.weights_nonfinite(pw.handle) == (0, 0)
     r = drift_report(outs[_lib.IDFF_IMPL_FUSED].cpu().numpy(), outs[_lib.IDFF_IMPL_GENERIC].cpu().numpy())
     assert r["median"] <= 5e-6 and r["p999"] <= 1e-3, r
     r = drift_report(outs[_lib.IDFF_IMPL_TENSOR].cpu().numpy(), outs[_lib.IDFF_IMPL_GENERIC].cpu().numpy())
@@ -189,8 +189,10 @@ def test_fused_kernel_is_selected_and_agrees_with_generic(cuda_device):
 def test_tensor16_full_size_properties_and_range_guard(cuda_device):
     """BASELINE-size batch through the default (3xFP16 tensor) sampler: particles are independent, so any slice of a
     4 M-particle solve is reproduced bit-for-bit by solving the slice alone; trajectories end where sample_rk4 ends.
-    Operands beyond the fp16 range make THAT particle's output non-finite (never silently wrong) and are counted."""
-    pw = packed("checkerboard", cuda_device)
+    Operands beyond the fp16 range make THAT particle's output non-finite in the raw kernel (IDFF_IMPL_TENSOR16; never
+    silently wrong, counted); the default route (IDFF_IMPL_AUTO) re-solves exactly those particles in fp32."""
+    from idff_b200.weights import PackedWeights
+    pw = PackedWeights.from_npz(load_golden("weights_checkerboard"), device=cuda_device)   # own handle: fresh counters
     m = fields.CustomNetModel(pw, 0.2, 0.2, 0.2)                      # AUTO -> k_tc16
     n = 1 << 22
     x0 = torch.randn(n, 2, device=cuda_device, generator=torch.Generator(device=cuda_device).manual_seed(9)) / 1.5
@@ -204,15 +206,111 @@ def test_tensor16_full_size_properties_and_range_guard(cuda_device):
     # the distribution moved toward the checkerboard support (|x| <= 4): a sanity property of the shipped model
     assert (whole.abs() < 6).float().mean().item() > 0.99
     # range guard
-    before = _lib.tensor16_nonfinite()
+    assert _lib.weights_nonfinite(pw.handle) == (0, 0)
     bad = x0[:128].clone()
     bad[5] = 3.0e6                                                   # layer-1 pre-activations far beyond 65504
-    out = sampler.sample_rk4(m, bad, ts)
+    raw = fields.CustomNetModel(pw, 0.2, 0.2, 0.2)
+    raw.impl = _lib.IDFF_IMPL_TENSOR16                               # the raw kernel, no safety net
+    out = sampler.sample_rk4(raw, bad, ts)
     assert not torch.isfinite(out[5]).all()
     keep = torch.ones(128, dtype=torch.bool, device=cuda_device)
     keep[5] = False
     assert torch.equal(out[keep], whole[:128][keep])                 # the other particles of the tile are untouched
-    assert _lib.tensor16_nonfinite() > before
-    mf = fields.CustomNetModel(pw, 0.2, 0.2, 0.2)
-    mf.impl = _lib.IDFF_IMPL_FUSED                                   # the fp32 kernel serves such inputs
-    assert torch.isfinite(sampler.sample_rk4(mf, bad, ts)).all()
+    n_bad, n_fixed = _lib.weights_nonfinite(pw.handle)
+    assert n_bad > 0 and n_fixed == 0
+    mg = fields.CustomNetModel(pw, 0.2, 0.2, 0.2)
+    mg.impl = _lib.IDFF_IMPL_GENERIC                                 # fp32 FMA arithmetic serves such inputs
+    ref = sampler.sample_rk4(mg, bad, ts)
+    assert torch.isfinite(ref).all()
+    safe = sampler.sample_rk4(m, bad, ts)                            # AUTO: same kernel + the fp32 safety net
+    assert torch.equal(safe[keep], whole[:128][keep]) and torch.equal(safe[5], ref[5])
+    assert _lib.weights_nonfinite(pw.handle)[1] == 1
+    inplace = bad.clone()                                            # in place: the safety net keeps its own copy of the input
+    assert torch.equal(sampler.sample_rk4(m, inplace, ts, out=inplace), safe)
+
+
+def _scaled_layers(name, s0, s12):
+    """the shipped network with layer 0 scaled by s0 and layers 1, 2 by s12: activations, jets and adjoints leave the fp16
+    range for part of the batch while every fp32 quantity stays finite"""
+    from conftest import golden_layers
+    layers, _ = golden_layers(name)
+    sc = [s0, s12, s12, 1.0]
+    return [(W * k, b * k) for (W, b), k in zip(layers, sc)]
+
+
+def test_auto_route_is_range_safe_vs_oracle(cuda_device):
+    """IDFF_IMPL_AUTO never returns a value the reference would not.  A network whose activations overflow
+    fp16 (weights x 8..64, inputs up to 1e4): AUTO = 3xFP16 tensor kernel + fp32 re-solve of the overflowed particles
+    (idff_fixup.cu) against the oracle (the reference's nested-autograd field, Autograd_example_order2.py:44-76) at the
+    normal per-evaluation tolerance, for single evaluations, whole solves, trajectories and the batched gamma sweep."""
+    import idff_oracle as O
+    from idff_b200.weights import PackedWeights
+    layers = _scaled_layers("checkerboard", 64.0, 8.0)
+    pw = PackedWeights([W.numpy() for W, _ in layers], [b.numpy() for _, b in layers], device=cuda_device)
+    gen = torch.Generator().manual_seed(11)
+    n = 4096 + 77
+    x = torch.randn(n, 2, generator=gen) / 1.5
+    x[::7] *= 1.0e4                                                  # every 7th particle far outside the data range
+    xd = x.to(cuda_device)
+    auto = fields.CustomNetModel(pw, 0.2, 0.2, 0.2)                  # impl AUTO
+    raw = fields.CustomNetModel(pw, 0.2, 0.2, 0.2)
+    raw.impl = _lib.IDFF_IMPL_TENSOR16
+    gen_m = fields.CustomNetModel(pw, 0.2, 0.2, 0.2)
+    gen_m.impl = _lib.IDFF_IMPL_GENERIC
+    orc = O.Field2D(layers, 0.2, (0.2, 0.2), 2)
+    for t in (0.0, 0.37, 5.0 / 6.0, 1.0):
+        tt = torch.tensor(t)
+        f_raw = raw(tt, xd)
+        bad = ~torch.isfinite(f_raw).all(dim=1)
+        assert bad.any() and not bad.all(), (t, int(bad.sum()))      # the test network does overflow fp16, for part of the batch
+        f_auto = auto(tt, xd)
+        assert torch.isfinite(f_auto).all()
+        assert torch.equal(f_auto[~bad], f_raw[~bad])                # clean particles: the tensor kernel's own result
+        assert torch.equal(f_auto[bad], gen_m(tt, xd)[bad])          # overflowed ones: fp32 FMA arithmetic
+        ref = orc(tt, x)
+        assert torch.isfinite(ref).all()
+        # per-evaluation tolerance per particle group: a 1e4-scale particle must not hide the O(1) ones behind max|f|
+        for grp in (bad.cpu(), ~bad.cpu()):
+            assert_field_close(f_auto.cpu()[grp].numpy(), ref[grp].numpy(), 2e-5, f"range-safe eval t={t}")
+    assert _lib.weights_nonfinite(pw.handle)[1] > 0
+    # whole solves (in-range start points; the x64 / x8 network drives part of them out of the fp16 range on the way)
+    x0 = (torch.randn(2048 + 5, 2, generator=gen) / 1.5)
+    x0d = x0.to(cuda_device)
+    ts = torch.linspace(0, 1, 3)
+    out_raw = sampler.sample_rk4(raw, x0d, ts)
+    bad = ~torch.isfinite(out_raw).all(dim=1)
+    traj = sampler.odeint(auto, x0d, ts, method="rk4")
+    out = sampler.sample_rk4(auto, x0d, ts)
+    ref_traj = sampler.odeint(gen_m, x0d, ts, method="rk4")
+    assert torch.equal(traj[-1], out) and torch.equal(traj[0], x0d)
+    assert torch.equal(out[~bad], out_raw[~bad])
+    assert torch.equal(traj[:, bad], ref_traj[:, bad])               # re-solved particles incl. their trajectory rows
+    fin = torch.isfinite(ref_traj[-1]).all(dim=1)
+    assert torch.equal(torch.isfinite(out).all(dim=1), fin)          # non-finite only where fp32 itself overflows
+    # batched gamma sweep: same rows as per-tuple AUTO calls
+    gam = [(0.2, 0.0), (0.2, 0.2), (1.0, 2.0), (0.5, 0.0)]
+    models = [fields.CustomNetModel(pw, 0.2, a, b) for a, b in gam]
+    outs = sampler.sample_rk4_sweep(models, x0d, ts)
+    for mdl, o in zip(models, outs):
+        assert torch.equal(o, sampler.sample_rk4(mdl, x0d, ts))
+
+
+def test_cfm_solve_longer_than_one_launch(cuda_device):
+    """CFMModel keeps the x captured at t == 0 for the whole solve (Autograd_example_order2.py:310-332); a grid of
+    more than 96 intervals spans several launches and every launch must see that x0.  Against the oracle's CFM field under
+    the restated rk4, every kernel family; a grid that does not start at t == 0 has no x0 in the reference either."""
+    import idff_oracle as O
+    from conftest import golden_layers
+    layers, _ = golden_layers("checkerboard")
+    pw = packed("checkerboard", cuda_device)
+    x0 = torch.tensor(load_golden("traj2d")["x0"][:300])
+    ts = torch.linspace(0, 1, 131)                                   # 130 intervals
+    ref = O.odeint_rk4(O.FieldCFM(layers), x0, ts)
+    for impl in IMPLS:
+        c = fields.CFMModel(pw)
+        c.impl = impl
+        traj = sampler.odeint(c, x0.to(cuda_device), ts, method="rk4")
+        assert drift_report(traj[-1].cpu().numpy(), ref[-1].numpy())["max"] <= 2e-4, impl
+        assert drift_report(traj[100].cpu().numpy(), ref[100].numpy())["max"] <= 2e-4, impl
+        with pytest.raises(_lib.IdffError):
+            sampler.sample_rk4(c, x0.to(cuda_device), torch.linspace(0.25, 1, 4))
