@@ -35,6 +35,25 @@ void count_launch(int n = 1);
     }                                                                                                \
   } while (0)
 
+// Entry points without a handle launch on the device that owns their buffers, whatever device is current on the calling
+// thread (a tensor on cuda:1 while cuda:0 is current must not launch on cuda:0).
+struct PtrDeviceGuard {
+  int prev = -1, dev = 0;
+  explicit PtrDeviceGuard(const void* p) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    dev = prev < 0 ? 0 : prev;
+    cudaPointerAttributes a;
+    if (p != nullptr && cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeDevice && a.device != dev &&
+        cudaSetDevice(a.device) == cudaSuccess)
+      dev = a.device;
+    else
+      cudaGetLastError();   // a host pointer in a validation test is not an error here
+  }
+  ~PtrDeviceGuard() {
+    if (prev >= 0 && dev != prev) cudaSetDevice(prev);
+  }
+};
+
 // ---- the packed network --------------------------------------------------------------------------------------
 // Device view of one 4-layer SELU MLP (torchcfm/models/models.py:4-21).  All pointers are device pointers.
 struct NetView {

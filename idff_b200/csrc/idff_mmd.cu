@@ -180,6 +180,7 @@ extern "C" int idff_mmd_rbf(const float* d_x, int64_t N, const float* d_y, int64
   IDFF_CHECK_ARG(sigma_k > 0.0f, "idff_mmd_rbf: sigma_k must be positive");
   IDFF_CHECK_ARG(0 <= x_row_begin && x_row_begin <= x_row_end && x_row_end <= N, "idff_mmd_rbf: bad x row range");
   IDFF_CHECK_ARG(0 <= y_row_begin && y_row_begin <= y_row_end && y_row_end <= M, "idff_mmd_rbf: bad y row range");
+  PtrDeviceGuard guard(d_sums);
   MmdJobs jobs;
   const bool small = D <= 4;   // the symmetric shortcut is implemented by the small-D kernel
   jobs.job[0] = {d_x, d_x, (long)x_row_begin, (long)x_row_end, (long)N, small && x_row_begin == 0 && x_row_end == N};
@@ -220,6 +221,7 @@ extern "C" int idff_mmd_rbf_sweep(const float* d_x, int64_t N, const float* d_y,
     set_error("idff_mmd_rbf_sweep: D = %d (the batched kernel serves D <= 4; call idff_mmd_rbf per set)", D);
     return IDFF_EUNSUPPORTED;
   }
+  PtrDeviceGuard guard(d_sums);
   const float scale = (float)sqrt(1.4426950408889634 / (2.0 * (double)sigma_k * (double)sigma_k));
   const long amax = N > M ? N : M;
   dim3 grid((unsigned)((amax + 256 * kSmallRA - 1) / (256 * kSmallRA)), (unsigned)((amax + kSmallBC - 1) / kSmallBC),

@@ -414,6 +414,7 @@ extern "C" int idff_ot_assign(const float* d_x0, const float* d_x1, int32_t n, i
   IDFF_CHECK_ARG(D >= 1, "idff_ot_assign: D = %d", D);
   if (n == 0) return IDFF_OK;
   IDFF_CHECK_ARG(d_x0 && d_x1 && d_perm, "idff_ot_assign: null pointer");
+  PtrDeviceGuard guard(d_perm);
   cudaStream_t s = (cudaStream_t)stream;
   if (n > 64 && !g_ot_sap) {   // auction: parallel over the unassigned rows
     const size_t sm = ot::auction_smem_bytes(n, D == 2 ? 2 : 0);

@@ -291,8 +291,8 @@ extern "C" int idff_path_sample(const float* d_x0, const float* d_x1, const floa
   if (B == 0) return IDFF_OK;
   IDFF_CHECK_ARG(d_x0 && d_x1 && d_t && d_xt, "idff_path_sample: null pointer");
   IDFF_CHECK_ARG(sigma_mode == 0 || sigma_mode == 1, "idff_path_sample: sigma_mode %d", sigma_mode);
-  int dev = 0;
-  IDFF_CUDA(cudaGetDevice(&dev));
+  PtrDeviceGuard guard(d_xt);
+  const int dev = guard.dev;
   const long n = (long)B * (long)D;
   auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const bool vec = !d_idx0 && !d_idx1 && (n % 4 == 0) && al16(d_x0) && al16(d_x1) && al16(d_eps) && al16(d_xt) && al16(d_ut);
@@ -322,8 +322,8 @@ extern "C" int idff_compute_lambda(const float* d_t, float sigma, int32_t sigma_
                                    int64_t B, void* stream) {
   if (B == 0) return IDFF_OK;
   IDFF_CHECK_ARG(d_t && d_out && B > 0, "idff_compute_lambda: bad argument");
-  int dev = 0;
-  IDFF_CUDA(cudaGetDevice(&dev));
+  PtrDeviceGuard guard(d_out);
+  const int dev = guard.dev;
   k_lambda<<<stream_grid(B, 256, dev, 4), 256, 0, (cudaStream_t)stream>>>(d_t, sigma, sigma_mode, dynamic, d_out, (long)B);
   IDFF_CUDA(cudaGetLastError());
   count_launch();
@@ -340,8 +340,8 @@ extern "C" int idff_loss(int32_t kind, const float* d_a, const float* d_x1, cons
   IDFF_CHECK_ARG(d_a && d_x1 && d_loss && d_scratch, "idff_loss: null pointer");
   IDFF_CHECK_ARG(kind == 2 || d_t, "idff_loss: kind %d needs t", kind);
   IDFF_CHECK_ARG(kind != 1 || (d_x0 && d_xt), "idff_loss: the score loss needs x0 and xt");
-  int dev = 0;
-  IDFF_CUDA(cudaGetDevice(&dev));
+  PtrDeviceGuard guard(d_loss);
+  const int dev = guard.dev;
   const long n = (long)B * (long)D;
   auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const bool vec = (n % 4 == 0) && al16(d_a) && al16(d_x1) && al16(d_x0) && al16(d_xt) && al16(d_grad);

@@ -747,6 +747,7 @@ extern "C" int idff_debug_train_stamps(int64_t* h_out, int32_t n_ctas) {
 
 extern "C" int idff_train_flow_init(float* d_state, void* stream) {
   IDFF_CHECK_ARG(d_state && (reinterpret_cast<uintptr_t>(d_state) & 15) == 0, "idff_train_flow_init: state must be a 16-byte aligned device pointer");
+  PtrDeviceGuard guard(d_state);
   k_train_init<<<(W * W + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_state);
   IDFF_CUDA(cudaGetLastError());
   count_launch();
@@ -768,8 +769,8 @@ extern "C" int idff_train_flow_steps(float* d_state, const float* d_x0, const fl
   IDFF_CHECK_ARG(sigma_mode == 0 || sigma_mode == 1, "idff_train_flow_steps: sigma_mode %d", sigma_mode);
   IDFF_CHECK_ARG(steps_done >= 0, "idff_train_flow_steps: steps_done < 0");
   if (n_steps == 0) return IDFF_OK;
-  int dev = 0, sms = 0, coop = 0;
-  IDFF_CUDA(cudaGetDevice(&dev));
+  PtrDeviceGuard guard(d_state);
+  int dev = guard.dev, sms = 0, coop = 0;
   IDFF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   IDFF_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
   if (!coop || sms < N_JOBS) {
@@ -777,11 +778,11 @@ extern "C" int idff_train_flow_steps(float* d_state, const float* d_x0, const fl
     return IDFF_EUNSUPPORTED;
   }
   int grid = sms < MAX_GRID ? sms : MAX_GRID;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_set = 0;   // bit per device: the attribute is per device, not per process
+  if (dev >= 64 || !((attr_set >> dev) & 1ull)) {
     IDFF_CUDA(cudaFuncSetAttribute(k_train_flow<1, RMIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     IDFF_CUDA(cudaFuncSetAttribute(k_train_flow<2, RMIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    attr_set = true;
+    if (dev < 64) attr_set |= 1ull << dev;
   }
   Args a;
   a.S = d_state;

@@ -63,9 +63,18 @@ class ConditionalFlowMatcher:
     def compute_sigma_t(self, t):
         del t
         return self.sigma
+    compute_sigma_t._idff_sigma_mode = 0     # the kernel's sigma_mode that computes exactly this function
+
+    def _kernel_sigma_mode(self):
+        """sigma_mode of the path-sample kernel that reproduces type(self).compute_sigma_t, or None when a subclass
+        overrides it with something the kernel does not know (the reference routes everything through compute_sigma_t)."""
+        return getattr(type(self).compute_sigma_t, "_idff_sigma_mode", None)
 
     def sample_xt(self, x0, x1, t, epsilon):
-        xt, _ = _path_sample(x0, x1, t, epsilon, self.sigma, self._sigma_mode, want_ut=False)
+        mode = self._kernel_sigma_mode()
+        if mode is None or type(self).compute_mu_t is not ConditionalFlowMatcher.compute_mu_t:
+            return self.compute_mu_t(x0, x1, t) + pad_t_like_x(self.compute_sigma_t(t), x0) * epsilon   # reference :119-123
+        xt, _ = _path_sample(x0, x1, t, epsilon, self.sigma, mode, want_ut=False)
         return xt
 
     def compute_conditional_flow(self, x0, x1, t, xt):
@@ -79,7 +88,7 @@ class ConditionalFlowMatcher:
         c = type(self)
         base = ConditionalFlowMatcher
         return (c.compute_mu_t is base.compute_mu_t and c.sample_xt is base.sample_xt
-                and c.compute_conditional_flow is base.compute_conditional_flow)
+                and c.compute_conditional_flow is base.compute_conditional_flow and self._kernel_sigma_mode() is not None)
 
     def sample_location_and_conditional_flow(self, x0, x1, t=None, return_noise=False):
         if t is None:
@@ -87,7 +96,7 @@ class ConditionalFlowMatcher:
         assert len(t) == x0.shape[0], "t has to have batch size dimension"
         eps = self.sample_noise_like(x0)                     # then the noise (reference :187)
         if self._fusable():
-            xt, ut = _path_sample(x0, x1, t, eps, self.sigma, self._sigma_mode)
+            xt, ut = _path_sample(x0, x1, t, eps, self.sigma, self._kernel_sigma_mode())
         else:
             xt = self.sample_xt(x0, x1, t, eps)
             ut = self.compute_conditional_flow(x0, x1, t, xt)
@@ -96,10 +105,14 @@ class ConditionalFlowMatcher:
         return t, xt, ut
 
     def compute_lambda(self, t):
+        mode = self._kernel_sigma_mode()
+        if mode is None:     # a compute_sigma_t the kernel does not know: the reference's expression (:210-211 / _dynamic :213-214)
+            sigma_t = self.compute_sigma_t(t)
+            return 2 * (sigma_t if self._lambda_dynamic else sigma_t ** 2) / (self.sigma ** 2 + 1e-8)
         _lib.require_cuda(t, "t")
         tc = t.contiguous()
         out = torch.empty_like(tc)
-        _lib.check(_lib.lib().idff_compute_lambda(_lib.ptr(tc), float(self.sigma), self._sigma_mode,
+        _lib.check(_lib.lib().idff_compute_lambda(_lib.ptr(tc), float(self.sigma), mode,
                                                   self._lambda_dynamic, _lib.ptr(out), tc.numel(),
                                                   _lib.stream_of(tc)), "idff_compute_lambda")
         return out
@@ -117,6 +130,7 @@ class ExactOptimalTransportConditionalFlowMatcher(ConditionalFlowMatcher):
 
     def compute_sigma_t(self, t):
         return self.sigma * torch.sqrt(t * (1 - t))
+    compute_sigma_t._idff_sigma_mode = 1
 
     def sample_location_and_conditional_flow(self, x0, x1, t=None, return_noise=False):
         self.x1 = x1
@@ -169,6 +183,7 @@ class SchrodingerBridgeConditionalFlowMatcher(ConditionalFlowMatcher):
 
     def compute_sigma_t(self, t):
         return self.sigma * torch.sqrt(t * (1 - t))
+    compute_sigma_t._idff_sigma_mode = 1
 
     def compute_conditional_flow(self, x0, x1, t, xt):
         tp = pad_t_like_x(t, x0)

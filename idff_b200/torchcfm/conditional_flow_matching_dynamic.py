@@ -29,6 +29,15 @@ class ExactOptimalTransportConditionalFlowMatcher(ConditionalFlowMatcher):
 
     def compute_sigma_t(self, t):
         return self.sigma * torch.sqrt(t * (1 - t))
+    compute_sigma_t._idff_sigma_mode = 1
+
+    def _paired_path_sample(self, x0, x1, t, eps, i, j):
+        mode = self._kernel_sigma_mode()
+        if mode is None:     # a subclass changed compute_sigma_t: gather in torch, then the reference's expressions
+            xi, xj = x0[i], x1[j]
+            xt = self.sample_xt(xi, xj, t, eps)
+            return xt, self.compute_conditional_flow(xi, xj, t, xt)
+        return _cfm._path_sample(x0, x1, t, eps, self.sigma, mode, idx0=i, idx1=j)   # gather fused into the kernel
 
     def sample_location_and_conditional_flow(self, x0, x1, t=None, return_noise=False):
         i, j = self.ot_sampler.sample_map_indices(x0, x1)          # int64 device tensors, (bs,)
@@ -36,7 +45,7 @@ class ExactOptimalTransportConditionalFlowMatcher(ConditionalFlowMatcher):
             t = torch.rand(x0.shape[0]).type_as(x0)
         assert len(t) == x0.shape[0], "t has to have batch size dimension"
         eps = self.sample_noise_like(x0)
-        xt, ut = _cfm._path_sample(x0, x1, t, eps, self.sigma, self._sigma_mode, idx0=i, idx1=j)
+        xt, ut = self._paired_path_sample(x0, x1, t, eps, i, j)
         self.x0, self.x1 = x0[i], x1[j]
         if return_noise:
             return t, xt, ut, eps
@@ -49,7 +58,7 @@ class ExactOptimalTransportConditionalFlowMatcher(ConditionalFlowMatcher):
             t = torch.rand(x0.shape[0]).type_as(x0)
         assert len(t) == x0.shape[0], "t has to have batch size dimension"
         eps = self.sample_noise_like(x0)
-        xt, ut = _cfm._path_sample(x0, x1, t, eps, self.sigma, self._sigma_mode, idx0=i, idx1=j)
+        xt, ut = self._paired_path_sample(x0, x1, t, eps, i, j)
         self.x0, self.x1 = x0[i], x1[j]
         y0 = y0[i] if y0 is not None else None
         y1 = y1[j] if y1 is not None else None

@@ -244,6 +244,7 @@ def main():
 
     golden_metrics()
     golden_aux_matchers()
+    golden_mlp_embedding()
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"wrote {len(os.listdir(OUT))} files, {tot / 1e6:.2f} MB -> {OUT}")
 
@@ -281,9 +282,32 @@ def golden_aux_matchers():
     np.savez(os.path.join(OUT, "matchers.npz"), **out)
 
 
+def golden_mlp_embedding():
+    """a2: the reference's MLP_Embedding.forward (torchcfm/models/models.py:23-42) itself -- the shipped PolyALA module
+    (Linear(175,128) .. Linear(128,46), Embedding(200,128)) called as the scripts call it, model(cat[y, t], ti) with one
+    time index per batch (MD_simulation.py:501-504) -- and the plain MLP.forward (:4-21) of the 2-D checkpoint."""
+    net = R.load_md_checkpoint()
+    g = torch.Generator().manual_seed(33)
+    out = {}
+    y = torch.randn(33, 46, generator=g) * 60
+    for ti in (0, 7, 199):
+        for tv in (0.0, 0.4, 1.0):
+            inp = torch.cat([y, torch.full((33, 1), tv)], -1)
+            with torch.no_grad():
+                out[f"emb_ti{ti}_t{tv}"] = net(inp, torch.full((33, 1), float(ti))).numpy()
+    out["y"] = y.numpy()
+    net2 = R.load_2d_checkpoint("checkerboard")
+    x = torch.cat([torch.randn(257, 2, generator=g) * 2, torch.rand(257, 1, generator=g)], -1)
+    with torch.no_grad():
+        out["mlp_in"], out["mlp_out"] = x.numpy(), net2(x).numpy()
+    np.savez(os.path.join(OUT, "mlp_modules.npz"), **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "metrics":
         golden_metrics()
+    elif len(sys.argv) > 1 and sys.argv[1] == "mlp":
+        golden_mlp_embedding()
     elif len(sys.argv) > 1 and sys.argv[1] == "matchers":
         golden_aux_matchers()
     else:

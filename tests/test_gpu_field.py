@@ -131,6 +131,17 @@ def test_mlp_embedding_module(cuda_device):
         out = net(inp, ti)                                  # kernel path with the folded bias of row 7
         assert _lib.launch_count() == before + 1
     assert_field_close(out.cpu().numpy(), ref.detach().cpu().numpy(), 2e-6, "MLP_Embedding kernel vs torch")
+    # against the reference's own module: outputs of torchcfm/models/models.py:23-42 on the shipped PolyALA
+    # checkpoint, written by oracle/make_golden.py.  Folding the embedding into the layer-0 bias re-associates a 175-term
+    # fp32 dot product: 3e-5 abs on O(100) outputs
+    g = load_golden("mlp_modules")
+    yg = torch.tensor(g["y"]).to(cuda_device)
+    with torch.no_grad():
+        for tidx in (0, 7, 199):
+            for tv in (0.0, 0.4, 1.0):
+                inp = torch.cat([yg, torch.full((33, 1), tv, device=cuda_device)], -1)
+                out = net(inp, torch.full((33, 1), float(tidx), device=cuda_device))
+                assert_field_close(out.cpu().numpy(), g[f"emb_ti{tidx}_t{tv}"], 2e-6, f"MLP_Embedding vs reference module ti={tidx} t={tv}")
 
 
 def test_field_shape_errors(cuda_device):

@@ -354,3 +354,25 @@ def test_aux_matchers_vs_reference_golden(cuda_device):
                                        atol=2e-4 if name == "sb" else 2e-6, err_msg=f"{key} {name} ut")
     with pytest.raises(ValueError):
         cfm.SchrodingerBridgeConditionalFlowMatcher(0.0)
+    # compute_lambda and the path noise go through compute_sigma_t (reference :195-211), also for subclasses
+    # that override only that method -- the kernel serves the two sigma_t forms it knows, everything else is torch
+    t = torch.rand(64, device=cuda_device)
+    FM = cfm.TargetConditionalFlowMatcher(0.1)
+    np.testing.assert_allclose(FM.compute_lambda(t).cpu().numpy(),
+                               (2 * (1 - (1 - 0.1) * t) ** 2 / (0.1 ** 2 + 1e-8)).cpu().numpy(), rtol=1e-6)
+
+    class Halved(cfm.ConditionalFlowMatcher):
+        def compute_sigma_t(self, t):
+            return 0.5 * self.sigma * (1 - t)
+
+    FM = Halved(0.3)
+    assert FM._kernel_sigma_mode() is None and not FM._fusable()
+    x0, x1, eps = (torch.randn(64, 2, device=cuda_device) for _ in range(3))
+    FM.sample_noise_like = lambda x: eps
+    _, xt, ut = FM.sample_location_and_conditional_flow(x0, x1, t=t)
+    tp = t[:, None]
+    np.testing.assert_allclose(xt.cpu().numpy(), (tp * x1 + (1 - tp) * x0 + 0.5 * 0.3 * (1 - tp) * eps).cpu().numpy(), rtol=1e-6, atol=1e-6)
+    assert torch.equal(ut, x1 - x0)
+    np.testing.assert_allclose(FM.compute_lambda(t).cpu().numpy(),
+                               (2 * (0.15 * (1 - t)) ** 2 / (0.3 ** 2 + 1e-8)).cpu().numpy(), rtol=1e-6)
+    assert cfm.ExactOptimalTransportConditionalFlowMatcher(0.5)._kernel_sigma_mode() == 1 and cfm.ConditionalFlowMatcher(0.5)._fusable()

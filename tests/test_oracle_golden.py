@@ -147,3 +147,18 @@ def test_md_metrics_match_golden():
     r = O.md_compute_metrics(g["y_hat"], g["dataset"])
     for k in ("CC_mean", "CC_std", "RMSE_mean", "RMSE_std", "MAE_mean", "MAE_std"):
         assert float(r[k]) == float(g[k]), k
+
+
+def test_mlp_modules_match_golden():
+    """a1/a2: the oracle's MLP / MLP_Embedding restatement against outputs of the reference's own modules
+    (tests/golden/mlp_modules.npz, written by oracle/make_golden.py golden_mlp_embedding)."""
+    g = load_golden("mlp_modules")
+    layers, emb = golden_layers("polyala")
+    y = torch.tensor(g["y"])
+    for ti in (0, 7, 199):
+        for tv in (0.0, 0.4, 1.0):
+            inp = torch.cat([y, torch.full((33, 1), tv)], -1)
+            out = O.mlp_embedding_forward(layers, emb, inp, torch.full((33, 1), float(ti)))
+            assert torch.equal(out, torch.tensor(g[f"emb_ti{ti}_t{tv}"]))
+    l2, _ = golden_layers("checkerboard")
+    assert torch.equal(O.mlp_forward(l2, torch.tensor(g["mlp_in"])), torch.tensor(g["mlp_out"]))
