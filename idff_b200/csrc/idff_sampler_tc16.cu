@@ -53,14 +53,15 @@ constexpr int NKB = W / 64;               // 4 weight k-blocks of 64 (= 8 operan
 constexpr int ACT_BYTES = (W / 32) * KB_BYTES;
 constexpr int NE = 512;                   // epilogue threads: warp w -> lane quarter w & 3, particle quarter w >> 2
 constexpr int NEW = NE / 32;
-constexpr int NTHREADS = NE + 64;         // + producer warp 16 + MMA warp 17
+constexpr int NTHREADS = NE + 128;        // + producer warp 16 + MMA warp 17 + integrator warps 18, 19
 constexpr int HP = 16;                    // particles per epilogue thread
 constexpr int TMEM_COLS = 512;
 constexpr int COL_CORR = 128, COL_STASH = 256;
 
 using namespace tcg;
 
-// phase timestamps (clock64) of CTA 0, first tile, evaluation 1 (an interior one): diagnostic only
+// phase timestamps (clock64) of CTA 0, first tile, evaluation 1 (an interior one): diagnostic only, compiled in with
+// -DIDFF_TC16_STAMPS (make STAMPS=1); all zero in the production build
 __device__ long long g_tc16_stamps[32];
 
 struct TParams {
@@ -168,10 +169,24 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
     const long g = (blockIdx.x + it * gridDim.x) / tiles_per_set;
     return (int)(g < P.n_sets ? g : P.n_sets - 1);
   };
-  auto stage_of = [&](int e, int g) -> const Stage& { return P.mode == 0 ? one : (P.mode == 1 ? rk.st[e] : P.tabs[g].st[e]); };
-  auto heavy_of = [&](const Stage& st, int g) { return st.kind == 2 && (P.mode == 2 ? P.tabs[g].reverse : P.reverse) != 0; };
+  // by value: `one` / `rk` live in the constant bank, sweep tables in global memory -- a reference to "one of the three" makes
+  // every field access a generic-address load (LD.E, long scoreboard) in the middle of the epilogue
+  auto stage_of = [&](int e, int g) -> Stage {
+    if (P.mode == 0) return one;
+    if (P.mode == 1) return rk.st[e];
+    return P.tabs[g].st[e];
+  };
+  auto kind_of = [&](int e, int g) -> int { return P.mode == 0 ? one.kind : (P.mode == 1 ? rk.st[e].kind : P.tabs[g].st[e].kind); };
+  auto heavy_of = [&](int kind, int g) { return kind == 2 && (P.mode == 2 ? P.tabs[g].reverse : P.reverse) != 0; };
 
+  // Register budget: 20 warps x 96 registers at launch.  The four service warps (TMA, MMA, 2 x integrator) give back 64 each,
+  // the sixteen epilogue warps take 16 each: their jet / adjoint algebra holds 2 x 16 accumulators + 32 packed operand words.
+  // (Each setmaxnreg sits at the top of the branch it governs: ptxas budgets the code a setmaxnreg DOMINATES -- placed in
+  // an if / else ahead of the role branches, every role was compiled under the smaller limit.  Warps 16..19 are one
+  // warpgroup and execute the same instruction.)
+  if (warp >= NEW) {
   if (warp == NEW) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     // ===== TMA producer: weight tile images of every layer pass, in consumption order.  Whole warp in uniform control
     // flow (addresses in uniform registers), one elected lane issues; no back-off on the slot wait: the ring is only
     // three stages deep and a late refill stalls the tensor pipe
@@ -184,7 +199,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
       for (long it = 0; it < n_iter; ++it)
         for (int e = 0; e < n_eval; ++e) {
           const int gs = set_of(it);
-          const int ng = heavy_of(stage_of(e, gs), gs) ? 4 : 2;
+          const int ng = heavy_of(kind_of(e, gs), gs) ? 4 : 2;
           for (int g = 0; g < ng; ++g)
             for (int t = 0; t < 2 * NKB; ++t) {   // (m-tile, k-block) tiles of gemm g are contiguous
               mbar_wait(&empty[stage], phase ^ 1u);
@@ -199,6 +214,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
         }
     }
   } else if (warp == NEW + 1) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     // ===== MMA issuer.  The whole warp walks the schedule in uniform control flow, so descriptors, TMEM addresses and
     // barrier phases live in uniform registers and each tcgen05.mma costs a handful of instructions; one elected lane
     // issues.  (Issued from an `if (lane == 0)` region every UTCHMMA was preceded by an ELECT / 7 x R2UR.BROADCAST /
@@ -216,11 +232,15 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
       for (long it = 0; it < n_iter; ++it)
         for (int e = 0; e < n_eval; ++e) {
           const int gs = set_of(it);
-          const bool heavy = heavy_of(stage_of(e, gs), gs);
+          const bool heavy = heavy_of(kind_of(e, gs), gs);
           const int ng = heavy ? 4 : 2;
+#ifdef IDFF_TC16_STAMPS
           const bool mstamp = blockIdx.x == 0 && it == 0 && e == 1 && lane == 0;
           if (mstamp)
             for (int i = 24; i < 29; ++i) g_tc16_stamps[i] = 0;
+#else
+          constexpr bool mstamp = false;   // phase stamps cost the issuing warp registers it does not have: diagnostic builds only
+#endif
           for (int g = 0; g < ng; ++g) {
             for (int mt = 0; mt < 2; ++mt) {
               long long c0 = mstamp ? clock64() : 0;
@@ -280,6 +300,104 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
         }
     }
   } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    // ===== integrator warps (18, 19): one particle per lane.  x1hat / gradient totals from red[], the field's closed form
+    // and the RK4 (3/8 rule) stage update in torchdiffeq's operation order; the state (y, k1..k3, x0) lives in this thread's
+    // registers for the whole solve -- and no longer in those of the 512 epilogue threads, whose budget it strained.
+    const float* red = misc + Smem::f_red;
+    float* sxs = misc + Smem::f_xs;
+    const float third = (float)(1.0 / 3.0);
+    float sy[2] = {0.f, 0.f}, sk1[2] = {0.f, 0.f}, sk2[2] = {0.f, 0.f}, sk3[2] = {0.f, 0.f}, sx0[2] = {0.f, 0.f};
+    const int myp = (warp - (NEW + 2)) * 32 + lane;
+    // where red[] holds the totals of particle myp: warps 4*(myp/16) .. +3, lane (2*(c/4) + d)*4 + c%4 with c = myp%16
+    const int red_w = (myp >> 4) * 4, red_l = ((myp & 15) >> 2) * 8 + (myp & 3);
+    for (long it = 0; it < n_iter; ++it) {
+      const long tile = blockIdx.x + it * gridDim.x;
+      const int gs = set_of(it);
+      // first particle of the tile; may lie beyond N: an all-padding tile
+      const long base = (P.mode == 2 ? (tile < n_tiles ? tile - (long)gs * tiles_per_set : tiles_per_set) : tile) * NP;
+      float* const out_set = P.out + (P.mode == 2 ? (size_t)gs * P.N * 2 : (size_t)0);
+      const long row = base + myp;
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        const float v = row < P.N ? P.x_in[row * 2 + d] : 0.0f;
+        sy[d] = v;
+        sxs[2 * myp + d] = v;
+        if (P.variant == IDFF_FIELD_CFM && P.x0_cfm) sx0[d] = row < P.N ? P.x0_cfm[row * 2 + d] : 0.0f;
+      }
+      ebar576();
+#pragma unroll 1
+      for (int ev = 0; ev < n_eval; ++ev) {
+        const Stage st = stage_of(ev, gs);
+        const bool heavy = heavy_of(st.kind, gs);
+        ebar576();   // x1hat partial sums are in red[]
+        float pr_tot[2], gg[2] = {0.f, 0.f};
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {   // fixed summation order over the 4 lane-quarter warps of the particle's quarter
+          float acc = __ldg(P.net.b3 + d);
+#pragma unroll
+          for (int w4 = 0; w4 < 4; ++w4) acc += red[(red_w + w4) * 32 + red_l + 4 * d];
+          pr_tot[d] = acc;
+        }
+        if (heavy) {
+          ebar576();   // gradient partial sums are in red[]
+#pragma unroll
+          for (int d = 0; d < 2; ++d) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int w4 = 0; w4 < 4; ++w4) acc += red[(red_w + w4) * 32 + red_l + 4 * d];
+            gg[d] = acc;
+          }
+        }
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          const float pr = pr_tot[d];
+          const float x = sxs[2 * myp + d];
+          float f;
+          if (P.variant == IDFF_FIELD_CFM) {
+            if (st.kind == 0) sx0[d] = x;
+            f = __fsub_rn(pr, sx0[d]);
+          } else {
+            const float diff = __fsub_rn(pr, x);
+            if (st.kind == 0) f = diff;
+            else if (st.kind == 1) f = __fdiv_rn(diff, st.end_div);
+            else {
+              f = __fdiv_rn(__fmul_rn(st.a, diff), st.den);
+              if (heavy) f = __fadd_rn(f, gg[d]);
+            }
+          }
+          if (row < P.N && !(fabsf(f) <= 3.0e38f)) atomicAdd(P.counters, 1ull);
+          if (P.mode == 0) {
+            if (row < P.N) out_set[row * 2 + d] = f;
+          } else {
+            const int iv = ev >> 2, sg = ev & 3;
+            const float dt = P.mode == 2 ? P.tabs[gs].dt[iv] : rk.dt[iv], y = sy[d];
+            float xn;
+            if (sg == 0) {
+              sk1[d] = f;
+              xn = __fadd_rn(y, __fmul_rn(__fmul_rn(dt, f), third));
+            } else if (sg == 1) {
+              sk2[d] = f;
+              xn = __fadd_rn(y, __fmul_rn(dt, __fsub_rn(f, __fmul_rn(sk1[d], third))));
+            } else if (sg == 2) {
+              sk3[d] = f;
+              xn = __fadd_rn(y, __fmul_rn(dt, __fadd_rn(__fsub_rn(sk1[d], sk2[d]), f)));
+            } else {
+              const float sum = __fadd_rn(__fadd_rn(sk1[d], __fmul_rn(3.0f, __fadd_rn(sk2[d], sk3[d]))), f);
+              xn = __fadd_rn(y, __fmul_rn(__fmul_rn(sum, dt), 0.125f));
+              sy[d] = xn;
+              if (P.traj != nullptr && row < P.N) P.traj[((size_t)(iv + 1) * P.N + row) * 2 + d] = xn;
+              if (ev == n_eval - 1 && row < P.N) out_set[row * 2 + d] = xn;
+            }
+            sxs[2 * myp + d] = xn;
+          }
+        }
+        ebar576();   // the next stage's input is in sxs
+      }
+    }
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     // ===== epilogue warps: thread <-> 4 consecutive hidden units x 4 particles (see the header comment)
     const int q = warp & 3, pq = warp >> 2;
     const int p0 = pq * HP;
@@ -292,13 +410,6 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
     float* sxs = misc + Smem::f_xs;        // stage input of the 64 particles, [p][2]
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + p0;   // + (16 << 16) for the upper 16 lanes
     uint32_t aphase = 0, kphase = 0;
-    const float third = (float)(1.0 / 3.0);
-    // integrator state of particle warp*32 + lane, held by warps 0 and 1 (2 components each)
-    float sy[2] = {0.f, 0.f}, sk1[2] = {0.f, 0.f}, sk2[2] = {0.f, 0.f}, sk3[2] = {0.f, 0.f}, sx0[2] = {0.f, 0.f};
-    float pr_tot[2] = {0.f, 0.f};
-    const int myp = (warp & 1) * 32 + lane;   // particle served by this thread in the integrator part (warps 0, 1)
-    // where red[] holds the totals of particle myp: warps 4*(myp/16) .. +3, lane (2*(c/4) + d)*4 + c%4 with c = myp%16
-    const int red_w = (myp >> 4) * 4, red_l = ((myp & 15) >> 2) * 8 + (myp & 3);
     // this thread's 8-byte group inside the operand rows of its particles p0 + 4r + c4: operand k-block mt*4 + q, 16-byte
     // chunk (slot >> 1) ^ ((row >> 1) & 3) [SWIZZLE_64B], half slot & 1.  (row >> 1) & 3 = ((r & 1) << 1) | (c4 >> 1).
     uint32_t sa0[2];
@@ -325,8 +436,11 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
       tmem_ld8(lane_base + COL_CORR + j * NP, c);
       tmem_ld8(lane_base + (16u << 16) + COL_CORR + j * NP, c + 8);
       tmem_wait_ld();
+      const uint64_t inv2 = pk2(LO_INV, LO_INV);
 #pragma unroll
-      for (int i = 0; i < HP; ++i) z[i] = fmaf(__uint_as_float(c[i]), LO_INV, __uint_as_float(m[i]));
+      for (int i = 0; i < HP; i += 2)   // FFMA2: the loaded registers are consecutive pairs already
+        upk2(fma2(pk2(__uint_as_float(c[i]), __uint_as_float(c[i + 1])), inv2, pk2(__uint_as_float(m[i]), __uint_as_float(m[i + 1]))),
+             z[i], z[i + 1]);
     };
     // boundary evaluations: jet 0 summed over the two accumulator sets [main 64 | corr 64] at columns 0 and 128
     auto load_acc2 = [&](float (&z)[HP]) {
@@ -374,27 +488,17 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
 
     mbar_arrive(acc_free);   // nothing to read out before the very first m-tile
     for (long it = 0; it < n_iter; ++it) {
-      const long tile = blockIdx.x + it * gridDim.x;
       const int gs = set_of(it);
-      // first particle of the tile; may lie beyond N: an all-padding tile
-      const long base = (P.mode == 2 ? (tile < n_tiles ? tile - (long)gs * tiles_per_set : tiles_per_set) : tile) * NP;
-      float* const out_set = P.out + (P.mode == 2 ? (size_t)gs * P.N * 2 : (size_t)0);
-      if (warp < 2) {
-        const long row = base + myp;
-#pragma unroll
-        for (int d = 0; d < 2; ++d) {
-          const float v = row < P.N ? P.x_in[row * 2 + d] : 0.0f;
-          sy[d] = v;
-          sxs[2 * myp + d] = v;
-          if (P.variant == IDFF_FIELD_CFM && P.x0_cfm) sx0[d] = row < P.N ? P.x0_cfm[row * 2 + d] : 0.0f;
-        }
-      }
-      ebar();
+      ebar576();   // the integrator warps have written the tile's start points to sxs
 #pragma unroll 1
       for (int ev = 0; ev < n_eval; ++ev) {
-        const Stage& st = stage_of(ev, gs);
-        const bool heavy = heavy_of(st, gs);
+        const Stage st = stage_of(ev, gs);
+        const bool heavy = heavy_of(st.kind, gs);
+#ifdef IDFF_TC16_STAMPS
         const bool stamp = blockIdx.x == 0 && it == 0 && ev == 1 && tid == 0;
+#else
+        constexpr bool stamp = false;
+#endif
         if (stamp) g_tc16_stamps[0] = clock64();
         // ---- layer 1 (K = 3, computed directly): a1 and, for interior evaluations, a1' = s'(z1) * (W0 d).
         // Every MMA of the previous evaluation is complete (this thread waited for its last accumulators).
@@ -542,18 +646,8 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
           red[warp * 32 + lane] = rsum;
         }
         if (stamp) g_tc16_stamps[5] = clock64();
-        ebar();
-        if (warp < 2) {   // x1hat of particle myp: fixed summation order over the 4 lane-quarter warps of its quarter
-#pragma unroll
-          for (int d = 0; d < 2; ++d) {
-            float acc = __ldg(P.net.b3 + d);
-#pragma unroll
-            for (int w4 = 0; w4 < 4; ++w4) acc += red[(red_w + w4) * 32 + red_l + 4 * d];
-            pr_tot[d] = acc;
-          }
-        }
+        ebar576();   // x1hat partial sums are in red[]: the integrator warps add them up
         if (stamp) g_tc16_stamps[6] = clock64();
-        float gg[2] = {0.f, 0.f};
         if (heavy) {
           // ---- gemm 2: reverse, layer 3 -> 2
 #pragma unroll 1
@@ -630,66 +724,10 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
           }
           red[warp * 32 + lane] = gsum;
           if (stamp) g_tc16_stamps[10] = clock64();
-          ebar();
-          if (warp < 2) {
-#pragma unroll
-            for (int d = 0; d < 2; ++d) {
-              float acc = 0.0f;
-#pragma unroll
-              for (int w4 = 0; w4 < 4; ++w4) acc += red[(red_w + w4) * 32 + red_l + 4 * d];
-              gg[d] = acc;
-            }
-          }
+          ebar576();   // gradient partial sums are in red[]
         }
         if (stamp) g_tc16_stamps[11] = clock64();
-        // ---- combine + integrator stage update: warps 0 and 1, one particle per lane
-        if (warp < 2) {
-          const long row = base + myp;
-#pragma unroll
-          for (int d = 0; d < 2; ++d) {
-            const float pr = pr_tot[d];
-            const float x = sxs[2 * myp + d];
-            float f;
-            if (P.variant == IDFF_FIELD_CFM) {
-              if (st.kind == 0) sx0[d] = x;
-              f = __fsub_rn(pr, sx0[d]);
-            } else {
-              const float diff = __fsub_rn(pr, x);
-              if (st.kind == 0) f = diff;
-              else if (st.kind == 1) f = __fdiv_rn(diff, st.end_div);
-              else {
-                f = __fdiv_rn(__fmul_rn(st.a, diff), st.den);
-                if (heavy) f = __fadd_rn(f, gg[d]);
-              }
-            }
-            if (row < P.N && !(fabsf(f) <= 3.0e38f)) atomicAdd(P.counters, 1ull);
-            if (P.mode == 0) {
-              if (row < P.N) out_set[row * 2 + d] = f;
-            } else {
-              const int iv = ev >> 2, sg = ev & 3;
-              const float dt = P.mode == 2 ? P.tabs[gs].dt[iv] : rk.dt[iv], y = sy[d];
-              float xn;
-              if (sg == 0) {
-                sk1[d] = f;
-                xn = __fadd_rn(y, __fmul_rn(__fmul_rn(dt, f), third));
-              } else if (sg == 1) {
-                sk2[d] = f;
-                xn = __fadd_rn(y, __fmul_rn(dt, __fsub_rn(f, __fmul_rn(sk1[d], third))));
-              } else if (sg == 2) {
-                sk3[d] = f;
-                xn = __fadd_rn(y, __fmul_rn(dt, __fadd_rn(__fsub_rn(sk1[d], sk2[d]), f)));
-              } else {
-                const float sum = __fadd_rn(__fadd_rn(sk1[d], __fmul_rn(3.0f, __fadd_rn(sk2[d], sk3[d]))), f);
-                xn = __fadd_rn(y, __fmul_rn(__fmul_rn(sum, dt), 0.125f));
-                sy[d] = xn;
-                if (P.traj != nullptr && row < P.N) P.traj[((size_t)(iv + 1) * P.N + row) * 2 + d] = xn;
-                if (ev == n_eval - 1 && row < P.N) out_set[row * 2 + d] = xn;
-              }
-              sxs[2 * myp + d] = xn;
-            }
-          }
-        }
-        ebar();
+        ebar576();   // the integrator warps have written the next stage's input to sxs
         if (stamp) g_tc16_stamps[12] = clock64();
       }
     }

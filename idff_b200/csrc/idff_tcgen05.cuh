@@ -68,6 +68,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void ebar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // epilogue warps only
+__device__ __forceinline__ void ebar576() { asm volatile("bar.sync 1, 576;" ::: "memory"); }   // epilogue + integrator warps (k_tc16)
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (8-row groups 1024 B apart)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -90,12 +91,36 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t da, uint64_t d
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// v0, v1 -> packed fp16 pairs: h2 = {lo half: hi(v0), hi half: hi(v1)}, l2 likewise for the scaled remainders
+// packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2: two IEEE fp32 operations per instruction on a 64-bit register pair)
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// v0, v1 -> packed fp16 pairs: h2 = {lo half: hi(v0), hi half: hi(v1)}, l2 likewise for the scaled remainders.
+// The remainder (v - hi) * 2^11 of both values is one FADD2 + one FMUL2 (both exact or correctly rounded like the scalar ops).
 __device__ __forceinline__ void split2(float v0, float v1, uint32_t& h2, uint32_t& l2) {
-  float f0, f1;
+  float f0, f1, d0, d1;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(v1), "f"(v0));
   asm("{\n.reg .b16 a, b;\nmov.b32 {a, b}, %2;\ncvt.f32.f16 %0, a;\ncvt.f32.f16 %1, b;\n}\n" : "=f"(f0), "=f"(f1) : "r"(h2));
-  const float d0 = __fmul_rn(__fsub_rn(v0, f0), LO_SCALE), d1 = __fmul_rn(__fsub_rn(v1, f1), LO_SCALE);
+  upk2(mul2(sub2(pk2(v0, v1), pk2(f0, f1)), pk2(LO_SCALE, LO_SCALE)), d0, d1);
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(l2) : "f"(d1), "f"(d0));
 }
 // tcgen05.ld/st.16x128b.x4: 16 TMEM lanes x 16 columns; thread T: register 2r + h <-> lane T/4 + 8h, column 4r + T%4

@@ -111,7 +111,7 @@ def test_batched_sweep_equals_per_field_solves(cuda_device):
             ts = torch.linspace(0, 1, nfe + 1)
             before = _lib.launch_count()
             got = sampler.sample_rk4_sweep(models, x0, ts)
-            assert _lib.launch_count() == before + 1                       # ONE launch for the whole sweep
+            assert _lib.launch_count() == before + 2                       # ONE sampler launch for the whole sweep + the AUTO route's range safety net
             assert got.shape == (len(tuples), n, 2)
             for k, m in enumerate(models):
                 assert torch.equal(got[k], sampler.sample_rk4(m, x0, ts)), (n, nfe, tuples[k])
@@ -289,7 +289,7 @@ def test_order3_sweep_batched_on_layered_engine(cuda_device):
         per_set_launches = _lib.launch_count() - before
         before = _lib.launch_count()
         got = sampler.sample_rk4_sweep(models, x0, ts)
-        assert _lib.launch_count() - before <= per_set_launches + 1          # the whole sweep costs one solve's launches (+ replicate)
+        assert _lib.launch_count() - before <= per_set_launches + 2          # the whole sweep costs one solve's launches (+ replicate + safety net)
         assert torch.equal(one, per[0])
         for k in range(len(tuples)):
             assert torch.equal(got[k], per[k]), (nfe, tuples[k])

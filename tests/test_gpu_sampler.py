@@ -229,23 +229,27 @@ def test_tensor16_full_size_properties_and_range_guard(cuda_device):
     assert torch.equal(sampler.sample_rk4(m, inplace, ts, out=inplace), safe)
 
 
-def _scaled_layers(name, s0, s12):
+def _scaled_layers(name, s0, s12, dtype=torch.float32):
     """the shipped network with layer 0 scaled by s0 and layers 1, 2 by s12: activations, jets and adjoints leave the fp16
     range for part of the batch while every fp32 quantity stays finite"""
     from conftest import golden_layers
     layers, _ = golden_layers(name)
     sc = [s0, s12, s12, 1.0]
-    return [(W * k, b * k) for (W, b), k in zip(layers, sc)]
+    return [((W * k).to(dtype), (b * k).to(dtype)) for (W, b), k in zip(layers, sc)]
 
 
 def test_auto_route_is_range_safe_vs_oracle(cuda_device):
     """IDFF_IMPL_AUTO never returns a value the reference would not.  A network whose activations overflow
-    fp16 (weights x 8..64, inputs up to 1e4): AUTO = 3xFP16 tensor kernel + fp32 re-solve of the overflowed particles
-    (idff_fixup.cu) against the oracle (the reference's nested-autograd field, Autograd_example_order2.py:44-76) at the
-    normal per-evaluation tolerance, for single evaluations, whole solves, trajectories and the batched gamma sweep."""
+    fp16 (layer-0 weights x 8, every 7th input x 1e4): AUTO = 3xFP16 tensor kernel + fp32 re-solve of the overflowed
+    particles (idff_fixup.cu) against the oracle (the reference's nested-autograd field, Autograd_example_order2.py:44-76)
+    under the normal per-evaluation contract (1e-5 max|f|, or the reference's own fp32<->fp64 gap where that is larger --
+    the x 8 network is stiffer than the shipped one), for single evaluations, whole solves, trajectories and the batched
+    gamma sweep."""
     import idff_oracle as O
+    from gpu_common import assert_field_vs_refs
     from idff_b200.weights import PackedWeights
-    layers = _scaled_layers("checkerboard", 64.0, 8.0)
+    layers = _scaled_layers("checkerboard", 8.0, 1.0)
+    layers64 = _scaled_layers("checkerboard", 8.0, 1.0, torch.float64)
     pw = PackedWeights([W.numpy() for W, _ in layers], [b.numpy() for _, b in layers], device=cuda_device)
     gen = torch.Generator().manual_seed(11)
     n = 4096 + 77
@@ -258,6 +262,7 @@ def test_auto_route_is_range_safe_vs_oracle(cuda_device):
     gen_m = fields.CustomNetModel(pw, 0.2, 0.2, 0.2)
     gen_m.impl = _lib.IDFF_IMPL_GENERIC
     orc = O.Field2D(layers, 0.2, (0.2, 0.2), 2)
+    orc64 = O.Field2D(layers64, 0.2, (0.2, 0.2), 2)
     for t in (0.0, 0.37, 5.0 / 6.0, 1.0):
         tt = torch.tensor(t)
         f_raw = raw(tt, xd)
@@ -268,17 +273,20 @@ def test_auto_route_is_range_safe_vs_oracle(cuda_device):
         assert torch.equal(f_auto[~bad], f_raw[~bad])                # clean particles: the tensor kernel's own result
         assert torch.equal(f_auto[bad], gen_m(tt, xd)[bad])          # overflowed ones: fp32 FMA arithmetic
         ref = orc(tt, x)
+        ref64 = orc64(tt.double(), x.double())
         assert torch.isfinite(ref).all()
-        # per-evaluation tolerance per particle group: a 1e4-scale particle must not hide the O(1) ones behind max|f|
+        # per-evaluation contract per particle group: a 1e4-scale particle must not hide the O(1) ones behind max|f|
         for grp in (bad.cpu(), ~bad.cpu()):
-            assert_field_close(f_auto.cpu()[grp].numpy(), ref[grp].numpy(), 2e-5, f"range-safe eval t={t}")
+            assert_field_vs_refs(f_auto.cpu()[grp].numpy(), ref[grp].numpy(), ref64[grp].numpy(), 1e-5, f"range-safe eval t={t}")
     assert _lib.weights_nonfinite(pw.handle)[1] > 0
-    # whole solves (in-range start points; the x64 / x8 network drives part of them out of the fp16 range on the way)
+    # whole solves: every 5th start point is out of the fp16 range from the first evaluation on
     x0 = (torch.randn(2048 + 5, 2, generator=gen) / 1.5)
+    x0[::5] *= 1.0e4
     x0d = x0.to(cuda_device)
     ts = torch.linspace(0, 1, 3)
     out_raw = sampler.sample_rk4(raw, x0d, ts)
     bad = ~torch.isfinite(out_raw).all(dim=1)
+    assert bad.any() and not bad.all()
     traj = sampler.odeint(auto, x0d, ts, method="rk4")
     out = sampler.sample_rk4(auto, x0d, ts)
     ref_traj = sampler.odeint(gen_m, x0d, ts, method="rk4")
