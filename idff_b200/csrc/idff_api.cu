@@ -44,6 +44,15 @@ int tensor16_sample_rk4_sweep(const idff_weights_t* w, const idff_field_params_t
                               const Stage* stages, const float* dts, int n_iv, float* d_out, int64_t N, void* stream);
 int tensor16_debug_stamps(long long* h_out, int n);
 
+// idff_sampler_tc16o3.cu: the fused three-jet kernel (order-3 field)
+bool tensor16o3_supports(const idff_weights_t* w, const idff_field_params_t* p);
+int tensor16o3_field_eval(const idff_weights_t* w, const idff_field_params_t* p, float t, const float* d_x, float* d_out,
+                          int64_t N, bool safe, void* stream);
+int tensor16o3_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, const float* d_x0, const Stage* stages,
+                          const float* dts, int n_iv, float* d_out_final, float* d_out_traj, int64_t N, bool safe, void* stream);
+int tensor16o3_sample_rk4_sweep(const idff_weights_t* w, const idff_field_params_t* params, int n_sets, const float* d_x0,
+                                const Stage* stages, const float* dts, int n_iv, float* d_out, int64_t N, bool safe, void* stream);
+
 // idff_sampler_wide.cu
 bool wide_supports(const idff_weights_t* w, const idff_field_params_t* p);
 bool wide_sweep_supports(const idff_weights_t* w, const idff_field_params_t* params, int n_sets, int64_t N);
@@ -156,6 +165,9 @@ extern "C" int idff_field_eval(const idff_weights_t* w, const idff_field_params_
   IDFF_CHECK_ARG(p->variant != IDFF_FIELD_CFM || t == 0.0f || d_x0, "idff_field_eval: the CFM field needs x0 (captured at t == 0) when t != 0");
   DeviceGuard g(w->device);
   if (p->impl == IDFF_IMPL_LAYERED) return wide_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
+  // order 3 (three jets) on the 3-256-256-256-2 network: the fused three-jet tcgen05 kernel
+  if ((p->impl == IDFF_IMPL_TENSOR16 || (p->impl == IDFF_IMPL_AUTO && N >= 4096)) && tensor16o3_supports(w, p))
+    return tensor16o3_field_eval(w, p, t, d_x, d_out, N, p->impl == IDFF_IMPL_AUTO, stream);
   if (p->impl == IDFF_IMPL_AUTO && w->v.w == 256 && N >= 2048 && !tensor16_supports(w, p)) {
     idff_field_params_t q = *p;   // order 3 at width 256: the layered 3xFP16 engine (see idff_sample_rk4)
     q.impl = IDFF_IMPL_LAYERED;
@@ -181,7 +193,7 @@ extern "C" int idff_field_eval(const idff_weights_t* w, const idff_field_params_
 static bool routes_to_wide(const idff_weights_t* w, const idff_field_params_t* p, int64_t N, idff_field_params_t* q) {
   *q = *p;
   if (p->impl == IDFF_IMPL_LAYERED) return wide_supports(w, p);
-  if (p->impl == IDFF_IMPL_TENSOR16 || (p->impl == IDFF_IMPL_AUTO && tensor16_supports(w, p))) return false;
+  if (p->impl == IDFF_IMPL_TENSOR16 || (p->impl == IDFF_IMPL_AUTO && (tensor16_supports(w, p) || tensor16o3_supports(w, p)))) return false;
   if (p->impl == IDFF_IMPL_AUTO && w->v.w == 256 && N >= 2048) {
     q->impl = IDFF_IMPL_LAYERED;
     if (wide_supports(w, q)) return true;
@@ -233,6 +245,8 @@ extern "C" int idff_sample_rk4(const idff_weights_t* w, const idff_field_params_
   }
   if (p->impl == IDFF_IMPL_LAYERED)
     return wide_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream);
+  if ((p->impl == IDFF_IMPL_TENSOR16 || p->impl == IDFF_IMPL_AUTO) && tensor16o3_supports(w, p))   // order 3: three jets
+    return tensor16o3_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, p->impl == IDFF_IMPL_AUTO, stream);
   if (p->impl == IDFF_IMPL_TENSOR16 || (p->impl == IDFF_IMPL_AUTO && tensor16_supports(w, p)))
     return tensor16_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream);
   if (p->impl == IDFF_IMPL_AUTO && w->v.w == 256 && N >= 2048 && !tensor16_supports(w, p)) {
@@ -283,21 +297,26 @@ extern "C" int idff_sample_rk4_sweep(const idff_weights_t* w, const idff_field_p
   for (int g = 0; g < n_sets && batched; ++g)
     batched = (params[g].impl == IDFF_IMPL_AUTO || params[g].impl == IDFF_IMPL_TENSOR16) && tensor16_supports(w, &params[g]) &&
               params[g].variant == params[0].variant && params[g].t_idx == params[0].t_idx;
-  // order 3 / wide networks: one batch on the layered engine when that engine would serve every set anyway
+  // every set needs three jets: one launch of the fused three-jet kernel
+  bool batched3 = !batched && n_iv >= 1 && n_iv <= kMaxSweepIntervals;
+  for (int g = 0; g < n_sets && batched3; ++g)
+    batched3 = (params[g].impl == IDFF_IMPL_AUTO || params[g].impl == IDFF_IMPL_TENSOR16) && tensor16o3_supports(w, &params[g]) &&
+               params[g].t_idx == params[0].t_idx;
+  // wide networks: one batch on the layered engine when that engine would serve every set anyway
   std::vector<idff_field_params_t> wp;
-  bool wide_batched = !batched && n_iv >= 1 && N % 128 == 0 && n_sets >= 2;
+  bool wide_batched = !batched && !batched3 && n_iv >= 1 && N % 128 == 0 && n_sets >= 2;
   if (wide_batched) {
     wp.resize(n_sets);
     for (int g = 0; g < n_sets && wide_batched; ++g) wide_batched = routes_to_wide(w, &params[g], N, &wp[g]);
     wide_batched = wide_batched && wide_sweep_supports(w, wp.data(), n_sets, N);
   }
-  if (!batched && !wide_batched) {
+  if (!batched && !batched3 && !wide_batched) {
     // Mixed sweep (the order-3 grid holds tuples with gamma3 == 0, which the fused tensor kernel serves, next to tuples that
     // need three jets): split the sets into classes that batch -- class 0: fused tensor kernel; class 1 + 2 nj + rev: layered
     // engine with that jet count -- solve every class of two or more sets as one batch into a staging buffer and scatter the
     // rows to their slots; the rest one call per set.
     std::vector<int> cls(n_sets, -1);
-    std::vector<std::vector<int>> members(8);
+    std::vector<std::vector<int>> members(9);
     if (n_iv >= 1 && n_iv <= kMaxSweepIntervals) {
       for (int g = 0; g < n_sets; ++g) {
         const idff_field_params_t& q = params[g];
@@ -305,6 +324,8 @@ extern "C" int idff_sample_rk4_sweep(const idff_weights_t* w, const idff_field_p
         if ((q.impl == IDFF_IMPL_AUTO || q.impl == IDFF_IMPL_TENSOR16) && tensor16_supports(w, &q) && q.variant == params[0].variant &&
             q.t_idx == params[0].t_idx) {
           cls[g] = 0;
+        } else if ((q.impl == IDFF_IMPL_AUTO || q.impl == IDFF_IMPL_TENSOR16) && tensor16o3_supports(w, &q) && q.t_idx == params[0].t_idx) {
+          cls[g] = 8;   // fused three-jet kernel
         } else if (N % 128 == 0 && q.variant == IDFF_FIELD_MOMENTUM && routes_to_wide(w, &q, N, &qq)) {
           int nj, rev;
           jets_needed(q, &nj, &rev);
@@ -313,7 +334,7 @@ extern "C" int idff_sample_rk4_sweep(const idff_weights_t* w, const idff_field_p
         if (cls[g] >= 0) members[cls[g]].push_back(g);
       }
     }
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < 9; ++c) {
       const std::vector<int>& mem = members[c];
       if (mem.size() < 2 || (int)mem.size() == n_sets) {   // (a class that is the whole sweep already failed to batch above)
         for (int g : mem) cls[g] = -1;
@@ -369,6 +390,11 @@ extern "C" int idff_sample_rk4_sweep(const idff_weights_t* w, const idff_field_p
       make_stage(params[g], tc, &s4[2]);
       make_stage(params[g], t1, &s4[3]);
     }
+  }
+  if (batched3) {
+    bool safe = false;
+    for (int g = 0; g < n_sets; ++g) safe = safe || params[g].impl == IDFF_IMPL_AUTO;
+    return tensor16o3_sample_rk4_sweep(w, params, n_sets, d_x0, st.data(), dts.data(), n_iv, d_out, N, safe, stream);
   }
   if (wide_batched) {
     int rc = wide_sample_rk4_sweep(w, wp.data(), n_sets, d_x0, st.data(), dts.data(), n_iv, d_out, N, stream);

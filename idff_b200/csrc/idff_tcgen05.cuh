@@ -108,6 +108,12 @@ __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t bc2(float v) { return pk2(v, v); }
 __device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
   uint64_t d;
   asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -121,6 +127,15 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t& h2, uint32_
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(v1), "f"(v0));
   asm("{\n.reg .b16 a, b;\nmov.b32 {a, b}, %2;\ncvt.f32.f16 %0, a;\ncvt.f32.f16 %1, b;\n}\n" : "=f"(f0), "=f"(f1) : "r"(h2));
   upk2(mul2(sub2(pk2(v0, v1), pk2(f0, f1)), pk2(LO_SCALE, LO_SCALE)), d0, d1);
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(l2) : "f"(d1), "f"(d0));
+}
+// the same on a packed pair
+__device__ __forceinline__ void split2p(uint64_t v, uint32_t& h2, uint32_t& l2) {
+  float v0, v1, f0, f1, d0, d1;
+  upk2(v, v0, v1);
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(v1), "f"(v0));
+  asm("{\n.reg .b16 a, b;\nmov.b32 {a, b}, %2;\ncvt.f32.f16 %0, a;\ncvt.f32.f16 %1, b;\n}\n" : "=f"(f0), "=f"(f1) : "r"(h2));
+  upk2(mul2(sub2(v, pk2(f0, f1)), bc2(LO_SCALE)), d0, d1);
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(l2) : "f"(d1), "f"(d0));
 }
 // tcgen05.ld/st.16x128b.x4: 16 TMEM lanes x 16 columns; thread T: register 2r + h <-> lane T/4 + 8h, column 4r + T%4
@@ -173,6 +188,41 @@ __device__ __forceinline__ void selu_jet_code(float z, float& a, float& s1, floa
   a = pos ? z * kSeluLambda : (e - 1.0f) * kSeluLA;
   s1 = pos ? kSeluLambda : t;
   code = pos ? -1.0f : t;
+}
+
+// SELU jets of a packed pair of pre-activations (the scalar formulas above, two lanes per FMUL2 / FADD2): a = s(z), s1 = s'(z),
+// E = every higher derivative.  MUFU.EX2, the min and the selects stay scalar.
+__device__ __forceinline__ void selu_jet2(uint64_t z, uint64_t& a, uint64_t& s1, uint64_t& E) {
+  float z0, z1, g0, g1, e0, e1, t0, t1, n0, n1, p0, p1;
+  upk2(z, z0, z1);
+  upk2(mul2(pk2(fminf(z0, 0.0f), fminf(z1, 0.0f)), bc2(1.4426950408889634f)), g0, g1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(g0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(g1));
+  const uint64_t e = pk2(e0, e1);
+  upk2(mul2(e, bc2(kSeluLA)), t0, t1);
+  upk2(mul2(add2(e, bc2(-1.0f)), bc2(kSeluLA)), n0, n1);
+  upk2(mul2(z, bc2(kSeluLambda)), p0, p1);
+  const bool q0 = !(z0 <= 0.0f), q1 = !(z1 <= 0.0f);   // keeps NaN on the linear branch
+  a = pk2(q0 ? p0 : n0, q1 ? p1 : n1);
+  s1 = pk2(q0 ? kSeluLambda : t0, q1 ? kSeluLambda : t1);
+  E = pk2(q0 ? 0.0f : t0, q1 ? 0.0f : t1);
+}
+// same, with the derivative code kept in the stash: LA * exp(z) (= s1 = E) on the exp branch, -1 on the linear one
+__device__ __forceinline__ void selu_jet_code2(uint64_t z, uint64_t& a, uint64_t& s1, float& code0, float& code1) {
+  float z0, z1, g0, g1, e0, e1, t0, t1, n0, n1, p0, p1;
+  upk2(z, z0, z1);
+  upk2(mul2(pk2(fminf(z0, 0.0f), fminf(z1, 0.0f)), bc2(1.4426950408889634f)), g0, g1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(g0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(g1));
+  const uint64_t e = pk2(e0, e1);
+  upk2(mul2(e, bc2(kSeluLA)), t0, t1);
+  upk2(mul2(add2(e, bc2(-1.0f)), bc2(kSeluLA)), n0, n1);
+  upk2(mul2(z, bc2(kSeluLambda)), p0, p1);
+  const bool q0 = !(z0 <= 0.0f), q1 = !(z1 <= 0.0f);
+  a = pk2(q0 ? p0 : n0, q1 ? p1 : n1);
+  s1 = pk2(q0 ? kSeluLambda : t0, q1 ? kSeluLambda : t1);
+  code0 = q0 ? -1.0f : t0;
+  code1 = q1 ? -1.0f : t1;
 }
 
 }  // namespace tcg

@@ -6,6 +6,7 @@
 `sample_location_and_conditional_flow` keeps the reference's draw order (t from torch.rand on the CPU generator,
 then eps = randn_like(x0)) and produces xt and ut in ONE kernel launch, bit-exact with the reference's fp32
 operation order.  Inputs must be CUDA float32 tensors; there is no CPU path."""
+import ctypes as C
 import math
 from typing import Union
 
@@ -45,6 +46,33 @@ def _path_sample(x0, x1, t, eps, sigma, sigma_mode, want_ut=True, idx0=None, idx
                                            _lib.ptr(xt), _lib.ptr(ut), B, D, _lib.stream_of(x0)),
                "idff_path_sample")
     return xt, ut
+
+
+def _path_sample_philox(x0, x1, t, sigma, sigma_mode, want_eps):
+    """xt, ut[, eps] with eps = torch.randn_like(x0) drawn inside the kernel from the torch CUDA generator's Philox stream:
+    the same numbers, element for element, and the generator ends where randn_like would have left it.  Returns None when
+    the fused draw does not apply (stream capture, > 2^31 elements, non-contiguous / non-fp32 inputs)."""
+    if not (x0.is_cuda and x1.is_cuda and t.is_cuda and x0.dtype == torch.float32 and x1.dtype == torch.float32
+            and t.dtype == torch.float32 and x0.is_contiguous() and x1.is_contiguous() and t.is_contiguous()):
+        return None
+    n = x0.numel()
+    if n == 0 or n >= 2 ** 31 or x0.shape != x1.shape or torch.cuda.is_current_stream_capturing():
+        return None
+    gen = torch.cuda.default_generators[x0.device.index if x0.device.index is not None else torch.cuda.current_device()]
+    st = gen.get_state()                              # ... | seed (8 bytes LE) | philox offset (8 bytes LE)
+    raw = bytes(st[-16:].tolist())
+    seed, offset = int.from_bytes(raw[:8], "little"), int.from_bytes(raw[8:], "little")
+    B, D = x0.shape[0], n // x0.shape[0]
+    xt, ut = torch.empty_like(x0), torch.empty_like(x0)
+    eps = torch.empty_like(x0) if want_eps else None
+    inc = C.c_uint64(0)
+    _lib.check(_lib.lib().idff_path_sample_philox(_lib.ptr(x0), _lib.ptr(x1), _lib.ptr(t), seed, offset, float(sigma),
+                                                  int(sigma_mode), _lib.ptr(xt), _lib.ptr(ut), _lib.ptr(eps), B, D,
+                                                  C.byref(inc), _lib.stream_of(x0)), "idff_path_sample_philox")
+    st = st.clone()
+    st[-8:] = torch.tensor(list((offset + inc.value).to_bytes(8, "little")), dtype=torch.uint8)
+    gen.set_state(st)                                 # book the draw on the generator, as ATen's randn kernel does
+    return xt, ut, eps
 
 
 class ConditionalFlowMatcher:
@@ -94,6 +122,14 @@ class ConditionalFlowMatcher:
         if t is None:
             t = torch.rand(x0.shape[0]).type_as(x0)          # CPU generator first (reference :184)
         assert len(t) == x0.shape[0], "t has to have batch size dimension"
+        if (self._fusable() and "sample_noise_like" not in self.__dict__
+                and type(self).sample_noise_like is ConditionalFlowMatcher.sample_noise_like):
+            # noise drawn inside the path-sample kernel: the very numbers randn_like(x0) would produce (same Philox stream,
+            # same element layout), without the round trip of eps through HBM
+            got = _path_sample_philox(x0, x1, t, self.sigma, self._kernel_sigma_mode(), return_noise)
+            if got is not None:
+                xt, ut, eps = got
+                return (t, xt, ut, eps) if return_noise else (t, xt, ut)
         eps = self.sample_noise_like(x0)                     # then the noise (reference :187)
         if self._fusable():
             xt, ut = _path_sample(x0, x1, t, eps, self.sigma, self._kernel_sigma_mode())

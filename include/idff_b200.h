@@ -47,7 +47,8 @@ extern "C" {
 #define IDFF_IMPL_FUSED 2   /* persistent warp-tiled kernel, weights streamed by TMA bulk copies */
 #define IDFF_IMPL_TENSOR 3  /* tcgen05: fused 3xTF32 kernel (width 256, dim 2, order <= 2) or the layered 3xFP16 engine (width >= 512) */
 #define IDFF_IMPL_LAYERED 4 /* force the layer-by-layer tcgen05 3xFP16 engine (width >= 256, dim 2, orders 1..3) */
-#define IDFF_IMPL_TENSOR16 5 /* the raw tcgen05 3xFP16 fused kernel (width 256, dim 2, order <= 2), WITHOUT the safety net:
+#define IDFF_IMPL_TENSOR16 5 /* the raw tcgen05 3xFP16 fused kernels (width 256, dim 2: k_tc16 for up to two jets -- orders 1, 2, and
+                                order 3 with gamma3 == 0 -- and the three-jet k_tc16o3 for order 3), WITHOUT the safety net:
                                 values beyond the fp16 range (|activation|, |jet|, |adjoint| > 65504) make that particle's
                                 output NaN (counted by idff_weights_nonfinite()).  AUTO = this kernel + the safety net */
 
@@ -144,6 +145,19 @@ int idff_sample_sde(const idff_weights_t* w, const idff_field_params_t* p, const
 int idff_path_sample(const float* d_x0, const float* d_x1, const float* d_t, const float* d_eps,
                      const int64_t* d_idx0, const int64_t* d_idx1, float sigma, int32_t sigma_mode, float* d_xt,
                      float* d_ut, int64_t B, int64_t D, void* stream);
+
+/* The same with eps = torch.randn_like(x0) (conditional_flow_matching.py:150-151,187) drawn INSIDE the kernel: Philox4x32-10
+ * in ATen's element layout (distribution_elementwise_grid_stride_kernel: block 256, grid = min(SMs * maxThreadsPerSM / 256,
+ * ceil(B D / 256)), thread idx = subsequence idx, curand_normal4 per iteration, element idx + S (4 j + ii) gets component ii),
+ * so for the torch CUDA generator's current (seed, philox_offset) every element receives exactly the number randn_like would
+ * have written -- eps never goes through HBM (36 instead of 44 B per row at D = 2) unless d_eps_out (optional [B][D]) asks for
+ * it.  *h_offset_increment (optional) = what the caller must add to the generator's offset afterwards, as ATen would have
+ * (idff_philox_plan returns it, and the grid, without launching).  B D < 2^31 (beyond that ATen splits the tensor into several
+ * RNG launches: IDFF_EUNSUPPORTED); no index gather (the _dynamic matcher re-pairs first and injects eps). */
+int idff_philox_plan(int64_t numel, int32_t device, int32_t* h_grid, uint64_t* h_offset_increment);
+int idff_path_sample_philox(const float* d_x0, const float* d_x1, const float* d_t, uint64_t seed, uint64_t philox_offset,
+                            float sigma, int32_t sigma_mode, float* d_xt, float* d_ut, float* d_eps_out, int64_t B, int64_t D,
+                            uint64_t* h_offset_increment, void* stream);
 
 /* ---- a11: compute_lambda, conditional_flow_matching.py:195-211 (dynamic = 0: 2 sigma_t^2/(sigma^2+1e-8))
  * and conditional_flow_matching_dynamic.py:198-214 (dynamic = 1: 2 sigma_t/(sigma^2+1e-8)). */

@@ -269,16 +269,20 @@ def test_md_compute_metrics_matches_reference_golden(cuda_device):
         md.compute_metrics(torch.tensor(g["y_hat"]), torch.tensor(g["dataset"]))
 
 
-def test_order3_sweep_batched_on_layered_engine(cuda_device):
-    """The order-3 gamma sweep (Autograd_example_order3.py:288-314): sets with gamma3 != 0 are not served by the fused tensor
-    kernel; at N >= 2048 (multiple of 128) they are solved as ONE batch of n_sets * N particles on the layered tcgen05 engine
-    (per-set coefficients looked up by particle row) -- bit-identical to one idff_sample_rk4 call per tuple, far fewer launches."""
+@pytest.mark.parametrize("impl", [0, 4])
+def test_order3_sweep_batched(cuda_device, impl):
+    """The order-3 gamma sweep (Autograd_example_order3.py:288-314).  Default route (impl 0): sets with gamma3 != 0 go out as
+    ONE launch of the fused three-jet tcgen05 kernel (k_tc16o3), per-set stage tables in global memory.  impl 4 (layered
+    engine, the route of wide networks): at N >= 2048 (multiple of 128) they are solved as ONE batch of n_sets * N particles,
+    per-set coefficients looked up by particle row.  Either way bit-identical to one idff_sample_rk4 call per tuple."""
     import time
 
     from idff_b200 import _lib, fields, sampler
     pw = packed("checkerboard", cuda_device)
     tuples = [(0.2, 0.2, 0.2), (0.0, 0.0, 0.1), (1.0, 2.0, 0.5), (0.3, 0.1, -0.2), (0.2, 0.0, 0.7)]
     models = [fields.CustomNetModelOrder3(pw, 0.2, *g) for g in tuples]
+    for m in models:
+        m.impl = impl
     n = 2048
     x0 = torch.randn(n, 2, device=cuda_device, generator=torch.Generator(device=cuda_device).manual_seed(5)) / 1.5
     for nfe in (2, 3):
@@ -297,6 +301,8 @@ def test_order3_sweep_batched_on_layered_engine(cuda_device):
     # are split into classes, each class solved as one batch and scattered to its slots -- still bit-identical per tuple
     mixed = [(0.2, 0.2, 0.0), (0.2, 0.2, 0.2), (0.5, 0.0, 0.0), (0.0, 0.0, 0.1), (1.0, 2.0, 0.0), (0.3, 0.1, -0.2), (0.5, 0.0, 0.3)]
     mm = [fields.CustomNetModelOrder3(pw, 0.2, *g) for g in mixed]
+    for m in mm:
+        m.impl = impl
     ts = torch.linspace(0, 1, 3)
     per = [sampler.sample_rk4(m, x0, ts) for m in mm]
     before = _lib.launch_count()
@@ -312,6 +318,8 @@ def test_order3_sweep_batched_on_layered_engine(cuda_device):
     # timing, reported: 5 x 5 x 5 tuples (the reference sweeps 10^3), 2048 particles, nfe 2
     g5 = [0.0, 0.2, 0.5, 1.0, 2.0]
     ms = [fields.CustomNetModelOrder3(pw, 0.2, a, b, c if c else 0.05) for a in g5 for b in g5 for c in g5]
+    for m in ms:
+        m.impl = impl
     ts = torch.linspace(0, 1, 3)
     sampler.sample_rk4_sweep(ms, x0, ts)
     torch.cuda.synchronize()

@@ -33,7 +33,7 @@ def test_field2d_order2_order3(cuda_device, which, impl):
     for gi, gam in enumerate(GAMMAS3):
         m = fields.CustomNetModelOrder3(pw, 0.2, *gam)
         m.impl = impl
-        if impl in (_lib.IDFF_IMPL_TENSOR, _lib.IDFF_IMPL_TENSOR16) and gam[2] != 0:      # the tcgen05 kernel carries two jets: no silent fallback
+        if impl == _lib.IDFF_IMPL_TENSOR and gam[2] != 0:      # the 3xTF32 tcgen05 kernel carries two jets: no silent fallback
             with pytest.raises(_lib.IdffError):
                 m(torch.tensor(0.5), x)
             continue

@@ -68,7 +68,7 @@ def test_rk4_order3_and_cfm_vs_golden(cuda_device, impl):
             key = f"checkerboard_o3_nfe{nfe}_g{gi}"
             m = fields.CustomNetModelOrder3(pw, 0.2, *gam)
             m.impl = impl
-            if impl in (_lib.IDFF_IMPL_TENSOR, _lib.IDFF_IMPL_TENSOR16) and gam[2] != 0:
+            if impl == _lib.IDFF_IMPL_TENSOR and gam[2] != 0:      # the 3xTF32 fused kernel holds two jets; 3xFP16 has a three-jet kernel
                 with pytest.raises(_lib.IdffError):
                     sampler.sample_rk4(m, x0, torch.linspace(0, 1, nfe + 1))
                 continue
@@ -322,3 +322,52 @@ def test_cfm_solve_longer_than_one_launch(cuda_device):
         assert drift_report(traj[100].cpu().numpy(), ref[100].numpy())["max"] <= 2e-4, impl
         with pytest.raises(_lib.IdffError):
             sampler.sample_rk4(c, x0.to(cuda_device), torch.linspace(0.25, 1, 4))
+
+
+def test_order3_fused_three_jet_kernel(cuda_device):
+    """The order-3 field (Autograd_example_order3.py:34-77) on its fused three-jet tcgen05 kernel (k_tc16o3, the default
+    route for gamma3 != 0): independent particles (any slice reproduces the whole bit for bit, ragged tile counts included),
+    trajectories end where sample_rk4 ends, agreement with the fp32 FMA kernels inside the accumulated-drift contract, and the
+    fp16 range guard + fp32 safety net of the default route."""
+    from idff_b200.weights import PackedWeights
+    pw = PackedWeights.from_npz(load_golden("weights_checkerboard"), device=cuda_device)   # own handle: fresh counters
+    m = fields.CustomNetModelOrder3(pw, 0.2, 0.2, 0.2, 0.2)                                # AUTO -> k_tc16o3
+    n = (1 << 18) + 17
+    x0 = torch.randn(n, 2, device=cuda_device, generator=torch.Generator(device=cuda_device).manual_seed(21)) / 1.5
+    for nfe in (2, 5):
+        ts = torch.linspace(0, 1, nfe + 1)
+        before = _lib.launch_count()
+        whole = sampler.sample_rk4(m, x0, ts)
+        assert _lib.launch_count() - before == 2                       # ONE sampler launch + the safety net's scan
+        assert torch.isfinite(whole).all()
+        for lo, hi in ((0, 1), (0, 31), (5, 5 + 33), (1000, 1000 + 4737), (n - 9473, n)):
+            assert torch.equal(sampler.sample_rk4(m, x0[lo:hi].contiguous(), ts), whole[lo:hi])
+        traj = sampler.odeint(m, x0[:5000], ts, method="rk4")
+        assert torch.equal(traj[-1], whole[:5000]) and torch.equal(traj[0], x0[:5000])
+        for other in (_lib.IDFF_IMPL_GENERIC, _lib.IDFF_IMPL_FUSED, _lib.IDFF_IMPL_LAYERED):
+            mo = fields.CustomNetModelOrder3(pw, 0.2, 0.2, 0.2, 0.2)
+            mo.impl = other
+            r = drift_report(whole[:8192].cpu().numpy(), sampler.sample_rk4(mo, x0[:8192], ts).cpu().numpy())
+            assert r["median"] <= 5e-5 and r["p999"] <= 0.05, (nfe, other, r)   # order-3 kink outliers: SURVEY section 8(d)
+    assert _lib.weights_nonfinite(pw.handle) == (0, 0)
+    # single evaluations through forward(t, x): interior and boundary times
+    mg = fields.CustomNetModelOrder3(pw, 0.2, 0.2, 0.2, 0.2)
+    mg.impl = _lib.IDFF_IMPL_GENERIC
+    for t in (0.0, 0.37, 1.0):
+        a, b = m(torch.tensor(t), x0[:8192]), mg(torch.tensor(t), x0[:8192])
+        assert_field_close(a.cpu().numpy(), b.cpu().numpy(), 1e-5, f"order-3 eval t={t}")
+    # range guard
+    ts = torch.linspace(0, 1, 3)
+    bad = x0[:100].clone()
+    bad[7] = 3.0e6
+    raw = fields.CustomNetModelOrder3(pw, 0.2, 0.2, 0.2, 0.2)
+    raw.impl = _lib.IDFF_IMPL_TENSOR16
+    out = sampler.sample_rk4(raw, bad, ts)
+    assert not torch.isfinite(out[7]).all()
+    keep = torch.ones(100, dtype=torch.bool, device=cuda_device)
+    keep[7] = False
+    good = sampler.sample_rk4(m, x0[:100].contiguous(), ts)
+    assert torch.equal(out[keep], good[keep])
+    safe = sampler.sample_rk4(m, bad, ts)
+    assert torch.equal(safe[keep], good[keep]) and torch.equal(safe[7], sampler.sample_rk4(mg, bad, ts)[7])
+    assert _lib.weights_nonfinite(pw.handle)[1] == 1

@@ -376,3 +376,39 @@ def test_aux_matchers_vs_reference_golden(cuda_device):
     np.testing.assert_allclose(FM.compute_lambda(t).cpu().numpy(),
                                (2 * (0.15 * (1 - t)) ** 2 / (0.3 ** 2 + 1e-8)).cpu().numpy(), rtol=1e-6)
     assert cfm.ExactOptimalTransportConditionalFlowMatcher(0.5)._kernel_sigma_mode() == 1 and cfm.ConditionalFlowMatcher(0.5)._fusable()
+
+
+@pytest.mark.parametrize("shape", [(256, 2), (10, 46), (1, 1), (4097, 3), (1 << 24, 2)])
+def test_in_kernel_noise_is_randn_like_bit_for_bit(cuda_device, shape):
+    """the fused path sample draws eps inside the kernel (Philox4x32-10 in ATen's element layout) -- the very
+    tensor torch.randn_like(x0) returns for the same seed, the generator left where randn_like leaves it, xt / ut bit-exact
+    against the reference's expression on that noise (torchcfm/conditional_flow_matching.py:184-189)."""
+    B, D = shape
+    g = torch.Generator(device=cuda_device).manual_seed(B + D)
+    x0 = torch.randn(B, D, device=cuda_device, generator=g)
+    x1 = torch.randn(B, D, device=cuda_device, generator=g)
+    for sigma, FMc in ((0.5, cfm.ExactOptimalTransportConditionalFlowMatcher), (0.3, cfm.ConditionalFlowMatcher)):
+        FM = FMc(sigma=sigma)
+        torch.manual_seed(1234 + B)
+        pre = torch.randn(7, device=cuda_device)                      # the generator is mid-stream, not at offset 0
+        before = _lib.launch_count()
+        t, xt, ut, eps = FM.sample_location_and_conditional_flow(x0, x1, return_noise=True)
+        assert _lib.launch_count() == before + 1                      # ONE kernel: noise, xt and ut
+        after = torch.randn(5, device=cuda_device)                    # what the next torch draw sees
+        torch.manual_seed(1234 + B)
+        assert torch.equal(torch.randn(7, device=cuda_device), pre)
+        t_ref = torch.rand(B).to(cuda_device)
+        eps_ref = torch.randn_like(x0)
+        assert torch.equal(t, t_ref)
+        assert torch.equal(eps, eps_ref), (shape, (eps != eps_ref).sum().item())
+        assert torch.equal(torch.randn(5, device=cuda_device), after)  # same generator offset afterwards
+        xt_ref, ut_ref = cfm._path_sample(x0, x1, t, eps_ref, sigma, FM._kernel_sigma_mode())   # the injected-eps kernel (bit-exact
+        assert torch.equal(xt, xt_ref) and torch.equal(ut, ut_ref)                               # vs the oracle: tests above)
+        # without return_noise the same xt comes back and eps never exists
+        torch.manual_seed(1234 + B)
+        torch.randn(7, device=cuda_device)
+        t2, xt2, ut2 = FM.sample_location_and_conditional_flow(x0, x1)
+        assert torch.equal(t2, t) and torch.equal(xt2, xt) and torch.equal(ut2, ut)
+    if B <= 4097:
+        xr, ur = O.path_sample(x0.cpu(), x1.cpu(), t.cpu(), eps.cpu(), 0.3, False, ieee_sqrt=True)
+        assert torch.equal(xt.cpu(), xr) and torch.equal(ut.cpu(), ur)
