@@ -355,6 +355,16 @@ def aux_measurements(dev, pw, model, peaks):
     by = (5 * D + 1) * 4 * B
     aux["path_sample"] = {"rows_per_s": B / s, "GBps": by / s / 1e9, "frac_hbm": by / s / 1e9 / peaks["hbm_gbs"],
                           "shape": [B, D], "bound": "hbm", "bytes_per_row": (5 * D + 1) * 4}
+    # the same with eps drawn inside the kernel (Philox in ATen's layout, bit-exact with randn_like): eps never crosses HBM
+    FMp = cfm.ExactOptimalTransportConditionalFlowMatcher(sigma=0.2)
+    s = timeit(lambda: FMp.sample_location_and_conditional_flow(x0, x1, t=t))
+    by = (4 * D + 1) * 4 * B
+    s_two = timeit(lambda: cfm._path_sample(x0, x1, t, torch.randn_like(x0), 0.2, 1))
+    aux["path_sample_in_kernel_noise"] = {"rows_per_s": B / s, "GBps": by / s / 1e9, "frac_hbm": by / s / 1e9 / peaks["hbm_gbs"],
+                                          "shape": [B, D], "bound": "hbm", "bytes_per_row": (4 * D + 1) * 4,
+                                          "randn_like_then_path_sample_rows_per_s": B / s_two,
+                                          "note": "one launch: Philox4x32-10 noise + xt + ut (idff_path_sample_philox) vs the "
+                                                  "reference's two steps (ATen randn_like kernel, then the path sample)"}
     vt = torch.randn(B, D, device=dev, generator=g)
     s = timeit(lambda: losses._run(0, vt, x1, None, None, t, 0.0, True))
     by = (3 * D + 1) * 4 * B
@@ -392,6 +402,9 @@ def aux_measurements(dev, pw, model, peaks):
             ts = torch.linspace(0, 1, nfe + 1)
             s = timeit(lambda: sampler.sample_rk4(m2, xs, ts), reps=2, warm=1)
             sweep[str(nfe)] = xs.shape[0] * 4 * nfe / s
+            # a longer grid has a larger share of interior evaluations (4 MLP passes) against boundary ones (1 pass): fewer
+            # particle-steps/s at the same -- or higher -- arithmetic rate
+            sweep[f"{nfe}_algorithmic_tflops"] = xs.shape[0] * flops_per_particle_solve(nfe) / s / 1e12
         aux[f"sampler_{name}_nfe_sweep_particle_steps_per_s"] = sweep
     # BASELINE configs[1]: "NFE 2-10, 1M-64M particles on 1 B200" -- the default sampler over particle counts (nfe = 2)
     try:
@@ -601,12 +614,13 @@ def aux_measurements(dev, pw, model, peaks):
             aux[f"c3_order3_w{wide}_layered_tcgen05"] = {"particle_steps_per_s": xw.shape[0] * 8 / s,
                                                  "algorithmic_tflops": xw.shape[0] * 2.0 * F * (6 * 6 + 2) / s / 1e12,
                                                  "particles": xw.shape[0], "nfe": 2}
-        # C2 order 3 at w = 256: FFMA2 kernel vs the layered tcgen05 engine (AUTO picks the latter for large batches)
-        for name, impl in (("ffma2", 2), ("layered_tcgen05", 4)):
+        # C2 order 3 at w = 256: the fused three-jet tcgen05 kernel (AUTO) vs the layered tcgen05 engine vs the FFMA2 kernel
+        for name, impl in (("fused_three_jet_tcgen05", 0), ("ffma2", 2), ("layered_tcgen05", 4)):
             m3 = fields.CustomNetModelOrder3(pw, SIGMA, 0.2, 0.2, 0.2)
             m3.impl = impl
             s = timeit(lambda: sampler.sample_rk4(m3, xs, torch.linspace(0, 1, 3)), reps=2, warm=1)
-            aux[f"order3_w256_{name}"] = {"particle_steps_per_s": xs.shape[0] * 8 / s}
+            aux[f"order3_w256_{name}"] = {"particle_steps_per_s": xs.shape[0] * 8 / s, "particles": xs.shape[0], "nfe": 2,
+                                          "algorithmic_tflops": xs.shape[0] * flops_per_particle_solve(2, 3) / s / 1e12}
         # C4: PolyALA SDE_cal (47-128-128-128-46, folded embedding), srk, ts = linspace(0,1,3), dt = 0.3
         pwm = PackedWeights.from_npz(os.path.join(GOLDEN, "weights_polyala.npz"), device=dev)
         sde = fields.SDE_cal(pwm, input_dim=46, sigma=0.5, init_ind=3, max_length=200, dt=0.3, gamma1=0.2, gamma2=1.25)

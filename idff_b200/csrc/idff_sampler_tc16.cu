@@ -428,25 +428,22 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
       fence_proxy_async();
       mbar_arrive(&b_ready[mt]);
     };
-    // A thread's 16 values of one jet are 8 packed pairs: pair i = 4*ld + r holds units (2*ld, 2*ld + 1) of its 4 consecutive
-    // units for particle r of its 4 -- the order the accumulators arrive in (register 2r + h <-> lane g + 8h, column 4r + c4) --
-    // so the jet / adjoint algebra runs on FADD2 / FMUL2 / FFMA2.  Per-unit constants: pair ld of a float4.
-    // z = main + 2^-11 * corr, jet j
-    auto load_acc = [&](int j, uint64_t (&z)[8]) {
+    // z = main + 2^-11 * corr, jet j, element e = 8*ld + 2*r + h
+    auto load_acc = [&](int j, float (&z)[HP]) {
       uint32_t m[HP], c[HP];
       tmem_ld8(lane_base + j * NP, m);
       tmem_ld8(lane_base + (16u << 16) + j * NP, m + 8);
       tmem_ld8(lane_base + COL_CORR + j * NP, c);
       tmem_ld8(lane_base + (16u << 16) + COL_CORR + j * NP, c + 8);
       tmem_wait_ld();
-      const uint64_t inv2 = bc2(LO_INV);
+      const uint64_t inv2 = pk2(LO_INV, LO_INV);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)   // the loaded registers are consecutive pairs already
-        z[i] = fma2(pk2(__uint_as_float(c[2 * i]), __uint_as_float(c[2 * i + 1])), inv2,
-                    pk2(__uint_as_float(m[2 * i]), __uint_as_float(m[2 * i + 1])));
+      for (int i = 0; i < HP; i += 2)   // FFMA2: the loaded registers are consecutive pairs already
+        upk2(fma2(pk2(__uint_as_float(c[i]), __uint_as_float(c[i + 1])), inv2, pk2(__uint_as_float(m[i]), __uint_as_float(m[i + 1]))),
+             z[i], z[i + 1]);
     };
     // boundary evaluations: jet 0 summed over the two accumulator sets [main 64 | corr 64] at columns 0 and 128
-    auto load_acc2 = [&](uint64_t (&z)[8]) {
+    auto load_acc2 = [&](float (&z)[HP]) {
       uint32_t m0[HP], c0[HP], m1[HP], c1[HP];
       tmem_ld8(lane_base, m0);
       tmem_ld8(lane_base + (16u << 16), m0 + 8);
@@ -457,21 +454,9 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
       tmem_ld8(lane_base + 192, c1);
       tmem_ld8(lane_base + (16u << 16) + 192, c1 + 8);
       tmem_wait_ld();
-      const uint64_t inv2 = bc2(LO_INV);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        z[i] = fma2(add2(pk2(__uint_as_float(c0[2 * i]), __uint_as_float(c0[2 * i + 1])),
-                         pk2(__uint_as_float(c1[2 * i]), __uint_as_float(c1[2 * i + 1]))),
-                    inv2,
-                    add2(pk2(__uint_as_float(m0[2 * i]), __uint_as_float(m0[2 * i + 1])),
-                         pk2(__uint_as_float(m1[2 * i]), __uint_as_float(m1[2 * i + 1]))));
-    };
-    // hi / lo' fp16 words of the 8 pairs: hw[2r + ld] = units (2 ld, 2 ld + 1) of particle r
-    auto pack_pairs = [&](const uint64_t (&v)[8], uint32_t (&hw)[8], uint32_t (&lw)[8]) {
-#pragma unroll
-      for (int ld = 0; ld < 2; ++ld)
-#pragma unroll
-        for (int r = 0; r < 4; ++r) split2p(v[4 * ld + r], hw[2 * r + ld], lw[2 * r + ld]);
+      for (int i = 0; i < HP; ++i)
+        z[i] = fmaf(__uint_as_float(c0[i]) + __uint_as_float(c1[i]), LO_INV, __uint_as_float(m0[i]) + __uint_as_float(m1[i]));
     };
     auto wait_acc = [&]() {
       mbar_wait(acc_full, aphase);
@@ -486,7 +471,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
       tc_fence_before();
       mbar_arrive(acc_free);
     };
-    // sum over the 8 threads that share the thread's particles: v[2r + d] -> lane g keeps v[g]
+    // sum over the thread's 4 units, then over the 8 threads that share its particles: v[2r + d] -> lane g keeps v[g]
     auto reduce_units = [&](float (&v)[8]) -> float {
 #pragma unroll
       for (int off = 16, cnt = 4; off >= 4; off >>= 1, cnt >>= 1) {
@@ -499,34 +484,6 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
         }
       }
       return v[0];
-    };
-    // the two lanes of the packed partial sums px[r] (first output) / py[r] (second) -> v[2r], v[2r + 1]
-    auto fold_pairs = [&](const uint64_t (&px)[4], const uint64_t (&py)[4], float (&v)[8]) {
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        float lo, hi;
-        upk2(px[r], lo, hi);
-        v[2 * r] = lo + hi;
-        upk2(py[r], lo, hi);
-        v[2 * r + 1] = lo + hi;
-      }
-    };
-    // layer 1 of the thread's 4 units x 4 particles: z1 = W0 [x; t] + b0 (K = 3, computed directly), per pair
-    auto layer1_pre = [&](int n0, float tcur, uint64_t (&z1)[8]) {
-      const float4 wx0 = __ldg(reinterpret_cast<const float4*>(P.net.wt0 + 0 * W + n0));
-      const float4 wx1 = __ldg(reinterpret_cast<const float4*>(P.net.wt0 + 1 * W + n0));
-      const float4 wtt = __ldg(reinterpret_cast<const float4*>(P.net.wt0 + 2 * W + n0));
-      const float4 bb0 = __ldg(reinterpret_cast<const float4*>(P.net.b0 + (size_t)P.tidx * W + n0));
-      const uint64_t t2 = bc2(tcur);
-      const uint64_t zb[2] = {fma2(pk2(wtt.x, wtt.y), t2, pk2(bb0.x, bb0.y)), fma2(pk2(wtt.z, wtt.w), t2, pk2(bb0.z, bb0.w))};
-      const uint64_t w0p[2] = {pk2(wx0.x, wx0.y), pk2(wx0.z, wx0.w)}, w1p[2] = {pk2(wx1.x, wx1.y), pk2(wx1.z, wx1.w)};
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const float2 xp = *reinterpret_cast<const float2*>(sxs + 2 * (p0 + 4 * r + c4));
-        const uint64_t xx = bc2(xp.x), xy = bc2(xp.y);
-#pragma unroll
-        for (int ld = 0; ld < 2; ++ld) z1[4 * ld + r] = fma2(w1p[ld], xy, fma2(w0p[ld], xx, zb[ld]));
-      }
     };
 
     mbar_arrive(acc_free);   // nothing to read out before the very first m-tile
@@ -543,27 +500,34 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
         constexpr bool stamp = false;
 #endif
         if (stamp) g_tc16_stamps[0] = clock64();
-        // ---- layer 1: a1 and, for interior evaluations, a1' = s'(z1) * (W0 d).
+        // ---- layer 1 (K = 3, computed directly): a1 and, for interior evaluations, a1' = s'(z1) * (W0 d).
         // Every MMA of the previous evaluation is complete (this thread waited for its last accumulators).
 #pragma unroll 1
         for (int mt = 0; mt < 2; ++mt) {
           const int n0 = mt * 128 + q * 32 + 4 * slot;
-          uint64_t v0[8], v1[8];
-          layer1_pre(n0, st.t, v0);
-          const float4 zz1 = __ldg(reinterpret_cast<const float4*>(P.net.zd1 + n0));
-          const uint64_t zz1p[2] = {pk2(zz1.x, zz1.y), pk2(zz1.z, zz1.w)};
+          float2 xp[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            uint64_t s1, E;
-            selu_jet2(v0[i], v0[i], s1, E);
-            v1[i] = mul2(s1, zz1p[i >> 2]);
+          for (int r = 0; r < 4; ++r) xp[r] = *reinterpret_cast<const float2*>(sxs + 2 * (p0 + 4 * r + c4));
+          const float4 wx0 = __ldg(reinterpret_cast<const float4*>(P.net.wt0 + 0 * W + n0));
+          const float4 wx1 = __ldg(reinterpret_cast<const float4*>(P.net.wt0 + 1 * W + n0));
+          const float4 wtt = __ldg(reinterpret_cast<const float4*>(P.net.wt0 + 2 * W + n0));
+          const float4 bb0 = __ldg(reinterpret_cast<const float4*>(P.net.b0 + (size_t)P.tidx * W + n0));
+          const float4 zz1 = __ldg(reinterpret_cast<const float4*>(P.net.zd1 + n0));
+          float v0[HP], v1[HP];
+#pragma unroll
+          for (int e = 0; e < HP; ++e) {
+            const int r = (e >> 1) & 3;
+            const float zb = fmaf(IDFF_UC(wtt, e), st.t, IDFF_UC(bb0, e));
+            float s1, E;
+            selu_jet(fmaf(IDFF_UC(wx1, e), xp[r].y, fmaf(IDFF_UC(wx0, e), xp[r].x, zb)), v0[e], s1, E);
+            v1[e] = s1 * IDFF_UC(zz1, e);
           }
           uint32_t sa[2], hw[8], lw[8];
           make_sa(mt, sa);
-          pack_pairs(v0, hw, lw);
+          pack_jet(v0, hw, lw);
           if (heavy) {
             store_jet<0>(sa, hw, lw);
-            pack_pairs(v1, hw, lw);
+            pack_jet(v1, hw, lw);
             store_jet<1>(sa, hw, lw);
           } else {
             store_jet<0, 4096>(sa, hw, lw);
@@ -577,7 +541,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
           const int n0 = mt * 128 + q * 32 + 4 * slot;
           wait_acc();
           if (stamp && mt == 0) g_tc16_stamps[2] = clock64();
-          uint64_t z[8], zd[8];
+          float z[HP], zd[HP];
           if (heavy) {
             load_acc(0, z);
             load_acc(1, zd);
@@ -586,41 +550,33 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
           }
           release_acc();
           const float4 bb1 = __ldg(reinterpret_cast<const float4*>(P.net.b1 + n0));
-          const uint64_t bb1p[2] = {pk2(bb1.x, bb1.y), pk2(bb1.z, bb1.w)};
           const uint32_t stash = lane_base + COL_STASH + mt * 128;
           uint32_t h0[8], l0[8], h1[8], l1[8];
           if (heavy) {   // stash z2' (raw) and the derivative code of z2
             uint32_t u[HP];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float lo, hi;
-              upk2(zd[i], lo, hi);
-              u[2 * i] = __float_as_uint(lo);
-              u[2 * i + 1] = __float_as_uint(hi);
-            }
+            for (int e = 0; e < HP; ++e) u[e] = __float_as_uint(zd[e]);
             tmem_st8(stash + NP, u);
             tmem_st8(stash + (16u << 16) + NP, u + 8);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              uint64_t s1;
-              float c0, c1;
-              selu_jet_code2(add2(z[i], bb1p[i >> 2]), z[i], s1, c0, c1);
-              u[2 * i] = __float_as_uint(c0);
-              u[2 * i + 1] = __float_as_uint(c1);
-              zd[i] = mul2(s1, zd[i]);
+            for (int e = 0; e < HP; ++e) {
+              float s1, code;
+              selu_jet_code(z[e] + IDFF_UC(bb1, e), z[e], s1, code);
+              u[e] = __float_as_uint(code);
+              zd[e] = s1 * zd[e];
             }
             tmem_st8(stash, u);
             tmem_st8(stash + (16u << 16), u + 8);
             tmem_wait_st();
-            pack_pairs(z, h0, l0);
-            pack_pairs(zd, h1, l1);
+            pack_jet(z, h0, l0);
+            pack_jet(zd, h1, l1);
           } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              uint64_t s1, E;
-              selu_jet2(add2(z[i], bb1p[i >> 2]), z[i], s1, E);
+            for (int e = 0; e < HP; ++e) {
+              float s1, E;
+              selu_jet(z[e] + IDFF_UC(bb1, e), z[e], s1, E);
             }
-            pack_pairs(z, h0, l0);
+            pack_jet(z, h0, l0);
           }
           if (mt == 0) wait_kfree();   // k-blocks 0-1 have been read by every MMA of this pass
           uint32_t sa[2];
@@ -642,7 +598,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
             const int n0 = mt * 128 + q * 32 + 4 * slot;
             wait_acc();
             if (stamp && mt == 0) g_tc16_stamps[4] = clock64();
-            uint64_t z[8], zd[8];
+            float z[HP], zd[HP];
             if (heavy) {
               load_acc(0, z);
               load_acc(1, zd);
@@ -654,33 +610,29 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
             const float4 uu3 = __ldg(reinterpret_cast<const float4*>(P.net.u3 + n0));
             const float4 w30 = __ldg(reinterpret_cast<const float4*>(P.net.w3 + 0 * W + n0));
             const float4 w31 = __ldg(reinterpret_cast<const float4*>(P.net.w3 + 1 * W + n0));
-            const uint64_t bb2p[2] = {pk2(bb2.x, bb2.y), pk2(bb2.z, bb2.w)};
-            const uint64_t w30p[2] = {pk2(w30.x, w30.y), pk2(w30.z, w30.w)}, w31p[2] = {pk2(w31.x, w31.y), pk2(w31.z, w31.w)};
-            // adjoint seeds of z3 and z3': A_i = c_i * (W3^T 1)
-            const uint64_t A0p[2] = {mul2(bc2(st.c[0]), pk2(uu3.x, uu3.y)), mul2(bc2(st.c[0]), pk2(uu3.z, uu3.w))};
-            const uint64_t A1p[2] = {mul2(bc2(st.c[1]), pk2(uu3.x, uu3.y)), mul2(bc2(st.c[1]), pk2(uu3.z, uu3.w))};
-            uint64_t px[4] = {0ull, 0ull, 0ull, 0ull}, py[4] = {0ull, 0ull, 0ull, 0ull};
+            float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int ld = 0; ld < 2; ++ld)       // fixed summation order: units (0, 1) then (2, 3) per lane, lanes added last
+            for (int ld = 0; ld < 2; ++ld)       // fixed summation order over the thread's units 0, 1, 2, 3
 #pragma unroll
-              for (int r = 0; r < 4; ++r) {
-                const int i = 4 * ld + r;
-                uint64_t a, s1, E;
-                selu_jet2(add2(z[i], bb2p[ld]), a, s1, E);
-                px[r] = fma2(a, w30p[ld], px[r]);
-                py[r] = fma2(a, w31p[ld], py[r]);
-                if (heavy) {   // adjoints of z3 and z3', in place
-                  z[i] = fma2(mul2(A1p[ld], E), zd[i], mul2(A0p[ld], s1));
-                  zd[i] = mul2(A1p[ld], s1);
+              for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                  const int e = 8 * ld + 2 * r + h;
+                  float a, s1, E;
+                  selu_jet(z[e] + IDFF_UC(bb2, e), a, s1, E);
+                  part[2 * r] += a * IDFF_UC(w30, e);
+                  part[2 * r + 1] += a * IDFF_UC(w31, e);
+                  if (heavy) {   // adjoints of z3 and z3', in place
+                    const float A0 = st.c[0] * IDFF_UC(uu3, e), A1 = st.c[1] * IDFF_UC(uu3, e);
+                    z[e] = fmaf(A1 * E, zd[e], A0 * s1);
+                    zd[e] = A1 * s1;
+                  }
                 }
-              }
-            float part[8];
-            fold_pairs(px, py, part);
             rsum += reduce_units(part);
             if (heavy) {
               uint32_t h0[8], l0[8], h1[8], l1[8];
-              pack_pairs(z, h0, l0);
-              pack_pairs(zd, h1, l1);
+              pack_jet(z, h0, l0);
+              pack_jet(zd, h1, l1);
               if (mt == 0) wait_kfree();
               uint32_t sa[2];
               make_sa(mt, sa);
@@ -702,7 +654,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
           for (int mt = 0; mt < 2; ++mt) {
             wait_acc();
             if (stamp && mt == 0) g_tc16_stamps[7] = clock64();
-            uint64_t a0[8], a1[8];
+            float a0[HP], a1[HP];
             load_acc(0, a0);
             load_acc(1, a1);
             release_acc();
@@ -715,17 +667,16 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
               tmem_ld8(stash + (16u << 16) + NP, zdu + 8);
               tmem_wait_ld();
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float c0 = __uint_as_float(cd[2 * i]), c1 = __uint_as_float(cd[2 * i + 1]);
-                const uint64_t s1 = pk2(c0 < 0.0f ? kSeluLambda : c0, c1 < 0.0f ? kSeluLambda : c1);
-                const uint64_t E = pk2(c0 < 0.0f ? 0.0f : c0, c1 < 0.0f ? 0.0f : c1);
-                a0[i] = fma2(mul2(a1[i], E), pk2(__uint_as_float(zdu[2 * i]), __uint_as_float(zdu[2 * i + 1])), mul2(a0[i], s1));
-                a1[i] = mul2(a1[i], s1);
+              for (int e = 0; e < HP; ++e) {
+                const float code = __uint_as_float(cd[e]);
+                const float s1 = code < 0.0f ? kSeluLambda : code, E = code < 0.0f ? 0.0f : code;
+                a0[e] = fmaf(a1[e] * E, __uint_as_float(zdu[e]), a0[e] * s1);
+                a1[e] = a1[e] * s1;
               }
             }
             uint32_t h0[8], l0[8], h1[8], l1[8];
-            pack_pairs(a0, h0, l0);
-            pack_pairs(a1, h1, l1);
+            pack_jet(a0, h0, l0);
+            pack_jet(a1, h1, l1);
             if (mt == 0) wait_kfree();
             uint32_t sa[2];
             make_sa(mt, sa);
@@ -741,31 +692,33 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
             const int n0 = mt * 128 + q * 32 + 4 * slot;
             wait_acc();
             if (stamp && mt == 0) g_tc16_stamps[9] = clock64();
-            uint64_t a0[8], a1[8];
+            float a0[HP], a1[HP];
             load_acc(0, a0);
             load_acc(1, a1);
             release_acc();
-            uint64_t z1[8];
-            layer1_pre(n0, st.t, z1);   // layer 1 is recomputed from x (K = 3) rather than kept across the four passes
             const float4 wx0 = __ldg(reinterpret_cast<const float4*>(P.net.wt0 + 0 * W + n0));
             const float4 wx1 = __ldg(reinterpret_cast<const float4*>(P.net.wt0 + 1 * W + n0));
+            const float4 wtt = __ldg(reinterpret_cast<const float4*>(P.net.wt0 + 2 * W + n0));
+            const float4 bb0 = __ldg(reinterpret_cast<const float4*>(P.net.b0 + (size_t)P.tidx * W + n0));
             const float4 zz1 = __ldg(reinterpret_cast<const float4*>(P.net.zd1 + n0));
-            const uint64_t w0p[2] = {pk2(wx0.x, wx0.y), pk2(wx0.z, wx0.w)}, w1p[2] = {pk2(wx1.x, wx1.y), pk2(wx1.z, wx1.w)};
-            const uint64_t zz1p[2] = {pk2(zz1.x, zz1.y), pk2(zz1.z, zz1.w)};
-            uint64_t px[4] = {0ull, 0ull, 0ull, 0ull}, py[4] = {0ull, 0ull, 0ull, 0ull};
+            float2 xp[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) xp[r] = *reinterpret_cast<const float2*>(sxs + 2 * (p0 + 4 * r + c4));
+            float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int ld = 0; ld < 2; ++ld)
 #pragma unroll
-              for (int r = 0; r < 4; ++r) {
-                const int i = 4 * ld + r;
-                uint64_t a, s1, E;
-                selu_jet2(z1[i], a, s1, E);
-                const uint64_t P1 = fma2(mul2(a1[i], E), zz1p[ld], mul2(a0[i], s1));
-                px[r] = fma2(P1, w0p[ld], px[r]);
-                py[r] = fma2(P1, w1p[ld], py[r]);
-              }
-            float part[8];
-            fold_pairs(px, py, part);
+              for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                  const int e = 8 * ld + 2 * r + h;
+                  const float zb = fmaf(IDFF_UC(wtt, e), st.t, IDFF_UC(bb0, e));
+                  float a, s1, E;
+                  selu_jet(fmaf(IDFF_UC(wx1, e), xp[r].y, fmaf(IDFF_UC(wx0, e), xp[r].x, zb)), a, s1, E);
+                  const float P1 = fmaf(a1[e] * E, IDFF_UC(zz1, e), a0[e] * s1);
+                  part[2 * r] += P1 * IDFF_UC(wx0, e);
+                  part[2 * r + 1] += P1 * IDFF_UC(wx1, e);
+                }
             gsum += reduce_units(part);
             if (mt == 0) wait_kfree();   // keeps the barrier phase in step
           }
