@@ -53,6 +53,13 @@ int tensor16o3_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p,
 int tensor16o3_sample_rk4_sweep(const idff_weights_t* w, const idff_field_params_t* params, int n_sets, const float* d_x0,
                                 const Stage* stages, const float* dts, int n_iv, float* d_out, int64_t N, bool safe, void* stream);
 
+// idff_md_tc16.cu: the PolyALA tensor kernel
+bool md16_supports(const idff_weights_t* w, const idff_field_params_t* p);
+int md16_field_eval(const idff_weights_t* w, const idff_field_params_t* p, float t, const float* d_x, float* d_out, int64_t N,
+                    void* stream);
+int md16_sample_sde(const idff_weights_t* w, const idff_field_params_t* p, const SdeTable& tab, const float* d_y0,
+                    const float* d_Ik, const float* d_Ik0, float* d_out, int64_t N, void* stream);
+
 // idff_sampler_wide.cu
 bool wide_supports(const idff_weights_t* w, const idff_field_params_t* p);
 bool wide_sweep_supports(const idff_weights_t* w, const idff_field_params_t* params, int n_sets, int64_t N);
@@ -165,6 +172,7 @@ extern "C" int idff_field_eval(const idff_weights_t* w, const idff_field_params_
   IDFF_CHECK_ARG(p->variant != IDFF_FIELD_CFM || t == 0.0f || d_x0, "idff_field_eval: the CFM field needs x0 (captured at t == 0) when t != 0");
   DeviceGuard g(w->device);
   if (p->impl == IDFF_IMPL_LAYERED) return wide_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
+  if (p->impl == IDFF_IMPL_TENSOR16 && p->variant == IDFF_FIELD_MD) return md16_field_eval(w, p, t, d_x, d_out, N, stream);
   // order 3 (three jets) on the 3-256-256-256-2 network: the fused three-jet tcgen05 kernel
   if ((p->impl == IDFF_IMPL_TENSOR16 || (p->impl == IDFF_IMPL_AUTO && N >= 4096)) && tensor16o3_supports(w, p))
     return tensor16o3_field_eval(w, p, t, d_x, d_out, N, p->impl == IDFF_IMPL_AUTO, stream);
@@ -494,6 +502,7 @@ extern "C" int idff_sample_sde(const idff_weights_t* w, const idff_field_params_
     if (tab.emit_step[e] < 0)
       IDFF_CUDA(cudaMemcpyAsync(d_out + (size_t)tab.emit_out[e] * N * p->dim, d_y0, (size_t)N * p->dim * sizeof(float),
                                 cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  if (p->impl == IDFF_IMPL_TENSOR16) return md16_sample_sde(w, p, tab, d_y0, d_I_k, d_I_k0, d_out, N, stream);
   const bool want_fused = p->impl == IDFF_IMPL_FUSED || (p->impl == IDFF_IMPL_AUTO && fused_supports(w, p));
   if (want_fused) {
     if (!fused_supports(w, p)) {

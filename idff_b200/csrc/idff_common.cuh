@@ -97,6 +97,10 @@ struct NetView {
   // 3xFP16 operand tiles of the layered engine (w % 128 == 0, 256..2048): [gemm 0..3][m-tile < w/128][k-block < w/64][hi, lo']
   // [128 rows x 64 fp16], same images as tc16_tiles but with the rows in natural unit order (tile row r = unit r).
   const float* tcw16_tiles;
+  // 3xFP16 operand tiles of the PolyALA tensor kernel (w == 128, din - 1 == dout <= 64; idff_md_tc16.cu): 13 tiles [128 rows x 64 k]
+  // hi | lo' (32 KB each, rows permuted like tc16_tiles): 0: W0[:, :D] (k = state dimension, zero beyond D); 1-2: W1; 3-4: W2;
+  // 5-6: W3 (rows = outputs, zero beyond dout); 7-8: W2^T; 9-10: W1^T; 11-12: W0[:, :D]^T (rows = state dimensions).
+  const float* md16_tiles;
 };
 
 }  // namespace idff

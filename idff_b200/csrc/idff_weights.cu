@@ -129,6 +129,10 @@ extern "C" int idff_weights_create(const float* const* h_W, const float* const* 
   const size_t tc16_floats = (size_t)4 * 2 * 4 * 2 * 128 * 32;   // 4 gemms x 2 m-tiles x 4 k-blocks x (hi, lo') x 16 KB
   off = (off + 255) & ~size_t(255);
   const size_t o_tc16 = tc16_layout ? take(tc16_floats) : 0;
+  const bool md16_layout = (w == 128) && din >= 2 && din - 1 == dout && dout <= 64;
+  const size_t md16_floats = (size_t)13 * 2 * 4096;
+  off = (off + 255) & ~size_t(255);
+  const size_t o_md16 = md16_layout ? take(md16_floats) : 0;
   std::vector<float> blob(off, 0.0f);
 
   const float *W0 = h_W[0], *W1 = h_W[1], *W2 = h_W[2], *W3 = h_W[3];
@@ -246,6 +250,37 @@ extern "C" int idff_weights_create(const float* const* h_W, const float* const* 
   for (int n = 0; n < w; ++n)
     for (int d = 0; d < din - 1; ++d) blob[o_w0n + (size_t)n * (din - 1) + d] = W0[(size_t)n * din_total + d];
 
+  if (md16_layout) {
+    const int Dm = din - 1;
+    for (int t = 0; t < 13; ++t) {
+      uint16_t* hi = reinterpret_cast<uint16_t*>(&blob[o_md16 + (size_t)t * 2 * 4096]);
+      uint16_t* lo = hi + 8192;
+      const int kb = t == 0 ? 0 : (t - 1) & 1;   // k-block of 64 inside the GEMM
+      const int gm = t == 0 ? 0 : 1 + (t - 1) / 2;   // 0: W0, 1: W1, 2: W2, 3: W3, 4: W2^T, 5: W1^T, 6: W0^T
+      for (int r = 0; r < 128; ++r)
+        for (int kk = 0; kk < 64; ++kk) {
+          const int gq = r & 7, slot = (gq & 1) | (((gq >> 1) & 1) << 2) | ((gq >> 2) << 1);
+          const int row = (r & ~31) + 4 * slot + ((r >> 3) & 3);   // TMEM lane r holds output row `row` (see tc16_tiles)
+          const int col = kb * 64 + kk;
+          float v = 0.0f;
+          switch (gm) {
+            case 0: v = col < Dm ? W0[(size_t)row * din_total + col] : 0.0f; break;
+            case 1: v = W1[(size_t)row * w + col]; break;
+            case 2: v = W2[(size_t)row * w + col]; break;
+            case 3: v = row < dout ? W3[(size_t)row * w + col] : 0.0f; break;
+            case 4: v = W2[(size_t)col * w + row]; break;
+            case 5: v = W1[(size_t)col * w + row]; break;
+            default: v = row < Dm ? W0[(size_t)col * din_total + row] : 0.0f; break;
+          }
+          const __half h = __float2half_rn(v);
+          const __half l = __float2half_rn((v - __half2float(h)) * 2048.0f);
+          const size_t o = (size_t)r * 64 + ((((kk >> 3) ^ (r & 7)) << 3) | (kk & 7));
+          memcpy(&hi[o], &h, 2);
+          memcpy(&lo[o], &l, 2);
+        }
+    }
+  }
+
   int prev = 0;
   IDFF_CUDA(cudaGetDevice(&prev));
   IDFF_CUDA(cudaSetDevice(device));
@@ -286,6 +321,7 @@ extern "C" int idff_weights_create(const float* const* h_W, const float* const* 
   v.tc_tiles = tc_layout ? d_blob + o_tc : nullptr;
   v.tc16_tiles = tc16_layout ? d_blob + o_tc16 : nullptr;
   v.tcw16_tiles = wide_layout ? d_blob + o_tw : nullptr;
+  v.md16_tiles = md16_layout ? d_blob + o_md16 : nullptr;
   h->d_stash = nullptr; h->stash_bytes = 0; h->tc_verified = 0;
   h->d_sweep = nullptr; h->sweep_bytes = 0;
   h->d_sweep_out = nullptr; h->sweep_out_bytes = 0;

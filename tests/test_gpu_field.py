@@ -93,7 +93,7 @@ def test_scorehead_and_cfm_fields(cuda_device):
     assert f1.shape == x.shape and torch.isfinite(f1).all()
 
 
-@pytest.mark.parametrize("impl", [_lib.IDFF_IMPL_GENERIC, _lib.IDFF_IMPL_FUSED, _lib.IDFF_IMPL_AUTO])
+@pytest.mark.parametrize("impl", [_lib.IDFF_IMPL_GENERIC, _lib.IDFF_IMPL_FUSED, _lib.IDFF_IMPL_TENSOR16, _lib.IDFF_IMPL_AUTO])
 def test_md_field_with_folded_embedding(cuda_device, impl):
     g = load_golden("md")
     y = torch.tensor(g["y"]).to(cuda_device)

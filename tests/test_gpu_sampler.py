@@ -129,7 +129,7 @@ def test_rk4_properties_at_scale(cuda_device):
         sampler.sample_rk4(m, x0[:8], torch.tensor([0.0, 0.5, 0.5, 1.0]))
 
 
-@pytest.mark.parametrize("impl", [_lib.IDFF_IMPL_GENERIC, _lib.IDFF_IMPL_FUSED, _lib.IDFF_IMPL_AUTO])
+@pytest.mark.parametrize("impl", [_lib.IDFF_IMPL_GENERIC, _lib.IDFF_IMPL_FUSED, _lib.IDFF_IMPL_TENSOR16, _lib.IDFF_IMPL_AUTO])
 def test_sde_srk_and_euler_vs_golden(cuda_device, impl):
     g = load_golden("md")
     y = torch.tensor(g["y"]).to(cuda_device)
