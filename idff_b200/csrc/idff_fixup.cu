@@ -178,6 +178,154 @@ int fixup_nonfinite(const idff_weights_t* w, const idff_field_params_t* p, int m
   return pl.multi ? launch(k_fixup<3, 4, true>) : launch(k_fixup<3, 8, false>);
 }
 
+// The same safety net behind the PolyALA tensor kernel (k_md16): trajectories whose last output row is non-finite are
+// integrated again from y0 with the fp32 generic evaluator under torchsde's srk / euler (the update of idff_generic_sde.cu,
+// rows taken from the queue), every requested output row rewritten.
+template <int NJ, int PB, bool MULTI>
+__global__ void __launch_bounds__(256) k_fixup_sde(NetView net, FieldCfg cfg, const __grid_constant__ SdeTable tab,
+                                                   const float* __restrict__ y0, const float* __restrict__ Ik,
+                                                   const float* __restrict__ Ik0, float* __restrict__ out, long N, int n_ts,
+                                                   unsigned long long* counters) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ long q_rows[256 + PB];
+  __shared__ int q_n;
+  SmemPlan s = carve<NJ, PB>(smem, net, cfg.D);
+  const int D = cfg.D, tid = threadIdx.x, nth = blockDim.x;
+  float* yprev = s.k3;
+  const float* last = out + (size_t)(n_ts - 1) * N * D;
+  const long per = (N + gridDim.x - 1) / gridDim.x;
+  const long lo = (long)blockIdx.x * per, hi = lo + per < N ? lo + per : N;
+  if (tid == 0) q_n = 0;
+  __syncthreads();
+  long base = lo;
+  while (true) {
+    while (true) {
+      const int n = q_n;
+      __syncthreads();
+      if (n >= PB || base >= hi) break;
+      const long end = base + nth < hi ? base + nth : hi;
+      const long idx = base + tid;
+      if (idx < end) {
+        bool bad = false;
+        for (int d = 0; d < D; ++d) bad = bad || !(fabsf(last[idx * D + d]) <= 3.0e38f);
+        if (bad) q_rows[atomicAdd(&q_n, 1)] = idx;
+      }
+      base = end;
+      __syncthreads();
+    }
+    const int n = q_n;
+    if (n == 0) break;
+    const int cnt = n < PB ? n : PB, q0 = n - cnt;
+    auto row_of = [&](int p) -> long { return p < cnt ? q_rows[q0 + p] : -1; };
+    for (int o = tid; o < PB * D; o += nth) {
+      const long row = row_of(o / D);
+      const float v = row >= 0 ? y0[row * D + (o % D)] : 0.0f;
+      s.y[o] = v;
+      s.xs[o] = v;
+    }
+    __syncthreads();
+    int emit = 0;
+    while (emit < tab.n_emit && tab.emit_step[emit] < 0) ++emit;
+    for (int stp = 0; stp < tab.n_steps; ++stp) {
+      const float h = tab.h[stp];
+      const size_t noff = (size_t)stp * N * D;
+      const float rdt = __fdiv_rn(1.0f, h), sq = __fsqrt_rn(h);
+      const int nstage = tab.method == 1 ? 1 : 3;
+#pragma unroll 1
+      for (int sg = 0; sg < nstage; ++sg) {
+        float* kout = sg == 0 ? s.k1 : (sg == 1 ? s.k2 : s.fs);
+        eval_dispatch<NJ, PB, MULTI>(net, cfg, tab.st[stp][sg], s.xs, s.x0s, kout, s.actA, s.actB, s.pred, s.gout);
+        for (int o = tid; o < PB * D; o += nth) {   // torchsde srk / euler, as in k_sample_sde
+          const long row = row_of(o / D);
+          const size_t gi = noff + (size_t)(row >= 0 ? row : 0) * D + (o % D);
+          const float y = s.y[o];
+          if (tab.method == 1) {
+            const float ik = row >= 0 ? Ik[gi] : 0.0f;
+            const float yn = __fadd_rn(__fadd_rn(y, __fmul_rn(s.k1[o], h)), __fmul_rn(tab.gval[stp][0], ik));
+            yprev[o] = y; s.y[o] = yn; s.xs[o] = yn;
+          } else if (sg == 0) {
+            const float ik0 = row >= 0 ? Ik0[gi] : 0.0f;
+            const float t1 = __fmul_rn(__fmul_rn(1.0f, s.k1[o]), h);
+            const float t2 = __fmul_rn(__fmul_rn(__fmul_rn(0.0f, tab.gval[stp][0]), ik0), rdt);
+            s.xs[o] = __fadd_rn(__fadd_rn(y, t1), t2);
+          } else if (sg == 1) {
+            const float ik0 = row >= 0 ? Ik0[gi] : 0.0f;
+            float v = y;
+            v = __fadd_rn(__fadd_rn(v, __fmul_rn(__fmul_rn(0.25f, s.k1[o]), h)),
+                          __fmul_rn(__fmul_rn(__fmul_rn(1.0f, tab.gval[stp][0]), ik0), rdt));
+            v = __fadd_rn(__fadd_rn(v, __fmul_rn(__fmul_rn(0.25f, s.k2[o]), h)),
+                          __fmul_rn(__fmul_rn(__fmul_rn(0.5f, tab.gval[stp][1]), ik0), rdt));
+            s.xs[o] = v;
+          } else {
+            const float ik = row >= 0 ? Ik[gi] : 0.0f;
+            const float ik0 = row >= 0 ? Ik0[gi] : 0.0f;
+            const float ikk = __fmul_rn(__fsub_rn(__fmul_rn(ik, ik), h), 0.5f);
+            const float ikkk = __fdiv_rn(__fsub_rn(__fmul_rn(__fmul_rn(ik, ik), ik), __fmul_rn(__fmul_rn(3.0f, h), ik)), 6.0f);
+            const float b1[4] = {-1.0f, (float)(4.0 / 3.0), (float)(2.0 / 3.0), 0.0f};
+            const float b2[4] = {1.0f, (float)(-4.0 / 3.0), (float)(1.0 / 3.0), 0.0f};
+            const float b3[4] = {2.0f, (float)(-4.0 / 3.0), (float)(-2.0 / 3.0), 0.0f};
+            const float b4[4] = {-2.0f, (float)(5.0 / 3.0), (float)(-2.0 / 3.0), 1.0f};
+            const float al[4] = {(float)(1.0 / 6.0), (float)(1.0 / 6.0), (float)(2.0 / 3.0), 0.0f};
+            const float F[4] = {s.k1[o], s.k2[o], s.fs[o], 0.0f};
+            float v = y;
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              float gw = __fmul_rn(b1[qq], ik);
+              gw = __fadd_rn(gw, __fdiv_rn(__fmul_rn(b2[qq], ikk), sq));
+              gw = __fadd_rn(gw, __fmul_rn(__fmul_rn(b3[qq], ik0), rdt));
+              gw = __fadd_rn(gw, __fmul_rn(__fmul_rn(b4[qq], ikkk), rdt));
+              v = __fadd_rn(__fadd_rn(v, __fmul_rn(__fmul_rn(al[qq], F[qq]), h)), __fmul_rn(tab.gval[stp][qq], gw));
+            }
+            yprev[o] = y; s.y[o] = v; s.xs[o] = v;
+          }
+        }
+        __syncthreads();
+      }
+      while (emit < tab.n_emit && tab.emit_step[emit] == stp) {
+        const float w0 = tab.emit_w0[emit], w1 = tab.emit_w1[emit];
+        const size_t ooff = (size_t)tab.emit_out[emit] * N * D;
+        for (int o = tid; o < PB * D; o += nth) {
+          const long row = row_of(o / D);
+          if (row >= 0) out[ooff + row * D + (o % D)] = __fadd_rn(__fmul_rn(w0, yprev[o]), __fmul_rn(w1, s.y[o]));
+        }
+        ++emit;
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      q_n = q0;
+      if (counters) atomicAdd(counters + 1, (unsigned long long)cnt);
+    }
+    __syncthreads();
+  }
+}
+
+int fixup_nonfinite_sde(const idff_weights_t* w, const idff_field_params_t* p, const SdeTable& tab, int n_ts, const float* d_y0,
+                        const float* d_Ik, const float* d_Ik0, float* d_out, int64_t N, void* stream) {
+  if (N <= 0 || n_ts < 2 || tab.n_steps == 0) return IDFF_OK;
+  FieldCfg cfg;
+  int nj;
+  cfg.variant = p->variant; cfg.D = p->dim; cfg.tidx = p->t_idx;
+  jets_needed(*p, &nj, &cfg.reverse);
+  const int njk = nj <= 2 ? 2 : 3;
+  GenPlan pl;
+  int rc = plan_generic(w, p->dim, njk, N, &pl);
+  if (rc) return rc;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
+  const long want = ((long)N + 255) / 256;
+  const int grid = (int)(want < 2L * sms ? want : 2L * sms);
+  auto launch = [&](auto kern) -> int {
+    IDFF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    kern<<<grid, pl.threads, pl.smem, (cudaStream_t)stream>>>(w->v, cfg, tab, d_y0, d_Ik, d_Ik0, d_out, (long)N, n_ts, w->d_counters);
+    IDFF_CUDA(cudaGetLastError());
+    count_launch();
+    return IDFF_OK;
+  };
+  if (njk == 2) return pl.multi ? launch(k_fixup_sde<2, 4, true>) : launch(k_fixup_sde<2, 8, false>);
+  return pl.multi ? launch(k_fixup_sde<3, 4, true>) : launch(k_fixup_sde<3, 8, false>);
+}
+
 // AUTO is range safe: a launch must leave its input rows intact for the safety net.  Copies them into handle-owned scratch
 // when the call runs in place or continues a chunked solve; *src then points at the copy.
 int keep_input(idff_weights_t* wm, const float** src, const float* d_out, bool force, size_t bytes, void* stream) {

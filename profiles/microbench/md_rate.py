@@ -8,6 +8,7 @@ from gpu_common import packed, drift_report
 from idff_b200 import fields, sampler, _lib
 dev = torch.device("cuda:0")
 pw = packed("polyala", dev)
+g = torch.Generator(device=dev).manual_seed(1)
 
 
 def timeit(fn, reps=3, warm=2):
@@ -23,15 +24,33 @@ def timeit(fn, reps=3, warm=2):
     return a.elapsed_time(b) / reps * 1e-3
 
 
+from idff_b200 import _lib as L
+import ctypes as C
+
+
+def manifold(K, frame=3):
+    """data-like states: fixed points of the denoiser x -> x1hat(t = .5, x), iterated on the device; rows that do not
+    converge are replaced by rows that do (the reference's SDE stays within +-190 degrees from such states)"""
+    z = (torch.rand(2 * K + 4096, 46, device=dev, generator=g) * 2 - 1) * 180
+    for _ in range(12):
+        inp = torch.cat([z, torch.full((z.shape[0], 1), 0.5, device=dev)], -1).contiguous()
+        out = torch.empty_like(z)
+        L.check(L.lib().idff_mlp_forward(pw.handle, L.ptr(inp), L.ptr(out), z.shape[0], frame, L.stream_of(z)), "mlp")
+        z = out
+    ok = torch.isfinite(z).all(1) & (z.abs().max(1).values < 400)
+    good = z[ok]
+    reps = (K + good.shape[0] - 1) // good.shape[0]
+    return (good.repeat(reps, 1)[:K] + 0.5 * torch.randn(K, 46, device=dev, generator=g)).contiguous()
+
+
 tsd = torch.linspace(0, 1, 3)
 nst = sampler.sde_num_steps(tsd, 0.3)
-g = torch.Generator(device=dev).manual_seed(1)
 for lg in (10, 13, 17, 20):
     K = 1 << lg
-    y0 = torch.randn(K, 46, device=dev, generator=g) * 60
+    y0 = manifold(K)
     bm = sampler.brownian_increments(nst, tsd, 0.3, (K, 46), dev)
     outs, row = {}, {}
-    for name, impl in (("tensor16", 5), ("ffma2", 2)):
+    for name, impl in (("tensor16", 5), ("auto", 0), ("ffma2", 2)):
         sde = fields.SDE_cal(pw, input_dim=46, sigma=0.5, init_ind=3, max_length=200, dt=0.3, gamma1=0.2, gamma2=1.25)
         sde.impl = impl
         outs[name] = sampler.sdeint(sde, y0, tsd, dt=0.3, bm=bm)
@@ -40,6 +59,6 @@ for lg in (10, 13, 17, 20):
     d = (outs["tensor16"][-1] - outs["ffma2"][-1]).abs()
     scale = outs["ffma2"][-1].abs().max().item()
     fin = torch.isfinite(outs["tensor16"]).all().item()
-    print(f"K=2^{lg}: M drift-evals/s {row}  tensor16 vs ffma2: max {d.max().item():.3e} median {d.median().item():.3e} (scale {scale:.3g}) finite={fin}"
+    print(f"K=2^{lg}: max|y0| {y0.abs().max().item():.0f} M drift-evals/s {row}  tensor16 vs ffma2: max {d.max().item():.3e} median {d.median().item():.3e} (scale {scale:.3g}) finite={fin}"
           f"  tensor16 {row['tensor16'] * 1e6 * 2.0 * 44672 * (nst * 3 * 4 - 2 * 3) / (nst * 3) / 1e12:.0f} TFLOP/s algorithmic", flush=True)
 print("nonfinite counters", _lib.weights_nonfinite(pw.handle))
