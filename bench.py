@@ -330,7 +330,7 @@ def run_ours(args):
 
 def aux_measurements(dev, pw, model, peaks):
     """Secondary kernels, each timed alone with CUDA events on inputs larger than L2 (reported, not the headline)."""
-    from idff_b200 import losses, sampler
+    from idff_b200 import _lib, losses, sampler
     from idff_b200.mmd import mmd_partial_sums
     from idff_b200.torchcfm import conditional_flow_matching as cfm
     aux = {}
@@ -625,14 +625,28 @@ def aux_measurements(dev, pw, model, peaks):
         pwm = PackedWeights.from_npz(os.path.join(GOLDEN, "weights_polyala.npz"), device=dev)
         sde = fields.SDE_cal(pwm, input_dim=46, sigma=0.5, init_ind=3, max_length=200, dt=0.3, gamma1=0.2, gamma2=1.25)
         K = 1 << 17
-        y0 = torch.randn(K, 46, device=dev, generator=g) * 60
+        # data-like start states: fixed points of the shipped denoiser x -> x1hat(t = .5, x) (iterated on the device, rows that
+        # converge), jittered.  From such states the reference's SDE stays within +-190 degrees, as its generator does from real
+        # frames; from arbitrary synthetic angles a quarter of the reference's own trajectories run away to 1e18.
+        z = (torch.rand(2 * K + 4096, 46, device=dev, generator=g) * 2 - 1) * 180
+        for _ in range(12):
+            inp = torch.cat([z, torch.full((z.shape[0], 1), 0.5, device=dev)], -1).contiguous()
+            zo = torch.empty_like(z)
+            _lib.check(_lib.lib().idff_mlp_forward(pwm.handle, _lib.ptr(inp), _lib.ptr(zo), z.shape[0], 3, _lib.stream_of(z)), "idff_mlp_forward")
+            z = zo
+        good = z[torch.isfinite(z).all(1) & (z.abs().max(1).values < 400)]
+        y0 = (good.repeat((K + good.shape[0] - 1) // good.shape[0], 1)[:K] + 0.5 * torch.randn(K, 46, device=dev, generator=g)).contiguous()
         tsd = torch.linspace(0, 1, 3)
         nst = sampler.sde_num_steps(tsd, 0.3)
         bm = sampler.brownian_increments(nst, tsd, 0.3, (K, 46), dev)
-        s = timeit(lambda: sampler.sdeint(sde, y0, tsd, dt=0.3, bm=bm), reps=2, warm=1)
-        aux["c4_polyala_srk_fused"] = {"particle_steps_per_s": K * nst * 3 / s, "trajectories": K, "steps": nst,
-                                       "drift_evals_per_step": 3,
-                                       "algorithmic_tflops": K * 2.0 * 44672 * (nst * 3 * 4 - 2 * 3) / s / 1e12}
+        for name, impl in (("c4_polyala_srk_tensor16", 0), ("c4_polyala_srk_fused", 2)):
+            sde.impl = impl
+            res = sampler.sdeint(sde, y0, tsd, dt=0.3, bm=bm)
+            s = timeit(lambda: sampler.sdeint(sde, y0, tsd, dt=0.3, bm=bm), reps=2, warm=1)
+            aux[name] = {"particle_steps_per_s": K * nst * 3 / s, "trajectories": K, "steps": nst, "drift_evals_per_step": 3,
+                         "algorithmic_tflops": K * 2.0 * 44672 * (nst * 3 * 4 - 2 * 3) / s / 1e12,
+                         "max_abs_state": float(res.abs().max()), "finite": bool(torch.isfinite(res).all()),
+                         "kernel": "k_md16 (tcgen05 3xFP16, default route) + fp32 safety net" if impl == 0 else "k_fused FFMA2 (fp32)"}
     except Exception as exc:   # secondary numbers must never break the headline line
         aux["other_configs_error"] = repr(exc)
     return aux
