@@ -326,6 +326,10 @@ def run_ours(args):
                 "particles_per_sec": value / steps_per_solve, "aux": aux}
         sys.stderr.flush()
         print(json.dumps(line), flush=True)
+        if ws > 1:
+            # with NCCL_DEBUG=INFO the library prints a teardown line from its process-exit finaliser: leave without running
+            # finalisers so that the JSON line stays the last line on stdout (everything is flushed, the group is destroyed)
+            os._exit(0)
 
 
 def aux_measurements(dev, pw, model, peaks):
