@@ -10,10 +10,15 @@
  *     idff_last_error() returns a thread-local message for the last failure on the calling thread;
  *   - pointers named d_* are DEVICE pointers owned by the caller (torch tensors), fp32 row-major unless
  *     stated; pointers named h_* are HOST pointers;  `stream` is a cudaStream_t passed as void*;
- *   - nothing is allocated per call; the only persistent allocation is the weights handle;
- *   - no global mutable state on the product path: handles are independent, calls on one handle may be issued
- *     from one host thread at a time.  The idff_debug_* entry points are process-wide diagnostic switches /
- *     read-outs (phase timestamps, alternative evaluators) for tests and profiling, not for production use.
+ *   - the only persistent allocation is the weights handle.  A handle also owns grow-only scratch that some routes size on
+ *     first use (the order-3 stash of the FFMA2 kernel, the buffers of the layered engine, the stage tables of the last
+ *     sweep, the input copy / tables of the AUTO route's safety net): those calls may cudaMalloc once and are not
+ *     CUDA-graph-capturable the first time; steady-state calls allocate nothing;
+ *   - a handle serves ONE in-flight call at a time (one stream, one host thread): the scratch above and the per-handle
+ *     counters are not keyed by stream.  Use one handle per stream for concurrent sampling with the same network;
+ *   - no process-global state on the product path: counters live in the handle (idff_weights_nonfinite).  The idff_debug_*
+ *     entry points are process-wide diagnostic switches / read-outs (phase timestamps, alternative evaluators) for tests
+ *     and profiling, not for production use.
  */
 #ifndef IDFF_B200_H
 #define IDFF_B200_H
