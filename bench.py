@@ -625,6 +625,15 @@ def aux_measurements(dev, pw, model, peaks):
             s = timeit(lambda: sampler.sample_rk4(m3, xs, torch.linspace(0, 1, 3)), reps=2, warm=1)
             aux[f"order3_w256_{name}"] = {"particle_steps_per_s": xs.shape[0] * 8 / s, "particles": xs.shape[0], "nfe": 2,
                                           "algorithmic_tflops": xs.shape[0] * flops_per_particle_solve(2, 3) / s / 1e12}
+        # score-head field (order-1 script, 5-256-256-256-4): k_tc16<score head> (AUTO) vs the generic fp32 kernel
+        pwsh = PackedWeights.from_npz(os.path.join(GOLDEN, "weights_scorehead256.npz"), device=dev)
+        Fsh = 5 * 256 + 2 * 256 * 256 + 256 * 4
+        for name, impl, xin in (("tcgen05", 0, xs), ("generic", 1, xs[: 1 << 18].contiguous())):
+            msh = fields.CustomNetModelScoreHead(pwsh, SIGMA, 0.2, 0.2)
+            msh.impl = impl
+            s = timeit(lambda: sampler.sample_rk4(msh, xin, torch.linspace(0, 1, 3)), reps=2, warm=1)
+            aux[f"scorehead_w256_{name}"] = {"particle_steps_per_s": xin.shape[0] * 8 / s, "particles": xin.shape[0], "nfe": 2,
+                                             "algorithmic_tflops": xin.shape[0] * 8 * 2.0 * Fsh / s / 1e12}
         # C4: PolyALA SDE_cal (47-128-128-128-46, folded embedding), srk, ts = linspace(0,1,3), dt = 0.3
         pwm = PackedWeights.from_npz(os.path.join(GOLDEN, "weights_polyala.npz"), device=dev)
         sde = fields.SDE_cal(pwm, input_dim=46, sigma=0.5, init_ind=3, max_length=200, dt=0.3, gamma1=0.2, gamma2=1.25)

@@ -114,6 +114,12 @@ __device__ __forceinline__ void store_jet(const uint32_t (&sa)[2], const uint32_
 // per-unit constant c[0..3] of the thread's four units for element e
 #define IDFF_UC(c, e) ((((e) >> 3) * 2 + ((e) & 1)) == 0 ? (c).x : (((e) >> 3) * 2 + ((e) & 1)) == 1 ? (c).y : (((e) >> 3) * 2 + ((e) & 1)) == 2 ? (c).z : (c).w)
 
+// SH = true: the score-head field (example_order1_with_prediction_head.py:64-96) on its 5-256-256-256-4 network -- input
+// cat[x, x, t], outputs x1hat = out[:, :2] and the score st = out[:, 2:], no autograd terms: every evaluation is a one-jet
+// forward pass (the boundary-evaluation machinery), with a 5-term first layer, four output sums and the closed form
+// a*(x1hat - x)/(1 - t) + c0*st + c1.  The second pair of output sums travels through operand rows 128.. of k-block 0, which
+// no MMA of a one-jet pass reads.
+template <bool SH>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, const __grid_constant__ Stage one) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -177,7 +183,8 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
     return P.tabs[g].st[e];
   };
   auto kind_of = [&](int e, int g) -> int { return P.mode == 0 ? one.kind : (P.mode == 1 ? rk.st[e].kind : P.tabs[g].st[e].kind); };
-  auto heavy_of = [&](int kind, int g) { return kind == 2 && (P.mode == 2 ? P.tabs[g].reverse : P.reverse) != 0; };
+  auto heavy_of = [&](int kind, int g) { return !SH && kind == 2 && (P.mode == 2 ? P.tabs[g].reverse : P.reverse) != 0; };
+  float* const red2 = reinterpret_cast<float*>(smem + Smem::act + KB_BYTES / 2);   // SH: [16 warps][32] sums of outputs 2, 3
 
   // Register budget: 20 warps x 96 registers at launch.  The four service warps (TMA, MMA, 2 x integrator) give back 64 each,
   // the sixteen epilogue warps take 16 each: their jet / adjoint algebra holds 2 x 16 accumulators + 32 packed operand words.
@@ -349,6 +356,15 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
             gg[d] = acc;
           }
         }
+        if (SH) {   // the score head's outputs: gg = st
+#pragma unroll
+          for (int d = 0; d < 2; ++d) {
+            float acc = __ldg(P.net.b3 + 2 + d);
+#pragma unroll
+            for (int w4 = 0; w4 < 4; ++w4) acc += red2[(red_w + w4) * 32 + red_l + 4 * d];
+            gg[d] = acc;
+          }
+        }
 #pragma unroll
         for (int d = 0; d < 2; ++d) {
           const float pr = pr_tot[d];
@@ -363,6 +379,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
             else if (st.kind == 1) f = __fdiv_rn(diff, st.end_div);
             else {
               f = __fdiv_rn(__fmul_rn(st.a, diff), st.den);
+              if (SH) f = __fadd_rn(__fadd_rn(f, __fmul_rn(st.c[0], gg[d])), st.c[1]);   // operation order of idff_field_generic.cuh
               if (heavy) f = __fadd_rn(f, gg[d]);
             }
           }
@@ -510,16 +527,21 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
           for (int r = 0; r < 4; ++r) xp[r] = *reinterpret_cast<const float2*>(sxs + 2 * (p0 + 4 * r + c4));
           const float4 wx0 = __ldg(reinterpret_cast<const float4*>(P.net.wt0 + 0 * W + n0));
           const float4 wx1 = __ldg(reinterpret_cast<const float4*>(P.net.wt0 + 1 * W + n0));
-          const float4 wtt = __ldg(reinterpret_cast<const float4*>(P.net.wt0 + 2 * W + n0));
+          const float4 wtt = __ldg(reinterpret_cast<const float4*>(P.net.wt0 + (SH ? 4 : 2) * W + n0));
           const float4 bb0 = __ldg(reinterpret_cast<const float4*>(P.net.b0 + (size_t)P.tidx * W + n0));
           const float4 zz1 = __ldg(reinterpret_cast<const float4*>(P.net.zd1 + n0));
+          // SH: the network's input is cat[x, x, t] -- rows 2, 3 of W0^T meet the same x again
+          const float4 wx2 = __ldg(reinterpret_cast<const float4*>(P.net.wt0 + (SH ? 2 : 0) * W + n0));
+          const float4 wx3 = __ldg(reinterpret_cast<const float4*>(P.net.wt0 + (SH ? 3 : 1) * W + n0));
           float v0[HP], v1[HP];
 #pragma unroll
           for (int e = 0; e < HP; ++e) {
             const int r = (e >> 1) & 3;
             const float zb = fmaf(IDFF_UC(wtt, e), st.t, IDFF_UC(bb0, e));
             float s1, E;
-            selu_jet(fmaf(IDFF_UC(wx1, e), xp[r].y, fmaf(IDFF_UC(wx0, e), xp[r].x, zb)), v0[e], s1, E);
+            float z1 = fmaf(IDFF_UC(wx1, e), xp[r].y, fmaf(IDFF_UC(wx0, e), xp[r].x, zb));
+            if (SH) z1 = fmaf(IDFF_UC(wx3, e), xp[r].y, fmaf(IDFF_UC(wx2, e), xp[r].x, z1));
+            selu_jet(z1, v0[e], s1, E);
             v1[e] = s1 * IDFF_UC(zz1, e);
           }
           uint32_t sa[2], hw[8], lw[8];
@@ -592,7 +614,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
         if (stamp) g_tc16_stamps[3] = clock64();
         // ---- gemm 1: layer 3 forward; x1hat partial sums; adjoint seeds
         {
-          float rsum = 0.0f;
+          float rsum = 0.0f, rsum2 = 0.0f;
 #pragma unroll 1
           for (int mt = 0; mt < 2; ++mt) {
             const int n0 = mt * 128 + q * 32 + 4 * slot;
@@ -610,7 +632,10 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
             const float4 uu3 = __ldg(reinterpret_cast<const float4*>(P.net.u3 + n0));
             const float4 w30 = __ldg(reinterpret_cast<const float4*>(P.net.w3 + 0 * W + n0));
             const float4 w31 = __ldg(reinterpret_cast<const float4*>(P.net.w3 + 1 * W + n0));
+            const float4 w32 = __ldg(reinterpret_cast<const float4*>(P.net.w3 + (SH ? 2 : 0) * W + n0));
+            const float4 w33 = __ldg(reinterpret_cast<const float4*>(P.net.w3 + (SH ? 3 : 1) * W + n0));
             float part[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float part2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int ld = 0; ld < 2; ++ld)       // fixed summation order over the thread's units 0, 1, 2, 3
 #pragma unroll
@@ -622,6 +647,10 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
                   selu_jet(z[e] + IDFF_UC(bb2, e), a, s1, E);
                   part[2 * r] += a * IDFF_UC(w30, e);
                   part[2 * r + 1] += a * IDFF_UC(w31, e);
+                  if (SH) {
+                    part2[2 * r] += a * IDFF_UC(w32, e);
+                    part2[2 * r + 1] += a * IDFF_UC(w33, e);
+                  }
                   if (heavy) {   // adjoints of z3 and z3', in place
                     const float A0 = st.c[0] * IDFF_UC(uu3, e), A1 = st.c[1] * IDFF_UC(uu3, e);
                     z[e] = fmaf(A1 * E, zd[e], A0 * s1);
@@ -629,6 +658,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
                   }
                 }
             rsum += reduce_units(part);
+            if (SH) rsum2 += reduce_units(part2);
             if (heavy) {
               uint32_t h0[8], l0[8], h1[8], l1[8];
               pack_jet(z, h0, l0);
@@ -644,6 +674,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
             }
           }
           red[warp * 32 + lane] = rsum;
+          if (SH) red2[warp * 32 + lane] = rsum2;
         }
         if (stamp) g_tc16_stamps[5] = clock64();
         ebar576();   // x1hat partial sums are in red[]: the integrator warps add them up
@@ -754,7 +785,9 @@ int keep_input(idff_weights_t* wm, const float** src, const float* d_out, bool f
 
 bool tensor16_supports(const idff_weights_t* w, const idff_field_params_t* p) {
   const NetView& v = w->v;
-  if (v.w != 256 || v.tc16_tiles == nullptr || p->dim != 2 || v.din != 3 || v.dout != 2) return false;
+  if (v.w != 256 || v.tc16_tiles == nullptr || p->dim != 2) return false;
+  if (p->variant == IDFF_FIELD_SCOREHEAD) return v.din == 5 && v.dout == 4;   // cat[x, x, t] -> (x1hat, st)
+  if (v.din != 3 || v.dout != 2) return false;
   if (!(p->variant == IDFF_FIELD_MOMENTUM || p->variant == IDFF_FIELD_CFM)) return false;
   int nj, rev;
   jets_needed(*p, &nj, &rev);
@@ -777,7 +810,8 @@ static int verify_tc16_launch(idff_weights_t* w, void* stream) {
 static int launch_tc16(const idff_weights_t* w, const idff_field_params_t* p, tch::TParams& P, const Rk4Table* rk,
                        const Stage* one, void* stream) {
   if (!tensor16_supports(w, p)) {
-    set_error("3xFP16 tensor-core sampler: needs a 3-256-256-256-2 network, dim 2, order <= 2 (momentum / CFM field)");
+    set_error("3xFP16 tensor-core sampler: needs a 3-256-256-256-2 network, dim 2, order <= 2 (momentum / CFM field) or the "
+              "5-256-256-256-4 score-head network");
     return IDFF_EUNSUPPORTED;
   }
   int sms = 148;
@@ -790,7 +824,8 @@ static int launch_tc16(const idff_weights_t* w, const idff_field_params_t* p, tc
   const Rk4Table& rkr = rk ? *rk : rk0;
   const Stage& oner = one ? *one : one0;
   const int smem = tch::Smem::total;
-  IDFF_CUDA(cudaFuncSetAttribute(tch::k_tc16, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const bool sh = p->variant == IDFF_FIELD_SCOREHEAD;
+  IDFF_CUDA(cudaFuncSetAttribute(sh ? tch::k_tc16<true> : tch::k_tc16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
@@ -804,7 +839,8 @@ static int launch_tc16(const idff_weights_t* w, const idff_field_params_t* p, tc
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  IDFF_CUDA(cudaLaunchKernelEx(&cfg, tch::k_tc16, P, rkr, oner));
+  if (sh) IDFF_CUDA(cudaLaunchKernelEx(&cfg, tch::k_tc16<true>, P, rkr, oner));
+  else IDFF_CUDA(cudaLaunchKernelEx(&cfg, tch::k_tc16<false>, P, rkr, oner));
   IDFF_CUDA(cudaGetLastError());
   count_launch();
   return verify_tc16_launch(const_cast<idff_weights_t*>(w), stream);

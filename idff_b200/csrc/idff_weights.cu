@@ -125,7 +125,8 @@ extern "C" int idff_weights_create(const float* const* h_W, const float* const* 
   const size_t tw_floats = (size_t)4 * tw_mt * tw_kb * 2 * 4096;   // 16 KB (4096 floats) per hi / lo' image
   off = (off + 255) & ~size_t(255);
   const size_t o_tw = wide_layout ? take(tw_floats) : 0;
-  const bool tc16_layout = tc_layout && w == 256;
+  // k_tc16 also serves the score-head network of the order-1 script (5-256-256-256-4: cat[x, x, t] -> (x1hat, st))
+  const bool tc16_layout = (tc_layout && w == 256) || (w == 256 && din == 5 && dout == 4 && !has_emb);
   const size_t tc16_floats = (size_t)4 * 2 * 4 * 2 * 128 * 32;   // 4 gemms x 2 m-tiles x 4 k-blocks x (hi, lo') x 16 KB
   off = (off + 255) & ~size_t(255);
   const size_t o_tc16 = tc16_layout ? take(tc16_floats) : 0;

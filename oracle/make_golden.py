@@ -11,6 +11,7 @@ Files:
   weights_{checkerboard,8gaussians}.npz   W0..W3,b0..b3 of 2D_examples/sample_*/best_IDFF_model.pt
   weights_polyala.npz                     + emb, of timeseris_example/MD/polyALA/MD_trained_polyALA.pt
   weights_scorehead.npz                   MLP(dim=4,w=64) default init, torch.manual_seed(0)
+  weights_scorehead256.npz scorehead256.npz   MLP(dim=4,w=256) (the order-1 script's network), `make_golden.py scorehead256`
   field2d.npz  traj2d.npz  scorehead.npz  md.npz  path.npz  loss.npz  mmd.npz
 """
 from __future__ import annotations
@@ -303,8 +304,37 @@ def golden_mlp_embedding():
     np.savez(os.path.join(OUT, "mlp_modules.npz"), **out)
 
 
+def golden_scorehead256():
+    """a5 at the width the order-1 script trains (example_order1_with_prediction_head.py:101: MLP(dim=4, w=256,
+    time_varying=True)): the reference's module (default init, torch.manual_seed(0)) under the script's own CustomNetModel
+    (:64-96) -- field evaluations and rk4 end points, fp32 and fp64 twins.  This is the shape the tcgen05 kernel serves."""
+    models = R.models()
+    torch.manual_seed(0)
+    net = models.MLP(dim=4, w=256, time_varying=True).eval()
+    export_weights(net, os.path.join(OUT, "weights_scorehead256.npz"))
+    import copy
+    net64 = copy.deepcopy(net).double()
+    o1 = R.script_symbols(R.ORDER1, ["CustomNetModel"])
+    x = x0_2d(256, seed=1) * 3.0
+    x0 = x0_2d(1024, seed=0)
+    sd = {"x": x.numpy(), "x0": x0.numpy(), "times": np.array(FIELD_TIMES, dtype=np.float32), "gammas": np.array(GAMMAS2[:4])}
+    ts = torch.linspace(0, 1, 6)
+    for gi, g in enumerate(GAMMAS2[:4]):
+        m = o1["CustomNetModel"](net, sigma=0.2, gamma1=g[0], gamma2=g[1])
+        m64 = o1["CustomNetModel"](net64, sigma=0.2, gamma1=g[0], gamma2=g[1])
+        sd[f"field_g{gi}"] = np.stack([run_field(m, torch.tensor(t, dtype=torch.float32), x).numpy() for t in FIELD_TIMES])
+        sd[f"field_g{gi}_f64"] = np.stack([run_field(m64, torch.tensor(t, dtype=torch.float32).double(), x.double()).numpy()
+                                           for t in FIELD_TIMES])
+        sd[f"traj_nfe5_g{gi}"] = O.odeint_rk4(m, x0.clone(), ts).detach()[-1].numpy()
+        sd[f"traj_nfe5_g{gi}_f64"] = O.odeint_rk4(m64, x0.double(), ts.double()).detach()[-1].numpy()
+    np.savez(os.path.join(OUT, "scorehead256.npz"), **sd)
+    print("wrote scorehead256.npz, weights_scorehead256.npz")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "metrics":
+    if len(sys.argv) > 1 and sys.argv[1] == "scorehead256":
+        golden_scorehead256()
+    elif len(sys.argv) > 1 and sys.argv[1] == "metrics":
         golden_metrics()
     elif len(sys.argv) > 1 and sys.argv[1] == "mlp":
         golden_mlp_embedding()

@@ -83,6 +83,17 @@ def test_scorehead_and_cfm_fields(cuda_device):
         for ti, tv in enumerate(FIELD_TIMES):
             out = m(torch.tensor(tv, dtype=torch.float32), x).cpu().numpy()
             assert_field_close(out, g[f"field_g{gi}"][ti], 1e-5, f"scorehead g{gi} t={tv}")
+    # the order-1 script's own network (w = 256): generic fp32 kernel and the tcgen05 kernel k_tc16<score head>, against the
+    # reference's fp32 and fp64 results
+    g = load_golden("scorehead256")
+    pw = packed("scorehead256", cuda_device)
+    for gi, gam in enumerate(g["gammas"]):
+        for impl in (_lib.IDFF_IMPL_AUTO, _lib.IDFF_IMPL_GENERIC, _lib.IDFF_IMPL_TENSOR16):
+            m = fields.CustomNetModelScoreHead(pw, 0.2, float(gam[0]), float(gam[1]))
+            m.impl = impl
+            for ti, tv in enumerate(FIELD_TIMES):
+                out = m(torch.tensor(tv, dtype=torch.float32), x).cpu().numpy()
+                assert_field_vs_refs(out, g[f"field_g{gi}"][ti], g[f"field_g{gi}_f64"][ti], 1e-5, f"scorehead256 g{gi} t={tv} impl={impl}")
     c = fields.CFMModel(packed("checkerboard", cuda_device))
     with pytest.raises(_lib.IdffError):
         c(torch.tensor(0.5), x)                  # no x0 captured yet

@@ -89,6 +89,57 @@ def test_rk4_scorehead_vs_golden(cuda_device):
         final = sampler.sample_rk4(m, x0, torch.linspace(0, 1, 6))
         r = drift_report(final.cpu().numpy(), g[f"traj_nfe5_g{gi}"])
         assert r["median"] <= 1e-5 and r["p999"] <= 1e-3, r
+    g = load_golden("scorehead256")   # the script's width: every kernel family that serves it
+    x0 = torch.tensor(g["x0"]).to(cuda_device)
+    pw = packed("scorehead256", cuda_device)
+    for gi, gam in enumerate(g["gammas"]):
+        for impl in (_lib.IDFF_IMPL_AUTO, _lib.IDFF_IMPL_GENERIC, _lib.IDFF_IMPL_TENSOR16):
+            m = fields.CustomNetModelScoreHead(pw, 0.2, float(gam[0]), float(gam[1]))
+            m.impl = impl
+            final = sampler.sample_rk4(m, x0, torch.linspace(0, 1, 6))
+            _check_drift(final.cpu().numpy(), g[f"traj_nfe5_g{gi}"], g[f"traj_nfe5_g{gi}_f64"], f"scorehead256 g{gi} impl={impl}",
+                         med=1e-5, p999=1e-3)
+
+
+def test_scorehead_tensor_kernel_properties(cuda_device):
+    """The score-head field on the tcgen05 kernel (k_tc16<SH>) at a ragged size: against the fp32 generic kernel per evaluation
+    and over a solve with a trajectory; sub-batches reproduce the whole bit for bit; AUTO = raw kernel on clean particles and the
+    fp32 re-solve where the fp16 split overflows."""
+    pw = packed("scorehead256", cuda_device)
+    N = 64 * 149 + 37
+    x0 = (torch.randn(N, 2, generator=torch.Generator().manual_seed(5)) / 1.5).to(cuda_device)
+    ts = torch.linspace(0, 1, 4)
+    outs = {}
+    for impl in (_lib.IDFF_IMPL_GENERIC, _lib.IDFF_IMPL_TENSOR16, _lib.IDFF_IMPL_AUTO):
+        m = fields.CustomNetModelScoreHead(pw, 0.2, 0.2, 0.3)
+        m.impl = impl
+        for tv in (0.0, 0.4, 1.0):
+            f = m(torch.tensor(tv), x0)
+            if impl == _lib.IDFF_IMPL_GENERIC:
+                outs[tv] = f
+            else:
+                scale = max(1.0, outs[tv].abs().max().item())
+                assert (f - outs[tv]).abs().max().item() <= 1e-5 * scale, (impl, tv)
+        traj = sampler.odeint(m, x0, ts, method="rk4")
+        if impl == _lib.IDFF_IMPL_GENERIC:
+            outs["traj"] = traj
+        else:
+            r = drift_report(traj.cpu().numpy(), outs["traj"].cpu().numpy())
+            assert r["median"] <= 1e-5 and r["p999"] <= 1e-3, (impl, r)
+            sub = sampler.odeint(m, x0[1000:3000].contiguous(), ts, method="rk4")
+            assert torch.equal(sub, traj[:, 1000:3000])
+    # range guard: huge inputs overflow the fp16 split; AUTO re-solves exactly those rows in fp32
+    xb = x0.clone()
+    xb[::7] *= 3.0e4
+    g = fields.CustomNetModelScoreHead(pw, 0.2, 0.2, 0.3)
+    g.impl = _lib.IDFF_IMPL_GENERIC
+    a = fields.CustomNetModelScoreHead(pw, 0.2, 0.2, 0.3)
+    ref = sampler.sample_rk4(g, xb, ts)
+    got = sampler.sample_rk4(a, xb, ts)
+    fin = torch.isfinite(ref).all(dim=1)
+    assert torch.isfinite(got[fin]).all()
+    d = (got[fin] - ref[fin]).abs() / ref[fin].abs().clamp(min=1.0)
+    assert d.median().item() <= 1e-5 and d.quantile(0.999).item() <= 1e-3
 
 
 def test_host_stepped_odeint_equals_fused(cuda_device):

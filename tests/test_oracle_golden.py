@@ -43,14 +43,20 @@ def test_traj2d_matches_golden():
                                   g["checkerboard_cfm_nfe5"])
 
 
-def test_scorehead_matches_golden():
-    g = load_golden("scorehead")
-    layers, _ = golden_layers("scorehead")
+@pytest.mark.parametrize("which", ["scorehead", "scorehead256"])
+def test_scorehead_matches_golden(which):
+    """w = 64 and the order-1 script's own width 256 (example_order1_with_prediction_head.py:101)."""
+    g = load_golden(which)
+    layers, _ = golden_layers(which)
     x = torch.tensor(g["x"])
     for gi, gam in enumerate(g["gammas"]):
         f = O.FieldScoreHead(layers, 0.2, tuple(gam))
         out = np.stack([f(torch.tensor(t, dtype=torch.float32), x).numpy() for t in FIELD_TIMES])
         np.testing.assert_array_equal(out, g[f"field_g{gi}"])
+    if which == "scorehead256":
+        f = O.FieldScoreHead(layers, 0.2, tuple(g["gammas"][2]))
+        tr = O.odeint_rk4(f, torch.tensor(g["x0"]), torch.linspace(0, 1, 6)).numpy()[-1]
+        np.testing.assert_array_equal(tr, g["traj_nfe5_g2"])
 
 
 def test_md_field_matches_golden():
