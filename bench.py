@@ -538,6 +538,18 @@ def aux_measurements(dev, pw, model, peaks):
                 "fused_steps_per_launch": S,
                 "fused_note": "one persistent cooperative kernel; rows phase streams 1 MB of weights per step per CTA "
                               "through a TMA ring (per-SM L2 ingest bound), 3 grid barriers per step"})
+        # the order-1 script's step with the score head (MLP(dim=4) on cat[xt, xt, t], flow loss + score regression): the same
+        # persistent kernel (IDFF_TRAIN_NET_SCOREHEAD) vs the torch step captured as a CUDA graph
+        torch.manual_seed(0)
+        fs = train.FusedFlowTrainer(MLP(dim=4, w=256, time_varying=True).to(dev), batch_size=256, lr=1e-3, score_sigma=0.2,
+                                    data=train.eight_gaussians_device)
+        x0d, x1d, td, _ = fs.draw(1024)
+        s_k = timeit(lambda: fs.steps(x0d, x1d, td), reps=5, warm=2) / 1024
+        gs = train.GraphedFlowTrainer(MLP(dim=4, w=256, time_varying=True).to(dev), batch_size=256, lr=1e-3, score_sigma=0.2,
+                                      data=train.eight_gaussians_device)
+        s_g = timeit(gs.step, reps=200, warm=5)
+        tr_out["scorehead_B256"] = {"fused_us_per_step": s_k * 1e6, "fused_samples_per_s": 256 / s_k,
+                                    "graph_us_per_step": s_g * 1e6, "graph_samples_per_s": 256 / s_g}
         # the reference's own step on the CPU (torch CPU, all host threads), B = 256
         torch.manual_seed(0)
         netc = MLP(dim=2, w=256, time_varying=True)

@@ -35,10 +35,8 @@
 namespace idff {
 namespace trn {
 
-constexpr int W = 256, DIN = 3, DOUT = 2, RMIN = 4, RMAX = 4, NC = 512, NT = NC + 32, MAXB = IDFF_TRAIN_MAX_BATCH;   // RMIN / RMAX: batch rows per row group (template R of the kernels; both 4 -- 8 rows per CTA pair was measured slower)
-constexpr int oW0 = 0, ob0 = oW0 + W * DIN, oW1 = ob0 + W, ob1 = oW1 + W * W, oW2 = ob1 + W, ob2 = oW2 + W * W,
-              oW3 = ob2 + W, ob3 = oW3 + DOUT * W, NP = ob3 + DOUT;
-constexpr int NPP = (NP + 63) / 64 * 64;
+constexpr int W = 256, RMIN = 4, RMAX = 4, NC = 512, NT = NC + 32, MAXB = IDFF_TRAIN_MAX_BATCH;   // RMIN / RMAX: batch rows per row group (template R of the kernels; both 4 -- 8 rows per CTA pair was measured slower)
+constexpr int MDOUT = 4, NSLOT = 6;    // widest output layer served; parameters a thread can own
 constexpr int JOB_W0 = 128, JOB_W3 = 136, JOB_B3 = 144, N_JOBS = 145;
 constexpr int MAX_GRID = 256;
 constexpr int NSMAX = 8, CH_ROWS = 32, CH_FLOATS = CH_ROWS * W, CH_PER_PASS = W / CH_ROWS, CH_PER_STEP = 4 * CH_PER_PASS;
@@ -49,18 +47,31 @@ static_assert(CH_PER_STEP % NSMAX == 0, "ring phase bookkeeping");
 // clock64 phase stamps of the last step of the last launch, per CTA: diagnostic only (idff_debug_train_stamps)
 __device__ long long g_train_stamps[256][8];
 
-// offsets (floats) into the caller-owned state buffer
+// The two networks the 2-D scripts train.  NET 0: MLP(dim=2): cat[xt, t] (3) -> 256 -> 256 -> 256 -> 2, flow loss
+// (Autograd_example_order2.py:79,98-105).  NET 1: the score-head MLP(dim=4) of the order-1 script: cat[xt, xt, t] (5) -> ... -> 4,
+// outputs (vt | st), flow loss + score regression (example_order1_with_prediction_head.py:101,119-132).
+// Parameter block (nn.Linear layout) and offsets (floats) into the caller-owned state buffer.
 // streaming copies [2 halves][256][128]: F_l[h][k][jj] = W_l[128 h + jj][k] (forward), B_l[h][j][kk] = W_l[j][128 h + kk] (backward)
-constexpr size_t sP = 0, sM = sP + NPP, sV = sM + NPP, sF1 = sV + NPP, sF2 = sF1 + W * W, sB1 = sF2 + W * W, sB2 = sB1 + W * W,
-                 sIN = sB2 + W * W,
-                 sA1 = sIN + (size_t)MAXB * 4, sA2 = sA1 + (size_t)MAXB * W, sA3 = sA2 + (size_t)MAXB * W,
-                 sZ1 = sA3 + (size_t)MAXB * W, sZ2 = sZ1 + (size_t)MAXB * W, sZ3 = sZ2 + (size_t)MAXB * W,
-                 sDO = sZ3 + (size_t)MAXB * W, sLP = sDO + (size_t)MAXB * DOUT, sNP = sLP + MAX_GRID, sBAR = sNP + MAX_GRID,
-                 sTOTAL = sBAR + 64;
+template <int DIN_, int DOUT_>
+struct LayT {
+  static constexpr int DIN = DIN_, DOUT = DOUT_;
+  static constexpr int oW0 = 0, ob0 = oW0 + W * DIN, oW1 = ob0 + W, ob1 = oW1 + W * W, oW2 = ob1 + W, ob2 = oW2 + W * W,
+                       oW3 = ob2 + W, ob3 = oW3 + DOUT * W, NP = ob3 + DOUT;
+  static constexpr int NPP = (NP + 63) / 64 * 64;
+  static constexpr size_t sP = 0, sM = sP + NPP, sV = sM + NPP, sF1 = sV + NPP, sF2 = sF1 + W * W, sB1 = sF2 + W * W, sB2 = sB1 + W * W,
+                          sIN = sB2 + W * W,
+                          sA1 = sIN + (size_t)MAXB * 4, sA2 = sA1 + (size_t)MAXB * W, sA3 = sA2 + (size_t)MAXB * W,
+                          sZ1 = sA3 + (size_t)MAXB * W, sZ2 = sZ1 + (size_t)MAXB * W, sZ3 = sZ2 + (size_t)MAXB * W,
+                          sDO = sZ3 + (size_t)MAXB * W, sLP = sDO + (size_t)MAXB * DOUT, sNP = sLP + MAX_GRID, sBAR = sNP + MAX_GRID,
+                          sTOTAL = sBAR + 64;
+};
+template <int NET> struct Lay;
+template <> struct Lay<0> : LayT<3, 2> {};
+template <> struct Lay<1> : LayT<5, 4> {};
 
 // dynamic shared memory (floats).  Phase A: ring | act | part | raw | in4 | dout | lterm.  Phases B / C alias it.
 constexpr int mRING = 0, mACT = mRING + 4 * CH_FLOATS, mPART = mACT + 2 * RMAX * W, mRAW = mPART + 2048 * RMAX,
-              mIN4 = mRAW + 2 * RMAX * 8, mDOUT = mIN4 + RMAX * 4, mLT = mDOUT + RMAX * DOUT, mTOTAL = mLT + RMAX * DOUT;
+              mIN4 = mRAW + 2 * RMAX * 8, mDOUT = mIN4 + RMAX * 4, mLT = mDOUT + RMAX * MDOUT, mTOTAL = mLT + RMAX * MDOUT;
 constexpr int mDZS = 0, mAS = mDZS + 256 * 32, mRED = mAS + 256 * 32, mREDB = mRED + 8 * 16 * 64, mPT = mREDB + 16 * 32,
               mBTOTAL = mPT + 32 * 33;
 static_assert(mBTOTAL <= mRAW, "phase B scratch must not overlap the input prefetch buffer");
@@ -74,6 +85,7 @@ struct Args {
   long long steps_done;
   float sigma;
   int sigma_mode;
+  float score_sigma;   // NET 1: the sigma0_sq argument of log_prob_xt_given_x1_dimwise (the script passes sigma, :126)
   double lr, beta1, beta2, b1pow, b2pow;            // bias corrections in double like torch's Python scalars; b?pow = beta?^steps_done
   float decay, omb1, omb2, beta2f, eps_adam, clip;  // 1 - lr*wd, 1 - beta1, 1 - beta2 (rounded to fp32 from double)
 };
@@ -244,34 +256,37 @@ __device__ __forceinline__ void load_raw(const Args& a, int s, int row_in_cta, i
 }
 
 // ---- phase A (consumer warps): path sample, forward, loss, backward-data for the 4 rows of this CTA (pair) ------------------
-template <int CL, int R>
+template <int NET, int CL, int R>
 __device__ void phase_rows(const Args& a, int s, float* smem, int grp, uint32_t rank, uint64_t* full, uint64_t* empty,
                            uint64_t* actbar, uint32_t& aph, uint32_t& cc) {
   using G = Geo<CL, R>;
+  using L = Lay<NET>;
   const float* ring = smem + mRING;
   float* actb = smem + mACT;      // [2][R][W]: layer n reads buffer n & 1 and writes the other one
   float* part = smem + mPART;     // [KSL][R][UPC]
   const float* raw = smem + mRAW + (s & 1) * R * 8;
   float* in4 = smem + mIN4;       // [R][4]   xt0, xt1, t, 1
-  float* dout = smem + mDOUT;     // [R][2]
+  float* dout = smem + mDOUT;     // [R][DOUT]
   float* lterm = smem + mLT;      // [R*DOUT]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ks = tid / G::NU4, u4 = tid % G::NU4;
   const int row0 = grp * R;
-  const float* P = a.S + sP;
+  const float* P = a.S + L::sP;
   const uint32_t peer_act = CL == 2 ? mapa(actb, rank ^ 1) : 0, peer_bar = CL == 2 ? mapa(actbar, rank ^ 1) : 0;
 
   // the (row, unit) outputs this thread finalises in every layer, and its share of the thin layers / biases (issued now)
   int orow[G::NQ], oj[G::NQ], ojl[G::NQ];
-  float w00[G::NQ], w01[G::NQ], w02[G::NQ], bias0[G::NQ], bias1[G::NQ], bias2[G::NQ], w30[G::NQ], w31[G::NQ];
+  float w0c[G::NQ][L::DIN], bias0[G::NQ], bias1[G::NQ], bias2[G::NQ], w3c[G::NQ][L::DOUT];
 #pragma unroll
   for (int q = 0; q < G::NQ; ++q) {
     const int o = tid + q * NC;
     orow[q] = o / G::UPC; ojl[q] = o % G::UPC; oj[q] = (int)rank * G::UPC + ojl[q];
     const int j = oj[q];
-    w00[q] = __ldcg(P + oW0 + j * 3); w01[q] = __ldcg(P + oW0 + j * 3 + 1); w02[q] = __ldcg(P + oW0 + j * 3 + 2);
-    bias0[q] = __ldcg(P + ob0 + j); bias1[q] = __ldcg(P + ob1 + j); bias2[q] = __ldcg(P + ob2 + j);
-    w30[q] = __ldcg(P + oW3 + j); w31[q] = __ldcg(P + oW3 + W + j);
+#pragma unroll
+    for (int c = 0; c < L::DIN; ++c) w0c[q][c] = __ldcg(P + L::oW0 + j * L::DIN + c);
+    bias0[q] = __ldcg(P + L::ob0 + j); bias1[q] = __ldcg(P + L::ob1 + j); bias2[q] = __ldcg(P + L::ob2 + j);
+#pragma unroll
+    for (int c = 0; c < L::DOUT; ++c) w3c[q][c] = __ldcg(P + L::oW3 + c * W + j);
   }
   // publish one value of the next layer's input: own copy + (pair) the peer's copy through distributed shared memory
   auto put = [&](int buf, int r, int j, float v) {
@@ -303,18 +318,20 @@ __device__ void phase_rows(const Args& a, int s, float* smem, int grp, uint32_t 
     const float xt1 = __fadd_rn(__fadd_rn(__fmul_rn(t, q0.w), __fmul_rn(omt, q0.y)), __fmul_rn(st, q1.y));
     const float4 v = make_float4(xt0, xt1, t, 1.0f);
     *reinterpret_cast<float4*>(in4 + tid * 4) = v;
-    if (rank == 0) *reinterpret_cast<float4*>(a.S + sIN + (size_t)(row0 + tid) * 4) = v;
+    if (rank == 0) *reinterpret_cast<float4*>(a.S + L::sIN + (size_t)(row0 + tid) * 4) = v;
   }
   csync();
 
   float code1[G::NQ], code2[G::NQ], code3[G::NQ];
 #pragma unroll
-  for (int q = 0; q < G::NQ; ++q) {   // layer 1 (K = 3) -> buffer 0
+  for (int q = 0; q < G::NQ; ++q) {   // layer 1 (K = 3; NET 1: K = 5, the input is cat[xt, xt, t]) -> buffer 0
     const int r = orow[q];
-    const float z = fmaf(in4[r * 4 + 2], w02[q], fmaf(in4[r * 4 + 1], w01[q], fmaf(in4[r * 4], w00[q], bias0[q])));
+    float z = fmaf(in4[r * 4 + 1], w0c[q][1], fmaf(in4[r * 4], w0c[q][0], bias0[q]));
+    if (NET == 1) z = fmaf(in4[r * 4 + 1], w0c[q][3], fmaf(in4[r * 4], w0c[q][2], z));
+    z = fmaf(in4[r * 4 + 2], w0c[q][L::DIN - 1], z);
     const float av = selu_fwd(z, code1[q]);
     put(0, r, oj[q], av);
-    a.S[sA1 + (size_t)(row0 + r) * W + oj[q]] = av;
+    a.S[L::sA1 + (size_t)(row0 + r) * W + oj[q]] = av;
   }
   layer_sync();
 
@@ -322,7 +339,7 @@ __device__ void phase_rows(const Args& a, int s, float* smem, int grp, uint32_t 
   for (int l = 0; l < 2; ++l) {   // layers 2, 3: ring passes 0 (W1^T), 1 (W2^T); reads buffer l, writes buffer l ^ 1
     gemm_ring<CL, R>(ring, actb + l * R * W, part, full, empty, cc, ks, u4, lane);
     csync();
-    float* Aout = a.S + (l ? sA3 : sA2);
+    float* Aout = a.S + (l ? L::sA3 : L::sA2);
 #pragma unroll
     for (int q = 0; q < G::NQ; ++q) {
       const int r = orow[q];
@@ -337,46 +354,63 @@ __device__ void phase_rows(const Args& a, int s, float* smem, int grp, uint32_t 
   }
 
   // output layer + loss (Autograd_example_order2.py:105) + d loss / d vt; a3 is in buffer 0 (both CTAs of a pair compute it)
-  if (warp < R * DOUT) {
-    const int r = warp >> 1, o = warp & 1;
+  if (warp < R * L::DOUT) {
+    const int r = warp / L::DOUT, o = warp % L::DOUT;
     float sum = 0.0f;
 #pragma unroll
-    for (int i = 0; i < W / 32; ++i) sum = fmaf(actb[r * W + lane + 32 * i], __ldcg(P + oW3 + o * W + lane + 32 * i), sum);
+    for (int i = 0; i < W / 32; ++i) sum = fmaf(actb[r * W + lane + 32 * i], __ldcg(P + L::oW3 + o * W + lane + 32 * i), sum);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
     if (lane == 0) {
-      const float vt = sum + __ldcg(P + ob3 + o);
+      const float vt = sum + __ldcg(P + L::ob3 + o);
       const float t = in4[r * 4 + 2];
-      const float x1v = raw[r * 8 + 2 + o];
-      const float wgt = __fdiv_rn(1.0f, __fsub_rn(1.01f, t));
-      const float rr = __fmul_rn(wgt, __fsub_rn(vt, x1v));
-      lterm[warp] = __fmul_rn(rr, rr);
-      const float gk = 1.0f / (float)(a.B * DOUT);
-      const float d = 2.0f * rr * wgt * gk;
-      dout[r * DOUT + o] = d;
-      if (rank == 0) a.S[sDO + (size_t)(row0 + r) * DOUT + o] = d;
+      const float gk = 1.0f / (float)(a.B * 2);   // both loss terms are means over B x 2 elements
+      float d;
+      if (o < 2) {   // flow loss, Autograd_example_order2.py:105 (= example_order1_with_prediction_head.py:129)
+        const float x1v = raw[r * 8 + 2 + o];
+        const float wgt = __fdiv_rn(1.0f, __fsub_rn(1.01f, t));
+        const float rr = __fmul_rn(wgt, __fsub_rn(vt, x1v));
+        lterm[warp] = __fmul_rn(rr, rr);
+        d = 2.0f * rr * wgt * gk;
+      } else {       // score regression mean((st - logp)^2), logp = log_prob_xt_given_x1_dimwise(xt, x1, x0, t, sigma) (:26-51, :126-131;
+                     // the operation order of k_loss<1>, idff_train.cu)
+        const int dd = o - 2;
+        const float x0v = raw[r * 8 + dd], x1v = raw[r * 8 + 2 + dd], xtv = in4[r * 4 + dd];
+        const float omt = __fsub_rn(1.0f, t);
+        const float mu = __fadd_rn(__fmul_rn(t, x1v), __fmul_rn(omt, x0v));
+        const float s2v = __fadd_rn(__fmul_rn(__fmul_rn(a.score_sigma, t), omt), 1e-4f);
+        const float diff = __fsub_rn(xtv, mu);
+        const float lp = __fmul_rn(-0.5f, __fadd_rn(logf(__fmul_rn(6.283185307179586f, s2v)), __fdiv_rn(__fmul_rn(diff, diff), s2v)));
+        const float rr = __fsub_rn(vt, lp);
+        lterm[warp] = __fmul_rn(rr, rr);
+        d = 2.0f * rr * gk;
+      }
+      dout[r * L::DOUT + o] = d;
+      if (rank == 0) a.S[L::sDO + (size_t)(row0 + r) * L::DOUT + o] = d;
     }
   }
   csync();
   if (tid == 0 && rank == 0) {
     float ls = 0.0f;
 #pragma unroll
-    for (int i = 0; i < R * DOUT; ++i) ls += lterm[i];
-    a.S[sLP + grp] = ls;
+    for (int i = 0; i < R * L::DOUT; ++i) ls += lterm[i];
+    a.S[L::sLP + grp] = ls;
   }
 #pragma unroll
   for (int q = 0; q < G::NQ; ++q) {   // dZ3 = (dOut W3) * selu'(z3) -> buffer 1
     const int r = orow[q];
-    const float dz = fmaf(dout[r * 2 + 1], w31[q], dout[r * 2] * w30[q]) * selu_d1(code3[q]);
+    float dsum = fmaf(dout[r * L::DOUT + 1], w3c[q][1], dout[r * L::DOUT] * w3c[q][0]);
+    if (NET == 1) dsum = fmaf(dout[r * L::DOUT + 3], w3c[q][3], fmaf(dout[r * L::DOUT + 2], w3c[q][2], dsum));
+    const float dz = dsum * selu_d1(code3[q]);
     put(1, r, oj[q], dz);
-    a.S[sZ3 + (size_t)(row0 + r) * W + oj[q]] = dz;
+    a.S[L::sZ3 + (size_t)(row0 + r) * W + oj[q]] = dz;
   }
   layer_sync();
 #pragma unroll 1
   for (int l = 0; l < 2; ++l) {   // dZ2 = (dZ3 W2) * selu'(z2), dZ1 = (dZ2 W1) * selu'(z1): ring passes 2 (W2), 3 (W1)
     gemm_ring<CL, R>(ring, actb + (l ^ 1) * R * W, part, full, empty, cc, ks, u4, lane);
     csync();
-    float* Zout = a.S + (l ? sZ1 : sZ2);
+    float* Zout = a.S + (l ? L::sZ1 : L::sZ2);
 #pragma unroll
     for (int q = 0; q < G::NQ; ++q) {
       const int r = orow[q];
@@ -390,23 +424,25 @@ __device__ void phase_rows(const Args& a, int s, float* smem, int grp, uint32_t 
 
 // One thread's share of the parameters: up to 4 gradients and their flat indices (-1: none).
 struct Owned {
-  float g[4];
-  int idx[4];
+  float g[NSLOT];
+  int idx[NSLOT];
   int tile;     // tile jobs: the job index (layer, jb, kb) whose streaming copies this CTA refreshes, else -1
 };
 
 // ---- phase B ---------------------------------------------------------------------------------------------------------------
 // tile (jb, kb) of dW = dZ^T A: thread (ksl, jj, kk) accumulates the 4 x 4 block (4 jj.., 4 kk..) over rows r = ksl (mod 8);
 // the 8 partial blocks meet in shared memory; thread (j = tid / 16, kp = tid % 16) ends up owning (j, 2 kp), (j, 2 kp + 1).
+template <int NET>
 __device__ void job_tile(const Args& a, int job, float* smem, Owned& own) {
+  using L = Lay<NET>;
   float* dZs = smem + mDZS;     // [256][32]
   float* As = smem + mAS;       // [256][32]
   float* red = smem + mRED;     // [8][16][64]
   float* redb = smem + mREDB;   // [16][32]
   const int tid = threadIdx.x;
   const int m = job >> 6, tile = job & 63, jb = tile >> 3, kb = tile & 7;
-  const float* dZ = a.S + (m ? sZ3 : sZ2);
-  const float* Ain = a.S + (m ? sA2 : sA1);
+  const float* dZ = a.S + (m ? L::sZ3 : L::sZ2);
+  const float* Ain = a.S + (m ? L::sA2 : L::sA1);
   const int ksl = tid >> 6, t64 = tid & 63, jj = t64 >> 3, kk = t64 & 7;
   float acc[4][4], gbs = 0.f;
 #pragma unroll
@@ -469,7 +505,7 @@ __device__ void job_tile(const Args& a, int job, float* smem, Owned& own) {
       g0 += red[(k * 16 + e) * 64 + src];
       g1 += red[(k * 16 + e + 1) * 64 + src];
     }
-    const int oW = m ? oW2 : oW1;
+    const int oW = m ? L::oW2 : L::oW1;
     own.g[0] = g0; own.g[1] = g1;
     own.idx[0] = oW + (jb * 32 + j) * W + kb * 32 + 2 * kp;
     own.idx[1] = own.idx[0] + 1;
@@ -479,7 +515,7 @@ __device__ void job_tile(const Args& a, int job, float* smem, Owned& own) {
 #pragma unroll
       for (int k = 0; k < 16; ++k) b += redb[k * 32 + j];
       own.g[2] = b;
-      own.idx[2] = (m ? ob2 : ob1) + jb * 32 + j;
+      own.idx[2] = (m ? L::ob2 : L::ob1) + jb * 32 + j;
     }
   }
 }
@@ -513,9 +549,10 @@ __device__ void job_thin(const Args& a, const float* X, const float* Y, int q, f
   }
 }
 
-template <int CL, int R>
+template <int NET, int CL, int R>
 __global__ void __launch_bounds__(NT, 1) k_train_flow(const Args a) {
   using G = Geo<CL, R>;
+  using L = Lay<NET>;
   constexpr int NS = G::NS;
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t full[NSMAX], empty[NSMAX], actbar[1];
@@ -545,7 +582,7 @@ __global__ void __launch_bounds__(NT, 1) k_train_flow(const Args a) {
 #ifndef IDFF_TRN_NOTMA
       if (lane == 0) {
         fence_async_global();
-        const float* src[4] = {a.S + sF1, a.S + sF2, a.S + sB2, a.S + sB1};
+        const float* src[4] = {a.S + L::sF1, a.S + L::sF2, a.S + L::sB2, a.S + L::sB1};
 #pragma unroll 1
         for (int c = 0; c < CH_PER_STEP; ++c, ++cc) {
           const uint32_t stage = cc % NS;
@@ -569,64 +606,71 @@ __global__ void __launch_bounds__(NT, 1) k_train_flow(const Args a) {
 
   // ---- consumer warps ------------------------------------------------------------------------------------------------------
   unsigned epoch = 0;
-  unsigned* bar = reinterpret_cast<unsigned*>(a.S + sBAR);
-  float* P = a.S + sP;
-  float* M = a.S + sM;
-  float* V = a.S + sV;
+  unsigned* bar = reinterpret_cast<unsigned*>(a.S + L::sBAR);
+  float* P = a.S + L::sP;
+  float* M = a.S + L::sM;
+  float* V = a.S + L::sV;
   double b1pow = a.b1pow, b2pow = a.b2pow;
 
   for (int s = 0; s < a.n_steps; ++s) {
     const bool stamp = tid == 0 && s == a.n_steps - 1;
     if (stamp) g_train_stamps[cta][0] = clock64();
-    if (row_cta) phase_rows<CL, R>(a, s, smem, grp, rank, full, empty, actbar, aph, cc);
+    if (row_cta) phase_rows<NET, CL, R>(a, s, smem, grp, rank, full, empty, actbar, aph, cc);
     if (stamp) g_train_stamps[cta][1] = clock64();
     grid_barrier(bar, epoch, false);
     if (stamp) g_train_stamps[cta][2] = clock64();
 
     Owned own;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { own.g[i] = 0.0f; own.idx[i] = -1; }
+    for (int i = 0; i < NSLOT; ++i) { own.g[i] = 0.0f; own.idx[i] = -1; }
     own.tile = -1;
     if (cta < JOB_W0) {
-      job_tile(a, cta, smem, own);
-    } else if (cta < JOB_W3) {   // dW0, db0 for units [32 q, 32 q + 32)
+      job_tile<NET>(a, cta, smem, own);
+    } else if (cta < JOB_W3) {   // dW0, db0 for units [32 q, 32 q + 32): sums of dZ1 * (xt0, xt1, t, 1)
       float o[4];
       const int q = cta - JOB_W0;
-      job_thin<4>(a, a.S + sZ1, a.S + sIN, q, smem, o);
+      job_thin<4>(a, a.S + L::sZ1, a.S + L::sIN, q, smem, o);
       if (tid < 32) {
         const int j = 32 * q + tid;
+        if (NET == 0) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { own.g[c] = o[c]; own.idx[c] = oW0 + j * 3 + c; }
-        own.g[3] = o[3]; own.idx[3] = ob0 + j;
+          for (int c = 0; c < 3; ++c) { own.g[c] = o[c]; own.idx[c] = L::oW0 + j * 3 + c; }
+          own.g[3] = o[3]; own.idx[3] = L::ob0 + j;
+        } else {   // input cat[xt, xt, t]: columns 0, 2 see xt0, columns 1, 3 see xt1
+          own.g[0] = o[0]; own.g[1] = o[1]; own.g[2] = o[0]; own.g[3] = o[1]; own.g[4] = o[2]; own.g[5] = o[3];
+#pragma unroll
+          for (int c = 0; c < 5; ++c) own.idx[c] = L::oW0 + j * L::DIN + c;
+          own.idx[5] = L::ob0 + j;
+        }
       }
     } else if (cta < JOB_B3) {   // dW3 for units [32 q, 32 q + 32)
       float o[4];
       const int q = cta - JOB_W3;
-      job_thin<2>(a, a.S + sA3, a.S + sDO, q, smem, o);
+      job_thin<L::DOUT>(a, a.S + L::sA3, a.S + L::sDO, q, smem, o);
       if (tid < 32) {
         const int j = 32 * q + tid;
-        own.g[0] = o[0]; own.idx[0] = oW3 + j;
-        own.g[1] = o[1]; own.idx[1] = oW3 + W + j;
+#pragma unroll
+        for (int c = 0; c < L::DOUT; ++c) { own.g[c] = o[c]; own.idx[c] = L::oW3 + c * W + j; }
       }
     } else if (cta == JOB_B3) {   // db3 and the loss value
-      if (warp < 2) {
+      if (warp < L::DOUT) {
         float sum = 0.0f;
-        for (int r = lane; r < a.B; r += 32) sum += __ldcg(a.S + sDO + (size_t)r * DOUT + warp);
+        for (int r = lane; r < a.B; r += 32) sum += __ldcg(a.S + L::sDO + (size_t)r * L::DOUT + warp);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-        if (lane == 0) { own.g[0] = sum; own.idx[0] = ob3 + warp; }
-      } else if (warp == 2) {
+        if (lane == 0) { own.g[0] = sum; own.idx[0] = L::ob3 + warp; }
+      } else if (warp == 8) {
         double sum = 0.0;
-        for (int c = lane; c < a.B / R; c += 32) sum += (double)__ldcg(a.S + sLP + c);
+        for (int c = lane; c < a.B / R; c += 32) sum += (double)__ldcg(a.S + L::sLP + c);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-        if (lane == 0 && a.loss_out) a.loss_out[s] = (float)(sum / (double)(a.B * DOUT));
+        if (lane == 0 && a.loss_out) a.loss_out[s] = (float)(sum / (double)(a.B * 2));   // each loss term: a mean over B x 2 elements
       }
     }
     // the owner's parameter and moment loads do not depend on the clip coefficient: in flight across the barrier
-    float pv[4], mv[4], vv[4];
+    float pv[NSLOT], mv[NSLOT], vv[NSLOT];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NSLOT; ++i) {
       const int ix = own.idx[i];
       pv[i] = mv[i] = vv[i] = 0.0f;
       if (ix >= 0) { pv[i] = __ldcg(P + ix); mv[i] = __ldcg(M + ix); vv[i] = __ldcg(V + ix); }
@@ -634,7 +678,7 @@ __global__ void __launch_bounds__(NT, 1) k_train_flow(const Args a) {
     {   // this CTA's sum of squared gradients
       double ss = 0.0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) ss += (double)own.g[i] * (double)own.g[i];
+      for (int i = 0; i < NSLOT; ++i) ss += (double)own.g[i] * (double)own.g[i];
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
       if (lane == 0) sred[warp] = ss;
@@ -642,7 +686,7 @@ __global__ void __launch_bounds__(NT, 1) k_train_flow(const Args a) {
       if (tid == 0) {
         double tot = 0.0;
         for (int i = 0; i < NC / 32; ++i) tot += sred[i];
-        a.S[sNP + cta] = (float)tot;
+        a.S[L::sNP + cta] = (float)tot;
       }
     }
     if (stamp) g_train_stamps[cta][3] = clock64();
@@ -656,7 +700,7 @@ __global__ void __launch_bounds__(NT, 1) k_train_flow(const Args a) {
 #pragma unroll
       for (int i = 0; i < MAX_GRID / 32; ++i) {
         const int c = lane + 32 * i;
-        tot += c < (int)gridDim.x ? (double)__ldcg(a.S + sNP + c) : 0.0;
+        tot += c < (int)gridDim.x ? (double)__ldcg(a.S + L::sNP + c) : 0.0;
       }
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, off);
@@ -671,9 +715,9 @@ __global__ void __launch_bounds__(NT, 1) k_train_flow(const Args a) {
     csync();
     {   // AdamW, torch/optim/adamw.py op order
       const float coef = s_coef, step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
-      float pn[4];
+      float pn[NSLOT];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < NSLOT; ++i) {
         pn[i] = 0.0f;
         const int ix = own.idx[i];
         if (ix < 0) continue;
@@ -688,8 +732,8 @@ __global__ void __launch_bounds__(NT, 1) k_train_flow(const Args a) {
       }
       if (own.tile >= 0) {   // streaming copies of this 32 x 32 tile: backward (as stored) and forward (transposed via smem)
         const int m = own.tile >> 6, jb = (own.tile >> 3) & 7, kb = own.tile & 7;
-        float* Bc = a.S + (m ? sB2 : sB1) + (size_t)(kb >> 2) * HALF + (kb & 3) * 32;   // B[h][j][kk], kk = k - 128 h
-        float* Fc = a.S + (m ? sF2 : sF1) + (size_t)(jb >> 2) * HALF + (jb & 3) * 32;   // F[h][k][jj], jj = j - 128 h
+        float* Bc = a.S + (m ? L::sB2 : L::sB1) + (size_t)(kb >> 2) * HALF + (kb & 3) * 32;   // B[h][j][kk], kk = k - 128 h
+        float* Fc = a.S + (m ? L::sF2 : L::sF1) + (size_t)(jb >> 2) * HALF + (jb & 3) * 32;   // F[h][k][jj], jj = j - 128 h
         float* pt = smem + mPT;
         const int j = tid >> 4, kp = tid & 15;
         *reinterpret_cast<float2*>(Bc + (jb * 32 + j) * 128 + 2 * kp) = make_float2(pn[0], pn[1]);
@@ -707,14 +751,16 @@ __global__ void __launch_bounds__(NT, 1) k_train_flow(const Args a) {
   }
 }
 
-__global__ void k_train_init(float* S) {   // streaming copies of layers 2 and 3 from the parameter block
+template <int NET>
+__global__ void k_train_init(float* S) {
+  using L = Lay<NET>;   // streaming copies of layers 2 and 3 from the parameter block
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < W * W) {
     const int j = i / W, k = i % W;   // W_l[j][k]
-    const float w1 = S[sP + oW1 + i], w2 = S[sP + oW2 + i];
+    const float w1 = S[L::sP + L::oW1 + i], w2 = S[L::sP + L::oW2 + i];
     const size_t f = (size_t)(j >> 7) * HALF + k * 128 + (j & 127), b = (size_t)(k >> 7) * HALF + j * 128 + (k & 127);
-    S[sF1 + f] = w1; S[sF2 + f] = w2;
-    S[sB1 + b] = w1; S[sB2 + b] = w2;
+    S[L::sF1 + f] = w1; S[L::sF2 + f] = w2;
+    S[L::sB1 + b] = w1; S[L::sB2 + b] = w2;
   }
 }
 
@@ -724,14 +770,25 @@ __global__ void k_train_init(float* S) {   // streaming copies of layers 2 and 3
 using namespace idff;
 using namespace idff::trn;
 
-extern "C" int64_t idff_train_flow_state_floats(void) { return (int64_t)sTOTAL; }
-
-extern "C" int idff_train_flow_offsets(int64_t* h_out12) {
-  IDFF_CHECK_ARG(h_out12, "idff_train_flow_offsets: null pointer");
-  const int64_t v[12] = {oW0, ob0, oW1, ob1, oW2, ob2, oW3, ob3, NP, (int64_t)sP, (int64_t)sM, (int64_t)sV};
+template <int NET>
+static int offsets_impl(int64_t* h_out12) {
+  using L = Lay<NET>;
+  const int64_t v[12] = {L::oW0, L::ob0, L::oW1, L::ob1, L::oW2, L::ob2, L::oW3, L::ob3, L::NP, (int64_t)L::sP, (int64_t)L::sM, (int64_t)L::sV};
   for (int i = 0; i < 12; ++i) h_out12[i] = v[i];
   return IDFF_OK;
 }
+
+extern "C" int64_t idff_train_state_floats(int32_t net) {
+  return net == IDFF_TRAIN_NET_FLOW ? (int64_t)Lay<0>::sTOTAL : net == IDFF_TRAIN_NET_SCOREHEAD ? (int64_t)Lay<1>::sTOTAL : (int64_t)-1;
+}
+extern "C" int64_t idff_train_flow_state_floats(void) { return idff_train_state_floats(IDFF_TRAIN_NET_FLOW); }
+
+extern "C" int idff_train_offsets(int32_t net, int64_t* h_out12) {
+  IDFF_CHECK_ARG(h_out12, "idff_train_offsets: null pointer");
+  IDFF_CHECK_ARG(net == IDFF_TRAIN_NET_FLOW || net == IDFF_TRAIN_NET_SCOREHEAD, "idff_train_offsets: unknown network %d", net);
+  return net == IDFF_TRAIN_NET_FLOW ? offsets_impl<0>(h_out12) : offsets_impl<1>(h_out12);
+}
+extern "C" int idff_train_flow_offsets(int64_t* h_out12) { return idff_train_offsets(IDFF_TRAIN_NET_FLOW, h_out12); }
 
 static int g_pair_mode = 0;   // diagnostic: 1 = run a row group on a CTA pair where possible (idff_debug_train_pair_mode)
 extern "C" int idff_debug_train_pair_mode(int32_t on) {
@@ -745,43 +802,36 @@ extern "C" int idff_debug_train_stamps(int64_t* h_out, int32_t n_ctas) {
   return IDFF_OK;
 }
 
-extern "C" int idff_train_flow_init(float* d_state, void* stream) {
-  IDFF_CHECK_ARG(d_state && (reinterpret_cast<uintptr_t>(d_state) & 15) == 0, "idff_train_flow_init: state must be a 16-byte aligned device pointer");
+extern "C" int idff_train_init(int32_t net, float* d_state, void* stream) {
+  IDFF_CHECK_ARG(net == IDFF_TRAIN_NET_FLOW || net == IDFF_TRAIN_NET_SCOREHEAD, "idff_train_init: unknown network %d", net);
+  IDFF_CHECK_ARG(d_state && (reinterpret_cast<uintptr_t>(d_state) & 15) == 0, "idff_train_init: state must be a 16-byte aligned device pointer");
   PtrDeviceGuard guard(d_state);
-  k_train_init<<<(W * W + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_state);
+  if (net == IDFF_TRAIN_NET_FLOW) k_train_init<0><<<(W * W + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_state);
+  else k_train_init<1><<<(W * W + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_state);
   IDFF_CUDA(cudaGetLastError());
   count_launch();
   return IDFF_OK;
 }
+extern "C" int idff_train_flow_init(float* d_state, void* stream) { return idff_train_init(IDFF_TRAIN_NET_FLOW, d_state, stream); }
 
-extern "C" int idff_train_flow_steps(float* d_state, const float* d_x0, const float* d_x1, const float* d_t,
-                                     const float* d_eps, int32_t n_steps, int32_t B, float sigma, int32_t sigma_mode,
-                                     const idff_adamw_t* opt, int64_t steps_done, float* d_loss, float* d_gnorm,
-                                     float* d_grad_dump, void* stream) {
-  IDFF_CHECK_ARG(d_state && (reinterpret_cast<uintptr_t>(d_state) & 15) == 0, "idff_train_flow_steps: state must be a 16-byte aligned device pointer");
-  IDFF_CHECK_ARG(n_steps >= 0 && n_steps <= (1 << 20), "idff_train_flow_steps: n_steps %d outside [0, 2^20]", n_steps);
-  if (n_steps == 0) return IDFF_OK;
-  IDFF_CHECK_ARG(d_x0 && d_x1 && d_t && opt, "idff_train_flow_steps: null pointer");
-  IDFF_CHECK_ARG(((reinterpret_cast<uintptr_t>(d_x0) | reinterpret_cast<uintptr_t>(d_x1) | reinterpret_cast<uintptr_t>(d_eps)) & 7) == 0,
-                 "idff_train_flow_steps: x0, x1, eps must be 8-byte aligned");
-  IDFF_CHECK_ARG(n_steps >= 0 && n_steps <= (1 << 20), "idff_train_flow_steps: n_steps %d outside [0, 2^20]", n_steps);
-  IDFF_CHECK_ARG(B >= RMIN && B <= MAXB && B % RMIN == 0, "idff_train_flow_steps: batch %d must be a multiple of %d in [%d, %d]", B, RMIN, RMIN, MAXB);
-  IDFF_CHECK_ARG(sigma_mode == 0 || sigma_mode == 1, "idff_train_flow_steps: sigma_mode %d", sigma_mode);
-  IDFF_CHECK_ARG(steps_done >= 0, "idff_train_flow_steps: steps_done < 0");
-  if (n_steps == 0) return IDFF_OK;
+template <int NET>
+static int steps_impl(float* d_state, const float* d_x0, const float* d_x1, const float* d_t, const float* d_eps, int32_t n_steps,
+                      int32_t B, float sigma, int32_t sigma_mode, float score_sigma, const idff_adamw_t* opt, int64_t steps_done,
+                      float* d_loss, float* d_gnorm, float* d_grad_dump, void* stream) {
+  using L = Lay<NET>;
   PtrDeviceGuard guard(d_state);
   int dev = guard.dev, sms = 0, coop = 0;
   IDFF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   IDFF_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
   if (!coop || sms < N_JOBS) {
-    set_error("idff_train_flow_steps: needs cooperative launch and >= %d SMs (device has %d)", N_JOBS, sms);
+    set_error("idff_train_steps: needs cooperative launch and >= %d SMs (device has %d)", N_JOBS, sms);
     return IDFF_EUNSUPPORTED;
   }
   int grid = sms < MAX_GRID ? sms : MAX_GRID;
-  static unsigned long long attr_set = 0;   // bit per device: the attribute is per device, not per process
+  static unsigned long long attr_set = 0;   // bit per device: the attribute is per device, not per process (one static per NET)
   if (dev >= 64 || !((attr_set >> dev) & 1ull)) {
-    IDFF_CUDA(cudaFuncSetAttribute(k_train_flow<1, RMIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    IDFF_CUDA(cudaFuncSetAttribute(k_train_flow<2, RMIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    IDFF_CUDA(cudaFuncSetAttribute(k_train_flow<NET, 1, RMIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    if (NET == 0) IDFF_CUDA(cudaFuncSetAttribute(k_train_flow<0, 2, RMIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     if (dev < 64) attr_set |= 1ull << dev;
   }
   Args a;
@@ -789,17 +839,17 @@ extern "C" int idff_train_flow_steps(float* d_state, const float* d_x0, const fl
   a.x0 = d_x0; a.x1 = d_x1; a.t = d_t; a.eps = d_eps;
   a.loss_out = d_loss; a.gnorm_out = d_gnorm; a.grad_dump = d_grad_dump;
   a.B = B; a.n_steps = n_steps; a.steps_done = steps_done;
-  a.sigma = sigma; a.sigma_mode = sigma_mode;
+  a.sigma = sigma; a.sigma_mode = sigma_mode; a.score_sigma = score_sigma;
   a.lr = opt->lr; a.beta1 = opt->beta1; a.beta2 = opt->beta2;
   a.decay = (float)(1.0 - opt->lr * opt->weight_decay);
   a.omb1 = (float)(1.0 - opt->beta1); a.omb2 = (float)(1.0 - opt->beta2);
   a.beta2f = (float)opt->beta2; a.eps_adam = (float)opt->eps; a.clip = (float)opt->max_grad_norm;
   a.b1pow = std::pow(opt->beta1, (double)steps_done); a.b2pow = std::pow(opt->beta2, (double)steps_done);
   cudaStream_t st = (cudaStream_t)stream;
-  IDFF_CUDA(cudaMemsetAsync(d_state + sBAR, 0, 64 * sizeof(float), st));
-  // one CTA per 4 rows by default.  Opt-in (idff_debug_train_pair_mode): a CTA pair (cluster of 2) per 4 rows, each CTA streaming
-  // and computing half of the units -- measured SLOWER (27 vs 25 us/step at B = 256): the five cluster-scope activation
-  // exchanges per step cost more than the halved weight stream and FMA work save
+  IDFF_CUDA(cudaMemsetAsync(d_state + L::sBAR, 0, 64 * sizeof(float), st));
+  // one CTA per 4 rows by default.  Opt-in (idff_debug_train_pair_mode, flow network only): a CTA pair (cluster of 2) per 4 rows,
+  // each CTA streaming and computing half of the units -- measured SLOWER (27 vs 25 us/step at B = 256): the five cluster-scope
+  // activation exchanges per step cost more than the halved weight stream and FMA work save
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeCooperative;
   attr[0].val.cooperative = 1;
@@ -812,20 +862,47 @@ extern "C" int idff_train_flow_steps(float* d_state, const float* d_x0, const fl
   cfg.attrs = attr;
   int pairs = 0;
   const int grid2 = grid & ~1;
-  if (g_pair_mode && 2 * (B / RMIN) <= grid2 && grid2 >= N_JOBS) {
+  if (NET == 0 && g_pair_mode && 2 * (B / RMIN) <= grid2 && grid2 >= N_JOBS) {
     cfg.gridDim = dim3(grid2);
     cfg.numAttrs = 2;
     int ncl = 0;
-    if (cudaOccupancyMaxActiveClusters(&ncl, k_train_flow<2, RMIN>, &cfg) == cudaSuccess && 2 * ncl >= grid2) pairs = 1;
+    if (cudaOccupancyMaxActiveClusters(&ncl, k_train_flow<0, 2, RMIN>, &cfg) == cudaSuccess && 2 * ncl >= grid2) pairs = 1;
     else (void)cudaGetLastError();
   }
   if (pairs) {
-    IDFF_CUDA(cudaLaunchKernelEx(&cfg, k_train_flow<2, RMIN>, a));
+    IDFF_CUDA(cudaLaunchKernelEx(&cfg, k_train_flow<0, 2, RMIN>, a));
   } else {
     cfg.gridDim = dim3(grid);
     cfg.numAttrs = 1;
-    IDFF_CUDA(cudaLaunchKernelEx(&cfg, k_train_flow<1, RMIN>, a));
+    IDFF_CUDA(cudaLaunchKernelEx(&cfg, k_train_flow<NET, 1, RMIN>, a));
   }
   count_launch();
   return IDFF_OK;
+}
+
+extern "C" int idff_train_steps(int32_t net, float* d_state, const float* d_x0, const float* d_x1, const float* d_t,
+                                const float* d_eps, int32_t n_steps, int32_t B, float sigma, int32_t sigma_mode, float score_sigma,
+                                const idff_adamw_t* opt, int64_t steps_done, float* d_loss, float* d_gnorm, float* d_grad_dump,
+                                void* stream) {
+  IDFF_CHECK_ARG(net == IDFF_TRAIN_NET_FLOW || net == IDFF_TRAIN_NET_SCOREHEAD, "idff_train_steps: unknown network %d", net);
+  IDFF_CHECK_ARG(d_state && (reinterpret_cast<uintptr_t>(d_state) & 15) == 0, "idff_train_steps: state must be a 16-byte aligned device pointer");
+  IDFF_CHECK_ARG(n_steps >= 0 && n_steps <= (1 << 20), "idff_train_steps: n_steps %d outside [0, 2^20]", n_steps);
+  if (n_steps == 0) return IDFF_OK;
+  IDFF_CHECK_ARG(d_x0 && d_x1 && d_t && opt, "idff_train_steps: null pointer");
+  IDFF_CHECK_ARG(((reinterpret_cast<uintptr_t>(d_x0) | reinterpret_cast<uintptr_t>(d_x1) | reinterpret_cast<uintptr_t>(d_eps)) & 7) == 0,
+                 "idff_train_steps: x0, x1, eps must be 8-byte aligned");
+  IDFF_CHECK_ARG(B >= RMIN && B <= MAXB && B % RMIN == 0, "idff_train_steps: batch %d must be a multiple of %d in [%d, %d]", B, RMIN, RMIN, MAXB);
+  IDFF_CHECK_ARG(sigma_mode == 0 || sigma_mode == 1, "idff_train_steps: sigma_mode %d", sigma_mode);
+  IDFF_CHECK_ARG(steps_done >= 0, "idff_train_steps: steps_done < 0");
+  if (net == IDFF_TRAIN_NET_FLOW)
+    return steps_impl<0>(d_state, d_x0, d_x1, d_t, d_eps, n_steps, B, sigma, sigma_mode, 0.0f, opt, steps_done, d_loss, d_gnorm, d_grad_dump, stream);
+  return steps_impl<1>(d_state, d_x0, d_x1, d_t, d_eps, n_steps, B, sigma, sigma_mode, score_sigma, opt, steps_done, d_loss, d_gnorm, d_grad_dump, stream);
+}
+
+extern "C" int idff_train_flow_steps(float* d_state, const float* d_x0, const float* d_x1, const float* d_t,
+                                     const float* d_eps, int32_t n_steps, int32_t B, float sigma, int32_t sigma_mode,
+                                     const idff_adamw_t* opt, int64_t steps_done, float* d_loss, float* d_gnorm,
+                                     float* d_grad_dump, void* stream) {
+  return idff_train_steps(IDFF_TRAIN_NET_FLOW, d_state, d_x0, d_x1, d_t, d_eps, n_steps, B, sigma, sigma_mode, 0.0f, opt, steps_done,
+                          d_loss, d_gnorm, d_grad_dump, stream);
 }

@@ -180,33 +180,42 @@ class GraphedMDTrainer:
 
 
 class FusedFlowTrainer:
-    """The reference's 2-D training loop (Autograd_example_order2.py:89-112) on `idff_train_flow_steps`.
+    """The reference's 2-D training loops on the persistent kernel `idff_train_steps`: Autograd_example_order2.py:89-112
+    (MLP(dim=2), flow loss) and, with `score_sigma` given, the order-1 script's step with the score head
+    (example_order1_with_prediction_head.py:111-137: MLP(dim=4, w=256) fed cat[xt, xt, t], flow loss + score regression against
+    log_prob_xt_given_x1_dimwise(.., score_sigma); the script uses data=eight_gaussians_device, lr=1e-3, sigma=0).
 
-    model: torchcfm MLP(dim=2, w=256, time_varying=True) on a CUDA device.  Its parameters are re-pointed at the
+    model: torchcfm MLP(dim=2 | 4, w=256, time_varying=True) on a CUDA device.  Its parameters are re-pointed at the
     kernel's state buffer, so the module (forward, state_dict, PackedWeights.from_module) always sees the trained weights.
         tr = FusedFlowTrainer(model, batch_size=256)
         losses = tr.steps(x0, x1, t, eps)          # [S][B][2], [S][B][2], [S][B], [S][B][2] (eps optional) -> [S] losses
         losses = tr.run(n_steps)                   # draws checkerboard / normal / uniform samples on the device first
     """
 
+    SHAPES = {0: [(256, 3), (256,), (256, 256), (256,), (256, 256), (256,), (2, 256), (2,)],      # MLP(dim=2): flow loss
+              1: [(256, 5), (256,), (256, 256), (256,), (256, 256), (256,), (4, 256), (4,)]}      # MLP(dim=4): score head
+
     def __init__(self, model: torch.nn.Module, batch_size: int = 256, sigma: float = 0.0, lr: float = 2e-4,
                  betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2, clip: float = 1.0,
-                 data=checkerboard_device, exact_ot_sigma: bool = True):
+                 data=checkerboard_device, exact_ot_sigma: bool = True, score_sigma=None):
         L = _lib.lib()
         params = [p for p in model.parameters()]
         shapes = [tuple(p.shape) for p in params]
-        if shapes != [(256, 3), (256,), (256, 256), (256,), (256, 256), (256,), (2, 256), (2,)]:
-            raise _lib.IdffError(f"FusedFlowTrainer serves MLP(dim=2, w=256, time_varying=True) only, got {shapes}; "
+        self.net = 0 if score_sigma is None else 1      # IDFF_TRAIN_NET_FLOW / IDFF_TRAIN_NET_SCOREHEAD
+        if shapes != self.SHAPES[self.net]:
+            raise _lib.IdffError(f"FusedFlowTrainer serves MLP(dim=2, w=256, time_varying=True) with the flow loss and MLP(dim=4, "
+                                 f"w=256, time_varying=True) with score_sigma (the order-1 script's step), got {shapes}; "
                                  "use GraphedFlowTrainer for other networks")
+        self.score_sigma = 0.0 if score_sigma is None else float(score_sigma)
         self.device = params[0].device
         if self.device.type != "cuda":
             raise _lib.IdffError("FusedFlowTrainer needs a CUDA device: idff_b200 has no CPU path")
         self.B = int(batch_size)
         off = (C.c_int64 * 12)()
-        _lib.check(L.idff_train_flow_offsets(off), "idff_train_flow_offsets")
+        _lib.check(L.idff_train_offsets(self.net, off), "idff_train_offsets")
         self.offsets = [int(v) for v in off]
         self.n_params = self.offsets[8]
-        self.state = torch.zeros(int(L.idff_train_flow_state_floats()), device=self.device, dtype=torch.float32)
+        self.state = torch.zeros(int(L.idff_train_state_floats(self.net)), device=self.device, dtype=torch.float32)
         base = self.offsets[9]
         with torch.no_grad():
             for p, o in zip(params, self.offsets[:8]):
@@ -229,7 +238,7 @@ class FusedFlowTrainer:
     def sync_params(self):
         """Rebuild the kernel's streaming weight copies after the parameters were written from outside (load_state_dict,
         manual edits).  `steps` calls it by itself when a parameter's version counter moved since the last launch."""
-        _lib.check(_lib.lib().idff_train_flow_init(_lib.ptr(self.state), _lib.stream_of(self.state)), "idff_train_flow_init")
+        _lib.check(_lib.lib().idff_train_init(self.net, _lib.ptr(self.state), _lib.stream_of(self.state)), "idff_train_init")
         self._versions = [p._version for p in self.model.parameters()]
 
     def _block(self, name):   # parameter-block shaped views: "param", "exp_avg", "exp_avg_sq"
@@ -238,7 +247,7 @@ class FusedFlowTrainer:
 
     def named_block(self, name):
         """The 8 tensors (nn.Linear layout) of the parameter / exp_avg / exp_avg_sq block."""
-        flat, shapes = self._block(name), [(256, 3), (256,), (256, 256), (256,), (256, 256), (256,), (2, 256), (2,)]
+        flat, shapes = self._block(name), self.SHAPES[self.net]
         out = []
         for o, sh in zip(self.offsets[:8], shapes):
             n = 1
@@ -262,10 +271,10 @@ class FusedFlowTrainer:
             self.sync_params()                 # somebody wrote the parameters in place since the last launch
         loss = torch.empty(S, device=self.device, dtype=torch.float32)
         gnorm = torch.empty(S, device=self.device, dtype=torch.float32) if return_gnorm else None
-        _lib.check(_lib.lib().idff_train_flow_steps(
-            _lib.ptr(self.state), _lib.ptr(x0), _lib.ptr(x1), _lib.ptr(t), _lib.ptr(eps), S, B, self.sigma, self.sigma_mode,
-            C.byref(self.opt), self.steps_done, _lib.ptr(loss), _lib.ptr(gnorm), _lib.ptr(grad_dump),
-            _lib.stream_of(self.state)), "idff_train_flow_steps")
+        _lib.check(_lib.lib().idff_train_steps(
+            self.net, _lib.ptr(self.state), _lib.ptr(x0), _lib.ptr(x1), _lib.ptr(t), _lib.ptr(eps), S, B, self.sigma, self.sigma_mode,
+            self.score_sigma, C.byref(self.opt), self.steps_done, _lib.ptr(loss), _lib.ptr(gnorm), _lib.ptr(grad_dump),
+            _lib.stream_of(self.state)), "idff_train_steps")
         self.steps_done += S
         torch.autograd.graph.increment_version(list(self.model.parameters()))   # the kernel wrote them in place
         self._versions = [p._version for p in self.model.parameters()]

@@ -231,6 +231,23 @@ int idff_debug_train_pair_mode(int32_t on);
 int idff_train_flow_steps(float* d_state, const float* d_x0, const float* d_x1, const float* d_t, const float* d_eps,
                           int32_t n_steps, int32_t B, float sigma, int32_t sigma_mode, const idff_adamw_t* opt,
                           int64_t steps_done, float* d_loss, float* d_gnorm, float* d_grad_dump, void* stream);
+/* The same persistent kernel for either network the 2-D scripts train (`net`):
+ *   IDFF_TRAIN_NET_FLOW       MLP(dim=2): cat[xt, t] -> 256 -> 256 -> 256 -> 2, flow loss (the idff_train_flow_* entry points)
+ *   IDFF_TRAIN_NET_SCOREHEAD  the order-1 script's step (example_order1_with_prediction_head.py:111-137): MLP(dim=4):
+ *                             outs = model(cat[xt, xt, t]) (5 -> 256 -> 256 -> 256 -> 4), vt = outs[:, :2], st = outs[:, 2:],
+ *                             loss = mean(((vt - x1) / (1e-2 + 1 - t))^2) + mean((st - logp)^2),
+ *                             logp = log_prob_xt_given_x1_dimwise(xt, x1, x0, t, score_sigma) (:26-51; the script passes sigma
+ *                             where sigma^2 is named, :126), clip_grad_norm_, AdamW.
+ * State size, offsets (0.weight is [256][5], 6.weight [4][256] for the score head) and init per network; the inputs,
+ * outputs and conventions are those of idff_train_flow_steps; score_sigma is ignored by IDFF_TRAIN_NET_FLOW. */
+#define IDFF_TRAIN_NET_FLOW 0
+#define IDFF_TRAIN_NET_SCOREHEAD 1
+int64_t idff_train_state_floats(int32_t net);
+int idff_train_offsets(int32_t net, int64_t* h_out12);
+int idff_train_init(int32_t net, float* d_state, void* stream);
+int idff_train_steps(int32_t net, float* d_state, const float* d_x0, const float* d_x1, const float* d_t, const float* d_eps,
+                     int32_t n_steps, int32_t B, float sigma, int32_t sigma_mode, float score_sigma, const idff_adamw_t* opt,
+                     int64_t steps_done, float* d_loss, float* d_gnorm, float* d_grad_dump, void* stream);
 
 /* ---- OTPlanSampler.get_map for the reference's use (torchcfm/optimal_transport.py:59-94: uniform marginals over
  * two minibatches of EQUAL size n, squared-Euclidean cost, exact plan from pot.emd -- POT's network simplex, un-vendored).  The

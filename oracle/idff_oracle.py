@@ -352,10 +352,13 @@ def flow_loss(vt, x1, t):
     return torch.mean(((1 / (1e-2 + 1 - t[:, None])) * (vt - x1)) ** 2)
 
 
-def train_steps_2d(layers, x0, x1, t, eps, sigma=0.0, lr=2e-4, clip=1.0, return_grads=False):
+def train_steps_2d(layers, x0, x1, t, eps, sigma=0.0, lr=2e-4, clip=1.0, return_grads=False, score_sigma=None):
     """The 2-D training loop, Autograd_example_order2.py:89-112 (= Autograd_example_order3.py:90-109), with the random
     draws passed in: x0, x1, eps [S][B][2], t [S][B].  MLP(dim=2, w=256, time_varying=True) as nn.Sequential of the given
     layers, AdamW(lr) with torch defaults (:80), ExactOT matcher sigma (:81, OT pairing off), clip_grad_norm_(1) (:111).
+    score_sigma not None: the order-1 script's loop instead (example_order1_with_prediction_head.py:111-137) on its
+    MLP(dim=4): outs = net(cat[xt, xt, t]) (:119), vt | st (:120-121), loss = flow_loss + mean((st - logp)^2) with
+    logp = log_prob_xt_given_x1_dimwise(xt, x1, x0, t, score_sigma) (:126-132).
     Returns (per-step losses, per-step total gradient norms, final layers[, unclipped gradients of the last step])."""
     dt = layers[0][0].dtype
     mods = []
@@ -374,8 +377,14 @@ def train_steps_2d(layers, x0, x1, t, eps, sigma=0.0, lr=2e-4, clip=1.0, return_
         optimizer.zero_grad()                                                     # :91
         xt, ut = path_sample(x0[s], x1[s], t[s], eps[s] if eps is not None else torch.zeros_like(x0[s]), sigma, True,
                              ieee_sqrt=True)                                      # :95
-        vt = net(torch.cat([xt, t[s][:, None]], dim=-1))                          # :98
-        loss = flow_loss(vt, x1[s], t[s])                                         # :105
+        if score_sigma is None:
+            vt = net(torch.cat([xt, t[s][:, None]], dim=-1))                      # :98
+            loss = flow_loss(vt, x1[s], t[s])                                     # :105
+        else:
+            outs = net(torch.cat([xt, xt, t[s][:, None]], dim=-1))                # order1:119
+            vt, st = outs[:, :2], outs[:, 2:]                                     # order1:120-121
+            grads_lp = log_prob_xt_given_x1_dimwise(xt, x1[s], x0[s], t[s], score_sigma)   # order1:126
+            loss = flow_loss(vt, x1[s], t[s]) + torch.mean((st - grads_lp) ** 2)  # order1:129-132
         loss.backward()                                                           # :109
         if return_grads and s == t.shape[0] - 1:
             grads = [p.grad.detach().clone() for p in net.parameters()]

@@ -238,3 +238,79 @@ def test_train_then_sample_end_to_end(cuda_device):
     prior, got = compute_mmd_rbf(true_s, x0, 1.0), compute_mmd_rbf(true_s, out, 1.0)
     print(f"8gaussians, 10000 fused training steps, nfe 10: MMD {got:.4f} (prior {prior:.3f})")
     assert prior > 0.4 and got < 0.06
+
+
+def _fresh_scorehead(device, seed=0):
+    from idff_b200.torchcfm.models.models import MLP
+    torch.manual_seed(seed)
+    return MLP(dim=4, w=256, time_varying=True).to(device)     # example_order1_with_prediction_head.py:101
+
+
+@pytest.mark.parametrize("B,sigma", [(256, 0.0), (64, 0.5)])
+def test_scorehead_step_gradients_loss_and_update(cuda_device, B, sigma):
+    """The order-1 script's step (example_order1_with_prediction_head.py:111-137: MLP(dim=4) on cat[xt, xt, t], flow loss +
+    score regression, clip, AdamW lr 1e-3) in the persistent kernel against the oracle's loop on the same weights and draws --
+    the bounds of the flow-network test."""
+    np.random.seed(5)
+    dev, lr, s0 = cuda_device, 1e-3, 0.2
+    model = _fresh_scorehead(dev, seed=B)
+    layers = _layers_of(model)
+    x0, x1, t, eps = _draws(1, B, 13, sigma)
+    losses_r, norms_r, after_r, grads_r = O.train_steps_2d(layers, x0, x1, t, eps, sigma=sigma, lr=lr, return_grads=True, score_sigma=s0)
+    tr = train.FusedFlowTrainer(model, batch_size=B, sigma=sigma, lr=lr, score_sigma=s0)
+    dump = torch.zeros(tr.n_params, device=dev)
+    before = _lib.launch_count()
+    loss, gnorm = tr.steps(x0.to(dev), x1.to(dev), t.to(dev), eps.to(dev) if eps is not None else None, return_gnorm=True,
+                           grad_dump=dump)
+    assert _lib.launch_count() - before == 1
+    assert loss.item() == pytest.approx(losses_r[0], rel=2e-6)
+    assert gnorm.item() == pytest.approx(norms_r[0], rel=2e-6)
+    shapes = [tuple(p.shape) for p in model.parameters()]
+    assert shapes[0] == (256, 5) and shapes[6] == (4, 256)
+    for o, sh, gr in zip(tr.offsets[:8], shapes, grads_r):
+        got = dump[o: o + gr.numel()].view(sh).cpu().numpy()
+        ref = gr.numpy()
+        assert np.abs(got - ref).max() <= 1e-5 * max(np.abs(ref).max(), 1e-12), (sh, np.abs(got - ref).max(), np.abs(ref).max())
+    coef = min(1.0, 1.0 / (norms_r[0] + 1e-6))
+    flat_r = torch.cat([torch.cat([W.reshape(-1), b.reshape(-1)]) for W, b in after_r]).numpy()
+    flat_g = torch.cat([g.reshape(-1) for g in grads_r]).numpy() * coef
+    flat_o = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).cpu().numpy()
+    d = np.abs(flat_o - flat_r)
+    solid = np.abs(flat_g) > 1e-6
+    assert d[solid].max() <= 1e-3 * lr, d[solid].max()
+    assert d.max() <= 2 * lr
+
+
+def test_scorehead_many_steps_and_field(cuda_device):
+    """30 consecutive score-head steps in one launch track the oracle's loop; the trained module then drives the score-head field
+    through the tcgen05 sampler (the packed weights follow the kernel-trained parameters)."""
+    from idff_b200 import fields, sampler
+    np.random.seed(6)
+    dev, lr, s0, S, B = cuda_device, 1e-3, 0.2, 30, 256
+    model = _fresh_scorehead(dev, seed=3)
+    layers = _layers_of(model)
+    x0, x1, t, eps = _draws(S, B, 23, 0.0)
+    losses_r, norms_r, after_r = O.train_steps_2d(layers, x0, x1, t, eps, sigma=0.0, lr=lr, score_sigma=s0)
+    tr = train.FusedFlowTrainer(model, batch_size=B, lr=lr, score_sigma=s0)
+    loss = tr.steps(x0.to(dev), x1.to(dev), t.to(dev), None).cpu().numpy()
+    np.testing.assert_allclose(loss, np.array(losses_r), rtol=2e-4)
+    flat_r = torch.cat([torch.cat([W.reshape(-1), b.reshape(-1)]) for W, b in after_r]).numpy()
+    flat_o = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).cpu().numpy()
+    d = np.abs(flat_o - flat_r)
+    assert np.median(d) <= 1e-6 and d.max() <= 5 * lr, (np.median(d), d.max())
+    # bit-reproducible, independent of the launch split
+    model2 = _fresh_scorehead(dev, seed=3)
+    tr2 = train.FusedFlowTrainer(model2, batch_size=B, lr=lr, score_sigma=s0)
+    la = tr2.steps(x0[:11].to(dev), x1[:11].to(dev), t[:11].to(dev), None)
+    lb = tr2.steps(x0[11:].to(dev), x1[11:].to(dev), t[11:].to(dev), None)
+    assert np.array_equal(torch.cat([la, lb]).cpu().numpy(), loss)
+    for p, q in zip(model.parameters(), model2.parameters()):
+        assert torch.equal(p, q)
+    # the trained module as base_model of the score-head field
+    m = fields.CustomNetModelScoreHead(model, 0.2, 0.2, 0.2)
+    xs = torch.randn(4096, 2, device=dev) / 1.5
+    out = sampler.sample_rk4(m, xs, torch.linspace(0, 1, 3))
+    ref_layers = _layers_of(model)
+    ref = O.odeint_rk4(O.FieldScoreHead(ref_layers, 0.2, (0.2, 0.2)), xs.cpu(), torch.linspace(0, 1, 3))[-1]
+    dd = (out.cpu() - ref).abs()
+    assert dd.median().item() <= 1e-5 and dd.quantile(0.999).item() <= 1e-3
