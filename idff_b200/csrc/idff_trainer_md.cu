@@ -1,0 +1,510 @@
+// The PolyALA training step (TrajectoryGenerator.train_model, timeseris_example/MD_simulation.py:117-144) as ONE persistent kernel
+// on a thread-block CLUSTER of 8 CTAs whose shared memories hold the whole training state.
+//
+// Reference step (batch_size = 10, MD_simulation.py:544):
+//   index_sel = randint(1, T, (B,)); x0 = dataset[index_sel - 1]; x1 = dataset[index_sel]                      :128-130
+//   t, xt, ut, eps = FM.sample_location_and_conditional_flow(x0, x1)      ExactOT matcher, sigma 0.5            :121,132
+//   vt = model(cat[xt, t], index_sel)         MLP_Embedding: cat[xt, t, Embedding(T,128)[idx]] (175) -> 128 -> 128 -> 128 -> 46   :135
+//   loss = mean((vt - x1)^2) + mean((vt - (x1 + 360))^2) + mean((vt - (x1 - 360))^2)                            :137-141
+//   loss.backward(); Adam().step()            torch.optim.Adam defaults, no clipping                            :119,143-144
+//
+// At batch 10 the step is 87 086 parameters and 3.6 MFLOP: pure latency (~70 torch kernels; 300 us even as a CUDA graph).  Here the
+// parameters AND both Adam moments (3 x 348 KB) live in the shared memory of 8 CTAs for the whole launch, `n_steps` steps run back to
+// back, and nothing but the step's inputs (a few KB) is read from global memory:
+//   * CTA c owns hidden units [16c, 16c+16) of every hidden layer (rows of W0, W1, W2 with their biases), outputs [6c, 6c+6) (rows of
+//     W3) and columns [16c, 16c+16) of the embedding table -- parameter, exp_avg and exp_avg_sq side by side.
+//   * forward:  a layer's input activations [B][128] are complete in every CTA; a CTA computes its 16 units and PUSHES them into the
+//     8 activation buffers of the cluster (st.shared::cluster, 16-byte stores), one hardware cluster barrier per layer.
+//   * backward: dA_{l-1}[r][k] = sum_j dZ_l[r][j] W_l[j][k] is a sum over all units j: a CTA forms the partial sums of its 16 units for
+//     all k and scatters them to the owners of k (reduce-scatter through distributed shared memory, fixed summation order ->
+//     bit-reproducible); the owner applies SELU' (derivative codes kept from the forward pass).
+//   * weight gradients never leave their owner: dW_l[j][k] = sum_r dZ_l[r][j] a_{l-1}[r][k] needs only the owner's dZ rows and the
+//     (complete) activations; Adam (torch's operation order, bias corrections in double) is applied in the same thread, right after the
+//     layer's backward-data partials have been formed from the old weights.  No gradient norm, so no other cross-CTA reduction.
+//   * the embedding rows of the batch are gathered by the column owners and pushed like activations; their gradient comes back through
+//     the same reduce-scatter (duplicated indices accumulate in row order); the dense Adam update touches all T rows, as torch does.
+// 8 cluster barriers per step.  Parameters are read from / written back to the caller's state buffer (nn.Module layout, so the torch
+// parameters can alias it) at the start / end of a launch.
+#include <cmath>
+
+#include "idff_common.cuh"
+
+namespace idff {
+namespace tmd {
+
+constexpr int W = 128, CL = 8, UPC = 16, NT = 512, BMAX = IDFF_TRAIN_MD_MAX_BATCH, DMAX = 47, DP = 48, TMAX = IDFF_TRAIN_MD_MAX_FRAMES;
+constexpr int OPC = 6;                // outputs per CTA (ceil(47 / 8))
+constexpr int K0P = DP + W;           // layer-0 input as laid out on chip: [x (D) | t | zero pad to 48 | embedding (128)]
+constexpr int W0S = K0P + 4, WS = W + 4;   // row strides of the weight slices (bank spread for 16 rows read at once)
+constexpr int C0S = K0P + 4;          // row stride of the layer-0 input rows
+
+// shared-memory plan (floats).  Parameter slices: three copies (param, exp_avg, exp_avg_sq) `PT` apart.
+constexpr int pW0 = 0, pb0 = pW0 + UPC * W0S, pW1 = pb0 + UPC, pb1 = pW1 + UPC * WS, pW2 = pb1 + UPC, pb2 = pW2 + UPC * WS,
+              pW3 = pb2 + UPC, pb3 = pW3 + OPC * WS, pE = pb3 + 8, PT = pE + TMAX * UPC;
+constexpr int mCAT = 3 * PT, mA1 = mCAT + BMAX * C0S, mA2 = mA1 + BMAX * W, mA3 = mA2 + BMAX * W, mX1 = mA3 + BMAX * W,
+              mDVT = mX1 + BMAX * DP, mCODE = mDVT + BMAX * 8, mDZ = mCODE + 3 * BMAX * UPC, mSTG = mDZ + BMAX * UPC,
+              mRECV = mSTG + BMAX * UPC, mCOMB = mRECV + 2 * CL * BMAX * UPC, mLT = mCOMB + NT, mLRECV = mLT + BMAX * 8 * 3,
+              mMISC = mLRECV + CL * 3 * 2, mTOTAL = mMISC + 64;
+constexpr size_t kSmemBytes = (size_t)mTOTAL * sizeof(float);
+static_assert(kSmemBytes <= 232448, "shared memory budget");
+static_assert(mLRECV % 2 == 0 && mMISC % 2 == 0, "8-byte aligned slots");
+
+struct Args {
+  float* S;                 // state: [param block | exp_avg | exp_avg_sq], each NPP floats
+  const float* dataset;     // [T][D]
+  const long long* idx;     // [n_steps][B]
+  const float *t, *eps;     // [n_steps][B], [n_steps][B][D] (eps may be null)
+  float *loss_out, *grad_dump;
+  int B, D, T, n_steps;
+  long long npp;            // floats per block of the state
+  float sigma;
+  int sigma_mode;
+  double lr, beta1, beta2, b1pow, b2pow;
+  float omb1, omb2, beta2f, eps_adam;
+};
+
+// parameter-block offsets (module.parameters() order of MLP_Embedding: time_index_embedding.weight, net.0.weight, net.0.bias, ...)
+struct Off {
+  int K0, oE, oW0, ob0, oW1, ob1, oW2, ob2, oW3, ob3, NP;
+  __host__ __device__ explicit Off(int D, int T) {
+    K0 = D + 1 + W;
+    oE = 0; oW0 = oE + T * W; ob0 = oW0 + W * K0; oW1 = ob0 + W; ob1 = oW1 + W * W; oW2 = ob1 + W; ob2 = oW2 + W * W;
+    oW3 = ob2 + W; ob3 = oW3 + D * W; NP = ob3 + D;
+  }
+};
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster4(uint32_t addr, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_cluster_f64(uint32_t addr, double v) {
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+
+__device__ __forceinline__ float selu_d1(float code) { return code < 0.0f ? kSeluLambda : code; }
+
+// torch.optim.Adam (single tensor, weight_decay 0): exp_avg.lerp_(g, 1 - b1); exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2);
+// denom = sqrt(v) / sqrt(bc2) + eps; p -= (lr / bc1) * m / denom
+struct AdamK {
+  float omb1, omb2, beta2f, eps, step_size, bc2_sqrt;
+};
+__device__ __forceinline__ void adam1(const AdamK& k, float g, float& p, float& m, float& v) {
+  m = fmaf(g - m, k.omb1, m);
+  v = fmaf(k.omb2 * g, g, v * k.beta2f);
+  const float denom = sqrtf(v) / k.bc2_sqrt + k.eps;
+  p = p - k.step_size * (m / denom);
+}
+
+// ---- one hidden layer forward for this CTA's 16 units: thread (kh, r, u) sums half of K; a = selu(z) goes to `stg` [r][u], the
+// derivative code to `code` [r][u].  in: [BMAX][is] (complete), Wp: [16][ws] (K4 float4 per row used), bias [16].
+__device__ __forceinline__ void fwd_units(const float* in, int is, int K4, const float* Wp, int ws, const float* bias, float* comb,
+                                          float* stg, float* code, int tid) {
+  const int kh = tid >> 8, r = (tid >> 4) & 15, u = tid & 15;
+  const int half = (K4 + 1) >> 1, k0 = kh * half, k1 = min(K4, k0 + half);
+  const float4* w4 = reinterpret_cast<const float4*>(Wp + u * ws);
+  const float4* a4 = reinterpret_cast<const float4*>(in + r * is);
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll 4
+  for (int k = k0; k < k1; ++k) {
+    const float4 w = w4[k], a = a4[k];
+    acc0 = fmaf(a.x, w.x, acc0); acc1 = fmaf(a.y, w.y, acc1); acc2 = fmaf(a.z, w.z, acc2); acc3 = fmaf(a.w, w.w, acc3);
+  }
+  comb[tid] = (acc0 + acc1) + (acc2 + acc3);
+  __syncthreads();
+  if (tid < 256) {
+    const float z = (comb[tid] + comb[tid + 256]) + bias[u];
+    float c;
+    stg[r * UPC + u] = selu_fwd(z, c);
+    code[r * UPC + u] = c;
+  }
+  __syncthreads();
+}
+
+// push stg [B][16] into column block `rank` of the [BMAX][stride] buffer at shared offset `dst_off` (+ col0) of every CTA
+__device__ __forceinline__ void push_units(const float* stg, int B, uint32_t dst_saddr, int stride, int col0, uint32_t rank, int tid) {
+  if (tid < 64 * CL) {
+    const int peer = tid >> 6, r = (tid >> 2) & 15, u4 = tid & 3;
+    if (r < B) {
+      const float4 v = *reinterpret_cast<const float4*>(stg + r * UPC + 4 * u4);
+      st_cluster4(mapa(dst_saddr + (uint32_t)((r * stride + col0 + (int)rank * UPC + 4 * u4) * 4), (uint32_t)peer), v);
+    }
+  }
+}
+
+// partial sums of the backward-data product over this CTA's J rows: out[r][k] = sum_{j<J} dz[r][j] * Wp[j][wc0 + k], k < 128,
+// scattered to the owners of k: recv[rank][r][k % 16] of CTA k / 16.  ALIGNED: wc0 is a multiple of 4 floats.
+template <bool ALIGNED>
+__device__ __forceinline__ void partial_scatter(const float* dz, int dzs, int J, const float* Wp, int ws, int wc0, int B,
+                                                uint32_t recv_saddr, uint32_t rank, int tid) {
+  const int r = tid >> 5, kq = tid & 31;
+  if (r < B) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < J; ++j) {
+      const float d = dz[r * dzs + j];
+      float4 w;
+      if (ALIGNED) {
+        w = *reinterpret_cast<const float4*>(Wp + j * ws + wc0 + 4 * kq);
+      } else {
+        const float* wp = Wp + j * ws + wc0 + 4 * kq;
+        w = make_float4(wp[0], wp[1], wp[2], wp[3]);
+      }
+      acc.x = fmaf(d, w.x, acc.x); acc.y = fmaf(d, w.y, acc.y); acc.z = fmaf(d, w.z, acc.z); acc.w = fmaf(d, w.w, acc.w);
+    }
+    st_cluster4(mapa(recv_saddr + (uint32_t)((((int)rank * BMAX + r) * UPC + 4 * (kq & 3)) * 4), (uint32_t)(kq >> 2)), acc);
+  }
+}
+
+// dst[r][u] = (sum over the 8 sources of recv[src][r][u]) [* selu'(code[r][u])], r < B; rows >= B are left alone (zero)
+__device__ __forceinline__ void gather_recv(const float* recv, const float* code, float* dst, int B, int tid) {
+  if (tid < 256) {
+    const int r = tid >> 4, u = tid & 15;
+    if (r < B) {
+      float s = recv[r * UPC + u];
+#pragma unroll
+      for (int c = 1; c < CL; ++c) s += recv[(c * BMAX + r) * UPC + u];
+      dst[r * UPC + u] = code ? s * selu_d1(code[r * UPC + u]) : s;
+    }
+  }
+}
+
+// weight gradient of J rows x K4 float4 columns, dW[j][k] = sum_{r<B} dz[r][j] * act[r][k], and Adam on the owner's copies.
+// gidx(j, k) -> index in the parameter block (for the gradient dump) or -1 for padding columns.
+template <class GI>
+__device__ __forceinline__ void wgrad_adam(const float* dz, int dzs, int J, const float* act, int as, int K4, float* P, int ws, int B,
+                                           const AdamK& ak, float* dump, GI gidx, int tid) {
+  for (int it = tid; it < J * K4; it += NT) {
+    const int j = it / K4, k4 = it - j * K4;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < B; ++r) {
+      const float d = dz[r * dzs + j];
+      const float4 a = *reinterpret_cast<const float4*>(act + r * as + 4 * k4);
+      g.x = fmaf(d, a.x, g.x); g.y = fmaf(d, a.y, g.y); g.z = fmaf(d, a.z, g.z); g.w = fmaf(d, a.w, g.w);
+    }
+    float4* p4 = reinterpret_cast<float4*>(P + j * ws + 4 * k4);
+    float4* m4 = reinterpret_cast<float4*>(P + PT + j * ws + 4 * k4);
+    float4* v4 = reinterpret_cast<float4*>(P + 2 * PT + j * ws + 4 * k4);
+    float4 p = *p4, m = *m4, v = *v4;
+    adam1(ak, g.x, p.x, m.x, v.x); adam1(ak, g.y, p.y, m.y, v.y); adam1(ak, g.z, p.z, m.z, v.z); adam1(ak, g.w, p.w, m.w, v.w);
+    *p4 = p; *m4 = m; *v4 = v;
+    if (dump) {
+      const float gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int ix = gidx(j, 4 * k4 + c);
+        if (ix >= 0) dump[ix] = gg[c];
+      }
+    }
+  }
+}
+__device__ __forceinline__ void bgrad_adam(const float* dz, int dzs, int J, float* P, int B, const AdamK& ak, float* dump, int gbase,
+                                           int tid) {
+  if (tid < J) {
+    float g = 0.f;
+    for (int r = 0; r < B; ++r) g += dz[r * dzs + tid];
+    adam1(ak, g, P[tid], P[PT + tid], P[2 * PT + tid]);
+    if (dump) dump[gbase + tid] = g;
+  }
+}
+
+// chip column c of the layer-0 input <-> column of net.0.weight: [x (D) | t] first, the embedding after the pad
+__device__ __forceinline__ int w0_col(int c, int D) { return c <= D ? c : (c >= DP ? c - (DP - (D + 1)) : -1); }
+
+// copy this CTA's slices between the state buffer and shared memory (dir 0: load P, M, V; dir 1: store)
+__device__ void move_params(const Args& a, const Off& o, float* sm, uint32_t rank, int n_own, int dir, int tid) {
+  const int D = a.D, T = a.T, K0 = o.K0;
+  for (int b = 0; b < 3; ++b) {
+    float* G = a.S + (size_t)b * a.npp;
+    float* L = sm + b * PT;
+    auto mv = [&](int li, int gi) {
+      if (dir == 0) L[li] = gi >= 0 ? G[gi] : 0.0f;
+      else if (gi >= 0) G[gi] = L[li];
+    };
+    for (int i = tid; i < UPC * K0P; i += NT) {
+      const int j = i / K0P, c = i - j * K0P, gc = w0_col(c, D);
+      mv(pW0 + j * W0S + c, gc >= 0 ? o.oW0 + ((int)rank * UPC + j) * K0 + gc : -1);
+    }
+    for (int i = tid; i < UPC * W; i += NT) {
+      const int j = i >> 7, c = i & 127;
+      mv(pW1 + j * WS + c, o.oW1 + ((int)rank * UPC + j) * W + c);
+      mv(pW2 + j * WS + c, o.oW2 + ((int)rank * UPC + j) * W + c);
+    }
+    for (int i = tid; i < OPC * W; i += NT) {
+      const int j = i >> 7, c = i & 127;
+      mv(pW3 + j * WS + c, j < n_own ? o.oW3 + ((int)rank * OPC + j) * W + c : -1);
+    }
+    if (tid < UPC) {
+      mv(pb0 + tid, o.ob0 + (int)rank * UPC + tid);
+      mv(pb1 + tid, o.ob1 + (int)rank * UPC + tid);
+      mv(pb2 + tid, o.ob2 + (int)rank * UPC + tid);
+    }
+    if (tid < 8) mv(pb3 + tid, tid < n_own ? o.ob3 + (int)rank * OPC + tid : -1);
+    for (int i = tid; i < T * UPC; i += NT) {
+      const int row = i >> 4, e = i & 15;
+      mv(pE + row * UPC + e, o.oE + row * W + (int)rank * UPC + e);
+    }
+  }
+}
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(const Args a) {
+  extern __shared__ __align__(16) float sm[];
+  const int tid = threadIdx.x, B = a.B, D = a.D, T = a.T;
+  const uint32_t rank = cluster_ctarank();
+  const Off o(D, T);
+  const int n_own = max(0, min(OPC, D - (int)rank * OPC));   // outputs [6 rank, 6 rank + n_own)
+  float* cat0 = sm + mCAT;     // [BMAX][C0S]: x (D), t, pad, embedding row (128 at column DP)
+  float* a1 = sm + mA1; float* a2 = sm + mA2; float* a3 = sm + mA3;
+  float* x1s = sm + mX1;       // [BMAX][DP]
+  float* dvt = sm + mDVT;      // [BMAX][8]
+  float* code = sm + mCODE;    // [3][BMAX][16]
+  float* dz = sm + mDZ;        // [BMAX][16]
+  float* stg = sm + mSTG;      // [BMAX][16]
+  float* recv = sm + mRECV;    // [2][CL][BMAX][16]
+  float* comb = sm + mCOMB;
+  float* lt = sm + mLT;        // [BMAX][8][3]
+  double* lrecv = reinterpret_cast<double*>(sm + mLRECV);   // [CL][3] (CTA 0)
+  int* idxs = reinterpret_cast<int*>(sm + mMISC);           // [BMAX]
+  float* sc = sm + mMISC + 32;                              // step_size, bc2_sqrt
+
+  for (int i = tid; i < mTOTAL - 3 * PT; i += NT) sm[3 * PT + i] = 0.0f;
+  move_params(a, o, sm, rank, n_own, 0, tid);
+  __syncthreads();
+  cluster_sync_all();   // every CTA's buffers are initialised before the first push arrives
+
+  const int n_el = B * D;   // (row, dim) elements of a batch: up to 2 per thread
+  float px0[2], px1[2], pep[2], ptt[2];
+  int pidx[2];
+  auto prefetch = [&](int s) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = tid + q * NT;
+      if (e < n_el) {
+        const int r = e / D, d = e - r * D;
+        long long ix = a.idx[(size_t)s * B + r];
+        ix = ix < 1 ? 1 : (ix > T - 1 ? T - 1 : ix);   // frames [1, T): randint(1, T) in the reference (torch would raise outside)
+        pidx[q] = (int)ix;
+        px0[q] = a.dataset[(size_t)(ix - 1) * D + d];
+        px1[q] = a.dataset[(size_t)ix * D + d];
+        pep[q] = a.eps ? a.eps[((size_t)s * B + r) * D + d] : 0.0f;
+        ptt[q] = a.t[(size_t)s * B + r];
+      }
+    }
+  };
+  if (a.n_steps > 0) prefetch(0);
+  double b1pow = a.b1pow, b2pow = a.b2pow;
+  const uint32_t cat_s = s32(cat0), a1_s = s32(a1), a2_s = s32(a2), a3_s = s32(a3), recv_s = s32(recv);
+
+  for (int s = 0; s < a.n_steps; ++s) {
+    float* dump = (a.grad_dump && s == a.n_steps - 1) ? a.grad_dump : nullptr;
+    // ---- phase 0: path sample (conditional_flow_matching.py:98-123, no contraction), embedding gather + push
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = tid + q * NT;
+      if (e < n_el) {
+        const int r = e / D, d = e - r * D;
+        const float t = ptt[q];
+        const float st = a.sigma_mode == 0 ? a.sigma : __fmul_rn(a.sigma, __fsqrt_rn(__fmul_rn(t, __fsub_rn(1.0f, t))));
+        const float xt = __fadd_rn(__fadd_rn(__fmul_rn(t, px1[q]), __fmul_rn(__fsub_rn(1.0f, t), px0[q])), __fmul_rn(st, pep[q]));
+        cat0[r * C0S + d] = xt;
+        x1s[r * DP + d] = px1[q];
+        if (d == 0) { cat0[r * C0S + D] = t; idxs[r] = pidx[q]; }
+      }
+    }
+    if (tid == 0) {
+      b1pow *= a.beta1;
+      b2pow *= a.beta2;
+      sc[0] = (float)(a.lr / (1.0 - b1pow));
+      sc[1] = (float)sqrt(1.0 - b2pow);
+    }
+    __syncthreads();
+    if (s + 1 < a.n_steps) prefetch(s + 1);   // in flight for the whole step
+    AdamK ak;
+    ak.omb1 = a.omb1; ak.omb2 = a.omb2; ak.beta2f = a.beta2f; ak.eps = a.eps_adam; ak.step_size = sc[0]; ak.bc2_sqrt = sc[1];
+    if (tid < 64) {   // this CTA's 16 embedding columns of the batch rows -> stg
+      const int r = tid >> 2, u4 = tid & 3;
+      if (r < B) *reinterpret_cast<float4*>(stg + r * UPC + 4 * u4) = *reinterpret_cast<const float4*>(sm + pE + idxs[r] * UPC + 4 * u4);
+    }
+    __syncthreads();
+    push_units(stg, B, cat_s, C0S, DP, rank, tid);
+    cluster_sync_all();                                                                   // barrier 1
+    // ---- forward
+    fwd_units(cat0, C0S, K0P / 4, sm + pW0, W0S, sm + pb0, comb, stg, code, tid);
+    push_units(stg, B, a1_s, W, 0, rank, tid);
+    cluster_sync_all();                                                                   // barrier 2
+    fwd_units(a1, W, W / 4, sm + pW1, WS, sm + pb1, comb, stg, code + BMAX * UPC, tid);
+    push_units(stg, B, a2_s, W, 0, rank, tid);
+    cluster_sync_all();                                                                   // barrier 3
+    fwd_units(a2, W, W / 4, sm + pW2, WS, sm + pb2, comb, stg, code + 2 * BMAX * UPC, tid);
+    push_units(stg, B, a3_s, W, 0, rank, tid);
+    cluster_sync_all();                                                                   // barrier 4
+    // ---- output layer (this CTA's outputs), periodic loss (MD_simulation.py:137-141) and d loss / d vt
+    {
+      const int i8 = tid >> 2, ks = tid & 3, r = i8 >> 3, oo = i8 & 7;
+      const bool valid = r < B && oo < n_own;
+      float acc = 0.f;
+      if (valid) {
+        const float4* w4 = reinterpret_cast<const float4*>(sm + pW3 + oo * WS);
+        const float4* a4 = reinterpret_cast<const float4*>(a3 + r * W);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 w = w4[ks + 4 * i], av = a4[ks + 4 * i];
+          acc = fmaf(av.x, w.x, acc); acc = fmaf(av.y, w.y, acc); acc = fmaf(av.z, w.z, acc); acc = fmaf(av.w, w.w, acc);
+        }
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (ks == 0) {
+        float d = 0.f, l0 = 0.f, l1 = 0.f, l2 = 0.f;
+        if (valid) {
+          const float vt = acc + sm[pb3 + oo];
+          const float b1 = x1s[r * DP + (int)rank * OPC + oo];
+          const float r0 = __fsub_rn(vt, b1), r1 = __fsub_rn(vt, __fadd_rn(b1, 360.0f)), r2 = __fsub_rn(vt, __fsub_rn(b1, 360.0f));
+          l0 = __fmul_rn(r0, r0); l1 = __fmul_rn(r1, r1); l2 = __fmul_rn(r2, r2);
+          d = 2.0f * (r0 + r1 + r2) * (1.0f / (float)(B * D));
+        }
+        dvt[r * 8 + oo] = d;
+        lt[(r * 8 + oo) * 3 + 0] = l0; lt[(r * 8 + oo) * 3 + 1] = l1; lt[(r * 8 + oo) * 3 + 2] = l2;
+      }
+    }
+    __syncthreads();
+    if (tid < 3) {   // this CTA's share of the three loss sums, fixed order -> CTA 0
+      double sum = 0.0;
+      for (int i = 0; i < B * 8; ++i) sum += (double)lt[i * 3 + tid];
+      st_cluster_f64(mapa(s32(lrecv + (int)rank * 3 + tid), 0u), sum);
+    }
+    partial_scatter<true>(dvt, 8, n_own, sm + pW3, WS, 0, B, recv_s, rank, tid);                       // -> recv[0]
+    __syncthreads();   // W3 has been read by the partial products
+    wgrad_adam(dvt, 8, n_own, a3, W, W / 4, sm + pW3, WS, B, ak, dump,
+               [&](int j, int c) { return o.oW3 + ((int)rank * OPC + j) * W + c; }, tid);
+    bgrad_adam(dvt, 8, n_own, sm + pb3, B, ak, dump, o.ob3 + (int)rank * OPC, tid);
+    cluster_sync_all();                                                                   // barrier 5
+    if (rank == 0 && tid == 0 && a.loss_out) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+      for (int c = 0; c < CL; ++c) { s0 += lrecv[c * 3]; s1 += lrecv[c * 3 + 1]; s2 += lrecv[c * 3 + 2]; }
+      const double n = (double)(B * D);
+      a.loss_out[s] = ((float)(s0 / n) + (float)(s1 / n)) + (float)(s2 / n);
+    }
+    // ---- backward through layers 3, 2 (dZ of the owner's units, partials of the next dA, weight gradients + Adam)
+    gather_recv(recv, code + 2 * BMAX * UPC, dz, B, tid);
+    __syncthreads();
+    partial_scatter<true>(dz, UPC, UPC, sm + pW2, WS, 0, B, recv_s + CL * BMAX * UPC * 4, rank, tid);   // -> recv[1]
+    __syncthreads();
+    wgrad_adam(dz, UPC, UPC, a2, W, W / 4, sm + pW2, WS, B, ak, dump,
+               [&](int j, int c) { return o.oW2 + ((int)rank * UPC + j) * W + c; }, tid);
+    bgrad_adam(dz, UPC, UPC, sm + pb2, B, ak, dump, o.ob2 + (int)rank * UPC, tid);
+    cluster_sync_all();                                                                   // barrier 6
+    gather_recv(recv + CL * BMAX * UPC, code + BMAX * UPC, dz, B, tid);
+    __syncthreads();
+    partial_scatter<true>(dz, UPC, UPC, sm + pW1, WS, 0, B, recv_s, rank, tid);                        // -> recv[0]
+    __syncthreads();
+    wgrad_adam(dz, UPC, UPC, a1, W, W / 4, sm + pW1, WS, B, ak, dump,
+               [&](int j, int c) { return o.oW1 + ((int)rank * UPC + j) * W + c; }, tid);
+    bgrad_adam(dz, UPC, UPC, sm + pb1, B, ak, dump, o.ob1 + (int)rank * UPC, tid);
+    cluster_sync_all();                                                                   // barrier 7
+    // ---- layer 1: dZ1; the gradient of the embedding inputs goes back to the column owners; dW0 over the whole input row
+    gather_recv(recv, code, dz, B, tid);
+    __syncthreads();
+    partial_scatter<true>(dz, UPC, UPC, sm + pW0, W0S, DP, B, recv_s + CL * BMAX * UPC * 4, rank, tid);   // -> recv[1]
+    __syncthreads();
+    wgrad_adam(dz, UPC, UPC, cat0, C0S, K0P / 4, sm + pW0, W0S, B, ak, dump,
+               [&](int j, int c) { const int gc = w0_col(c, D); return gc >= 0 ? o.oW0 + ((int)rank * UPC + j) * o.K0 + gc : -1; }, tid);
+    bgrad_adam(dz, UPC, UPC, sm + pb0, B, ak, dump, o.ob0 + (int)rank * UPC, tid);
+    cluster_sync_all();                                                                   // barrier 8
+    // ---- embedding: gradient rows of the batch (duplicates accumulate in row order), dense Adam over all T rows
+    gather_recv(recv + CL * BMAX * UPC, nullptr, dz, B, tid);
+    __syncthreads();
+    for (int it = tid; it < T * UPC; it += NT) {
+      const int row = it >> 4, e = it & 15;
+      float g = 0.f;
+      for (int r = 0; r < B; ++r)
+        if (idxs[r] == row) g += dz[r * UPC + e];
+      float* p = sm + pE + it;
+      adam1(ak, g, p[0], p[PT], p[2 * PT]);
+      if (dump) dump[o.oE + row * W + (int)rank * UPC + e] = g;
+    }
+    __syncthreads();
+  }
+  move_params(a, o, sm, rank, n_own, 1, tid);
+  cluster_sync_all();   // no CTA exits while a peer may still push into it
+}
+
+}  // namespace tmd
+}  // namespace idff
+
+using namespace idff;
+using namespace idff::tmd;
+
+static int check_md_shape(int32_t D, int32_t T, const char* who) {
+  IDFF_CHECK_ARG(D >= 1 && D <= DMAX, "%s: state dimension %d outside [1, %d]", who, D, DMAX);
+  IDFF_CHECK_ARG(T >= 2 && T <= TMAX, "%s: %d frames outside [2, %d]", who, T, TMAX);
+  return IDFF_OK;
+}
+
+extern "C" int64_t idff_train_md_state_floats(int32_t D, int32_t T) {
+  if (check_md_shape(D, T, "idff_train_md_state_floats")) return -1;
+  const Off o(D, T);
+  return 3 * (int64_t)((o.NP + 63) / 64 * 64);
+}
+
+extern "C" int idff_train_md_offsets(int32_t D, int32_t T, int64_t* h_out13) {
+  IDFF_CHECK_ARG(h_out13, "idff_train_md_offsets: null pointer");
+  int rc = check_md_shape(D, T, "idff_train_md_offsets");
+  if (rc) return rc;
+  const Off o(D, T);
+  const int64_t npp = (o.NP + 63) / 64 * 64;
+  const int64_t v[13] = {o.oE, o.oW0, o.ob0, o.oW1, o.ob1, o.oW2, o.ob2, o.oW3, o.ob3, o.NP, 0, npp, 2 * npp};
+  for (int i = 0; i < 13; ++i) h_out13[i] = v[i];
+  return IDFF_OK;
+}
+
+extern "C" int idff_train_md_steps(float* d_state, const float* d_dataset, int32_t T, int32_t D, const int64_t* d_idx,
+                                   const float* d_t, const float* d_eps, int32_t n_steps, int32_t B, float sigma,
+                                   int32_t sigma_mode, const idff_adamw_t* opt, int64_t steps_done, float* d_loss,
+                                   float* d_grad_dump, void* stream) {
+  int rc = check_md_shape(D, T, "idff_train_md_steps");
+  if (rc) return rc;
+  IDFF_CHECK_ARG(d_state && (reinterpret_cast<uintptr_t>(d_state) & 15) == 0, "idff_train_md_steps: state must be a 16-byte aligned device pointer");
+  IDFF_CHECK_ARG(n_steps >= 0 && n_steps <= (1 << 20), "idff_train_md_steps: n_steps %d outside [0, 2^20]", n_steps);
+  if (n_steps == 0) return IDFF_OK;
+  IDFF_CHECK_ARG(d_dataset && d_idx && d_t && opt, "idff_train_md_steps: null pointer");
+  IDFF_CHECK_ARG(B >= 1 && B <= BMAX, "idff_train_md_steps: batch %d outside [1, %d]", B, BMAX);
+  IDFF_CHECK_ARG(sigma_mode == 0 || sigma_mode == 1, "idff_train_md_steps: sigma_mode %d", sigma_mode);
+  IDFF_CHECK_ARG(steps_done >= 0, "idff_train_md_steps: steps_done < 0");
+  IDFF_CHECK_ARG(opt->weight_decay == 0.0 && opt->max_grad_norm <= 0.0,
+                 "idff_train_md_steps: the PolyALA loop uses torch.optim.Adam without weight decay or clipping (MD_simulation.py:119,143-144)");
+  PtrDeviceGuard guard(d_state);
+  int cl = 0;
+  IDFF_CUDA(cudaDeviceGetAttribute(&cl, cudaDevAttrClusterLaunch, guard.dev));
+  if (!cl) {
+    set_error("idff_train_md_steps: the device does not support thread-block clusters");
+    return IDFF_EUNSUPPORTED;
+  }
+  IDFF_CUDA(cudaFuncSetAttribute(k_train_md, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+  const Off o(D, T);
+  Args a;
+  memset(&a, 0, sizeof(a));
+  a.S = d_state; a.dataset = d_dataset; a.idx = reinterpret_cast<const long long*>(d_idx); a.t = d_t; a.eps = d_eps;
+  a.loss_out = d_loss; a.grad_dump = d_grad_dump;
+  a.B = B; a.D = D; a.T = T; a.n_steps = n_steps;
+  a.npp = (o.NP + 63) / 64 * 64;
+  a.sigma = sigma; a.sigma_mode = sigma_mode;
+  a.lr = opt->lr; a.beta1 = opt->beta1; a.beta2 = opt->beta2;
+  a.b1pow = std::pow(opt->beta1, (double)steps_done); a.b2pow = std::pow(opt->beta2, (double)steps_done);
+  a.omb1 = (float)(1.0 - opt->beta1); a.omb2 = (float)(1.0 - opt->beta2); a.beta2f = (float)opt->beta2; a.eps_adam = (float)opt->eps;
+  k_train_md<<<CL, NT, kSmemBytes, (cudaStream_t)stream>>>(a);
+  IDFF_CUDA(cudaGetLastError());
+  count_launch();
+  return IDFF_OK;
+}

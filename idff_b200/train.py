@@ -291,3 +291,101 @@ class FusedFlowTrainer:
     def run(self, n_steps: int) -> torch.Tensor:
         x0, x1, t, eps = self.draw(n_steps)
         return self.steps(x0, x1, t, eps)
+
+
+class FusedMDTrainer:
+    """TrajectoryGenerator.train_model's loop (timeseris_example/MD_simulation.py:117-144) on `idff_train_md_steps`: every step --
+    frame-pair gather, path sample, MLP_Embedding forward, periodic loss, backward, Adam -- inside one persistent kernel on a
+    cluster of 8 CTAs that keeps the parameters and both Adam moments in shared memory (csrc/idff_trainer_md.cu); many steps per
+    launch, no torch kernel involved.
+
+    model: torchcfm MLP_Embedding(dim=D, w=128, time_embed=T, time_varying=True) on a CUDA device (D <= 47, T <= 224); its parameters
+    are re-pointed at the kernel's state buffer.  dataset: (T, D) CUDA tensor.
+        tr = FusedMDTrainer(model, dataset, batch_size=10, sigma=0.5)
+        losses = tr.steps(idx, t, eps)          # [S][B] int64 in [1, T), [S][B], [S][B][D] -> [S] losses
+        losses = tr.run(n_steps)                # draws idx / t / eps on the device first
+    """
+
+    def __init__(self, model: torch.nn.Module, dataset: torch.Tensor, batch_size: int = 10, sigma: float = 0.5, lr: float = 1e-3,
+                 betas=(0.9, 0.999), eps: float = 1e-8, exact_ot_sigma: bool = True):
+        L = _lib.lib()
+        _lib.require_cuda(dataset, "dataset")
+        self.dataset = dataset.contiguous().float()
+        self.T, self.D = int(dataset.shape[0]), int(dataset.shape[1])
+        params = [p for p in model.parameters()]
+        shapes = [tuple(p.shape) for p in params]
+        D, T, w = self.D, self.T, 128
+        want = [(T, w), (w, D + 1 + w), (w,), (w, w), (w,), (w, w), (w,), (D, w), (D,)]
+        if shapes != want:
+            raise _lib.IdffError(f"FusedMDTrainer serves MLP_Embedding(dim={D}, w=128, time_embed={T}, time_varying=True), got {shapes}; "
+                                 "use GraphedMDTrainer for other networks")
+        self.shapes = want
+        self.device = params[0].device
+        if self.device != self.dataset.device:
+            raise _lib.IdffError("model and dataset live on different devices")
+        self.B = int(batch_size)
+        n = int(L.idff_train_md_state_floats(D, T))
+        if n < 0:
+            raise _lib.IdffError("idff_train_md_state_floats: " + L.idff_last_error().decode())
+        off = (C.c_int64 * 13)()
+        _lib.check(L.idff_train_md_offsets(D, T, off), "idff_train_md_offsets")
+        self.offsets = [int(v) for v in off]
+        self.n_params = self.offsets[9]
+        self.state = torch.zeros(n, device=self.device, dtype=torch.float32)
+        with torch.no_grad():
+            for p, o in zip(params, self.offsets[:9]):
+                view = self.state[o: o + p.numel()].view(p.shape)
+                view.copy_(p)
+                p.data = view
+        self.model = model
+        self.opt = _lib.AdamW(lr, betas[0], betas[1], eps, 0.0, 0.0)     # torch.optim.Adam defaults: no decay; the loop does not clip
+        self.sigma, self.sigma_mode = float(sigma), 1 if exact_ot_sigma else 0
+        self.steps_done = 0
+
+    def named_block(self, name):
+        """The 9 tensors (module.parameters() order) of the "param" / "exp_avg" / "exp_avg_sq" block."""
+        base = self.offsets[{"param": 10, "exp_avg": 11, "exp_avg_sq": 12}[name]]
+        out = []
+        for o, sh in zip(self.offsets[:9], self.shapes):
+            n = 1
+            for v in sh:
+                n *= v
+            out.append(self.state[base + o: base + o + n].view(sh))
+        return out
+
+    def state_dict(self):
+        return {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+
+    def steps(self, idx, t, eps=None, grad_dump: torch.Tensor | None = None):
+        if not idx.is_cuda or idx.dtype != torch.int64:
+            raise _lib.IdffError("idx must be a CUDA int64 tensor (torch.randint's dtype): idff_b200 has no CPU path")
+        for name, v in (("t", t),) + ((("eps", eps),) if eps is not None else ()):
+            _lib.require_cuda(v, name)
+        for name, v in (("idx", idx), ("t", t)) + ((("eps", eps),) if eps is not None else ()):
+            if not v.is_contiguous():
+                raise _lib.IdffError(f"{name} must be contiguous")
+        if idx.dim() == 1:
+            idx, t = idx[None], t[None]
+            eps = eps[None] if eps is not None else None
+        S, B = int(idx.shape[0]), int(idx.shape[1])
+        if tuple(t.shape) != (S, B) or (eps is not None and tuple(eps.shape) != (S, B, self.D)):
+            raise _lib.IdffError(f"expected t of shape ({S}, {B}) and eps of shape ({S}, {B}, {self.D})")
+        loss = torch.empty(S, device=self.device, dtype=torch.float32)
+        _lib.check(_lib.lib().idff_train_md_steps(
+            _lib.ptr(self.state), _lib.ptr(self.dataset), self.T, self.D, _lib.ptr(idx), _lib.ptr(t), _lib.ptr(eps), S, B, self.sigma,
+            self.sigma_mode, C.byref(self.opt), self.steps_done, _lib.ptr(loss), _lib.ptr(grad_dump), _lib.stream_of(self.state)),
+            "idff_train_md_steps")
+        self.steps_done += S
+        torch.autograd.graph.increment_version(list(self.model.parameters()))   # the kernel wrote them in place
+        return loss
+
+    def draw(self, n_steps: int):
+        """Device draws for n_steps steps: idx = randint(1, T) (MD_simulation.py:128), t ~ U(0, 1), eps ~ N(0, 1)."""
+        idx = torch.randint(1, self.T, (n_steps, self.B), device=self.device)
+        t = torch.rand(n_steps, self.B, device=self.device)
+        eps = torch.randn(n_steps, self.B, self.D, device=self.device) if self.sigma != 0.0 else None
+        return idx, t, eps
+
+    def run(self, n_steps: int) -> torch.Tensor:
+        idx, t, eps = self.draw(n_steps)
+        return self.steps(idx, t, eps)

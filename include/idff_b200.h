@@ -249,6 +249,30 @@ int idff_train_steps(int32_t net, float* d_state, const float* d_x0, const float
                      int32_t n_steps, int32_t B, float sigma, int32_t sigma_mode, float score_sigma, const idff_adamw_t* opt,
                      int64_t steps_done, float* d_loss, float* d_gnorm, float* d_grad_dump, void* stream);
 
+/* ---- the PolyALA training step (TrajectoryGenerator.train_model, timeseris_example/MD_simulation.py:117-144):
+ *   idx = randint(1, T, (B,)); x0 = dataset[idx - 1]; x1 = dataset[idx]                                   (:128-130)
+ *   t, xt, ut, eps = FM.sample_location_and_conditional_flow(x0, x1)     (ExactOT matcher sigma 0.5, :121,132)
+ *   vt = model(cat[xt, t], idx)       MLP_Embedding(dim=D, w=128, time_embed=T): cat[xt, t, Embedding[idx]] -> 128 -> 128 -> 128 -> D
+ *   loss = mean((vt-x1)^2) + mean((vt-(x1+360))^2) + mean((vt-(x1-360))^2); loss.backward(); Adam().step()   (:137-144)
+ * n_steps consecutive steps in ONE launch on a cluster of 8 CTAs whose shared memories hold every parameter and both Adam
+ * moments for the whole launch (idff_trainer_md.cu).  The caller owns d_state = idff_train_md_state_floats(D, T) fp32,
+ * zero-initialised then filled with the parameters: three blocks [parameters | exp_avg | exp_avg_sq];
+ * idff_train_md_offsets fills h_out13 = {offsets of time_index_embedding.weight [T][128], net.0.weight [128][D+1+128],
+ * net.0.bias, net.2.weight, net.2.bias, net.4.weight, net.4.bias, net.6.weight [D][128], net.6.bias inside a block (the
+ * module's parameters() order, nn layouts), parameter count, state offsets of the three blocks}.  D <= 47, 2 <= T <=
+ * IDFF_TRAIN_MD_MAX_FRAMES, 1 <= B <= IDFF_TRAIN_MD_MAX_BATCH (the reference: D 46, T 200, B 10).
+ * Inputs of step s: d_idx [n_steps][B] int64 frame indices in [1, T) (clamped), d_t [n_steps][B], d_eps [n_steps][B][D] (NULL:
+ * sigma_t * eps = 0); d_dataset [T][D].  opt: torch.optim.Adam's lr / betas / eps (weight_decay must be 0, max_grad_norm <= 0:
+ * the loop neither decays nor clips).  Outputs (optional): d_loss [n_steps], d_grad_dump [parameter count] (gradient of the last
+ * step, block layout). */
+#define IDFF_TRAIN_MD_MAX_BATCH 16
+#define IDFF_TRAIN_MD_MAX_FRAMES 224
+int64_t idff_train_md_state_floats(int32_t D, int32_t T);
+int idff_train_md_offsets(int32_t D, int32_t T, int64_t* h_out13);
+int idff_train_md_steps(float* d_state, const float* d_dataset, int32_t T, int32_t D, const int64_t* d_idx, const float* d_t,
+                        const float* d_eps, int32_t n_steps, int32_t B, float sigma, int32_t sigma_mode, const idff_adamw_t* opt,
+                        int64_t steps_done, float* d_loss, float* d_grad_dump, void* stream);
+
 /* ---- OTPlanSampler.get_map for the reference's use (torchcfm/optimal_transport.py:59-94: uniform marginals over
  * two minibatches of EQUAL size n, squared-Euclidean cost, exact plan from pot.emd -- POT's network simplex, un-vendored).  The
  * exact plan of uniform equal-size marginals is 1/n times a permutation matrix, so the plan is returned as the permutation:

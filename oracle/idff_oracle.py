@@ -396,6 +396,42 @@ def train_steps_2d(layers, x0, x1, t, eps, sigma=0.0, lr=2e-4, clip=1.0, return_
     return res + (grads,) if return_grads else res
 
 
+def md_train_steps(emb, layers, dataset, idx, t, eps, sigma=0.5, lr=1e-3, return_grads=False):
+    """TrajectoryGenerator.train_model's loop (timeseris_example/MD_simulation.py:117-144) with the random draws passed in:
+    idx [S][B] int64 frame indices (randint(1, T), :128), t [S][B], eps [S][B][D].  MLP_Embedding (models.py:23-42) rebuilt from
+    (emb, layers); torch.optim.Adam with defaults (:119); ExactOT matcher sigma (:121, pairing off).
+    Returns (per-step losses, final (emb, layers)[, gradients of the last step in module.parameters() order])."""
+    E = torch.nn.Embedding(emb.shape[0], emb.shape[1]).to(emb.dtype)
+    mods = []
+    with torch.no_grad():
+        E.weight.copy_(emb)
+        for i, (W, b) in enumerate(layers):
+            lin = torch.nn.Linear(W.shape[1], W.shape[0]).to(W.dtype)
+            lin.weight.copy_(W)
+            lin.bias.copy_(b)
+            mods.append(lin)
+            if i + 1 < len(layers):
+                mods.append(torch.nn.SELU())
+    net = torch.nn.Sequential(*mods)                                              # models.py:30-38
+    params = [E.weight] + list(net.parameters())                                  # module.parameters() order
+    optimizer = torch.optim.Adam(params, lr=lr)                                   # MD_simulation.py:119
+    losses, grads = [], None
+    for s in range(idx.shape[0]):
+        optimizer.zero_grad()                                                     # :127
+        x0, x1 = dataset[idx[s] - 1], dataset[idx[s]]                             # :129-130
+        xt, ut = path_sample(x0, x1, t[s], eps[s] if eps is not None else torch.zeros_like(x0), sigma, True, ieee_sqrt=True)   # :132
+        x = torch.cat([xt, t[s][:, None]], dim=-1)
+        vt = net(torch.cat([x, E(idx[s].to(torch.long)).squeeze()], dim=-1))      # :135, models.py:40-42
+        loss = md_periodic_loss(vt, x1)                                           # :137-141
+        loss.backward()                                                           # :143
+        if return_grads and s == idx.shape[0] - 1:
+            grads = [p.grad.detach().clone() for p in params]
+        optimizer.step()                                                          # :144
+        losses.append(float(loss.detach()))
+    out = (E.weight.detach().clone(), [(mods[2 * i].weight.detach().clone(), mods[2 * i].bias.detach().clone()) for i in range(4)])
+    return (losses, out, grads) if return_grads else (losses, out)
+
+
 def log_prob_xt_given_x1_dimwise(x_t, x_1, x_0, t, sigma0_sq):
     """example_order1_with_prediction_head.py:26-51."""
     if t.ndim == 1:

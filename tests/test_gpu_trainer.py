@@ -314,3 +314,105 @@ def test_scorehead_many_steps_and_field(cuda_device):
     ref = O.odeint_rk4(O.FieldScoreHead(ref_layers, 0.2, (0.2, 0.2)), xs.cpu(), torch.linspace(0, 1, 3))[-1]
     dd = (out.cpu() - ref).abs()
     assert dd.median().item() <= 1e-5 and dd.quantile(0.999).item() <= 1e-3
+
+
+def _polyala_case(device, T=200, D=46, seed=0):
+    """A PolyALA-shaped data set (180 sin(cumsum(randn 0.05) + phase)) and a fresh MLP_Embedding (MD_simulation.py:118)."""
+    from idff_b200.torchcfm.models.models import MLP_Embedding
+    g = torch.Generator().manual_seed(seed)
+    ds = 180.0 * torch.sin(torch.cumsum(torch.randn(T, D, generator=g) * 0.05, 0) + torch.rand(1, D, generator=g) * 6.28)
+    torch.manual_seed(seed)
+    model = MLP_Embedding(dim=D, w=128, time_embed=T, time_varying=True).to(device)
+    return ds.float(), model
+
+
+def _md_parts(model):
+    ps = [p.detach().cpu().clone() for p in model.parameters()]
+    return ps[0], [(ps[1 + 2 * i], ps[2 + 2 * i]) for i in range(4)]
+
+
+@pytest.mark.parametrize("B,T,D", [(10, 200, 46), (16, 64, 47), (3, 200, 46), (7, 33, 5)])
+def test_md_step_gradients_loss_and_update(cuda_device, B, T, D):
+    """One PolyALA step in the cluster-resident kernel (idff_train_md_steps) vs the oracle's loop (MD_simulation.py:126-144 on torch
+    CPU, same weights and draws): loss to 2e-6 relative, every gradient tensor (embedding included, duplicated indices too) within
+    1e-5 * max|g|, Adam's first update to 1e-3 * lr where |g| is above the fp32 noise floor."""
+    dev, lr = cuda_device, 1e-3
+    ds, model = _polyala_case(dev, T, D, seed=B)
+    emb, layers = _md_parts(model)
+    g = torch.Generator().manual_seed(31 + B)
+    idx = torch.randint(1, T, (1, B), generator=g)
+    if B >= 3:
+        idx[0, 2] = idx[0, 0]                      # a duplicated frame: its embedding gradient rows add up
+    t = torch.rand(1, B, generator=g)
+    eps = torch.randn(1, B, D, generator=g)
+    losses_r, (emb_r, layers_r), grads_r = O.md_train_steps(emb, layers, ds, idx, t, eps, sigma=0.5, lr=lr, return_grads=True)
+    tr = train.FusedMDTrainer(model, ds.to(dev), batch_size=B, sigma=0.5, lr=lr)
+    dump = torch.zeros(tr.n_params, device=dev)
+    before = _lib.launch_count()
+    loss = tr.steps(idx.to(dev), t.to(dev), eps.to(dev), grad_dump=dump)
+    assert _lib.launch_count() - before == 1
+    assert loss.item() == pytest.approx(losses_r[0], rel=2e-6)
+    for o, sh, gr in zip(tr.offsets[:9], tr.shapes, grads_r):
+        got = dump[o: o + gr.numel()].view(sh).cpu().numpy()
+        ref = gr.numpy()
+        assert np.abs(got - ref).max() <= 1e-5 * max(np.abs(ref).max(), 1e-12), (sh, np.abs(got - ref).max(), np.abs(ref).max())
+    after_r = [emb_r] + [x for Wb in layers_r for x in Wb]
+    for p, ref, gr in zip(model.parameters(), after_r, grads_r):
+        d = (p.detach().cpu() - ref).abs().numpy()
+        solid = np.abs(gr.numpy()) > 1e-4
+        if solid.any():
+            assert d[solid].max() <= 1e-3 * lr, (tuple(p.shape), d[solid].max())
+        assert d.max() <= 2 * lr
+    # moments live next to the parameters and follow torch's: exp_avg = (1 - beta1) g after one step
+    m_blocks = tr.named_block("exp_avg")
+    for mb, gr in zip(m_blocks, grads_r):
+        np.testing.assert_allclose(mb.cpu().numpy(), 0.1 * gr.numpy(), rtol=1e-4, atol=1e-5 * max(float(gr.abs().max()), 1e-12))
+
+
+def test_md_many_steps_track_the_reference(cuda_device):
+    """50 consecutive PolyALA steps in ONE launch track the oracle's loop; bit-reproducible and independent of the launch split;
+    the trained module drives SDE_cal through the sampler kernels."""
+    dev, lr, S, B = cuda_device, 1e-3, 50, 10
+    ds, model = _polyala_case(dev, seed=2)
+    emb, layers = _md_parts(model)
+    g = torch.Generator().manual_seed(77)
+    idx = torch.randint(1, 200, (S, B), generator=g)
+    t = torch.rand(S, B, generator=g)
+    eps = torch.randn(S, B, 46, generator=g)
+    losses_r, (emb_r, layers_r) = O.md_train_steps(emb, layers, ds, idx, t, eps, sigma=0.5, lr=lr)
+    tr = train.FusedMDTrainer(model, ds.to(dev), batch_size=B, sigma=0.5, lr=lr)
+    loss = tr.steps(idx.to(dev), t.to(dev), eps.to(dev)).cpu().numpy()
+    np.testing.assert_allclose(loss, np.array(losses_r), rtol=2e-3)
+    assert loss[-1] < loss[0]
+    after_r = [emb_r] + [x for Wb in layers_r for x in Wb]
+    dall = np.concatenate([(p.detach().cpu() - ref).abs().numpy().reshape(-1) for p, ref in zip(model.parameters(), after_r)])
+    assert np.median(dall) <= 1e-5 and dall.max() <= 20 * lr, (np.median(dall), dall.max())
+    ds2, model2 = _polyala_case(dev, seed=2)
+    tr2 = train.FusedMDTrainer(model2, ds2.to(dev), batch_size=B, sigma=0.5, lr=lr)
+    la = tr2.steps(idx[:17].to(dev).contiguous(), t[:17].to(dev).contiguous(), eps[:17].to(dev).contiguous())
+    lb = tr2.steps(idx[17:].to(dev).contiguous(), t[17:].to(dev).contiguous(), eps[17:].to(dev).contiguous())
+    assert np.array_equal(torch.cat([la, lb]).cpu().numpy(), loss)
+    for p, q in zip(model.parameters(), model2.parameters()):
+        assert torch.equal(p, q)
+    # the kernel-trained module under the generator's field
+    from idff_b200 import fields
+    sde = fields.SDE_cal(model, input_dim=46, sigma=0.5, init_ind=3, max_length=200, dt=0.3, gamma1=0.2, gamma2=1.25)
+    y = ds[5:9].to(dev).contiguous()
+    f = sde.f(torch.tensor(0.3), y)
+    emb2, layers2 = _md_parts(model)
+    ref = O.FieldMD(layers2, emb2, 46, sigma=0.5, init_ind=3, dt=0.3, gamma1=0.2, gamma2=1.25).f(torch.tensor(0.3), y.cpu())
+    assert (f.cpu() - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+
+
+def test_md_trainer_argument_checks(cuda_device):
+    dev = cuda_device
+    ds, model = _polyala_case(dev, seed=1)
+    tr = train.FusedMDTrainer(model, ds.to(dev))
+    idx = torch.randint(1, 200, (2, 17), device=dev)
+    with pytest.raises(_lib.IdffError):
+        tr.steps(idx, torch.rand(2, 17, device=dev))           # batch above IDFF_TRAIN_MD_MAX_BATCH
+    with pytest.raises(_lib.IdffError):
+        tr.steps(idx[:, :10].int(), torch.rand(2, 10, device=dev))
+    from idff_b200.torchcfm.models.models import MLP_Embedding
+    with pytest.raises(_lib.IdffError):
+        train.FusedMDTrainer(MLP_Embedding(dim=46, w=64, time_embed=200, time_varying=True).to(dev), ds.to(dev))
