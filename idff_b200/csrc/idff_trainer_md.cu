@@ -23,7 +23,7 @@
 //     layer's backward-data partials have been formed from the old weights.  No gradient norm, so no other cross-CTA reduction.
 //   * the embedding rows of the batch are gathered by the column owners and pushed like activations; their gradient comes back through
 //     the same reduce-scatter (duplicated indices accumulate in row order); the dense Adam update touches all T rows, as torch does.
-// 8 cluster barriers per step.  Parameters are read from / written back to the caller's state buffer (nn.Module layout, so the torch
+// 8 exchanges per step, each a set of st.async stores that signal the destination's mbarrier (no cluster barrier in the loop).  Parameters are read from / written back to the caller's state buffer (nn.Module layout, so the torch
 // parameters can alias it) at the start / end of a launch.
 #include <cmath>
 
@@ -37,17 +37,22 @@ constexpr int OPC = 6;                // outputs per CTA (ceil(47 / 8))
 constexpr int K0P = DP + W;           // layer-0 input as laid out on chip: [x (D) | t | zero pad to 48 | embedding (128)]
 constexpr int W0S = K0P + 4, WS = W + 4;   // row strides of the weight slices (bank spread for 16 rows read at once)
 constexpr int C0S = K0P + 4;          // row stride of the layer-0 input rows
+constexpr int AS = W + 4;             // row stride of the activation buffers
+constexpr int NX = 8;                 // exchange points per step, one mbarrier each
 
 // shared-memory plan (floats).  Parameter slices: three copies (param, exp_avg, exp_avg_sq) `PT` apart.
 constexpr int pW0 = 0, pb0 = pW0 + UPC * W0S, pW1 = pb0 + UPC, pb1 = pW1 + UPC * WS, pW2 = pb1 + UPC, pb2 = pW2 + UPC * WS,
               pW3 = pb2 + UPC, pb3 = pW3 + OPC * WS, pE = pb3 + 8, PT = pE + TMAX * UPC;
-constexpr int mCAT = 3 * PT, mA1 = mCAT + BMAX * C0S, mA2 = mA1 + BMAX * W, mA3 = mA2 + BMAX * W, mX1 = mA3 + BMAX * W,
-              mDVT = mX1 + BMAX * DP, mCODE = mDVT + BMAX * 8, mDZ = mCODE + 3 * BMAX * UPC, mSTG = mDZ + BMAX * UPC,
-              mRECV = mSTG + BMAX * UPC, mCOMB = mRECV + 2 * CL * BMAX * UPC, mLT = mCOMB + NT, mLRECV = mLT + BMAX * 8 * 3,
-              mMISC = mLRECV + CL * 3 * 2, mTOTAL = mMISC + 64;
+constexpr int mCAT = 3 * PT, mA1 = mCAT + 2 * BMAX * C0S, mA2 = mA1 + BMAX * AS, mA3 = mA2 + BMAX * AS, mX1 = mA3 + BMAX * AS,
+              mDVT = mX1 + BMAX * DP, mCODE = mDVT + BMAX * 8, mDZ = mCODE + 3 * BMAX * UPC, mDE = mDZ + BMAX * UPC,
+              mSTG = mDE + BMAX * UPC, mRECV = mSTG + BMAX * UPC, mCOMB = mRECV + 2 * CL * BMAX * UPC, mLT = mCOMB + 8 * BMAX * UPC,
+              mLRECV = mLT + BMAX * 8 * 3, mMISC = mLRECV + CL * 3 * 2, mROW = mMISC + 64, mBAR = mROW + 3 * TMAX, mTOTAL = mBAR + 2 * NX;
 constexpr size_t kSmemBytes = (size_t)mTOTAL * sizeof(float);
 static_assert(kSmemBytes <= 232448, "shared memory budget");
-static_assert(mLRECV % 2 == 0 && mMISC % 2 == 0, "8-byte aligned slots");
+static_assert(mLRECV % 2 == 0 && mMISC % 2 == 0 && mBAR % 2 == 0, "8-byte aligned slots");
+
+// clock64 stamps of the last step of the last launch (CTA 0, thread 0): diagnostic (idff_debug_train_md_stamps)
+__device__ long long g_md_stamps[32];
 
 struct Args {
   float* S;                 // state: [param block | exp_avg | exp_avg_sq], each NPP floats
@@ -82,64 +87,105 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void st_cluster4(uint32_t addr, float4 v) {
-  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+// remote store that carries its own completion signal: the destination CTA's mbarrier `bar` receives complete_tx(bytes) when the
+// data has landed (SASS STAS) -- the consumer waits for its expected byte count, no fence / arrive / cluster barrier on either side
+__device__ __forceinline__ void st_async4(uint32_t addr, float4 v, uint32_t bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w), "r"(bar)
+               : "memory");
 }
-__device__ __forceinline__ void st_cluster_f64(uint32_t addr, double v) {
-  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+__device__ __forceinline__ void st_async_f64(uint32_t addr, double v, uint32_t bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(addr),
+               "l"(__double_as_longlong(v)), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
 }
 
 __device__ __forceinline__ float selu_d1(float code) { return code < 0.0f ? kSeluLambda : code; }
 
 // torch.optim.Adam (single tensor, weight_decay 0): exp_avg.lerp_(g, 1 - b1); exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2);
-// denom = sqrt(v) / sqrt(bc2) + eps; p -= (lr / bc1) * m / denom
+// denom = sqrt(v) / sqrt(bc2) + eps; p -= (lr / bc1) * m / denom.  The step is instruction-bound at 16 warps per SM, and IEEE
+// sqrt / division cost ~35 instructions per element: sqrt and the quotient use the approximate units (sqrt.approx, rcp-based
+// division: <= 2 ulp each), 1 / sqrt(bc2) is formed once per step in double.  The update differs from torch's by ~1e-7 relative.
 struct AdamK {
-  float omb1, omb2, beta2f, eps, step_size, bc2_sqrt;
+  float omb1, omb2, beta2f, eps, step_size, inv_bc2_sqrt;
 };
 __device__ __forceinline__ void adam1(const AdamK& k, float g, float& p, float& m, float& v) {
   m = fmaf(g - m, k.omb1, m);
   v = fmaf(k.omb2 * g, g, v * k.beta2f);
-  const float denom = sqrtf(v) / k.bc2_sqrt + k.eps;
-  p = p - k.step_size * (m / denom);
+  float sq;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(v));
+  const float denom = fmaf(sq, k.inv_bc2_sqrt, k.eps);
+  p = fmaf(-k.step_size, __fdividef(m, denom), p);
 }
 
-// ---- one hidden layer forward for this CTA's 16 units: thread (kh, r, u) sums half of K; a = selu(z) goes to `stg` [r][u], the
-// derivative code to `code` [r][u].  in: [BMAX][is] (complete), Wp: [16][ws] (K4 float4 per row used), bias [16].
+// ---- one hidden layer forward for this CTA's 16 units.  Thread (kh, rp, up): rows {rp, rp + 8} x units {up, up + 8} over K-slice kh
+// of 8 -- per float4 step two weight loads (8 distinct rows, conflict free at stride 132 / 180) and two activation loads serve 16
+// FMAs.  The slices meet in `comb` [8][16][16]; a = selu(z) goes to `stg` [r][u], the derivative code to `code` [r][u].
+// in: [BMAX][is] (complete), Wp: [16][ws] (K4 float4 per row used), bias [16].
 __device__ __forceinline__ void fwd_units(const float* in, int is, int K4, const float* Wp, int ws, const float* bias, float* comb,
                                           float* stg, float* code, int tid) {
-  const int kh = tid >> 8, r = (tid >> 4) & 15, u = tid & 15;
-  const int half = (K4 + 1) >> 1, k0 = kh * half, k1 = min(K4, k0 + half);
-  const float4* w4 = reinterpret_cast<const float4*>(Wp + u * ws);
-  const float4* a4 = reinterpret_cast<const float4*>(in + r * is);
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-#pragma unroll 4
+  const int kh = tid >> 6, rp = (tid >> 3) & 7, up = tid & 7;
+  const int per = (K4 + 7) >> 3, k0 = kh * per, k1 = min(K4, k0 + per);
+  const float4* w0 = reinterpret_cast<const float4*>(Wp + up * ws);
+  const float4* w1 = reinterpret_cast<const float4*>(Wp + (up + 8) * ws);
+  const float4* x0 = reinterpret_cast<const float4*>(in + rp * is);
+  const float4* x1 = reinterpret_cast<const float4*>(in + (rp + 8) * is);
+  float c00 = 0.f, c01 = 0.f, c10 = 0.f, c11 = 0.f;
+#pragma unroll 2
   for (int k = k0; k < k1; ++k) {
-    const float4 w = w4[k], a = a4[k];
-    acc0 = fmaf(a.x, w.x, acc0); acc1 = fmaf(a.y, w.y, acc1); acc2 = fmaf(a.z, w.z, acc2); acc3 = fmaf(a.w, w.w, acc3);
+    const float4 wa = w0[k], wb = w1[k], xa = x0[k], xb = x1[k];
+    c00 = fmaf(xa.x, wa.x, c00); c00 = fmaf(xa.y, wa.y, c00); c00 = fmaf(xa.z, wa.z, c00); c00 = fmaf(xa.w, wa.w, c00);
+    c01 = fmaf(xa.x, wb.x, c01); c01 = fmaf(xa.y, wb.y, c01); c01 = fmaf(xa.z, wb.z, c01); c01 = fmaf(xa.w, wb.w, c01);
+    c10 = fmaf(xb.x, wa.x, c10); c10 = fmaf(xb.y, wa.y, c10); c10 = fmaf(xb.z, wa.z, c10); c10 = fmaf(xb.w, wa.w, c10);
+    c11 = fmaf(xb.x, wb.x, c11); c11 = fmaf(xb.y, wb.y, c11); c11 = fmaf(xb.z, wb.z, c11); c11 = fmaf(xb.w, wb.w, c11);
   }
-  comb[tid] = (acc0 + acc1) + (acc2 + acc3);
+  float* cb = comb + kh * (BMAX * UPC);
+  cb[rp * UPC + up] = c00; cb[rp * UPC + up + 8] = c01; cb[(rp + 8) * UPC + up] = c10; cb[(rp + 8) * UPC + up + 8] = c11;
   __syncthreads();
   if (tid < 256) {
-    const float z = (comb[tid] + comb[tid + 256]) + bias[u];
+    float z = comb[tid];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) z += comb[k * (BMAX * UPC) + tid];
+    z += bias[tid & 15];
     float c;
-    stg[r * UPC + u] = selu_fwd(z, c);
-    code[r * UPC + u] = c;
+    stg[tid] = selu_fwd(z, c);
+    code[tid] = c;
   }
   __syncthreads();
 }
 
 // push stg [B][16] into column block `rank` of the [BMAX][stride] buffer at shared offset `dst_off` (+ col0) of every CTA
-__device__ __forceinline__ void push_units(const float* stg, int B, uint32_t dst_saddr, int stride, int col0, uint32_t rank, int tid) {
+__device__ __forceinline__ void push_units(const float* stg, int B, uint32_t dst_saddr, int stride, int col0, uint32_t rank, uint32_t bar,
+                                           int tid) {
   if (tid < 64 * CL) {
     const int peer = tid >> 6, r = (tid >> 2) & 15, u4 = tid & 3;
     if (r < B) {
       const float4 v = *reinterpret_cast<const float4*>(stg + r * UPC + 4 * u4);
-      st_cluster4(mapa(dst_saddr + (uint32_t)((r * stride + col0 + (int)rank * UPC + 4 * u4) * 4), (uint32_t)peer), v);
+      st_async4(mapa(dst_saddr + (uint32_t)((r * stride + col0 + (int)rank * UPC + 4 * u4) * 4), (uint32_t)peer), v,
+                mapa(bar, (uint32_t)peer));
     }
   }
 }
@@ -148,7 +194,7 @@ __device__ __forceinline__ void push_units(const float* stg, int B, uint32_t dst
 // scattered to the owners of k: recv[rank][r][k % 16] of CTA k / 16.  ALIGNED: wc0 is a multiple of 4 floats.
 template <bool ALIGNED>
 __device__ __forceinline__ void partial_scatter(const float* dz, int dzs, int J, const float* Wp, int ws, int wc0, int B,
-                                                uint32_t recv_saddr, uint32_t rank, int tid) {
+                                                uint32_t recv_saddr, uint32_t rank, uint32_t bar, int tid) {
   const int r = tid >> 5, kq = tid & 31;
   if (r < B) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -163,7 +209,8 @@ __device__ __forceinline__ void partial_scatter(const float* dz, int dzs, int J,
       }
       acc.x = fmaf(d, w.x, acc.x); acc.y = fmaf(d, w.y, acc.y); acc.z = fmaf(d, w.z, acc.z); acc.w = fmaf(d, w.w, acc.w);
     }
-    st_cluster4(mapa(recv_saddr + (uint32_t)((((int)rank * BMAX + r) * UPC + 4 * (kq & 3)) * 4), (uint32_t)(kq >> 2)), acc);
+    st_async4(mapa(recv_saddr + (uint32_t)((((int)rank * BMAX + r) * UPC + 4 * (kq & 3)) * 4), (uint32_t)(kq >> 2)), acc,
+              mapa(bar, (uint32_t)(kq >> 2)));
   }
 }
 
@@ -260,28 +307,48 @@ __device__ void move_params(const Args& a, const Off& o, float* sm, uint32_t ran
 
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(const Args a) {
   extern __shared__ __align__(16) float sm[];
-  const int tid = threadIdx.x, B = a.B, D = a.D, T = a.T;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, B = a.B, D = a.D, T = a.T;
   const uint32_t rank = cluster_ctarank();
   const Off o(D, T);
   const int n_own = max(0, min(OPC, D - (int)rank * OPC));   // outputs [6 rank, 6 rank + n_own)
-  float* cat0 = sm + mCAT;     // [BMAX][C0S]: x (D), t, pad, embedding row (128 at column DP)
+  // layer-0 input rows [BMAX][C0S]: x (D), t, pad, embedding row (128 at column DP) -- one buffer per step parity: a peer that is
+  // already in the next step pushes its embedding columns while this CTA may still read the current rows for dW0
   float* a1 = sm + mA1; float* a2 = sm + mA2; float* a3 = sm + mA3;
   float* x1s = sm + mX1;       // [BMAX][DP]
   float* dvt = sm + mDVT;      // [BMAX][8]
   float* code = sm + mCODE;    // [3][BMAX][16]
   float* dz = sm + mDZ;        // [BMAX][16]
+  float* dE = sm + mDE;        // [BMAX][16]: gradient of this CTA's embedding columns, per batch row
   float* stg = sm + mSTG;      // [BMAX][16]
   float* recv = sm + mRECV;    // [2][CL][BMAX][16]
   float* comb = sm + mCOMB;
   float* lt = sm + mLT;        // [BMAX][8][3]
   double* lrecv = reinterpret_cast<double*>(sm + mLRECV);   // [CL][3] (CTA 0)
-  int* idxs = reinterpret_cast<int*>(sm + mMISC);           // [BMAX]
-  float* sc = sm + mMISC + 32;                              // step_size, bc2_sqrt
+  int* idxb = reinterpret_cast<int*>(sm + mMISC);           // [2][BMAX]: frame indices of the current / the other step (by parity)
+  float* sc = sm + mMISC + 32;                              // [2][2]: step_size, 1 / bc2_sqrt by step parity
+  int* rowfirst = reinterpret_cast<int*>(sm + mROW);        // [2][TMAX]: first batch row that uses frame `row` (-1: none), by parity
+  int* need = rowfirst + 2 * TMAX;                          // [TMAX]: the next step gathers this embedding row
+
+  // one mbarrier per exchange point of a step: every remote store (st.async) signals its byte count on the destination's barrier,
+  // the consumer waits for the bytes of all 8 sources.  A step uses one phase of each barrier (parity = step parity); thread 0
+  // re-arms a barrier for the next step right after its own wait.
+  const uint32_t xbar = s32(sm + mBAR);
+  const uint32_t xbytes = (uint32_t)(CL * B * UPC * 4);
+  auto xb = [&](int k) { return xbar + 8u * (uint32_t)k; };
+  auto xexpect = [&](int k) { return xbytes + ((k == 4 && rank == 0) ? (uint32_t)(CL * 3 * 8) : 0u); };   // + the loss sums (CTA 0)
 
   for (int i = tid; i < mTOTAL - 3 * PT; i += NT) sm[3 * PT + i] = 0.0f;
+  __syncthreads();
+  for (int i = tid; i < 2 * TMAX; i += NT) rowfirst[i] = -1;
+  if (tid == 0) {
+    for (int k = 0; k < NX; ++k) mbar_init(xb(k), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   move_params(a, o, sm, rank, n_own, 0, tid);
   __syncthreads();
-  cluster_sync_all();   // every CTA's buffers are initialised before the first push arrives
+  cluster_sync_all();   // every CTA's buffers and barriers are initialised before the first push arrives
+  if (tid == 0 && a.n_steps > 0)
+    for (int k = 0; k < NX; ++k) mbar_arrive_expect_tx(xb(k), xexpect(k));
 
   const int n_el = B * D;   // (row, dim) elements of a batch: up to 2 per thread
   float px0[2], px1[2], pep[2], ptt[2];
@@ -302,12 +369,56 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(c
       }
     }
   };
-  if (a.n_steps > 0) prefetch(0);
+  // frame indices of the prefetched step -> idxb[par]; rowfirst[par] (first batch row per frame)
+  auto publish_idx = [&](int par) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = tid + q * NT;
+      if (e < n_el && e % D == 0) idxb[par * BMAX + e / D] = pidx[q];
+    }
+  };
+  auto adam_of = [&](int par) {
+    AdamK k;
+    k.omb1 = a.omb1; k.omb2 = a.omb2; k.beta2f = a.beta2f; k.eps = a.eps_adam; k.step_size = sc[par * 2]; k.inv_bc2_sqrt = sc[par * 2 + 1];
+    return k;
+  };
+  // Adam on one element of this CTA's embedding columns with the gradient of step parity `par` (rows of the batch that use the frame)
+  auto emb_item = [&](int row, int e, int par, const AdamK& k, float* dump) {
+    const int* ix = idxb + par * BMAX;
+    float g = 0.f;
+    const int rs = rowfirst[par * TMAX + row];
+    if (rs >= 0)
+      for (int r = rs; r < B; ++r)
+        if (ix[r] == row) g += dE[r * UPC + e];
+    float* p = sm + pE + row * UPC + e;
+    adam1(k, g, p[0], p[PT], p[2 * PT]);
+    if (dump) dump[o.oE + row * W + (int)rank * UPC + e] = g;
+  };
   double b1pow = a.b1pow, b2pow = a.b2pow;
-  const uint32_t cat_s = s32(cat0), a1_s = s32(a1), a2_s = s32(a2), a3_s = s32(a3), recv_s = s32(recv);
+  const uint32_t a1_s = s32(a1), a2_s = s32(a2), a3_s = s32(a3), recv_s = s32(recv);
+
+  if (a.n_steps > 0) {
+    prefetch(0);
+    publish_idx(0);
+  }
+  __syncthreads();
 
   for (int s = 0; s < a.n_steps; ++s) {
+    const int par = s & 1;
+    const bool more = s + 1 < a.n_steps;
+    const int* idxs = idxb + par * BMAX;
+    float* cat0 = sm + mCAT + par * (BMAX * C0S);
+    const uint32_t cat_s = s32(cat0);
+    // wait for exchange k of this step; thread 0 arms the barrier for the next step
+    auto xwait = [&](int k) {
+      mbar_wait(xb(k), (uint32_t)par);
+      if (tid == 0 && more) mbar_arrive_expect_tx(xb(k), xexpect(k));
+    };
     float* dump = (a.grad_dump && s == a.n_steps - 1) ? a.grad_dump : nullptr;
+    const bool stamp = rank == 0 && tid == 0 && s == a.n_steps - 1;
+    int sti = 0;
+#define MD_STAMP() do { if (stamp) g_md_stamps[sti] = clock64(); ++sti; } while (0)
+    MD_STAMP();
     // ---- phase 0: path sample (conditional_flow_matching.py:98-123, no contraction), embedding gather + push
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -319,36 +430,59 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(c
         const float xt = __fadd_rn(__fadd_rn(__fmul_rn(t, px1[q]), __fmul_rn(__fsub_rn(1.0f, t), px0[q])), __fmul_rn(st, pep[q]));
         cat0[r * C0S + d] = xt;
         x1s[r * DP + d] = px1[q];
-        if (d == 0) { cat0[r * C0S + D] = t; idxs[r] = pidx[q]; }
+        if (d == 0) cat0[r * C0S + D] = t;
       }
     }
     if (tid == 0) {
       b1pow *= a.beta1;
       b2pow *= a.beta2;
-      sc[0] = (float)(a.lr / (1.0 - b1pow));
-      sc[1] = (float)sqrt(1.0 - b2pow);
+      sc[par * 2] = (float)(a.lr / (1.0 - b1pow));
+      sc[par * 2 + 1] = (float)(1.0 / sqrt(1.0 - b2pow));
     }
-    __syncthreads();
-    if (s + 1 < a.n_steps) prefetch(s + 1);   // in flight for the whole step
-    AdamK ak;
-    ak.omb1 = a.omb1; ak.omb2 = a.omb2; ak.beta2f = a.beta2f; ak.eps = a.eps_adam; ak.step_size = sc[0]; ak.bc2_sqrt = sc[1];
-    if (tid < 64) {   // this CTA's 16 embedding columns of the batch rows -> stg
-      const int r = tid >> 2, u4 = tid & 3;
+    if (tid < B) {   // first batch row of every frame in use (duplicates add up in row order)
+      bool first = true;
+      for (int r = 0; r < tid; ++r) first = first && idxs[r] != idxs[tid];
+      if (first) rowfirst[par * TMAX + idxs[tid]] = tid;
+    }
+    if (tid >= 64 && tid < 128) {   // this CTA's 16 embedding columns of the batch rows -> stg
+      const int r = (tid - 64) >> 2, u4 = tid & 3;
       if (r < B) *reinterpret_cast<float4*>(stg + r * UPC + 4 * u4) = *reinterpret_cast<const float4*>(sm + pE + idxs[r] * UPC + 4 * u4);
     }
     __syncthreads();
-    push_units(stg, B, cat_s, C0S, DP, rank, tid);
-    cluster_sync_all();                                                                   // barrier 1
+    if (s + 1 < a.n_steps) prefetch(s + 1);   // in flight for the whole step
+    const AdamK ak = adam_of(par);
+    push_units(stg, B, cat_s, C0S, DP, rank, xb(0), tid);                                 // exchange 0
+    MD_STAMP();
+    if (s > 0) {
+      // the previous step's dense Adam update of the embedding rows this step does NOT gather (the gathered ones were updated at
+      // the end of that step): off the critical path, while the pushes of the cluster land
+      const AdamK akp = adam_of(par ^ 1);
+      for (int it = tid; it < T * UPC; it += NT)
+        if (!need[it >> 4]) emb_item(it >> 4, it & 15, par ^ 1, akp, nullptr);
+      __syncthreads();
+      if (tid < B) {
+        need[idxs[tid]] = 0;
+        rowfirst[(par ^ 1) * TMAX + idxb[(par ^ 1) * BMAX + tid]] = -1;
+      }
+    }
+    xwait(0);
+    MD_STAMP();
     // ---- forward
     fwd_units(cat0, C0S, K0P / 4, sm + pW0, W0S, sm + pb0, comb, stg, code, tid);
-    push_units(stg, B, a1_s, W, 0, rank, tid);
-    cluster_sync_all();                                                                   // barrier 2
-    fwd_units(a1, W, W / 4, sm + pW1, WS, sm + pb1, comb, stg, code + BMAX * UPC, tid);
-    push_units(stg, B, a2_s, W, 0, rank, tid);
-    cluster_sync_all();                                                                   // barrier 3
-    fwd_units(a2, W, W / 4, sm + pW2, WS, sm + pb2, comb, stg, code + 2 * BMAX * UPC, tid);
-    push_units(stg, B, a3_s, W, 0, rank, tid);
-    cluster_sync_all();                                                                   // barrier 4
+    push_units(stg, B, a1_s, AS, 0, rank, xb(1), tid);                                    // exchange 1
+    MD_STAMP();
+    xwait(1);
+    MD_STAMP();
+    fwd_units(a1, AS, W / 4, sm + pW1, WS, sm + pb1, comb, stg, code + BMAX * UPC, tid);
+    push_units(stg, B, a2_s, AS, 0, rank, xb(2), tid);                                    // exchange 2
+    MD_STAMP();
+    xwait(2);
+    MD_STAMP();
+    fwd_units(a2, AS, W / 4, sm + pW2, WS, sm + pb2, comb, stg, code + 2 * BMAX * UPC, tid);
+    push_units(stg, B, a3_s, AS, 0, rank, xb(3), tid);                                    // exchange 3
+    MD_STAMP();
+    xwait(3);
+    MD_STAMP();
     // ---- output layer (this CTA's outputs), periodic loss (MD_simulation.py:137-141) and d loss / d vt
     {
       const int i8 = tid >> 2, ks = tid & 3, r = i8 >> 3, oo = i8 & 7;
@@ -356,7 +490,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(c
       float acc = 0.f;
       if (valid) {
         const float4* w4 = reinterpret_cast<const float4*>(sm + pW3 + oo * WS);
-        const float4* a4 = reinterpret_cast<const float4*>(a3 + r * W);
+        const float4* a4 = reinterpret_cast<const float4*>(a3 + r * AS);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 w = w4[ks + 4 * i], av = a4[ks + 4 * i];
@@ -379,62 +513,85 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(c
       }
     }
     __syncthreads();
-    if (tid < 3) {   // this CTA's share of the three loss sums, fixed order -> CTA 0
+    if (warp < 3) {   // this CTA's share of the three loss sums (fp64, fixed order: lane-strided, then a butterfly) -> CTA 0
       double sum = 0.0;
-      for (int i = 0; i < B * 8; ++i) sum += (double)lt[i * 3 + tid];
-      st_cluster_f64(mapa(s32(lrecv + (int)rank * 3 + tid), 0u), sum);
+      for (int i = lane; i < B * 8; i += 32) sum += (double)lt[i * 3 + warp];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+      if (lane == 0) st_async_f64(mapa(s32(lrecv + (int)rank * 3 + warp), 0u), sum, mapa(xb(4), 0u));
     }
-    partial_scatter<true>(dvt, 8, n_own, sm + pW3, WS, 0, B, recv_s, rank, tid);                       // -> recv[0]
+    partial_scatter<true>(dvt, 8, n_own, sm + pW3, WS, 0, B, recv_s, rank, xb(4), tid);               // exchange 4 -> recv[0]
+    MD_STAMP();
     __syncthreads();   // W3 has been read by the partial products
-    wgrad_adam(dvt, 8, n_own, a3, W, W / 4, sm + pW3, WS, B, ak, dump,
+    wgrad_adam(dvt, 8, n_own, a3, AS, W / 4, sm + pW3, WS, B, ak, dump,
                [&](int j, int c) { return o.oW3 + ((int)rank * OPC + j) * W + c; }, tid);
     bgrad_adam(dvt, 8, n_own, sm + pb3, B, ak, dump, o.ob3 + (int)rank * OPC, tid);
-    cluster_sync_all();                                                                   // barrier 5
+    xwait(4);
+    MD_STAMP();
     if (rank == 0 && tid == 0 && a.loss_out) {
       double s0 = 0.0, s1 = 0.0, s2 = 0.0;
       for (int c = 0; c < CL; ++c) { s0 += lrecv[c * 3]; s1 += lrecv[c * 3 + 1]; s2 += lrecv[c * 3 + 2]; }
       const double n = (double)(B * D);
       a.loss_out[s] = ((float)(s0 / n) + (float)(s1 / n)) + (float)(s2 / n);
     }
-    // ---- backward through layers 3, 2 (dZ of the owner's units, partials of the next dA, weight gradients + Adam)
+    // ---- backward through layers 3, 2 (dZ of the owner's units, partials of the next dA; the weight gradients + Adam run
+    // after the CTA has ARRIVED at the layer's cluster barrier, i.e. while its partial sums travel and the peers catch up)
     gather_recv(recv, code + 2 * BMAX * UPC, dz, B, tid);
     __syncthreads();
-    partial_scatter<true>(dz, UPC, UPC, sm + pW2, WS, 0, B, recv_s + CL * BMAX * UPC * 4, rank, tid);   // -> recv[1]
+    partial_scatter<true>(dz, UPC, UPC, sm + pW2, WS, 0, B, recv_s + CL * BMAX * UPC * 4, rank, xb(5), tid);   // exchange 5 -> recv[1]
+    MD_STAMP();
     __syncthreads();
-    wgrad_adam(dz, UPC, UPC, a2, W, W / 4, sm + pW2, WS, B, ak, dump,
+    wgrad_adam(dz, UPC, UPC, a2, AS, W / 4, sm + pW2, WS, B, ak, dump,
                [&](int j, int c) { return o.oW2 + ((int)rank * UPC + j) * W + c; }, tid);
     bgrad_adam(dz, UPC, UPC, sm + pb2, B, ak, dump, o.ob2 + (int)rank * UPC, tid);
-    cluster_sync_all();                                                                   // barrier 6
+    __syncthreads();   // dz is rewritten below
+    xwait(5);
+    MD_STAMP();
     gather_recv(recv + CL * BMAX * UPC, code + BMAX * UPC, dz, B, tid);
     __syncthreads();
-    partial_scatter<true>(dz, UPC, UPC, sm + pW1, WS, 0, B, recv_s, rank, tid);                        // -> recv[0]
+    partial_scatter<true>(dz, UPC, UPC, sm + pW1, WS, 0, B, recv_s, rank, xb(6), tid);                // exchange 6 -> recv[0]
+    MD_STAMP();
     __syncthreads();
-    wgrad_adam(dz, UPC, UPC, a1, W, W / 4, sm + pW1, WS, B, ak, dump,
+    wgrad_adam(dz, UPC, UPC, a1, AS, W / 4, sm + pW1, WS, B, ak, dump,
                [&](int j, int c) { return o.oW1 + ((int)rank * UPC + j) * W + c; }, tid);
     bgrad_adam(dz, UPC, UPC, sm + pb1, B, ak, dump, o.ob1 + (int)rank * UPC, tid);
-    cluster_sync_all();                                                                   // barrier 7
+    __syncthreads();
+    xwait(6);
+    MD_STAMP();
     // ---- layer 1: dZ1; the gradient of the embedding inputs goes back to the column owners; dW0 over the whole input row
     gather_recv(recv, code, dz, B, tid);
     __syncthreads();
-    partial_scatter<true>(dz, UPC, UPC, sm + pW0, W0S, DP, B, recv_s + CL * BMAX * UPC * 4, rank, tid);   // -> recv[1]
+    partial_scatter<true>(dz, UPC, UPC, sm + pW0, W0S, DP, B, recv_s + CL * BMAX * UPC * 4, rank, xb(7), tid);   // exchange 7 -> recv[1]
+    MD_STAMP();
     __syncthreads();
     wgrad_adam(dz, UPC, UPC, cat0, C0S, K0P / 4, sm + pW0, W0S, B, ak, dump,
                [&](int j, int c) { const int gc = w0_col(c, D); return gc >= 0 ? o.oW0 + ((int)rank * UPC + j) * o.K0 + gc : -1; }, tid);
     bgrad_adam(dz, UPC, UPC, sm + pb0, B, ak, dump, o.ob0 + (int)rank * UPC, tid);
-    cluster_sync_all();                                                                   // barrier 8
-    // ---- embedding: gradient rows of the batch (duplicates accumulate in row order), dense Adam over all T rows
-    gather_recv(recv + CL * BMAX * UPC, nullptr, dz, B, tid);
+    if (more) publish_idx(par ^ 1);   // the next step's frames (prefetched long ago)
+    xwait(7);
+    MD_STAMP();
+    // ---- embedding: gradient rows of the batch; dense Adam over all T rows, as torch's.  Now: the rows the next step gathers
+    // (the rest follows behind that step's first barrier); last step of the launch: all rows.
+    gather_recv(recv + CL * BMAX * UPC, nullptr, dE, B, tid);
     __syncthreads();
-    for (int it = tid; it < T * UPC; it += NT) {
-      const int row = it >> 4, e = it & 15;
-      float g = 0.f;
-      for (int r = 0; r < B; ++r)
-        if (idxs[r] == row) g += dz[r * UPC + e];
-      float* p = sm + pE + it;
-      adam1(ak, g, p[0], p[PT], p[2 * PT]);
-      if (dump) dump[o.oE + row * W + (int)rank * UPC + e] = g;
+    if (more) {
+      const int* ixn = idxb + (par ^ 1) * BMAX;
+      if (tid < 256) {
+        const int r = tid >> 4, e = tid & 15;
+        if (r < B) {
+          bool first = true;
+          for (int q = 0; q < r; ++q) first = first && ixn[q] != ixn[r];
+          if (first) {
+            emb_item(ixn[r], e, par, ak, nullptr);
+            if (e == 0) need[ixn[r]] = 1;
+          }
+        }
+      }
+    } else {
+      for (int it = tid; it < T * UPC; it += NT) emb_item(it >> 4, it & 15, par, ak, dump);
     }
     __syncthreads();
+    MD_STAMP();
   }
   move_params(a, o, sm, rank, n_own, 1, tid);
   cluster_sync_all();   // no CTA exits while a peer may still push into it
@@ -445,6 +602,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(c
 
 using namespace idff;
 using namespace idff::tmd;
+
+extern "C" int idff_debug_train_md_stamps(int64_t* h_out32) {
+  IDFF_CHECK_ARG(h_out32, "idff_debug_train_md_stamps: null pointer");
+  IDFF_CUDA(cudaMemcpyFromSymbol(h_out32, g_md_stamps, sizeof(long long) * 32));
+  return IDFF_OK;
+}
 
 static int check_md_shape(int32_t D, int32_t T, const char* who) {
   IDFF_CHECK_ARG(D >= 1 && D <= DMAX, "%s: state dimension %d outside [1, %d]", who, D, DMAX);

@@ -267,6 +267,9 @@ int idff_train_steps(int32_t net, float* d_state, const float* d_x0, const float
  * step, block layout). */
 #define IDFF_TRAIN_MD_MAX_BATCH 16
 #define IDFF_TRAIN_MD_MAX_FRAMES 224
+/* Diagnostic: clock64 stamps of the last step of the last idff_train_md_steps launch (CTA 0), h_out32: step start, then the
+ * arrival at / the release from each of the 8 cluster barriers, then step end (18 stamps). */
+int idff_debug_train_md_stamps(int64_t* h_out32);
 int64_t idff_train_md_state_floats(int32_t D, int32_t T);
 int idff_train_md_offsets(int32_t D, int32_t T, int64_t* h_out13);
 int idff_train_md_steps(float* d_state, const float* d_dataset, int32_t T, int32_t D, const int64_t* d_idx, const float* d_t,
