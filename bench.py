@@ -550,6 +550,18 @@ def aux_measurements(dev, pw, model, peaks):
         s_g = timeit(gs.step, reps=200, warm=5)
         tr_out["scorehead_B256"] = {"fused_us_per_step": s_k * 1e6, "fused_samples_per_s": 256 / s_k,
                                     "graph_us_per_step": s_g * 1e6, "graph_samples_per_s": 256 / s_g}
+        # the PolyALA step (MD_simulation.py:126-144, B = 10, MLP_Embedding 175-128-128-128-46 + Embedding(200,128), Adam): the
+        # cluster-resident kernel (8 CTAs hold parameters + moments in shared memory) vs the torch step as a CUDA graph
+        from idff_b200.torchcfm.models.models import MLP_Embedding
+        dsm = (180.0 * torch.sin(torch.cumsum(torch.randn(200, 46, device=dev) * 0.05, 0))).contiguous()
+        torch.manual_seed(0)
+        fm = train.FusedMDTrainer(MLP_Embedding(dim=46, w=128, time_embed=200, time_varying=True).to(dev), dsm, batch_size=10)
+        idm, tm, em = fm.draw(2048)
+        s_k = timeit(lambda: fm.steps(idm, tm, em), reps=5, warm=2) / 2048
+        gm = train.GraphedMDTrainer(MLP_Embedding(dim=46, w=128, time_embed=200, time_varying=True).to(dev), dsm, batch_size=10)
+        s_g = timeit(gm.step, reps=200, warm=5)
+        tr_out["polyala_B10"] = {"fused_us_per_step": s_k * 1e6, "fused_samples_per_s": 10 / s_k,
+                                 "graph_us_per_step": s_g * 1e6, "graph_samples_per_s": 10 / s_g, "fused_steps_per_launch": 2048}
         # the reference's own step on the CPU (torch CPU, all host threads), B = 256
         torch.manual_seed(0)
         netc = MLP(dim=2, w=256, time_varying=True)

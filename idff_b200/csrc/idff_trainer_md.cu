@@ -325,7 +325,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(c
   float* lt = sm + mLT;        // [BMAX][8][3]
   double* lrecv = reinterpret_cast<double*>(sm + mLRECV);   // [CL][3] (CTA 0)
   int* idxb = reinterpret_cast<int*>(sm + mMISC);           // [2][BMAX]: frame indices of the current / the other step (by parity)
-  float* sc = sm + mMISC + 32;                              // [2][2]: step_size, 1 / bc2_sqrt by step parity
+  float* sc = sm + mMISC + 32;                              // [3][2]: step_size, 1 / bc2_sqrt of step s at slot s % 3
   int* rowfirst = reinterpret_cast<int*>(sm + mROW);        // [2][TMAX]: first batch row that uses frame `row` (-1: none), by parity
   int* need = rowfirst + 2 * TMAX;                          // [TMAX]: the next step gathers this embedding row
 
@@ -352,13 +352,19 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(c
 
   const int n_el = B * D;   // (row, dim) elements of a batch: up to 2 per thread
   float px0[2], px1[2], pep[2], ptt[2];
-  int pidx[2];
+  int pidx[2], er[2], ed[2];   // this thread's elements: row, dimension (fixed for the launch)
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int e = tid + q * NT;
+    er[q] = e / D;
+    ed[q] = e - er[q] * D;
+  }
   auto prefetch = [&](int s) {
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       const int e = tid + q * NT;
       if (e < n_el) {
-        const int r = e / D, d = e - r * D;
+        const int r = er[q], d = ed[q];
         long long ix = a.idx[(size_t)s * B + r];
         ix = ix < 1 ? 1 : (ix > T - 1 ? T - 1 : ix);   // frames [1, T): randint(1, T) in the reference (torch would raise outside)
         pidx[q] = (int)ix;
@@ -374,13 +380,21 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(c
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       const int e = tid + q * NT;
-      if (e < n_el && e % D == 0) idxb[par * BMAX + e / D] = pidx[q];
+      if (e < n_el && ed[q] == 0) idxb[par * BMAX + er[q]] = pidx[q];
     }
   };
-  auto adam_of = [&](int par) {
+  double b1pow = a.b1pow, b2pow = a.b2pow;
+  auto adam_of = [&](int slot) {
     AdamK k;
-    k.omb1 = a.omb1; k.omb2 = a.omb2; k.beta2f = a.beta2f; k.eps = a.eps_adam; k.step_size = sc[par * 2]; k.inv_bc2_sqrt = sc[par * 2 + 1];
+    k.omb1 = a.omb1; k.omb2 = a.omb2; k.beta2f = a.beta2f; k.eps = a.eps_adam; k.step_size = sc[slot * 2]; k.inv_bc2_sqrt = sc[slot * 2 + 1];
     return k;
+  };
+  // bias corrections in double like torch's Python scalars; the last thread forms them one step ahead, off the critical path
+  auto step_scalars = [&](int slot) {
+    b1pow *= a.beta1;
+    b2pow *= a.beta2;
+    sc[slot * 2] = (float)(a.lr / (1.0 - b1pow));
+    sc[slot * 2 + 1] = (float)(1.0 / sqrt(1.0 - b2pow));
   };
   // Adam on one element of this CTA's embedding columns with the gradient of step parity `par` (rows of the batch that use the frame)
   auto emb_item = [&](int row, int e, int par, const AdamK& k, float* dump) {
@@ -394,12 +408,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(c
     adam1(k, g, p[0], p[PT], p[2 * PT]);
     if (dump) dump[o.oE + row * W + (int)rank * UPC + e] = g;
   };
-  double b1pow = a.b1pow, b2pow = a.b2pow;
   const uint32_t a1_s = s32(a1), a2_s = s32(a2), a3_s = s32(a3), recv_s = s32(recv);
 
   if (a.n_steps > 0) {
     prefetch(0);
     publish_idx(0);
+    if (tid == NT - 1) step_scalars(0);
   }
   __syncthreads();
 
@@ -424,7 +438,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(c
     for (int q = 0; q < 2; ++q) {
       const int e = tid + q * NT;
       if (e < n_el) {
-        const int r = e / D, d = e - r * D;
+        const int r = er[q], d = ed[q];
         const float t = ptt[q];
         const float st = a.sigma_mode == 0 ? a.sigma : __fmul_rn(a.sigma, __fsqrt_rn(__fmul_rn(t, __fsub_rn(1.0f, t))));
         const float xt = __fadd_rn(__fadd_rn(__fmul_rn(t, px1[q]), __fmul_rn(__fsub_rn(1.0f, t), px0[q])), __fmul_rn(st, pep[q]));
@@ -432,12 +446,6 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(c
         x1s[r * DP + d] = px1[q];
         if (d == 0) cat0[r * C0S + D] = t;
       }
-    }
-    if (tid == 0) {
-      b1pow *= a.beta1;
-      b2pow *= a.beta2;
-      sc[par * 2] = (float)(a.lr / (1.0 - b1pow));
-      sc[par * 2 + 1] = (float)(1.0 / sqrt(1.0 - b2pow));
     }
     if (tid < B) {   // first batch row of every frame in use (duplicates add up in row order)
       bool first = true;
@@ -450,37 +458,43 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(c
     }
     __syncthreads();
     if (s + 1 < a.n_steps) prefetch(s + 1);   // in flight for the whole step
-    const AdamK ak = adam_of(par);
+    const AdamK ak = adam_of(s % 3);
     push_units(stg, B, cat_s, C0S, DP, rank, xb(0), tid);                                 // exchange 0
     MD_STAMP();
-    if (s > 0) {
-      // the previous step's dense Adam update of the embedding rows this step does NOT gather (the gathered ones were updated at
-      // the end of that step): off the critical path, while the pushes of the cluster land
-      const AdamK akp = adam_of(par ^ 1);
-      for (int it = tid; it < T * UPC; it += NT)
-        if (!need[it >> 4]) emb_item(it >> 4, it & 15, par ^ 1, akp, nullptr);
-      __syncthreads();
-      if (tid < B) {
-        need[idxs[tid]] = 0;
-        rowfirst[(par ^ 1) * TMAX + idxb[(par ^ 1) * BMAX + tid]] = -1;
-      }
-    }
+    if (tid == NT - 1 && more) step_scalars((s + 1) % 3);
+    // The previous step's dense Adam update of the embedding rows this step does NOT gather (the gathered ones were updated at the
+    // end of that step) runs in four slices behind the four forward hand-overs, while the pushes of the cluster are in flight.
+    const AdamK akp = adam_of((s + 2) % 3);
+    auto emb_deferred = [&](int q) {
+      if (s > 0)
+        for (int it = tid + q * NT; it < T * UPC; it += 4 * NT)
+          if (!need[it >> 4]) emb_item(it >> 4, it & 15, par ^ 1, akp, nullptr);
+    };
+    emb_deferred(0);
     xwait(0);
     MD_STAMP();
     // ---- forward
     fwd_units(cat0, C0S, K0P / 4, sm + pW0, W0S, sm + pb0, comb, stg, code, tid);
     push_units(stg, B, a1_s, AS, 0, rank, xb(1), tid);                                    // exchange 1
     MD_STAMP();
+    emb_deferred(1);
     xwait(1);
     MD_STAMP();
     fwd_units(a1, AS, W / 4, sm + pW1, WS, sm + pb1, comb, stg, code + BMAX * UPC, tid);
     push_units(stg, B, a2_s, AS, 0, rank, xb(2), tid);                                    // exchange 2
     MD_STAMP();
+    emb_deferred(2);
     xwait(2);
     MD_STAMP();
     fwd_units(a2, AS, W / 4, sm + pW2, WS, sm + pb2, comb, stg, code + 2 * BMAX * UPC, tid);
     push_units(stg, B, a3_s, AS, 0, rank, xb(3), tid);                                    // exchange 3
     MD_STAMP();
+    emb_deferred(3);
+    __syncthreads();
+    if (s > 0 && tid < B) {   // the deferred update is complete: retire its bookkeeping
+      need[idxs[tid]] = 0;
+      rowfirst[(par ^ 1) * TMAX + idxb[(par ^ 1) * BMAX + tid]] = -1;
+    }
     xwait(3);
     MD_STAMP();
     // ---- output layer (this CTA's outputs), periodic loss (MD_simulation.py:137-141) and d loss / d vt
@@ -491,11 +505,13 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(c
       if (valid) {
         const float4* w4 = reinterpret_cast<const float4*>(sm + pW3 + oo * WS);
         const float4* a4 = reinterpret_cast<const float4*>(a3 + r * AS);
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 w = w4[ks + 4 * i], av = a4[ks + 4 * i];
-          acc = fmaf(av.x, w.x, acc); acc = fmaf(av.y, w.y, acc); acc = fmaf(av.z, w.z, acc); acc = fmaf(av.w, w.w, acc);
+          c0 = fmaf(av.x, w.x, c0); c1 = fmaf(av.y, w.y, c1); c2 = fmaf(av.z, w.z, c2); c3 = fmaf(av.w, w.w, c3);
         }
+        acc = (c0 + c1) + (c2 + c3);
       }
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
