@@ -34,14 +34,20 @@ def checkerboard_device(n: int, device, generator=None) -> torch.Tensor:
     return torch.stack([u, v], 1) * 2
 
 
+_CENTERS = {}
+
+
 def eight_gaussians_device(n: int, device, generator=None) -> torch.Tensor:
     """sample_8gaussians (torchcfm/utils.py:12-33,85-86) with the draws taken on the device: 8 modes on a circle of radius 5,
-    noise of covariance sqrt(0.1) I -- i.e. std 0.1**0.25, the reference passes sqrt(var) I as the covariance."""
-    r = 0.5 ** 0.5
-    centers = torch.tensor([(1, 0), (-1, 0), (0, 1), (0, -1), (r, r), (r, -r), (-r, r), (-r, -r)], device=device,
-                           dtype=torch.float32) * 5.0
+    noise of covariance sqrt(0.1) I -- i.e. std 0.1**0.25, the reference passes sqrt(var) I as the covariance.  (The mode table is
+    cached per device: a host-to-device copy cannot be captured into a CUDA graph.)"""
+    key = str(torch.device(device))
+    if key not in _CENTERS:
+        r = 0.5 ** 0.5
+        _CENTERS[key] = torch.tensor([(1, 0), (-1, 0), (0, 1), (0, -1), (r, r), (r, -r), (-r, r), (-r, -r)], device=device,
+                                     dtype=torch.float32) * 5.0
     which = torch.randint(0, 8, (n,), device=device, generator=generator)
-    return centers[which] + torch.randn(n, 2, device=device, generator=generator) * (0.1 ** 0.25)
+    return _CENTERS[key][which] + torch.randn(n, 2, device=device, generator=generator) * (0.1 ** 0.25)
 
 
 def flow_train_step(model, optimizer, FM, x0, x1, t=None, clip: float = 1.0):
