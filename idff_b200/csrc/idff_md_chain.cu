@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(NT, 1) k_md_chain(NetView net, const __grid_co
 
 }  // namespace chain
 
-static int g_chain_fma = 0;   // diagnostic: 1 = the FMA evaluator instead of the mma.sync one (idff_debug_md_chain_fma)
+static thread_local int g_chain_fma = 0;   // diagnostic: 1 = the FMA evaluator instead of the mma.sync one (idff_debug_md_chain_fma)
 void md_chain_set_fma(int on) { g_chain_fma = on ? 1 : 0; }
 
 bool md_chain_supports(const idff_weights_t* w, const idff_field_params_t* p, int64_t K) {

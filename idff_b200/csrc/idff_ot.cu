@@ -402,7 +402,7 @@ static size_t smem_bytes(int n, int dfix) { return (size_t)n * 8 + 64 * sizeof(B
 
 using namespace idff;
 
-static int g_ot_sap = 0;   // diagnostic: 1 = always the augmenting-path kernel (idff_debug_ot_sap)
+static thread_local int g_ot_sap = 0;   // diagnostic: 1 = always the augmenting-path kernel (idff_debug_ot_sap)
 extern "C" int idff_debug_ot_sap(int32_t on) {
   g_ot_sap = on ? 1 : 0;
   return IDFF_OK;

@@ -790,7 +790,7 @@ extern "C" int idff_train_offsets(int32_t net, int64_t* h_out12) {
 }
 extern "C" int idff_train_flow_offsets(int64_t* h_out12) { return idff_train_offsets(IDFF_TRAIN_NET_FLOW, h_out12); }
 
-static int g_pair_mode = 0;   // diagnostic: 1 = run a row group on a CTA pair where possible (idff_debug_train_pair_mode)
+static thread_local int g_pair_mode = 0;   // diagnostic: 1 = run a row group on a CTA pair where possible (idff_debug_train_pair_mode)
 extern "C" int idff_debug_train_pair_mode(int32_t on) {
   g_pair_mode = on ? 1 : 0;
   return IDFF_OK;

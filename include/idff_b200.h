@@ -17,8 +17,9 @@
  *   - a handle serves ONE in-flight call at a time (one stream, one host thread): the scratch above and the per-handle
  *     counters are not keyed by stream.  Use one handle per stream for concurrent sampling with the same network;
  *   - no process-global state on the product path: counters live in the handle (idff_weights_nonfinite).  The idff_debug_*
- *     entry points are process-wide diagnostic switches / read-outs (phase timestamps, alternative evaluators) for tests
- *     and profiling, not for production use.
+ *     switches (alternative evaluators / algorithms) are thread-local: they affect calls made by the thread that set them and
+ *     nothing else; the idff_debug_*_stamps read-outs return device-side phase timestamps of the last launch of that kernel in
+ *     the process, and idff_launch_count() is one process-wide atomic counter -- diagnostics for tests and profiling only.
  */
 #ifndef IDFF_B200_H
 #define IDFF_B200_H
