@@ -404,6 +404,29 @@ def test_md_many_steps_track_the_reference(cuda_device):
     assert (f.cpu() - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
 
 
+def test_md_trainer_is_deterministic_under_load(cuda_device):
+    """The cluster kernel's hand-overs (st.async + mbarrier, no cluster barrier) leave no room for a race to hide: 6 repeats of
+    400 steps at the largest batch, from the same state and draws, must agree bit for bit -- losses, parameters and both moments."""
+    dev, S, B = cuda_device, 400, 16
+    ds, _ = _polyala_case(dev, seed=9)
+    g = torch.Generator().manual_seed(5)
+    idx = torch.randint(1, 200, (S, B), generator=g).to(dev)
+    t = torch.rand(S, B, generator=g).to(dev)
+    eps = torch.randn(S, B, 46, generator=g).to(dev)
+    ref = None
+    for rep in range(6):
+        _, model = _polyala_case(dev, seed=9)
+        tr = train.FusedMDTrainer(model, ds.to(dev), batch_size=B, sigma=0.5)
+        loss = tr.steps(idx, t, eps)
+        snap = (loss.clone(), tr.state.clone())
+        assert torch.isfinite(snap[0]).all() and torch.isfinite(snap[1]).all()
+        if ref is None:
+            ref = snap
+        else:
+            assert torch.equal(snap[0], ref[0]) and torch.equal(snap[1], ref[1]), rep
+    assert ref[0][-1] < ref[0][0]
+
+
 def test_md_trainer_argument_checks(cuda_device):
     dev = cuda_device
     ds, model = _polyala_case(dev, seed=1)
