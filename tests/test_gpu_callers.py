@@ -410,3 +410,29 @@ def test_md_evaluate_model_grid(cuda_device):
     assert all(set(r) == keys and np.isfinite(r["MMD"]) and np.isfinite(r["RMSE_mean"]) for r in rows)
     # degree-valued frames with sigma_kernel = 1: the MMD is dominated by the diagonals, 1/T + 1/(5 T)
     assert rows[0]["MMD"] == pytest.approx(1 / T + 1 / (5 * T), rel=0.05)
+
+
+def test_scorehead_gamma_sweep_is_one_launch_and_equals_per_tuple(cuda_device):
+    """The order-1 script's gamma sweep (example_order1_with_prediction_head.py:305-328) on the score-head field: all tuples in ONE
+    launch of the tcgen05 kernel (k_tc16<score head>, per-set stage tables), bit-identical to per-tuple solves; MMD per tuple."""
+    from idff_b200 import fields, sampler
+    dev = cuda_device
+    pw = packed("scorehead256", dev)
+    x0 = (torch.randn(2048, 2, generator=torch.Generator().manual_seed(2)) / 1.5).to(dev)
+    gr = [0.0, 0.2, 1.0]
+    tuples = [(a, b) for a in gr for b in gr]
+    models = []
+    for g in tuples:
+        models.append(fields.CustomNetModelScoreHead(pw, 0.2, g[0], g[1]))
+    ts = torch.linspace(0, 1, 3)
+    before = _lib.launch_count()
+    outs = sampler.sample_rk4_sweep(models, x0, ts)
+    assert _lib.launch_count() - before <= 2          # the sweep kernel + the fp32 safety net's scan
+    for k, m in enumerate(models):
+        assert torch.equal(outs[k], sampler.sample_rk4(m, x0, ts)), tuples[k]
+    true = (torch.randn(2048, 2, generator=torch.Generator().manual_seed(3)) * 2).to(dev)
+    best, table = sweep.find_best_gammas_mmd(pw, x0, true, gamma_range=gr, nfe=2, score_head=True)
+    assert len(table) == 9 and best in tuples
+    from idff_b200.mmd import compute_mmd_rbf
+    for (g, v), k in zip(table, range(9)):
+        assert abs(v - compute_mmd_rbf(true, outs[k], 1.0)) <= 1e-6 + 1e-4 * abs(v)
