@@ -421,6 +421,17 @@ def aux_measurements(dev, pw, model, peaks):
             nsweep[f"2^{lg}"] = (1 << lg) * 8 / s
             del xn
         aux["sampler_default_particle_sweep_nfe2_particle_steps_per_s"] = nsweep
+        # the reference's own call size (2048 particles, Autograd_example_order2.py:134-137): default route vs the opt-in
+        # 32-particle-tile route (sampler.set_small_n_route), per call incl. launch
+        x2k = torch.randn(2048, 2, device=dev, generator=g) / 1.5
+        ts2 = torch.linspace(0, 1, 3)
+        small = {"default_us": timeit(lambda: sampler.sample_rk4(m2, x2k, ts2), reps=20, warm=5) * 1e6}
+        try:
+            sampler.set_small_n_route(4736)
+            small["opt_in_32_particle_tiles_us"] = timeit(lambda: sampler.sample_rk4(m2, x2k, ts2), reps=20, warm=5) * 1e6
+        finally:
+            sampler.set_small_n_route(0)
+        aux["sampler_2048_particles_nfe2"] = small
     except Exception as exc:
         aux["sampler_particle_sweep_error"] = repr(exc)
     # the exact minibatch-OT coupling of the _dynamic matcher at the reference's batch (256) and PolyALA's (10)

@@ -46,6 +46,7 @@ int tensor16_debug_stamps(long long* h_out, int n);
 
 // idff_sampler_tc16o3.cu: the fused three-jet kernel (order-3 field)
 bool tensor16o3_supports(const idff_weights_t* w, const idff_field_params_t* p);
+bool tensor16o3_can_run(const idff_weights_t* w, const idff_field_params_t* p);
 int tensor16o3_field_eval(const idff_weights_t* w, const idff_field_params_t* p, float t, const float* d_x, float* d_out,
                           int64_t N, bool safe, void* stream);
 int tensor16o3_sample_rk4(const idff_weights_t* w, const idff_field_params_t* p, const float* d_x0, const Stage* stages,
@@ -126,6 +127,12 @@ static std::vector<float> sde_grid(const float* ts, int n_ts, float dt) {
 }  // namespace idff
 
 using namespace idff;
+
+static thread_local int64_t g_small_n = 0;   // solves of at most this many particles take the 32-particle-tile route (0: off)
+extern "C" int idff_tune_small_n_route(int64_t n_max) {
+  g_small_n = n_max;
+  return IDFF_OK;
+}
 
 extern "C" int idff_debug_tensor_stamps(int64_t* h_out32) {
   IDFF_CHECK_ARG(h_out32, "idff_debug_tensor_stamps: null pointer");
@@ -267,6 +274,11 @@ extern "C" int idff_sample_rk4(const idff_weights_t* w, const idff_field_params_
     return wide_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream);
   if ((p->impl == IDFF_IMPL_TENSOR16 || p->impl == IDFF_IMPL_AUTO) && tensor16o3_supports(w, p))   // order 3: three jets
     return tensor16o3_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, p->impl == IDFF_IMPL_AUTO, stream);
+  // opt-in (idff_tune_small_n_route): small solves of the order-1 / order-2 field (the reference's own call: 2048 particles,
+  // Autograd_example_order2.py:134-137) on the three-jet kernel's 32-particle tiles -- twice as many SMs as k_tc16's 64-particle
+  // tiles; the idle third jet costs less than the idle SMs (128 vs 160 us at nfe 2 up to 4736 particles, slower beyond)
+  if (p->impl == IDFF_IMPL_AUTO && N <= g_small_n && tensor16_supports(w, p) && tensor16o3_can_run(w, p))
+    return tensor16o3_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, true, stream);
   if (p->impl == IDFF_IMPL_TENSOR16 || (p->impl == IDFF_IMPL_AUTO && tensor16_supports(w, p)))
     return tensor16_sample_rk4(w, p, d_x0, st.data(), dts.data(), n_iv, d_out_final, d_out_traj, N, stream);
   if (p->impl == IDFF_IMPL_AUTO && w->v.w == 256 && N >= 2048 && !tensor16_supports(w, p)) {

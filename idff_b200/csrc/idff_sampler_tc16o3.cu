@@ -748,6 +748,14 @@ bool tensor16o3_supports(const idff_weights_t* w, const idff_field_params_t* p) 
   return nj == 3;
 }
 
+// ... and can run any momentum field of that network: a jet whose coefficient is zero contributes nothing to the reverse sweep.
+// idff_sample_rk4 uses this for SMALL order-1 / order-2 solves: 32 particles per CTA put 2048 particles on 64 SMs where the
+// 64-particle tiles of k_tc16 reach 32 (measured: see idff_api.cu).
+bool tensor16o3_can_run(const idff_weights_t* w, const idff_field_params_t* p) {
+  const NetView& v = w->v;
+  return v.w == 256 && v.tc16_tiles != nullptr && p->dim == 2 && v.din == 3 && v.dout == 2 && p->variant == IDFF_FIELD_MOMENTUM;
+}
+
 static int verify_launch(idff_weights_t* w, void* stream) {
   if (w->tc_verified & 8) return IDFF_OK;
   int flag = 0;
@@ -763,8 +771,8 @@ static int verify_launch(idff_weights_t* w, void* stream) {
 
 static int launch_o3(const idff_weights_t* w, const idff_field_params_t* p, tc3::TParams& P, const Rk4Table* rk, const Stage* one,
                      void* stream) {
-  if (!tensor16o3_supports(w, p)) {
-    set_error("3xFP16 three-jet sampler: needs a 3-256-256-256-2 network, dim 2, the order-3 momentum field with gamma3 != 0");
+  if (!tensor16o3_can_run(w, p)) {
+    set_error("3xFP16 three-jet sampler: needs a 3-256-256-256-2 network, dim 2, the momentum field");
     return IDFF_EUNSUPPORTED;
   }
   int sms = 148;

@@ -39,6 +39,13 @@ def sample_rk4(model: _FieldBase, x0, t_span, return_traj=False, out=None):
     return traj if return_traj else final
 
 
+def set_small_n_route(n_max: int = 4736):
+    """Opt in (calling thread): AUTO solves of the order-1 / order-2 field with at most n_max particles run on 32-particle tiles
+    (the three-jet kernel with an idle jet) -- 1.25 x faster up to 4736 particles on a B200; results then depend in their last bits
+    on the batch size (see include/idff_b200.h).  0 turns it off (the default)."""
+    _lib.check(_lib.lib().idff_tune_small_n_route(int(n_max)), "idff_tune_small_n_route")
+
+
 def sample_rk4_sweep(models, x0, t_span, out=None):
     """The same x0 and grid solved under every field of `models` (wrappers around ONE packed network that differ in
     gammas / order / sigma): -> (len(models), N, D) = traj[-1] per field.  One launch for the whole sweep where the

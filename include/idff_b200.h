@@ -225,6 +225,13 @@ int idff_train_flow_init(float* d_state, void* stream);
 /* Diagnostic: clock64 stamps of the last step of the last idff_train_flow_steps launch, h_out [n_ctas][8]: per CTA
  * {step start, rows phase done, barrier 1 passed, weight-gradient job done, barrier 2 passed, AdamW done, barrier 3 passed, 0}. */
 int idff_debug_train_stamps(int64_t* h_out, int32_t n_ctas);
+/* Tuning knob (thread-local, default 0 = off): idff_sample_rk4 under IDFF_IMPL_AUTO sends order-1 / order-2 solves of at most n_max
+ * particles on the 3-256-256-256-2 network to the 32-particle-tile kernel (the three-jet kernel with an idle jet) instead of
+ * k_tc16's 64-particle tiles: twice as many SMs for a small batch -- measured 128 vs 160 us for the reference's 2048-particle call
+ * (nfe 2), a gain up to 4736 particles (one wave of 148 CTAs), a loss beyond.  Off by default because the two kernels round
+ * differently: with the knob on, a particle's result depends (in its last bits) on how many particles share the call, and a
+ * sweep is no longer bit-identical to per-tuple solves.  Same parity bounds either way. */
+int idff_tune_small_n_route(int64_t n_max);
 /* Diagnostic: on != 0 makes idff_train_flow_steps run every group of 4 batch rows on a CTA pair (cluster of 2 that splits the
  * units, activation halves exchanged through distributed shared memory; B <= 296) instead of one CTA.  Measured slower; the
  * two modes sum the K-slices of a layer in different (fixed) orders, so they agree to fp32 rounding, not bit for bit. */

@@ -524,3 +524,32 @@ def test_polyala_tensor_kernel_vs_oracle(cuda_device, impl):
         if sel.any():
             r = (got[-1][sel] - want[-1][sel]).abs().max().item()
             assert r <= 1e-3 * max(1.0, float(want[-1][sel].abs().max())), r
+
+
+def test_small_n_route_is_opt_in_and_within_bounds(cuda_device):
+    """idff_tune_small_n_route: small order-2 solves on the 32-particle-tile kernel.  Off by default (AUTO = k_tc16 for every N,
+    so sub-batches reproduce the whole bit for bit); switched on, the golden bounds still hold and large batches are untouched."""
+    g = load_golden("traj2d")
+    x0 = torch.tensor(g["x0"]).to(cuda_device)
+    pw = packed("checkerboard", cuda_device)
+    m = fields.CustomNetModel(pw, 0.2, 0.2, 0.2)
+    raw = fields.CustomNetModel(pw, 0.2, 0.2, 0.2)
+    raw.impl = _lib.IDFF_IMPL_TENSOR16
+    ts = torch.linspace(0, 1, 3)
+    base = sampler.sample_rk4(m, x0, ts)
+    assert torch.equal(base, sampler.sample_rk4(raw, x0, ts))          # default: k_tc16
+    try:
+        sampler.set_small_n_route(4736)
+        small = sampler.sample_rk4(m, x0, ts)
+        _check_drift(small.cpu().numpy(), g["checkerboard_o2_nfe2_g2"][-1] if g["checkerboard_o2_nfe2_g2"].ndim == 3 else g["checkerboard_o2_nfe2_g2"],
+                     g["checkerboard_o2_nfe2_g2_f64"], "small-N route")
+        assert not torch.equal(small, base)                             # a different kernel rounds differently ...
+        assert (small - base).abs().max().item() <= 1e-3
+        big = torch.randn(6000, 2, device=cuda_device) / 1.5
+        assert torch.equal(sampler.sample_rk4(m, big, ts), sampler.sample_rk4(raw, big, ts))   # ... and is not used above n_max
+        m1 = fields.CustomNetModel(pw, 0.2, 0.2, 0.0)                   # one jet
+        o1 = sampler.sample_rk4(m1, x0, ts)
+    finally:
+        sampler.set_small_n_route(0)
+    r = drift_report(o1.cpu().numpy(), sampler.sample_rk4(m1, x0, ts).cpu().numpy())
+    assert r["median"] <= 2e-5 and r["p999"] <= 2e-3, r
