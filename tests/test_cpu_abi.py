@@ -112,3 +112,40 @@ def test_new_entry_points_validate_without_a_gpu():
     assert L.idff_ot_assign(None, None, 5000, 2, None, None, None) == -1
     assert L.idff_ot_assign(None, None, 8, 2, None, None, None) == -1
     assert L.idff_debug_train_stamps(None, 4) == -1
+
+
+def test_round2_trainer_entry_points_validate_without_a_gpu():
+    """Score-head and PolyALA trainers: state layouts follow the modules' parameters() order and shapes; bad arguments are rejected
+    (and empty work accepted) before any device is touched."""
+    L = _lib.lib()
+    from idff_b200.torchcfm.models.models import MLP, MLP_Embedding
+    off = (C.c_int64 * 12)()
+    assert L.idff_train_offsets(1, off) == 0                                         # IDFF_TRAIN_NET_SCOREHEAD
+    o = list(off)
+    sizes = [p.numel() for p in MLP(dim=4, w=256, time_varying=True).parameters()]   # example_order1_with_prediction_head.py:101
+    assert sizes[0] == 256 * 5 and sizes[6] == 4 * 256
+    assert o[0] == 0 and [o[i + 1] - o[i] for i in range(7)] == sizes[:7] and o[8] == sum(sizes)
+    assert L.idff_train_state_floats(1) > o[11] + o[8] and L.idff_train_state_floats(0) == L.idff_train_flow_state_floats()
+    assert L.idff_train_state_floats(7) == -1 and L.idff_train_offsets(7, off) == -1
+    opt = _lib.AdamW(1e-3, 0.9, 0.999, 1e-8, 1e-2, 1.0)
+    fake = C.c_void_p(4096)
+    assert L.idff_train_steps(1, fake, None, None, None, None, 0, 256, 0.0, 1, 0.2, C.byref(opt), 0, None, None, None, None) == 0
+    assert L.idff_train_steps(2, fake, fake, fake, fake, None, 1, 256, 0.0, 1, 0.2, C.byref(opt), 0, None, None, None, None) == -1
+    assert L.idff_train_steps(1, fake, fake, fake, fake, None, 1, 258, 0.0, 1, 0.2, C.byref(opt), 0, None, None, None, None) == -1
+    # PolyALA: MLP_Embedding(dim=46, w=128, time_embed=200) -- embedding first, as module.parameters() yields it
+    off13 = (C.c_int64 * 13)()
+    assert L.idff_train_md_offsets(46, 200, off13) == 0
+    o = list(off13)
+    sizes = [p.numel() for p in MLP_Embedding(dim=46, w=128, time_embed=200, time_varying=True).parameters()]
+    assert sizes[0] == 200 * 128 and sizes[1] == 128 * 175
+    assert o[0] == 0 and [o[i + 1] - o[i] for i in range(8)] == sizes[:8] and o[9] == sum(sizes) == 87086
+    assert o[10] == 0 and o[11] >= o[9] and o[12] == 2 * o[11] and L.idff_train_md_state_floats(46, 200) == 3 * o[11]
+    assert L.idff_train_md_state_floats(48, 200) == -1 and L.idff_train_md_state_floats(46, 500) == -1
+    adam = _lib.AdamW(1e-3, 0.9, 0.999, 1e-8, 0.0, 0.0)
+    assert L.idff_train_md_steps(fake, None, 200, 46, None, None, None, 0, 10, 0.5, 1, C.byref(adam), 0, None, None, None) == 0
+    assert L.idff_train_md_steps(fake, fake, 200, 46, fake, fake, None, 1, 17, 0.5, 1, C.byref(adam), 0, None, None, None) == -1
+    assert b"batch" in L.idff_last_error()
+    decay = _lib.AdamW(1e-3, 0.9, 0.999, 1e-8, 1e-2, 0.0)                            # torch.optim.Adam's weight_decay is L2, not served
+    assert L.idff_train_md_steps(fake, fake, 200, 46, fake, fake, None, 1, 10, 0.5, 1, C.byref(decay), 0, None, None, None) == -1
+    assert L.idff_debug_train_md_stamps(None) == -1
+    assert L.idff_tune_small_n_route(0) == 0
