@@ -10,7 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "idff_b200", "lib", "libidff_b200.so")
 KEY = ("UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UTMALDG", "SYNCS", "FFMA2", "FFMA", "FMUL2", "FADD2", "HMMA", "MUFU",
-       "STL", "LDL", "BSSY", "BSYNC", "STS", "LDS", "LDG", "STG", "ELECT", "R2UR", "F2FP", "BAR", "ATOM", "RED")
+       "STAS", "STL", "LDL", "BSSY", "BSYNC", "STS", "LDS", "LDG", "STG", "ELECT", "R2UR", "F2FP", "BAR", "ATOM", "RED")
 
 
 def main():
