@@ -145,17 +145,22 @@ __device__ __forceinline__ void adam1(const AdamK& k, float g, float& p, float& 
 // of 8 -- per float4 step two weight loads (8 distinct rows, conflict free at stride 132 / 180) and two activation loads serve 16
 // FMAs.  The slices meet in `comb` [8][16][16]; a = selu(z) goes to `stg` [r][u], the derivative code to `code` [r][u].
 // in: [BMAX][is] (complete), Wp: [16][ws] (K4 float4 per row used), bias [16].
-__device__ __forceinline__ void fwd_units(const float* in, int is, int K4, const float* Wp, int ws, const float* bias, float* comb,
-                                          float* stg, float* code, int tid) {
+template <int K4, int IS, int WSTR>
+__device__ __forceinline__ void fwd_units(const float* in, const float* Wp, const float* bias, float* comb, float* stg, float* code,
+                                          int tid) {
+  constexpr int is = IS, ws = WSTR;
   const int kh = tid >> 6, rp = (tid >> 3) & 7, up = tid & 7;
-  const int per = (K4 + 7) >> 3, k0 = kh * per, k1 = min(K4, k0 + per);
+  constexpr int per = (K4 + 7) >> 3;
+  const int k0 = kh * per, k1 = min(K4, k0 + per);
   const float4* w0 = reinterpret_cast<const float4*>(Wp + up * ws);
   const float4* w1 = reinterpret_cast<const float4*>(Wp + (up + 8) * ws);
   const float4* x0 = reinterpret_cast<const float4*>(in + rp * is);
   const float4* x1 = reinterpret_cast<const float4*>(in + (rp + 8) * is);
   float c00 = 0.f, c01 = 0.f, c10 = 0.f, c11 = 0.f;
-#pragma unroll 2
-  for (int k = k0; k < k1; ++k) {
+#pragma unroll
+  for (int kk = 0; kk < per; ++kk) {
+    const int k = k0 + kk;
+    if (k >= k1) break;
     const float4 wa = w0[k], wb = w1[k], xa = x0[k], xb = x1[k];
     c00 = fmaf(xa.x, wa.x, c00); c00 = fmaf(xa.y, wa.y, c00); c00 = fmaf(xa.z, wa.z, c00); c00 = fmaf(xa.w, wa.w, c00);
     c01 = fmaf(xa.x, wb.x, c01); c01 = fmaf(xa.y, wb.y, c01); c01 = fmaf(xa.z, wb.z, c01); c01 = fmaf(xa.w, wb.w, c01);
@@ -229,9 +234,10 @@ __device__ __forceinline__ void gather_recv(const float* recv, const float* code
 
 // weight gradient of J rows x K4 float4 columns, dW[j][k] = sum_{r<B} dz[r][j] * act[r][k], and Adam on the owner's copies.
 // gidx(j, k) -> index in the parameter block (for the gradient dump) or -1 for padding columns.
-template <class GI>
-__device__ __forceinline__ void wgrad_adam(const float* dz, int dzs, int J, const float* act, int as, int K4, float* P, int ws, int B,
-                                           const AdamK& ak, float* dump, GI gidx, int tid) {
+template <int K4, int AST, int WSTR, int DZS, class GI>
+__device__ __forceinline__ void wgrad_adam(const float* dz, int J, const float* act, float* P, int B, const AdamK& ak, float* dump,
+                                           GI gidx, int tid) {
+  constexpr int as = AST, ws = WSTR, dzs = DZS;
   for (int it = tid; it < J * K4; it += NT) {
     const int j = it / K4, k4 = it - j * K4;
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -474,19 +480,19 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(c
     xwait(0);
     MD_STAMP();
     // ---- forward
-    fwd_units(cat0, C0S, K0P / 4, sm + pW0, W0S, sm + pb0, comb, stg, code, tid);
+    fwd_units<K0P / 4, C0S, W0S>(cat0, sm + pW0, sm + pb0, comb, stg, code, tid);
     push_units(stg, B, a1_s, AS, 0, rank, xb(1), tid);                                    // exchange 1
     MD_STAMP();
     emb_deferred(1);
     xwait(1);
     MD_STAMP();
-    fwd_units(a1, AS, W / 4, sm + pW1, WS, sm + pb1, comb, stg, code + BMAX * UPC, tid);
+    fwd_units<W / 4, AS, WS>(a1, sm + pW1, sm + pb1, comb, stg, code + BMAX * UPC, tid);
     push_units(stg, B, a2_s, AS, 0, rank, xb(2), tid);                                    // exchange 2
     MD_STAMP();
     emb_deferred(2);
     xwait(2);
     MD_STAMP();
-    fwd_units(a2, AS, W / 4, sm + pW2, WS, sm + pb2, comb, stg, code + 2 * BMAX * UPC, tid);
+    fwd_units<W / 4, AS, WS>(a2, sm + pW2, sm + pb2, comb, stg, code + 2 * BMAX * UPC, tid);
     push_units(stg, B, a3_s, AS, 0, rank, xb(3), tid);                                    // exchange 3
     MD_STAMP();
     emb_deferred(3);
@@ -539,8 +545,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(c
     partial_scatter<true>(dvt, 8, n_own, sm + pW3, WS, 0, B, recv_s, rank, xb(4), tid);               // exchange 4 -> recv[0]
     MD_STAMP();
     __syncthreads();   // W3 has been read by the partial products
-    wgrad_adam(dvt, 8, n_own, a3, AS, W / 4, sm + pW3, WS, B, ak, dump,
-               [&](int j, int c) { return o.oW3 + ((int)rank * OPC + j) * W + c; }, tid);
+    wgrad_adam<W / 4, AS, WS, 8>(dvt, n_own, a3, sm + pW3, B, ak, dump,
+                                 [&](int j, int c) { return o.oW3 + ((int)rank * OPC + j) * W + c; }, tid);
     bgrad_adam(dvt, 8, n_own, sm + pb3, B, ak, dump, o.ob3 + (int)rank * OPC, tid);
     xwait(4);
     MD_STAMP();
@@ -557,8 +563,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(c
     partial_scatter<true>(dz, UPC, UPC, sm + pW2, WS, 0, B, recv_s + CL * BMAX * UPC * 4, rank, xb(5), tid);   // exchange 5 -> recv[1]
     MD_STAMP();
     __syncthreads();
-    wgrad_adam(dz, UPC, UPC, a2, AS, W / 4, sm + pW2, WS, B, ak, dump,
-               [&](int j, int c) { return o.oW2 + ((int)rank * UPC + j) * W + c; }, tid);
+    wgrad_adam<W / 4, AS, WS, UPC>(dz, UPC, a2, sm + pW2, B, ak, dump,
+                                   [&](int j, int c) { return o.oW2 + ((int)rank * UPC + j) * W + c; }, tid);
     bgrad_adam(dz, UPC, UPC, sm + pb2, B, ak, dump, o.ob2 + (int)rank * UPC, tid);
     __syncthreads();   // dz is rewritten below
     xwait(5);
@@ -568,8 +574,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(c
     partial_scatter<true>(dz, UPC, UPC, sm + pW1, WS, 0, B, recv_s, rank, xb(6), tid);                // exchange 6 -> recv[0]
     MD_STAMP();
     __syncthreads();
-    wgrad_adam(dz, UPC, UPC, a1, AS, W / 4, sm + pW1, WS, B, ak, dump,
-               [&](int j, int c) { return o.oW1 + ((int)rank * UPC + j) * W + c; }, tid);
+    wgrad_adam<W / 4, AS, WS, UPC>(dz, UPC, a1, sm + pW1, B, ak, dump,
+                                   [&](int j, int c) { return o.oW1 + ((int)rank * UPC + j) * W + c; }, tid);
     bgrad_adam(dz, UPC, UPC, sm + pb1, B, ak, dump, o.ob1 + (int)rank * UPC, tid);
     __syncthreads();
     xwait(6);
@@ -580,8 +586,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(c
     partial_scatter<true>(dz, UPC, UPC, sm + pW0, W0S, DP, B, recv_s + CL * BMAX * UPC * 4, rank, xb(7), tid);   // exchange 7 -> recv[1]
     MD_STAMP();
     __syncthreads();
-    wgrad_adam(dz, UPC, UPC, cat0, C0S, K0P / 4, sm + pW0, W0S, B, ak, dump,
-               [&](int j, int c) { const int gc = w0_col(c, D); return gc >= 0 ? o.oW0 + ((int)rank * UPC + j) * o.K0 + gc : -1; }, tid);
+    wgrad_adam<K0P / 4, C0S, W0S, UPC>(dz, UPC, cat0, sm + pW0, B, ak, dump,
+                                       [&](int j, int c) { const int gc = w0_col(c, D); return gc >= 0 ? o.oW0 + ((int)rank * UPC + j) * o.K0 + gc : -1; }, tid);
     bgrad_adam(dz, UPC, UPC, sm + pb0, B, ak, dump, o.ob0 + (int)rank * UPC, tid);
     if (more) publish_idx(par ^ 1);   // the next step's frames (prefetched long ago)
     xwait(7);
