@@ -49,3 +49,19 @@ class MLP_Embedding(nn.Module):
             if bool((frames == f0).all()):      # one frame for the whole batch: folded into the layer-0 bias table
                 return B.mlp_forward(self, x, f0)
         return self.net(torch.cat([x, self.time_index_embedding(ti.long()).squeeze()], dim=-1))
+
+
+class GradModel(nn.Module):
+    """Gradient field of a scalar potential network: x = cat[state, t] -> d/dx sum(action(x)) without its time column
+    (torchcfm/models/models.py:45-53).  Plain autograd with the graph kept (the potential's parameters train through it);
+    no configuration of the hot path uses it -- provided so that `from torchcfm.models.models import *` finds the same names."""
+
+    def __init__(self, action):
+        super().__init__()
+        self.action = action
+
+    def forward(self, x):
+        x = x.requires_grad_(True)
+        potential = self.action(x).sum()
+        (g,) = torch.autograd.grad(potential, x, create_graph=True)
+        return g[:, :-1]

@@ -95,3 +95,29 @@ def test_toy_samplers_equal_reference_functions():
     a = f["eight_normal_sample"](128, 2, scale=5, var=0.1)
     torch.manual_seed(4)
     assert torch.equal(a, U.eight_normal_sample(128, 2, scale=5, var=0.1))
+
+
+def test_mirror_module_surface_equals_reference():
+    """The torchcfm mirror exports what the reference's modules define for the path (plots and torchdyn's moons aside), and the
+    small GradModel wrapper computes what the reference's does (models.py:45-53)."""
+    import ast
+    import os
+    from idff_b200.torchcfm.models import models as mirror
+    ref = R.models()
+    for name in ("MLP", "MLP_Embedding", "GradModel"):
+        assert hasattr(mirror, name) and hasattr(ref, name)
+    torch.manual_seed(0)
+    act = torch.nn.Sequential(torch.nn.Linear(4, 16), torch.nn.Tanh(), torch.nn.Linear(16, 1))
+    x = torch.randn(7, 4)
+    a = ref.GradModel(act)(x.clone())
+    b = mirror.GradModel(act)(x.clone())
+    assert a.shape == (7, 3) and torch.equal(a, b) and b.requires_grad
+    root = "/root/reference/torchcfm"
+    skip = {"plot_trajectories", "plot_trajectories_m", "plt_flow_samples", "sample_moons"}     # presentation / torchdyn
+    import importlib
+    for mod in ("conditional_flow_matching", "conditional_flow_matching_dynamic", "optimal_transport", "utils"):
+        tree = ast.parse(open(os.path.join(root, mod + ".py")).read())
+        want = {n.name for n in tree.body if isinstance(n, (ast.ClassDef, ast.FunctionDef))} - skip
+        have = importlib.import_module("idff_b200.torchcfm." + mod)
+        missing = [n for n in sorted(want) if not hasattr(have, n)]
+        assert not missing, (mod, missing)
