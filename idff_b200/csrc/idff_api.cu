@@ -183,7 +183,10 @@ extern "C" int idff_field_eval(const idff_weights_t* w, const idff_field_params_
   DeviceGuard g(w->device);
   if (p->impl == IDFF_IMPL_LAYERED) return wide_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
   if (p->impl == IDFF_IMPL_TENSOR16 && p->variant == IDFF_FIELD_MD) return md16_field_eval(w, p, t, d_x, d_out, N, stream);
-  if (p->impl == IDFF_IMPL_AUTO && p->variant == IDFF_FIELD_MD && N >= 4096 && md16_supports(w, p)) {   // tensor kernel + safety net
+  // Single evaluations take the tensor-core kernels at every size they serve (round 2: measured 28 vs 91 us for one order-2
+  // evaluation of 256..2048 particles, 23 vs 127 us at order 3, 18.5 vs 41..50 us for the score head --
+  // profiles/microbench/field_eval_latency.py; AUTO adds the safety net's scan, ~4 us).
+  if (p->impl == IDFF_IMPL_AUTO && p->variant == IDFF_FIELD_MD && N >= 256 && md16_supports(w, p)) {   // tensor kernel + safety net
     int rc2 = keep_input(const_cast<idff_weights_t*>(w), &d_x, d_out, false, (size_t)N * p->dim * sizeof(float), stream);
     if (rc2) return rc2;
     rc2 = md16_field_eval(w, p, t, d_x, d_out, N, stream);
@@ -193,7 +196,7 @@ extern "C" int idff_field_eval(const idff_weights_t* w, const idff_field_params_
     return fixup_with_tables(w, p, 0, 1, &st, nullptr, 0, d_x, nullptr, d_out, nullptr, N, stream);
   }
   // order 3 (three jets) on the 3-256-256-256-2 network: the fused three-jet tcgen05 kernel
-  if ((p->impl == IDFF_IMPL_TENSOR16 || (p->impl == IDFF_IMPL_AUTO && N >= 4096)) && tensor16o3_supports(w, p))
+  if ((p->impl == IDFF_IMPL_TENSOR16 || p->impl == IDFF_IMPL_AUTO) && tensor16o3_supports(w, p))
     return tensor16o3_field_eval(w, p, t, d_x, d_out, N, p->impl == IDFF_IMPL_AUTO, stream);
   if (p->impl == IDFF_IMPL_AUTO && w->v.w == 256 && N >= 2048 && !tensor16_supports(w, p)) {
     idff_field_params_t q = *p;   // order 3 at width 256: the layered 3xFP16 engine (see idff_sample_rk4)
@@ -203,7 +206,7 @@ extern "C" int idff_field_eval(const idff_weights_t* w, const idff_field_params_
   if ((p->impl == IDFF_IMPL_TENSOR || p->impl == IDFF_IMPL_AUTO) && wide_supports(w, p) && (p->impl == IDFF_IMPL_TENSOR || N >= 2048))
     return p->impl == IDFF_IMPL_AUTO ? safe_wide_field_eval(w, p, t, d_x, d_x0, d_out, N, stream)
                                      : wide_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
-  if (p->impl == IDFF_IMPL_TENSOR16 || (p->impl == IDFF_IMPL_AUTO && tensor16_supports(w, p) && N >= 4096))
+  if (p->impl == IDFF_IMPL_TENSOR16 || (p->impl == IDFF_IMPL_AUTO && tensor16_supports(w, p)))
     return tensor16_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
   if (p->impl == IDFF_IMPL_TENSOR) return tensor_field_eval(w, p, t, d_x, d_x0, d_out, N, stream);
   if (p->impl == IDFF_IMPL_FUSED || (p->impl == IDFF_IMPL_AUTO && fused_supports(w, p))) {
