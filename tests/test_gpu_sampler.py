@@ -128,6 +128,13 @@ def test_scorehead_tensor_kernel_properties(cuda_device):
             assert r["median"] <= 1e-5 and r["p999"] <= 1e-3, (impl, r)
             sub = sampler.odeint(m, x0[1000:3000].contiguous(), ts, method="rk4")
             assert torch.equal(sub, traj[:, 1000:3000])
+    # BASELINE configs[1] scale (2^22 particles): finite, and any slice of the batch reproduces bit for bit on its own
+    big = (torch.randn(1 << 22, 2, generator=torch.Generator().manual_seed(6)) / 1.5).to(cuda_device)
+    mb = fields.CustomNetModelScoreHead(pw, 0.2, 0.2, 0.3)
+    whole = sampler.sample_rk4(mb, big, ts)
+    assert torch.isfinite(whole).all()
+    for lo, hi in ((0, 64 * 500), (123457, 123457 + 70001), ((1 << 22) - 4099, 1 << 22)):
+        assert torch.equal(sampler.sample_rk4(mb, big[lo:hi].contiguous(), ts), whole[lo:hi]), (lo, hi)
     # range guard: huge inputs overflow the fp16 split; AUTO re-solves exactly those rows in fp32
     xb = x0.clone()
     xb[::7] *= 3.0e4
