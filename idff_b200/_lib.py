@@ -74,6 +74,7 @@ SIGNATURES = {
     "idff_train_flow_steps": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _i32, C.POINTER(AdamW), _i64, _vp, _vp,
                                         _vp, _vp]),
     "idff_tune_small_n_route": (C.c_int, [_i64]),
+    "idff_debug_wide_dense3": (C.c_int, [_i32]),
     "idff_debug_train_md_stamps": (C.c_int, [_vp]),
     "idff_train_md_state_floats": (C.c_int64, [_i32, _i32]),
     "idff_train_md_offsets": (C.c_int, [_i32, _i32, _vp]),

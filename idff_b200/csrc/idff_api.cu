@@ -597,6 +597,12 @@ extern "C" int idff_md_generate(const idff_weights_t* w, const idff_field_params
   return md_chain_run(w, p, n_frames, tab0, stages.data(), d_x_init, d_I_k, d_I_k0, d_y_hat, K, stream);
 }
 
+namespace idff { void wide_set_dense3(int on); }
+extern "C" int idff_debug_wide_dense3(int32_t on) {
+  idff::wide_set_dense3(on);
+  return IDFF_OK;
+}
+
 extern "C" int idff_debug_md_chain_fma(int32_t on) {
   md_chain_set_fma(on);
   return IDFF_OK;

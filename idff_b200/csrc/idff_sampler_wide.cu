@@ -122,6 +122,13 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 // ---- layouts ----------------------------------------------------------------------------------------------------------
 // NJ jets -> PPT particles per column tile; column of (jet j, particle p) = j*PPT + p; columns >= NJ*PPT are padding.
 __host__ __device__ constexpr int ppt_of(int nj) { return nj == 1 ? 128 : (nj == 2 ? 64 : 32); }
+// Three jets x 32 particles fill 96 of a tile's 128 columns: a quarter of every MMA and of every X-tile load is padding.  Plain
+// solves therefore use 40 particles per tile (120 columns) -- five groups of 8 particles on the four group-warps of a lane
+// quarter, the first of which serves a second group (the accumulators are double buffered: there is a whole item of slack).
+// Sweeps keep 32 (a tile must not straddle two parameter sets and the reference's 2048 rows are not a multiple of 40).
+constexpr int kPpt3Dense = 40;
+__host__ __device__ constexpr int hp_of(int ppt) { return ppt == kPpt3Dense ? 8 : ppt / 4; }   // particles per epilogue thread and group
+__host__ __device__ constexpr int ng_of(int ppt) { return ppt / hp_of(ppt); }                    // particle groups per tile: 4, or 5
 
 // byte offset of fp16 element (col, k) inside the X operand of one column tile (KB k-blocks of XT_BYTES)
 __device__ __forceinline__ size_t xt_off(int col, int k, int lo) {
@@ -201,9 +208,8 @@ __device__ __forceinline__ void store_part(float* part, const float (&v)[NV], in
 }
 
 // ---- layer 1 (K = 3): writes the X operand of gemm 0 -------------------------------------------------------------------
-template <int NJ>
+template <int NJ, int PPT>
 __global__ void __launch_bounds__(256) k_wide_l1(const __grid_constant__ WParams P) {
-  constexpr int PPT = ppt_of(NJ);
   const int w = P.w;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < (long)P.n_ctiles * w; idx += (long)gridDim.x * blockDim.x) {
     const int ct = (int)(idx / w), n = (int)(idx - (long)ct * w);
@@ -229,9 +235,9 @@ __global__ void __launch_bounds__(256) k_wide_l1(const __grid_constant__ WParams
 }
 
 // ---- one layer pass -------------------------------------------------------------------------------------------------------
-template <int NJ>
+template <int NJ, int PPT>
 __global__ void __launch_bounds__(NTHREADS, 1) k_wide_layer(const __grid_constant__ WParams P) {
-  constexpr int PPT = ppt_of(NJ), HP = PPT / NPART;
+  constexpr int HP = hp_of(PPT), NG = ng_of(PPT);
   extern __shared__ __align__(1024) unsigned char smem[];
   if ((s32(smem) & 1023u) != 0u) {   // SWIZZLE_128B operands need a 1024-byte aligned base: report and do nothing
     if (threadIdx.x == 0) g_tc_misaligned = 1;
@@ -321,7 +327,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_wide_layer(const __grid_constan
   } else {
     // ===== epilogue warps
     const int lq = warp & 3, h = warp >> 2;
-    const int p0 = h * HP;
     int q = 0;
     uint32_t fphase[2] = {0, 0};
     const int w = P.w;
@@ -332,6 +337,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_wide_layer(const __grid_constan
       fphase[q] ^= 1u;
       tc_fence_after();
       const uint32_t lane_base = tmem + ((uint32_t)(lq * 32) << 16) + q * COL_BUF;
+      unsigned char* xt = P.xout + (size_t)ct * KB * XT_BYTES;
+      // particle groups of this warp: h, and for the 40-particle geometry group 4 on the h == 0 warps.  The accumulator buffer is
+      // handed back to the MMA warp after the LAST group's read-out (double buffered: the next item's MMAs are not waiting for it)
+#pragma unroll 1
+      for (int grp = h; grp < NG; grp += NPART) {
+      const int p0 = grp * HP;
       float acc[NJ][HP];
 #pragma unroll
       for (int j = 0; j < NJ; ++j)
@@ -363,13 +374,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_wide_layer(const __grid_constan
           for (int i = 0; i < 8; ++i) acc[0][c8 * 8 + i] += fmaf(__uint_as_float(c1[i]), LO_INV, __uint_as_float(m1[i]));
         }
       }
-      tc_fence_before();
-      mbar_arrive(&acc_empty[q]);
-      q ^= 1;
-
-      unsigned char* xt = P.xout + (size_t)ct * KB * XT_BYTES;
-      float* stash = P.stash + ((((size_t)ct * MT + mt) * NPART + h) * (NJ * HP)) * 128 + lq * 32 + lane;
-      float* part = P.part + ((((size_t)ct * MT + mt) * 4 + lq) * NPART + h) * (2 * HP);
+      if (grp + NPART >= NG) {
+        tc_fence_before();
+        mbar_arrive(&acc_empty[q]);
+      }
+      float* stash = P.stash + ((((size_t)ct * MT + mt) * NG + grp) * (NJ * HP)) * 128 + lq * 32 + lane;
+      float* part = P.part + ((((size_t)ct * MT + mt) * 4 + lq) * NG + grp) * (2 * HP);
       if (P.gemm == 0) {
         // layer 2 forward: activations of all jets, derivative stash
         const float bb = __ldg(P.net.b1 + n);
@@ -471,6 +481,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_wide_layer(const __grid_constan
         warp_reduce_scatter<2 * HP>(pv, lane);
         store_part<2 * HP>(part, pv, lane);
       }
+      }   // particle groups
+      q ^= 1;
     }
   }
   tc_fence_before();
@@ -479,15 +491,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_wide_layer(const __grid_constan
 }
 
 // ---- sum the partials of a small layer over (m-tile, lane quarter) in a fixed order ----------------------------------------
-template <int NJ>
+template <int NJ, int PPT>
 __global__ void k_wide_sum(const __grid_constant__ WParams P, float* __restrict__ dst) {
-  constexpr int PPT = ppt_of(NJ), HP = PPT / NPART;
+  constexpr int HP = hp_of(PPT), NG = ng_of(PPT);
   for (long o = (long)blockIdx.x * blockDim.x + threadIdx.x; o < P.P * 2; o += (long)gridDim.x * blockDim.x) {
     const long row = o >> 1;
     const int d = (int)(o & 1), ct = (int)(row / PPT), p = (int)(row - (long)ct * PPT), h = p / HP, pl = p - h * HP;
     float s = 0.0f;
     for (int mt = 0; mt < P.MT; ++mt)
-      for (int lq = 0; lq < 4; ++lq) s += P.part[((((size_t)ct * P.MT + mt) * 4 + lq) * NPART + h) * (2 * HP) + 2 * pl + d];
+      for (int lq = 0; lq < 4; ++lq) s += P.part[((((size_t)ct * P.MT + mt) * 4 + lq) * NG + h) * (2 * HP) + 2 * pl + d];
     dst[o] = s;
   }
 }
@@ -559,6 +571,9 @@ bool wide_supports(const idff_weights_t* w, const idff_field_params_t* p) {
   return p->variant == IDFF_FIELD_MOMENTUM || p->variant == IDFF_FIELD_CFM;
 }
 
+static thread_local int g_wide_dense3 = 1;   // diagnostic: 0 = three-jet solves in the 32-particle tile geometry (idff_debug_wide_dense3)
+void wide_set_dense3(int on) { g_wide_dense3 = on ? 1 : 0; }
+
 struct WideScratch {
   unsigned char *xa, *xb;
   float *stash, *part, *pred, *grad, *y, *k1, *k2, *k3, *xs, *x0c;
@@ -576,12 +591,16 @@ static int wide_run(const idff_weights_t* w, const idff_field_params_t* p, int m
   int nj, rev;
   jets_needed(*p, &nj, &rev);
   const NetView& v = w->v;
-  const int W = v.w, MT = W / 128, KB = W / 64, PPT = ppt_of(nj), HP = PPT / NPART;
+  // particles per column tile: 128 / 64 / 32 for 1 / 2 / 3 jets; three-jet solves outside sweeps use the dense 40-particle geometry
+  const bool dense3 = nj == 3 && d_coef == nullptr && g_wide_dense3;
+  auto ppt_for = [&](int njk) { return (njk == 3 && dense3) ? kPpt3Dense : ppt_of(njk); };
+  const int W = v.w, MT = W / 128, KB = W / 64, PPT = ppt_for(nj);
   // chunk of particles whose scratch stays around 3 GB
   // boundary evaluations of a one-jet field run in the two-jet tile geometry (64 particles per tile) so that they too
   // have a free column slot for the split-K accumulation (put_light): twice the column tiles for those evaluations
-  const int nj_light = nj < 2 ? 2 : nj, xmul = ppt_of(nj) / ppt_of(nj_light);
-  const size_t per_ctile = (size_t)2 * xmul * KB * XT_BYTES + (size_t)MT * NPART * nj * HP * 128 * 4 + (size_t)MT * 4 * NPART * 2 * HP * 4;
+  const int nj_light = nj < 2 ? 2 : nj, xmul = ppt_for(nj) / ppt_for(nj_light);
+  // per tile: two X operand buffers, the stash [MT][groups][nj * HP][128] and the partial sums [MT][4][groups][2 * HP] (groups * HP = PPT)
+  const size_t per_ctile = (size_t)2 * xmul * KB * XT_BYTES + (size_t)MT * nj * PPT * 128 * 4 + (size_t)MT * 4 * 2 * PPT * 4;
   long chunk_ctiles = (long)std::max<size_t>(1, ((size_t)3 << 30) / per_ctile);
   const long total_ctiles = (N + PPT - 1) / PPT;
   if (chunk_ctiles > total_ctiles) chunk_ctiles = total_ctiles;
@@ -600,8 +619,8 @@ static int wide_run(const idff_weights_t* w, const idff_field_params_t* p, int m
     unsigned char* b = reinterpret_cast<unsigned char*>(wm->d_stash);
     sc.xa = b; b += (size_t)chunk_ctiles * xmul * KB * XT_BYTES;
     sc.xb = b; b += (size_t)chunk_ctiles * xmul * KB * XT_BYTES;
-    sc.stash = reinterpret_cast<float*>(b); b += (size_t)chunk_ctiles * MT * NPART * nj * HP * 128 * 4;
-    sc.part = reinterpret_cast<float*>(b); b += (size_t)chunk_ctiles * MT * 4 * NPART * 2 * HP * 4;
+    sc.stash = reinterpret_cast<float*>(b); b += (size_t)chunk_ctiles * MT * nj * PPT * 128 * 4;
+    sc.part = reinterpret_cast<float*>(b); b += (size_t)chunk_ctiles * MT * 4 * 2 * PPT * 4;
     float* f = reinterpret_cast<float*>(b);
     const size_t n2 = (size_t)chunkP * 2;
     sc.pred = f; sc.grad = f + n2; sc.y = f + 2 * n2; sc.k1 = f + 3 * n2; sc.k2 = f + 4 * n2; sc.k3 = f + 5 * n2;
@@ -614,9 +633,10 @@ static int wide_run(const idff_weights_t* w, const idff_field_params_t* p, int m
     IDFF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     return IDFF_OK;
   };
-  int rc = set_attr(k_wide_layer<1>);
-  if (!rc) rc = set_attr(k_wide_layer<2>);
-  if (!rc) rc = set_attr(k_wide_layer<3>);
+  int rc = set_attr(k_wide_layer<1, 128>);
+  if (!rc) rc = set_attr(k_wide_layer<2, 64>);
+  if (!rc) rc = set_attr(k_wide_layer<3, 32>);
+  if (!rc) rc = set_attr(k_wide_layer<3, kPpt3Dense>);
   if (rc) return rc;
 
   for (long c0 = 0; c0 < total_ctiles; c0 += chunk_ctiles) {
@@ -630,7 +650,8 @@ static int wide_run(const idff_weights_t* w, const idff_field_params_t* p, int m
     for (int e = 0; e < n_eval; ++e) {
       const Stage& st = stages[e];
       const int heavy = (st.kind == 2 && rev) ? 1 : 0;
-      const int njk = heavy ? nj : nj_light, PPTk = ppt_of(njk);
+      const int njk = heavy ? nj : nj_light, PPTk = ppt_for(njk);
+      const bool d3 = njk == 3 && PPTk == kPpt3Dense;
       const long nctk = (Pn + PPTk - 1) / PPTk;
       WParams P;
       memset(&P, 0, sizeof(P));
@@ -639,9 +660,10 @@ static int wide_run(const idff_weights_t* w, const idff_field_params_t* p, int m
       P.coef = d_coef ? d_coef + (size_t)e * n_sets * 4 : nullptr; P.set_rows = set_rows; P.row0 = row0;
       const int ew_grid = (int)std::min<long>((nctk * W + 255) / 256, (long)sms * 8);
       P.xout = sc.xa;
-      if (njk == 1) k_wide_l1<1><<<ew_grid, 256, 0, s>>>(P);
-      else if (njk == 2) k_wide_l1<2><<<ew_grid, 256, 0, s>>>(P);
-      else k_wide_l1<3><<<ew_grid, 256, 0, s>>>(P);
+      if (njk == 1) k_wide_l1<1, 128><<<ew_grid, 256, 0, s>>>(P);
+      else if (njk == 2) k_wide_l1<2, 64><<<ew_grid, 256, 0, s>>>(P);
+      else if (d3) k_wide_l1<3, kPpt3Dense><<<ew_grid, 256, 0, s>>>(P);
+      else k_wide_l1<3, 32><<<ew_grid, 256, 0, s>>>(P);
       count_launch();
       const int ng = heavy ? 4 : 2;
       const int lgrid = (int)std::min<long>(nctk * MT, (long)sms);
@@ -649,16 +671,18 @@ static int wide_run(const idff_weights_t* w, const idff_field_params_t* p, int m
         P.gemm = g;
         P.xin = (g & 1) ? sc.xb : sc.xa;
         P.xout = (g & 1) ? sc.xa : sc.xb;
-        if (njk == 1) k_wide_layer<1><<<lgrid, NTHREADS, smem, s>>>(P);
-        else if (njk == 2) k_wide_layer<2><<<lgrid, NTHREADS, smem, s>>>(P);
-        else k_wide_layer<3><<<lgrid, NTHREADS, smem, s>>>(P);
+        if (njk == 1) k_wide_layer<1, 128><<<lgrid, NTHREADS, smem, s>>>(P);
+        else if (njk == 2) k_wide_layer<2, 64><<<lgrid, NTHREADS, smem, s>>>(P);
+        else if (d3) k_wide_layer<3, kPpt3Dense><<<lgrid, NTHREADS, smem, s>>>(P);
+        else k_wide_layer<3, 32><<<lgrid, NTHREADS, smem, s>>>(P);
         count_launch();
         if (g == 1 || g == 3) {
           float* dst = g == 1 ? sc.pred : sc.grad;
           const int sg_grid = (int)std::min<long>((Pn * 2 + 255) / 256, (long)sms * 8);
-          if (njk == 1) k_wide_sum<1><<<sg_grid, 256, 0, s>>>(P, dst);
-          else if (njk == 2) k_wide_sum<2><<<sg_grid, 256, 0, s>>>(P, dst);
-          else k_wide_sum<3><<<sg_grid, 256, 0, s>>>(P, dst);
+          if (njk == 1) k_wide_sum<1, 128><<<sg_grid, 256, 0, s>>>(P, dst);
+          else if (njk == 2) k_wide_sum<2, 64><<<sg_grid, 256, 0, s>>>(P, dst);
+          else if (d3) k_wide_sum<3, kPpt3Dense><<<sg_grid, 256, 0, s>>>(P, dst);
+          else k_wide_sum<3, 32><<<sg_grid, 256, 0, s>>>(P, dst);
           count_launch();
         }
       }

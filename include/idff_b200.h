@@ -225,6 +225,9 @@ int idff_train_flow_init(float* d_state, void* stream);
 /* Diagnostic: clock64 stamps of the last step of the last idff_train_flow_steps launch, h_out [n_ctas][8]: per CTA
  * {step start, rows phase done, barrier 1 passed, weight-gradient job done, barrier 2 passed, AdamW done, barrier 3 passed, 0}. */
 int idff_debug_train_stamps(int64_t* h_out, int32_t n_ctas);
+/* Diagnostic (thread-local): on == 0 makes the layered engine run three-jet solves in the 32-particle column-tile geometry
+ * (96 of 128 columns used) instead of the default 40-particle one (120 of 128). */
+int idff_debug_wide_dense3(int32_t on);
 /* Tuning knob (thread-local, default 0 = off): idff_sample_rk4 under IDFF_IMPL_AUTO sends order-1 / order-2 solves of at most n_max
  * particles on the 3-256-256-256-2 network to the 32-particle-tile kernel (the three-jet kernel with an idle jet) instead of
  * k_tc16's 64-particle tiles: twice as many SMs for a small batch -- measured 128 vs 160 us for the reference's 2048-particle call
