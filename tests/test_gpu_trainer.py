@@ -246,7 +246,7 @@ def _fresh_scorehead(device, seed=0):
     return MLP(dim=4, w=256, time_varying=True).to(device)     # example_order1_with_prediction_head.py:101
 
 
-@pytest.mark.parametrize("B,sigma", [(256, 0.0), (64, 0.5)])
+@pytest.mark.parametrize("B,sigma", [(256, 0.0), (64, 0.5), (512, 0.0), (4, 0.3)])
 def test_scorehead_step_gradients_loss_and_update(cuda_device, B, sigma):
     """The order-1 script's step (example_order1_with_prediction_head.py:111-137: MLP(dim=4) on cat[xt, xt, t], flow loss +
     score regression, clip, AdamW lr 1e-3) in the persistent kernel against the oracle's loop on the same weights and draws --
