@@ -316,6 +316,35 @@ def test_scorehead_many_steps_and_field(cuda_device):
     assert dd.median().item() <= 1e-5 and dd.quantile(0.999).item() <= 1e-3
 
 
+def test_scorehead_train_then_sample_end_to_end(cuda_device):
+    """The order-1 script end to end on the device (example_order1_with_prediction_head.py): its MLP(dim=4) trained on 8gaussians
+    by the persistent kernel (flow loss + score regression, lr 1e-3, sigma 0.2; 10 000 steps, a quarter of a second), wrapped in
+    its score-head field, solved by the tcgen05 sampler, judged by the MMD kernel."""
+    from idff_b200 import fields, sampler
+    from idff_b200.mmd import compute_mmd_rbf
+    dev = cuda_device
+    model = _fresh_scorehead(dev, seed=0)
+    tr = train.FusedFlowTrainer(model, batch_size=256, lr=1e-3, score_sigma=0.2, data=train.eight_gaussians_device)
+    for _ in range(10):
+        loss = tr.run(1000)
+    assert torch.isfinite(loss).all() and loss[-1] < 0.25 * tr_first_loss(model, dev)
+    g = torch.Generator(device=dev).manual_seed(1)
+    true_s = train.eight_gaussians_device(2048, dev, generator=g)
+    x0 = torch.randn(2048, 2, device=dev, generator=g) / 1.5
+    field = fields.CustomNetModelScoreHead(model, 0.2, 0.5, 0.0)      # gamma1 = 1/2: the score term vanishes, pure x1hat flow
+    out = sampler.sample_rk4(field, x0, torch.linspace(0, 1, 11))
+    prior, got = compute_mmd_rbf(true_s, x0, 1.0), compute_mmd_rbf(true_s, out, 1.0)
+    print(f"8gaussians, score-head network, 10000 fused training steps, nfe 10: MMD {got:.4f} (prior {prior:.3f}), loss {loss[-1].item():.3f}")
+    assert prior > 0.4 and got < 0.1
+
+
+def tr_first_loss(model, dev):
+    """loss of an untrained score-head network on the same task (a fresh copy, one step)"""
+    fresh = _fresh_scorehead(dev, seed=0)
+    t0 = train.FusedFlowTrainer(fresh, batch_size=256, lr=1e-3, score_sigma=0.2, data=train.eight_gaussians_device)
+    return t0.run(1)[0]
+
+
 def _polyala_case(device, T=200, D=46, seed=0):
     """A PolyALA-shaped data set (180 sin(cumsum(randn 0.05) + phase)) and a fresh MLP_Embedding (MD_simulation.py:118)."""
     from idff_b200.torchcfm.models.models import MLP_Embedding
