@@ -598,14 +598,19 @@ static int wide_run(const idff_weights_t* w, const idff_field_params_t* p, int m
   // chunk of particles whose scratch stays around 3 GB
   // boundary evaluations of a one-jet field run in the two-jet tile geometry (64 particles per tile) so that they too
   // have a free column slot for the split-K accumulation (put_light): twice the column tiles for those evaluations
-  const int nj_light = nj < 2 ? 2 : nj, xmul = ppt_for(nj) / ppt_for(nj_light);
+  // ... and boundary evaluations of a three-jet field outside sweeps need one jet + the split slot only: they too run in the
+  // two-jet geometry (64 particles per tile, all 128 columns used) instead of 40 particles x 3 column slots of which one idles
+  const int nj_light = (nj < 2 || dense3) ? 2 : nj;
+  const int xmul = std::max(1, ppt_for(nj) / ppt_for(nj_light));
   // per tile: two X operand buffers, the stash [MT][groups][nj * HP][128] and the partial sums [MT][4][groups][2 * HP] (groups * HP = PPT)
   const size_t per_ctile = (size_t)2 * xmul * KB * XT_BYTES + (size_t)MT * nj * PPT * 128 * 4 + (size_t)MT * 4 * 2 * PPT * 4;
   long chunk_ctiles = (long)std::max<size_t>(1, ((size_t)3 << 30) / per_ctile);
   const long total_ctiles = (N + PPT - 1) / PPT;
   if (chunk_ctiles > total_ctiles) chunk_ctiles = total_ctiles;
   const long chunkP = chunk_ctiles * PPT;
-  const size_t bytes = (size_t)chunk_ctiles * per_ctile + (size_t)chunkP * 2 * 4 * 8 + 4096;
+  // (boundary evaluations may use a coarser tile geometry: their last tile pads to at most 127 rows beyond the chunk)
+  const size_t part_slack = (size_t)MT * 4 * 2 * 128 * 4;
+  const size_t bytes = (size_t)chunk_ctiles * per_ctile + part_slack + (size_t)chunkP * 2 * 4 * 8 + 4096;
   idff_weights_t* wm = const_cast<idff_weights_t*>(w);
   if (wm->stash_bytes < bytes) {
     if (wm->d_stash) cudaFree(wm->d_stash);
@@ -620,7 +625,7 @@ static int wide_run(const idff_weights_t* w, const idff_field_params_t* p, int m
     sc.xa = b; b += (size_t)chunk_ctiles * xmul * KB * XT_BYTES;
     sc.xb = b; b += (size_t)chunk_ctiles * xmul * KB * XT_BYTES;
     sc.stash = reinterpret_cast<float*>(b); b += (size_t)chunk_ctiles * MT * nj * PPT * 128 * 4;
-    sc.part = reinterpret_cast<float*>(b); b += (size_t)chunk_ctiles * MT * 4 * 2 * PPT * 4;
+    sc.part = reinterpret_cast<float*>(b); b += (size_t)chunk_ctiles * MT * 4 * 2 * PPT * 4 + part_slack;
     float* f = reinterpret_cast<float*>(b);
     const size_t n2 = (size_t)chunkP * 2;
     sc.pred = f; sc.grad = f + n2; sc.y = f + 2 * n2; sc.k1 = f + 3 * n2; sc.k2 = f + 4 * n2; sc.k3 = f + 5 * n2;
