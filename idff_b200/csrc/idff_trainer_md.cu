@@ -87,8 +87,6 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
@@ -311,6 +309,9 @@ __device__ void move_params(const Args& a, const Off& o, float* sm, uint32_t ran
   }
 }
 
+// phase stamp of the last step (CTA 0, thread 0): one predicated store per call site
+#define MD_STAMP() do { if (stamp) g_md_stamps[sti] = clock64(); ++sti; } while (0)
+
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(const Args a) {
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, B = a.B, D = a.D, T = a.T;
@@ -437,7 +438,6 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(c
     float* dump = (a.grad_dump && s == a.n_steps - 1) ? a.grad_dump : nullptr;
     const bool stamp = rank == 0 && tid == 0 && s == a.n_steps - 1;
     int sti = 0;
-#define MD_STAMP() do { if (stamp) g_md_stamps[sti] = clock64(); ++sti; } while (0)
     MD_STAMP();
     // ---- phase 0: path sample (conditional_flow_matching.py:98-123, no contraction), embedding gather + push
 #pragma unroll
@@ -618,6 +618,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(c
   move_params(a, o, sm, rank, n_own, 1, tid);
   cluster_sync_all();   // no CTA exits while a peer may still push into it
 }
+#undef MD_STAMP
 
 }  // namespace tmd
 }  // namespace idff
