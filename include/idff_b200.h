@@ -3,7 +3,7 @@
  * The reference (MrRezaeiUofT/IDFF) is pure Python and has no FFI; each entry point below names the
  * reference interface it replaces (file:line under the reference root).  The host-side mirror of the
  * reference's call conventions (torchcfm matchers, forward(t,x) modules, f/g SDE objects) lives in
- * idff_b200/*.py and reaches these functions through ctypes -- see INTEGRATION.md.
+ * the modules of idff_b200/ and reaches these functions through ctypes -- see INTEGRATION.md.
  *
  * Conventions
  *   - every function returns 0 on success or a negative IDFF_E* code; it never throws and never aborts;
@@ -73,7 +73,7 @@ typedef struct idff_field_params {
 } idff_field_params_t;
 
 int idff_version(void);
-/* first 16 hex digits of the sha256 over the library's sources (csrc/*.cu, csrc/*.cuh in sorted order, this header, the
+/* first 16 hex digits of the sha256 over the library's sources (the .cu and .cuh files of csrc/ in sorted order, this header, the
  * Makefile) as they were when the library was built: lets a caller prove the loaded binary matches its checkout */
 const char* idff_source_hash(void);
 const char* idff_last_error(void);

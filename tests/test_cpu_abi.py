@@ -149,3 +149,30 @@ def test_round2_trainer_entry_points_validate_without_a_gpu():
     assert L.idff_train_md_steps(fake, fake, 200, 46, fake, fake, None, 1, 10, 0.5, 1, C.byref(decay), 0, None, None, None) == -1
     assert L.idff_debug_train_md_stamps(None) == -1
     assert L.idff_tune_small_n_route(0) == 0
+
+
+def test_header_is_valid_c_and_links_from_a_c_program(tmp_path):
+    """include/idff_b200.h is the boundary a non-Python host binds: it must compile as plain C (gcc -std=c99 -pedantic) and a C
+    program that takes the address of every declared entry point must link against libidff_b200.so and run (no GPU touched)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    names = _declared_symbols()
+    src = tmp_path / "abi.c"
+    lines = ['#include "idff_b200.h"', "#include <stdio.h>", "int main(void) {", "  const void* fn[] = {"]
+    lines += [f"    (const void*)&{n}," for n in names]
+    lines += ["  };", "  unsigned i, n = 0;", "  for (i = 0; i < sizeof(fn) / sizeof(fn[0]); ++i) n += fn[i] != 0;",
+              '  printf("%u %d %s\\n", n, idff_version(), idff_source_hash());',
+              "  return idff_sde_num_steps(0, 0, 0.1f) == IDFF_EINVAL ? 0 : 1;", "}"]
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-Wno-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+           "-L", libdir, "-lidff_b200", f"-Wl,-rpath,{libdir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    n, ver, h = r.stdout.split()
+    assert int(n) == len(names) and int(ver) >= 200 and h == _lib.expected_source_hash()
