@@ -176,3 +176,20 @@ def test_header_is_valid_c_and_links_from_a_c_program(tmp_path):
     assert r.returncode == 0, (r.stdout, r.stderr)
     n, ver, h = r.stdout.split()
     assert int(n) == len(names) and int(ver) >= 200 and h == _lib.expected_source_hash()
+
+
+def test_sde_step_count_matches_the_oracle_grid_on_random_grids():
+    """idff_sde_num_steps (torchsde's fixed-step grid: curr_t += dt in fp32, the last step clipped to ts[-1]) against the oracle's
+    restatement on random output grids and step sizes -- host logic only."""
+    import idff_oracle as O
+    rng = np.random.default_rng(0)
+    L = _lib.lib()
+    for _ in range(300):
+        n = int(rng.integers(2, 9))
+        ts = np.sort(rng.uniform(0.0, 1.0, n)).astype(np.float32)
+        ts[0], ts[-1] = 0.0, np.float32(rng.choice([1.0, 0.75, float(ts[-1]) if ts[-1] > ts[0] else 1.0]))
+        ts = np.sort(ts)
+        dt = float(np.float32(rng.choice([0.3, 0.1, 1.0 / 3.0, 0.25, float(rng.uniform(0.05, 0.6))])))
+        got = L.idff_sde_num_steps(ts.ctypes.data_as(C.c_void_p), n, dt)
+        want = len(O.sde_step_grid(torch.tensor(ts), dt)) - 1
+        assert got == want, (ts, dt, got, want)
