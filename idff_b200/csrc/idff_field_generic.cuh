@@ -98,7 +98,7 @@ __device__ __noinline__ void eval_field(const NetView& net, const FieldCfg& cfg,
   const int D = cfg.D, w = net.w;
   const int nblk = MULTI ? (w + nth - 1) / nth : 1;
 
-  // ---- layer-0 input rows: jet 0 = [x, t] (SCOREHEAD: [x, x, t]); jet 1 = d = (1..1, 0); jet 2 = 0
+  // ---- layer-0 input rows: jet 0 = [x, t] (score-head network, din = 2 D + 1: [x, x, t]); jet 1 = d = (1..1, 0); jet 2 = 0
   for (int i = tid; i < net.din_pad * RT; i += nth) {
     const int k = i / RT, r = i - k * RT;
     const int j = r / PB, p = r - j * PB;
@@ -106,7 +106,7 @@ __device__ __noinline__ void eval_field(const NetView& net, const FieldCfg& cfg,
     if (k < net.din) {
       if (j == 0) {
         if (cfg.variant == kRaw) v = rawin[p * net.din + k];
-        else if (cfg.variant == IDFF_FIELD_SCOREHEAD) v = (k < 2 * D) ? xs[p * D + (k % D)] : st.t;
+        else if (net.din == 2 * D + 1) v = (k < 2 * D) ? xs[p * D + (k % D)] : st.t;   // score-head network: cat[x, x, t]
         else v = (k < D) ? xs[p * D + k] : st.t;
       } else if (j == 1) {
         v = (k < D) ? 1.0f : 0.0f;

@@ -87,6 +87,10 @@ int check_field_args(const idff_weights_t* w, const idff_field_params_t* p, cons
       IDFF_CHECK_ARG(p->order >= 1 && p->order <= 3, "%s: order %d not in 1..3", who, p->order);
       /* fallthrough */
     case IDFF_FIELD_CFM:
+      // the order-1 script's CFM comparator runs on its score-head network: cat[x, x, t] -> out[:, :dim] - x0
+      // (example_order1_with_prediction_head.py:335-356)
+      if (v.din == 2 * p->dim + 1 && v.dout == 2 * p->dim) break;
+      /* fallthrough */
     case IDFF_FIELD_MD:
       IDFF_CHECK_ARG(v.din == p->dim + 1 && v.dout == p->dim,
                      "%s: network is %d->%d but the field needs %d->%d (cat[x,t] -> x1hat)", who, v.din, v.dout,

@@ -786,7 +786,8 @@ int keep_input(idff_weights_t* wm, const float** src, const float* d_out, bool f
 bool tensor16_supports(const idff_weights_t* w, const idff_field_params_t* p) {
   const NetView& v = w->v;
   if (v.w != 256 || v.tc16_tiles == nullptr || p->dim != 2) return false;
-  if (p->variant == IDFF_FIELD_SCOREHEAD) return v.din == 5 && v.dout == 4;   // cat[x, x, t] -> (x1hat, st)
+  if (v.din == 5 && v.dout == 4)   // the score-head network, cat[x, x, t] -> (x1hat, st): its field and its CFM comparator
+    return p->variant == IDFF_FIELD_SCOREHEAD || p->variant == IDFF_FIELD_CFM;
   if (v.din != 3 || v.dout != 2) return false;
   if (!(p->variant == IDFF_FIELD_MOMENTUM || p->variant == IDFF_FIELD_CFM)) return false;
   int nj, rev;
@@ -824,7 +825,7 @@ static int launch_tc16(const idff_weights_t* w, const idff_field_params_t* p, tc
   const Rk4Table& rkr = rk ? *rk : rk0;
   const Stage& oner = one ? *one : one0;
   const int smem = tch::Smem::total;
-  const bool sh = p->variant == IDFF_FIELD_SCOREHEAD;
+  const bool sh = w->v.din == 5;   // score-head network (field or CFM comparator): the one-jet instance
   IDFF_CUDA(cudaFuncSetAttribute(sh ? tch::k_tc16<true> : tch::k_tc16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

@@ -40,7 +40,8 @@ extern "C" {
 #define IDFF_FIELD_MOMENTUM 0 /* CustomNetModel, 2D_examples/Autograd_example_order2.py:36-76 (order 2),
                                  Autograd_example_order3.py:34-77 (order 3); order 1 = g2 = g3 = 0 */
 #define IDFF_FIELD_SCOREHEAD 1 /* CustomNetModel, 2D_examples/example_order1_with_prediction_head.py:64-96 */
-#define IDFF_FIELD_CFM 2       /* CFMModel, 2D_examples/Autograd_example_order2.py:310-332 */
+#define IDFF_FIELD_CFM 2       /* CFMModel, 2D_examples/Autograd_example_order2.py:310-332; on a score-head network (din = 2 dim + 1,
+                                  dout = 2 dim) the order-1 script's variant, example_order1_with_prediction_head.py:335-356 */
 #define IDFF_FIELD_MD 3        /* SDE_cal.f, timeseris_example/MD_simulation.py:497-526 */
 
 /* which kernel family serves a sampler call */

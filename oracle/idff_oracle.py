@@ -117,15 +117,19 @@ class FieldScoreHead(torch.nn.Module):
 
 
 class FieldCFM(torch.nn.Module):
-    """CFMModel.forward (Autograd_example_order2.py:310-332): x1-hat(t, x) - x0 captured at t == 0."""
+    """CFMModel.forward (Autograd_example_order2.py:310-332): x1-hat(t, x) - x0 captured at t == 0.  score_head: the order-1
+    script's variant on its MLP(dim=4) (example_order1_with_prediction_head.py:335-356): input cat[xt, xt, t], predictions[:, :2]."""
 
-    def __init__(self, layers):
+    def __init__(self, layers, score_head=False):
         super().__init__()
-        self.layers, self.x0 = layers, None
+        self.layers, self.x0, self.score_head = layers, None, score_head
 
     def forward(self, t, xt):
         t_input = t * torch.ones((xt.shape[0], 1), dtype=xt.dtype)
-        pred = mlp_forward(self.layers, torch.cat([xt, t_input], dim=-1))
+        if self.score_head:
+            pred = mlp_forward(self.layers, torch.cat([xt, xt, t_input], dim=-1))[:, :xt.shape[1]]
+        else:
+            pred = mlp_forward(self.layers, torch.cat([xt, t_input], dim=-1))
         if t == 0:
             self.x0 = xt
         return pred - self.x0

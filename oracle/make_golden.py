@@ -314,7 +314,7 @@ def golden_scorehead256():
     export_weights(net, os.path.join(OUT, "weights_scorehead256.npz"))
     import copy
     net64 = copy.deepcopy(net).double()
-    o1 = R.script_symbols(R.ORDER1, ["CustomNetModel"])
+    o1 = R.script_symbols(R.ORDER1, ["CustomNetModel", "CFMModel"])
     x = x0_2d(256, seed=1) * 3.0
     x0 = x0_2d(1024, seed=0)
     sd = {"x": x.numpy(), "x0": x0.numpy(), "times": np.array(FIELD_TIMES, dtype=np.float32), "gammas": np.array(GAMMAS2[:4])}
@@ -327,6 +327,9 @@ def golden_scorehead256():
                                            for t in FIELD_TIMES])
         sd[f"traj_nfe5_g{gi}"] = O.odeint_rk4(m, x0.clone(), ts).detach()[-1].numpy()
         sd[f"traj_nfe5_g{gi}_f64"] = O.odeint_rk4(m64, x0.double(), ts.double()).detach()[-1].numpy()
+    # the script's CFM comparator on the same network (:335-356)
+    sd["cfm_nfe5"] = O.odeint_rk4(o1["CFMModel"](net, sigma=0, gamma1=0, gamma2=0), x0.clone(), ts).detach()[-1].numpy()
+    sd["cfm_nfe5_f64"] = O.odeint_rk4(o1["CFMModel"](net64, sigma=0, gamma1=0, gamma2=0), x0.double(), ts.double()).detach()[-1].numpy()
     np.savez(os.path.join(OUT, "scorehead256.npz"), **sd)
     print("wrote scorehead256.npz, weights_scorehead256.npz")
 

@@ -101,6 +101,27 @@ def test_rk4_scorehead_vs_golden(cuda_device):
                          med=1e-5, p999=1e-3)
 
 
+def test_cfm_comparator_on_the_scorehead_network(cuda_device):
+    """The order-1 script's CFMModel (example_order1_with_prediction_head.py:335-356): predictions[:, :2] - x0 on the score-head
+    network fed cat[xt, xt, t] -- generic kernel and k_tc16<score head>, one-launch solve and host-stepped forward(t, x) calls,
+    against the end points the reference's own class produces."""
+    g = load_golden("scorehead256")
+    x0 = torch.tensor(g["x0"]).to(cuda_device)
+    pw = packed("scorehead256", cuda_device)
+    ts = torch.linspace(0, 1, 6)
+    for impl in (_lib.IDFF_IMPL_AUTO, _lib.IDFF_IMPL_GENERIC, _lib.IDFF_IMPL_TENSOR16):
+        c = fields.CFMModel(pw)
+        c.impl = impl
+        final = sampler.sample_rk4(c, x0, ts)
+        _check_drift(final.cpu().numpy(), g["cfm_nfe5"], g["cfm_nfe5_f64"], f"scorehead CFM impl={impl}", med=1e-5, p999=1e-3)
+    c = fields.CFMModel(pw)
+    stepped = sampler.odeint(lambda t, x: c(t, x), x0, ts, method="rk4")[-1]
+    r = drift_report(stepped.cpu().numpy(), g["cfm_nfe5"])
+    assert r["median"] <= 1e-5 and r["p999"] <= 1e-3, r
+    with pytest.raises(_lib.IdffError):      # a flow network of another shape is still rejected
+        fields.CFMModel(packed("scorehead", cuda_device))(torch.tensor(0.0), torch.zeros(4, 3, device=cuda_device))
+
+
 def test_scorehead_tensor_kernel_properties(cuda_device):
     """The score-head field on the tcgen05 kernel (k_tc16<SH>) at a ragged size: against the fp32 generic kernel per evaluation
     and over a solve with a trajectory; sub-batches reproduce the whole bit for bit; AUTO = raw kernel on clean particles and the

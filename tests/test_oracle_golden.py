@@ -57,6 +57,8 @@ def test_scorehead_matches_golden(which):
         f = O.FieldScoreHead(layers, 0.2, tuple(g["gammas"][2]))
         tr = O.odeint_rk4(f, torch.tensor(g["x0"]), torch.linspace(0, 1, 6)).numpy()[-1]
         np.testing.assert_array_equal(tr, g["traj_nfe5_g2"])
+        cfm = O.FieldCFM(layers, score_head=True)          # the order-1 script's CFM comparator on the same network
+        np.testing.assert_array_equal(O.odeint_rk4(cfm, torch.tensor(g["x0"]), torch.linspace(0, 1, 6)).numpy()[-1], g["cfm_nfe5"])
 
 
 def test_md_field_matches_golden():
