@@ -60,6 +60,17 @@ constexpr int COL_CORR = 128, COL_STASH = 256;
 
 using namespace tcg;
 
+// One-jet passes leave TMEM columns 256..511 -- the stash of the reverse sweep -- unused: m-tile 1 can accumulate there with its
+// own barrier pair, so the MMA warp does not wait for the read-out of m-tile 0 before it starts m-tile 1.  Used by the score-head
+// instance (every pass is one-jet: +5..9 %, 987 -> 1079 M particle-steps/s at 2^21 particles).  For the boundary evaluations of the
+// momentum instance the same switch measured SLOWER (415 vs 430 M particle-steps/s, profiles/r2_ab_variants.txt run 5): the extra
+// branches raise the spills of the two-jet epilogue (40 -> 56 B) and that costs more than 10 % of the evaluations gain.
+#ifdef IDFF_TC16_NO_LIGHT_DB
+constexpr bool kLightDB = false;
+#else
+constexpr bool kLightDB = true;
+#endif
+
 // phase timestamps (clock64) of CTA 0, first tile, evaluation 1 (an interior one): diagnostic only, compiled in with
 // -DIDFF_TC16_STAMPS (make STAMPS=1); all zero in the production build
 __device__ long long g_tc16_stamps[32];
@@ -122,6 +133,7 @@ __device__ __forceinline__ void store_jet(const uint32_t (&sa)[2], const uint32_
 template <bool SH>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, const __grid_constant__ Stage one) {
+  constexpr bool DB = SH && kLightDB;   // second accumulator set for m-tile 1 of one-jet passes: the score-head instance only (see DB)
   extern __shared__ __align__(1024) unsigned char smem[];
   if ((s32(smem) & 1023u) != 0u) {   // SWIZZLE_128B operands need a 1024-byte aligned base: report and do nothing
     if (threadIdx.x == 0) g_tc16_misaligned = 1;
@@ -135,7 +147,12 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
   uint64_t* acc_free = acc_full + 1;        // epilogue -> MMA: every thread has read its accumulators out
   uint64_t* b_ready = acc_full + 2;         // [2] epilogue -> MMA: k-blocks 0-1 / 2-3 of the next pass are written
   uint64_t* kfree = acc_full + 4;           // MMA -> epilogue: k-blocks 0-1 have been read by both m-tiles of this pass
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 5);
+  // SH: the score-head instance never uses the stash columns, so m-tile 1 accumulates in TMEM columns 256..511 with its own
+  // barrier pair: the MMA warp does not wait for the read-out of m-tile 0 before it starts m-tile 1 (nor for m-tile 1's before the
+  // next pass)
+  uint64_t* acc_full1 = acc_full + 5;
+  uint64_t* acc_free1 = acc_full + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 7);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
@@ -146,6 +163,8 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
     mbar_init(acc_full, 1);
     mbar_init(kfree, 1);
     mbar_init(acc_free, NE);
+    mbar_init(acc_full1, 1);
+    mbar_init(acc_free1, NE);
     mbar_init(&b_ready[0], NE);
     mbar_init(&b_ready[1], NE);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -235,7 +254,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
       const uint32_t ring0 = s32(smem + Smem::ring);
       const bool leader = elect_one();
       int stage = 0;
-      uint32_t phase = 0, fphase = 0, bphase0 = 0, bphase1 = 0;
+      uint32_t phase = 0, fphase = 0, fphase1 = 0, bphase0 = 0, bphase1 = 0;
       for (long it = 0; it < n_iter; ++it)
         for (int e = 0; e < n_eval; ++e) {
           const int gs = set_of(it);
@@ -251,8 +270,13 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
           for (int g = 0; g < ng; ++g) {
             for (int mt = 0; mt < 2; ++mt) {
               long long c0 = mstamp ? clock64() : 0;
-              mbar_wait(acc_free, fphase);   // the previous m-tile's accumulators have been read out
-              fphase ^= 1u;
+              if (DB && !heavy && mt == 1) {
+                mbar_wait(acc_free1, fphase1);   // m-tile 1's own accumulator set (previous one-jet pass) has been read out
+                fphase1 ^= 1u;
+              } else {
+                mbar_wait(acc_free, fphase);   // the previous m-tile's accumulators have been read out
+                fphase ^= 1u;
+              }
               tc_fence_after();
               if (mstamp) g_tc16_stamps[24 + mt] += clock64() - c0;
               for (int kb = 0; kb < NKB; ++kb) {
@@ -278,7 +302,8 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
                 // interior evaluation: [main | corr] += W_hi * [X_hi ; X_lo'] (N = 256), corr += W_lo' * X_hi (N = 128).
                 // boundary evaluation (one jet): rows 0..63 hold X_hi, rows 64..127 X_lo' (the jet-1 hi slot is free), so the
                 // two MMAs are N = 128 and N = 64; accumulator set (kb & 1): [main 64 | corr 64] at columns 128 * (kb & 1)
-                const uint32_t d1 = tmem + (heavy ? 0u : (uint32_t)((kb & 1) * 128)), d2 = d1 + (heavy ? 128u : 64u);
+                const uint32_t d1 = tmem + (heavy ? 0u : (uint32_t)((kb & 1) * 128)) + ((DB && !heavy && mt == 1) ? 256u : 0u),
+                               d2 = d1 + (heavy ? 128u : 64u);
                 const uint32_t i1 = heavy ? idesc_256 : idesc_128, i2 = heavy ? idesc_128 : idesc_64;
                 const uint32_t first = (uint32_t)(heavy ? kb : (kb >> 1));
                 // descriptors advance by 32 bytes (2 address units) per 16-wide k-step; the operand k-block (32 wide) is
@@ -299,7 +324,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
                 __syncwarp();
                 if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
               }
-              if (leader) mma_commit(acc_full);
+              if (leader) mma_commit((DB && !heavy && mt == 1) ? acc_full1 : acc_full);
               __syncwarp();
             }
             if (mstamp) g_tc16_stamps[17 + 2 * g] = clock64();
@@ -426,7 +451,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
     float* red = misc + Smem::f_red;       // [16 warps][32]
     float* sxs = misc + Smem::f_xs;        // stage input of the 64 particles, [p][2]
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16) + p0;   // + (16 << 16) for the upper 16 lanes
-    uint32_t aphase = 0, kphase = 0;
+    uint32_t aphase = 0, aphase1 = 0, kphase = 0;
     // this thread's 8-byte group inside the operand rows of its particles p0 + 4r + c4: operand k-block mt*4 + q, 16-byte
     // chunk (slot >> 1) ^ ((row >> 1) & 3) [SWIZZLE_64B], half slot & 1.  (row >> 1) & 3 = ((r & 1) << 1) | (c4 >> 1).
     uint32_t sa0[2];
@@ -460,33 +485,39 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
              z[i], z[i + 1]);
     };
     // boundary evaluations: jet 0 summed over the two accumulator sets [main 64 | corr 64] at columns 0 and 128
-    auto load_acc2 = [&](float (&z)[HP]) {
+    auto load_acc2 = [&](float (&z)[HP], int buf) {
       uint32_t m0[HP], c0[HP], m1[HP], c1[HP];
-      tmem_ld8(lane_base, m0);
-      tmem_ld8(lane_base + (16u << 16), m0 + 8);
-      tmem_ld8(lane_base + 64, c0);
-      tmem_ld8(lane_base + (16u << 16) + 64, c0 + 8);
-      tmem_ld8(lane_base + 128, m1);
-      tmem_ld8(lane_base + (16u << 16) + 128, m1 + 8);
-      tmem_ld8(lane_base + 192, c1);
-      tmem_ld8(lane_base + (16u << 16) + 192, c1 + 8);
+      const uint32_t lb = lane_base + (buf ? 256u : 0u);
+      tmem_ld8(lb, m0);
+      tmem_ld8(lb + (16u << 16), m0 + 8);
+      tmem_ld8(lb + 64, c0);
+      tmem_ld8(lb + (16u << 16) + 64, c0 + 8);
+      tmem_ld8(lb + 128, m1);
+      tmem_ld8(lb + (16u << 16) + 128, m1 + 8);
+      tmem_ld8(lb + 192, c1);
+      tmem_ld8(lb + (16u << 16) + 192, c1 + 8);
       tmem_wait_ld();
 #pragma unroll
       for (int i = 0; i < HP; ++i)
         z[i] = fmaf(__uint_as_float(c0[i]) + __uint_as_float(c1[i]), LO_INV, __uint_as_float(m0[i]) + __uint_as_float(m1[i]));
     };
-    auto wait_acc = [&]() {
-      mbar_wait(acc_full, aphase);
-      aphase ^= 1u;
+    auto wait_acc = [&](int buf) {
+      if (DB && buf) {
+        mbar_wait(acc_full1, aphase1);
+        aphase1 ^= 1u;
+      } else {
+        mbar_wait(acc_full, aphase);
+        aphase ^= 1u;
+      }
       tc_fence_after();
     };
     auto wait_kfree = [&]() {
       mbar_wait(kfree, kphase);
       kphase ^= 1u;
     };
-    auto release_acc = [&]() {
+    auto release_acc = [&](int buf) {
       tc_fence_before();
-      mbar_arrive(acc_free);
+      mbar_arrive((DB && buf) ? acc_free1 : acc_free);
     };
     // sum over the thread's 4 units, then over the 8 threads that share its particles: v[2r + d] -> lane g keeps v[g]
     auto reduce_units = [&](float (&v)[8]) -> float {
@@ -504,6 +535,7 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
     };
 
     mbar_arrive(acc_free);   // nothing to read out before the very first m-tile
+    if (DB) mbar_arrive(acc_free1);
     for (long it = 0; it < n_iter; ++it) {
       const int gs = set_of(it);
       ebar576();   // the integrator warps have written the tile's start points to sxs
@@ -561,16 +593,17 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
 #pragma unroll 1
         for (int mt = 0; mt < 2; ++mt) {
           const int n0 = mt * 128 + q * 32 + 4 * slot;
-          wait_acc();
+          const int abuf = (DB && !heavy && mt == 1) ? 1 : 0;   // one-jet passes: m-tile 1 has its own accumulator set
+          wait_acc(abuf);
           if (stamp && mt == 0) g_tc16_stamps[2] = clock64();
           float z[HP], zd[HP];
           if (heavy) {
             load_acc(0, z);
             load_acc(1, zd);
           } else {
-            load_acc2(z);
+            load_acc2(z, abuf);
           }
-          release_acc();
+          release_acc(abuf);
           const float4 bb1 = __ldg(reinterpret_cast<const float4*>(P.net.b1 + n0));
           const uint32_t stash = lane_base + COL_STASH + mt * 128;
           uint32_t h0[8], l0[8], h1[8], l1[8];
@@ -618,16 +651,17 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
 #pragma unroll 1
           for (int mt = 0; mt < 2; ++mt) {
             const int n0 = mt * 128 + q * 32 + 4 * slot;
-            wait_acc();
+            const int abuf = (DB && !heavy && mt == 1) ? 1 : 0;
+            wait_acc(abuf);
             if (stamp && mt == 0) g_tc16_stamps[4] = clock64();
             float z[HP], zd[HP];
             if (heavy) {
               load_acc(0, z);
               load_acc(1, zd);
             } else {
-              load_acc2(z);
+              load_acc2(z, abuf);
             }
-            release_acc();
+            release_acc(abuf);
             const float4 bb2 = __ldg(reinterpret_cast<const float4*>(P.net.b2 + n0));
             const float4 uu3 = __ldg(reinterpret_cast<const float4*>(P.net.u3 + n0));
             const float4 w30 = __ldg(reinterpret_cast<const float4*>(P.net.w3 + 0 * W + n0));
@@ -683,12 +717,12 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
           // ---- gemm 2: reverse, layer 3 -> 2
 #pragma unroll 1
           for (int mt = 0; mt < 2; ++mt) {
-            wait_acc();
+            wait_acc(0);
             if (stamp && mt == 0) g_tc16_stamps[7] = clock64();
             float a0[HP], a1[HP];
             load_acc(0, a0);
             load_acc(1, a1);
-            release_acc();
+            release_acc(0);
             {
               const uint32_t stash = lane_base + COL_STASH + mt * 128;
               uint32_t cd[HP], zdu[HP];
@@ -721,12 +755,12 @@ k_tc16(const __grid_constant__ TParams P, const __grid_constant__ Rk4Table rk, c
 #pragma unroll 1
           for (int mt = 0; mt < 2; ++mt) {
             const int n0 = mt * 128 + q * 32 + 4 * slot;
-            wait_acc();
+            wait_acc(0);
             if (stamp && mt == 0) g_tc16_stamps[9] = clock64();
             float a0[HP], a1[HP];
             load_acc(0, a0);
             load_acc(1, a1);
-            release_acc();
+            release_acc(0);
             const float4 wx0 = __ldg(reinterpret_cast<const float4*>(P.net.wt0 + 0 * W + n0));
             const float4 wx1 = __ldg(reinterpret_cast<const float4*>(P.net.wt0 + 1 * W + n0));
             const float4 wtt = __ldg(reinterpret_cast<const float4*>(P.net.wt0 + 2 * W + n0));
