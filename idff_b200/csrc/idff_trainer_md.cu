@@ -14,7 +14,7 @@
 //   * CTA c owns hidden units [16c, 16c+16) of every hidden layer (rows of W0, W1, W2 with their biases), outputs [6c, 6c+6) (rows of
 //     W3) and columns [16c, 16c+16) of the embedding table -- parameter, exp_avg and exp_avg_sq side by side.
 //   * forward:  a layer's input activations [B][128] are complete in every CTA; a CTA computes its 16 units and PUSHES them into the
-//     8 activation buffers of the cluster (st.shared::cluster, 16-byte stores), one hardware cluster barrier per layer.
+//     8 activation buffers of the cluster (16-byte st.async stores that signal the destination's mbarrier), one hand-over per layer.
 //   * backward: dA_{l-1}[r][k] = sum_j dZ_l[r][j] W_l[j][k] is a sum over all units j: a CTA forms the partial sums of its 16 units for
 //     all k and scatters them to the owners of k (reduce-scatter through distributed shared memory, fixed summation order ->
 //     bit-reproducible); the owner applies SELU' (derivative codes kept from the forward pass).
@@ -557,7 +557,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(c
       a.loss_out[s] = ((float)(s0 / n) + (float)(s1 / n)) + (float)(s2 / n);
     }
     // ---- backward through layers 3, 2 (dZ of the owner's units, partials of the next dA; the weight gradients + Adam run
-    // after the CTA has ARRIVED at the layer's cluster barrier, i.e. while its partial sums travel and the peers catch up)
+    // after the CTA has pushed the layer's partial sums, i.e. while they travel and the peers catch up)
     gather_recv(recv, code + 2 * BMAX * UPC, dz, B, tid);
     __syncthreads();
     partial_scatter<true>(dz, UPC, UPC, sm + pW2, WS, 0, B, recv_s + CL * BMAX * UPC * 4, rank, xb(5), tid);   // exchange 5 -> recv[1]
@@ -593,7 +593,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(c
     xwait(7);
     MD_STAMP();
     // ---- embedding: gradient rows of the batch; dense Adam over all T rows, as torch's.  Now: the rows the next step gathers
-    // (the rest follows behind that step's first barrier); last step of the launch: all rows.
+    // (the rest follows behind that step's forward hand-overs); last step of the launch: all rows.
     gather_recv(recv + CL * BMAX * UPC, nullptr, dE, B, tid);
     __syncthreads();
     if (more) {
