@@ -136,6 +136,10 @@ __device__ __forceinline__ uint32_t mapa(const void* p, uint32_t rank) {
 __device__ __forceinline__ void st_cluster(uint32_t addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+// remote store that signals `bytes` on the destination CTA's mbarrier when it has landed (SASS STAS): data and hand-over in one
+__device__ __forceinline__ void st_async_f32(uint32_t addr, float v, uint32_t bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(addr), "f"(v), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
 }
@@ -289,23 +293,23 @@ __device__ void phase_rows(const Args& a, int s, float* smem, int grp, uint32_t 
     for (int c = 0; c < L::DOUT; ++c) w3c[q][c] = __ldcg(P + L::oW3 + c * W + j);
   }
   // publish one value of the next layer's input: own copy + (pair) the peer's copy through distributed shared memory
+  // (pair: the remote copy is a st.async that signals the peer's hand-over barrier of this exchange: actbar[aph & 1])
   auto put = [&](int buf, int r, int j, float v) {
     actb[(buf * R + r) * W + j] = v;
-    if (CL == 2) st_cluster(peer_act + ((buf * R + r) * W + j) * 4, v);
+    if (CL == 2) st_async_f32(peer_act + ((buf * R + r) * W + j) * 4, v, peer_bar + 8u * (aph & 1u));
   };
   // all 256 units of the next layer's input are in place in this CTA (and, pair, this CTA's half in the peer)
   auto layer_sync = [&]() {
     if (CL == 1) {
       csync();
     } else {
-      csync();   // every local and remote write of this CTA's threads is ordered before thread 0's release
-      if (tid == 0) {
-        mbar_arrive_cluster(s32(actbar));
-        mbar_arrive_cluster(peer_bar);
-        mbar_wait_cluster(actbar, aph);   // one poller per CTA: 512 spinning threads slow the hand-over down
-      }
-      aph ^= 1;
-      csync();
+      // exchange number aph: barrier aph & 1, phase (aph >> 1) & 1.  The peer's half (R x 128 values) arrives as st.async stores
+      // that complete_tx on that barrier; thread 0 armed it with the byte count two exchanges ago and re-arms it right after
+      // the wait (the peer cannot push exchange aph + 2 before it has received this CTA's exchange aph + 1).
+      mbar_wait(&actbar[aph & 1u], (aph >> 1) & 1u);
+      if (tid == 0) mbar_arrive_expect_tx(&actbar[aph & 1u], (uint32_t)(R * (W / 2) * 4));
+      ++aph;
+      csync();   // own half: the local stores of every thread
     }
   };
 
@@ -555,7 +559,7 @@ __global__ void __launch_bounds__(NT, 1) k_train_flow(const Args a) {
   using L = Lay<NET>;
   constexpr int NS = G::NS;
   extern __shared__ __align__(128) float smem[];
-  __shared__ __align__(8) uint64_t full[NSMAX], empty[NSMAX], actbar[1];
+  __shared__ __align__(8) uint64_t full[NSMAX], empty[NSMAX], actbar[2];
   __shared__ double sred[NC / 32];
   __shared__ float s_coef, s_step_size, s_bc2_sqrt;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, cta = blockIdx.x;
@@ -564,14 +568,19 @@ __global__ void __launch_bounds__(NT, 1) k_train_flow(const Args a) {
   const bool row_cta = grp < a.B / R;
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], NC / 32); }
-    mbar_init(&actbar[0], 2);   // pair: one arrival per CTA per layer
+    mbar_init(&actbar[0], 1);   // pair: hand-over barriers of the even / odd activation exchanges (armed by thread 0, completed
+    mbar_init(&actbar[1], 1);   // by the bytes of the peer's st.async stores)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (row_cta && tid < R) load_raw(a, 0, tid, grp * R, R, smem + mRAW);
   __syncthreads();
   if (CL == 2) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
+  if (CL == 2 && tid == 0 && row_cta) {
+    mbar_arrive_expect_tx(&actbar[0], (uint32_t)(R * (W / 2) * 4));
+    mbar_arrive_expect_tx(&actbar[1], (uint32_t)(R * (W / 2) * 4));
+  }
   uint32_t cc = 0;    // ring chunks issued (producer) / consumed (consumers): the same sequence on both sides
-  uint32_t aph = 0;   // phase of actbar
+  uint32_t aph = 0;   // activation exchanges done (pair mode)
 
   if (warp == NC / 32) {
     // ---- producer warp: streams this CTA's share of the step's four weight matrices through the ring (pair: the half that
@@ -790,7 +799,7 @@ extern "C" int idff_train_offsets(int32_t net, int64_t* h_out12) {
 }
 extern "C" int idff_train_flow_offsets(int64_t* h_out12) { return idff_train_offsets(IDFF_TRAIN_NET_FLOW, h_out12); }
 
-static thread_local int g_pair_mode = 0;   // diagnostic: 1 = run a row group on a CTA pair where possible (idff_debug_train_pair_mode)
+static thread_local int g_pair_mode = 1;   // 1 (default) = run a row group on a CTA pair where possible; 0 = always one CTA per row group (idff_debug_train_pair_mode)
 extern "C" int idff_debug_train_pair_mode(int32_t on) {
   g_pair_mode = on ? 1 : 0;
   return IDFF_OK;
@@ -831,7 +840,7 @@ static int steps_impl(float* d_state, const float* d_x0, const float* d_x1, cons
   static unsigned long long attr_set = 0;   // bit per device: the attribute is per device, not per process (one static per NET)
   if (dev >= 64 || !((attr_set >> dev) & 1ull)) {
     IDFF_CUDA(cudaFuncSetAttribute(k_train_flow<NET, 1, RMIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    if (NET == 0) IDFF_CUDA(cudaFuncSetAttribute(k_train_flow<0, 2, RMIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    IDFF_CUDA(cudaFuncSetAttribute(k_train_flow<NET, 2, RMIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     if (dev < 64) attr_set |= 1ull << dev;
   }
   Args a;
@@ -847,9 +856,11 @@ static int steps_impl(float* d_state, const float* d_x0, const float* d_x1, cons
   a.b1pow = std::pow(opt->beta1, (double)steps_done); a.b2pow = std::pow(opt->beta2, (double)steps_done);
   cudaStream_t st = (cudaStream_t)stream;
   IDFF_CUDA(cudaMemsetAsync(d_state + L::sBAR, 0, 64 * sizeof(float), st));
-  // one CTA per 4 rows by default.  Opt-in (idff_debug_train_pair_mode, flow network only): a CTA pair (cluster of 2) per 4 rows,
-  // each CTA streaming and computing half of the units -- measured SLOWER (27 vs 25 us/step at B = 256): the five cluster-scope
-  // activation exchanges per step cost more than the halved weight stream and FMA work save
+  // Default where the batch allows it (2 * B / 4 CTAs fit the grid: B <= 296 on 148 SMs): a CTA PAIR (cluster of 2) per 4 rows, each
+  // CTA streaming and computing half of the units, activation halves exchanged through distributed shared memory.  With the
+  // hand-over as st.async stores that signal the peer's mbarrier this measures 22.0 against 25.8 us/step at B = 256 (round 1,
+  // with st.shared::cluster + a cluster-scope arrive / wait per layer, the pair was SLOWER: 27 vs 25 us).  Larger batches, and
+  // idff_debug_train_pair_mode(0): one CTA per 4 rows.
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeCooperative;
   attr[0].val.cooperative = 1;
@@ -862,15 +873,15 @@ static int steps_impl(float* d_state, const float* d_x0, const float* d_x1, cons
   cfg.attrs = attr;
   int pairs = 0;
   const int grid2 = grid & ~1;
-  if (NET == 0 && g_pair_mode && 2 * (B / RMIN) <= grid2 && grid2 >= N_JOBS) {
+  if (g_pair_mode && 2 * (B / RMIN) <= grid2 && grid2 >= N_JOBS) {
     cfg.gridDim = dim3(grid2);
     cfg.numAttrs = 2;
     int ncl = 0;
-    if (cudaOccupancyMaxActiveClusters(&ncl, k_train_flow<0, 2, RMIN>, &cfg) == cudaSuccess && 2 * ncl >= grid2) pairs = 1;
+    if (cudaOccupancyMaxActiveClusters(&ncl, k_train_flow<NET, 2, RMIN>, &cfg) == cudaSuccess && 2 * ncl >= grid2) pairs = 1;
     else (void)cudaGetLastError();
   }
   if (pairs) {
-    IDFF_CUDA(cudaLaunchKernelEx(&cfg, k_train_flow<0, 2, RMIN>, a));
+    IDFF_CUDA(cudaLaunchKernelEx(&cfg, k_train_flow<NET, 2, RMIN>, a));
   } else {
     cfg.gridDim = dim3(grid);
     cfg.numAttrs = 1;

@@ -236,9 +236,10 @@ int idff_debug_wide_dense3(int32_t on);
  * differently: with the knob on, a particle's result depends (in its last bits) on how many particles share the call, and a
  * sweep is no longer bit-identical to per-tuple solves.  Same parity bounds either way. */
 int idff_tune_small_n_route(int64_t n_max);
-/* Diagnostic: on != 0 makes idff_train_flow_steps run every group of 4 batch rows on a CTA pair (cluster of 2 that splits the
- * units, activation halves exchanged through distributed shared memory; B <= 296) instead of one CTA.  Measured slower; the
- * two modes sum the K-slices of a layer in different (fixed) orders, so they agree to fp32 rounding, not bit for bit. */
+/* Thread-local switch, default on: every group of 4 batch rows runs on a CTA pair (cluster of 2 that splits the hidden units,
+ * activation halves exchanged through distributed shared memory with st.async hand-overs) whenever the batch allows it (B <= 296
+ * on 148 SMs); on == 0 forces one CTA per row group.  The two modes sum the K-slices of a layer in different (fixed) orders, so
+ * they agree to fp32 rounding, not bit for bit; each is bit-reproducible in itself. */
 int idff_debug_train_pair_mode(int32_t on);
 int idff_train_flow_steps(float* d_state, const float* d_x0, const float* d_x1, const float* d_t, const float* d_eps,
                           int32_t n_steps, int32_t B, float sigma, int32_t sigma_mode, const idff_adamw_t* opt,
