@@ -547,8 +547,8 @@ def aux_measurements(dev, pw, model, peaks):
                 "fused_samples_per_s": Bt / s_k, "fused_us_per_step": s_k * 1e6,
                 "fused_incl_draws_samples_per_s": Bt / s_d, "fused_e2e_host_inputs_samples_per_s": Bt / s_h,
                 "fused_steps_per_launch": S,
-                "fused_note": "one persistent cooperative kernel; rows phase streams 1 MB of weights per step per CTA "
-                              "through a TMA ring (per-SM L2 ingest bound), 3 grid barriers per step"})
+                "fused_note": "one persistent cooperative kernel; row groups on CTA pairs (B <= 296) that stream half of the weights each "
+                              "through a TMA ring and exchange activation halves by st.async, 3 grid barriers per step"})
         # the order-1 script's step with the score head (MLP(dim=4) on cat[xt, xt, t], flow loss + score regression): the same
         # persistent kernel (IDFF_TRAIN_NET_SCOREHEAD) vs the torch step captured as a CUDA graph
         torch.manual_seed(0)
