@@ -35,7 +35,7 @@
 namespace idff {
 namespace trn {
 
-constexpr int W = 256, RMIN = 4, RMAX = 4, NC = 512, NT = NC + 32, MAXB = IDFF_TRAIN_MAX_BATCH;   // RMIN / RMAX: batch rows per row group (template R of the kernels; both 4 -- 8 rows per CTA pair was measured slower)
+constexpr int W = 256, RMIN = 4, RMAX = 4, NC = 512, NT = NC + 32, MAXB = IDFF_TRAIN_MAX_BATCH;   // RMIN / RMAX: batch rows per row group (template R of the kernels; both 4 -- 8 rows per CTA pair measured slower in both rounds: 33.4 vs 30.1 us at B = 512 with the st.async hand-over, profiles/r2_trainer_pair8_rate.txt)
 constexpr int MDOUT = 4, NSLOT = 6;    // widest output layer served; parameters a thread can own
 constexpr int JOB_W0 = 128, JOB_W3 = 136, JOB_B3 = 144, N_JOBS = 145;
 constexpr int MAX_GRID = 256;

@@ -19,4 +19,4 @@ for B in (256, 128, 296):
         x0, x1, t, _ = ft.draw(1024)
         s = timeit(lambda: ft.steps(x0, x1, t)) / 1024
         print(f"B={B} pair={pair}: {s * 1e6:.2f} us/step", flush=True)
-_lib.lib().idff_debug_train_pair_mode(0)
+_lib.lib().idff_debug_train_pair_mode(1)
