@@ -441,6 +441,9 @@ def aux_measurements(dev, pw, model, peaks):
         for n_ot, d_ot in ((256, 2), (10, 46)):
             xa, xb = torch.randn(n_ot, d_ot, device=dev, generator=g), torch.randn(n_ot, d_ot, device=dev, generator=g) + 1.0
             ot_out[f"n{n_ot}_D{d_ot}_us"] = timeit(lambda: otm.ot_assign(xa, xb), reps=5, warm=1) * 1e6
+            # the couplings of 1024 training steps in one launch, one CTA per minibatch (idff_ot_assign_batch)
+            xa, xb = torch.randn(1024, n_ot, d_ot, device=dev, generator=g), torch.randn(1024, n_ot, d_ot, device=dev, generator=g) + 1.0
+            ot_out[f"n{n_ot}_D{d_ot}_batch1024_us_per_problem"] = timeit(lambda: otm.ot_assign_batch(xa, xb), reps=3, warm=1) * 1e6 / 1024
         aux["ot_assign"] = ot_out
     except Exception as exc:
         aux["ot_assign_error"] = repr(exc)

@@ -45,6 +45,9 @@ template <int DFIX>
 __global__ void __launch_bounds__(MAXN, 1) k_ot_assign(const float* __restrict__ x0, const float* __restrict__ x1, int n, int D,
                                                        int64_t* __restrict__ perm, double* __restrict__ cost_out) {
   extern __shared__ __align__(16) unsigned char smraw[];
+  x0 += (size_t)blockIdx.x * n * D; x1 += (size_t)blockIdx.x * n * D;   // one CTA per problem of a batch (idff_ot_assign_batch)
+  perm += (size_t)blockIdx.x * n;
+  if (cost_out) cost_out += blockIdx.x;
   double* u = reinterpret_cast<double*>(smraw);                    // [n] row duals
   Best* wbest = reinterpret_cast<Best*>(u + n);                     // [2][32]
   int* col4row = reinterpret_cast<int*>(wbest + 64);                // [n]
@@ -195,6 +198,9 @@ template <int DFIX>
 __global__ void __launch_bounds__(512, 1) k_ot_auction(const float* __restrict__ x0, const float* __restrict__ x1, int n, int D,
                                                        int64_t* __restrict__ perm, double* __restrict__ cost_out) {
   extern __shared__ __align__(16) unsigned char smraw[];
+  x0 += (size_t)blockIdx.x * n * D; x1 += (size_t)blockIdx.x * n * D;   // one CTA per problem of a batch (idff_ot_assign_batch)
+  perm += (size_t)blockIdx.x * n;
+  if (cost_out) cost_out += blockIdx.x;
   double* price = reinterpret_cast<double*>(smraw);                                // [n]
   double* bidval = price + n;                                                      // [n] bid of row i this round
   unsigned long long* maxbid = reinterpret_cast<unsigned long long*>(bidval + n);  // [n] highest bid on column j (bit pattern)
@@ -408,30 +414,40 @@ extern "C" int idff_debug_ot_sap(int32_t on) {
   return IDFF_OK;
 }
 
-extern "C" int idff_ot_assign(const float* d_x0, const float* d_x1, int32_t n, int32_t D, int64_t* d_perm, double* d_cost,
-                              void* stream) {
+// P independent problems (x0, x1 [P][n][D] -> perm [P][n], cost [P]), one CTA each: the kernels are latency-bound one-CTA solvers,
+// so a batch of problems -- the minibatches of the next S training steps, which do not depend on the parameters -- fills the
+// machine: several CTAs per SM, 148 SMs.
+extern "C" int idff_ot_assign_batch(const float* d_x0, const float* d_x1, int32_t n_problems, int32_t n, int32_t D, int64_t* d_perm,
+                                    double* d_cost, void* stream) {
   IDFF_CHECK_ARG(n >= 0 && n <= ot::MAXN, "idff_ot_assign: n = %d outside [0, %d]", n, ot::MAXN);
   IDFF_CHECK_ARG(D >= 1, "idff_ot_assign: D = %d", D);
-  if (n == 0) return IDFF_OK;
+  IDFF_CHECK_ARG(n_problems >= 0 && n_problems <= (1 << 20), "idff_ot_assign_batch: n_problems = %d outside [0, 2^20]", n_problems);
+  if (n == 0 || n_problems == 0) return IDFF_OK;
   IDFF_CHECK_ARG(d_x0 && d_x1 && d_perm, "idff_ot_assign: null pointer");
   PtrDeviceGuard guard(d_perm);
   cudaStream_t s = (cudaStream_t)stream;
+  const dim3 grid(n_problems);
   if (n > 64 && !g_ot_sap) {   // auction: parallel over the unassigned rows
     const size_t sm = ot::auction_smem_bytes(n, D == 2 ? 2 : 0);
     if (D == 2) {
       IDFF_CUDA(cudaFuncSetAttribute(ot::k_ot_auction<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      ot::k_ot_auction<2><<<1, 512, sm, s>>>(d_x0, d_x1, n, D, d_perm, d_cost);
+      ot::k_ot_auction<2><<<grid, 512, sm, s>>>(d_x0, d_x1, n, D, d_perm, d_cost);
     } else {
       IDFF_CUDA(cudaFuncSetAttribute(ot::k_ot_auction<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      ot::k_ot_auction<0><<<1, 512, sm, s>>>(d_x0, d_x1, n, D, d_perm, d_cost);
+      ot::k_ot_auction<0><<<grid, 512, sm, s>>>(d_x0, d_x1, n, D, d_perm, d_cost);
     }
   } else {                     // augmenting paths: small problems, and the yardstick behind idff_debug_ot_sap
     const int threads = ((n + 31) / 32) * 32;
     const size_t sm = ot::smem_bytes(n, D == 2 ? 2 : 0);
-    if (D == 2) ot::k_ot_assign<2><<<1, threads, sm, s>>>(d_x0, d_x1, n, D, d_perm, d_cost);
-    else ot::k_ot_assign<0><<<1, threads, sm, s>>>(d_x0, d_x1, n, D, d_perm, d_cost);
+    if (D == 2) ot::k_ot_assign<2><<<grid, threads, sm, s>>>(d_x0, d_x1, n, D, d_perm, d_cost);
+    else ot::k_ot_assign<0><<<grid, threads, sm, s>>>(d_x0, d_x1, n, D, d_perm, d_cost);
   }
   IDFF_CUDA(cudaGetLastError());
   count_launch();
   return IDFF_OK;
+}
+
+extern "C" int idff_ot_assign(const float* d_x0, const float* d_x1, int32_t n, int32_t D, int64_t* d_perm, double* d_cost,
+                              void* stream) {
+  return idff_ot_assign_batch(d_x0, d_x1, 1, n, D, d_perm, d_cost, stream);
 }

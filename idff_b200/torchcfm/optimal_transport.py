@@ -37,6 +37,27 @@ def ot_assign(x0: torch.Tensor, x1: torch.Tensor, return_cost: bool = False):
     return (perm, cost) if return_cost else perm
 
 
+def ot_assign_batch(x0: torch.Tensor, x1: torch.Tensor, return_cost: bool = False):
+    """The couplings of P independent minibatch pairs in ONE launch (`idff_ot_assign_batch`, one CTA per problem): x0, x1
+    (P, n, ...) -> perm (P, n) int64 [, cost (P,) fp64]; row p is exactly ot_assign(x0[p], x1[p]).  The minibatches of the next
+    P training steps do not depend on the parameters, so they are coupled together: at n = 256 a launch of 1024 problems costs
+    what a handful of single ones do."""
+    _lib.require_cuda(x0, "x0")
+    _lib.require_cuda(x1, "x1")
+    if x0.dim() < 3 or x0.shape[:2] != x1.shape[:2]:
+        raise _lib.IdffError(f"ot_assign_batch needs x0, x1 of shape (P, n, ...) with equal P and n, got {tuple(x0.shape)} and {tuple(x1.shape)}")
+    P, n = int(x0.shape[0]), int(x0.shape[1])
+    a = x0.detach().reshape(P, n, -1).contiguous()
+    b = x1.detach().reshape(P, n, -1).contiguous()
+    if a.shape[2] != b.shape[2]:
+        raise _lib.IdffError(f"x0 and x1 differ in dimension: {a.shape[2]} vs {b.shape[2]}")
+    perm = torch.empty((P, n), dtype=torch.int64, device=a.device)
+    cost = torch.zeros(P, dtype=torch.float64, device=a.device) if return_cost else None
+    _lib.check(_lib.lib().idff_ot_assign_batch(_lib.ptr(a), _lib.ptr(b), P, n, int(a.shape[2]), _lib.ptr(perm), _lib.ptr(cost),
+                                               _lib.stream_of(a)), "idff_ot_assign_batch")
+    return (perm, cost) if return_cost else perm
+
+
 class OTPlanSampler:
     def __init__(self, method: str = "exact"):
         if method != "exact":
@@ -80,6 +101,19 @@ class OTPlanSampler:
     def sample_plan(self, x0, x1, replace=True):
         i, j = self.sample_map_indices(x0, x1, replace=replace)
         return x0[i], x1[j]
+
+    def sample_plan_batch(self, x0, x1, generator=None):
+        """sample_plan for P independent minibatch pairs at once (CUDA tensors (P, n, ...)): one batched assignment launch, index
+        pairs drawn with replacement per problem as sample_map does -> (x0[p][i_p], x1[p][perm_p[i_p]]) stacked over p.  What a
+        many-steps-per-launch trainer calls once for the draws of all its steps (train.FusedFlowTrainer(ot_pairing=True))."""
+        perm = ot_assign_batch(x0, x1)
+        P, n = perm.shape
+        i = torch.randint(0, n, (P, n), device=x0.device, generator=generator)
+        j = torch.gather(perm, 1, i)
+        tail = (1,) * (x0.dim() - 2)
+        gi = i.view(P, n, *tail).expand(P, n, *x0.shape[2:])
+        gj = j.view(P, n, *tail).expand(P, n, *x1.shape[2:])
+        return torch.gather(x0, 1, gi), torch.gather(x1, 1, gj)
 
     def sample_plan_with_labels(self, x0, x1, y0=None, y1=None, replace=True):
         """(x0[i], x1[j], y0[i], y1[j]) for index pairs drawn from the plan (reference :144-179)."""

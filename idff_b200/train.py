@@ -203,8 +203,10 @@ class FusedFlowTrainer:
 
     def __init__(self, model: torch.nn.Module, batch_size: int = 256, sigma: float = 0.0, lr: float = 2e-4,
                  betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2, clip: float = 1.0,
-                 data=checkerboard_device, exact_ot_sigma: bool = True, score_sigma=None):
+                 data=checkerboard_device, exact_ot_sigma: bool = True, score_sigma=None, ot_pairing: bool = False):
         L = _lib.lib()
+        self.ot_pairing = bool(ot_pairing)   # draw(): couple every step's (x0, x1) minibatch by the exact OT plan, as the
+        # `_dynamic` matcher's sample_plan does per step (conditional_flow_matching_dynamic.py:268) -- all steps in one launch
         params = [p for p in model.parameters()]
         shapes = [tuple(p.shape) for p in params]
         self.net = 0 if score_sigma is None else 1      # IDFF_TRAIN_NET_FLOW / IDFF_TRAIN_NET_SCOREHEAD
@@ -290,6 +292,9 @@ class FusedFlowTrainer:
         """Device draws for n_steps steps: x1 ~ data, x0 = randn_like, t ~ U(0,1) (order2.py:92-95; t on the device)."""
         x1 = self.data(n_steps * self.B, self.device).view(n_steps, self.B, 2).contiguous()
         x0 = torch.randn_like(x1)
+        if self.ot_pairing:
+            from .torchcfm.optimal_transport import OTPlanSampler
+            x0, x1 = OTPlanSampler().sample_plan_batch(x0, x1)
         t = torch.rand(n_steps, self.B, device=self.device)
         eps = torch.randn_like(x1) if self.sigma != 0.0 else None
         return x0, x1, t, eps

@@ -300,6 +300,12 @@ int idff_train_md_steps(float* d_state, const float* d_dataset, int32_t T, int32
  * epsilon-scaling auction, exact up to plans whose costs differ by less than n max(c) 2^-40). */
 int idff_debug_ot_sap(int32_t on);
 int idff_ot_assign(const float* d_x0, const float* d_x1, int32_t n, int32_t D, int64_t* d_perm, double* d_cost, void* stream);
+/* n_problems independent couplings in ONE launch, one CTA per problem: d_x0, d_x1 [n_problems][n][D] -> d_perm [n_problems][n],
+ * d_cost [n_problems] (may be NULL); every problem gets exactly the result idff_ot_assign returns for it.  The solvers are
+ * latency-bound one-CTA kernels, so the minibatches of the next S training steps -- they do not depend on the parameters -- are
+ * coupled together and fill the machine (n = 256: 1024 problems in one launch cost what 7-8 single problems cost).  n_problems <= 2^20. */
+int idff_ot_assign_batch(const float* d_x0, const float* d_x1, int32_t n_problems, int32_t n, int32_t D, int64_t* d_perm,
+                         double* d_cost, void* stream);
 
 /* ---- TrajectoryGenerator.generate_trajectories, timeseris_example/MD_simulation.py:197-213 -- n_frames
  * sequential solves  x1 = sdeint(SDE_cal(model, gamma2 = gamma2 / (1 + f), init_ind = f, dt, ...), x1, ts, dt)[-1],  f = 0 ..

@@ -121,3 +121,52 @@ def test_wasserstein_distance(cuda_device):
     assert 0 < w1 <= w2 + 1e-9                                                        # W1 <= W2
     with pytest.raises(ValueError):
         ot.wasserstein(x0, x1, method="sinkhorn")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("P,n,D", [(7, 10, 46), (40, 256, 2), (300, 64, 2), (5, 100, 3)])
+def test_batched_couplings_equal_single_calls(cuda_device, P, n, D):
+    """idff_ot_assign_batch: one CTA per problem -> every row is exactly the single-problem result (same permutation, same
+    fp64 cost bits), and a sample of them is scipy's optimum."""
+    from scipy.optimize import linear_sum_assignment
+    g = torch.Generator().manual_seed(100 + P)
+    x0, x1 = torch.randn(P, n, D, generator=g), torch.randn(P, n, D, generator=g) * 1.5 + 0.3
+    a, b = x0.to(cuda_device), x1.to(cuda_device)
+    perm, cost = ot.ot_assign_batch(a, b, return_cost=True)
+    assert perm.shape == (P, n) and cost.shape == (P,)
+    for p in list(range(min(P, 6))) + [P - 1]:
+        ps, cs = ot.ot_assign(a[p], b[p], return_cost=True)
+        assert torch.equal(ps, perm[p]) and cs.item() == cost[p].item()
+        M = (torch.cdist(x0[p].double(), x1[p].double()) ** 2).numpy()
+        r, c = linear_sum_assignment(M)
+        assert np.array_equal(perm[p].cpu().numpy(), c)
+    assert all(sorted(row.tolist()) == list(range(n)) for row in perm.cpu())
+
+
+@pytest.mark.gpu
+def test_batched_plan_sampling_and_ot_paired_trainer(cuda_device):
+    """OTPlanSampler.sample_plan_batch returns, per problem, rows of x0 paired with their OT partners (the reference's sample_plan
+    per step, conditional_flow_matching_dynamic.py:268); FusedFlowTrainer(ot_pairing=True) trains on such pairs: the coupled
+    pairs are shorter than the independent ones, and the loss goes down."""
+    from idff_b200 import train
+    from idff_b200.torchcfm.models.models import MLP
+    dev = cuda_device
+    g = torch.Generator(device=dev).manual_seed(3)
+    x0 = torch.randn(12, 64, 2, device=dev, generator=g)
+    x1 = torch.randn(12, 64, 2, device=dev, generator=g) * 2.0
+    s0, s1 = ot.OTPlanSampler().sample_plan_batch(x0, x1, generator=g)
+    perm = ot.ot_assign_batch(x0, x1)
+    for p in range(12):
+        for r in range(0, 64, 7):
+            i = (x0[p] == s0[p, r]).all(dim=1).nonzero()[0, 0]
+            assert torch.equal(s1[p, r], x1[p, perm[p, i]])
+    torch.manual_seed(0)
+    tr = train.FusedFlowTrainer(MLP(dim=2, w=256, time_varying=True).to(dev), batch_size=64, ot_pairing=True)
+    a0, a1, _, _ = tr.draw(16)
+    tr.ot_pairing = False
+    b0, b1, _, _ = tr.draw(16)
+    tr.ot_pairing = True
+    assert ((a1 - a0) ** 2).sum(-1).mean() < 0.8 * ((b1 - b0) ** 2).sum(-1).mean()
+    first = tr.run(64).mean().item()
+    tr.run(1024)
+    assert tr.run(64).mean().item() < first
