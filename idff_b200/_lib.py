@@ -66,6 +66,7 @@ SIGNATURES = {
     "idff_mmd_rbf_sweep": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _f32, _vp, _vp]),
     "idff_debug_ot_sap": (C.c_int, [_i32]),
     "idff_ot_assign": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "idff_debug_ot_threads": (C.c_int, [_i32]),
     "idff_ot_assign_batch": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "idff_train_flow_state_floats": (C.c_int64, []),
     "idff_train_flow_offsets": (C.c_int, [_vp]),

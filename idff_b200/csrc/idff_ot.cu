@@ -382,17 +382,15 @@ __global__ void __launch_bounds__(512, 1) k_ot_auction(const float* __restrict__
   }
   __syncthreads();
   for (int i = tid; i < n; i += blockDim.x) perm[i] = (int64_t)mine[i];
-  if (cost_out) {
-    double c = 0.0;
-    for (int i = tid; i < n; i += blockDim.x) c += cost(i, mine[i]);
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
-    if (lane == 0) wred[warp] = c;
+  if (cost_out) {   // total cost in an order that does not depend on the block size: per-row costs, then warp 0 (lane l sums rows l, l + 32, ...)
+    for (int i = tid; i < n; i += blockDim.x) bidval[i] = cost(i, mine[i]);
     __syncthreads();
-    if (tid == 0) {
-      double t = 0.0;
-      for (int w = 0; w < nwarps; ++w) t += wred[w];
-      *cost_out = t;
+    if (warp == 0) {
+      double c = 0.0;
+      for (int i = lane; i < n; i += 32) c += bidval[i];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+      if (lane == 0) *cost_out = c;
     }
   }
 }
@@ -408,6 +406,12 @@ static size_t smem_bytes(int n, int dfix) { return (size_t)n * 8 + 64 * sizeof(B
 
 using namespace idff;
 
+static thread_local int g_ot_threads = 0;   // diagnostic: block size of the auction kernel (0 = chosen by the batch size), idff_debug_ot_threads
+extern "C" int idff_debug_ot_threads(int32_t threads) {
+  IDFF_CHECK_ARG(threads == 0 || (threads >= 64 && threads <= 512 && threads % 32 == 0), "idff_debug_ot_threads: %d", threads);
+  g_ot_threads = threads;
+  return IDFF_OK;
+}
 static thread_local int g_ot_sap = 0;   // diagnostic: 1 = always the augmenting-path kernel (idff_debug_ot_sap)
 extern "C" int idff_debug_ot_sap(int32_t on) {
   g_ot_sap = on ? 1 : 0;
@@ -429,12 +433,18 @@ extern "C" int idff_ot_assign_batch(const float* d_x0, const float* d_x1, int32_
   const dim3 grid(n_problems);
   if (n > 64 && !g_ot_sap) {   // auction: parallel over the unassigned rows
     const size_t sm = ot::auction_smem_bytes(n, D == 2 ? 2 : 0);
+    // one problem: 16 warps bid in parallel (latency).  A batch that fills the machine several times over: smaller CTAs, more of
+    // them resident per SM (throughput) -- same rounds, same result for any block size
+    int sms = 148;
+    (void)cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, guard.dev);
+    // (measured, profiles/r2_ot_batch_rate.txt: n = 256, 4096 problems: 23.1 / 11.8 / 9.6 us per problem at 512 / 256 / 128 threads)
+    const int threads = g_ot_threads ? g_ot_threads : n_problems <= sms ? 512 : n <= 512 ? 128 : 256;
     if (D == 2) {
       IDFF_CUDA(cudaFuncSetAttribute(ot::k_ot_auction<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      ot::k_ot_auction<2><<<grid, 512, sm, s>>>(d_x0, d_x1, n, D, d_perm, d_cost);
+      ot::k_ot_auction<2><<<grid, threads, sm, s>>>(d_x0, d_x1, n, D, d_perm, d_cost);
     } else {
       IDFF_CUDA(cudaFuncSetAttribute(ot::k_ot_auction<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      ot::k_ot_auction<0><<<grid, 512, sm, s>>>(d_x0, d_x1, n, D, d_perm, d_cost);
+      ot::k_ot_auction<0><<<grid, threads, sm, s>>>(d_x0, d_x1, n, D, d_perm, d_cost);
     }
   } else {                     // augmenting paths: small problems, and the yardstick behind idff_debug_ot_sap
     const int threads = ((n + 31) / 32) * 32;

@@ -299,11 +299,14 @@ int idff_train_md_steps(float* d_state, const float* d_dataset, int32_t T, int32
 /* Diagnostic: on != 0 makes idff_ot_assign use the augmenting-path kernel for every size (default: n <= 64 only; above that an
  * epsilon-scaling auction, exact up to plans whose costs differ by less than n max(c) 2^-40). */
 int idff_debug_ot_sap(int32_t on);
+/* Diagnostic (calling thread): block size of the auction kernel, a multiple of 32 in [64, 512]; 0 = default (512 threads up to one
+ * problem per SM, 128 (n <= 512) or 256 for larger batches).  The result does not depend on it. */
+int idff_debug_ot_threads(int32_t threads);
 int idff_ot_assign(const float* d_x0, const float* d_x1, int32_t n, int32_t D, int64_t* d_perm, double* d_cost, void* stream);
 /* n_problems independent couplings in ONE launch, one CTA per problem: d_x0, d_x1 [n_problems][n][D] -> d_perm [n_problems][n],
  * d_cost [n_problems] (may be NULL); every problem gets exactly the result idff_ot_assign returns for it.  The solvers are
  * latency-bound one-CTA kernels, so the minibatches of the next S training steps -- they do not depend on the parameters -- are
- * coupled together and fill the machine (n = 256: 1024 problems in one launch cost what 7-8 single problems cost).  n_problems <= 2^20. */
+ * coupled together and fill the machine (n = 256: 1024 problems in one launch cost what 5 single problems cost).  n_problems <= 2^20. */
 int idff_ot_assign_batch(const float* d_x0, const float* d_x1, int32_t n_problems, int32_t n, int32_t D, int64_t* d_perm,
                          double* d_cost, void* stream);
 

@@ -124,7 +124,7 @@ def test_wasserstein_distance(cuda_device):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("P,n,D", [(7, 10, 46), (40, 256, 2), (300, 64, 2), (5, 100, 3)])
+@pytest.mark.parametrize("P,n,D", [(7, 10, 46), (40, 256, 2), (300, 64, 2), (5, 100, 3), (200, 128, 2)])
 def test_batched_couplings_equal_single_calls(cuda_device, P, n, D):
     """idff_ot_assign_batch: one CTA per problem -> every row is exactly the single-problem result (same permutation, same
     fp64 cost bits), and a sample of them is scipy's optimum."""
@@ -141,6 +141,14 @@ def test_batched_couplings_equal_single_calls(cuda_device, P, n, D):
         r, c = linear_sum_assignment(M)
         assert np.array_equal(perm[p].cpu().numpy(), c)
     assert all(sorted(row.tolist()) == list(range(n)) for row in perm.cpu())
+    if n > 64:   # the auction's result does not depend on its block size (large batches run on smaller CTAs)
+        try:
+            for th in (64, 256):
+                _lib.check(_lib.lib().idff_debug_ot_threads(th), "ot_threads")
+                p2, c2 = ot.ot_assign_batch(a, b, return_cost=True)
+                assert torch.equal(p2, perm) and torch.equal(c2, cost)
+        finally:
+            _lib.check(_lib.lib().idff_debug_ot_threads(0), "ot_threads")
 
 
 @pytest.mark.gpu
