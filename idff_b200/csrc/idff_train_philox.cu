@@ -7,9 +7,9 @@
 // (ATen/native/cuda/DistributionTemplates.h): block 256, grid = min(SMs * (maxThreadsPerSM / 256), ceil(numel / 256)),
 // thread idx owns Philox subsequence idx (curand_init(seed, idx, offset)); loop iteration j draws curand_normal4 and element
 // idx + S (4 j + ii), S = grid * 256, receives component ii.  The generator's offset then advances by
-// ((numel - 1) / (S * 4) + 1) * 4.  This kernel walks exactly that schedule with cuRAND's own device functions (the same
-// curand_normal4 -> Box-Muller on logf / sqrtf / __sincosf ATen calls), so for the same (seed, offset) every element sees the
-// number randn_like would have written; idff_philox_plan tells the caller the grid and the offset increment to book on the
+// ((numel - 1) / (S * 4) + 1) * 4.  This kernel walks exactly that schedule with cuRAND's own device functions (the Philox4x32-10
+// block function and the Box-Muller on logf / sqrtf / __sincosf that curand_normal4 is made of), so for the same (seed, offset)
+// every element sees the number randn_like would have written; idff_philox_plan tells the caller the grid and the offset increment to book on the
 // torch generator.  xt / ut use the reference's fp32 operation order (no contraction), as in idff_train.cu.
 #include <curand_kernel.h>
 
@@ -22,6 +22,21 @@ __device__ __forceinline__ float sigma_t_of_p(float t, float sigma, int mode) {
   return __fmul_rn(sigma, __fsqrt_rn(__fmul_rn(t, __fsub_rn(1.0f, t))));   // ExactOT matcher, conditional_flow_matching.py:231-233
 }
 
+// One element of the schedule: element e receives normal `eps`.
+template <int DM>
+__device__ __forceinline__ void philox_elem(unsigned e, float a, float b, float tt, float eps, float sigma, int mode,
+                                            float* __restrict__ xt, float* __restrict__ ut, float* __restrict__ eps_out) {
+  const float mu = __fadd_rn(__fmul_rn(tt, b), __fmul_rn(__fsub_rn(1.0f, tt), a));
+  __stcs(xt + e, __fadd_rn(mu, __fmul_rn(sigma_t_of_p(tt, sigma, mode), eps)));
+  if (ut) __stcs(ut + e, __fsub_rn(b, a));
+  if (eps_out) __stcs(eps_out + e, eps);
+}
+
+// Thread idx is Philox subsequence idx: key = seed, counter = (offset / 4 + iteration, idx) -- what curand_init(seed, idx, offset)
+// followed by one curand_normal4 per iteration walks when offset is a multiple of 4 (torch's always is: the generator state
+// machine of curand4 then only ever returns whole 4-word outputs, so it is skipped here and the raw Philox4x32-10 block function
+// and Box-Muller of cuRAND's headers are called directly).  32-bit element indices (numel < 2^31, and the rounded-up schedule
+// stays below 2^32); every iteration but the last has all four of its elements inside the tensor and runs without bounds checks.
 template <int DM>   // DM = 1, 2: D == 1 / 2; 0: any D
 __global__ void __launch_bounds__(256, 4) k_path_sample_philox(const float* __restrict__ x0, const float* __restrict__ x1,
                                                                const float* __restrict__ t, unsigned long long seed,
@@ -30,36 +45,36 @@ __global__ void __launch_bounds__(256, 4) k_path_sample_philox(const float* __re
                                                                float* __restrict__ eps_out, unsigned n, unsigned D) {
   const unsigned idx = blockIdx.x * 256u + threadIdx.x;
   const unsigned S = gridDim.x * 256u;
-  curandStatePhilox4_32_10_t state;
-  curand_init(seed, idx, offset, &state);
-  const unsigned long long rounded = ((unsigned long long)(n - 1) / (4ull * S) + 1ull) * 4ull * S;
-  for (unsigned long long base = idx; base < rounded; base += 4ull * S) {
-    // the four elements of this iteration: issue their loads before the Box-Muller arithmetic
+  const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
+  unsigned long long c01 = offset >> 2;                 // counter words 0, 1; words 2, 3 = the subsequence (idx, 0)
+  const unsigned iters = (n - 1u) / (4u * S) + 1u;      // the same for every thread (ATen's rounded-up loop bound)
+  auto row_of = [&](unsigned e) -> unsigned { return DM == 1 ? e : (DM == 2 ? e >> 1 : e / D); };
+  // (Tried on this loop, same 127 us at 2^24 x 2 each time, profiles/r2_ncu_k_path_sample_philox.txt: loads issued one iteration
+  // ahead with the values moved, or with two register sets and the loop unrolled by two; 8 instead of 4 resident blocks per SM.)
+  unsigned base = idx;
+  for (unsigned it = 0; it + 1u < iters; ++it, base += 4u * S, ++c01) {
     float a[4], b[4], tv[4];
-    bool live[4];
 #pragma unroll
-    for (int ii = 0; ii < 4; ++ii) {
-      const unsigned long long li = base + (unsigned long long)S * ii;
-      live[ii] = li < n;
-      if (live[ii]) {
-        const unsigned e = (unsigned)li;
-        const unsigned row = DM == 1 ? e : (DM == 2 ? e >> 1 : e / D);
-        a[ii] = __ldcs(x0 + e);
-        b[ii] = __ldcs(x1 + e);
-        tv[ii] = __ldg(t + row);
-      }
+    for (int ii = 0; ii < 4; ++ii) {   // the four elements of this iteration: loads in flight during the Philox / Box-Muller arithmetic
+      const unsigned e = base + S * ii;
+      a[ii] = __ldcs(x0 + e);
+      b[ii] = __ldcs(x1 + e);
+      tv[ii] = __ldg(t + row_of(e));
     }
-    const float4 r = curand_normal4(&state);
+    const uint4 r = curand_Philox4x32_10(make_uint4((unsigned)c01, (unsigned)(c01 >> 32), idx, 0u), key);
+    const float2 n0 = _curand_box_muller(r.x, r.y), n1 = _curand_box_muller(r.z, r.w);
+    const float eps[4] = {n0.x, n0.y, n1.x, n1.y};
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) philox_elem<DM>(base + S * ii, a[ii], b[ii], tv[ii], eps[ii], sigma, mode, xt, ut, eps_out);
+  }
+  {   // last iteration: elements past the end of the tensor are skipped (their normals are drawn and dropped, as ATen does)
+    const uint4 r = curand_Philox4x32_10(make_uint4((unsigned)c01, (unsigned)(c01 >> 32), idx, 0u), key);
+    const float2 n0 = _curand_box_muller(r.x, r.y), n1 = _curand_box_muller(r.z, r.w);
+    const float eps[4] = {n0.x, n0.y, n1.x, n1.y};
 #pragma unroll
     for (int ii = 0; ii < 4; ++ii) {
-      if (!live[ii]) continue;
-      const unsigned e = (unsigned)(base + (unsigned long long)S * ii);
-      const float eps = (&r.x)[ii];
-      const float tt = tv[ii];
-      const float mu = __fadd_rn(__fmul_rn(tt, b[ii]), __fmul_rn(__fsub_rn(1.0f, tt), a[ii]));
-      __stcs(xt + e, __fadd_rn(mu, __fmul_rn(sigma_t_of_p(tt, sigma, mode), eps)));
-      if (ut) __stcs(ut + e, __fsub_rn(b[ii], a[ii]));
-      if (eps_out) __stcs(eps_out + e, eps);
+      const unsigned e = base + S * ii;
+      if (e < n) philox_elem<DM>(e, __ldcs(x0 + e), __ldcs(x1 + e), __ldg(t + row_of(e)), eps[ii], sigma, mode, xt, ut, eps_out);
     }
   }
 }
