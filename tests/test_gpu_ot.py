@@ -178,3 +178,30 @@ def test_batched_plan_sampling_and_ot_paired_trainer(cuda_device):
     first = tr.run(64).mean().item()
     tr.run(1024)
     assert tr.run(64).mean().item() < first
+
+
+@pytest.mark.gpu
+def test_dynamic_matcher_many_minibatches_at_once(cuda_device):
+    """ExactOptimalTransportConditionalFlowMatcher.sample_location_and_conditional_flow_many: S minibatches coupled in one
+    batched launch and path-sampled in one launch; every returned row is a pair of its own minibatch's exact plan and obeys
+    xt = t x1 + (1 - t) x0 + sigma sqrt(t (1 - t)) eps,  ut = x1 - x0  (conditional_flow_matching_dynamic.py:268-271)."""
+    dev = cuda_device
+    torch.manual_seed(5)
+    S, B, D = 9, 128, 2
+    x0 = torch.randn(S, B, D, device=dev)
+    x1 = torch.randn(S, B, D, device=dev) * 1.5 + 0.5
+    FM = cfmd.ExactOptimalTransportConditionalFlowMatcher(sigma=0.3)
+    t, xt, ut, eps = FM.sample_location_and_conditional_flow_many(x0, x1, return_noise=True)
+    assert t.shape == (S, B) and xt.shape == (S, B, D) and ut.shape == (S, B, D) and eps.shape == (S, B, D)
+    perm = ot.ot_assign_batch(x0, x1)
+    for s in range(S):
+        plan_ut = x1[s][perm[s]] - x0[s]                                    # the B pairs of minibatch s's plan
+        d = torch.cdist(ut[s].double(), plan_ut.double())
+        near, which = d.min(dim=1)
+        assert near.max().item() < 1e-6                                     # every drawn pair is a pair of the plan
+        xi, xj = x0[s][which], x1[s][perm[s][which]]
+        tt = t[s][:, None]
+        ref = tt * xj + (1 - tt) * xi + 0.3 * torch.sqrt(tt * (1 - tt)) * eps[s]
+        assert (xt[s] - ref).abs().max().item() < 1e-5
+    with pytest.raises(_lib.IdffError):      # host tensors: no CPU path
+        FM.sample_location_and_conditional_flow_many(x0[:2, :16].cpu(), x1[:2, :16].cpu())
