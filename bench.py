@@ -546,8 +546,12 @@ def aux_measurements(dev, pw, model, peaks):
                 hl.copy_(ft.steps(hx0.to(dev, non_blocking=True), hx1.to(dev, non_blocking=True),
                                   ht.to(dev, non_blocking=True)), non_blocking=True)
             s_h = timeit(fused_e2e, reps=5, warm=2) / S
+            ft.ot_pairing = True      # the `_dynamic` matcher's step: every minibatch re-paired by its exact OT plan (one batched launch)
+            s_ot = timeit(lambda: ft.run(S), reps=3, warm=1) / S
+            ft.ot_pairing = False
             tr_out[f"B{Bt}"] = dict(tr_out.get(f"B{Bt}", {}), **{
                 "fused_samples_per_s": Bt / s_k, "fused_us_per_step": s_k * 1e6,
+                "fused_ot_paired_incl_draws_us_per_step": s_ot * 1e6,
                 "fused_incl_draws_samples_per_s": Bt / s_d, "fused_e2e_host_inputs_samples_per_s": Bt / s_h,
                 "fused_steps_per_launch": S,
                 "fused_note": "one persistent cooperative kernel; row groups on CTA pairs (B <= 296) that stream half of the weights each "
