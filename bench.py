@@ -623,6 +623,10 @@ def aux_measurements(dev, pw, model, peaks):
         aux["polyala_generation_T200_K5"] = {"chain_kernel_ms": s_chain * 1e3, "launch_per_frame_ms": s_frame * 1e3,
                                              "launches": {"chain": 1, "per_frame": 200},
                                              "particle_steps": 200 * 5 * 12}
+        # evaluate_model's (sigma, gamma1, gamma2) loop (MD_simulation.py:166-169), 64 parameter sets at this shape: one launch
+        sets64 = [(0.2 + 0.1 * a, 0.1 * b, 1.0 + c) for a in range(4) for b in range(4) for c in range(4)]
+        s_sw = timeit(lambda: md_mod.generate_trajectories_sweep(pwm, sets64, 5, 46, 200, 3, dt=0.3, device=dev), reps=2, warm=1)
+        aux["polyala_generation_T200_K5"]["sweep_64_sets_one_launch_ms"] = s_sw * 1e3
         # the reference's loop on the host cores (oracle: SDE_cal.f with nested autograd under the restated srk), 4 frames x 50
         import idff_oracle as O4
         wz = np.load(os.path.join(ROOT, "tests", "golden", "weights_polyala.npz"))

@@ -56,6 +56,7 @@ SIGNATURES = {
     "idff_sample_sde": (C.c_int, [_vp, _PP, _vp, _vp, _i32, _f32, _i32, _vp, _vp, _vp, _i64, _vp]),
     "idff_debug_md_chain_fma": (C.c_int, [_i32]),
     "idff_md_generate": (C.c_int, [_vp, _PP, _i32, _vp, _vp, _i32, _f32, _i32, _vp, _vp, _vp, _i64, _vp]),
+    "idff_md_generate_sweep": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _i32, _f32, _i32, _vp, _vp, _vp, _i64, _vp]),
     "idff_path_sample": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _f32, _i32, _vp, _vp, _i64, _i64, _vp]),
     "idff_philox_plan": (C.c_int, [_i64, _i32, _vp, _vp]),
     "idff_path_sample_philox": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_uint64, _f32, _i32, _vp, _vp, _vp, _i64, _i64, _vp, _vp]),

@@ -553,7 +553,8 @@ namespace idff {
 bool md_chain_supports(const idff_weights_t* w, const idff_field_params_t* p, int64_t K);
 void md_chain_set_fma(int on);
 int md_chain_run(const idff_weights_t* w, const idff_field_params_t* p, int n_frames, const SdeTable& tab0, const Stage* stages,
-                 const float* d_x_init, const float* d_I_k, const float* d_I_k0, float* d_y_hat, int64_t K, void* stream);
+                 const float* d_x_init, const float* d_I_k, const float* d_I_k0, float* d_y_hat, int64_t K, void* stream,
+                 int n_sets, const float* gvals, int nj_sets, int reverse_sets);
 }
 
 extern "C" int idff_md_generate(const idff_weights_t* w, const idff_field_params_t* p, int32_t n_frames, const float* d_x_init,
@@ -594,7 +595,68 @@ extern "C" int idff_md_generate(const idff_weights_t* w, const idff_field_params
       for (int g = 0; g < 3; ++g) stages[((size_t)f * n_steps + s) * 3 + g] = t.st[s][g];
   }
   DeviceGuard guard(w->device);
-  return md_chain_run(w, p, n_frames, tab0, stages.data(), d_x_init, d_I_k, d_I_k0, d_y_hat, K, stream);
+  return md_chain_run(w, p, n_frames, tab0, stages.data(), d_x_init, d_I_k, d_I_k0, d_y_hat, K, stream, 1, nullptr, 0, 0);
+}
+
+// The (sigma, gamma1, gamma2) sweep of TrajectoryGenerator.evaluate_model (MD_simulation.py:159-194) at one nfe: every parameter
+// set generates its K trajectories in the SAME launch (a tile of 4 trajectories never mixes sets; per-set stage tables and
+// diffusion values in global memory).  Rows are set-major: d_x_init [n_sets * K][D], increments [n_frames][n_steps][n_sets * K][D],
+// d_y_hat [n_frames][n_sets * K][D]; set i's rows are exactly what idff_md_generate returns for p_sets[i] on those inputs.
+extern "C" int idff_md_generate_sweep(const idff_weights_t* w, const idff_field_params_t* p_sets, int32_t n_sets, int32_t n_frames,
+                                      const float* d_x_init, const float* h_ts, int32_t n_ts, float dt, int32_t method,
+                                      const float* d_I_k, const float* d_I_k0, float* d_y_hat, int64_t K, void* stream) {
+  IDFF_CHECK_ARG(p_sets && n_sets >= 1 && n_sets <= 4096, "idff_md_generate_sweep: %d parameter sets outside [1, 4096]", n_sets);
+  if (n_sets == 1)
+    return idff_md_generate(w, p_sets, n_frames, d_x_init, h_ts, n_ts, dt, method, d_I_k, d_I_k0, d_y_hat, K, stream);
+  for (int i = 0; i < n_sets; ++i) {
+    int rc = check_field_args(w, p_sets + i, "idff_md_generate_sweep");
+    if (rc) return rc;
+    IDFF_CHECK_ARG(p_sets[i].variant == IDFF_FIELD_MD && p_sets[i].dim == p_sets[0].dim,
+                   "idff_md_generate_sweep: every set must be an SDE_cal field (variant IDFF_FIELD_MD) of the same dimension");
+  }
+  IDFF_CHECK_ARG(n_frames >= 1 && n_frames <= w->v.n_tidx, "idff_md_generate_sweep: %d frames, the embedding has %d rows", n_frames,
+                 w->v.n_tidx);
+  IDFF_CHECK_ARG(h_ts && n_ts >= 2 && dt > 0.0f, "idff_md_generate_sweep: bad ts/dt");
+  IDFF_CHECK_ARG(method == 0 || method == 1, "idff_md_generate_sweep: method %d (0 srk, 1 euler)", method);
+  for (int i = 1; i < n_ts; ++i) IDFF_CHECK_ARG(h_ts[i] >= h_ts[i - 1], "idff_md_generate_sweep: ts must be non-decreasing");
+  IDFF_CHECK_ARG(h_ts[n_ts - 1] > h_ts[0], "idff_md_generate_sweep: empty time span");
+  if (K == 0) return IDFF_OK;
+  IDFF_CHECK_ARG(K > 0 && d_x_init && d_y_hat && d_I_k && (method == 1 || d_I_k0), "idff_md_generate_sweep: null pointer or negative K");
+  const std::vector<float> grid = sde_grid(h_ts, n_ts, dt);
+  const int n_steps = (int)grid.size() - 1;
+  if (n_steps > kMaxSdeSteps || n_ts - 1 > kMaxSdeEmit) {
+    set_error("idff_md_generate_sweep: %d steps / %d outputs exceed the per-call limits (%d / %d)", n_steps, n_ts - 1, kMaxSdeSteps, kMaxSdeEmit);
+    return IDFF_EUNSUPPORTED;
+  }
+  if (!md_chain_supports(w, p_sets, K)) {
+    set_error("idff_md_generate_sweep: needs a width-128 network with at most 63 state dimensions");
+    return IDFF_EUNSUPPORTED;
+  }
+  static thread_local SdeTable tab0, tabf;
+  std::vector<Stage> stages((size_t)n_sets * n_frames * n_steps * 3);
+  std::vector<float> gvals((size_t)n_sets * kMaxSdeSteps * 4, 0.0f);
+  int nj_max = 1, reverse_any = 0;
+  for (int i = 0; i < n_sets; ++i) {
+    int nj, rev;
+    jets_needed(p_sets[i], &nj, &rev);
+    nj_max = nj > nj_max ? nj : nj_max;
+    reverse_any |= rev;
+    for (int f = 0; f < n_frames; ++f) {
+      idff_field_params_t q = p_sets[i];
+      q.t_idx = f;
+      q.gamma[1] = p_sets[i].gamma[1] / (double)(1 + f);
+      SdeTable& t = (i == 0 && f == 0) ? tab0 : tabf;
+      build_sde_table(&q, h_ts, n_ts, method, grid, t);
+      for (int s = 0; s < n_steps; ++s)
+        for (int g = 0; g < 3; ++g) stages[(((size_t)i * n_frames + f) * n_steps + s) * 3 + g] = t.st[s][g];
+      if (f == 0)
+        for (int s = 0; s < n_steps; ++s)
+          for (int g = 0; g < 4; ++g) gvals[((size_t)i * kMaxSdeSteps + s) * 4 + g] = t.gval[s][g];
+    }
+  }
+  DeviceGuard guard(w->device);
+  return md_chain_run(w, p_sets, n_frames, tab0, stages.data(), d_x_init, d_I_k, d_I_k0, d_y_hat, K, stream, n_sets, gvals.data(),
+                      nj_max, reverse_any);
 }
 
 namespace idff { void wide_set_dense3(int on); }

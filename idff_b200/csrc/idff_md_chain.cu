@@ -31,18 +31,24 @@ struct Args {
   const Stage* stages;     // device [n_frames][n_steps][3]
   const float *x_init, *Ik, *Ik0;
   float* y_hat;
-  long K;
+  long K;                  // all trajectories (the row count of x_init / Ik / y_hat): n_sets * Kset
+  // parameter sweep (idff_md_generate_sweep): rows [set * Kset, (set + 1) * Kset) run under parameter set `set`, whose stage table
+  // is stages[set][n_frames][n_steps][3] and whose diffusion values are gval_sets[set][kMaxSdeSteps][4] (NULL: one set, gval above)
+  int n_sets;
+  long Kset;
+  const float* gval_sets;
 };
 
 struct Smem {
   float *W1, *W2, *wt0, *w3, *b0, *b1, *b2, *b3, *u3, *actA, *actB, *part, *opart, *y, *xs, *fs, *k1, *k2, *yprev, *pred, *gout;
+  float* gv;   // [kMaxSdeSteps][4] diffusion values of the tile's parameter set
   Stage* st;
 };
 constexpr int kStateFloats = PB * DMAX;
 // rows0 / rows3: rows of the W0^T / W3 images (the mma.sync path rounds them up to 16 and zero-fills); ld: row pitch
 __host__ __device__ inline size_t smem_floats(int rows0, int rows3, int ld) {
   return 2 * W * ld + (size_t)(rows0 * ld + 3) / 4 * 4 + (size_t)(rows3 * ld + 3) / 4 * 4 + 4 * W + DMAX +
-         (2 + KS - 1) * W * 2 * PB + 2 * NT + 8 * kStateFloats;
+         (2 + KS - 1) * W * 2 * PB + 2 * NT + 8 * kStateFloats + kMaxSdeSteps * 4;
 }
 inline size_t smem_bytes(int rows0, int rows3, int ld) { return smem_floats(rows0, rows3, ld) * 4 + kMaxSdeSteps * 3 * sizeof(Stage); }
 
@@ -58,6 +64,7 @@ __device__ __forceinline__ Smem carve(float* m, int rows0, int rows3, int ld) {
   s.opart = m; m += 2 * NT;
   s.y = m; m += kStateFloats; s.xs = m; m += kStateFloats; s.fs = m; m += kStateFloats; s.k1 = m; m += kStateFloats;
   s.k2 = m; m += kStateFloats; s.yprev = m; m += kStateFloats; s.pred = m; m += kStateFloats; s.gout = m; m += kStateFloats;
+  s.gv = m; m += kMaxSdeSteps * 4;
   s.st = reinterpret_cast<Stage*>(m);
   return s;
 }
@@ -443,20 +450,24 @@ __global__ void __launch_bounds__(NT, 1) k_md_chain(NetView net, const __grid_co
   if (tid < A.dout) s.b3[tid] = __ldg(net.b3 + tid);
 
   const int nstage = A.method == 1 ? 1 : 3;
-  const long ntiles = (A.K + PB - 1) / PB;
+  const long tps = (A.Kset + PB - 1) / PB;   // tiles per parameter set: a tile never mixes sets
+  const long ntiles = tps * A.n_sets;
   for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {   // a CTA runs the whole chain of one group of 4, then the next
-  const long base = tile * PB;
+  const long set = tile / tps, in_set = (tile % tps) * PB;
+  const long base = set * A.Kset + in_set;   // first row of the tile; row base + r is live iff in_set + r < Kset
+  const Stage* stages = A.stages + (size_t)set * A.n_frames * A.n_steps * 3;
   __syncthreads();
   for (int o = tid; o < PB * D; o += NT) {
     const long row = base + o / D;
-    s.y[o] = row < A.K ? A.x_init[row * D + (o % D)] : 0.0f;
+    s.y[o] = in_set + o / D < A.Kset ? A.x_init[row * D + (o % D)] : 0.0f;
   }
+  for (int i = tid; i < A.n_steps * 4; i += NT) s.gv[i] = A.gval_sets ? __ldg(A.gval_sets + (size_t)set * kMaxSdeSteps * 4 + i) : A.gval[i >> 2][i & 3];
   __syncthreads();
   for (int f = 0; f < A.n_frames; ++f) {
     // frame constants: folded layer-0 bias b0 + W0[:, D+1:] . emb[f], stage scalars with gamma2 / (1 + f)
     if (tid < W) s.b0[tid] = __ldg(net.b0 + (size_t)f * W + tid);
     {
-      const int* src = reinterpret_cast<const int*>(A.stages + (size_t)f * A.n_steps * 3);
+      const int* src = reinterpret_cast<const int*>(stages + (size_t)f * A.n_steps * 3);
       int* dst = reinterpret_cast<int*>(s.st);
       for (int i = tid; i < A.n_steps * 3 * (int)(sizeof(Stage) / 4); i += NT) dst[i] = __ldg(src + i);
     }
@@ -479,30 +490,31 @@ __global__ void __launch_bounds__(NT, 1) k_md_chain(NetView net, const __grid_co
         // torchsde srk (Roessler SRI2, diagonal noise, state-independent g) / euler: same update as idff_generic_sde.cu
         for (int o = tid; o < PB * D; o += NT) {
           const long row = base + o / D;
+          const bool live = in_set + o / D < A.Kset;
           const size_t gi = noff + (size_t)row * D + (o % D);
           const float y = s.y[o], fv = s.fs[o];
           if (A.method == 1) {
-            const float ik = row < A.K ? A.Ik[gi] : 0.0f;
-            const float yn = __fadd_rn(__fadd_rn(y, __fmul_rn(fv, h)), __fmul_rn(A.gval[stp][0], ik));
+            const float ik = live ? A.Ik[gi] : 0.0f;
+            const float yn = __fadd_rn(__fadd_rn(y, __fmul_rn(fv, h)), __fmul_rn(s.gv[stp * 4 + 0], ik));
             s.yprev[o] = y; s.y[o] = yn; s.xs[o] = yn;
           } else if (sg == 0) {
-            const float ik0 = row < A.K ? A.Ik0[gi] : 0.0f;
+            const float ik0 = live ? A.Ik0[gi] : 0.0f;
             s.k1[o] = fv;
             const float t1 = __fmul_rn(__fmul_rn(1.0f, fv), h);
-            const float t2 = __fmul_rn(__fmul_rn(__fmul_rn(0.0f, A.gval[stp][0]), ik0), rdt);
+            const float t2 = __fmul_rn(__fmul_rn(__fmul_rn(0.0f, s.gv[stp * 4 + 0]), ik0), rdt);
             s.xs[o] = __fadd_rn(__fadd_rn(y, t1), t2);
           } else if (sg == 1) {
-            const float ik0 = row < A.K ? A.Ik0[gi] : 0.0f;
+            const float ik0 = live ? A.Ik0[gi] : 0.0f;
             s.k2[o] = fv;
             float v = y;
             v = __fadd_rn(__fadd_rn(v, __fmul_rn(__fmul_rn(0.25f, s.k1[o]), h)),
-                          __fmul_rn(__fmul_rn(__fmul_rn(1.0f, A.gval[stp][0]), ik0), rdt));
+                          __fmul_rn(__fmul_rn(__fmul_rn(1.0f, s.gv[stp * 4 + 0]), ik0), rdt));
             v = __fadd_rn(__fadd_rn(v, __fmul_rn(__fmul_rn(0.25f, fv), h)),
-                          __fmul_rn(__fmul_rn(__fmul_rn(0.5f, A.gval[stp][1]), ik0), rdt));
+                          __fmul_rn(__fmul_rn(__fmul_rn(0.5f, s.gv[stp * 4 + 1]), ik0), rdt));
             s.xs[o] = v;
           } else {
-            const float ik = row < A.K ? A.Ik[gi] : 0.0f;
-            const float ik0 = row < A.K ? A.Ik0[gi] : 0.0f;
+            const float ik = live ? A.Ik[gi] : 0.0f;
+            const float ik0 = live ? A.Ik0[gi] : 0.0f;
             const float ikk = __fmul_rn(__fsub_rn(__fmul_rn(ik, ik), h), 0.5f);
             const float ikkk = __fdiv_rn(__fsub_rn(__fmul_rn(__fmul_rn(ik, ik), ik), __fmul_rn(__fmul_rn(3.0f, h), ik)), 6.0f);
             const float b1[4] = {-1.0f, (float)(4.0 / 3.0), (float)(2.0 / 3.0), 0.0f};
@@ -518,7 +530,7 @@ __global__ void __launch_bounds__(NT, 1) k_md_chain(NetView net, const __grid_co
               gw = __fadd_rn(gw, __fdiv_rn(__fmul_rn(b2[q], ikk), sq));
               gw = __fadd_rn(gw, __fmul_rn(__fmul_rn(b3[q], ik0), rdt));
               gw = __fadd_rn(gw, __fmul_rn(__fmul_rn(b4[q], ikkk), rdt));
-              v = __fadd_rn(__fadd_rn(v, __fmul_rn(__fmul_rn(al[q], F[q]), h)), __fmul_rn(A.gval[stp][q], gw));
+              v = __fadd_rn(__fadd_rn(v, __fmul_rn(__fmul_rn(al[q], F[q]), h)), __fmul_rn(s.gv[stp * 4 + q], gw));
             }
             s.yprev[o] = y; s.y[o] = v; s.xs[o] = v;
           }
@@ -531,7 +543,7 @@ __global__ void __launch_bounds__(NT, 1) k_md_chain(NetView net, const __grid_co
       const long row = base + o / D;
       const float v = __fadd_rn(__fmul_rn(A.w0, s.yprev[o]), __fmul_rn(A.w1, s.y[o]));
       s.y[o] = v;
-      if (row < A.K) A.y_hat[((size_t)f * A.K + row) * D + (o % D)] = v;
+      if (in_set + o / D < A.Kset) A.y_hat[((size_t)f * A.K + row) * D + (o % D)] = v;
     }
     __syncthreads();
   }
@@ -549,12 +561,17 @@ bool md_chain_supports(const idff_weights_t* w, const idff_field_params_t* p, in
          v.dout >= p->dim && p->dim * chain::PB <= 256 && v.dout * chain::PB <= 256 && v.din_pad % chain::KS == 0 && K >= 1;
 }
 
+// n_sets parameter sets (1: the plain call): `stages` holds [n_sets][n_frames][n_steps][3], `gvals` (n_sets > 1) [n_sets][kMaxSdeSteps][4];
+// K = trajectories per set, rows set-major in x_init / the increments / y_hat; nj / reverse: the jets the most demanding set needs
 int md_chain_run(const idff_weights_t* w, const idff_field_params_t* p, int n_frames, const SdeTable& tab0, const Stage* stages,
-                 const float* d_x_init, const float* d_I_k, const float* d_I_k0, float* d_y_hat, int64_t K, void* stream) {
+                 const float* d_x_init, const float* d_I_k, const float* d_I_k0, float* d_y_hat, int64_t K, void* stream,
+                 int n_sets, const float* gvals, int nj_sets, int reverse_sets) {
   using namespace chain;
   cudaStream_t s = (cudaStream_t)stream;
   idff_weights_t* wm = const_cast<idff_weights_t*>(w);
-  const size_t bytes = (size_t)n_frames * tab0.n_steps * 3 * sizeof(Stage);
+  const size_t st_bytes = (size_t)n_sets * n_frames * tab0.n_steps * 3 * sizeof(Stage);
+  const size_t gv_bytes = gvals ? (size_t)n_sets * kMaxSdeSteps * 4 * sizeof(float) : 0;
+  const size_t bytes = st_bytes + gv_bytes;
   if (wm->sweep_bytes < bytes) {
     if (wm->d_sweep) cudaFree(wm->d_sweep);
     wm->d_sweep = nullptr;
@@ -562,12 +579,14 @@ int md_chain_run(const idff_weights_t* w, const idff_field_params_t* p, int n_fr
     IDFF_CUDA(cudaMalloc(&wm->d_sweep, bytes));
     wm->sweep_bytes = bytes;
   }
-  IDFF_CUDA(cudaMemcpyAsync(wm->d_sweep, stages, bytes, cudaMemcpyHostToDevice, s));
-  IDFF_CUDA(cudaStreamSynchronize(s));   // `stages` is pageable host memory owned by the caller
+  IDFF_CUDA(cudaMemcpyAsync(wm->d_sweep, stages, st_bytes, cudaMemcpyHostToDevice, s));
+  if (gvals) IDFF_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(wm->d_sweep) + st_bytes, gvals, gv_bytes, cudaMemcpyHostToDevice, s));
+  IDFF_CUDA(cudaStreamSynchronize(s));   // `stages` / `gvals` are pageable host memory owned by the caller
   static thread_local Args A;
   memset(&A, 0, sizeof(A));
   int nj;
   jets_needed(*p, &nj, &A.reverse);
+  if (n_sets > 1) { nj = nj_sets; A.reverse = reverse_sets; }
   A.n_frames = n_frames; A.n_steps = tab0.n_steps; A.method = tab0.method;
   A.D = p->dim; A.din = w->v.din; A.din_pad = w->v.din_pad; A.dout = w->v.dout;
   for (int i = 0; i < tab0.n_steps; ++i) {
@@ -577,10 +596,12 @@ int md_chain_run(const idff_weights_t* w, const idff_field_params_t* p, int n_fr
   A.w0 = tab0.n_emit > 0 ? tab0.emit_w0[tab0.n_emit - 1] : 0.0f;
   A.w1 = tab0.n_emit > 0 ? tab0.emit_w1[tab0.n_emit - 1] : 1.0f;
   A.stages = reinterpret_cast<const Stage*>(wm->d_sweep);
-  A.x_init = d_x_init; A.Ik = d_I_k; A.Ik0 = d_I_k0; A.y_hat = d_y_hat; A.K = K;
+  A.x_init = d_x_init; A.Ik = d_I_k; A.Ik0 = d_I_k0; A.y_hat = d_y_hat; A.K = K * n_sets;
+  A.n_sets = n_sets; A.Kset = K;
+  A.gval_sets = gvals ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(wm->d_sweep) + st_bytes) : nullptr;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
-  const long tiles = (K + PB - 1) / PB;
+  const long tiles = (K + PB - 1) / PB * n_sets;
   const int grid = (int)(tiles < sms ? tiles : sms);
   const bool mma = g_chain_fma == 0;
   const int rows0 = mma ? ((A.din_pad + 15) & ~15) : A.din_pad, rows3 = mma ? ((A.dout + 15) & ~15) : A.dout;

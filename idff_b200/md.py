@@ -58,6 +58,46 @@ def generate_trajectories_chain(model, num_trajectories, data_dim, max_length, n
     return y_hat
 
 
+def generate_trajectories_sweep(model, param_sets, num_trajectories, data_dim, max_length, nfe, dt=0.3, device="cuda",
+                                x_init=None, generator=None, method="srk", noise=None):
+    """generate_trajectories for every (sigma, gamma1, gamma2) of `param_sets` in ONE launch (idff_md_generate_sweep): the loop body
+    of TrajectoryGenerator.evaluate_model (MD_simulation.py:166-169) at one nfe.  A generation of the reference's 5 trajectories
+    occupies 2 of the 148 SMs, so up to 74 parameter sets cost what one does.
+    -> y_hat (max_length, n_sets, num_trajectories, data_dim); slice [:, i] is bit for bit generate_trajectories_chain under
+    param_sets[i] on the same start rows and increments.  x_init: (n_sets, K, D) or None (randn); noise: (I_k, I_k0) of shape
+    (max_length, n_steps, n_sets, K, D) or None (drawn on the device)."""
+    device = torch.device(device)
+    S, K, D, T = len(param_sets), int(num_trajectories), int(data_dim), int(max_length)
+    if S == 0:
+        raise _lib.IdffError("generate_trajectories_sweep: no parameter sets given")
+    ts = torch.linspace(0, 1, int(nfe)).numpy().astype(np.float32)
+    n_steps = sampler.sde_num_steps(ts, dt)
+    if noise is None:
+        I_k, I_k0 = sampler.brownian_increments(n_steps, ts, dt, (T, S * K, D), device, generator)   # (n_steps, T, S K, D)
+        I_k, I_k0 = I_k.transpose(0, 1).contiguous(), I_k0.transpose(0, 1).contiguous()
+    else:
+        I_k, I_k0 = noise
+        I_k = I_k.contiguous().view(T, n_steps, S * K, D)
+        I_k0 = None if I_k0 is None else I_k0.contiguous().view(T, n_steps, S * K, D)
+    if tuple(I_k.shape) != (T, n_steps, S * K, D):
+        raise _lib.IdffError(f"I_k must be {(T, n_steps, S, K, D)}, got {tuple(I_k.shape)}")
+    if x_init is None:
+        x_init = torch.randn((S * K, D), device=device, generator=generator)
+    _lib.require_cuda(x_init, "x_init")
+    x_init = x_init.detach().contiguous().view(S * K, D)
+    sdes = [fields.SDE_cal(model, input_dim=D, gamma1=g1, gamma2=g2, init_ind=0, max_length=T, dt=dt, sigma=sg, device=device)
+            for sg, g1, g2 in param_sets]
+    pw = sdes[0]._packed(device)
+    params = (_lib.FieldParams * S)(*[m.field_params(D) for m in sdes])
+    y_hat = torch.empty((T, S * K, D), device=device, dtype=torch.float32)
+    meth = {"srk": 0, "euler": 1}[method]
+    _lib.check(_lib.lib().idff_md_generate_sweep(pw.handle, C.cast(params, C.c_void_p), S, T, _lib.ptr(x_init),
+                                                 ts.ctypes.data_as(C.c_void_p), len(ts), float(dt), meth, _lib.ptr(I_k),
+                                                 _lib.ptr(I_k0), _lib.ptr(y_hat), K, _lib.stream_of(x_init)),
+               "idff_md_generate_sweep")
+    return y_hat.view(T, S, K, D)
+
+
 def generate_trajectories(model, num_trajectories, data_dim, max_length, nfe, sigma, gamma1=1.0, gamma2=10.0, dt=0.3,
                           device="cuda", x_init=None, generator=None, method="srk", noise=None, chain=None):
     """-> y_hat (max_length, num_trajectories, data_dim) on `device`.
@@ -158,7 +198,8 @@ def compute_metrics(y_hat, dataset):
 def evaluate_model(model, dataset, gamma1_values, gamma2_values, sigma_values, nfes, num_trajectories=5, dt=0.3,
                    device="cuda", generator=None):
     """TrajectoryGenerator.evaluate_model (MD_simulation.py:159-194) without the plots, the KDE-KL and the CSV: for every
-    (nfe, sigma, gamma1, gamma2) generate `num_trajectories` chains (one launch each), compute the reference's metrics and the
+    (nfe, sigma, gamma1, gamma2) generate `num_trajectories` chains (all tuples of one nfe in ONE launch where the chain kernel serves
+    the network, generate_trajectories_sweep), compute the reference's metrics and the
     RBF-MMD (sigma_kernel = 1, :178) between all data frames and all generated frames.  -> list of dicts with the reference's
     keys (CC_mean .. MAE_std, nfe, sigma, gamma1, gamma2, MMD), in the reference's loop order."""
     from .mmd import compute_mmd_rbf
@@ -167,15 +208,21 @@ def evaluate_model(model, dataset, gamma1_values, gamma2_values, sigma_values, n
     T, D = data.shape
     results = []
     for nfe in nfes:
-        for sigma in sigma_values:
-            for gamma1 in gamma1_values:
-                for gamma2 in gamma2_values:
-                    y_hat = generate_trajectories(model, num_trajectories, D, T, nfe, sigma, gamma1=gamma1, gamma2=gamma2, dt=dt,
-                                                  device=device, generator=generator)
-                    m = compute_metrics(y_hat, data)
-                    for k in ("CC", "RMSE", "MAE"):
-                        m.pop(k)
-                    m.update({"nfe": nfe, "sigma": sigma, "gamma1": gamma1, "gamma2": gamma2,
-                              "MMD": compute_mmd_rbf(data, y_hat.reshape(-1, D), 1.0)})
-                    results.append(m)
+        sets = [(sigma, gamma1, gamma2) for sigma in sigma_values for gamma1 in gamma1_values for gamma2 in gamma2_values]
+        if len(sets) > 1 and chain_serves(model, num_trajectories, D, device):
+            # every (sigma, gamma1, gamma2) of this nfe in one launch of the chain kernel, 4096 sets at a time
+            ys = torch.cat([generate_trajectories_sweep(model, sets[a:a + 4096], num_trajectories, D, T, nfe, dt=dt, device=device,
+                                                        generator=generator) for a in range(0, len(sets), 4096)], dim=1)
+            y_of = lambda i: ys[:, i]
+        else:
+            y_of = lambda i: generate_trajectories(model, num_trajectories, D, T, nfe, sets[i][0], gamma1=sets[i][1],
+                                                   gamma2=sets[i][2], dt=dt, device=device, generator=generator)
+        for i, (sigma, gamma1, gamma2) in enumerate(sets):
+            y_hat = y_of(i)
+            m = compute_metrics(y_hat, data)
+            for k in ("CC", "RMSE", "MAE"):
+                m.pop(k)
+            m.update({"nfe": nfe, "sigma": sigma, "gamma1": gamma1, "gamma2": gamma2,
+                      "MMD": compute_mmd_rbf(data, y_hat.reshape(-1, D), 1.0)})
+            results.append(m)
     return results

@@ -324,6 +324,14 @@ int idff_debug_md_chain_fma(int32_t on);
 int idff_md_generate(const idff_weights_t* w, const idff_field_params_t* p, int32_t n_frames, const float* d_x_init,
                      const float* h_ts, int32_t n_ts, float dt, int32_t method, const float* d_I_k, const float* d_I_k0,
                      float* d_y_hat, int64_t K, void* stream);
+/* The (sigma, gamma1, gamma2) sweep of TrajectoryGenerator.evaluate_model (MD_simulation.py:159-194) at one nfe / dt: n_sets
+ * parameter sets (p_sets[i]: variant IDFF_FIELD_MD, same dim), each generating K trajectories, in ONE launch -- a generation uses
+ * ceil(K / 4) CTAs (2 of 148 SMs for the reference's K = 5), so up to 74 sets run in the time of one.  Rows are set-major:
+ * d_x_init [n_sets * K][D]; d_I_k, d_I_k0 [n_frames][n_steps][n_sets * K][D]; d_y_hat [n_frames][n_sets * K][D].  Set i's rows are
+ * bit for bit what idff_md_generate returns for p_sets[i] on those rows.  n_sets <= 4096. */
+int idff_md_generate_sweep(const idff_weights_t* w, const idff_field_params_t* p_sets, int32_t n_sets, int32_t n_frames,
+                           const float* d_x_init, const float* h_ts, int32_t n_ts, float dt, int32_t method, const float* d_I_k,
+                           const float* d_I_k0, float* d_y_hat, int64_t K, void* stream);
 
 #ifdef __cplusplus
 }

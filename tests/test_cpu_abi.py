@@ -114,6 +114,7 @@ def test_new_entry_points_validate_without_a_gpu():
     assert L.idff_ot_assign_batch(None, None, 0, 8, 2, None, None, None) == 0
     assert L.idff_ot_assign_batch(None, None, 4, 8, 2, None, None, None) == -1
     assert L.idff_ot_assign_batch(None, None, -1, 8, 2, None, None, None) == -1
+    assert L.idff_md_generate_sweep(None, None, 0, 4, None, None, 2, 0.3, 0, None, None, None, 5, None) == -1
     assert L.idff_debug_train_stamps(None, 4) == -1
 
 

@@ -436,3 +436,50 @@ def test_scorehead_gamma_sweep_is_one_launch_and_equals_per_tuple(cuda_device):
     from idff_b200.mmd import compute_mmd_rbf
     for (g, v), k in zip(table, range(9)):
         assert abs(v - compute_mmd_rbf(true, outs[k], 1.0)) <= 1e-6 + 1e-4 * abs(v)
+
+
+def test_md_generation_sweep_is_the_per_set_generation(cuda_device):
+    """idff_md_generate_sweep: the (sigma, gamma1, gamma2) loop of evaluate_model (MD_simulation.py:166-169) in one launch of the
+    chain kernel -> every set's trajectories are bit for bit what the one-set launch returns on the same start rows and increments,
+    including sets that need fewer jets than the others (gamma2 = 0; gamma1 = 0.5 and gamma2 = 0) and K not a multiple of 4."""
+    import time
+    from idff_b200 import sampler as sampler_mod
+    dev = cuda_device
+    pw = packed("polyala", dev)
+    K, D, T, NFE, dt = 5, 46, 30, 3, 0.3
+    sets = [(0.5, 0.2, 5.0), (0.2, 0.0, 1.0), (0.5, 0.2, 0.0), (0.3, 0.5, 0.0), (1.0, 1.0, 10.0), (0.05, 0.3, 2.0), (0.5, 0.5, 3.0)]
+    S = len(sets)
+    g = torch.Generator(device=dev).manual_seed(11)
+    n_steps = sampler_mod.sde_num_steps(torch.linspace(0, 1, NFE), dt)
+    x_init = torch.randn(S, K, D, device=dev, generator=g)
+    ik = torch.randn(T, n_steps, S, K, D, device=dev, generator=g) * 0.3
+    ik0 = torch.randn(T, n_steps, S, K, D, device=dev, generator=g) * 0.05
+    ys = md.generate_trajectories_sweep(pw, sets, K, D, T, NFE, dt=dt, device=dev, x_init=x_init, noise=(ik, ik0))
+    assert tuple(ys.shape) == (T, S, K, D) and torch.isfinite(ys[:, 0]).all()
+    same = lambda a, b: torch.equal(a.contiguous().view(torch.int32), b.contiguous().view(torch.int32))   # bit patterns: a set whose SDE runs away is NaN in both
+    for i, (sg, g1, g2) in enumerate(sets):
+        one = md.generate_trajectories_chain(pw, K, D, T, NFE, sigma=sg, gamma1=g1, gamma2=g2, dt=dt, device=dev,
+                                             x_init=x_init[i].contiguous(),
+                                             noise=(ik[:, :, i].contiguous(), ik0[:, :, i].contiguous()))
+        assert same(ys[:, i], one), (i, (ys[:, i] - one).abs().max().item())
+    # euler, one set through the sweep entry point, and the wall clock of a 60-set sweep against 60 launches
+    ye = md.generate_trajectories_sweep(pw, sets[:2], K, D, T, NFE, dt=dt, device=dev, x_init=x_init[:2].contiguous(),
+                                        noise=(ik[:, :, :2].contiguous(), None), method="euler")
+    for i in range(2):
+        one = md.generate_trajectories_chain(pw, K, D, T, NFE, sigma=sets[i][0], gamma1=sets[i][1], gamma2=sets[i][2], dt=dt,
+                                             device=dev, x_init=x_init[i].contiguous(), noise=(ik[:, :, i].contiguous(), None),
+                                             method="euler")
+        assert same(ye[:, i], one)
+    big = [(0.1 + 0.01 * i, 0.2, 1.0 + i) for i in range(60)]
+    md.generate_trajectories_sweep(pw, big, K, D, T, NFE, dt=dt, device=dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    md.generate_trajectories_sweep(pw, big, K, D, T, NFE, dt=dt, device=dev)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    for sg, g1, g2 in big:
+        md.generate_trajectories_chain(pw, K, D, T, NFE, sigma=sg, gamma1=g1, gamma2=g2, dt=dt, device=dev)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    print(f"60-set PolyALA generation sweep, {T} frames x {K} trajectories: one launch {1e3 * (t1 - t0):.2f} ms, per set {1e3 * (t2 - t1):.2f} ms")
+    assert (t1 - t0) < 0.5 * (t2 - t1)
