@@ -98,6 +98,15 @@ def generate_trajectories_sweep(model, param_sets, num_trajectories, data_dim, m
     return y_hat.view(T, S, K, D)
 
 
+def generate_overlay_sets(model, num_trajectories, data_dim, max_length, nfe, sigma, gamma1, gamma2, dt=0.3, device="cuda",
+                          generator=None):
+    """The three generations plot_overlayed_trajectories compares (MD_simulation.py:303-305) -- (gamma1, gamma2), (gamma1, 0),
+    (0, 0) -- in one launch: -> (y_hat_full, y_hat_gamma1_only, y_hat_no_gamma), each (max_length, K, D)."""
+    ys = generate_trajectories_sweep(model, [(sigma, gamma1, gamma2), (sigma, gamma1, 0.0), (sigma, 0.0, 0.0)], num_trajectories,
+                                     data_dim, max_length, nfe, dt=dt, device=device, generator=generator)
+    return ys[:, 0], ys[:, 1], ys[:, 2]
+
+
 def generate_trajectories(model, num_trajectories, data_dim, max_length, nfe, sigma, gamma1=1.0, gamma2=10.0, dt=0.3,
                           device="cuda", x_init=None, generator=None, method="srk", noise=None, chain=None):
     """-> y_hat (max_length, num_trajectories, data_dim) on `device`.

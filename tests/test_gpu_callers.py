@@ -470,6 +470,8 @@ def test_md_generation_sweep_is_the_per_set_generation(cuda_device):
                                              device=dev, x_init=x_init[i].contiguous(), noise=(ik[:, :, i].contiguous(), None),
                                              method="euler")
         assert same(ye[:, i], one)
+    full, g1only, none = md.generate_overlay_sets(pw, K, D, T, NFE, 0.5, 0.2, 5.0, dt=dt, device=dev)   # MD_simulation.py:303-305
+    assert full.shape == g1only.shape == none.shape == (T, K, D) and torch.isfinite(full).all()
     big = [(0.1 + 0.01 * i, 0.2, 1.0 + i) for i in range(60)]
     md.generate_trajectories_sweep(pw, big, K, D, T, NFE, dt=dt, device=dev)
     torch.cuda.synchronize()
