@@ -183,6 +183,25 @@ def generate_onestep(model, num_trajectories, data_dim, max_length, nfe, sigma, 
     return sampler.sdeint(sde, x_prev, torch.linspace(0, 1, int(nfe)), dt=1.0 / nfe, method=method, generator=generator)
 
 
+def _metric_stats(y_hat, dataset):
+    """(..., 6) fp64 device tensor [CC_mean, CC_std, RMSE_mean, RMSE_std, MAE_mean, MAE_std] for y_hat (T, ..., K, D)."""
+    y = y_hat.to(torch.float64)
+    d = torch.as_tensor(dataset, device=y_hat.device).to(torch.float64)
+    d = d.view(d.shape[0], *([1] * (y.dim() - 2)), d.shape[1])
+    err = y - d
+    rmse = torch.sqrt(torch.nanmean(err * err, dim=0))
+    mae = torch.nanmean(err.abs(), dim=0)
+    ya, da = y - y.mean(dim=0, keepdim=True), d - d.mean(dim=0, keepdim=True)
+    cc = (ya * da).sum(0) / torch.sqrt((ya * ya).sum(0) * (da * da).sum(0))
+    flat = lambda v: v.reshape(*v.shape[:-2], -1)          # the K * D series of a set
+    cc, rmse, mae = flat(cc), flat(rmse), flat(mae)
+    return torch.stack([cc.mean(-1), cc.std(-1, unbiased=False), rmse.mean(-1), rmse.std(-1, unbiased=False), mae.mean(-1),
+                        mae.std(-1, unbiased=False)], dim=-1)
+
+
+_METRIC_KEYS = ("CC_mean", "CC_std", "RMSE_mean", "RMSE_std", "MAE_mean", "MAE_std")
+
+
 def compute_metrics(y_hat, dataset):
     """TrajectoryGenerator.compute_metrics (MD_simulation.py:275-295) without leaving the device: per (trajectory,
     dimension) Pearson CC, RMSE and MAE of the generated series against the data over the T frames, then mean and std
@@ -190,18 +209,17 @@ def compute_metrics(y_hat, dataset):
     (nanmean) and poison CC, as in the reference.  The old keys CC / RMSE / MAE are the *_mean values."""
     if not y_hat.is_cuda:
         raise RuntimeError("compute_metrics needs a CUDA tensor: idff_b200 has no CPU path")
-    y = y_hat.to(torch.float64)
-    d = torch.as_tensor(dataset, device=y_hat.device).to(torch.float64)[:, None, :]
-    err = y - d
-    rmse = torch.sqrt(torch.nanmean(err * err, dim=0))
-    mae = torch.nanmean(err.abs(), dim=0)
-    ya, da = y - y.mean(dim=0, keepdim=True), d - d.mean(dim=0, keepdim=True)
-    cc = (ya * da).sum(0) / torch.sqrt((ya * ya).sum(0) * (da * da).sum(0))
-    stats = torch.stack([cc.mean(), cc.std(unbiased=False), rmse.mean(), rmse.std(unbiased=False), mae.mean(),
-                         mae.std(unbiased=False)]).tolist()          # one device -> host copy
-    out = dict(zip(("CC_mean", "CC_std", "RMSE_mean", "RMSE_std", "MAE_mean", "MAE_std"), stats))
+    out = dict(zip(_METRIC_KEYS, _metric_stats(y_hat, dataset).tolist()))          # one device -> host copy
     out.update(CC=out["CC_mean"], RMSE=out["RMSE_mean"], MAE=out["MAE_mean"])
     return out
+
+
+def compute_metrics_sets(y_hat_sets, dataset):
+    """compute_metrics for every parameter set of a sweep at once: y_hat_sets (T, S, K, D) -> list of S dicts (the reference's six
+    keys); one device -> host copy for all sets."""
+    if not y_hat_sets.is_cuda:
+        raise RuntimeError("compute_metrics_sets needs a CUDA tensor: idff_b200 has no CPU path")
+    return [dict(zip(_METRIC_KEYS, row)) for row in _metric_stats(y_hat_sets, dataset).tolist()]
 
 
 def evaluate_model(model, dataset, gamma1_values, gamma2_values, sigma_values, nfes, num_trajectories=5, dt=0.3,
@@ -211,27 +229,24 @@ def evaluate_model(model, dataset, gamma1_values, gamma2_values, sigma_values, n
     the network, generate_trajectories_sweep), compute the reference's metrics and the
     RBF-MMD (sigma_kernel = 1, :178) between all data frames and all generated frames.  -> list of dicts with the reference's
     keys (CC_mean .. MAE_std, nfe, sigma, gamma1, gamma2, MMD), in the reference's loop order."""
-    from .mmd import compute_mmd_rbf
     device = torch.device(device)
     data = torch.as_tensor(dataset, dtype=torch.float32, device=device)
     T, D = data.shape
     results = []
+    from .mmd import mmd_sweep
     for nfe in nfes:
         sets = [(sigma, gamma1, gamma2) for sigma in sigma_values for gamma1 in gamma1_values for gamma2 in gamma2_values]
         if len(sets) > 1 and chain_serves(model, num_trajectories, D, device):
             # every (sigma, gamma1, gamma2) of this nfe in one launch of the chain kernel, 4096 sets at a time
             ys = torch.cat([generate_trajectories_sweep(model, sets[a:a + 4096], num_trajectories, D, T, nfe, dt=dt, device=device,
                                                         generator=generator) for a in range(0, len(sets), 4096)], dim=1)
-            y_of = lambda i: ys[:, i]
         else:
-            y_of = lambda i: generate_trajectories(model, num_trajectories, D, T, nfe, sets[i][0], gamma1=sets[i][1],
-                                                   gamma2=sets[i][2], dt=dt, device=device, generator=generator)
-        for i, (sigma, gamma1, gamma2) in enumerate(sets):
-            y_hat = y_of(i)
-            m = compute_metrics(y_hat, data)
-            for k in ("CC", "RMSE", "MAE"):
-                m.pop(k)
-            m.update({"nfe": nfe, "sigma": sigma, "gamma1": gamma1, "gamma2": gamma2,
-                      "MMD": compute_mmd_rbf(data, y_hat.reshape(-1, D), 1.0)})
+            ys = torch.stack([generate_trajectories(model, num_trajectories, D, T, nfe, sg, gamma1=g1, gamma2=g2, dt=dt,
+                                                    device=device, generator=generator) for sg, g1, g2 in sets], dim=1)
+        # metrics and MMDs of all sets, then one copy to the host each
+        stats = compute_metrics_sets(ys, data)
+        mmds = mmd_sweep(data, ys.transpose(0, 1).reshape(len(sets), -1, D), 1.0).tolist()
+        for (sigma, gamma1, gamma2), m, mmd in zip(sets, stats, mmds):
+            m.update({"nfe": nfe, "sigma": sigma, "gamma1": gamma1, "gamma2": gamma2, "MMD": mmd})
             results.append(m)
     return results

@@ -485,3 +485,20 @@ def test_md_generation_sweep_is_the_per_set_generation(cuda_device):
     t2 = time.perf_counter()
     print(f"60-set PolyALA generation sweep, {T} frames x {K} trajectories: one launch {1e3 * (t1 - t0):.2f} ms, per set {1e3 * (t2 - t1):.2f} ms")
     assert (t1 - t0) < 0.5 * (t2 - t1)
+
+
+def test_metrics_of_all_sweep_sets_at_once(cuda_device):
+    """md.compute_metrics_sets (T, S, K, D) = md.compute_metrics per set (the reference's compute_metrics, MD_simulation.py:275-295,
+    pinned by tests/golden/metrics.npz), NaN handling included."""
+    g = torch.Generator().manual_seed(8)
+    T, S, K, D = 25, 3, 5, 6
+    data = 50 * torch.randn(T, D, generator=g)
+    ys = (data[:, None, None, :] + 10 * torch.randn(T, S, K, D, generator=g)).to(cuda_device)
+    ys[3, 1, 2, 4] = float("nan")
+    rows = md.compute_metrics_sets(ys, data.to(cuda_device))
+    assert len(rows) == S
+    for i in range(S):
+        one = md.compute_metrics(ys[:, i].contiguous(), data.to(cuda_device))
+        for k in ("CC_mean", "CC_std", "RMSE_mean", "RMSE_std", "MAE_mean", "MAE_std"):
+            a, b = rows[i][k], one[k]
+            assert (np.isnan(a) and np.isnan(b)) or a == pytest.approx(b, rel=1e-12, abs=1e-12), (i, k, a, b)
