@@ -265,7 +265,7 @@ __device__ __forceinline__ void mma_pass(const float* Wm, const float* X, int m0
   // three independent accumulation chains (lo*hi, hi*lo, hi*hi): an mma.sync depends on its accumulator, so one chain of
   // 3 * nks instructions would be latency-bound
   float c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
+#pragma unroll 8
   for (int ks = ks0; ks < ks0 + nks; ++ks) {
     const int k0 = 8 * ks;
     float af[4];
