@@ -581,3 +581,28 @@ def test_small_n_route_is_opt_in_and_within_bounds(cuda_device):
         sampler.set_small_n_route(0)
     r = drift_report(o1.cpu().numpy(), sampler.sample_rk4(m1, x0, ts).cpu().numpy())
     assert r["median"] <= 2e-5 and r["p999"] <= 2e-3, r
+
+
+def test_bench_size_64M_particles_properties(cuda_device):
+    """The upper end of BASELINE configs[1] and the bench workload (2^26 particles, nfe 2) through the default sampler, checked by
+    size-independent properties: the solve is deterministic (two runs, same bits), equals the concatenation of four 2^24-particle
+    solves (what four ranks of the particle-sharded launcher would return), any slice reproduces on its own, the output is finite
+    and no particle needed the fp32 safety net."""
+    from idff_b200.weights import PackedWeights
+    pw = PackedWeights.from_npz(load_golden("weights_checkerboard"), device=cuda_device)
+    m = fields.CustomNetModel(pw, 0.2, 0.2, 0.2)
+    n = 1 << 26
+    x0 = torch.randn(n, 2, device=cuda_device, generator=torch.Generator(device=cuda_device).manual_seed(26)) / 1.5
+    ts = torch.linspace(0, 1, 3)
+    whole = sampler.sample_rk4(m, x0, ts)
+    assert torch.isfinite(whole).all()
+    again = sampler.sample_rk4(m, x0, ts)
+    assert torch.equal(whole, again)
+    del again
+    q = n // 4
+    for r in range(4):
+        assert torch.equal(sampler.sample_rk4(m, x0[r * q:(r + 1) * q], ts), whole[r * q:(r + 1) * q])
+    for lo, hi in ((n - 70001, n), (3 * q - 33, 3 * q + 31)):
+        assert torch.equal(sampler.sample_rk4(m, x0[lo:hi], ts), whole[lo:hi])
+    assert (whole.abs() < 6).float().mean().item() > 0.99
+    assert _lib.weights_nonfinite(pw.handle) == (0, 0)
