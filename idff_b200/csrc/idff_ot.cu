@@ -212,12 +212,12 @@ __global__ void __launch_bounds__(512, 1) k_ot_auction(const float* __restrict__
   int* list = bidcol + n;                                                          // [n] unassigned rows, in row order
   int* bidcol2 = list + n;                                                         // [n] the other list buffer
   int* ccnt = bidcol2 + n;                                                         // [32] list lengths
-  float* xs0 = reinterpret_cast<float*>(ccnt + 32);                                // [n][DFIX]
-  float* xs1 = xs0 + (DFIX > 0 ? n * DFIX : 0);                                    // [n][DFIX]
+  double* xs0 = reinterpret_cast<double*>(ccnt + 32);                              // [n][DFIX] coordinates, converted to fp64 once
+  double* xs1 = xs0 + (DFIX > 0 ? n * DFIX : 0);                                   // [n][DFIX] (the conversions run on the XU pipe)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;   // 16 warps
 
   if (DFIX > 0)
-    for (int i = tid; i < n * DFIX; i += blockDim.x) { xs0[i] = x0[i]; xs1[i] = x1[i]; }
+    for (int i = tid; i < n * DFIX; i += blockDim.x) { xs0[i] = (double)x0[i]; xs1[i] = (double)x1[i]; }
   for (int j = tid; j < n; j += blockDim.x) { price[j] = 0.0; maxbid[j] = 0ull; winner[j] = 0x7fffffff; }
   __syncthreads();
   auto cost = [&](int i, int j) -> double {
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(512, 1) k_ot_auction(const float* __restrict__
     if (DFIX > 0) {
 #pragma unroll
       for (int d = 0; d < DFIX; ++d) {
-        const double df = (double)xs0[i * DFIX + d] - (double)xs1[j * DFIX + d];
+        const double df = xs0[i * DFIX + d] - xs1[j * DFIX + d];
         c = fma(df, df, c);
       }
     } else {
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(512, 1) k_ot_auction(const float* __restrict__
 }
 
 static size_t auction_smem_bytes(int n, int dfix) {
-  return (size_t)n * 8 * 3 + 32 * 8 + (size_t)n * 4 * 6 + 32 * 4 + (size_t)2 * n * dfix * 4 + 16;
+  return (size_t)n * 8 * 3 + 32 * 8 + (size_t)n * 4 * 6 + 32 * 4 + (size_t)2 * n * dfix * 8 + 16;
 }
 
 static size_t smem_bytes(int n, int dfix) { return (size_t)n * 8 + 64 * sizeof(Best) + (size_t)4 * n * 4 + (size_t)n * dfix * 4 + 16; }
