@@ -557,84 +557,37 @@ int md_chain_run(const idff_weights_t* w, const idff_field_params_t* p, int n_fr
                  int n_sets, const float* gvals, int nj_sets, int reverse_sets);
 }
 
-extern "C" int idff_md_generate(const idff_weights_t* w, const idff_field_params_t* p, int32_t n_frames, const float* d_x_init,
-                                const float* h_ts, int32_t n_ts, float dt, int32_t method, const float* d_I_k,
-                                const float* d_I_k0, float* d_y_hat, int64_t K, void* stream) {
-  int rc = check_field_args(w, p, "idff_md_generate");
-  if (rc) return rc;
-  IDFF_CHECK_ARG(p->variant == IDFF_FIELD_MD, "idff_md_generate: the generator integrates SDE_cal (variant IDFF_FIELD_MD)");
-  IDFF_CHECK_ARG(n_frames >= 1 && n_frames <= w->v.n_tidx, "idff_md_generate: %d frames, the embedding has %d rows", n_frames,
-                 w->v.n_tidx);
-  IDFF_CHECK_ARG(h_ts && n_ts >= 2 && dt > 0.0f, "idff_md_generate: bad ts/dt");
-  IDFF_CHECK_ARG(method == 0 || method == 1, "idff_md_generate: method %d (0 srk, 1 euler)", method);
-  for (int i = 1; i < n_ts; ++i) IDFF_CHECK_ARG(h_ts[i] >= h_ts[i - 1], "idff_md_generate: ts must be non-decreasing");
-  IDFF_CHECK_ARG(h_ts[n_ts - 1] > h_ts[0], "idff_md_generate: empty time span");
-  if (K == 0) return IDFF_OK;
-  IDFF_CHECK_ARG(K > 0 && d_x_init && d_y_hat && d_I_k && (method == 1 || d_I_k0), "idff_md_generate: null pointer or negative K");
-  const std::vector<float> grid = sde_grid(h_ts, n_ts, dt);
-  const int n_steps = (int)grid.size() - 1;
-  if (n_steps > kMaxSdeSteps || n_ts - 1 > kMaxSdeEmit) {
-    set_error("idff_md_generate: %d steps / %d outputs exceed the per-call limits (%d / %d)", n_steps, n_ts - 1, kMaxSdeSteps, kMaxSdeEmit);
-    return IDFF_EUNSUPPORTED;
-  }
-  if (!md_chain_supports(w, p, K)) {
-    set_error("idff_md_generate: needs a width-128 network with at most 63 state dimensions; use one idff_sample_sde call per "
-              "frame otherwise");
-    return IDFF_EUNSUPPORTED;
-  }
-  // frame f: init_ind = f, gamma2 / (1 + f)   (MD_simulation.py:201); everything else is shared by the frames
-  static thread_local SdeTable tab0, tabf;
-  std::vector<Stage> stages((size_t)n_frames * n_steps * 3);
-  for (int f = 0; f < n_frames; ++f) {
-    idff_field_params_t q = *p;
-    q.t_idx = f;
-    q.gamma[1] = p->gamma[1] / (double)(1 + f);
-    SdeTable& t = f == 0 ? tab0 : tabf;
-    build_sde_table(&q, h_ts, n_ts, method, grid, t);
-    for (int s = 0; s < n_steps; ++s)
-      for (int g = 0; g < 3; ++g) stages[((size_t)f * n_steps + s) * 3 + g] = t.st[s][g];
-  }
-  DeviceGuard guard(w->device);
-  return md_chain_run(w, p, n_frames, tab0, stages.data(), d_x_init, d_I_k, d_I_k0, d_y_hat, K, stream, 1, nullptr, 0, 0);
-}
-
-// The (sigma, gamma1, gamma2) sweep of TrajectoryGenerator.evaluate_model (MD_simulation.py:159-194) at one nfe: every parameter
-// set generates its K trajectories in the SAME launch (a tile of 4 trajectories never mixes sets; per-set stage tables and
-// diffusion values in global memory).  Rows are set-major: d_x_init [n_sets * K][D], increments [n_frames][n_steps][n_sets * K][D],
-// d_y_hat [n_frames][n_sets * K][D]; set i's rows are exactly what idff_md_generate returns for p_sets[i] on those inputs.
-extern "C" int idff_md_generate_sweep(const idff_weights_t* w, const idff_field_params_t* p_sets, int32_t n_sets, int32_t n_frames,
-                                      const float* d_x_init, const float* h_ts, int32_t n_ts, float dt, int32_t method,
-                                      const float* d_I_k, const float* d_I_k0, float* d_y_hat, int64_t K, void* stream) {
-  IDFF_CHECK_ARG(p_sets && n_sets >= 1 && n_sets <= 4096, "idff_md_generate_sweep: %d parameter sets outside [1, 4096]", n_sets);
-  if (n_sets == 1)
-    return idff_md_generate(w, p_sets, n_frames, d_x_init, h_ts, n_ts, dt, method, d_I_k, d_I_k0, d_y_hat, K, stream);
+// idff_md_generate (n_sets == 1) and idff_md_generate_sweep: argument checks, per-(set, frame) stage tables, one launch.
+// frame f of a set: init_ind = f, gamma2 / (1 + f)   (MD_simulation.py:201); everything else is shared by the frames.
+static int md_generate_impl(const char* who, const idff_weights_t* w, const idff_field_params_t* p_sets, int n_sets, int32_t n_frames,
+                            const float* d_x_init, const float* h_ts, int32_t n_ts, float dt, int32_t method, const float* d_I_k,
+                            const float* d_I_k0, float* d_y_hat, int64_t K, void* stream) {
   for (int i = 0; i < n_sets; ++i) {
-    int rc = check_field_args(w, p_sets + i, "idff_md_generate_sweep");
+    int rc = check_field_args(w, p_sets + i, who);
     if (rc) return rc;
     IDFF_CHECK_ARG(p_sets[i].variant == IDFF_FIELD_MD && p_sets[i].dim == p_sets[0].dim,
-                   "idff_md_generate_sweep: every set must be an SDE_cal field (variant IDFF_FIELD_MD) of the same dimension");
+                   "%s: the generator integrates SDE_cal (variant IDFF_FIELD_MD), every set in the same dimension", who);
   }
-  IDFF_CHECK_ARG(n_frames >= 1 && n_frames <= w->v.n_tidx, "idff_md_generate_sweep: %d frames, the embedding has %d rows", n_frames,
-                 w->v.n_tidx);
-  IDFF_CHECK_ARG(h_ts && n_ts >= 2 && dt > 0.0f, "idff_md_generate_sweep: bad ts/dt");
-  IDFF_CHECK_ARG(method == 0 || method == 1, "idff_md_generate_sweep: method %d (0 srk, 1 euler)", method);
-  for (int i = 1; i < n_ts; ++i) IDFF_CHECK_ARG(h_ts[i] >= h_ts[i - 1], "idff_md_generate_sweep: ts must be non-decreasing");
-  IDFF_CHECK_ARG(h_ts[n_ts - 1] > h_ts[0], "idff_md_generate_sweep: empty time span");
+  IDFF_CHECK_ARG(n_frames >= 1 && n_frames <= w->v.n_tidx, "%s: %d frames, the embedding has %d rows", who, n_frames, w->v.n_tidx);
+  IDFF_CHECK_ARG(h_ts && n_ts >= 2 && dt > 0.0f, "%s: bad ts/dt", who);
+  IDFF_CHECK_ARG(method == 0 || method == 1, "%s: method %d (0 srk, 1 euler)", who, method);
+  for (int i = 1; i < n_ts; ++i) IDFF_CHECK_ARG(h_ts[i] >= h_ts[i - 1], "%s: ts must be non-decreasing", who);
+  IDFF_CHECK_ARG(h_ts[n_ts - 1] > h_ts[0], "%s: empty time span", who);
   if (K == 0) return IDFF_OK;
-  IDFF_CHECK_ARG(K > 0 && d_x_init && d_y_hat && d_I_k && (method == 1 || d_I_k0), "idff_md_generate_sweep: null pointer or negative K");
+  IDFF_CHECK_ARG(K > 0 && d_x_init && d_y_hat && d_I_k && (method == 1 || d_I_k0), "%s: null pointer or negative K", who);
   const std::vector<float> grid = sde_grid(h_ts, n_ts, dt);
   const int n_steps = (int)grid.size() - 1;
   if (n_steps > kMaxSdeSteps || n_ts - 1 > kMaxSdeEmit) {
-    set_error("idff_md_generate_sweep: %d steps / %d outputs exceed the per-call limits (%d / %d)", n_steps, n_ts - 1, kMaxSdeSteps, kMaxSdeEmit);
+    set_error("%s: %d steps / %d outputs exceed the per-call limits (%d / %d)", who, n_steps, n_ts - 1, kMaxSdeSteps, kMaxSdeEmit);
     return IDFF_EUNSUPPORTED;
   }
   if (!md_chain_supports(w, p_sets, K)) {
-    set_error("idff_md_generate_sweep: needs a width-128 network with at most 63 state dimensions");
+    set_error("%s: needs a width-128 network with at most 63 state dimensions; use one idff_sample_sde call per frame otherwise", who);
     return IDFF_EUNSUPPORTED;
   }
   static thread_local SdeTable tab0, tabf;
   std::vector<Stage> stages((size_t)n_sets * n_frames * n_steps * 3);
-  std::vector<float> gvals((size_t)n_sets * kMaxSdeSteps * 4, 0.0f);
+  std::vector<float> gvals(n_sets > 1 ? (size_t)n_sets * kMaxSdeSteps * 4 : 0, 0.0f);   // one set: the values travel in the kernel arguments
   int nj_max = 1, reverse_any = 0;
   for (int i = 0; i < n_sets; ++i) {
     int nj, rev;
@@ -649,14 +602,33 @@ extern "C" int idff_md_generate_sweep(const idff_weights_t* w, const idff_field_
       build_sde_table(&q, h_ts, n_ts, method, grid, t);
       for (int s = 0; s < n_steps; ++s)
         for (int g = 0; g < 3; ++g) stages[(((size_t)i * n_frames + f) * n_steps + s) * 3 + g] = t.st[s][g];
-      if (f == 0)
+      if (f == 0 && n_sets > 1)
         for (int s = 0; s < n_steps; ++s)
           for (int g = 0; g < 4; ++g) gvals[((size_t)i * kMaxSdeSteps + s) * 4 + g] = t.gval[s][g];
     }
   }
   DeviceGuard guard(w->device);
-  return md_chain_run(w, p_sets, n_frames, tab0, stages.data(), d_x_init, d_I_k, d_I_k0, d_y_hat, K, stream, n_sets, gvals.data(),
-                      nj_max, reverse_any);
+  return md_chain_run(w, p_sets, n_frames, tab0, stages.data(), d_x_init, d_I_k, d_I_k0, d_y_hat, K, stream, n_sets,
+                      n_sets > 1 ? gvals.data() : nullptr, nj_max, reverse_any);
+}
+
+extern "C" int idff_md_generate(const idff_weights_t* w, const idff_field_params_t* p, int32_t n_frames, const float* d_x_init,
+                                const float* h_ts, int32_t n_ts, float dt, int32_t method, const float* d_I_k,
+                                const float* d_I_k0, float* d_y_hat, int64_t K, void* stream) {
+  IDFF_CHECK_ARG(p, "idff_md_generate: null field parameters");
+  return md_generate_impl("idff_md_generate", w, p, 1, n_frames, d_x_init, h_ts, n_ts, dt, method, d_I_k, d_I_k0, d_y_hat, K, stream);
+}
+
+// The (sigma, gamma1, gamma2) sweep of TrajectoryGenerator.evaluate_model (MD_simulation.py:159-194) at one nfe: every parameter
+// set generates its K trajectories in the SAME launch (a tile of 4 trajectories never mixes sets; per-set stage tables and
+// diffusion values in global memory).  Rows are set-major: d_x_init [n_sets * K][D], increments [n_frames][n_steps][n_sets * K][D],
+// d_y_hat [n_frames][n_sets * K][D]; set i's rows are exactly what idff_md_generate returns for p_sets[i] on those inputs.
+extern "C" int idff_md_generate_sweep(const idff_weights_t* w, const idff_field_params_t* p_sets, int32_t n_sets, int32_t n_frames,
+                                      const float* d_x_init, const float* h_ts, int32_t n_ts, float dt, int32_t method,
+                                      const float* d_I_k, const float* d_I_k0, float* d_y_hat, int64_t K, void* stream) {
+  IDFF_CHECK_ARG(p_sets && n_sets >= 1 && n_sets <= 4096, "idff_md_generate_sweep: %d parameter sets outside [1, 4096]", n_sets);
+  return md_generate_impl("idff_md_generate_sweep", w, p_sets, n_sets, n_frames, d_x_init, h_ts, n_ts, dt, method, d_I_k, d_I_k0,
+                          d_y_hat, K, stream);
 }
 
 namespace idff { void wide_set_dense3(int on); }
