@@ -250,3 +250,108 @@ def evaluate_model(model, dataset, gamma1_values, gamma2_values, sigma_values, n
             m.update({"nfe": nfe, "sigma": sigma, "gamma1": gamma1, "gamma2": gamma2, "MMD": mmd})
             results.append(m)
     return results
+
+
+class TrajectoryGenerator:
+    """The reference's driver class (timeseris_example/MD_simulation.py:88-295) with the same constructor arguments, attributes
+    and method names, minus the plots and the KDE-KL column: train_model -> FusedMDTrainer (the whole loop in persistent-kernel
+    launches), generate_trajectories / generate_onestep -> the chain kernel / fused SDE sampler, evaluate_model -> one generation
+    launch per nfe for the whole (sigma, gamma1, gamma2) grid.  Everything runs on the CUDA device (`use_cuda` is accepted for
+    signature compatibility; there is no CPU path).  The dataset is read from data/{dataset_name}_dataset.p like the reference
+    does (:105-115), or passed as `dataset` (T, D)."""
+
+    def __init__(self, dataset_name, sigma, nfe, batch_size, num_trajectories, save_dir, model_name, use_cuda=True, dataset=None,
+                 device="cuda"):
+        import os
+        self.dataset_name = dataset_name
+        self.sigma = sigma
+        self.batch_size = batch_size
+        self.num_trajectories = num_trajectories
+        self.save_dir = os.path.join(save_dir, dataset_name)
+        self.model_name = model_name
+        self.rgn_thr = 30
+        self.NFE = nfe
+        self.num_steps = 50000
+        self.vis_step = 10000
+        del use_cuda
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.IdffError("TrajectoryGenerator needs a CUDA device: idff_b200 has no CPU path")
+        os.makedirs(self.save_dir, exist_ok=True)
+        if dataset is None:
+            self._load_dataset()
+        else:
+            self.dataset = torch.as_tensor(dataset).squeeze().float().to(self.device)
+            self.DataDim = int(self.dataset.shape[-1])
+            self.max_length = int(self.dataset.shape[0])
+
+    def _load_dataset(self):
+        import os
+        import pickle
+        dataset_path = f"data/{self.dataset_name}_dataset.p"
+        if not os.path.exists(dataset_path):
+            raise FileNotFoundError(f"Dataset file not found: {dataset_path}")
+        with open(dataset_path, "rb") as file:
+            data = pickle.load(file)
+        orig = data["angles"][1].reshape([data["sim_length"], -1])
+        self.dataset = torch.tensor(orig).squeeze().float().to(self.device)
+        self.DataDim = orig.shape[-1]
+        self.max_length = self.dataset.shape[0]
+
+    def train_model(self, steps_per_launch=2048):
+        """:117-157 -- Adam on MLP_Embedding(dim, w=128, time_embed=max_length), the ExactOT matcher's path sample, the periodic
+        loss; the best model (lowest step loss, :146-148) is saved to save_dir/model_name.pt at the end of the launch it occurred in."""
+        import os
+        from .torchcfm.models.models import MLP_Embedding
+        from .train import FusedMDTrainer
+        model = MLP_Embedding(dim=self.DataDim, w=128, time_embed=self.max_length, time_varying=True).to(self.device)
+        tr = FusedMDTrainer(model, self.dataset, batch_size=self.batch_size, sigma=self.sigma)
+        best_loss, best_state = float("inf"), None
+        best_model_path = os.path.join(self.save_dir, f"{self.model_name}.pt")
+        done = 0
+        while done < self.num_steps:
+            n = min(steps_per_launch, self.num_steps - done)
+            low = tr.run(n).min().item()
+            done += n
+            if low < best_loss:
+                best_loss, best_state = low, tr.state_dict()
+            if done % self.vis_step < n:
+                print(f"Step {done}: best loss {best_loss:.3f}")
+        if best_state is not None:
+            torch.save(best_state, best_model_path)
+        print(f"Training completed. Best loss {best_loss:.3f}; state_dict at {best_model_path}")
+        self.trainer = tr
+        return model
+
+    def generate_trajectories(self, model, gamma1=1, gamma2=10):
+        """:197-213 -> numpy (max_length, num_trajectories, DataDim)"""
+        return generate_trajectories(model, self.num_trajectories, self.DataDim, self.max_length, self.NFE, self.sigma,
+                                     gamma1=gamma1, gamma2=gamma2, dt=0.3, device=self.device).cpu().numpy()
+
+    def generate_onestep(self, model, nfe, time_index, gamma1=1, gamma2=10):
+        """:215-230 -> numpy (nfe, num_trajectories, DataDim)"""
+        if time_index == 0:
+            x1 = torch.randn((self.num_trajectories, self.DataDim), device=self.device)
+        else:
+            x1 = self.dataset[time_index - 1].unsqueeze(0).repeat(self.num_trajectories, 1).contiguous()
+        return generate_onestep(model, self.num_trajectories, self.DataDim, self.max_length, nfe, self.sigma, x1, gamma1=gamma1,
+                                gamma2=gamma2).cpu().numpy()
+
+    def compute_metrics(self, y_hat):
+        """:275-295 (the six keys of the reference)"""
+        m = compute_metrics(torch.as_tensor(y_hat, dtype=torch.float32, device=self.device), self.dataset)
+        return {k: m[k] for k in _METRIC_KEYS}
+
+    def evaluate_model(self, model, gamma1_values, gamma2_values, sigma_values, nfes):
+        """:159-194 -> list of result rows (also written to save_dir/evaluation_results.csv like the reference's DataFrame)."""
+        import csv
+        import os
+        rows = evaluate_model(model, self.dataset, gamma1_values, gamma2_values, sigma_values, nfes,
+                              num_trajectories=self.num_trajectories, dt=0.3, device=self.device)
+        path = os.path.join(self.save_dir, "evaluation_results.csv")
+        with open(path, "w", newline="") as fh:
+            wr = csv.DictWriter(fh, fieldnames=list(rows[0].keys()) if rows else [])
+            wr.writeheader()
+            wr.writerows(rows)
+        print(f"Evaluation results saved to {path}")
+        return rows

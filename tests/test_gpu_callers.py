@@ -502,3 +502,31 @@ def test_metrics_of_all_sweep_sets_at_once(cuda_device):
         for k in ("CC_mean", "CC_std", "RMSE_mean", "RMSE_std", "MAE_mean", "MAE_std"):
             a, b = rows[i][k], one[k]
             assert (np.isnan(a) and np.isnan(b)) or a == pytest.approx(b, rel=1e-12, abs=1e-12), (i, k, a, b)
+
+
+def test_trajectory_generator_class_mirror(cuda_device, tmp_path):
+    """md.TrajectoryGenerator: the reference's driver class (MD_simulation.py:88-295) by name -- constructor attributes, train_model
+    on the persistent-kernel trainer (loss goes down, a state_dict is saved), generate_trajectories / generate_onestep shapes,
+    compute_metrics keys, evaluate_model rows + CSV."""
+    g = torch.Generator().manual_seed(4)
+    T, D = 24, 46
+    data = 120 * torch.sin(torch.cumsum(torch.randn(T, D, generator=g) * 0.2, 0))
+    tg = md.TrajectoryGenerator(dataset_name="synthetic", sigma=0.5, nfe=3, batch_size=10, num_trajectories=5,
+                                save_dir=str(tmp_path), model_name="m", use_cuda=True, dataset=data, device=cuda_device)
+    assert (tg.DataDim, tg.max_length, tg.NFE, tg.rgn_thr) == (D, T, 3, 30)
+    tg.num_steps, tg.vis_step = 3000, 1000
+    torch.manual_seed(0)
+    model = tg.train_model(steps_per_launch=1000)
+    assert (tmp_path / "synthetic" / "m.pt").exists()
+    first = tg.trainer.run(1).item()
+    assert np.isfinite(first)
+    y = tg.generate_trajectories(model, gamma1=0.2, gamma2=5)
+    assert isinstance(y, np.ndarray) and y.shape == (T, 5, D)
+    one = tg.generate_onestep(model, 3, 2, gamma1=0.2, gamma2=5)
+    assert one.shape == (3, 5, D)
+    m = tg.compute_metrics(y)
+    assert set(m) == {"CC_mean", "CC_std", "RMSE_mean", "RMSE_std", "MAE_mean", "MAE_std"}
+    rows = tg.evaluate_model(model, [0.0, 0.2], [1.0, 5.0], [0.5], [3])
+    assert len(rows) == 4 and (tmp_path / "synthetic" / "evaluation_results.csv").exists()
+    with pytest.raises(FileNotFoundError):
+        md.TrajectoryGenerator("no_such_dataset", 0.5, 3, 10, 5, str(tmp_path), "m", device=cuda_device)
