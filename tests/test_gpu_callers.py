@@ -530,3 +530,27 @@ def test_trajectory_generator_class_mirror(cuda_device, tmp_path):
     assert len(rows) == 4 and (tmp_path / "synthetic" / "evaluation_results.csv").exists()
     with pytest.raises(FileNotFoundError):
         md.TrajectoryGenerator("no_such_dataset", 0.5, 3, 10, 5, str(tmp_path), "m", device=cuda_device)
+
+
+def test_md_generation_sweep_more_tiles_than_sms(cuda_device):
+    """idff_md_generate_sweep with more trajectory tiles than SMs (100 sets x 2 tiles): a CTA then walks tiles of DIFFERENT parameter
+    sets one after the other and must reload the set's stage table and diffusion values -- every checked set is still bit for bit
+    the one-set launch."""
+    from idff_b200 import sampler as sampler_mod
+    dev = cuda_device
+    pw = packed("polyala", dev)
+    K, D, T, NFE, dt = 5, 46, 6, 3, 0.3
+    sets = [(0.2 + 0.005 * i, 0.1 + 0.002 * i, 1.0 + 0.05 * i) for i in range(100)]
+    S = len(sets)
+    g = torch.Generator(device=dev).manual_seed(21)
+    n_steps = sampler_mod.sde_num_steps(torch.linspace(0, 1, NFE), dt)
+    x_init = torch.randn(S, K, D, device=dev, generator=g)
+    ik = torch.randn(T, n_steps, S, K, D, device=dev, generator=g) * 0.3
+    ik0 = torch.randn(T, n_steps, S, K, D, device=dev, generator=g) * 0.05
+    ys = md.generate_trajectories_sweep(pw, sets, K, D, T, NFE, dt=dt, device=dev, x_init=x_init, noise=(ik, ik0))
+    for i in (0, 1, 73, 74, 75, 98, 99):
+        sg, g1, g2 = sets[i]
+        one = md.generate_trajectories_chain(pw, K, D, T, NFE, sigma=sg, gamma1=g1, gamma2=g2, dt=dt, device=dev,
+                                             x_init=x_init[i].contiguous(),
+                                             noise=(ik[:, :, i].contiguous(), ik0[:, :, i].contiguous()))
+        assert torch.equal(ys[:, i].contiguous().view(torch.int32), one.view(torch.int32)), i
