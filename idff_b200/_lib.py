@@ -83,6 +83,8 @@ SIGNATURES = {
     "idff_train_md_offsets": (C.c_int, [_i32, _i32, _vp]),
     "idff_train_md_steps": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _f32, _i32, C.POINTER(AdamW), _i64, _vp, _vp,
                                       _vp]),
+    "idff_train_md_steps_paired": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _i32, C.POINTER(AdamW),
+                                             _i64, _vp, _vp, _vp]),
     "idff_train_state_floats": (C.c_int64, [_i32]),
     "idff_train_offsets": (C.c_int, [_i32, _vp]),
     "idff_train_init": (C.c_int, [_i32, _vp, _vp]),

@@ -58,6 +58,7 @@ struct Args {
   float* S;                 // state: [param block | exp_avg | exp_avg_sq], each NPP floats
   const float* dataset;     // [T][D]
   const long long* idx;     // [n_steps][B]
+  const long long *row0, *row1;   // [n_steps][B] dataset rows of x0 / x1 when the batch was re-paired (NULL: idx - 1 / idx)
   const float *t, *eps;     // [n_steps][B], [n_steps][B][D] (eps may be null)
   float *loss_out, *grad_dump;
   int B, D, T, n_steps;
@@ -375,8 +376,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1) k_train_md(c
         long long ix = a.idx[(size_t)s * B + r];
         ix = ix < 1 ? 1 : (ix > T - 1 ? T - 1 : ix);   // frames [1, T): randint(1, T) in the reference (torch would raise outside)
         pidx[q] = (int)ix;
-        px0[q] = a.dataset[(size_t)(ix - 1) * D + d];
-        px1[q] = a.dataset[(size_t)ix * D + d];
+        long long r0 = a.row0 ? a.row0[(size_t)s * B + r] : ix - 1, r1 = a.row1 ? a.row1[(size_t)s * B + r] : ix;
+        r0 = r0 < 0 ? 0 : (r0 > T - 1 ? T - 1 : r0);
+        r1 = r1 < 0 ? 0 : (r1 > T - 1 ? T - 1 : r1);
+        px0[q] = a.dataset[(size_t)r0 * D + d];
+        px1[q] = a.dataset[(size_t)r1 * D + d];
         pep[q] = a.eps ? a.eps[((size_t)s * B + r) * D + d] : 0.0f;
         ptt[q] = a.t[(size_t)s * B + r];
       }
@@ -659,6 +663,17 @@ extern "C" int idff_train_md_steps(float* d_state, const float* d_dataset, int32
                                    const float* d_t, const float* d_eps, int32_t n_steps, int32_t B, float sigma,
                                    int32_t sigma_mode, const idff_adamw_t* opt, int64_t steps_done, float* d_loss,
                                    float* d_grad_dump, void* stream) {
+  return idff_train_md_steps_paired(d_state, d_dataset, T, D, d_idx, nullptr, nullptr, d_t, d_eps, n_steps, B, sigma, sigma_mode, opt,
+                                    steps_done, d_loss, d_grad_dump, stream);
+}
+
+// The same loop with the batch re-paired before the path sample, as the `_dynamic` matcher's sample_plan does
+// (conditional_flow_matching_dynamic.py:268): x0 = dataset[d_row0], x1 = dataset[d_row1] ([n_steps][B] each, NULL = idx - 1 / idx),
+// while the embedding still sees index_sel = d_idx in its original order (MD_simulation.py:135).
+extern "C" int idff_train_md_steps_paired(float* d_state, const float* d_dataset, int32_t T, int32_t D, const int64_t* d_idx,
+                                          const int64_t* d_row0, const int64_t* d_row1, const float* d_t, const float* d_eps,
+                                          int32_t n_steps, int32_t B, float sigma, int32_t sigma_mode, const idff_adamw_t* opt,
+                                          int64_t steps_done, float* d_loss, float* d_grad_dump, void* stream) {
   int rc = check_md_shape(D, T, "idff_train_md_steps");
   if (rc) return rc;
   IDFF_CHECK_ARG(d_state && (reinterpret_cast<uintptr_t>(d_state) & 15) == 0, "idff_train_md_steps: state must be a 16-byte aligned device pointer");
@@ -682,6 +697,7 @@ extern "C" int idff_train_md_steps(float* d_state, const float* d_dataset, int32
   Args a;
   memset(&a, 0, sizeof(a));
   a.S = d_state; a.dataset = d_dataset; a.idx = reinterpret_cast<const long long*>(d_idx); a.t = d_t; a.eps = d_eps;
+  a.row0 = reinterpret_cast<const long long*>(d_row0); a.row1 = reinterpret_cast<const long long*>(d_row1);
   a.loss_out = d_loss; a.grad_dump = d_grad_dump;
   a.B = B; a.D = D; a.T = T; a.n_steps = n_steps;
   a.npp = (o.NP + 63) / 64 * 64;

@@ -318,8 +318,9 @@ class FusedMDTrainer:
     """
 
     def __init__(self, model: torch.nn.Module, dataset: torch.Tensor, batch_size: int = 10, sigma: float = 0.5, lr: float = 1e-3,
-                 betas=(0.9, 0.999), eps: float = 1e-8, exact_ot_sigma: bool = True):
+                 betas=(0.9, 0.999), eps: float = 1e-8, exact_ot_sigma: bool = True, ot_pairing: bool = False):
         L = _lib.lib()
+        self.ot_pairing = bool(ot_pairing)   # run(): re-pair every batch by its exact OT plan first (the `_dynamic` matcher)
         _lib.require_cuda(dataset, "dataset")
         self.dataset = dataset.contiguous().float()
         self.T, self.D = int(dataset.shape[0]), int(dataset.shape[1])
@@ -367,7 +368,9 @@ class FusedMDTrainer:
     def state_dict(self):
         return {k: v.detach().clone() for k, v in self.model.state_dict().items()}
 
-    def steps(self, idx, t, eps=None, grad_dump: torch.Tensor | None = None):
+    def steps(self, idx, t, eps=None, grad_dump: torch.Tensor | None = None, rows=None):
+        """rows: optional (row0, row1) int64 (S, B) dataset rows of x0 / x1 when the batches were re-paired (the `_dynamic` matcher's
+        sample_plan, conditional_flow_matching_dynamic.py:268); default idx - 1 / idx."""
         if not idx.is_cuda or idx.dtype != torch.int64:
             raise _lib.IdffError("idx must be a CUDA int64 tensor (torch.randint's dtype): idff_b200 has no CPU path")
         for name, v in (("t", t),) + ((("eps", eps),) if eps is not None else ()):
@@ -382,10 +385,16 @@ class FusedMDTrainer:
         if tuple(t.shape) != (S, B) or (eps is not None and tuple(eps.shape) != (S, B, self.D)):
             raise _lib.IdffError(f"expected t of shape ({S}, {B}) and eps of shape ({S}, {B}, {self.D})")
         loss = torch.empty(S, device=self.device, dtype=torch.float32)
-        _lib.check(_lib.lib().idff_train_md_steps(
-            _lib.ptr(self.state), _lib.ptr(self.dataset), self.T, self.D, _lib.ptr(idx), _lib.ptr(t), _lib.ptr(eps), S, B, self.sigma,
-            self.sigma_mode, C.byref(self.opt), self.steps_done, _lib.ptr(loss), _lib.ptr(grad_dump), _lib.stream_of(self.state)),
-            "idff_train_md_steps")
+        r0 = r1 = None
+        if rows is not None:
+            r0, r1 = (v.contiguous().view(S, B) for v in rows)
+            for v in (r0, r1):
+                if not v.is_cuda or v.dtype != torch.int64:
+                    raise _lib.IdffError("rows must be CUDA int64 tensors")
+        _lib.check(_lib.lib().idff_train_md_steps_paired(
+            _lib.ptr(self.state), _lib.ptr(self.dataset), self.T, self.D, _lib.ptr(idx), _lib.ptr(r0), _lib.ptr(r1), _lib.ptr(t),
+            _lib.ptr(eps), S, B, self.sigma, self.sigma_mode, C.byref(self.opt), self.steps_done, _lib.ptr(loss), _lib.ptr(grad_dump),
+            _lib.stream_of(self.state)), "idff_train_md_steps")
         self.steps_done += S
         torch.autograd.graph.increment_version(list(self.model.parameters()))   # the kernel wrote them in place
         return loss
@@ -397,6 +406,15 @@ class FusedMDTrainer:
         eps = torch.randn(n_steps, self.B, self.D, device=self.device) if self.sigma != 0.0 else None
         return idx, t, eps
 
+    def ot_rows(self, idx):
+        """The `_dynamic` matcher's re-pairing for every step at once (conditional_flow_matching_dynamic.py:268 on x0 = dataset[idx - 1],
+        x1 = dataset[idx]): one batched exact-OT launch, index pairs drawn with replacement per step -> (row0, row1) for `steps`."""
+        from .torchcfm.optimal_transport import ot_assign_batch
+        perm = ot_assign_batch(self.dataset[idx - 1], self.dataset[idx])               # (S, B)
+        i = torch.randint(0, idx.shape[1], idx.shape, device=self.device)
+        j = torch.gather(perm, 1, i)
+        return torch.gather(idx, 1, i) - 1, torch.gather(idx, 1, j)
+
     def run(self, n_steps: int) -> torch.Tensor:
         idx, t, eps = self.draw(n_steps)
-        return self.steps(idx, t, eps)
+        return self.steps(idx, t, eps, rows=self.ot_rows(idx) if self.ot_pairing else None)

@@ -288,6 +288,14 @@ int idff_train_md_offsets(int32_t D, int32_t T, int64_t* h_out13);
 int idff_train_md_steps(float* d_state, const float* d_dataset, int32_t T, int32_t D, const int64_t* d_idx, const float* d_t,
                         const float* d_eps, int32_t n_steps, int32_t B, float sigma, int32_t sigma_mode, const idff_adamw_t* opt,
                         int64_t steps_done, float* d_loss, float* d_grad_dump, void* stream);
+/* The same loop with every batch RE-PAIRED before its path sample, as the `_dynamic` matcher's sample_plan does
+ * (torchcfm/conditional_flow_matching_dynamic.py:268): x0 = dataset[d_row0], x1 = dataset[d_row1] (int64 [n_steps][B] each; NULL =
+ * d_idx - 1 / d_idx, i.e. idff_train_md_steps), while the embedding sees index_sel = d_idx in its original order
+ * (MD_simulation.py:135).  The rows come from idff_ot_assign_batch on the gathered frames + one index draw per step. */
+int idff_train_md_steps_paired(float* d_state, const float* d_dataset, int32_t T, int32_t D, const int64_t* d_idx,
+                               const int64_t* d_row0, const int64_t* d_row1, const float* d_t, const float* d_eps, int32_t n_steps,
+                               int32_t B, float sigma, int32_t sigma_mode, const idff_adamw_t* opt, int64_t steps_done,
+                               float* d_loss, float* d_grad_dump, void* stream);
 
 /* ---- OTPlanSampler.get_map for the reference's use (torchcfm/optimal_transport.py:59-94: uniform marginals over
  * two minibatches of EQUAL size n, squared-Euclidean cost, exact plan from pot.emd -- POT's network simplex, un-vendored).  The

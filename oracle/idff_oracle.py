@@ -400,10 +400,12 @@ def train_steps_2d(layers, x0, x1, t, eps, sigma=0.0, lr=2e-4, clip=1.0, return_
     return res + (grads,) if return_grads else res
 
 
-def md_train_steps(emb, layers, dataset, idx, t, eps, sigma=0.5, lr=1e-3, return_grads=False):
+def md_train_steps(emb, layers, dataset, idx, t, eps, sigma=0.5, lr=1e-3, return_grads=False, rows=None):
     """TrajectoryGenerator.train_model's loop (timeseris_example/MD_simulation.py:117-144) with the random draws passed in:
     idx [S][B] int64 frame indices (randint(1, T), :128), t [S][B], eps [S][B][D].  MLP_Embedding (models.py:23-42) rebuilt from
-    (emb, layers); torch.optim.Adam with defaults (:119); ExactOT matcher sigma (:121, pairing off).
+    (emb, layers); torch.optim.Adam with defaults (:119); ExactOT matcher sigma (:121, pairing off).  rows = (row0, row1) [S][B]:
+    the batch re-paired as the `_dynamic` matcher's sample_plan would (conditional_flow_matching_dynamic.py:268) -- x0 / x1 from those
+    dataset rows, the embedding still on index_sel.
     Returns (per-step losses, final (emb, layers)[, gradients of the last step in module.parameters() order])."""
     E = torch.nn.Embedding(emb.shape[0], emb.shape[1]).to(emb.dtype)
     mods = []
@@ -423,6 +425,8 @@ def md_train_steps(emb, layers, dataset, idx, t, eps, sigma=0.5, lr=1e-3, return
     for s in range(idx.shape[0]):
         optimizer.zero_grad()                                                     # :127
         x0, x1 = dataset[idx[s] - 1], dataset[idx[s]]                             # :129-130
+        if rows is not None:
+            x0, x1 = dataset[rows[0][s]], dataset[rows[1][s]]
         xt, ut = path_sample(x0, x1, t[s], eps[s] if eps is not None else torch.zeros_like(x0), sigma, True, ieee_sqrt=True)   # :132
         x = torch.cat([xt, t[s][:, None]], dim=-1)
         vt = net(torch.cat([x, E(idx[s].to(torch.long)).squeeze()], dim=-1))      # :135, models.py:40-42

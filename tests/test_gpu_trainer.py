@@ -469,3 +469,35 @@ def test_md_trainer_argument_checks(cuda_device):
     from idff_b200.torchcfm.models.models import MLP_Embedding
     with pytest.raises(_lib.IdffError):
         train.FusedMDTrainer(MLP_Embedding(dim=46, w=64, time_embed=200, time_varying=True).to(dev), ds.to(dev))
+
+
+def test_md_steps_with_repaired_batches(cuda_device):
+    """idff_train_md_steps_paired: the PolyALA loop with every batch re-paired before its path sample (the `_dynamic` matcher,
+    conditional_flow_matching_dynamic.py:268) -- x0 / x1 from the given dataset rows, the embedding on index_sel in its original
+    order -- tracks the oracle's loop with the same rows; FusedMDTrainer(ot_pairing=True).ot_rows produces rows that are pairs of
+    each step's exact OT plan, and run() trains on them."""
+    from scipy.optimize import linear_sum_assignment
+    dev, lr, S, B, T, D = cuda_device, 1e-3, 12, 10, 200, 46
+    ds, model = _polyala_case(dev, seed=5)
+    emb, layers = _md_parts(model)
+    g = torch.Generator().manual_seed(91)
+    idx = torch.randint(1, T, (S, B), generator=g)
+    t = torch.rand(S, B, generator=g)
+    eps = torch.randn(S, B, D, generator=g)
+    tr = train.FusedMDTrainer(model, ds.to(dev), batch_size=B, sigma=0.5, lr=lr, ot_pairing=True)
+    torch.manual_seed(3)
+    r0, r1 = tr.ot_rows(idx.to(dev))
+    assert r0.shape == r1.shape == (S, B) and r0.dtype == torch.int64
+    for s in range(S):                              # every (row0, row1) is a pair of step s's exact plan
+        x0, x1 = ds[idx[s] - 1].double(), ds[idx[s]].double()
+        _, col = linear_sum_assignment((torch.cdist(x0, x1) ** 2).numpy())
+        plan = {(int(idx[s, i]) - 1, int(idx[s, col[i]])) for i in range(B)}
+        assert all((int(a), int(b)) in plan for a, b in zip(r0[s].cpu(), r1[s].cpu()))
+    losses_r, (emb_r, layers_r) = O.md_train_steps(emb, layers, ds, idx, t, eps, sigma=0.5, lr=lr, rows=(r0.cpu(), r1.cpu()))
+    loss = tr.steps(idx.to(dev), t.to(dev), eps.to(dev), rows=(r0, r1)).cpu().numpy()
+    np.testing.assert_allclose(loss, np.array(losses_r), rtol=1e-3)
+    after_r = [emb_r] + [x for Wb in layers_r for x in Wb]
+    dall = np.concatenate([(p.detach().cpu() - ref).abs().numpy().reshape(-1) for p, ref in zip(model.parameters(), after_r)])
+    assert np.median(dall) <= 1e-5 and dall.max() <= 20 * lr, (np.median(dall), dall.max())
+    out = tr.run(256)
+    assert torch.isfinite(out).all() and out.shape == (256,)
