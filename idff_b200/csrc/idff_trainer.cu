@@ -451,32 +451,46 @@ __device__ void job_tile(const Args& a, int job, float* smem, Owned& own) {
   float acc[4][4], gbs = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; acc[i][3] = 0.f; }
-  for (int r0 = 0; r0 < a.B; r0 += 256) {
-    const int rows = min(256, a.B - r0);
-    {   // stage the two 256 x 32 operand panels: all 8 128-bit loads of a thread in flight at once
-      float4 vz[4], va[4];
+  // The two operand panels (dZ and A, 32 columns each) move through shared memory in chunks of 128 batch rows, double buffered: the
+  // loads of chunk c + 1 are in flight while chunk c is multiplied (all 128 tile jobs ask the L2 for their 64 KB at the same moment
+  // right after the grid barrier).  Per thread the rows are still visited in ascending order: the sums keep their order.
+#ifndef IDFF_TRN_CR
+#define IDFF_TRN_CR 128
+#endif
+  constexpr int CR = IDFF_TRN_CR, NLD = CR * 8 / NC;   // rows per chunk (buffer b of a panel = its rows [b * CR, b * CR + CR)); 128-bit loads per thread and panel
+  const int nch = (a.B + CR - 1) / CR;
+  float4 vz[NLD], va[NLD];
+  auto fetch = [&](int c) {
+    const int rows = min(CR, a.B - c * CR);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = tid + u * NC, r = i >> 3, c4 = i & 7;
-        if (r < rows) {
-          vz[u] = __ldcg(reinterpret_cast<const float4*>(dZ + (size_t)(r0 + r) * W + jb * 32) + c4);
-          va[u] = __ldcg(reinterpret_cast<const float4*>(Ain + (size_t)(r0 + r) * W + kb * 32) + c4);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = tid + u * NC, r = i >> 3, c4 = i & 7;
-        if (r < rows) {
-          *reinterpret_cast<float4*>(dZs + r * 32 + c4 * 4) = vz[u];
-          *reinterpret_cast<float4*>(As + r * 32 + c4 * 4) = va[u];
-        }
+    for (int u = 0; u < NLD; ++u) {
+      const int i = tid + u * NC, r = i >> 3, c4 = i & 7;
+      if (r < rows) {
+        vz[u] = __ldcg(reinterpret_cast<const float4*>(dZ + (size_t)(c * CR + r) * W + jb * 32) + c4);
+        va[u] = __ldcg(reinterpret_cast<const float4*>(Ain + (size_t)(c * CR + r) * W + kb * 32) + c4);
       }
     }
-    csync();
+  };
+  fetch(0);
+  float bsum = 0.f;
+  for (int c = 0; c < nch; ++c) {
+    const int rows = min(CR, a.B - c * CR);
+    float* dzb = dZs + (c & 1) * CR * 32;
+    float* ab = As + (c & 1) * CR * 32;
+#pragma unroll
+    for (int u = 0; u < NLD; ++u) {
+      const int i = tid + u * NC, r = i >> 3, c4 = i & 7;
+      if (r < rows) {
+        *reinterpret_cast<float4*>(dzb + r * 32 + c4 * 4) = vz[u];
+        *reinterpret_cast<float4*>(ab + r * 32 + c4 * 4) = va[u];
+      }
+    }
+    if (c + 1 < nch) fetch(c + 1);
+    csync();   // chunk c is staged; everybody has finished chunk c - 1, whose buffer the NEXT iteration overwrites
 #pragma unroll 4
     for (int r = ksl; r < rows; r += 8) {
-      const float4 dz = *reinterpret_cast<const float4*>(dZs + r * 32 + 4 * jj);
-      const float4 av = *reinterpret_cast<const float4*>(As + r * 32 + 4 * kk);
+      const float4 dz = *reinterpret_cast<const float4*>(dzb + r * 32 + 4 * jj);
+      const float4 av = *reinterpret_cast<const float4*>(ab + r * 32 + 4 * kk);
       const float d[4] = {dz.x, dz.y, dz.z, dz.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -486,14 +500,13 @@ __device__ void job_tile(const Args& a, int job, float* smem, Owned& own) {
         acc[i][3] = fmaf(d[i], av.w, acc[i][3]);
       }
     }
-    if (kb == 0) {   // column sums of dZ: the bias gradient (tiles of the first k-block only); thread = (16 row groups, column)
-      const int c = tid & 31, rg = tid >> 5;
-      float sum = 0.f;
-      for (int r = rg; r < rows; r += 16) sum += dZs[r * 32 + c];
-      gbs += sum;
+    if (kb == 0) {   // column sums of dZ: the bias gradient (tiles of the first k-block only); thread = (16 row groups, column);
+      const int cc = tid & 31, rg = tid >> 5;   // one running sum per 256 batch rows, as before the panels were chunked
+      for (int r = rg; r < rows; r += 16) bsum += dzb[r * 32 + cc];
+      if ((c + 1) % (256 / CR) == 0 || c + 1 == nch) { gbs += bsum; bsum = 0.f; }
     }
-    csync();
   }
+  csync();
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
